@@ -1,0 +1,458 @@
+#!/usr/bin/env python
+"""
+bench.py -- model lnL evaluations per second (walkers x iterations).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c3|c4|s128]
+                    [--walkers NW] [--impl ours|reference] [--precision fp32|fp64]
+
+One "step" is one emcee iteration of an NW-walker ensemble: the two sequentially
+dependent half-ensemble batches emcee 2.x maps per iteration (SURVEY.md section
+3.2), i.e. NW lnL evaluations through the hot path. The default workload is the
+J0005-0006 quasar+host model (C1 frame, 128^2, Sky + PointSource + 2 Sersic, D=18)
+for a 4096-walker ensemble per GPU -- the configuration BASELINE.json's north_star
+quotes its target on. Walkers shard over GPUs with no data-path collective
+(weak scaling: every rank evaluates its own NW-walker ensemble).
+
+Prints ONE JSON line (rank 0). `value` = device-resident throughput (theta and
+lnL stay in HBM, CUDA events on the launching stream); `e2e` = the same metric
+through the C ABI with host buffers (pinned theta in, lnL out, copies inside the
+timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'model lnL evals/sec (walkers x iters)'
+UNIT = 'evals/s'
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c1', choices=['c1', 'c3', 'c4', 's128'])
+    ap.add_argument('--walkers', type=int, default=0,
+                    help='ensemble size per GPU (default: 4096 for c1/s128/c4, 1024 for c3)')
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp64'])
+    ap.add_argument('--cpu-seconds', type=float, default=12.0,
+                    help='budget of the cpu_baseline leg')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ workload --
+
+def workload_description(name, walkers):
+    desc = {
+        'c1': 'C1 J0005-0006 quasar+host, 128x128, Sky+PointSource+2 Sersic, D=18, '
+              '9176/16384 px unmasked',
+        'c3': 'C3 synthetic 256x256 quasar + two-Sersic host, PSF-variance term, D=18',
+        'c4': 'C4 synthetic 512x512 PointSource + three Sersic, D=25',
+        's128': 'synthetic 128x128, C1 component structure',
+    }[name]
+    return '{}; {}-walker ensemble per GPU, 2 half-ensemble batches per step'.format(
+        desc, walkers)
+
+
+def default_walkers(name):
+    return {'c1': 4096, 'c3': 1024, 'c4': 4096, 's128': 4096}[name]
+
+
+def build_components(name):
+    """Component list of the workload (built from files in this repository)."""
+    from psfmc_b200.model_parser import component_list_from_file
+    from psfmc_b200.synthetic import WORKLOADS, synthetic_components
+    if name == 'c1':
+        return component_list_from_file(os.path.join(GOLDEN, 'j0005', 'model_c1.py'))
+    size, n_sersic, _ = WORKLOADS[name]
+    return synthetic_components(size, n_sersic)
+
+
+def build_oracle(model_like):
+    """Oracle (CPU port of the reference path) over a model's arrays + program.
+    float32 inputs with float64 FFT/tail = the reference's pinned numpy-1.x
+    behaviour (mode M2)."""
+    from oracle import psfmc_oracle as orc
+    cfg = model_like['config']
+    return orc.OracleModel(cfg.obs_data, cfg.obs_var, cfg.bad_px,
+                           cfg.psf_selector.psf_images, cfg.psf_selector.var_images,
+                           cfg.mag_zeropoint, model_like['program'],
+                           model_like['psf_index_slot'], fft_upcast=True)
+
+
+# ------------------------------------------------------- CPU baseline (port) --
+
+_WORKER = {}
+
+
+def _worker_init(workload):
+    for var in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
+        os.environ[var] = '1'
+    from psfmc_b200.components import Configuration
+    from psfmc_b200.program import compile_program
+    comps = build_components(workload)
+    config = [c for c in comps if isinstance(c, Configuration)][0]
+    rest = [c for c in comps if c is not config] + [config.psf_selector]
+    program, psf_slot, _ = compile_program(rest)
+    _WORKER['oracle'] = build_oracle({'config': config, 'program': program,
+                                      'psf_index_slot': psf_slot})
+
+
+def _worker_eval(block):
+    return _WORKER['oracle'].lnlike_batch(block)
+
+
+class CpuPort(object):
+    """The oracle port on all host cores: a multiprocessing pool with one model per
+    worker (the reference's own parallel hook is emcee's pool.map; its model object
+    is not picklable, psfMC/fitting.py:55, hence one model per worker)."""
+
+    def __init__(self, workload):
+        import multiprocessing as mp
+        self.cores = os.cpu_count() or 1
+        ctx = mp.get_context('fork')
+        self.pool = ctx.Pool(self.cores, initializer=_worker_init,
+                             initargs=(workload,))
+
+    def evaluate(self, thetas):
+        nblk = max(1, min(len(thetas), self.cores * 4))
+        blocks = np.array_split(thetas, nblk)
+        return np.concatenate(self.pool.map(_worker_eval, blocks))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def time_cpu_port(workload, thetas, seconds):
+    port = CpuPort(workload)
+    try:
+        port.evaluate(thetas[:port.cores])            # warm the workers
+        per_call = max(port.cores * 4, 32)
+        done, start = 0, time.perf_counter()
+        while True:
+            lo = done % max(1, len(thetas) - per_call)
+            port.evaluate(thetas[lo:lo + per_call])
+            done += per_call
+            elapsed = time.perf_counter() - start
+            if elapsed >= seconds:
+                break
+        return done / elapsed, port.cores, done, elapsed
+    finally:
+        port.close()
+
+
+# ------------------------------------------------------------------- clocks --
+
+class ClockSampler(object):
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                universal_newlines=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for parts in self.samples:
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0.5 * max(sm)] if sm else []
+        return {'sm_mhz': float(np.median(busy)) if busy else None,
+                'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(power) if power else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------ our arm --
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    entry.build()
+    from psfmc_b200 import MultiComponentModel, fp32_peak_tflops
+    from psfmc_b200.synthetic import draw_walkers_fast
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the engine has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    walkers = args.walkers or default_walkers(args.workload)
+    half = walkers // 2
+    model = MultiComponentModel(build_components(args.workload),
+                                precision=args.precision, devices=[local])
+    engine = model.engine
+    ndim = model.num_params
+    nsets = 4   # distinct ensembles cycled through, so no step repeats its input
+    thetas = [draw_walkers_fast(model, walkers, seed=1000 * rank + s) for s in range(nsets)]
+    th_dev = [torch.from_numpy(t).to(dev) for t in thetas]
+    th_pin = [torch.from_numpy(t).pin_memory() for t in thetas]
+    lnl_dev = torch.empty(walkers, dtype=torch.float64, device=dev)
+    lnl_pin = torch.empty(walkers, dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device(s):
+        th = th_dev[s % nsets]
+        base = th.data_ptr()
+        for h in range(2):     # two sequentially dependent half-ensembles
+            engine.lnlike_device(base + h * half * ndim * 8, half, ndim,
+                                 lnl_dev.data_ptr() + h * half * 8,
+                                 stream=stream.cuda_stream)
+
+    def step_host(s):
+        th = th_pin[s % nsets].numpy()
+        out = lnl_pin.numpy()
+        for h in range(2):
+            engine.lnlike(th[h * half:(h + 1) * half], out=out[h * half:(h + 1) * half])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(value):
+        if world == 1:
+            return value
+        t = torch.tensor([value], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for s in range(max(args.warmup, 3)):
+        step_device(s)
+        step_host(s)
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) -------------------------------
+    sampler = ClockSampler(local)
+    launches0 = engine.info()['launches_total']
+    barrier()
+    total_ms = 0.0
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)                  # evict L2 between timed steps
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_device(s)
+        e1.record(stream)
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+    barrier()
+    launches = engine.info()['launches_total'] - launches0
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = world * walkers / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (`e2e`) -------------
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_host(s)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * walkers * args.steps / e2e_s
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        th = thetas[s % nsets]
+        for h in range(2):
+            model.log_posterior_batch(th[h * half:(h + 1) * half])
+    post_s = max_over_ranks(time.perf_counter() - t0)
+
+    info = engine.info()
+    result = None
+    if rank == 0:
+        peak_probe = fp32_peak_tflops(local)
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fobj:
+                peaks = json.load(fobj)
+        except (OSError, ValueError):
+            pass
+        evals_per_s_per_gpu = value / world
+        achieved = info['flops_per_eval'] * evals_per_s_per_gpu / 1e12
+        fft_achieved = info['fft_flops_per_eval'] * evals_per_s_per_gpu / 1e12
+        hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        roofline = {
+            'bound': 'fp32',
+            'achieved': round(achieved, 3), 'peak': round(peak_probe, 2),
+            'unit': 'TFLOP/s', 'frac': round(achieved / peak_probe, 4),
+            'traffic': None,
+            'note': 'FP32 CUDA-core bound path (north_star: no tensor cores); '
+                    'achieved = (10 N log2 N + (30 n_sersic + 16) N) FLOP/eval x evals/s '
+                    'per GPU over the device-timed step; peak = FP32 FMA probe '
+                    'measured in this run (MEASURED_PEAKS.json has no FP32 entry)',
+            'fft_stage_achieved': round(fft_achieved, 3),
+            'fft_stage_frac': round(fft_achieved / peak_probe, 4),
+            'flops_per_eval': info['flops_per_eval'],
+            'hbm': {'achieved': round(info['hbm_bytes_per_eval'] * evals_per_s_per_gpu / 1e9, 2),
+                    'peak': hbm_peak, 'unit': 'GB/s',
+                    'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
+                    'bytes_per_eval': info['hbm_bytes_per_eval']},
+            'engine_path': 'fused' if info['path'] == 1 else 'staged',
+        }
+        result = {
+            'metric': METRIC, 'value': round(value, 1), 'unit': UNIT,
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 render+FFT / f64 accumulate' if args.precision == 'fp32' else 'f64',
+            'data': 'synthetic walkers drawn from the model priors (seeded); '
+                    + ('J0005-0006 example frames' if args.workload == 'c1'
+                       else 'synthetic frames'),
+            'config': {'workload': workload_description(args.workload, walkers),
+                       'walkers_per_gpu': walkers, 'batch_per_launch': half,
+                       'ndim': ndim, 'frame': list(engine.shape),
+                       'l2': 'flushed (256 MiB write) between timed steps'},
+            'e2e': {'value': round(e2e_value, 1), 'unit': UNIT,
+                    'h2d_bytes_per_step': walkers * ndim * 8,
+                    'd2h_bytes_per_step': walkers * 8,
+                    'timer': 'host perf_counter around blocking C-ABI calls '
+                             '(psfmc_lnlike_batch), max over ranks',
+                    'with_python_priors': round(world * walkers * args.steps / post_s, 1)},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': roofline,
+        }
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, cores, count, elapsed = time_cpu_port(args.workload, thetas[0],
+                                                    args.cpu_seconds)
+        result['cpu_baseline'] = {
+            'value': round(rate, 1), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '{} evaluations of the same workload in {:.1f} s on {} worker '
+                      'processes (oracle numpy port of the reference path, lnL only: no '
+                      'priors, no point-source-subtracted blob)'.format(count, elapsed, cores)}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(result))
+
+
+# ------------------------------------------------------------ reference arm --
+
+def run_reference(args):
+    """The reference's CPU implementation of the path on the host cores. The
+    reference is pure Python and cannot travel to the GPU box, so this runs its
+    oracle port (oracle/psfmc_oracle.py, pinned bit-for-bit against the reference
+    by tests/golden/make_golden.py) on all host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from psfmc_b200.components import Configuration
+    from psfmc_b200.program import compile_program
+    walkers = args.walkers or default_walkers(args.workload)
+    comps = build_components(args.workload)
+    config = [c for c in comps if isinstance(c, Configuration)][0]
+    rest = [c for c in comps if c is not config] + [config.psf_selector]
+    _, _, ndim = compile_program(rest)
+
+    class _Shim(object):     # priors only, to draw the same walkers as the GPU arm
+        pass
+    from psfmc_b200.synthetic import draw_walkers_fast
+    shim = _Shim()
+    shim.components = rest
+    shim.num_params = ndim
+
+    def log_priors_batch(thetas):
+        total, start = np.zeros(len(thetas)), 0
+        for comp in rest:
+            count = comp.num_stochastics()
+            total = total + comp.log_priors_batch(thetas[:, start:start + count])
+            start += count
+        return total
+    shim.log_priors_batch = log_priors_batch
+    thetas = draw_walkers_fast(shim, walkers, seed=0)
+
+    port = CpuPort(args.workload)
+    # bounded sample per step so that the whole run ends within minutes
+    probe = port.cores * 4
+    t0 = time.perf_counter()
+    port.evaluate(thetas[:probe])
+    per_eval = (time.perf_counter() - t0) / probe
+    total_steps = args.steps + args.warmup
+    sample = int(min(walkers, max(port.cores * 4, 60.0 / max(total_steps, 1) / per_eval)))
+    for s in range(args.warmup):
+        port.evaluate(thetas[:sample])
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        lo = (s * sample) % max(1, walkers - sample)
+        port.evaluate(thetas[lo:lo + sample])
+    elapsed = time.perf_counter() - t0
+    port.close()
+    rate = sample * args.steps / elapsed
+    sample_text = ('{} of the {} evaluations of a step, per step, on {} worker processes '
+                   '(oracle numpy port, lnL only)'.format(sample, walkers, port.cores))
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': round(rate, 1), 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': round(1e3 * elapsed / args.steps, 3), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 (numpy, float32 storage)',
+        'data': 'synthetic walkers drawn from the model priors (seeded)',
+        'config': {'workload': workload_description(args.workload, walkers)},
+        'cpu_baseline': {'value': round(rate, 1), 'unit': UNIT, 'cores': port.cores,
+                         'kind': 'port', 'sample': sample_text},
+        'e2e': {'value': round(rate, 1), 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+    }))
+
+
+if __name__ == '__main__':
+    cli = parse_args()
+    if cli.impl == 'reference':
+        run_reference(cli)
+    else:
+        run_ours(cli)

@@ -1,0 +1,174 @@
+/*
+ * psfmc_b200 -- C ABI of the B200-native batched likelihood engine.
+ *
+ * Drop-in boundary for the one hot path of mmechtley/psfMC: what emcee calls once
+ * per walker per (half-)iteration,
+ *     MultiComponentModel.log_posterior            psfMC/models.py:193-243
+ * minus the priors (which stay in Python): render the parametric model
+ * (psfMC/models.py:245-253), FFT-convolve it with the PSF (psfMC/utils.py:25-32),
+ * form the composite inverse-variance map with the PSF-variance term
+ * (psfMC/models.py:265-280) and reduce the masked Normal log-likelihood
+ * (psfMC/models.py:233-241) -- for a whole batch of parameter vectors per call.
+ *
+ * Plain C types only: no CUDA, torch or C++ types cross this boundary, so the
+ * library can be bound with ctypes (psfmc_b200/_lib.py), cffi, or any FFI.
+ * Every entry point returns 0 on success or a PSFMC_ERR_* code; the message is
+ * available (per calling thread) from psfmc_last_error(). Numerical failure is
+ * NOT an error: a walker whose lnL is NaN/Inf gets -inf, mirroring
+ * psfMC/models.py:238-241.
+ *
+ * Ownership: the caller owns every host buffer; psfmc_engine_create copies what
+ * it needs to each device and keeps no caller pointer. Outputs are written into
+ * caller-allocated buffers. An engine is not re-entrant: one call at a time.
+ */
+#ifndef PSFMC_B200_H
+#define PSFMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSFMC_ABI_VERSION 1
+
+/* error codes */
+#define PSFMC_OK 0
+#define PSFMC_ERR_INVALID_ARG 1   /* bad descriptor / shapes / slot indices        */
+#define PSFMC_ERR_UNSUPPORTED 2   /* frame size the kernels do not cover             */
+#define PSFMC_ERR_CUDA 3          /* a CUDA runtime call failed (message has detail) */
+#define PSFMC_ERR_NO_DEVICE 4     /* no usable sm_100 device                          */
+
+/* component kinds: psfMC/ModelComponents/{Sky,PointSource,Sersic}.py */
+#define PSFMC_SKY 0
+#define PSFMC_POINT 1
+#define PSFMC_SERSIC 2
+
+/* component flags */
+#define PSFMC_FLAG_ANGLE_DEGREES 1 /* Sersic(angle_degrees=True)        Sersic.py:30-39   */
+#define PSFMC_FLAG_BILINEAR 2      /* PointSource(shift_method='bilinear'); default is
+                                      'lanczos3'                         PointSource.py:18-22 */
+
+/* parameter slots of a component (index into psfmc_component.slot[]) */
+#define PSFMC_P_ADU 0    /* Sky.adu                                              */
+#define PSFMC_P_X 0      /* xy[0], 0-based pixel coordinates                      */
+#define PSFMC_P_Y 1      /* xy[1]                                                */
+#define PSFMC_P_MAG 2
+#define PSFMC_P_REFF 3   /* Sersic only from here on                              */
+#define PSFMC_P_REFF_B 4
+#define PSFMC_P_INDEX 5
+#define PSFMC_P_ANGLE 6
+#define PSFMC_NSLOTS 7
+
+#define PSFMC_MAX_COMPONENTS 32
+
+/* precision modes */
+#define PSFMC_PREC_FP64 0 /* everything in float64: parity mode, gated at 1e-10
+                             relative against the all-float64 oracle (mode M3)     */
+#define PSFMC_PREC_FP32 1 /* float32 render + FFT, float64 chi-square accumulation:
+                             the throughput mode, gated at a stated |dlnL|          */
+#define PSFMC_PREC_FP64_RAWF32 2 /* as FP64 but the raw model is rounded to float32
+                             after each component is added, which is what the
+                             reference does for float32 FITS inputs on numpy 1.x
+                             (oracle mode M2; psfMC/models.py:249)                  */
+
+/* images psfmc_render_batch can return: the blobs of psfMC/models.py:222-226 */
+#define PSFMC_IMG_RAW_MODEL 1u
+#define PSFMC_IMG_CONVOLVED_MODEL 2u
+#define PSFMC_IMG_RESIDUAL 4u
+#define PSFMC_IMG_COMPOSITE_IVM 8u
+#define PSFMC_IMG_POINT_SOURCE_SUBTRACTED 16u
+
+/* One parameter of one component: either a constant or an index into theta.
+ * (ComponentBase.assign_stochastic: priors vs constants, ComponentBase.py:26-35) */
+typedef struct psfmc_slot {
+  int32_t theta_index; /* >= 0: value = theta[theta_index]; < 0: value = value */
+  int32_t reserved;
+  double value;
+} psfmc_slot;
+
+typedef struct psfmc_component {
+  int32_t kind;  /* PSFMC_SKY / PSFMC_POINT / PSFMC_SERSIC */
+  int32_t flags; /* PSFMC_FLAG_* */
+  psfmc_slot slot[PSFMC_NSLOTS];
+} psfmc_component;
+
+/* Everything psfMC's Configuration + PSFSelector prepare once per model
+ * (Configuration.py:38-52, PSFSelector.py:16-43), plus the component program. */
+typedef struct psfmc_desc {
+  int32_t abi_version; /* PSFMC_ABI_VERSION */
+  int32_t height;      /* observation frame, rows    (power of two, 16..1024) */
+  int32_t width;       /* observation frame, columns (power of two, 16..1024) */
+  const double *obs_data;  /* [height*width] row-major                          */
+  const double *obs_var;   /* [height*width] 1/ivm, +inf at data-bad pixels      */
+  const uint8_t *bad_px;   /* [height*width] nonzero = excluded from the sum     */
+  int32_t n_psf;           /* K >= 1                                             */
+  int32_t psf_height;      /* <= height                                          */
+  int32_t psf_width;       /* <= width                                           */
+  const double *psf;       /* [K][psf_height*psf_width] normalised PSFs          */
+  const double *psf_var;   /* [K][psf_height*psf_width] variance maps            */
+  double mag_zeropoint;
+  int32_t n_components;
+  const psfmc_component *components; /* in model order (models.py:245-253)      */
+  psfmc_slot psf_index;    /* PSFSelector.psf_index; constant 0 when K == 1      */
+  int32_t precision;       /* PSFMC_PREC_*                                       */
+  int32_t n_devices;       /* 0: use the current CUDA device only                */
+  const int32_t *devices;  /* CUDA ordinals; batches are split contiguously       */
+  int32_t max_batch;       /* hint: largest B per call (0 = grow on demand)      */
+  int32_t flags;           /* reserved, 0                                         */
+} psfmc_desc;
+
+typedef struct psfmc_engine psfmc_engine;
+
+/* Build an engine: uploads the constants to every device, transforms the padded
+ * PSFs and variance maps on the device (pad offset pad//2 as utils.py:9-22, the
+ * ifftshift of utils.py:32 folded into the spectra) and sizes the scratch. */
+int psfmc_engine_create(const psfmc_desc *desc, psfmc_engine **out);
+void psfmc_engine_destroy(psfmc_engine *engine);
+
+/* lnL for B parameter vectors held in HOST memory (theta[b*ld + j], ld >= D).
+ * Blocking. Rows are split over the engine's devices; the only cross-device
+ * traffic is the per-walker lnL copied back. lnl_out[b] = -inf for non-finite
+ * results. This is what the pool-like map object calls for emcee. */
+int psfmc_lnlike_batch(psfmc_engine *engine, const double *theta, int64_t n_batch,
+                       int64_t ld, double *lnl_out);
+
+/* Same computation with DEVICE-resident theta and lnL on device `device_slot`
+ * (index into the engine's device list), enqueued on `cuda_stream` (a
+ * cudaStream_t passed as void*; NULL = the legacy default stream). Asynchronous:
+ * returns after the launches are enqueued. */
+int psfmc_lnlike_batch_device(psfmc_engine *engine, int32_t device_slot,
+                              const double *theta_dev, int64_t n_batch, int64_t ld,
+                              double *lnl_dev, void *cuda_stream);
+
+/* The blob images of psfMC/models.py:213-226 for B parameter vectors: for every
+ * image selected in `which` (ascending bit order), out receives
+ * [n_selected][B][height*width] doubles (host memory). */
+int psfmc_render_batch(psfmc_engine *engine, const double *theta, int64_t n_batch,
+                       int64_t ld, uint32_t which, double *out);
+
+/* Introspection (roofline bookkeeping for bench.py). */
+typedef struct psfmc_info {
+  int32_t height, width, n_components, n_sersic, n_point, n_psf, precision;
+  int32_t n_devices;
+  int32_t path;             /* 0 = staged row/column passes through L2/HBM,
+                               1 = fused single-kernel shared-memory path          */
+  int32_t kernels_per_call; /* kernels launched per lnlike call per device        */
+  double flops_per_eval;    /* 10 N log2 N + (30 n_sersic + 16) N     */
+  double fft_flops_per_eval;   /* 10 N log2 N                                     */
+  double hbm_bytes_per_eval;   /* algorithmic bytes through L2/HBM per walker     */
+  int64_t launches_total;   /* kernels launched by this engine since creation     */
+} psfmc_info;
+int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info);
+
+/* Measured FP32 FMA throughput of one device (TFLOP/s, FMA = 2 FLOP): the
+ * denominator of the FP32 roofline (MEASURED_PEAKS.json has no FP32 entry). */
+int psfmc_fp32_peak_probe(int32_t device, double *tflops_out, double *ms_out);
+
+const char *psfmc_last_error(void);
+int psfmc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSFMC_B200_H */

@@ -1,0 +1,138 @@
+"""
+ctypes binding of the C ABI declared in include/psfmc_b200.h.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a)
+as ``psfmc_b200/libpsfmc_b200.so``. There is no CPU fallback: if the library is
+missing or fails to load, importing this module's :func:`load` raises.
+"""
+import ctypes
+import os
+
+ABI_VERSION = 1
+
+SKY, POINT, SERSIC = 0, 1, 2
+FLAG_ANGLE_DEGREES, FLAG_BILINEAR = 1, 2
+P_ADU, P_X, P_Y, P_MAG, P_REFF, P_REFF_B, P_INDEX, P_ANGLE = 0, 0, 1, 2, 3, 4, 5, 6
+NSLOTS = 7
+MAX_COMPONENTS = 32
+PREC_FP64, PREC_FP32, PREC_FP64_RAWF32 = 0, 1, 2
+PRECISIONS = {'fp64': PREC_FP64, 'fp32': PREC_FP32, 'fp64_rawf32': PREC_FP64_RAWF32}
+IMAGE_BITS = {'raw_model': 1, 'convolved_model': 2, 'residual': 4,
+              'composite_ivm': 8, 'point_source_subtracted': 16}
+
+
+class Slot(ctypes.Structure):
+    _fields_ = [('theta_index', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('value', ctypes.c_double)]
+
+
+class Component(ctypes.Structure):
+    _fields_ = [('kind', ctypes.c_int32), ('flags', ctypes.c_int32),
+                ('slot', Slot * NSLOTS)]
+
+
+class Desc(ctypes.Structure):
+    _fields_ = [
+        ('abi_version', ctypes.c_int32),
+        ('height', ctypes.c_int32), ('width', ctypes.c_int32),
+        ('obs_data', ctypes.POINTER(ctypes.c_double)),
+        ('obs_var', ctypes.POINTER(ctypes.c_double)),
+        ('bad_px', ctypes.POINTER(ctypes.c_uint8)),
+        ('n_psf', ctypes.c_int32),
+        ('psf_height', ctypes.c_int32), ('psf_width', ctypes.c_int32),
+        ('psf', ctypes.POINTER(ctypes.c_double)),
+        ('psf_var', ctypes.POINTER(ctypes.c_double)),
+        ('mag_zeropoint', ctypes.c_double),
+        ('n_components', ctypes.c_int32),
+        ('components', ctypes.POINTER(Component)),
+        ('psf_index', Slot),
+        ('precision', ctypes.c_int32),
+        ('n_devices', ctypes.c_int32),
+        ('devices', ctypes.POINTER(ctypes.c_int32)),
+        ('max_batch', ctypes.c_int32),
+        ('flags', ctypes.c_int32),
+    ]
+
+
+class Info(ctypes.Structure):
+    _fields_ = [
+        ('height', ctypes.c_int32), ('width', ctypes.c_int32),
+        ('n_components', ctypes.c_int32), ('n_sersic', ctypes.c_int32),
+        ('n_point', ctypes.c_int32), ('n_psf', ctypes.c_int32),
+        ('precision', ctypes.c_int32), ('n_devices', ctypes.c_int32),
+        ('path', ctypes.c_int32), ('kernels_per_call', ctypes.c_int32),
+        ('flops_per_eval', ctypes.c_double),
+        ('fft_flops_per_eval', ctypes.c_double),
+        ('hbm_bytes_per_eval', ctypes.c_double),
+        ('launches_total', ctypes.c_int64),
+    ]
+
+
+# every symbol include/psfmc_b200.h declares
+EXPORTED_SYMBOLS = (
+    'psfmc_engine_create', 'psfmc_engine_destroy', 'psfmc_lnlike_batch',
+    'psfmc_lnlike_batch_device', 'psfmc_render_batch', 'psfmc_engine_info',
+    'psfmc_fp32_peak_probe', 'psfmc_last_error', 'psfmc_abi_version',
+)
+
+_DEFAULT_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                             'libpsfmc_b200.so')
+_cache = {}
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, message):
+        super(EngineError, self).__init__(
+            'psfmc_b200 error {}: {}'.format(code, message))
+        self.code = code
+
+
+def library_path():
+    return os.environ.get('PSFMC_B200_LIB', _DEFAULT_PATH)
+
+
+def load(path=None):
+    """Load (once per path) and prototype the shared library."""
+    path = path or library_path()
+    if path in _cache:
+        return _cache[path]
+    if not os.path.exists(path):
+        raise ImportError(
+            'psfmc_b200: CUDA library not found at {} -- build it with '
+            '`python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a). '
+            'There is no CPU fallback.'.format(path))
+    lib = ctypes.CDLL(path)
+    dbl_p = ctypes.POINTER(ctypes.c_double)
+    lib.psfmc_abi_version.restype = ctypes.c_int
+    lib.psfmc_abi_version.argtypes = []
+    lib.psfmc_last_error.restype = ctypes.c_char_p
+    lib.psfmc_last_error.argtypes = []
+    lib.psfmc_engine_create.restype = ctypes.c_int
+    lib.psfmc_engine_create.argtypes = [ctypes.POINTER(Desc),
+                                        ctypes.POINTER(ctypes.c_void_p)]
+    lib.psfmc_engine_destroy.restype = None
+    lib.psfmc_engine_destroy.argtypes = [ctypes.c_void_p]
+    lib.psfmc_lnlike_batch.restype = ctypes.c_int
+    lib.psfmc_lnlike_batch.argtypes = [ctypes.c_void_p, dbl_p, ctypes.c_int64,
+                                       ctypes.c_int64, dbl_p]
+    lib.psfmc_lnlike_batch_device.restype = ctypes.c_int
+    lib.psfmc_lnlike_batch_device.argtypes = [
+        ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64,
+        ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    lib.psfmc_render_batch.restype = ctypes.c_int
+    lib.psfmc_render_batch.argtypes = [ctypes.c_void_p, dbl_p, ctypes.c_int64,
+                                       ctypes.c_int64, ctypes.c_uint32, dbl_p]
+    lib.psfmc_engine_info.restype = ctypes.c_int
+    lib.psfmc_engine_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(Info)]
+    lib.psfmc_fp32_peak_probe.restype = ctypes.c_int
+    lib.psfmc_fp32_peak_probe.argtypes = [ctypes.c_int32, dbl_p, dbl_p]
+    if lib.psfmc_abi_version() != ABI_VERSION:
+        raise ImportError('psfmc_b200: ABI version mismatch between {} and the '
+                          'Python binding'.format(path))
+    _cache[path] = lib
+    return lib
+
+
+def check(lib, code):
+    if code != 0:
+        raise EngineError(code, lib.psfmc_last_error().decode('utf-8', 'replace'))

@@ -1,0 +1,748 @@
+// psfmc_b200 engine: C ABI (include/psfmc_b200.h) + host runtime.
+//
+// One engine = one model (constant frames, PSF spectra, component program)
+// replicated on every device of its device list; batches of parameter vectors
+// are split contiguously over the devices, each with its own stream, pinned
+// staging buffers and scratch. No collective is involved: walkers are independent
+// (SURVEY.md section 8e); the only cross-device traffic is theta in / lnL out.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "pipeline.cuh"
+#ifndef PSFMC_NO_FUSED
+#include "kernels_fused.cuh"
+#endif
+
+using namespace psfmc;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                              \
+  do {                                                                              \
+    cudaError_t err__ = (expr);                                                     \
+    if (err__ != cudaSuccess) {                                                     \
+      char buf__[512];                                                              \
+      snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #expr,                \
+               cudaGetErrorString(err__), __FILE__, __LINE__);                      \
+      return fail(PSFMC_ERR_CUDA, buf__);                                           \
+    }                                                                               \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *ptr = nullptr;
+  size_t count = 0;
+  int ensure(size_t n) {
+    if (n <= count) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+    size_t want = n + n / 2;
+    if (cudaMalloc(&ptr, want * sizeof(T)) != cudaSuccess) {
+      cudaGetLastError();
+      want = n;
+      if (cudaMalloc(&ptr, want * sizeof(T)) != cudaSuccess) return 1;
+    }
+    count = want;
+    return 0;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+};
+
+template <typename T>
+struct PinBuf {
+  T *ptr = nullptr;
+  size_t count = 0;
+  int ensure(size_t n) {
+    if (n <= count) return 0;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    count = 0;
+    size_t want = n + n / 2;
+    if (cudaMallocHost(&ptr, want * sizeof(T)) != cudaSuccess) return 1;
+    count = want;
+    return 0;
+  }
+  void release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+};
+
+// Per-device state for real type T.
+template <typename T>
+struct DeviceState {
+  int ordinal = 0;
+  cudaStream_t stream = nullptr;
+  Program *prog = nullptr;
+  cplx<T> *tw_w = nullptr, *tw_h = nullptr, *spec = nullptr;
+  T *obs = nullptr, *ovar = nullptr;
+  unsigned char *bad = nullptr;
+  DevBuf<double> derived, partials, theta, lnl, wscale;
+  double *vscale_inv = nullptr;
+  DevBuf<int> psf_sel;
+  DevBuf<cplx<T>> scratch;
+  DevBuf<T> img[4];
+  PinBuf<double> theta_pin, lnl_pin;
+  PinBuf<T> img_pin;
+  // rows of the current host call
+  long long row0 = 0, nrows = 0;
+};
+
+struct EngineBase {
+  virtual ~EngineBase() {}
+  virtual int lnlike_host(const double *theta, long long B, long long ld, double *out) = 0;
+  virtual int lnlike_device(int slot, const double *theta, long long B, long long ld,
+                            double *lnl, void *stream) = 0;
+  virtual int render(const double *theta, long long B, long long ld, unsigned which,
+                     double *out) = 0;
+  int H = 0, W = 0, precision = 0;
+  Program prog_h;
+  int n_sersic = 0, n_point = 0;
+  StagedPlan plan;
+  int path = 0;
+  long long launches = 0;
+  int n_devices = 0;
+};
+
+template <typename T>
+struct Engine : EngineBase {
+  std::vector<DeviceState<T>> devs;
+
+  ~Engine() override {
+    for (auto &d : devs) {
+      cudaSetDevice(d.ordinal);
+      if (d.stream) cudaStreamSynchronize(d.stream);
+      cudaFree(d.prog);
+      cudaFree(d.tw_w);
+      cudaFree(d.tw_h);
+      cudaFree(d.spec);
+      cudaFree(d.obs);
+      cudaFree(d.ovar);
+      cudaFree(d.bad);
+      cudaFree(d.vscale_inv);
+      d.wscale.release();
+      d.derived.release();
+      d.partials.release();
+      d.theta.release();
+      d.lnl.release();
+      d.psf_sel.release();
+      d.scratch.release();
+      for (auto &im : d.img) im.release();
+      d.theta_pin.release();
+      d.lnl_pin.release();
+      d.img_pin.release();
+      if (d.stream) cudaStreamDestroy(d.stream);
+    }
+  }
+
+  StagedBuffers<T> buffers(DeviceState<T> &d) {
+    StagedBuffers<T> b;
+    b.prog = d.prog;
+    b.tw_w = d.tw_w;
+    b.tw_h = d.tw_h;
+    b.spec = d.spec;
+    b.obs = d.obs;
+    b.ovar = d.ovar;
+    b.bad = d.bad;
+    b.derived = d.derived.ptr;
+    b.psf_sel = d.psf_sel.ptr;
+    b.wscale = d.wscale.ptr;
+    b.vscale_inv = d.vscale_inv;
+    b.scratch = d.scratch.ptr;
+    b.partials = d.partials.ptr;
+    return b;
+  }
+
+  int ensure_batch(DeviceState<T> &d, long long B) {
+    size_t nb = (size_t)B;
+    long long chunk = B < plan.chunk ? B : plan.chunk;
+    if (d.derived.ensure(nb * prog_h.n_components * PSFMC_DERIVED_STRIDE) ||
+        d.partials.ensure(nb * plan.n_rowblk) || d.psf_sel.ensure(nb) ||
+        d.wscale.ensure(nb) ||
+        d.scratch.ensure((size_t)chunk * plan.scratch_elems_per_walker))
+      return fail(PSFMC_ERR_CUDA, "device allocation failed while sizing the batch buffers");
+    return 0;
+  }
+
+  // Enqueue the whole lnL computation for device-resident theta.
+  int enqueue(DeviceState<T> &d, const double *theta_dev, long long B, long long ld,
+              double *lnl_dev, cudaStream_t stream) {
+    int rc = ensure_batch(d, B);
+    if (rc) return rc;
+    StagedBuffers<T> buf = buffers(d);
+#ifndef PSFMC_NO_FUSED
+    if (path == 1) {
+      launches += launch_fused_lnlike<T>(plan, buf, prog_h.n_components, precision,
+                                         theta_dev, B, ld, lnl_dev, stream);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
+#endif
+    launch_staged_lnlike<T>(plan, buf, prog_h.n_components, precision, theta_dev, B, ld,
+                            lnl_dev, stream);
+    launches += count_launches<T>(plan, B);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+
+  int lnlike_device(int slot, const double *theta, long long B, long long ld, double *lnl,
+                    void *stream) override {
+    if (slot < 0 || slot >= (int)devs.size())
+      return fail(PSFMC_ERR_INVALID_ARG, "device_slot out of range");
+    if (B <= 0) return 0;
+    DeviceState<T> &d = devs[slot];
+    CUDA_TRY(cudaSetDevice(d.ordinal));
+    return enqueue(d, theta, B, ld, lnl, (cudaStream_t)stream);
+  }
+
+  int lnlike_host(const double *theta, long long B, long long ld, double *out) override {
+    if (B <= 0) return 0;
+    const int D = (int)ld;
+    const int nd = (int)devs.size();
+    long long base = B / nd, extra = B % nd, row = 0;
+    // is the caller's memory already pinned? then skip the staging copies
+    bool theta_pinned = false, out_pinned = false;
+    {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, theta) == cudaSuccess)
+        theta_pinned = (at.type == cudaMemoryTypeHost);
+      else
+        cudaGetLastError();
+      if (cudaPointerGetAttributes(&at, out) == cudaSuccess)
+        out_pinned = (at.type == cudaMemoryTypeHost);
+      else
+        cudaGetLastError();
+    }
+    for (int i = 0; i < nd; ++i) {
+      DeviceState<T> &d = devs[i];
+      d.row0 = row;
+      d.nrows = base + (i < extra ? 1 : 0);
+      row += d.nrows;
+      if (d.nrows == 0) continue;
+      CUDA_TRY(cudaSetDevice(d.ordinal));
+      size_t nel = (size_t)d.nrows * D;
+      if (d.theta.ensure(nel) || d.lnl.ensure((size_t)d.nrows))
+        return fail(PSFMC_ERR_CUDA, "device allocation failed (theta/lnl)");
+      const double *src = theta + d.row0 * ld;
+      if (!theta_pinned) {
+        if (d.theta_pin.ensure(nel))
+          return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
+        memcpy(d.theta_pin.ptr, src, nel * sizeof(double));
+        src = d.theta_pin.ptr;
+      }
+      CUDA_TRY(cudaMemcpyAsync(d.theta.ptr, src, nel * sizeof(double),
+                               cudaMemcpyHostToDevice, d.stream));
+      int rc = enqueue(d, d.theta.ptr, d.nrows, ld, d.lnl.ptr, d.stream);
+      if (rc) return rc;
+      double *dst = out + d.row0;
+      if (!out_pinned) {
+        if (d.lnl_pin.ensure((size_t)d.nrows))
+          return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
+        dst = d.lnl_pin.ptr;
+      }
+      CUDA_TRY(cudaMemcpyAsync(dst, d.lnl.ptr, (size_t)d.nrows * sizeof(double),
+                               cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (int i = 0; i < nd; ++i) {
+      DeviceState<T> &d = devs[i];
+      if (d.nrows == 0) continue;
+      CUDA_TRY(cudaSetDevice(d.ordinal));
+      CUDA_TRY(cudaStreamSynchronize(d.stream));
+      if (!out_pinned)
+        memcpy(out + d.row0, d.lnl_pin.ptr, (size_t)d.nrows * sizeof(double));
+    }
+    return 0;
+  }
+
+  // Blob images (psfMC/models.py:213-226); device 0 only, chunked.
+  int render(const double *theta, long long B, long long ld, unsigned which,
+             double *out) override {
+    if (B <= 0 || which == 0) return 0;
+    DeviceState<T> &d = devs[0];
+    CUDA_TRY(cudaSetDevice(d.ordinal));
+    const size_t npx = (size_t)H * W;
+    int nsel = 0;
+    for (unsigned bit = 1; bit <= PSFMC_IMG_POINT_SOURCE_SUBTRACTED; bit <<= 1)
+      if (which & bit) ++nsel;
+    long long chunk = plan.chunk < 64 ? plan.chunk : 64;
+    if (chunk > B) chunk = B;
+    for (int k = 0; k < 4; ++k)
+      if (d.img[k].ensure((size_t)chunk * npx))
+        return fail(PSFMC_ERR_CUDA, "device allocation failed (images)");
+    if (d.img_pin.ensure((size_t)chunk * npx) || d.theta.ensure((size_t)chunk * ld) ||
+        d.lnl.ensure((size_t)chunk))
+      return fail(PSFMC_ERR_CUDA, "allocation failed (image staging)");
+    for (long long start = 0; start < B; start += chunk) {
+      long long nb = B - start < chunk ? B - start : chunk;
+      int rc = ensure_batch(d, nb);
+      if (rc) return rc;
+      CUDA_TRY(cudaMemcpyAsync(d.theta.ptr, theta + start * ld, (size_t)nb * ld * sizeof(double),
+                               cudaMemcpyHostToDevice, d.stream));
+      StagedBuffers<T> buf = buffers(d);
+      ImageOutputs<T> io;
+      io.raw = d.img[0].ptr;
+      io.conv = d.img[1].ptr;
+      io.resid = d.img[2].ptr;
+      io.ivm = d.img[3].ptr;
+      launch_staged_lnlike<T>(plan, buf, prog_h.n_components, precision, d.theta.ptr, nb, ld,
+                              d.lnl.ptr, d.stream, false, &io);
+      launches += count_launches<T>(plan, nb);
+      CUDA_TRY(cudaGetLastError());
+      int sel = 0;
+      for (int k = 0; k < 5; ++k) {
+        unsigned bit = 1u << k;
+        if (!(which & bit)) continue;
+        T *src = nullptr;
+        if (k < 4) {
+          src = d.img[k].ptr;
+        } else {
+          // point sources only -> convolve -> obs - that (models.py:296-306)
+          ImageOutputs<T> ps;
+          ps.resid = d.img[0].ptr;
+          launch_staged_lnlike<T>(plan, buf, prog_h.n_components, precision, d.theta.ptr, nb,
+                                  ld, d.lnl.ptr, d.stream, true, &ps);
+          launches += count_launches<T>(plan, nb);
+          CUDA_TRY(cudaGetLastError());
+          src = d.img[0].ptr;
+        }
+        CUDA_TRY(cudaMemcpyAsync(d.img_pin.ptr, src, (size_t)nb * npx * sizeof(T),
+                                 cudaMemcpyDeviceToHost, d.stream));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        double *dst = out + ((size_t)sel * B + start) * npx;
+        for (size_t e = 0; e < (size_t)nb * npx; ++e) dst[e] = (double)d.img_pin.ptr[e];
+        ++sel;
+      }
+    }
+    (void)nsel;
+    return 0;
+  }
+};
+
+int validate_desc(const psfmc_desc *d) {
+  if (!d) return fail(PSFMC_ERR_INVALID_ARG, "descriptor is null");
+  if (d->abi_version != PSFMC_ABI_VERSION)
+    return fail(PSFMC_ERR_INVALID_ARG, "psfmc_desc.abi_version does not match the library");
+  if (!frame_supported(d->height, d->width))
+    return fail(PSFMC_ERR_UNSUPPORTED,
+                "frame height/width must be powers of two between 16 and 1024 "
+                "(the reference itself requires an even width, psfMC/models.py:276)");
+  if (!d->obs_data || !d->obs_var || !d->bad_px || !d->psf || !d->psf_var)
+    return fail(PSFMC_ERR_INVALID_ARG, "null image pointer in descriptor");
+  if (d->n_psf < 1) return fail(PSFMC_ERR_INVALID_ARG, "n_psf must be >= 1");
+  if (d->psf_height < 1 || d->psf_width < 1 || d->psf_height > d->height ||
+      d->psf_width > d->width)
+    return fail(PSFMC_ERR_UNSUPPORTED,
+                "PSF images larger than observation images are not supported "
+                "(psfMC/utils.py:16-18)");
+  if (d->n_components < 0 || d->n_components > PSFMC_MAX_COMPONENTS)
+    return fail(PSFMC_ERR_INVALID_ARG, "n_components out of range");
+  if (d->n_components > 0 && !d->components)
+    return fail(PSFMC_ERR_INVALID_ARG, "components pointer is null");
+  for (int c = 0; c < d->n_components; ++c) {
+    int k = d->components[c].kind;
+    if (k != PSFMC_SKY && k != PSFMC_POINT && k != PSFMC_SERSIC)
+      return fail(PSFMC_ERR_INVALID_ARG, "unknown component kind");
+  }
+  if (d->precision != PSFMC_PREC_FP64 && d->precision != PSFMC_PREC_FP32 &&
+      d->precision != PSFMC_PREC_FP64_RAWF32)
+    return fail(PSFMC_ERR_INVALID_ARG, "unknown precision mode");
+  if (d->n_devices < 0 || (d->n_devices > 0 && !d->devices))
+    return fail(PSFMC_ERR_INVALID_ARG, "bad device list");
+  return 0;
+}
+
+void build_program(const psfmc_desc *d, Program *p, int *n_sersic, int *n_point) {
+  memset(p, 0, sizeof(*p));
+  p->n_components = d->n_components;
+  *n_sersic = *n_point = 0;
+  for (int c = 0; c < d->n_components; ++c) {
+    const psfmc_component &cc = d->components[c];
+    p->kind[c] = cc.kind;
+    p->flags[c] = cc.flags;
+    if (cc.kind == PSFMC_SERSIC) ++*n_sersic;
+    if (cc.kind == PSFMC_POINT) ++*n_point;
+    for (int s = 0; s < PSFMC_NSLOTS; ++s) {
+      p->theta_index[c][s] = cc.slot[s].theta_index;
+      p->value[c][s] = cc.slot[s].value;
+    }
+  }
+  p->psf_theta_index = d->psf_index.theta_index;
+  p->psf_value = d->psf_index.value;
+  p->n_psf = d->n_psf;
+  p->mag_zp = d->mag_zeropoint;
+}
+
+template <typename T>
+int upload(T **dst, const std::vector<T> &src) {
+  CUDA_TRY(cudaMalloc(dst, src.size() * sizeof(T)));
+  CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// Spectra of the padded PSFs / variance maps, float64, on the current device.
+int compute_spectra(const psfmc_desc *d, const StagedPlan &plan,
+                    std::vector<cplx<double>> *spec_host) {
+  const int H = d->height, W = d->width, K = d->n_psf;
+  const size_t npx = (size_t)H * W, nps = (size_t)d->psf_height * d->psf_width;
+  // zero-pad at offset pad//2 (psfMC/utils.py:15-21)
+  std::vector<double> pad_psf(K * npx, 0.0), pad_var(K * npx, 0.0);
+  const int oy = (H - d->psf_height) / 2, ox = (W - d->psf_width) / 2;
+  for (int k = 0; k < K; ++k)
+    for (int y = 0; y < d->psf_height; ++y)
+      for (int x = 0; x < d->psf_width; ++x) {
+        size_t dst = k * npx + (size_t)(y + oy) * W + (x + ox);
+        size_t src = k * nps + (size_t)y * d->psf_width + x;
+        pad_psf[dst] = d->psf[src];
+        pad_var[dst] = d->psf_var[src];
+      }
+  // The PSF and its variance map share one packed transform (z = psf + i var);
+  // scale the (much smaller) variance channel by an exact power of two so that
+  // rounding errors of the PSF channel do not leak into it; undone below.
+  std::vector<double> chan_scale(K, 1.0);
+  for (int k = 0; k < K; ++k) {
+    double mp = 0.0, mv = 0.0;
+    for (size_t e = 0; e < npx; ++e) {
+      double a = fabs(pad_psf[k * npx + e]), b = fabs(pad_var[k * npx + e]);
+      if (isfinite(a) && a > mp) mp = a;
+      if (isfinite(b) && b > mv) mv = b;
+    }
+    if (mp > 0.0 && mv > 0.0) {
+      int ex = (int)lrint(log2(mp / mv));
+      if (ex > 900) ex = 900;
+      if (ex < -900) ex = -900;
+      chan_scale[k] = ldexp(1.0, ex);
+    }
+    for (size_t e = 0; e < npx; ++e) pad_var[k * npx + e] *= chan_scale[k];
+  }
+  std::vector<cplx<double>> tww(W), twh(H);
+  fill_twiddles<double>(tww.data(), W);
+  fill_twiddles<double>(twh.data(), H);
+  double *pp = nullptr, *pv = nullptr;
+  cplx<double> *tw_w = nullptr, *tw_h = nullptr, *scratch = nullptr, *spec = nullptr;
+  int rc = 0;
+  if ((rc = upload(&pp, pad_psf)) || (rc = upload(&pv, pad_var)) ||
+      (rc = upload(&tw_w, tww)) || (rc = upload(&tw_h, twh)))
+    return rc;
+  size_t nspec = (size_t)K * plan.scratch_elems_per_walker;
+  CUDA_TRY(cudaMalloc(&scratch, nspec * sizeof(cplx<double>)));
+  CUDA_TRY(cudaMalloc(&spec, nspec * sizeof(cplx<double>)));
+  StagedPlan dplan = make_staged_plan(H, W, 0, sizeof(double), 1.0);
+  launch_staged_setup(dplan, tw_w, tw_h, pp, pv, K, scratch, spec, (cudaStream_t)0);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  spec_host->resize(nspec);
+  CUDA_TRY(cudaMemcpy(spec_host->data(), spec, nspec * sizeof(cplx<double>),
+                      cudaMemcpyDeviceToHost));
+  {
+    const size_t per_psf = plan.scratch_elems_per_walker, half = per_psf / 2;
+    for (int k = 0; k < K; ++k) {
+      const double inv = 1.0 / chan_scale[k];
+      for (size_t e = half; e < per_psf; ++e) {
+        (*spec_host)[k * per_psf + e].x *= inv;
+        (*spec_host)[k * per_psf + e].y *= inv;
+      }
+    }
+  }
+  cudaFree(pp);
+  cudaFree(pv);
+  cudaFree(tw_w);
+  cudaFree(tw_h);
+  cudaFree(scratch);
+  cudaFree(spec);
+  return 0;
+}
+
+double chunk_mbytes_from_env() {
+  const char *env = getenv("PSFMC_CHUNK_MB");
+  if (env) {
+    double v = atof(env);
+    if (v > 0.0) return v;
+  }
+  return 48.0;
+}
+
+template <typename T>
+int create_engine(const psfmc_desc *d, EngineBase **out) {
+  Engine<T> *eng = new Engine<T>();
+  eng->H = d->height;
+  eng->W = d->width;
+  eng->precision = d->precision;
+  build_program(d, &eng->prog_h, &eng->n_sersic, &eng->n_point);
+  eng->plan = make_staged_plan(d->height, d->width, d->n_components, sizeof(T),
+                               chunk_mbytes_from_env());
+  eng->path = 0;
+  std::vector<int> ordinals;
+  if (d->n_devices == 0) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) {
+      delete eng;
+      return fail(PSFMC_ERR_NO_DEVICE, "no CUDA device available");
+    }
+    ordinals.push_back(cur);
+  } else {
+    ordinals.assign(d->devices, d->devices + d->n_devices);
+  }
+  int ndev_total = 0;
+  if (cudaGetDeviceCount(&ndev_total) != cudaSuccess || ndev_total < 1) {
+    delete eng;
+    return fail(PSFMC_ERR_NO_DEVICE, "no CUDA device available (cudaGetDeviceCount)");
+  }
+  const size_t npx = (size_t)d->height * d->width;
+  std::vector<T> obs(npx), ovar(npx);
+  for (size_t e = 0; e < npx; ++e) {
+    obs[e] = (T)d->obs_data[e];
+    ovar[e] = (T)d->obs_var[e];
+  }
+  std::vector<unsigned char> bad(d->bad_px, d->bad_px + npx);
+  std::vector<cplx<T>> tww(d->width), twh(d->height);
+  fill_twiddles<T>(tww.data(), d->width);
+  fill_twiddles<T>(twh.data(), d->height);
+  std::vector<Program> progv(1, eng->prog_h);
+
+  eng->devs.resize(ordinals.size());
+  eng->n_devices = (int)ordinals.size();
+  int rc = 0;
+  for (size_t i = 0; i < ordinals.size() && !rc; ++i) {
+    DeviceState<T> &ds = eng->devs[i];
+    ds.ordinal = ordinals[i];
+    if (ds.ordinal < 0 || ds.ordinal >= ndev_total) {
+      rc = fail(PSFMC_ERR_INVALID_ARG, "device ordinal out of range");
+      break;
+    }
+    if (cudaSetDevice(ds.ordinal) != cudaSuccess) {
+      rc = fail(PSFMC_ERR_CUDA, "cudaSetDevice failed");
+      break;
+    }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, ds.ordinal);
+    if (major < 10) {
+      rc = fail(PSFMC_ERR_NO_DEVICE,
+                "device is not sm_100 (Blackwell B200); this library carries sm_100a code only");
+      break;
+    }
+    if (cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking) != cudaSuccess) {
+      rc = fail(PSFMC_ERR_CUDA, "cudaStreamCreate failed");
+      break;
+    }
+    std::vector<cplx<double>> spec64;
+    if ((rc = compute_spectra(d, eng->plan, &spec64))) break;
+    // Balance the two channels of the packed inverse transform: scale the
+    // variance spectrum of PSF k by the power of two nearest ||P_k|| / ||V_k||.
+    std::vector<cplx<T>> spec(spec64.size());
+    std::vector<double> vscale_inv(d->n_psf, 1.0);
+    {
+      const size_t per_psf = eng->plan.scratch_elems_per_walker, half = per_psf / 2;
+      for (int k = 0; k < d->n_psf; ++k) {
+        double np2 = 0.0, nv2 = 0.0;
+        for (size_t e = 0; e < half; ++e) {
+          const cplx<double> &pp = spec64[k * per_psf + e];
+          const cplx<double> &vv = spec64[k * per_psf + half + e];
+          np2 += pp.x * pp.x + pp.y * pp.y;
+          nv2 += vv.x * vv.x + vv.y * vv.y;
+        }
+        double vs = 1.0;
+        if (np2 > 0.0 && nv2 > 0.0 && isfinite(np2) && isfinite(nv2)) {
+          int ex = (int)lrint(0.5 * log2(np2 / nv2));
+          if (ex > 200) ex = 200;
+          if (ex < -200) ex = -200;
+          vs = ldexp(1.0, ex);
+        }
+        vscale_inv[k] = 1.0 / vs;
+        for (size_t e = 0; e < per_psf; ++e) {
+          double f = e < half ? 1.0 : vs;
+          spec[k * per_psf + e].x = (T)(spec64[k * per_psf + e].x * f);
+          spec[k * per_psf + e].y = (T)(spec64[k * per_psf + e].y * f);
+        }
+      }
+    }
+    if ((rc = upload(&ds.prog, progv)) || (rc = upload(&ds.tw_w, tww)) ||
+        (rc = upload(&ds.tw_h, twh)) || (rc = upload(&ds.spec, spec)) ||
+        (rc = upload(&ds.obs, obs)) || (rc = upload(&ds.ovar, ovar)) ||
+        (rc = upload(&ds.bad, bad)) || (rc = upload(&ds.vscale_inv, vscale_inv)))
+      break;
+#ifndef PSFMC_NO_FUSED
+    if (i == 0) eng->path = fused_path_available<T>(eng->plan, eng->prog_h) ? 1 : 0;
+    if (eng->path == 1 && (rc = fused_prepare_device<T>(eng->plan))) break;
+#endif
+    if (d->max_batch > 0 && (rc = eng->ensure_batch(ds, d->max_batch))) break;
+  }
+  if (rc) {
+    delete eng;
+    return rc;
+  }
+  const char *force = getenv("PSFMC_FORCE_STAGED");
+  if (force && force[0] == '1') eng->path = 0;
+  *out = eng;
+  return 0;
+}
+
+// ------------------------------------------------------- FP32 peak probe --
+__global__ void fma_probe_kernel(float *out, int iters, float a, float b) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+  float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+    x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+  }
+  float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+struct psfmc_engine {
+  EngineBase *impl;
+};
+
+extern "C" {
+
+int psfmc_abi_version(void) { return PSFMC_ABI_VERSION; }
+
+const char *psfmc_last_error(void) { return g_last_error.c_str(); }
+
+int psfmc_engine_create(const psfmc_desc *desc, psfmc_engine **out) {
+  if (!out) return fail(PSFMC_ERR_INVALID_ARG, "out pointer is null");
+  *out = nullptr;
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  EngineBase *impl = nullptr;
+  if (desc->precision == PSFMC_PREC_FP32)
+    rc = create_engine<float>(desc, &impl);
+  else
+    rc = create_engine<double>(desc, &impl);
+  cudaSetDevice(prev);
+  if (rc) return rc;
+  psfmc_engine *eng = new psfmc_engine();
+  eng->impl = impl;
+  *out = eng;
+  return 0;
+}
+
+void psfmc_engine_destroy(psfmc_engine *engine) {
+  if (!engine) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  delete engine->impl;
+  delete engine;
+  cudaSetDevice(prev);
+}
+
+int psfmc_lnlike_batch(psfmc_engine *engine, const double *theta, int64_t n_batch, int64_t ld,
+                       double *lnl_out) {
+  if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
+  if (n_batch < 0 || ld < 0) return fail(PSFMC_ERR_INVALID_ARG, "negative batch or ld");
+  if (n_batch == 0) return 0;
+  if (!theta || !lnl_out) return fail(PSFMC_ERR_INVALID_ARG, "null theta / lnl_out");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int rc = engine->impl->lnlike_host(theta, n_batch, ld, lnl_out);
+  cudaSetDevice(prev);
+  return rc;
+}
+
+int psfmc_lnlike_batch_device(psfmc_engine *engine, int32_t device_slot, const double *theta_dev,
+                              int64_t n_batch, int64_t ld, double *lnl_dev, void *cuda_stream) {
+  if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
+  if (n_batch < 0 || ld < 0) return fail(PSFMC_ERR_INVALID_ARG, "negative batch or ld");
+  if (n_batch == 0) return 0;
+  if (!theta_dev || !lnl_dev) return fail(PSFMC_ERR_INVALID_ARG, "null theta / lnl pointer");
+  return engine->impl->lnlike_device(device_slot, theta_dev, n_batch, ld, lnl_dev, cuda_stream);
+}
+
+int psfmc_render_batch(psfmc_engine *engine, const double *theta, int64_t n_batch, int64_t ld,
+                       uint32_t which, double *out) {
+  if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
+  if (n_batch < 0 || ld < 0) return fail(PSFMC_ERR_INVALID_ARG, "negative batch or ld");
+  if (n_batch == 0 || which == 0) return 0;
+  if (!theta || !out) return fail(PSFMC_ERR_INVALID_ARG, "null theta / out");
+  if (which >= 32u) return fail(PSFMC_ERR_INVALID_ARG, "unknown image bits in `which`");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int rc = engine->impl->render(theta, n_batch, ld, which, out);
+  cudaSetDevice(prev);
+  return rc;
+}
+
+int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info) {
+  if (!engine || !engine->impl || !info) return fail(PSFMC_ERR_INVALID_ARG, "null argument");
+  const EngineBase *e = engine->impl;
+  memset(info, 0, sizeof(*info));
+  info->height = e->H;
+  info->width = e->W;
+  info->n_components = e->prog_h.n_components;
+  info->n_sersic = e->n_sersic;
+  info->n_point = e->n_point;
+  info->n_psf = e->prog_h.n_psf;
+  info->precision = e->precision;
+  info->n_devices = e->n_devices;
+  info->path = e->path;
+  double N = (double)e->H * e->W;
+  info->fft_flops_per_eval = 10.0 * N * log2(N);
+  info->flops_per_eval = info->fft_flops_per_eval + (30.0 * e->n_sersic + 16.0) * N;
+  size_t csz = (e->precision == PSFMC_PREC_FP32) ? 8 : 16;
+  // staged path: each of the 2*Wc*H complex intermediates is written by rows_fwd,
+  // read+written by cols and read by rows_inv (~32 N bytes in float32)
+  info->hbm_bytes_per_eval =
+      e->path == 1 ? (double)(e->prog_h.n_components * 0 + 8 * 32 + 8)
+                   : 4.0 * (double)e->plan.scratch_elems_per_walker * csz;
+  info->kernels_per_call = e->path == 1 ? 2 : 5;
+  info->launches_total = e->launches;
+  return 0;
+}
+
+int psfmc_fp32_peak_probe(int32_t device, double *tflops_out, double *ms_out) {
+  if (!tflops_out) return fail(PSFMC_ERR_INVALID_ARG, "null output pointer");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CUDA_TRY(cudaSetDevice(device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int block = 256, grid = sms * 16, iters = 1 << 15;
+  float *out = nullptr;
+  CUDA_TRY(cudaMalloc(&out, (size_t)grid * block * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    launch_kernel(fma_probe_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)0, out, iters,
+                  1.0000001f, 1e-7f);
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  CUDA_TRY(cudaGetLastError());
+  double flops = 2.0 * 8.0 * (double)iters * (double)grid * block;
+  *tflops_out = flops / (best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  cudaSetDevice(prev);
+  return 0;
+}
+
+}  // extern "C"

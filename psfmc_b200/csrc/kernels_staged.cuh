@@ -1,0 +1,335 @@
+// Staged row/column path: works for every supported frame (16..1024, powers of
+// two) in both precisions; the row spectra of each walker are staged through a
+// global scratch buffer that stays L2-resident for the batch chunk in flight.
+//
+//   rows_fwd : render RB rows -> z = raw + i raw^2 -> FFT_W -> split into the row
+//              spectra of the two real images (A: raw, B: raw^2) -> scratch,
+//              transposed to column-major so that the column pass is contiguous
+//   cols     : FFT_H of each retained column, multiply by the PSF / PSF-variance
+//              spectrum, inverse FFT_H, in place in scratch
+//   rows_inv : rebuild Y = A' + i B' with Hermitian extension, inverse FFT_W;
+//              Re = convolved model, Im = model variance -> residual, composite
+//              IVM, masked chi-square terms, float64 partial sums per row block
+//   finalize : fixed-order sum of the partials, -0.5 factor, non-finite -> -inf
+//
+// Scratch layout per walker: S[c][y], c in [0, 2*Wc): c < Wc is column kx = c of
+// image A, c >= Wc is column kx = c - Wc of image B; y = 0..H-1 contiguous.
+// Spectrum layout per PSF: Spec[c][ky], same column index, including the factor
+// (-1)^(kx+ky) / (H*W) (the reference's ifftshift, psfMC/utils.py:32, and the
+// inverse-FFT normalisation).
+#pragma once
+#include "common.cuh"
+#include "fft.cuh"
+#include "render.cuh"
+
+namespace psfmc {
+
+#define PSFMC_SRC_RENDER 0      // rows come from the model renderer
+#define PSFMC_SRC_PSFPAD 1      // rows come from padded PSF / variance frames (setup)
+#define PSFMC_SRC_RENDER_PS 2   // renderer, point sources only
+
+template <typename T>
+__device__ __forceinline__ void load_twiddles(cplx<T> *tw_s, const cplx<T> *tw_g, int L,
+                                              int tid, int nthreads) {
+  for (int k = tid; k < L; k += nthreads) tw_s[k] = tw_g[k];
+}
+
+// ------------------------------------------------------------- rows_fwd --
+// grid = (H / RB, B), block = RB * (W / 8)
+// dynamic smem: (RB*W + W) cplx<T> + n_components*STRIDE doubles
+template <typename T, int SRC>
+__global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ prog,
+                                const double *__restrict__ derived,
+                                const double *__restrict__ wscale, int precision,
+                                const double *__restrict__ pad_a,
+                                const double *__restrict__ pad_b,
+                                const cplx<T> *__restrict__ tw_w,
+                                cplx<T> *__restrict__ scratch,
+                                T *__restrict__ raw_out) {
+  PSFMC_DYN_SMEM(smem_raw);
+  const int W = fr.W, H = fr.H, Wc = fr.Wc;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const long long b = blockIdx.y;
+  const int y0 = blockIdx.x * RB;
+  cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
+  cplx<T> *tw_s = tile + RB * W;
+  double *der_s = reinterpret_cast<double *>(tw_s + W);
+
+  load_twiddles<T>(tw_s, tw_w, W, tid, nthreads);
+  int ncomp = 0;
+  if (SRC != PSFMC_SRC_PSFPAD) {
+    ncomp = prog->n_components;
+    const double *der_b = derived + b * ncomp * PSFMC_DERIVED_STRIDE;
+    for (int k = tid; k < ncomp * PSFMC_DERIVED_STRIDE; k += nthreads) der_s[k] = der_b[k];
+    __syncthreads();
+  }
+
+  // ---- fill the tile: z = a + i b  (b = wscale * raw^2 when rendering)
+  const int npx = RB * W;
+  const T wsc = (SRC != PSFMC_SRC_PSFPAD) ? (T)wscale[b] : (T)1;
+  if (SRC == PSFMC_SRC_PSFPAD) {
+    for (int e = tid; e < npx; e += nthreads) {
+      int r = e / W, x = e - r * W;
+      long long g = (b * H + (y0 + r)) * (long long)W + x;
+      tile[e] = mk<T>((T)pad_a[g], (T)pad_b[g]);
+    }
+  } else if (sizeof(T) == 8 || SRC == PSFMC_SRC_RENDER_PS) {
+    const bool round_f32 = (precision == PSFMC_PREC_FP64_RAWF32);
+    for (int e = tid; e < npx; e += nthreads) {
+      int r = e / W, x = e - r * W;
+      double val = raw_pixel_f64(prog, der_s, x, y0 + r, round_f32,
+                                 SRC == PSFMC_SRC_RENDER_PS);
+      T a = (T)val;
+      tile[e] = mk<T>(a, a * a * wsc);
+      if (raw_out) raw_out[(b * H + (y0 + r)) * (long long)W + x] = a;
+    }
+  } else {
+    // float32 throughput path: Sky + Sersic in float, point-source taps in double.
+    // RB*W == 8*nthreads, so every thread owns exactly 8 pixels.
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    for (int c = 0; c < ncomp; ++c) {
+      const double *d = der_s + c * PSFMC_DERIVED_STRIDE;
+      const int kind = prog->kind[c];
+      if (kind == PSFMC_SKY) {
+        const float adu = (float)d[D_SKY_ADU];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += adu;
+      } else if (kind == PSFMC_POINT) {
+        const int flags = prog->flags[c];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int e = tid + i * nthreads;
+          int r = e / W, x = e - r * W;
+          acc[i] += (float)point_pixel(d, flags, x, y0 + r);
+        }
+      } else {
+        const SersicF32 s = make_sersic_f32(d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int e = tid + i * nthreads;
+          int r = e / W, x = e - r * W;
+          acc[i] += sersic_pixel_f32(s, (float)x, (float)(y0 + r));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int e = tid + i * nthreads;
+      int r = e / W, x = e - r * W;
+      tile[e] = mk<T>((T)acc[i], (T)(acc[i] * acc[i]) * wsc);
+      if (raw_out) raw_out[(b * H + (y0 + r)) * (long long)W + x] = (T)acc[i];
+    }
+  }
+  __syncthreads();
+
+  // ---- FFT along x of every row of the tile
+  {
+    const int tpr = W >> 3;  // threads per row
+    const int r = tid / tpr, tl = tid - r * tpr;
+    fft_line_smem<T, false>(tile + r * W, W, fr.logW, tl, tw_s);
+  }
+
+  // ---- split z-spectrum into the spectra of the two real rows and store
+  // A[kx] = (Z[kx] + conj Z[-kx]) / 2,  B[kx] = (Z[kx] - conj Z[-kx]) / (2i)
+  const int nout = RB * 2 * Wc;
+  const T half = (T)0.5;
+  for (int e = tid; e < nout; e += nthreads) {
+    int r = e % RB, c = e / RB;
+    int kx = (c < Wc) ? c : c - Wc;
+    cplx<T> zk = tile[r * W + kx];
+    cplx<T> zm = cconj(tile[r * W + ((W - kx) & (W - 1))]);
+    cplx<T> o;
+    if (c < Wc) {
+      o = mk<T>(half * (zk.x + zm.x), half * (zk.y + zm.y));
+    } else {
+      cplx<T> dlt = zk - zm;                    // (Zk - Zm) / (2i) = -i/2 * dlt
+      o = mk<T>(half * dlt.y, -half * dlt.x);
+    }
+    scratch[(b * (2 * Wc) + c) * (long long)H + (y0 + r)] = o;
+  }
+}
+
+// ----------------------------------------------------------------- cols --
+#define PSFMC_COLS_CONV 0   // forward, multiply by spectrum, inverse (hot path)
+#define PSFMC_COLS_SETUP 1  // forward only, scaled: produces the spectra themselves
+
+// grid = (ceil(2*Wc / CB), B), block = CB * (H / 8); smem (CB*H + H) cplx<T>
+template <typename T, int MODE>
+__global__ void cols_kernel(Frame fr, int CB, const cplx<T> *__restrict__ tw_h,
+                            const cplx<T> *__restrict__ spec,
+                            const int *__restrict__ psf_sel,
+                            cplx<T> *__restrict__ scratch,
+                            cplx<T> *__restrict__ spec_out) {
+  PSFMC_DYN_SMEM(smem_raw);
+  const int H = fr.H, Wc = fr.Wc, ncol = 2 * Wc;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const long long b = blockIdx.y;
+  const int c0 = blockIdx.x * CB;
+  cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
+  cplx<T> *tw_s = tile + CB * H;
+  load_twiddles<T>(tw_s, tw_h, H, tid, nthreads);
+
+  cplx<T> *base = scratch + (b * ncol + c0) * (long long)H;
+  const int nel = CB * H;
+  const int nvalid = (ncol - c0 < CB ? ncol - c0 : CB) * H;
+  for (int e = tid; e < nel; e += nthreads)
+    tile[e] = (e < nvalid) ? base[e] : mk<T>((T)0, (T)0);
+  __syncthreads();
+
+  const int tpc = H >> 3;
+  const int col = tid / tpc, tl = tid - col * tpc;
+  fft_line_smem<T, false>(tile + col * H, H, fr.logH, tl, tw_s);
+
+  if (MODE == PSFMC_COLS_SETUP) {
+    // spec_out[b][c][ky] = F * (-1)^(kx+ky) / (H*W)
+    const T scale = (T)(1.0 / ((double)fr.H * (double)fr.W));
+    cplx<T> *obase = spec_out + (b * ncol + c0) * (long long)H;
+    for (int e = tid; e < nvalid; e += nthreads) {
+      int cc = c0 + e / H, ky = e % H;
+      int kx = cc < Wc ? cc : cc - Wc;
+      T sgn = ((kx + ky) & 1) ? -scale : scale;
+      obase[e] = mk<T>(tile[e].x * sgn, tile[e].y * sgn);
+    }
+    return;
+  }
+
+  int sel = psf_sel[b];
+  if (sel < 0) sel = 0;  // walker is flagged invalid and overwritten in finalize
+  const cplx<T> *sp = spec + ((long long)sel * ncol + c0) * (long long)H;
+  for (int e = tid; e < nvalid; e += nthreads) tile[e] = tile[e] * sp[e];
+  __syncthreads();
+
+  fft_line_smem<T, true>(tile + col * H, H, fr.logH, tl, tw_s);
+
+  for (int e = tid; e < nvalid; e += nthreads) base[e] = tile[e];
+}
+
+// ------------------------------------------------------------- rows_inv --
+template <typename T>
+struct Epilogue;
+
+// float64: the reference's expressions (psfMC/models.py:294, :277-279, :235-236)
+template <>
+struct Epilogue<double> {
+  static __device__ __forceinline__ double term(double conv, double mvar, double obs,
+                                                double ovar, double *resid,
+                                                double *ivm) {
+    *resid = obs - conv;
+    *ivm = 1.0 / (mvar + ovar);
+    return (*resid) * (*resid) * (*ivm) - log(0.5 / PSFMC_PI * (*ivm));
+  }
+};
+// float32 arithmetic, float64 accumulation by the caller
+template <>
+struct Epilogue<float> {
+  static __device__ __forceinline__ double term(float conv, float mvar, float obs,
+                                                float ovar, float *resid, float *ivm) {
+    *resid = obs - conv;
+    float tot = mvar + ovar;
+#ifdef PSFMC_EMU
+    *ivm = 1.0f / tot;
+    float lg = logf(0.15915494309189535f * (*ivm));
+#else
+    *ivm = __frcp_rn(tot);
+    float lg = __logf(0.15915494309189535f * (*ivm));
+#endif
+    return (double)((*resid) * (*resid) * (*ivm) - lg);
+  }
+};
+
+// grid = (H / RB, B), block = RB * (W / 8); smem (RB*W + W) cplx<T> + 32 doubles
+// img_* (optional, may be null): residual / composite IVM / convolved images.
+template <typename T>
+__global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw_w,
+                                const cplx<T> *__restrict__ scratch,
+                                const T *__restrict__ obs, const T *__restrict__ ovar,
+                                const unsigned char *__restrict__ bad,
+                                const double *__restrict__ wscale,
+                                const int *__restrict__ psf_sel,
+                                const double *__restrict__ vscale_inv,
+                                double *__restrict__ partials,
+                                T *__restrict__ img_conv, T *__restrict__ img_resid,
+                                T *__restrict__ img_ivm) {
+  PSFMC_DYN_SMEM(smem_raw);
+  const int W = fr.W, H = fr.H, Wc = fr.Wc;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const long long b = blockIdx.y;
+  const int y0 = blockIdx.x * RB;
+  cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
+  cplx<T> *tw_s = tile + RB * W;
+  double *red_s = reinterpret_cast<double *>(tw_s + W);
+  load_twiddles<T>(tw_s, tw_w, W, tid, nthreads);
+
+  // Y[kx] = A'[kx] + i B'[kx]; Y[W-kx] = conj(A'[kx]) + i conj(B'[kx])
+  const cplx<T> *sa = scratch + b * (2 * Wc) * (long long)H;
+  const cplx<T> *sb = sa + (long long)Wc * H;
+  const int nin = RB * Wc;
+  for (int e = tid; e < nin; e += nthreads) {
+    int r = e % RB, kx = e / RB;
+    cplx<T> a = sa[(long long)kx * H + y0 + r];
+    cplx<T> bb = sb[(long long)kx * H + y0 + r];
+    if (kx > 0 && kx < W - kx) {
+      tile[r * W + kx] = mk<T>(a.x - bb.y, a.y + bb.x);
+      tile[r * W + (W - kx)] = mk<T>(a.x + bb.y, bb.x - a.y);
+    } else {
+      // DC and Nyquist terms of a real row are real: a c2r transform ignores
+      // their imaginary parts (numpy.fft.irfft does the same)
+      tile[r * W + kx] = mk<T>(a.x, bb.x);
+    }
+  }
+  __syncthreads();
+
+  {
+    const int tpr = W >> 3;
+    const int r = tid / tpr, tl = tid - r * tpr;
+    fft_line_smem<T, true>(tile + r * W, W, fr.logW, tl, tw_s);
+  }
+
+  // undo the (exact, power-of-two) channel scalings of the variance image
+  int sel = psf_sel[b];
+  if (sel < 0) sel = 0;
+  const T unscale = (T)(vscale_inv[sel] / wscale[b]);
+  double acc = 0.0;
+  const int npx = RB * W;
+  for (int e = tid; e < npx; e += nthreads) {
+    int r = e / W, x = e - r * W;
+    long long g = (long long)(y0 + r) * W + x;
+    cplx<T> yv = tile[e];
+    yv.y *= unscale;
+    T resid, ivm;
+    double t = Epilogue<T>::term(yv.x, yv.y, obs[g], ovar[g], &resid, &ivm);
+    if (!bad[g]) acc += t;
+    if (img_conv) img_conv[b * (long long)H * W + g] = yv.x;
+    if (img_resid) img_resid[b * (long long)H * W + g] = resid;
+    if (img_ivm) img_ivm[b * (long long)H * W + g] = ivm;
+  }
+  // block reduction in float64: warp shuffles, then one value per warp via smem
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  const int warp = tid >> 5, lane = tid & 31, nwarps = (nthreads + 31) >> 5;
+  if (lane == 0) red_s[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < nwarps; ++w) tot += red_s[w];
+    partials[b * gridDim.x + blockIdx.x] = tot;
+  }
+}
+
+// one thread per walker: lnL = -0.5 * sum(partials); non-finite => -inf
+// (psfMC/models.py:235-241); invalid PSF index => -inf.
+__global__ void finalize_kernel(const double *__restrict__ partials, int nblk,
+                                const int *__restrict__ psf_sel, long long n_batch,
+                                double *__restrict__ lnl) {
+  long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_batch) return;
+  double tot = 0.0;
+  for (int k = 0; k < nblk; ++k) tot += partials[b * nblk + k];
+  double v = -0.5 * tot;
+  if (!isfinite(v) || psf_sel[b] < 0) v = -INFINITY;
+  lnl[b] = v;
+}
+
+}  // namespace psfmc

@@ -1,0 +1,202 @@
+// Launch plan + launch sequence of the staged path. Shared by the engine
+// (engine.cu, real CUDA launches) and by the CPU emulator harness used in the
+// non-GPU test tier (tests/emu/, -DPSFMC_EMU), so that what is tested locally is
+// the launch sequence that runs on the B200.
+#pragma once
+#include <utility>
+
+#include "kernels_staged.cuh"
+
+namespace psfmc {
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                          cudaStream_t stream, Args &&...args) {
+#ifdef PSFMC_EMU
+  (void)stream;
+  emu::launch(grid, block, smem, [&] { kernel(args...); });
+#else
+  kernel<<<grid, block, smem, stream>>>(std::forward<Args>(args)...);
+#endif
+}
+
+inline int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+struct StagedPlan {
+  Frame fr;
+  int RB, CB;               // rows / columns per CTA
+  int n_rowblk, n_colblk;   // CTAs per walker in the row / column kernels
+  int threads_rows, threads_cols;
+  size_t smem_rows, smem_cols;
+  size_t scratch_elems_per_walker;  // complex elements
+  long long chunk;          // walkers whose scratch is in flight at once
+};
+
+inline bool frame_supported(int H, int W) {
+  auto ok = [](int v) { return v >= 16 && v <= 1024 && (v & (v - 1)) == 0; };
+  return ok(H) && ok(W);
+}
+
+inline StagedPlan make_staged_plan(int H, int W, int n_components, size_t sizeof_real,
+                                   double chunk_mbytes) {
+  StagedPlan p;
+  p.fr.H = H;
+  p.fr.W = W;
+  p.fr.Wc = W / 2 + 1;
+  p.fr.logH = ilog2(H);
+  p.fr.logW = ilog2(W);
+  int rb = 2048 / W;
+  if (rb < 1) rb = 1;
+  if (rb > H) rb = H;
+  p.RB = rb;
+  p.n_rowblk = H / rb;
+  p.threads_rows = rb * (W / 8);
+  // columns per CTA: at most 2048/H, chosen to minimise padding of the 2*Wc columns
+  int ncol = 2 * p.fr.Wc;
+  int cbmax = 2048 / H;
+  if (cbmax < 1) cbmax = 1;
+  int best = cbmax, best_waste = 1 << 30;
+  for (int cb = cbmax; cb >= (cbmax + 1) / 2 && cb >= 1; --cb) {
+    int waste = ((ncol + cb - 1) / cb) * cb - ncol;
+    if (waste < best_waste) {
+      best_waste = waste;
+      best = cb;
+    }
+  }
+  p.CB = best;
+  p.n_colblk = (ncol + best - 1) / best;
+  p.threads_cols = best * (H / 8);
+  size_t csz = 2 * sizeof_real;
+  p.smem_rows = (size_t)(rb * W + W) * csz +
+                (size_t)(n_components * PSFMC_DERIVED_STRIDE + 64) * sizeof(double);
+  p.smem_cols = (size_t)(best * H + H) * csz;
+  p.scratch_elems_per_walker = (size_t)ncol * H;
+  double per_walker = (double)p.scratch_elems_per_walker * csz;
+  long long chunk = (long long)(chunk_mbytes * 1048576.0 / per_walker);
+  if (chunk < 1) chunk = 1;
+  p.chunk = chunk;
+  return p;
+}
+
+// Device-resident state the launch sequence needs (one per device per precision).
+template <typename T>
+struct StagedBuffers {
+  const Program *prog;
+  const cplx<T> *tw_w, *tw_h;
+  const cplx<T> *spec;        // [K][2*Wc][H]
+  const T *obs, *ovar;        // [H*W]
+  const unsigned char *bad;   // [H*W]
+  double *derived;            // [B][ncomp][STRIDE]
+  int *psf_sel;               // [B]
+  double *wscale;             // [B] per-walker packing scale
+  const double *vscale_inv;   // [K] inverse of the scale folded into the V spectra
+  cplx<T> *scratch;           // [chunk][2*Wc][H]
+  double *partials;           // [B][n_rowblk]
+};
+
+// Optional image outputs of one chunk (null = not wanted), [chunk][H*W] each.
+template <typename T>
+struct ImageOutputs {
+  T *raw = nullptr, *conv = nullptr, *resid = nullptr, *ivm = nullptr;
+};
+
+template <typename T>
+inline int count_launches(const StagedPlan &plan, long long n_batch) {
+  long long nchunks = (n_batch + plan.chunk - 1) / plan.chunk;
+  return (int)(2 + 3 * nchunks);
+}
+
+// theta, lnl: device pointers. n_components: host copy of prog->n_components.
+// ps_only renders only the point sources (for the point-source-subtracted image).
+template <typename T>
+inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> &buf,
+                                 int n_components, int precision, const double *theta,
+                                 long long n_batch, long long ld, double *lnl,
+                                 cudaStream_t stream, bool ps_only = false,
+                                 const ImageOutputs<T> *images = nullptr,
+                                 long long images_chunk_offset = -1) {
+  if (n_batch <= 0) return;
+  const Frame fr = plan.fr;
+  {
+    long long nthreads = n_batch * n_components;
+    int block = 128;
+    unsigned grid = (unsigned)((nthreads + block - 1) / block);
+    launch_kernel(prepare_kernel, dim3(grid), dim3(block), 0, stream, buf.prog, theta,
+                  n_batch, ld, fr.H, fr.W, buf.derived, buf.psf_sel, buf.wscale);
+  }
+  for (long long start = 0; start < n_batch; start += plan.chunk) {
+    long long nb = n_batch - start < plan.chunk ? n_batch - start : plan.chunk;
+    const double *der = buf.derived + start * n_components * PSFMC_DERIVED_STRIDE;
+    ImageOutputs<T> img;
+    if (images && (images_chunk_offset < 0 || images_chunk_offset == start)) img = *images;
+    dim3 grid_rows(plan.n_rowblk, (unsigned)nb), grid_cols(plan.n_colblk, (unsigned)nb);
+    if (ps_only)
+      launch_kernel(rows_fwd_kernel<T, PSFMC_SRC_RENDER_PS>, grid_rows,
+                    dim3(plan.threads_rows), plan.smem_rows, stream, fr, plan.RB, buf.prog,
+                    der, (const double *)(buf.wscale + start), precision,
+                    (const double *)nullptr, (const double *)nullptr, buf.tw_w, buf.scratch,
+                    img.raw);
+    else
+      launch_kernel(rows_fwd_kernel<T, PSFMC_SRC_RENDER>, grid_rows,
+                    dim3(plan.threads_rows), plan.smem_rows, stream, fr, plan.RB, buf.prog,
+                    der, (const double *)(buf.wscale + start), precision,
+                    (const double *)nullptr, (const double *)nullptr, buf.tw_w, buf.scratch,
+                    img.raw);
+    launch_kernel(cols_kernel<T, PSFMC_COLS_CONV>, grid_cols, dim3(plan.threads_cols),
+                  plan.smem_cols, stream, fr, plan.CB, buf.tw_h, buf.spec,
+                  (const int *)(buf.psf_sel + start), buf.scratch, (cplx<T> *)nullptr);
+    launch_kernel(rows_inv_kernel<T>, grid_rows, dim3(plan.threads_rows), plan.smem_rows,
+                  stream, fr, plan.RB, buf.tw_w, (const cplx<T> *)buf.scratch, buf.obs,
+                  buf.ovar, buf.bad, (const double *)(buf.wscale + start),
+                  (const int *)(buf.psf_sel + start), buf.vscale_inv,
+                  buf.partials + start * plan.n_rowblk, img.conv, img.resid, img.ivm);
+  }
+  {
+    int block = 128;
+    unsigned grid = (unsigned)((n_batch + block - 1) / block);
+    launch_kernel(finalize_kernel, dim3(grid), dim3(block), 0, stream,
+                  (const double *)buf.partials, plan.n_rowblk, (const int *)buf.psf_sel,
+                  n_batch, lnl);
+  }
+}
+
+// Setup: spectra of the K padded PSF / variance frames, always float64.
+//   pad_psf, pad_var: [K][H][W] doubles on the device; spec_out: [K][2*Wc][H]
+inline void launch_staged_setup(const StagedPlan &plan, const cplx<double> *tw_w,
+                                const cplx<double> *tw_h, const double *pad_psf,
+                                const double *pad_var, int n_psf,
+                                cplx<double> *scratch, cplx<double> *spec_out,
+                                cudaStream_t stream) {
+  const Frame fr = plan.fr;
+  dim3 grid_rows(plan.n_rowblk, n_psf), grid_cols(plan.n_colblk, n_psf);
+  launch_kernel(rows_fwd_kernel<double, PSFMC_SRC_PSFPAD>, grid_rows,
+                dim3(plan.threads_rows), plan.smem_rows, stream, fr, plan.RB,
+                (const Program *)nullptr, (const double *)nullptr, (const double *)nullptr, 0,
+                pad_psf, pad_var, tw_w, scratch, (double *)nullptr);
+  launch_kernel(cols_kernel<double, PSFMC_COLS_SETUP>, grid_cols, dim3(plan.threads_cols),
+                plan.smem_cols, stream, fr, plan.CB, tw_h, (const cplx<double> *)nullptr,
+                (const int *)nullptr, scratch, spec_out);
+}
+
+// exp(-2 pi i k / L), k = 0..L-1, computed in long double on the host.
+template <typename T>
+inline void fill_twiddles(cplx<T> *tw, int L) {
+  for (int k = 0; k < L; ++k) {
+    long double ang = -2.0L * 3.14159265358979323846264338327950288L * k / L;
+    tw[k].x = (T)cosl(ang);
+    tw[k].y = (T)sinl(ang);
+  }
+  // exact values at the quadrant points
+  tw[0].x = (T)1; tw[0].y = (T)0;
+  if (L >= 4) {
+    tw[L / 4].x = (T)0; tw[L / 4].y = (T)-1;
+    tw[L / 2].x = (T)-1; tw[L / 2].y = (T)0;
+    tw[3 * L / 4].x = (T)0; tw[3 * L / 4].y = (T)1;
+  }
+}
+
+}  // namespace psfmc

@@ -1,0 +1,195 @@
+"""
+LikelihoodEngine: the Python face of the C ABI (include/psfmc_b200.h).
+
+It takes exactly the constants the reference's Configuration + PSFSelector prepare
+once per model (/root/reference/psfMC/ModelComponents/Configuration.py:38-52,
+PSFSelector.py:16-43) plus the component program, and evaluates the lnL part of
+MultiComponentModel.log_posterior (/root/reference/psfMC/models.py:213-241) for a
+whole batch of parameter vectors per call on the GPU(s).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+KIND_CODES = {'sky': _lib.SKY, 'point': _lib.POINT, 'sersic': _lib.SERSIC}
+SLOT_INDEX = {
+    'sky': {'adu': _lib.P_ADU},
+    'point': {'x': _lib.P_X, 'y': _lib.P_Y, 'mag': _lib.P_MAG},
+    'sersic': {'x': _lib.P_X, 'y': _lib.P_Y, 'mag': _lib.P_MAG,
+               'reff': _lib.P_REFF, 'reff_b': _lib.P_REFF_B,
+               'index': _lib.P_INDEX, 'angle': _lib.P_ANGLE},
+}
+
+
+def _fill_slot(slot, spec):
+    where, value = spec
+    if where == 'theta':
+        slot.theta_index = int(value)
+        slot.value = 0.0
+    elif where == 'const':
+        slot.theta_index = -1
+        slot.value = float(value)
+    else:
+        raise ValueError('slot must be ("theta", index) or ("const", value)')
+
+
+class LikelihoodEngine(object):
+    """
+    :param obs_data, obs_var, bad_px: (H, W) arrays; ``obs_var`` is 1/ivm with
+        +inf at data-bad pixels, ``bad_px`` nonzero where a pixel is excluded
+    :param psfs, psf_vars: sequences of K normalised PSF images / variance maps
+        (all the same shape, not larger than the observation)
+    :param mag_zeropoint: magnitude zeropoint
+    :param program: list of ``(kind, flags, slots)`` with kind in
+        {'sky','point','sersic'}, flags a dict (``angle_degrees``,
+        ``shift_method``), slots a dict name -> ('theta', i) | ('const', v)
+    :param psf_index_slot: slot of the PSF index (('const', 0) for one PSF)
+    :param precision: 'fp32' (float32 render/FFT, float64 accumulation; default),
+        'fp64' (everything float64) or 'fp64_rawf32'
+    :param devices: CUDA ordinals to shard batches over (default: current device)
+    """
+
+    def __init__(self, obs_data, obs_var, bad_px, psfs, psf_vars, mag_zeropoint,
+                 program, psf_index_slot=('const', 0), precision='fp32',
+                 devices=None, max_batch=0, library=None):
+        self._lib = _lib.load(library)
+        self._handle = ctypes.c_void_p()
+        obs = np.ascontiguousarray(obs_data, dtype=np.float64)
+        var = np.ascontiguousarray(obs_var, dtype=np.float64)
+        bad = np.ascontiguousarray(np.asarray(bad_px) != 0, dtype=np.uint8)
+        if obs.ndim != 2 or var.shape != obs.shape or bad.shape != obs.shape:
+            raise ValueError('obs_data, obs_var and bad_px must share a 2-D shape')
+        psf = np.ascontiguousarray(np.stack([np.asarray(p, dtype=np.float64)
+                                             for p in psfs]))
+        pvar = np.ascontiguousarray(np.stack([np.asarray(p, dtype=np.float64)
+                                              for p in psf_vars]))
+        if psf.shape != pvar.shape or psf.ndim != 3:
+            raise ValueError('psfs and psf_vars must be K images of one shape')
+        if len(program) > _lib.MAX_COMPONENTS:
+            raise ValueError('too many components')
+        comps = (_lib.Component * max(1, len(program)))()
+        n_theta = 0
+        for num, (kind, flags, slots) in enumerate(program):
+            comp = comps[num]
+            comp.kind = KIND_CODES[kind]
+            comp.flags = 0
+            if flags.get('angle_degrees'):
+                comp.flags |= _lib.FLAG_ANGLE_DEGREES
+            method = flags.get('shift_method', 'lanczos3')
+            if kind == 'point':
+                if method == 'bilinear':
+                    comp.flags |= _lib.FLAG_BILINEAR
+                elif method != 'lanczos3':
+                    raise ValueError('Unknown shift method: {}'.format(method))
+            for sidx in range(_lib.NSLOTS):
+                comp.slot[sidx].theta_index = -1
+            for name, sidx in SLOT_INDEX[kind].items():
+                _fill_slot(comp.slot[sidx], slots[name])
+                if slots[name][0] == 'theta':
+                    n_theta = max(n_theta, int(slots[name][1]) + 1)
+        desc = _lib.Desc()
+        desc.abi_version = _lib.ABI_VERSION
+        desc.height, desc.width = obs.shape
+        dbl_p = ctypes.POINTER(ctypes.c_double)
+        desc.obs_data = obs.ctypes.data_as(dbl_p)
+        desc.obs_var = var.ctypes.data_as(dbl_p)
+        desc.bad_px = bad.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+        desc.n_psf, desc.psf_height, desc.psf_width = psf.shape
+        desc.psf = psf.ctypes.data_as(dbl_p)
+        desc.psf_var = pvar.ctypes.data_as(dbl_p)
+        desc.mag_zeropoint = float(mag_zeropoint)
+        desc.n_components = len(program)
+        desc.components = comps
+        _fill_slot(desc.psf_index, psf_index_slot)
+        if psf_index_slot[0] == 'theta':
+            n_theta = max(n_theta, int(psf_index_slot[1]) + 1)
+        desc.precision = _lib.PRECISIONS[precision]
+        devs = None
+        if devices is not None:
+            devs = (ctypes.c_int32 * len(devices))(*[int(d) for d in devices])
+            desc.n_devices = len(devices)
+            desc.devices = devs
+        desc.max_batch = int(max_batch)
+        _lib.check(self._lib, self._lib.psfmc_engine_create(
+            ctypes.byref(desc), ctypes.byref(self._handle)))
+        self.shape = obs.shape
+        self.num_params = n_theta
+        self.precision = precision
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, '_handle', None) is not None and self._handle.value:
+            self._lib.psfmc_engine_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- hot path -----------------------------------------------------------
+    def lnlike(self, thetas, out=None):
+        """lnL for each row of ``thetas`` (B, D); -inf for non-finite results."""
+        thetas = np.ascontiguousarray(np.atleast_2d(thetas), dtype=np.float64)
+        n_batch, ld = thetas.shape
+        if ld < self.num_params:
+            raise ValueError('theta has {} columns, the program needs {}'.format(
+                ld, self.num_params))
+        if out is None:
+            out = np.empty(n_batch, dtype=np.float64)
+        dbl_p = ctypes.POINTER(ctypes.c_double)
+        _lib.check(self._lib, self._lib.psfmc_lnlike_batch(
+            self._handle, thetas.ctypes.data_as(dbl_p), n_batch, ld,
+            out.ctypes.data_as(dbl_p)))
+        return out
+
+    def lnlike_device(self, theta_ptr, n_batch, ld, lnl_ptr, stream=0,
+                      device_slot=0):
+        """Asynchronous evaluation on device-resident buffers (raw addresses,
+        e.g. ``tensor.data_ptr()``), enqueued on CUDA stream ``stream``."""
+        _lib.check(self._lib, self._lib.psfmc_lnlike_batch_device(
+            self._handle, device_slot, ctypes.c_void_p(theta_ptr), n_batch, ld,
+            ctypes.c_void_p(lnl_ptr), ctypes.c_void_p(stream)))
+
+    def render(self, thetas, which=('raw_model', 'convolved_model', 'residual',
+                                    'composite_ivm', 'point_source_subtracted')):
+        """Blob images (psfMC/models.py:222-226) as dict name -> (B, H, W)."""
+        thetas = np.ascontiguousarray(np.atleast_2d(thetas), dtype=np.float64)
+        n_batch, ld = thetas.shape
+        bits = 0
+        for name in which:
+            bits |= _lib.IMAGE_BITS[name]
+        ordered = [name for name, bit in sorted(_lib.IMAGE_BITS.items(),
+                                                key=lambda kv: kv[1])
+                   if bits & bit]
+        out = np.empty((len(ordered), n_batch) + tuple(self.shape), dtype=np.float64)
+        dbl_p = ctypes.POINTER(ctypes.c_double)
+        _lib.check(self._lib, self._lib.psfmc_render_batch(
+            self._handle, thetas.ctypes.data_as(dbl_p), n_batch, ld, bits,
+            out.ctypes.data_as(dbl_p)))
+        return {name: out[num] for num, name in enumerate(ordered)}
+
+    def info(self):
+        info = _lib.Info()
+        _lib.check(self._lib, self._lib.psfmc_engine_info(self._handle,
+                                                          ctypes.byref(info)))
+        return {name: getattr(info, name) for name, _ in _lib.Info._fields_}
+
+
+def fp32_peak_tflops(device=0, library=None):
+    """Measured FP32 FMA throughput of one device (TFLOP/s), the FP32 roofline
+    denominator."""
+    lib = _lib.load(library)
+    tflops, ms = ctypes.c_double(), ctypes.c_double()
+    _lib.check(lib, lib.psfmc_fp32_peak_probe(device, ctypes.byref(tflops),
+                                              ctypes.byref(ms)))
+    return tflops.value

@@ -1,0 +1,231 @@
+"""
+MultiComponentModel: the host-side model object with the reference's interface
+(/root/reference/psfMC/models.py:9-306), backed by the CUDA engine.
+
+``log_posterior(theta, model=...)`` keeps the reference's static signature and
+return value ``(lnL + lnprior, blobs)`` so it can still be handed to emcee as is;
+the fast path is :meth:`log_posterior_batch`, which :class:`psfmc_b200.pool.BatchPool`
+calls once per emcee ``map`` with the whole (half-)ensemble.
+"""
+import numpy as np
+
+from .components import Configuration, PointSource
+from .engine import LikelihoodEngine
+from .model_parser import component_list_from_file
+from .program import compile_program
+
+IMAGE_TYPES = ('raw_model', 'convolved_model', 'residual', 'composite_ivm',
+               'point_source_subtracted')
+
+
+class MultiComponentModel(object):
+    """
+    :param components: list of components (one Configuration among them) or the
+        name of a model file
+    :param precision: engine precision ('fp32' default, 'fp64', 'fp64_rawf32')
+    :param devices: CUDA ordinals to shard walker batches over
+    :param with_blobs: if True, ``log_posterior`` returns the five images per
+        evaluation like the reference (slow: they travel to the host); the default
+        returns empty blobs and posterior images are re-rendered from the chain
+    """
+
+    def __init__(self, components, precision='fp32', devices=None,
+                 with_blobs=False, library=None):
+        if isinstance(components, str):
+            components = component_list_from_file(components)
+        components = list(components)
+        configs = [comp for comp in components
+                   if isinstance(comp, Configuration)
+                   or type(comp).__name__ == 'Configuration']
+        if not configs:
+            raise ValueError('Unable to find the Configuration component, required '
+                             'for setting up input images.')
+        config = configs[-1]
+        components.remove(config)
+        components.append(config.psf_selector)      # PSF selector goes last
+        for count, comp in enumerate(components):
+            comp.update_stochastic_names(count=count)
+
+        self.config = config
+        self.components = components
+        self.psf_comps = [comp for comp in components
+                          if isinstance(comp, PointSource)]
+        self.obs_header = config.obs_header
+        self.with_blobs = with_blobs
+        self.precision = precision
+
+        self.program, self.psf_index_slot, self._num_params = \
+            compile_program(components)
+        selector = config.psf_selector
+        self.engine = LikelihoodEngine(
+            config.obs_data, config.obs_var, config.bad_px,
+            selector.psf_images, selector.var_images, config.mag_zeropoint,
+            self.program, self.psf_index_slot, precision=precision,
+            devices=devices, library=library)
+
+        self._param_vector = np.zeros(self.num_params)
+        self.posterior_images = {}
+        self.accumulated_samples = 0
+        self.reset_images()
+
+    # -- parameter bookkeeping -------------------------------------------------
+    @property
+    def num_params(self):
+        return int(self._num_params)
+
+    @property
+    def param_names(self):
+        return [name for comp in self.components for name in comp.stochastic_names()]
+
+    @property
+    def param_fits_abbrs(self):
+        return [name for comp in self.components
+                for name in comp.stochastic_names(name_attr='fitsname')]
+
+    @property
+    def param_lens(self):
+        return [length for comp in self.components for length in comp.stochastic_lens()]
+
+    @property
+    def param_values(self):
+        splits = np.cumsum(self.param_lens)[:-1]
+        return dict(zip(self.param_names, np.split(self._param_vector, splits)))
+
+    @param_values.setter
+    def param_values(self, value_vector):
+        value_vector = np.asarray(value_vector, dtype=np.float64)
+        self._param_vector = value_vector
+        start = 0
+        for comp in self.components:
+            count = comp.num_stochastics()
+            comp.set_stochastic_values(value_vector[start:start + count])
+            start += count
+
+    def get_distribution(self, param_name):
+        for comp in self.components:
+            try:
+                return comp.get_distribution(param_name)
+            except KeyError:
+                continue
+        return None
+
+    def init_params_from_priors(self, nwalkers):
+        """Starting positions drawn from the priors, redrawing per component until
+        its joint prior is finite (cf. models.py:108-130)."""
+        start_positions = np.zeros((nwalkers, self.num_params))
+        for walker in range(nwalkers):
+            pieces = []
+            for comp in self.components:
+                while True:
+                    values = comp.set_stochastic_values('random')
+                    if np.isfinite(comp.log_priors()):
+                        break
+                pieces.append(np.asarray(values, dtype=np.float64))
+            start_positions[walker] = np.concatenate(pieces) if pieces else []
+        return start_positions
+
+    # -- priors ------------------------------------------------------------------
+    def log_priors(self):
+        return np.sum([comp.log_priors() for comp in self.components])
+
+    def log_priors_batch(self, thetas):
+        """Joint log-prior of every row of ``thetas`` (B, D)."""
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        total = np.zeros(thetas.shape[0])
+        start = 0
+        for comp in self.components:
+            count = comp.num_stochastics()
+            if count or hasattr(comp, 'log_priors_batch'):
+                total = total + comp.log_priors_batch(thetas[:, start:start + count])
+            start += count
+        return total
+
+    # -- posterior ---------------------------------------------------------------
+    def log_likelihood_batch(self, thetas):
+        return self.engine.lnlike(thetas)
+
+    def log_posterior_batch(self, thetas):
+        """
+        lnL + lnprior for every row. Rows whose prior is not finite get -inf and
+        are not sent to the GPU (cf. models.py:209-211).
+        """
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        lnprior = self.log_priors_batch(thetas)
+        lnpost = np.full(thetas.shape[0], -np.inf)
+        alive = np.isfinite(lnprior)
+        if alive.any():
+            lnl = self.engine.lnlike(thetas[alive])
+            lnpost[alive] = np.where(np.isfinite(lnl), lnl + lnprior[alive], -np.inf)
+        return lnpost
+
+    @staticmethod
+    def log_posterior(param_values, **kwargs):
+        """emcee-compatible single evaluation: ``(lnpost, blobs)``
+        (cf. models.py:193-243)."""
+        model = kwargs.pop('model')
+        theta = np.asarray(param_values, dtype=np.float64)
+        lnpost = float(model.log_posterior_batch(theta[None, :])[0])
+        if not model.with_blobs:
+            return lnpost, {}
+        if not np.isfinite(model.log_priors_batch(theta[None, :])[0]):
+            return -np.inf, {}
+        return lnpost, model.sample_images(theta)
+
+    # -- images ------------------------------------------------------------------
+    def sample_images(self, theta=None, which=IMAGE_TYPES):
+        theta = self._param_vector if theta is None else theta
+        imgs = self.engine.render(np.asarray(theta, dtype=np.float64)[None, :], which)
+        return {name: arr[0] for name, arr in imgs.items()}
+
+    def raw_model(self):
+        return self.sample_images(which=('raw_model',))['raw_model']
+
+    def convolved_model(self, raw_px=None):
+        return self.sample_images(which=('convolved_model',))['convolved_model']
+
+    def composite_ivm(self, raw_px=None):
+        return self.sample_images(which=('composite_ivm',))['composite_ivm']
+
+    def residual(self, convolved_px=None, raw_px=None):
+        return self.sample_images(which=('residual',))['residual']
+
+    def point_source_subtracted(self):
+        return self.sample_images(
+            which=('point_source_subtracted',))['point_source_subtracted']
+
+    def reset_images(self):
+        shape = self.config.obs_data.shape
+        self.accumulated_samples = 0
+        for img_type in IMAGE_TYPES:
+            # ones, not zeros: the IVM image is averaged in variance space and
+            # 1/0 * 0 would poison it (weight of the initial value is 0 anyway)
+            self.posterior_images[img_type] = np.ones(shape, dtype=np.float64)
+
+    def accumulate_images(self, sample_images):
+        """Running per-pixel mean over samples; the composite IVM is averaged as a
+        variance (cf. models.py:74-97). ``sample_images``: list of blob dicts."""
+        with np.errstate(divide='ignore'):
+            self.posterior_images['composite_ivm'] = \
+                1 / self.posterior_images['composite_ivm']
+            for img_dict in sample_images:
+                self.accumulated_samples += 1
+                count = self.accumulated_samples
+                for img_type, img in img_dict.items():
+                    if img_type == 'composite_ivm':
+                        img = 1 / img
+                    mean = self.posterior_images[img_type]
+                    mean *= count - 1
+                    mean += img
+                    mean /= count
+            self.posterior_images['composite_ivm'] = \
+                1 / self.posterior_images['composite_ivm']
+
+    def accumulate_from_chain(self, thetas, which=IMAGE_TYPES, batch=64):
+        """Render every row of ``thetas`` on the GPU and fold the images into the
+        running means (the reference's re-render path, analysis/images.py:74-83)."""
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        for start in range(0, thetas.shape[0], batch):
+            imgs = self.engine.render(thetas[start:start + batch], which)
+            nrows = min(batch, thetas.shape[0] - start)
+            self.accumulate_images([{name: imgs[name][row] for name in imgs}
+                                    for row in range(nrows)])

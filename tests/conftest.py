@@ -1,0 +1,152 @@
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+EMU_DIR = os.path.join(ROOT, 'tests', 'emu')
+EMU_LIB = os.path.join(EMU_DIR, 'libpsfmc_emu.so')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a real B200 (run with -m gpu)')
+
+
+def load_golden(name):
+    with open(os.path.join(GOLDEN, name)) as fobj:
+        return json.load(fobj)
+
+
+def _emu_sources():
+    csrc = os.path.join(ROOT, 'psfmc_b200', 'csrc')
+    files = [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    files += [os.path.join(EMU_DIR, 'cuda_emu.h'),
+              os.path.join(ROOT, 'include', 'psfmc_b200.h')]
+    return files
+
+
+@pytest.fixture(scope='session')
+def emu_library():
+    """Build (if stale) the CPU-emulated copy of the CUDA kernel sources: the same
+    .cu/.cuh files compiled by g++ against tests/emu/cuda_emu.h. Test tool only."""
+    stale = not os.path.exists(EMU_LIB) or any(
+        os.path.getmtime(src) > os.path.getmtime(EMU_LIB) for src in _emu_sources())
+    if stale:
+        cmd = ['g++', '-O2', '-g', '-std=c++17', '-DPSFMC_EMU', '-x', 'c++',
+               '-I', EMU_DIR, '-shared', '-fPIC',
+               os.path.join(ROOT, 'psfmc_b200', 'csrc', 'engine.cu'), '-o', EMU_LIB]
+        subprocess.run(cmd, check=True)
+    return EMU_LIB
+
+
+@pytest.fixture(scope='session')
+def cuda_library():
+    """The real library; GPU tests fail loudly if it cannot be built/loaded."""
+    import __graft_entry__ as entry
+    return entry.build()
+
+
+def j0005_arrays(dtype=np.float64, two_psf=False):
+    """Raw inputs of the C1 fixture as arrays of the requested dtype."""
+    from psfmc_b200 import fitsio, preprocess
+    jdir = os.path.join(GOLDEN, 'j0005')
+    obs = fitsio.getdata(os.path.join(jdir, 'sci_J0005-0006.fits')).astype(dtype)
+    ivm = fitsio.getdata(os.path.join(jdir, 'ivm_J0005-0006.fits')).astype(dtype)
+    mask = preprocess.mask_from_file(os.path.join(jdir, 'mask_J0005-0006.reg'),
+                                     obs.shape)
+    psfs = [os.path.join(jdir, 'sci_psf.fits')]
+    ivms = [os.path.join(jdir, 'ivm_psf.fits')]
+    if two_psf:
+        psfs.append(os.path.join(jdir, 'sci_psf_b.fits'))
+        ivms.append(os.path.join(jdir, 'ivm_psf_b.fits'))
+    return obs, ivm, mask, psfs, ivms
+
+
+def model_from_file(model_file, precision, library=None, obs_dtype=None,
+                    two_psf=False, **kwargs):
+    """MultiComponentModel for a golden model file. obs_dtype=np.float64 re-creates
+    the Configuration from float64 arrays (oracle mode M3)."""
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.components import Configuration
+    from psfmc_b200.model_parser import component_list_from_file
+    path = os.path.join(GOLDEN, model_file)
+    comps = component_list_from_file(path)
+    if obs_dtype is not None:
+        old = [c for c in comps if isinstance(c, Configuration)][0]
+        from psfmc_b200 import fitsio
+        mdir = os.path.dirname(path)
+        comps = [c for c in comps if c is not old]
+        if 'j0005' in model_file:
+            obs, ivm, mask, psfs, ivms = j0005_arrays(obs_dtype, two_psf)
+        else:
+            # galfit models: files named inside the model file
+            import re
+            text = open(path).read()
+            obs_name = re.search(r"obs_file='([^']+)'", text).group(1)
+            obs = fitsio.getdata(os.path.join(mdir, obs_name)).astype(obs_dtype)
+            ivm = fitsio.getdata(os.path.join(mdir, 'ivm_const.fits')).astype(obs_dtype)
+            mask = None
+            psfs = [os.path.join(mdir, 'psf_delta.fits')]
+            ivms = [os.path.join(mdir, 'psfivm_delta.fits')]
+        config = Configuration(obs, ivm, psfs, ivms, mask_file=mask,
+                               mag_zeropoint=old.mag_zeropoint)
+        comps = [config] + comps
+    return MultiComponentModel(comps, precision=precision, library=library, **kwargs)
+
+
+def oracle_from_model(model, fft_upcast=True):
+    """Oracle over exactly the arrays and program the engine was given."""
+    from oracle import psfmc_oracle as orc
+    cfg = model.config
+    return orc.OracleModel(cfg.obs_data, cfg.obs_var, cfg.bad_px,
+                           cfg.psf_selector.psf_images, cfg.psf_selector.var_images,
+                           cfg.mag_zeropoint, model.program, model.psf_index_slot,
+                           fft_upcast=fft_upcast)
+
+
+# Stated tolerance of the float32-render / float64-accumulate mode:
+#   |dlnL| <= FP32_ATOL + FP32_ULPS * 2^-24 * sum_good |resid| * ivm * |model|
+# i.e. the first-order effect on chi-square of a relative model error of FP32_ULPS
+# float32 ulps; it scales with the signal-to-noise of the data, as it must.
+FP32_ATOL = 0.01
+FP32_ULPS = 32.0
+FP64_RTOL = 1.0e-10
+
+
+def fp32_bounds(model, thetas, oracle=None):
+    """Per-theta |dlnL| bound of the float32 mode, from the oracle's images."""
+    oracle = oracle or oracle_from_model(model)
+    good = ~np.asarray(model.config.bad_px, dtype=bool)
+    out = []
+    for theta in np.atleast_2d(thetas):
+        imgs = oracle.images(theta, with_point_source_subtracted=False)
+        with np.errstate(all='ignore'):
+            sens = np.sum(np.abs(imgs['residual'][good]) * imgs['composite_ivm'][good]
+                          * np.abs(imgs['convolved_model'][good]))
+        out.append(FP32_ATOL + FP32_ULPS * 2.0 ** -24 * sens)
+    return np.array(out)
+
+
+def assert_lnl_close(got, expect, precision, bounds=None):
+    """fp64*: FP64_RTOL relative. fp32: the per-theta ``bounds`` of fp32_bounds."""
+    got, expect = np.asarray(got), np.asarray(expect)
+    finite = np.isfinite(expect)
+    assert np.array_equal(np.isfinite(got), finite), (got, expect)
+    assert np.all(got[~finite] == -np.inf)
+    if not finite.any():
+        return
+    err = np.abs(got[finite] - expect[finite])
+    if precision == 'fp32':
+        assert bounds is not None, 'fp32 comparisons need fp32_bounds(...)'
+        bound = np.asarray(bounds)[finite]
+    else:
+        bound = FP64_RTOL * np.abs(expect[finite])
+    worst = np.argmax(err / bound)
+    assert np.all(err <= bound), 'worst |dlnL| {} (bound {}) at lnL {}'.format(
+        err[worst], bound[worst], expect[finite][worst])

@@ -229,7 +229,7 @@ def main():
         'F_edge_ur': [0.0, 21.0, 126.5, 127.4, 30, 0.3, 22.5, 6.0, 4.0, 64.8,
                       63.9, 120, 9.7, 24.5, 4.0, 3.0, 46.2, 85.4],
         'G_half_int': [0.002, 20.5, 64.5, 63.5, 45, 1.0, 21.0, 5.0, 5.0, 64.25,
-                       64.75, 0, 0.5, 25.5, 2.0, 2.0, 44.0, 88.0],
+                       64.75, 0, 0.5, 25.5, 2.0, 2.0, 44.3, 88.0],
         # exactly on an integer position: sinc(0) branch of the Lanczos kernel
         'H_integer_ps': [0.0, 21.5, 64.0, 65.0, 200, 2.0, 22.0, 8.0, 3.0, 66.3,
                          62.2, -30, 5.0, 24.0, 7.9, 2.1, 41.0, 90.5],

@@ -1,0 +1,210 @@
+"""
+Parity tests proper: the CUDA path on a real B200, called through the C ABI
+(ctypes -> libpsfmc_b200.so), against the golden vectors produced by the
+reference (tests/golden/make_golden.py) and against the oracle on seeded inputs.
+"""
+import numpy as np
+import pytest
+
+from conftest import (assert_lnl_close, fp32_bounds, load_golden, model_from_file,
+                      oracle_from_model)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def c1_golden():
+    return load_golden('c1_golden.json')
+
+
+def test_library_is_the_cuda_one(cuda_library):
+    from psfmc_b200 import _lib
+    assert _lib.library_path() == cuda_library
+    import torch
+    assert torch.cuda.is_available()
+
+
+def test_c1_fp64_matches_reference_m3(cuda_library, c1_golden):
+    """FP64 mode vs the reference's own lnL on float64 inputs: 1e-10 relative."""
+    model = model_from_file('j0005/model_c1.py', 'fp64', obs_dtype=np.float64)
+    thetas = np.array(c1_golden['theta'])
+    got = model.log_likelihood_batch(thetas)
+    assert_lnl_close(got, c1_golden['lnl']['M3'], 'fp64')
+    # the -inf cases are exactly the reference's
+    assert got[c1_golden['names'].index('C_exact_centre')] == -np.inf
+
+
+def test_c1_fp32_within_stated_tolerance(cuda_library, c1_golden):
+    model = model_from_file('j0005/model_c1.py', 'fp32', obs_dtype=np.float64)
+    thetas = np.array(c1_golden['theta'])
+    got = model.log_likelihood_batch(thetas)
+    bounds = fp32_bounds(model, thetas)
+    assert_lnl_close(got, c1_golden['lnl']['M3'], 'fp32', bounds)
+    # and against the numpy-1.x-faithful mode of the reference (float32 FITS)
+    model32 = model_from_file('j0005/model_c1.py', 'fp32')
+    got32 = model32.log_likelihood_batch(thetas)
+    assert_lnl_close(got32, c1_golden['lnl']['M2'], 'fp32', bounds)
+
+
+def test_c1_rawf32_mode_tracks_reference_m2(cuda_library, c1_golden):
+    """float32 raw-model storage + float64 FFT/tail = the reference on numpy 1.x
+    with float32 FITS inputs. A float32 rounding may flip where the float64 value
+    differs in the last ulp, so the gate is 1e-7 relative, not 1e-10."""
+    model = model_from_file('j0005/model_c1.py', 'fp64_rawf32')
+    thetas = np.array(c1_golden['theta'])
+    got = model.log_likelihood_batch(thetas)
+    expect = np.array(c1_golden['lnl']['M2'])
+    finite = np.isfinite(expect)
+    assert np.array_equal(np.isfinite(got), finite)
+    rel = np.abs(got[finite] - expect[finite]) / np.abs(expect[finite])
+    assert rel.max() < 1e-7, rel.max()
+
+
+def test_c1_two_psf_index_selection(cuda_library):
+    golden = load_golden('c1_2psf_golden.json')
+    thetas = np.array(golden['theta'])
+    model = model_from_file('j0005/model_c1_2psf.py', 'fp64', obs_dtype=np.float64,
+                            two_psf=True)
+    assert model.num_params == golden['setup']['num_params']
+    assert_lnl_close(model.log_likelihood_batch(thetas), golden['lnl']['M3'], 'fp64')
+    model32 = model_from_file('j0005/model_c1_2psf.py', 'fp32', obs_dtype=np.float64,
+                              two_psf=True)
+    assert_lnl_close(model32.log_likelihood_batch(thetas), golden['lnl']['M3'], 'fp32',
+                     fp32_bounds(model32, thetas))
+    # an out-of-range PSF index is -inf (the prior is -inf there)
+    bad = thetas[:2].copy()
+    bad[:, -1] = (2.6, -0.7)
+    assert np.all(model.log_likelihood_batch(bad) == -np.inf)
+
+
+@pytest.mark.parametrize('index', ['0.5', '1.0', '3.1', '4.0', '6.5'])
+def test_c2_galfit_sersic_sweep(cuda_library, index):
+    golden = load_golden('c2_golden.json')['cases'][index]
+    thetas = np.array(golden['theta'])
+    model = model_from_file(golden['model_file'], 'fp64', obs_dtype=np.float64)
+    assert_lnl_close(model.log_likelihood_batch(thetas), golden['lnl']['M3'], 'fp64')
+    model32 = model_from_file(golden['model_file'], 'fp32', obs_dtype=np.float64)
+    got = model32.log_likelihood_batch(thetas)
+    expect = np.array(golden['lnl']['M3'])
+    # noiseless fixture with weights 4e6: very high S/N, so the float32 bound
+    # (which scales with S/N) is correspondingly larger here
+    assert_lnl_close(got, expect, 'fp32', fp32_bounds(model32, thetas))
+
+
+def test_c1_images_match_reference_pixels(cuda_library, c1_golden):
+    """Blob images (raw, convolved, residual, composite IVM) at sampled pixels."""
+    model = model_from_file('j0005/model_c1.py', 'fp64', obs_dtype=np.float64)
+    thetas = np.array(c1_golden['theta'][:6])
+    imgs = model.engine.render(thetas)
+    px = np.array(c1_golden['sample_px'])
+    for row in range(len(thetas)):
+        ref = c1_golden['pixels']['M3'][row]
+        for key in ('raw_model', 'convolved_model', 'residual', 'composite_ivm'):
+            got = imgs[key][row].ravel()[px]
+            want = np.array(ref[key])
+            if not np.all(np.isfinite(want)):
+                continue
+            scale = np.abs(imgs[key][row][np.isfinite(imgs[key][row])]).max()
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-12 * scale), (row, key)
+    # point-source-subtracted image against the oracle
+    oracle = oracle_from_model(model)
+    ref = oracle.images(thetas[0])['point_source_subtracted']
+    assert np.allclose(imgs['point_source_subtracted'][0], ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize('size,n_sersic', [(256, 2), (512, 3), (64, 1), (32, 1)])
+def test_synthetic_frames_against_oracle(cuda_library, size, n_sersic):
+    """C3 / C4 frame sizes (and small ones) on seeded synthetic inputs."""
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.synthetic import draw_walkers_fast, synthetic_components
+    comps = synthetic_components(size, n_sersic, dtype=np.float64,
+                                 psf_size=min(64, size // 2))
+    model = MultiComponentModel(comps, precision='fp64')
+    thetas = draw_walkers_fast(model, 6, seed=size)
+    expect = oracle_from_model(model).lnlike_batch(thetas)
+    assert_lnl_close(model.log_likelihood_batch(thetas), expect, 'fp64')
+    comps = synthetic_components(size, n_sersic, dtype=np.float64,
+                                 psf_size=min(64, size // 2))
+    model32 = MultiComponentModel(comps, precision='fp32')
+    assert_lnl_close(model32.log_likelihood_batch(thetas), expect, 'fp32',
+                     fp32_bounds(model32, thetas))
+
+
+def test_nonsquare_frame(cuda_library):
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.components import Configuration, PointSource, Sersic, Sky
+    rng = np.random.RandomState(3)
+    obs = 0.05 * rng.standard_normal((64, 128))
+    ivm = np.full((64, 128), 400.0)
+    ivm[5, 7] = 0.0
+    obs[9, 100] = np.nan
+    psf = np.zeros((16, 32))
+    psf[6:11, 14:19] = rng.random_sample((5, 5)) + 0.1
+    psf_ivm = np.full((16, 32), 1.0e4)
+    comps = [Configuration(obs, ivm, psf, psf_ivm, mag_zeropoint=25.0),
+             Sky(adu=0.003), PointSource(xy=(70.3, 30.6), mag=19.0),
+             Sersic(xy=(60.2, 33.1), mag=20.0, reff=7.0, reff_b=3.0, index=2.2,
+                    angle=0.4)]
+    model = MultiComponentModel(comps, precision='fp64')
+    assert model.num_params == 0
+    theta = np.zeros((3, 1))
+    expect = oracle_from_model(model).lnlike_batch(np.zeros((3, 0)))
+    assert_lnl_close(model.log_likelihood_batch(theta), expect, 'fp64')
+
+
+def test_full_size_properties(cuda_library):
+    """Size-independent properties at the benchmark's full ensemble size:
+    determinism, independence of batch composition / chunking, permutation
+    equivariance, agreement of the host and device-pointer entry points."""
+    import torch
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model = model_from_file('j0005/model_c1.py', 'fp32')
+    thetas = draw_walkers_fast(model, 4096, seed=11)
+    full = model.log_likelihood_batch(thetas)
+    again = model.log_likelihood_batch(thetas)
+    assert np.array_equal(full, again)
+    perm = np.random.RandomState(0).permutation(len(thetas))
+    assert np.array_equal(model.log_likelihood_batch(thetas[perm]), full[perm])
+    pieces = np.concatenate([model.log_likelihood_batch(thetas[s:s + 333])
+                             for s in range(0, len(thetas), 333)])
+    assert np.array_equal(pieces, full)
+    assert np.isfinite(full).mean() > 0.9
+    # device-pointer entry point on torch's current stream
+    dev = torch.device('cuda:0')
+    th_d = torch.from_numpy(thetas).to(dev)
+    out_d = torch.empty(len(thetas), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    model.engine.lnlike_device(th_d.data_ptr(), len(thetas), thetas.shape[1],
+                               out_d.data_ptr(), stream=stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(out_d.cpu().numpy(), full)
+    # a sample of the full batch against the oracle
+    oracle = oracle_from_model(model)
+    rows = np.arange(0, 4096, 256)
+    assert_lnl_close(full[rows], oracle.lnlike_batch(thetas[rows]), 'fp32',
+                     fp32_bounds(model, thetas[rows], oracle))
+
+
+def test_edge_batches(cuda_library, c1_golden):
+    model = model_from_file('j0005/model_c1.py', 'fp32')
+    thetas = np.array(c1_golden['theta'])
+    assert model.log_likelihood_batch(thetas[:0].reshape(0, 18)).shape == (0,)
+    one = model.log_likelihood_batch(thetas[:1])
+    assert one.shape == (1,) and np.isfinite(one[0])
+    # ld larger than D (padded rows) is allowed
+    padded = np.concatenate([thetas, np.zeros((len(thetas), 3))], axis=1)
+    assert np.array_equal(model.log_likelihood_batch(padded),
+                          model.log_likelihood_batch(thetas))
+
+
+def test_multi_device_sharding(cuda_library):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs >= 2 GPUs')
+    from psfmc_b200.synthetic import draw_walkers_fast
+    single = model_from_file('j0005/model_c1.py', 'fp32')
+    multi = model_from_file('j0005/model_c1.py', 'fp32',
+                            devices=list(range(torch.cuda.device_count())))
+    thetas = draw_walkers_fast(single, 1001, seed=5)
+    assert np.array_equal(single.log_likelihood_batch(thetas),
+                          multi.log_likelihood_batch(thetas))
