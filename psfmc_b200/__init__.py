@@ -10,3 +10,6 @@ __version__ = '0.1.0'
 
 from .engine import LikelihoodEngine, fp32_peak_tflops  # noqa: F401
 from .models import MultiComponentModel                 # noqa: F401
+from .pool import BatchPool                             # noqa: F401
+from .sampler import EnsembleSampler                    # noqa: F401
+from .fitting import model_galaxy_mcmc                  # noqa: F401

@@ -42,7 +42,8 @@ __device__ __forceinline__ double gammaincinv_half(double a) {
   }
   if (!(x > 0.0)) x = 1.0e-300;
   const double lgam_a = lgam_a1 - log(a);
-  for (int it = 0; it < 60; ++it) {
+  double prev_dx = INFINITY;
+  for (int it = 0; it < 16; ++it) {
     double f = gamma_p_series(a, x, lgam_a1) - 0.5;
     double dens = exp((a - 1.0) * log(x) - x - lgam_a);  // dP/dx
     if (!(dens > 0.0)) break;
@@ -55,7 +56,9 @@ __device__ __forceinline__ double gammaincinv_half(double a) {
     if (xn > a + 1.0) xn = 0.5 * (x + a + 1.0);
     double dx = fabs(xn - x);
     x = xn;
-    if (dx <= 4.0e-16 * x) break;
+    // converged, or bouncing between neighbouring doubles (no further progress)
+    if (dx <= 4.0e-16 * x || (dx <= 1.0e-13 * x && dx >= prev_dx)) break;
+    prev_dx = dx;
   }
   return x;
 }

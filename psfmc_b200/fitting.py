@@ -1,0 +1,145 @@
+"""
+model_galaxy_mcmc with the reference's signature and behaviour
+(/root/reference/psfMC/fitting.py:13-113): build the model from a model file, burn
+in, sample with the stretch-move ensemble sampler, write the FITS trace database
+and the posterior images. The one difference: the sampler gets
+``pool=BatchPool(model)``, so each (half-)ensemble is one GPU batch, and posterior
+images are re-rendered on the GPU from the stored chain instead of travelling to
+the host as blobs at every step.
+"""
+import os
+from collections import OrderedDict
+from warnings import warn
+
+import numpy as np
+
+from . import fitsio
+from .database import (annotate_metadata, filter_lowp_walkers, load_database,
+                       param_matrix, save_database)
+from .models import IMAGE_TYPES, MultiComponentModel
+from .pool import BatchPool
+from .sampler import AutocorrError, EnsembleSampler
+
+default_filetypes = ('raw_model', 'convolved_model', 'composite_ivm', 'residual',
+                     'point_source_subtracted')
+
+
+def print_progress(step, total, label=''):
+    """Percent-complete line (cf. psfMC/utils.py:167-171)."""
+    if total and (step + 1) % max(1, total // 10) == 0:
+        print('{}: {:d}%'.format(label, int(100 * (step + 1) / total)))
+
+
+def check_convergence_autocorr(sampler, min_chain_to_tau_ratio=10, verbose=0):
+    """True when the chain is longer than ``min_chain_to_tau_ratio`` integrated
+    autocorrelation times of every parameter (cf. analysis/statistics.py:134-155)."""
+    try:
+        acorr = sampler.get_autocorr_time(c=1)
+    except AutocorrError:
+        warn('unable to estimate the autocorrelation time, assuming chain is not '
+             'converged')
+        return False
+    if verbose > 0:
+        print('Autocorrelation times: {}'.format(acorr))
+    return bool(np.all(sampler.chain.shape[1] > min_chain_to_tau_ratio * acorr))
+
+
+def save_posterior_images(model, database, output_name='out_{}', mode='weighted',
+                          filetypes=default_filetypes, bad_px_value=0,
+                          walker_min_percentile=10):
+    """Posterior-mean ('weighted') or maximum-a-posteriori ('maximum'/'MAP')
+    images as FITS files (cf. analysis/images.py:17-101); every database row is
+    rendered on the GPU."""
+    header = model.obs_header.copy()
+    if '{}' not in output_name:
+        output_name += '_{}'
+    database = filter_lowp_walkers(database, percentile=walker_min_percentile)
+    unknown = set(ftype for ftype in filetypes if ftype not in IMAGE_TYPES)
+    if unknown:
+        warn('Unknown filetypes requested: {} Output images will not be generated '
+             'for these types.'.format(unknown))
+    filetypes = [ftype for ftype in filetypes if ftype in IMAGE_TYPES]
+    thetas = param_matrix(database, model)
+    output = {}
+    if mode in ('maximum', 'MAP'):
+        best = int(np.argmax(database['lnprobability']))
+        imgs = model.sample_images(thetas[best], which=filetypes)
+        output = {ftype: np.array(imgs[ftype]) for ftype in filetypes}
+    elif mode == 'weighted':
+        if len(database) != model.accumulated_samples:
+            model.reset_images()
+            model.accumulate_from_chain(thetas, which=filetypes)
+        output = {ftype: np.array(model.posterior_images[ftype]) for ftype in filetypes}
+    else:
+        warn('Unknown posterior output mode ({}). Posterior model images will not '
+             'be saved.'.format(mode))
+        return None
+    for key, (value, comment) in annotate_metadata(
+            OrderedDict((k, database.meta[k]) for k in database.meta
+                        if k.startswith(('MC', 'MAP')))).items():
+        header.set(key, value, comment)
+    written = []
+    for ftype in filetypes:
+        img = output[ftype]
+        img[~np.isfinite(img)] = bad_px_value
+        header.set('OBJECT', ftype)
+        fname = output_name.format(ftype) + '.fits'
+        fitsio.writeto(fname, img, header=header, overwrite=True)
+        written.append(fname)
+    return written
+
+
+def model_galaxy_mcmc(model_file, output_name=None, write_fits=default_filetypes,
+                      iterations=0, burn=0, chains=None, max_iterations=1,
+                      convergence_check=check_convergence_autocorr,
+                      precision='fp32', devices=None, seed=None, verbose=True):
+    """Same arguments as the reference plus ``precision`` / ``devices`` (engine)
+    and ``seed`` (reproducible runs). Returns the trace database table."""
+    if output_name is None:
+        output_name = 'out_' + model_file.replace('.py', '')
+    output_name += '_{}'
+    mc_model = model_file if isinstance(model_file, MultiComponentModel) else \
+        MultiComponentModel(components=model_file, precision=precision,
+                            devices=devices)
+    if chains is None:
+        chains = 2 * mc_model.num_params + 2
+    sampler = EnsembleSampler(nwalkers=chains, dim=mc_model.num_params,
+                              lnpostfn=mc_model.log_posterior,
+                              kwargs={'model': mc_model},
+                              pool=BatchPool(mc_model))
+    if seed is not None:
+        sampler._random.seed(seed)
+        np.random.seed(seed)
+    db_name = output_name.format('db') + '.fits'
+    if not os.path.exists(db_name):
+        param_vec = mc_model.init_params_from_priors(chains)
+        for step, result in enumerate(sampler.sample(param_vec, iterations=burn)):
+            param_vec = result[0]
+            sampler.clear_blobs()
+            if verbose:
+                print_progress(step, burn, 'Burning')
+        sampler.reset()
+        converged = False
+        for sampling_iter in range(max_iterations):
+            for step, result in enumerate(
+                    sampler.sample(param_vec, iterations=iterations)):
+                sampler.clear_blobs()
+                if verbose:
+                    print_progress(step, iterations, 'Sampling')
+            if convergence_check(sampler):
+                converged = True
+                break
+            warn('Not yet converged after {:d} iterations:'.format(
+                (sampling_iter + 1) * iterations))
+        metadata = OrderedDict([
+            ('MCITER', sampler.chain.shape[1]), ('MCBURN', burn),
+            ('MCCHAINS', chains), ('MCCONVRG', converged),
+            ('MCACCEPT', float(sampler.acceptance_fraction.mean()))])
+        database = save_database(sampler, mc_model, db_name, meta_dict=metadata)
+    else:
+        print('Database already contains sampled chains, skipping sampling')
+        database = load_database(db_name)
+    if write_fits:
+        save_posterior_images(mc_model, database, output_name=output_name,
+                              filetypes=write_fits)
+    return database

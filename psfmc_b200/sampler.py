@@ -1,0 +1,236 @@
+"""
+Affine-invariant ensemble sampler with emcee 2.x semantics.
+
+emcee is the reference's sampler (/root/reference/psfMC/fitting.py:5,56-58; pinned
+2.2.1 in environment.yml:25) but is not installed in this image, so the stretch
+move is implemented here with the same interface and the same random-number call
+order per half-step -- ``rand(Ns)`` for the stretch factors, ``randint(Nc, size=Ns)``
+for the partners, ``rand(Ns)`` for the acceptance -- drawn from a
+``numpy.random.RandomState``, so that seeded runs are comparable with real emcee.
+The posterior is evaluated through ``pool.map`` once for the starting ensemble and
+then for two sequentially dependent half-ensembles per iteration: those are the
+batches the GPU engine sees.
+"""
+import numpy as np
+
+__all__ = ['EnsembleSampler', 'AutocorrError', 'integrated_time']
+
+
+class AutocorrError(Exception):
+    """The chain is too short to estimate the autocorrelation time."""
+
+
+def autocorr_function(x, axis=0):
+    """Normalised autocorrelation function along ``axis`` (FFT-based)."""
+    x = np.atleast_1d(x)
+    n = x.shape[axis]
+    f = np.fft.fft(x - np.mean(x, axis=axis, keepdims=True), n=2 * n, axis=axis)
+    index = [slice(None)] * x.ndim
+    index[axis] = slice(0, n)
+    acf = np.fft.ifft(f * np.conjugate(f), axis=axis)[tuple(index)].real
+    first = [slice(None)] * x.ndim
+    first[axis] = slice(0, 1)
+    return acf / acf[tuple(first)]
+
+
+def integrated_time(x, low=10, high=None, step=1, c=10, axis=0):
+    """Integrated autocorrelation time with emcee 2.x's windowing rule: the
+    smallest window M (low <= M < high) with M > c * tau(M)."""
+    size = 0.5 * x.shape[axis]
+    if int(c * low) >= size:
+        raise AutocorrError('The chain is too short')
+    acf = autocorr_function(x, axis=axis)
+    if high is None:
+        high = int(size / c)
+    for window in np.arange(low, high, step).astype(int):
+        index = [slice(None)] * acf.ndim
+        index[axis] = slice(1, window)
+        tau = 1 + 2 * np.sum(acf[tuple(index)], axis=axis)
+        if np.all(tau > 1.0) and window > c * np.max(tau):
+            return tau
+        if c * np.max(tau) >= size:
+            break
+    raise AutocorrError('The chain is too short to reliably estimate the '
+                        'autocorrelation time')
+
+
+class _FunctionWrapper(object):
+    """Picklable ``f(x, *args, **kwargs)`` (what emcee hands to ``pool.map``)."""
+
+    def __init__(self, f, args, kwargs):
+        self.f = f
+        self.args = list(args or [])
+        self.kwargs = dict(kwargs or {})
+
+    def __call__(self, x):
+        return self.f(x, *self.args, **self.kwargs)
+
+
+class EnsembleSampler(object):
+    """
+    :param nwalkers: ensemble size k (even, >= 2*dim unless ``live_dangerously``)
+    :param dim: number of parameters
+    :param lnpostfn: ``f(theta, *args, **kwargs) -> lnpost`` or ``(lnpost, blob)``
+    :param a: stretch scale (2.0)
+    :param pool: object with ``map(func, iterable)``; default: the builtin ``map``
+    """
+
+    def __init__(self, nwalkers, dim, lnpostfn, a=2.0, args=None, kwargs=None,
+                 pool=None, live_dangerously=False):
+        if nwalkers % 2 != 0:
+            raise AssertionError('The number of walkers must be even.')
+        if not live_dangerously and nwalkers < 2 * dim:
+            raise AssertionError('The number of walkers needs to be more than twice '
+                                 'the dimension of your parameter space.')
+        self.k = int(nwalkers)
+        self.dim = int(dim)
+        self.a = float(a)
+        self.pool = pool
+        self.lnprobfn = _FunctionWrapper(lnpostfn, args, kwargs)
+        self._random = np.random.mtrand.RandomState()
+        self.reset()
+
+    # -- state ------------------------------------------------------------------
+    @property
+    def random_state(self):
+        return self._random.get_state()
+
+    @random_state.setter
+    def random_state(self, state):
+        try:
+            self._random.set_state(state)
+        except Exception:
+            pass
+
+    def reset(self):
+        self.iterations = 0
+        self.naccepted = np.zeros(self.k)
+        self._chain = np.empty((self.k, 0, self.dim))
+        self._lnprob = np.empty((self.k, 0))
+        self._blobs = []
+
+    def clear_blobs(self):
+        self._blobs = []
+
+    @property
+    def chain(self):
+        """(nwalkers, iterations, dim)"""
+        return self._chain
+
+    @property
+    def flatchain(self):
+        shape = self._chain.shape
+        return self._chain.reshape(shape[0] * shape[1], shape[2])
+
+    @property
+    def lnprobability(self):
+        """(nwalkers, iterations)"""
+        return self._lnprob
+
+    @property
+    def flatlnprobability(self):
+        return self._lnprob.flatten()
+
+    @property
+    def blobs(self):
+        return self._blobs
+
+    @property
+    def acceptance_fraction(self):
+        return self.naccepted / self.iterations
+
+    def get_autocorr_time(self, low=10, high=None, step=1, c=10):
+        return integrated_time(np.mean(self.chain, axis=0), axis=0, low=low,
+                               high=high, step=step, c=c)
+
+    @property
+    def acor(self):
+        return self.get_autocorr_time()
+
+    # -- evaluation -------------------------------------------------------------
+    def _get_lnprob(self, pos):
+        pos = np.asarray(pos)
+        if np.any(np.isinf(pos)):
+            raise ValueError('At least one parameter value was infinite.')
+        if np.any(np.isnan(pos)):
+            raise ValueError('At least one parameter value was NaN.')
+        mapper = self.pool.map if self.pool is not None else map
+        results = list(mapper(self.lnprobfn, [pos[i] for i in range(len(pos))]))
+        try:
+            lnprob = np.array([float(r[0]) for r in results])
+            blob = [r[1] for r in results]
+        except (IndexError, TypeError):
+            lnprob = np.array([float(r) for r in results])
+            blob = None
+        if np.any(np.isnan(lnprob)):
+            raise ValueError('lnprob returned NaN.')
+        return lnprob, blob
+
+    def _propose_stretch(self, active, complement, lnprob_active):
+        s = np.atleast_2d(active)
+        c = np.atleast_2d(complement)
+        ns, nc = len(s), len(c)
+        zz = ((self.a - 1.0) * self._random.rand(ns) + 1) ** 2.0 / self.a
+        partner = self._random.randint(nc, size=(ns,))
+        q = c[partner] - zz[:, np.newaxis] * (c[partner] - s)
+        newlnprob, blob = self._get_lnprob(q)
+        lnpdiff = (self.dim - 1.0) * np.log(zz) + newlnprob - lnprob_active
+        accept = lnpdiff > np.log(self._random.rand(len(lnpdiff)))
+        return q, newlnprob, accept, blob
+
+    def sample(self, p0, lnprob0=None, rstate0=None, blobs0=None, iterations=1,
+               thin=1, storechain=True):
+        """Generator advancing the ensemble; yields ``(pos, lnprob, rstate)`` or
+        ``(pos, lnprob, rstate, blobs)`` after every iteration."""
+        if rstate0 is not None:
+            self.random_state = rstate0
+        p = np.array(p0, dtype=np.float64)
+        if p.shape != (self.k, self.dim):
+            raise ValueError('p0 must have shape (nwalkers, dim)')
+        halfk = self.k // 2
+        lnprob, blobs = lnprob0, blobs0
+        if lnprob is None:
+            lnprob, blobs = self._get_lnprob(p)
+        lnprob = np.array(lnprob, dtype=np.float64)
+        if np.any(np.isnan(lnprob)):
+            raise ValueError('The initial lnprob was NaN.')
+        start = self._chain.shape[1]
+        if storechain:
+            nstore = int(iterations / thin)
+            self._chain = np.concatenate(
+                (self._chain, np.zeros((self.k, nstore, self.dim))), axis=1)
+            self._lnprob = np.concatenate(
+                (self._lnprob, np.zeros((self.k, nstore))), axis=1)
+        halves = (slice(0, halfk), slice(halfk, self.k))
+        for it in range(int(iterations)):
+            self.iterations += 1
+            for s0, s1 in (halves, halves[::-1]):
+                q, newlnp, acc, blob = self._propose_stretch(p[s0], p[s1], lnprob[s0])
+                if np.any(acc):
+                    lnprob[s0][acc] = newlnp[acc]
+                    p[s0][acc] = q[acc]
+                    self.naccepted[s0][acc] += 1
+                    if blob is not None:
+                        if blobs is None:
+                            raise AssertionError(
+                                'If you start sampling with a given lnprob, you '
+                                'also need to provide the current list of blobs.')
+                        full = np.arange(self.k)[s0][acc]
+                        for src, dst in zip(np.flatnonzero(acc), full):
+                            blobs[dst] = blob[src]
+            if storechain and it % thin == 0:
+                ind = start + it // thin
+                self._chain[:, ind, :] = p
+                self._lnprob[:, ind] = lnprob
+                if blobs is not None:
+                    self._blobs.append(list(blobs))
+            if blobs is not None:
+                yield p, lnprob, self.random_state, blobs
+            else:
+                yield p, lnprob, self.random_state
+
+    def run_mcmc(self, pos0, nsteps, rstate0=None, lnprob0=None, **kwargs):
+        results = None
+        for results in self.sample(pos0, lnprob0, rstate0, iterations=nsteps, **kwargs):
+            pass
+        return results

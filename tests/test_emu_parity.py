@@ -1,0 +1,156 @@
+"""
+CPU tier: the CUDA kernel SOURCES (psfmc_b200/csrc/*.cu*) compiled by g++ against
+the SIMT emulator (tests/emu/cuda_emu.h) and driven through the same C ABI and the
+same host code as on the GPU, compared with the oracle / golden vectors. This
+checks the kernels' arithmetic, indexing, barriers and launch plans without a GPU;
+it says nothing about speed. The product library is never built this way.
+"""
+import numpy as np
+import pytest
+
+from conftest import (assert_lnl_close, fp32_bounds, load_golden, model_from_file,
+                      oracle_from_model)
+
+
+@pytest.fixture(scope='module')
+def c1_golden():
+    return load_golden('c1_golden.json')
+
+
+@pytest.mark.parametrize('path', ['fused', 'staged'])
+def test_emu_c1_fp64_m3(emu_library, c1_golden, path, monkeypatch):
+    monkeypatch.setenv('PSFMC_FORCE_STAGED', '1' if path == 'staged' else '0')
+    model = model_from_file('j0005/model_c1.py', 'fp64', library=emu_library,
+                            obs_dtype=np.float64)
+    thetas = np.array(c1_golden['theta'][:10])
+    got = model.log_likelihood_batch(thetas)
+    assert_lnl_close(got, c1_golden['lnl']['M3'][:10], 'fp64')
+    assert got[c1_golden['names'].index('C_exact_centre')] == -np.inf
+
+
+@pytest.mark.parametrize('path', ['fused', 'staged'])
+def test_emu_c1_fp32_tolerance(emu_library, c1_golden, path, monkeypatch):
+    monkeypatch.setenv('PSFMC_FORCE_STAGED', '1' if path == 'staged' else '0')
+    model = model_from_file('j0005/model_c1.py', 'fp32', library=emu_library,
+                            obs_dtype=np.float64)
+    assert model.engine.info()['path'] == (1 if path == 'fused' else 0)
+    thetas = np.array(c1_golden['theta'][:16])
+    got = model.log_likelihood_batch(thetas)
+    assert_lnl_close(got, c1_golden['lnl']['M3'][:16], 'fp32',
+                     fp32_bounds(model, thetas))
+
+
+def test_emu_rawf32_tracks_m2(emu_library, c1_golden):
+    model = model_from_file('j0005/model_c1.py', 'fp64_rawf32', library=emu_library)
+    thetas = np.array(c1_golden['theta'][:6])
+    got = model.log_likelihood_batch(thetas)
+    expect = np.array(c1_golden['lnl']['M2'][:6])
+    finite = np.isfinite(expect)
+    assert np.array_equal(np.isfinite(got), finite)
+    rel = np.abs(got[finite] - expect[finite]) / np.abs(expect[finite])
+    assert rel.max() < 1e-7
+
+
+def test_emu_two_psf_selection(emu_library):
+    golden = load_golden('c1_2psf_golden.json')
+    thetas = np.array(golden['theta'][:8])
+    for precision in ('fp64', 'fp32'):
+        model = model_from_file('j0005/model_c1_2psf.py', precision,
+                                library=emu_library, obs_dtype=np.float64,
+                                two_psf=True)
+        got = model.log_likelihood_batch(thetas)
+        bounds = fp32_bounds(model, thetas) if precision == 'fp32' else None
+        assert_lnl_close(got, golden['lnl']['M3'][:8], precision, bounds)
+    bad = thetas[:2].copy()
+    bad[:, -1] = (2.6, -0.7)
+    assert np.all(model.log_likelihood_batch(bad) == -np.inf)
+
+
+@pytest.mark.parametrize('index', ['0.5', '4.0'])
+def test_emu_c2_galfit(emu_library, index):
+    golden = load_golden('c2_golden.json')['cases'][index]
+    thetas = np.array(golden['theta'])
+    model = model_from_file(golden['model_file'], 'fp64', library=emu_library,
+                            obs_dtype=np.float64)
+    assert_lnl_close(model.log_likelihood_batch(thetas), golden['lnl']['M3'], 'fp64')
+    model32 = model_from_file(golden['model_file'], 'fp32', library=emu_library,
+                              obs_dtype=np.float64)
+    assert_lnl_close(model32.log_likelihood_batch(thetas), golden['lnl']['M3'],
+                     'fp32', fp32_bounds(model32, thetas))
+
+
+@pytest.mark.parametrize('size,n_sersic', [(32, 1), (64, 1), (256, 2)])
+def test_emu_synthetic_frames(emu_library, size, n_sersic):
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.synthetic import draw_walkers_fast, synthetic_components
+    nwalk = 2 if size >= 256 else 4
+    comps = synthetic_components(size, n_sersic, dtype=np.float64,
+                                 psf_size=min(64, size // 2))
+    model = MultiComponentModel(comps, precision='fp64', library=emu_library)
+    thetas = draw_walkers_fast(model, nwalk, seed=size)
+    expect = oracle_from_model(model).lnlike_batch(thetas)
+    assert_lnl_close(model.log_likelihood_batch(thetas), expect, 'fp64')
+    comps = synthetic_components(size, n_sersic, dtype=np.float64,
+                                 psf_size=min(64, size // 2))
+    model32 = MultiComponentModel(comps, precision='fp32', library=emu_library)
+    assert_lnl_close(model32.log_likelihood_batch(thetas), expect, 'fp32',
+                     fp32_bounds(model32, thetas))
+
+
+def test_emu_images_and_point_source_subtracted(emu_library, c1_golden):
+    model = model_from_file('j0005/model_c1.py', 'fp64', library=emu_library,
+                            obs_dtype=np.float64)
+    thetas = np.array(c1_golden['theta'][:2])
+    imgs = model.engine.render(thetas)
+    px = np.array(c1_golden['sample_px'])
+    for row in range(2):
+        ref = c1_golden['pixels']['M3'][row]
+        for key in ('raw_model', 'convolved_model', 'residual', 'composite_ivm'):
+            got = imgs[key][row].ravel()[px]
+            scale = np.abs(imgs[key][row]).max()
+            assert np.allclose(got, ref[key], rtol=1e-9, atol=1e-12 * scale), key
+    ref = oracle_from_model(model).images(thetas[0])['point_source_subtracted']
+    assert np.allclose(imgs['point_source_subtracted'][0], ref, rtol=1e-9, atol=1e-12)
+
+
+def test_emu_batch_edges_and_determinism(emu_library, c1_golden):
+    model = model_from_file('j0005/model_c1.py', 'fp32', library=emu_library)
+    thetas = np.array(c1_golden['theta'][:5])
+    assert model.log_likelihood_batch(thetas[:0].reshape(0, 18)).shape == (0,)
+    full = model.log_likelihood_batch(thetas)
+    assert np.array_equal(full, model.log_likelihood_batch(thetas))
+    assert np.array_equal(full[::-1], model.log_likelihood_batch(thetas[::-1]))
+    padded = np.concatenate([thetas, np.zeros((5, 3))], axis=1)
+    assert np.array_equal(model.log_likelihood_batch(padded), full)
+    pieces = np.concatenate([model.log_likelihood_batch(thetas[s:s + 2])
+                             for s in range(0, 5, 2)])
+    assert np.array_equal(pieces, full)
+
+
+def test_emu_device_kappa_matches_scipy(emu_library):
+    """kappa = gammaincinv(2n, 0.5) on the device (float64 Halley iteration) against
+    scipy over the whole prior range, through a one-Sersic model whose raw image
+    at the effective radius equals sb_eff."""
+    from scipy.special import gammaincinv
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.components import Configuration, Sersic
+    from psfmc_b200.distributions import Uniform
+    size = 32
+    obs = np.zeros((size, size))
+    ivm = np.ones((size, size))
+    psf = np.zeros((8, 8))
+    psf[4, 4] = 1.0
+    comps = [Configuration(obs, ivm, psf, np.full((8, 8), 1e12), mag_zeropoint=25.0),
+             Sersic(xy=(10.0, 16.0), mag=20.0, reff=6.0, reff_b=6.0,
+                    index=Uniform(loc=0.05, scale=20), angle=0.0)]
+    model = MultiComponentModel(comps, precision='fp64', library=emu_library)
+    ns = np.array([0.06, 0.13, 0.2, 0.36, 0.5, 0.75, 1.0, 1.7, 2.5, 4.0, 6.5, 9.9, 15.0])
+    raw = model.engine.render(ns[:, None], which=('raw_model',))['raw_model']
+    # pixel (x=16, y=16) is exactly at r = reff (circular): value = sbeff * (1 + corr)
+    from oracle import psfmc_oracle as orc
+    for n, img in zip(ns, raw):
+        kappa = gammaincinv(2 * n, 0.5)
+        sbeff = orc.sersic_sb_eff(orc.mag_to_flux(20.0, 25.0), n, 6.0, 6.0, kappa)
+        grad = -kappa / n          # normed_grad at sq_radii = 1
+        want = sbeff * (1 + grad * (1 / 36.0 / 12 * grad))
+        assert abs(img[16, 16] / want - 1) < 1e-12, (n, img[16, 16], want)
