@@ -64,7 +64,7 @@ __device__ __forceinline__ cplx<T> mul_pos_i(cplx<T> a) {
 // --------------------------------------------------------- derived params --
 // Per-walker, per-component constants produced by the prepare kernel (always in
 // float64) and consumed by the render code. Stride PSFMC_DERIVED_STRIDE doubles.
-#define PSFMC_DERIVED_STRIDE 12
+#define PSFMC_DERIVED_STRIDE 24
 // Sersic (psfMC/ModelComponents/Sersic.py:73-134)
 #define D_SER_X0 0
 #define D_SER_Y0 1
@@ -83,8 +83,14 @@ __device__ __forceinline__ cplx<T> mul_pos_i(cplx<T> a) {
 #define D_PS_YMAX 4
 #define D_PS_XMIN 5
 #define D_PS_XMAX 6
+#define D_PS_WX 7     // 7 separable stamp weights along x (x = XMIN + i), then
+#define D_PS_WY 14    // 7 along y (y = YMIN + i); unused taps are 0
 // Sky
 #define D_SKY_ADU 0
+
+// Float32 render constants of the fused path, PSFMC_RC_STRIDE floats per
+// (walker, component), written by the prepare kernel next to the float64 ones.
+#define PSFMC_RC_STRIDE 12
 
 // Compact, device-resident copy of the component program.
 struct Program {

@@ -98,6 +98,10 @@ struct DeviceState {
   DevBuf<double> derived, partials, theta, lnl, wscale;
   double *vscale_inv = nullptr;
   DevBuf<int> psf_sel;
+  DevBuf<float> rconst;
+  cplx<float> *fspec = nullptr, *fspecx = nullptr;
+  float2 *fow = nullptr;
+  int n_sms = 148;
   DevBuf<cplx<T>> scratch;
   DevBuf<T> img[4];
   PinBuf<double> theta_pin, lnl_pin;
@@ -138,6 +142,10 @@ struct Engine : EngineBase {
       cudaFree(d.ovar);
       cudaFree(d.bad);
       cudaFree(d.vscale_inv);
+      cudaFree(d.fspec);
+      cudaFree(d.fspecx);
+      cudaFree(d.fow);
+      d.rconst.release();
       d.wscale.release();
       d.derived.release();
       d.partials.release();
@@ -171,12 +179,20 @@ struct Engine : EngineBase {
     return b;
   }
 
-  int ensure_batch(DeviceState<T> &d, long long B) {
+  // for_images: the blob images always come from the staged kernels
+  int ensure_batch(DeviceState<T> &d, long long B, bool for_images = false) {
     size_t nb = (size_t)B;
+    size_t ncomp = prog_h.n_components > 0 ? prog_h.n_components : 1;
+    if (d.derived.ensure(nb * ncomp * PSFMC_DERIVED_STRIDE) || d.psf_sel.ensure(nb) ||
+        d.wscale.ensure(nb))
+      return fail(PSFMC_ERR_CUDA, "device allocation failed while sizing the batch buffers");
+    if (path == 1 && !for_images) {
+      if (d.rconst.ensure(nb * ncomp * PSFMC_RC_STRIDE))
+        return fail(PSFMC_ERR_CUDA, "device allocation failed (render constants)");
+      return 0;
+    }
     long long chunk = B < plan.chunk ? B : plan.chunk;
-    if (d.derived.ensure(nb * prog_h.n_components * PSFMC_DERIVED_STRIDE) ||
-        d.partials.ensure(nb * plan.n_rowblk) || d.psf_sel.ensure(nb) ||
-        d.wscale.ensure(nb) ||
+    if (d.partials.ensure(nb * plan.n_rowblk) ||
         d.scratch.ensure((size_t)chunk * plan.scratch_elems_per_walker))
       return fail(PSFMC_ERR_CUDA, "device allocation failed while sizing the batch buffers");
     return 0;
@@ -190,8 +206,14 @@ struct Engine : EngineBase {
     StagedBuffers<T> buf = buffers(d);
 #ifndef PSFMC_NO_FUSED
     if (path == 1) {
-      launches += launch_fused_lnlike<T>(plan, buf, prog_h.n_components, precision,
-                                         theta_dev, B, ld, lnl_dev, stream);
+      FusedBuffers fb;
+      fb.rconst = d.rconst.ptr;
+      fb.spec = d.fspec;
+      fb.specx = d.fspecx;
+      fb.ow = d.fow;
+      fb.n_sms = d.n_sms;
+      launches += launch_fused_lnlike<T>(plan, buf, fb, prog_h, theta_dev, B, ld, lnl_dev,
+                                         stream);
       CUDA_TRY(cudaGetLastError());
       return 0;
     }
@@ -292,7 +314,7 @@ struct Engine : EngineBase {
       return fail(PSFMC_ERR_CUDA, "allocation failed (image staging)");
     for (long long start = 0; start < B; start += chunk) {
       long long nb = B - start < chunk ? B - start : chunk;
-      int rc = ensure_batch(d, nb);
+      int rc = ensure_batch(d, nb, true);
       if (rc) return rc;
       CUDA_TRY(cudaMemcpyAsync(d.theta.ptr, theta + start * ld, (size_t)nb * ld * sizeof(double),
                                cudaMemcpyHostToDevice, d.stream));
@@ -579,8 +601,33 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
         (rc = upload(&ds.bad, bad)) || (rc = upload(&ds.vscale_inv, vscale_inv)))
       break;
 #ifndef PSFMC_NO_FUSED
-    if (i == 0) eng->path = fused_path_available<T>(eng->plan, eng->prog_h) ? 1 : 0;
-    if (eng->path == 1 && (rc = fused_prepare_device<T>(eng->plan))) break;
+    if (i == 0) {
+      eng->path = fused_path_available<T>(eng->plan, eng->prog_h) ? 1 : 0;
+      const char *force = getenv("PSFMC_FORCE_STAGED");
+      if (force && force[0] == '1') eng->path = 0;
+    }
+    if (eng->path == 1) {
+      if (fused_prepare_device<T>(eng->plan)) {
+        rc = fail(PSFMC_ERR_CUDA, "cannot reserve shared memory for the fused kernel");
+        break;
+      }
+      cudaDeviceGetAttribute(&ds.n_sms, cudaDevAttrMultiProcessorCount, ds.ordinal);
+      if (ds.n_sms < 1) ds.n_sms = 148;
+      const size_t N = PSFMC_FUSED_N;
+      std::vector<cplx<float>> fspec((size_t)d->n_psf * N * N), fspecx((size_t)d->n_psf * 2 * N);
+      std::vector<double> vs(d->n_psf);
+      for (int k = 0; k < d->n_psf; ++k) vs[k] = 1.0 / vscale_inv[k];
+      fused_spectrum_layout(spec64.data(), d->n_psf, vs.data(), fspec.data(), fspecx.data());
+      std::vector<float2> ow(npx);
+      for (size_t e = 0; e < npx; ++e) {
+        float v = fabsf((float)d->obs_var[e]);
+        ow[e].x = (float)d->obs_data[e];
+        ow[e].y = bad[e] ? -v : v;
+      }
+      if ((rc = upload(&ds.fspec, fspec)) || (rc = upload(&ds.fspecx, fspecx)) ||
+          (rc = upload(&ds.fow, ow)))
+        break;
+    }
 #endif
     if (d->max_batch > 0 && (rc = eng->ensure_batch(ds, d->max_batch))) break;
   }
@@ -588,8 +635,6 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
     delete eng;
     return rc;
   }
-  const char *force = getenv("PSFMC_FORCE_STAGED");
-  if (force && force[0] == '1') eng->path = 0;
   *out = eng;
   return 0;
 }
@@ -702,8 +747,12 @@ int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info) {
   size_t csz = (e->precision == PSFMC_PREC_FP32) ? 8 : 16;
   // staged path: each of the 2*Wc*H complex intermediates is written by rows_fwd,
   // read+written by cols and read by rows_inv (~32 N bytes in float32)
+  // fused path: theta in, render constants out+in, lnL out; spectra and observation
+  // (2 x 128 KB) are shared by all walkers and stay in L2
   info->hbm_bytes_per_eval =
-      e->path == 1 ? (double)(e->prog_h.n_components * 0 + 8 * 32 + 8)
+      e->path == 1 ? (double)(8 * 32 + 8 + e->prog_h.n_components *
+                                               (2 * 4 * PSFMC_RC_STRIDE +
+                                                2 * 8 * PSFMC_DERIVED_STRIDE))
                    : 4.0 * (double)e->plan.scratch_elems_per_walker * csz;
   info->kernels_per_call = e->path == 1 ? 2 : 5;
   info->launches_total = e->launches;

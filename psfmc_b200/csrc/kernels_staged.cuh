@@ -97,12 +97,11 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += adu;
       } else if (kind == PSFMC_POINT) {
-        const int flags = prog->flags[c];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           int e = tid + i * nthreads;
           int r = e / W, x = e - r * W;
-          acc[i] += (float)point_pixel(d, flags, x, y0 + r);
+          acc[i] += (float)point_pixel(d, x, y0 + r);
         }
       } else {
         const SersicF32 s = make_sersic_f32(d);

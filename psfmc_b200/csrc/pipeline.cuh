@@ -126,7 +126,8 @@ inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
     int block = 128;
     unsigned grid = (unsigned)((nthreads + block - 1) / block);
     launch_kernel(prepare_kernel, dim3(grid), dim3(block), 0, stream, buf.prog, theta,
-                  n_batch, ld, fr.H, fr.W, buf.derived, buf.psf_sel, buf.wscale);
+                  n_batch, ld, fr.H, fr.W, buf.derived, buf.psf_sel, buf.wscale,
+                  (float *)nullptr);
   }
   for (long long start = 0; start < n_batch; start += plan.chunk) {
     long long nb = n_batch - start < plan.chunk ? n_batch - start : plan.chunk;

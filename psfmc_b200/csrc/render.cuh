@@ -13,153 +13,6 @@ __device__ __forceinline__ double slot_value(const Program *prog, int comp, int 
   return ti >= 0 ? theta_row[ti] : prog->value[comp][slot];
 }
 
-// One thread per (walker, component): theta -> derived constants, float64.
-//   grid = ceil(B * n_components / blockDim)
-// wscale[b] receives the packing scale of the walker (see below);
-// psf_sel[b] receives the rint-ed PSF index (psfMC/distributions.py:130-138), or
-// -1 when it is out of range (the prior is -inf there; the walker gets -inf).
-__global__ void prepare_kernel(const Program *__restrict__ prog,
-                               const double *__restrict__ theta, long long n_batch,
-                               long long ld, int H, int W, double *__restrict__ derived,
-                               int *__restrict__ psf_sel, double *__restrict__ wscale) {
-  const int ncomp = prog->n_components;
-  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= n_batch * ncomp) return;
-  long long b = gid / ncomp;
-  int c = (int)(gid - b * ncomp);
-  const double *th = theta + b * ld;
-  double *out = derived + (b * ncomp + c) * PSFMC_DERIVED_STRIDE;
-  const int kind = prog->kind[c];
-  const int flags = prog->flags[c];
-  if (c == 0) {
-    int sel = 0;
-    if (prog->psf_theta_index >= 0) {
-      double v = rint(th[prog->psf_theta_index]);
-      sel = (v >= 0.0 && v < (double)prog->n_psf) ? (int)v : -1;
-    } else {
-      double v = rint(prog->psf_value);
-      sel = (v >= 0.0 && v < (double)prog->n_psf) ? (int)v : -1;
-    }
-    psf_sel[b] = sel;
-    // Per-walker power-of-two scale for the raw^2 channel of the packed transform
-    // (z = raw + i * wscale * raw^2): with wscale ~ 1/flux both channels have
-    // comparable magnitude, so rounding errors of the large one do not swamp
-    // the small one. Exact (power of two), undone in the epilogue.
-    double ftot = 0.0;
-    for (int k = 0; k < ncomp; ++k) {
-      if (prog->kind[k] == PSFMC_SKY)
-        ftot += fabs(slot_value(prog, k, PSFMC_P_ADU, th));
-      else
-        ftot += mag_to_flux(slot_value(prog, k, PSFMC_P_MAG, th), prog->mag_zp);
-    }
-    double sc = 1.0;
-    if (isfinite(ftot) && ftot > 1e-300) {
-      int ex = 0;
-      frexp(ftot, &ex);             // ftot = m * 2^ex, m in [0.5, 1)
-      if (ex > 500) ex = 500;
-      if (ex < -500) ex = -500;
-      sc = ldexp(1.0, -ex);
-    }
-    wscale[b] = sc;
-  }
-  if (kind == PSFMC_SKY) {
-    out[D_SKY_ADU] = slot_value(prog, c, PSFMC_P_ADU, th);
-  } else if (kind == PSFMC_POINT) {
-    double x = slot_value(prog, c, PSFMC_P_X, th);
-    double y = slot_value(prog, c, PSFMC_P_Y, th);
-    double mag = slot_value(prog, c, PSFMC_P_MAG, th);
-    double radius = (flags & PSFMC_FLAG_BILINEAR) ? 0.5 : 3.0;
-    out[D_PS_X] = x;
-    out[D_PS_Y] = y;
-    out[D_PS_FLUX] = mag_to_flux(mag, prog->mag_zp);
-    stamp_bounds(y, radius, H, &out[D_PS_YMIN], &out[D_PS_YMAX]);
-    stamp_bounds(x, radius, W, &out[D_PS_XMIN], &out[D_PS_XMAX]);
-  } else {  // PSFMC_SERSIC: Sersic.py:73-96 (transform), :47-71 (kappa, sb_eff)
-    double x0 = slot_value(prog, c, PSFMC_P_X, th);
-    double y0 = slot_value(prog, c, PSFMC_P_Y, th);
-    double mag = slot_value(prog, c, PSFMC_P_MAG, th);
-    double reff = slot_value(prog, c, PSFMC_P_REFF, th);
-    double reff_b = slot_value(prog, c, PSFMC_P_REFF_B, th);
-    double n = slot_value(prog, c, PSFMC_P_INDEX, th);
-    double angle = slot_value(prog, c, PSFMC_P_ANGLE, th);
-    if (flags & PSFMC_FLAG_ANGLE_DEGREES) angle = angle * (PSFMC_PI / 180.0);  // np.deg2rad
-    angle += 0.5 * PSFMC_PI;
-    double sn = sin(angle), cs = cos(angle);
-    double kappa = gammaincinv_half(2.0 * n);
-    double flux = mag_to_flux(mag, prog->mag_zp);
-    out[D_SER_X0] = x0;
-    out[D_SER_Y0] = y0;
-    out[D_SER_A00] = cs / reff;
-    out[D_SER_A01] = sn / reff;
-    out[D_SER_A10] = -sn / reff_b;
-    out[D_SER_A11] = cs / reff_b;
-    out[D_SER_P] = 0.5 / n;
-    out[D_SER_KAPPA] = kappa;
-    out[D_SER_SBEFF] = sersic_sb_eff(flux, n, reff, reff_b, kappa);
-  }
-}
-
-// ------------------------------------------------------------ pixel math --
-
-// float64: the reference's expressions, literally (Sersic.py:124-133,151-153).
-__device__ __forceinline__ double sersic_pixel(const double *d, double x, double y) {
-  double dx = x - d[D_SER_X0], dy = y - d[D_SER_Y0];
-  double u = d[D_SER_A00] * dx + d[D_SER_A01] * dy;
-  double v = d[D_SER_A10] * dx + d[D_SER_A11] * dy;
-  double sq = u * u + v * v;
-  double sdr = sq / (dx * dx + dy * dy);
-  double p = d[D_SER_P], kappa = d[D_SER_KAPPA];
-  double lg = log(sq);
-  double sb = exp(-kappa * expm1(lg * p));
-  double g = -kappa * 2.0 * p * exp(lg * (p - 0.5));
-  double cent = sdr / 12.0 * g;
-  return d[D_SER_SBEFF] * sb * (1.0 + g * cent);
-}
-
-// Point-source stamp weight at pixel (x, y); 0 outside the stamp
-// (PointSource.py:40-56). Always float64: at most 49 pixels per source.
-__device__ __forceinline__ double point_pixel(const double *d, int flags, int x, int y) {
-  if ((double)y < d[D_PS_YMIN] || (double)y > d[D_PS_YMAX] || (double)x < d[D_PS_XMIN] ||
-      (double)x > d[D_PS_XMAX])
-    return 0.0;
-  double ddx = (double)x - d[D_PS_X], ddy = (double)y - d[D_PS_Y];
-  double kern;
-  if (flags & PSFMC_FLAG_BILINEAR)
-    kern = (1.0 - fabs(ddx)) * (1.0 - fabs(ddy));
-  else
-    kern = lanczos3_ref(ddx) * lanczos3_ref(ddy);
-  return kern * d[D_PS_FLUX];
-}
-
-// Raw model at one pixel in float64 (PSFMC_PREC_FP64), components added in model
-// order. round_f32: round the running sum to float32 after every component, i.e.
-// the reference's float32 `arr +=` storage (PSFMC_PREC_FP64_RAWF32, oracle M2).
-// ps_only: only point sources (models.py:296-306).
-__device__ __forceinline__ double raw_pixel_f64(const Program *prog, const double *derived_b,
-                                                int x, int y, bool round_f32,
-                                                bool ps_only) {
-  double acc = 0.0;
-  const int ncomp = prog->n_components;
-  for (int c = 0; c < ncomp; ++c) {
-    const double *d = derived_b + c * PSFMC_DERIVED_STRIDE;
-    const int kind = prog->kind[c];
-    if (ps_only && kind != PSFMC_POINT) continue;
-    if (kind == PSFMC_SKY) {
-      acc += d[D_SKY_ADU];
-    } else if (kind == PSFMC_POINT) {
-      double w = point_pixel(d, prog->flags[c], x, y);
-      // pixels outside the stamp are not touched by the reference's slice `+=`
-      if ((double)y >= d[D_PS_YMIN] && (double)y <= d[D_PS_YMAX] &&
-          (double)x >= d[D_PS_XMIN] && (double)x <= d[D_PS_XMAX])
-        acc += w;
-    } else {
-      acc += sersic_pixel(d, (double)x, (double)y);
-    }
-    if (round_f32) acc = (double)(float)acc;
-  }
-  return acc;
-}
-
 // ---------------------------------------------------- float32 fast path --
 #ifdef PSFMC_EMU
 __device__ __forceinline__ float fast_lg2(float x) { return log2f(x); }
@@ -225,6 +78,171 @@ __device__ __forceinline__ float sersic_pixel_f32(const SersicF32 &s, float x, f
   float t = fminf(fast_ex2(s.p * fast_lg2(sq)), 1.0e18f);
   float sb = fast_ex2(s.c0 - s.c1 * t);
   return sb * (1.0f + s.kq * (t * t) * fast_rcp(r2));
+}
+
+// One thread per (walker, component): theta -> derived constants, float64.
+//   grid = ceil(B * n_components / blockDim)
+// wscale[b] receives the packing scale of the walker (see below);
+// psf_sel[b] receives the rint-ed PSF index (psfMC/distributions.py:130-138), or
+// -1 when it is out of range (the prior is -inf there; the walker gets -inf).
+__global__ void prepare_kernel(const Program *__restrict__ prog,
+                               const double *__restrict__ theta, long long n_batch,
+                               long long ld, int H, int W, double *__restrict__ derived,
+                               int *__restrict__ psf_sel, double *__restrict__ wscale,
+                               float *__restrict__ rconst) {
+  const int ncomp = prog->n_components;
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_batch * ncomp) return;
+  long long b = gid / ncomp;
+  int c = (int)(gid - b * ncomp);
+  const double *th = theta + b * ld;
+  double *out = derived + (b * ncomp + c) * PSFMC_DERIVED_STRIDE;
+  const int kind = prog->kind[c];
+  const int flags = prog->flags[c];
+  if (c == 0) {
+    int sel = 0;
+    if (prog->psf_theta_index >= 0) {
+      double v = rint(th[prog->psf_theta_index]);
+      sel = (v >= 0.0 && v < (double)prog->n_psf) ? (int)v : -1;
+    } else {
+      double v = rint(prog->psf_value);
+      sel = (v >= 0.0 && v < (double)prog->n_psf) ? (int)v : -1;
+    }
+    psf_sel[b] = sel;
+    // Per-walker power-of-two scale for the raw^2 channel of the packed transform
+    // (z = raw + i * wscale * raw^2): with wscale ~ 1/flux both channels have
+    // comparable magnitude, so rounding errors of the large one do not swamp
+    // the small one. Exact (power of two), undone in the epilogue.
+    double ftot = 0.0;
+    for (int k = 0; k < ncomp; ++k) {
+      if (prog->kind[k] == PSFMC_SKY)
+        ftot += fabs(slot_value(prog, k, PSFMC_P_ADU, th));
+      else
+        ftot += mag_to_flux(slot_value(prog, k, PSFMC_P_MAG, th), prog->mag_zp);
+    }
+    double sc = 1.0;
+    if (isfinite(ftot) && ftot > 1e-300) {
+      int ex = 0;
+      frexp(ftot, &ex);             // ftot = m * 2^ex, m in [0.5, 1)
+      if (ex > 500) ex = 500;
+      if (ex < -500) ex = -500;
+      sc = ldexp(1.0, -ex);
+    }
+    wscale[b] = sc;
+  }
+  if (kind == PSFMC_SKY) {
+    out[D_SKY_ADU] = slot_value(prog, c, PSFMC_P_ADU, th);
+  } else if (kind == PSFMC_POINT) {
+    double x = slot_value(prog, c, PSFMC_P_X, th);
+    double y = slot_value(prog, c, PSFMC_P_Y, th);
+    double mag = slot_value(prog, c, PSFMC_P_MAG, th);
+    double radius = (flags & PSFMC_FLAG_BILINEAR) ? 0.5 : 3.0;
+    out[D_PS_X] = x;
+    out[D_PS_Y] = y;
+    out[D_PS_FLUX] = mag_to_flux(mag, prog->mag_zp);
+    stamp_bounds(y, radius, H, &out[D_PS_YMIN], &out[D_PS_YMAX]);
+    stamp_bounds(x, radius, W, &out[D_PS_XMIN], &out[D_PS_XMAX]);
+    // separable stamp weights (PointSource.py:40-56: kern = prod over (x, y) of
+    // lanczos(diff) or 1 - |diff|), measured from the UNCLIPPED position
+    for (int i = 0; i < 7; ++i) {
+      double px = out[D_PS_XMIN] + (double)i, py = out[D_PS_YMIN] + (double)i;
+      double wx = 0.0, wy = 0.0;
+      if (px <= out[D_PS_XMAX])
+        wx = (flags & PSFMC_FLAG_BILINEAR) ? 1.0 - fabs(px - x) : lanczos3_ref(px - x);
+      if (py <= out[D_PS_YMAX])
+        wy = (flags & PSFMC_FLAG_BILINEAR) ? 1.0 - fabs(py - y) : lanczos3_ref(py - y);
+      out[D_PS_WX + i] = wx;
+      out[D_PS_WY + i] = wy;
+    }
+  } else {  // PSFMC_SERSIC: Sersic.py:73-96 (transform), :47-71 (kappa, sb_eff)
+    double x0 = slot_value(prog, c, PSFMC_P_X, th);
+    double y0 = slot_value(prog, c, PSFMC_P_Y, th);
+    double mag = slot_value(prog, c, PSFMC_P_MAG, th);
+    double reff = slot_value(prog, c, PSFMC_P_REFF, th);
+    double reff_b = slot_value(prog, c, PSFMC_P_REFF_B, th);
+    double n = slot_value(prog, c, PSFMC_P_INDEX, th);
+    double angle = slot_value(prog, c, PSFMC_P_ANGLE, th);
+    if (flags & PSFMC_FLAG_ANGLE_DEGREES) angle = angle * (PSFMC_PI / 180.0);  // np.deg2rad
+    angle += 0.5 * PSFMC_PI;
+    double sn = sin(angle), cs = cos(angle);
+    double kappa = gammaincinv_half(2.0 * n);
+    double flux = mag_to_flux(mag, prog->mag_zp);
+    out[D_SER_X0] = x0;
+    out[D_SER_Y0] = y0;
+    out[D_SER_A00] = cs / reff;
+    out[D_SER_A01] = sn / reff;
+    out[D_SER_A10] = -sn / reff_b;
+    out[D_SER_A11] = cs / reff_b;
+    out[D_SER_P] = 0.5 / n;
+    out[D_SER_KAPPA] = kappa;
+    out[D_SER_SBEFF] = sersic_sb_eff(flux, n, reff, reff_b, kappa);
+  }
+  if (rconst) {
+    float *rc = rconst + (b * ncomp + c) * PSFMC_RC_STRIDE;
+    if (kind == PSFMC_SKY) {
+      rc[0] = (float)out[D_SKY_ADU];
+    } else if (kind == PSFMC_SERSIC) {
+      SersicF32 s = make_sersic_f32(out);
+      rc[0] = s.xi; rc[1] = s.xf; rc[2] = s.yi; rc[3] = s.yf;
+      rc[4] = s.a00; rc[5] = s.a01; rc[6] = s.a10; rc[7] = s.a11;
+      rc[8] = s.p; rc[9] = s.c0; rc[10] = s.c1; rc[11] = s.kq;
+    }
+  }
+}
+
+// ------------------------------------------------------------ pixel math --
+
+// float64: the reference's expressions, literally (Sersic.py:124-133,151-153).
+__device__ __forceinline__ double sersic_pixel(const double *d, double x, double y) {
+  double dx = x - d[D_SER_X0], dy = y - d[D_SER_Y0];
+  double u = d[D_SER_A00] * dx + d[D_SER_A01] * dy;
+  double v = d[D_SER_A10] * dx + d[D_SER_A11] * dy;
+  double sq = u * u + v * v;
+  double sdr = sq / (dx * dx + dy * dy);
+  double p = d[D_SER_P], kappa = d[D_SER_KAPPA];
+  double lg = log(sq);
+  double sb = exp(-kappa * expm1(lg * p));
+  double g = -kappa * 2.0 * p * exp(lg * (p - 0.5));
+  double cent = sdr / 12.0 * g;
+  return d[D_SER_SBEFF] * sb * (1.0 + g * cent);
+}
+
+// Point-source stamp value at pixel (x, y); 0 outside the stamp
+// (PointSource.py:40-56): (w_x * w_y) * flux with the separable weights the
+// prepare kernel tabulated. Always float64: at most 49 pixels per source.
+__device__ __forceinline__ double point_pixel(const double *d, int x, int y) {
+  const int ix = x - (int)d[D_PS_XMIN], iy = y - (int)d[D_PS_YMIN];
+  if (ix < 0 || iy < 0 || (double)x > d[D_PS_XMAX] || (double)y > d[D_PS_YMAX]) return 0.0;
+  return (d[D_PS_WX + ix] * d[D_PS_WY + iy]) * d[D_PS_FLUX];
+}
+
+// Raw model at one pixel in float64 (PSFMC_PREC_FP64), components added in model
+// order. round_f32: round the running sum to float32 after every component, i.e.
+// the reference's float32 `arr +=` storage (PSFMC_PREC_FP64_RAWF32, oracle M2).
+// ps_only: only point sources (models.py:296-306).
+__device__ __forceinline__ double raw_pixel_f64(const Program *prog, const double *derived_b,
+                                                int x, int y, bool round_f32,
+                                                bool ps_only) {
+  double acc = 0.0;
+  const int ncomp = prog->n_components;
+  for (int c = 0; c < ncomp; ++c) {
+    const double *d = derived_b + c * PSFMC_DERIVED_STRIDE;
+    const int kind = prog->kind[c];
+    if (ps_only && kind != PSFMC_POINT) continue;
+    if (kind == PSFMC_SKY) {
+      acc += d[D_SKY_ADU];
+    } else if (kind == PSFMC_POINT) {
+      double w = point_pixel(d, x, y);
+      // pixels outside the stamp are not touched by the reference's slice `+=`
+      if ((double)y >= d[D_PS_YMIN] && (double)y <= d[D_PS_YMAX] &&
+          (double)x >= d[D_PS_XMIN] && (double)x <= d[D_PS_XMAX])
+        acc += w;
+    } else {
+      acc += sersic_pixel(d, (double)x, (double)y);
+    }
+    if (round_f32) acc = (double)(float)acc;
+  }
+  return acc;
 }
 
 }  // namespace psfmc

@@ -71,9 +71,16 @@ struct State {
     int departed = 0;
     unsigned long long gen = 0;
     unsigned long long gen2 = 0;
+    int sync_count = 0;
+    unsigned long long sync_gen = 0;
     int live = 0;
   };
   std::vector<Warp> warps;
+  struct Named {
+    int count = 0;
+    unsigned long long gen = 0;
+  };
+  std::vector<Named> named;
   int live = 0;
   unsigned long long progress = 0;
 };
@@ -125,6 +132,31 @@ inline void warp_barrier(State::Warp &w, int &count, unsigned long long &gen) {
   st.cur->wait_kind = 0;
 }
 
+// __syncwarp: fibers of a warp do not run in lockstep, so this is a real barrier
+inline void syncwarp() {
+  State &st = S();
+  State::Warp &w = st.warps[st.cur->linear / 32];
+  warp_barrier(w, w.sync_count, w.sync_gen);
+}
+
+// bar.sync id, nthreads: named barrier over `nthreads` threads of the CTA
+inline void named_barrier(int id, int nthreads) {
+  State &st = S();
+  if ((int)st.named.size() <= id) st.named.resize(id + 1);
+  State::Named &nb = st.named[id];
+  unsigned long long gen = nb.gen;
+  nb.count++;
+  if (nb.count >= nthreads) {
+    nb.count = 0;
+    nb.gen++;
+    st.progress++;
+    return;
+  }
+  st.cur->wait_kind = 3;
+  while (nb.gen == gen) yield_to_sched();
+  st.cur->wait_kind = 0;
+}
+
 // all live lanes of the warp publish `bytes` of data, then read lane `src`
 // (two warp-wide barriers per exchange: publish, then consume).
 inline void warp_exchange(const void *mine, void *out, int bytes, int src_lane) {
@@ -153,6 +185,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F &&body) {
         st.bid = uint3{bx, by, bz};
         st.live = nthreads;
         st.bar_count = 0;
+        st.named.clear();
         st.warps.assign((nthreads + 31) / 32, State::Warp());
         // poison shared memory so that reads of unwritten smem show up as NaNs
         std::memset(st.smem.data(), 0xFF, st.smem.size());
@@ -206,9 +239,7 @@ inline unsigned char *dyn_smem() {
 #define blockDim (emu::S().block)
 #define gridDim (emu::S().grid)
 #define __syncthreads() emu::syncthreads()
-#define __syncwarp(...) \
-  do {                  \
-  } while (0)
+#define __syncwarp(...) emu::syncwarp()
 
 template <typename T>
 inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
@@ -252,6 +283,7 @@ inline float atomicAdd(float *p, float v) { float o = *p; *p += v; return o; }
 inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p += v; return o; }
 inline void __threadfence() {}
+inline void __threadfence_block() {}
 
 inline void sincospi(double x, double *s, double *c) {
   // exact at multiples of 1/2 like the CUDA function

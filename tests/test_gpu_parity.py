@@ -46,6 +46,23 @@ def test_c1_fp32_within_stated_tolerance(cuda_library, c1_golden):
     assert_lnl_close(got32, c1_golden['lnl']['M2'], 'fp32', bounds)
 
 
+def test_c1_fused_and_staged_paths_agree(cuda_library, c1_golden, monkeypatch):
+    """128^2 float32 runs the fused shared-memory kernel; forcing the staged
+    row/column kernels must give the same lnL within the float32 tolerance."""
+    thetas = np.array(c1_golden['theta'])
+    fused = model_from_file('j0005/model_c1.py', 'fp32', obs_dtype=np.float64)
+    assert fused.engine.info()['path'] == 1
+    got_fused = fused.log_likelihood_batch(thetas)
+    monkeypatch.setenv('PSFMC_FORCE_STAGED', '1')
+    staged = model_from_file('j0005/model_c1.py', 'fp32', obs_dtype=np.float64)
+    assert staged.engine.info()['path'] == 0
+    got_staged = staged.log_likelihood_batch(thetas)
+    bounds = fp32_bounds(fused, thetas)
+    assert_lnl_close(got_fused, c1_golden['lnl']['M3'], 'fp32', bounds)
+    assert_lnl_close(got_staged, c1_golden['lnl']['M3'], 'fp32', bounds)
+    assert_lnl_close(got_fused, got_staged, 'fp32', 2 * bounds)
+
+
 def test_c1_rawf32_mode_tracks_reference_m2(cuda_library, c1_golden):
     """float32 raw-model storage + float64 FFT/tail = the reference on numpy 1.x
     with float32 FITS inputs. A float32 rounding may flip where the float64 value
