@@ -40,8 +40,8 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c1', choices=['c1', 'c3', 'c4', 's128'])
     ap.add_argument('--walkers', type=int, default=0,
@@ -158,55 +158,79 @@ def time_cpu_port(workload, thetas, seconds):
 # ------------------------------------------------------------------- clocks --
 
 class ClockSampler(object):
-    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-             'clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock / power / throttle reasons sampled every few milliseconds through
+    NVML (nvidia_ml_py) while the benchmark runs; `mark()` / `stop()` delimit the
+    samples that fall inside the timed region."""
+    REASONS = (('hw_slowdown', 'nvmlClocksEventReasonHwSlowdown', 0x8),
+               ('hw_thermal_slowdown', 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+               ('sw_thermal_slowdown', 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+               ('sw_power_cap', 'nvmlClocksEventReasonSwPowerCap', 0x4))
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.004):
         self.samples = []
-        self.proc = None
+        self.period = period
+        self.running = False
+        self.t_mark = None
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                universal_newlines=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.running = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+        except Exception as exc:                      # no NVML: report, do not fail
+            self.nvml = None
+            self.error = repr(exc)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            parts = [p.strip() for p in line.split(',')]
-            if len(parts) >= 7:
-                self.samples.append(parts)
+    def _reasons(self):
+        nvml = self.nvml
+        for name in ('nvmlDeviceGetCurrentClocksEventReasons',
+                     'nvmlDeviceGetCurrentClocksThrottleReasons'):
+            func = getattr(nvml, name, None)
+            if func is not None:
+                try:
+                    return int(func(self.handle))
+                except Exception:
+                    continue
+        return 0
+
+    def _loop(self):
+        nvml = self.nvml
+        while self.running:
+            try:
+                sm = nvml.nvmlDeviceGetClockInfo(self.handle, nvml.NVML_CLOCK_SM)
+                power = nvml.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((time.perf_counter(), sm, power, self._reasons()))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for parts in self.samples:
-            try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
-                power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, flag in zip(names, parts[3:7]):
-                if flag.lower().startswith('active'):
+        if self.nvml is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['NVML unavailable']}
+        t_end = time.perf_counter()
+        self.running = False
+        self.thread.join(timeout=1.0)
+        inside = [smp for smp in self.samples
+                  if self.t_mark is None or self.t_mark <= smp[0] <= t_end]
+        where = 'timed region'
+        if len(inside) < 3:       # very short region: use every sample taken under load
+            inside, where = self.samples, 'warm-up + timed region'
+        reasons = set()
+        for _, _, _, mask in inside:
+            for name, _, bit in self.REASONS:
+                if mask & bit:
                     reasons.add(name)
-        busy = [v for v in sm if v > 0.5 * max(sm)] if sm else []
-        return {'sm_mhz': float(np.median(busy)) if busy else None,
-                'sm_max_mhz': max(smax) if smax else None,
-                'power_w_max': max(power) if power else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+        clocks = [smp[1] for smp in inside]
+        return {'sm_mhz': float(np.median(clocks)) if clocks else None,
+                'sm_max_mhz': float(self.sm_max),
+                'power_w_max': max([smp[2] for smp in inside]) if inside else None,
+                'samples': len(inside), 'window': where, 'reasons': sorted(reasons)}
 
 
 # ------------------------------------------------------------------ our arm --
@@ -270,15 +294,18 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local)
     for s in range(max(args.warmup, 3)):
         step_device(s)
         step_host(s)
     torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`) -------------------------------
-    sampler = ClockSampler(local)
     launches0 = engine.info()['launches_total']
+    engine.profile(True)
+    engine.profile_read()
     barrier()
+    sampler.mark()
     total_ms = 0.0
     for s in range(args.steps):
         flush.fill_(s & 0xFF)                  # evict L2 between timed steps
@@ -292,6 +319,9 @@ def run_ours(args):
     barrier()
     launches = engine.info()['launches_total'] - launches0
     clocks = sampler.stop()
+    kernel_ms, kernel_launches = engine.profile_read()
+    engine.profile(False)
+    total_ms_local = total_ms
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps
     value = world * walkers / (ms_per_step * 1e-3)
@@ -322,27 +352,46 @@ def run_ours(args):
                 peaks = json.load(fobj)
         except (OSError, ValueError):
             pass
-        evals_per_s_per_gpu = value / world
-        achieved = info['flops_per_eval'] * evals_per_s_per_gpu / 1e12
-        fft_achieved = info['fft_flops_per_eval'] * evals_per_s_per_gpu / 1e12
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        # dominant kernel: events around each launch on the launching stream
+        kernel_us = 1e3 * kernel_ms / max(kernel_launches, 1)
+        evals_per_launch = half
+        achieved = info['flops_per_eval'] * evals_per_launch / (kernel_us * 1e-6) / 1e12
+        fft_achieved = info['fft_flops_per_eval'] * evals_per_launch / (kernel_us * 1e-6) / 1e12
+        ncu = {}
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'r1_fused_ncu_summary.json')) as fobj:
+                ncu = json.load(fobj)
+        except (OSError, ValueError):
+            pass
+        fused = info['path'] == 1
+        traffic = ncu.get('dram_bytes_per_launch') if (fused and args.workload == 'c1') else None
         roofline = {
             'bound': 'fp32',
             'achieved': round(achieved, 3), 'peak': round(peak_probe, 2),
             'unit': 'TFLOP/s', 'frac': round(achieved / peak_probe, 4),
-            'traffic': None,
-            'note': 'FP32 CUDA-core bound path (north_star: no tensor cores); '
-                    'achieved = (10 N log2 N + (30 n_sersic + 16) N) FLOP/eval x evals/s '
-                    'per GPU over the device-timed step; peak = FP32 FMA probe '
-                    'measured in this run (MEASURED_PEAKS.json has no FP32 entry)',
+            'traffic': traffic,
+            'kernel': 'fused_lnlike_kernel' if fused else 'rows_fwd + cols + rows_inv',
+            'kernel_us_per_launch': round(kernel_us, 2),
+            'kernel_launches_timed': int(kernel_launches),
+            'evals_per_launch': evals_per_launch,
+            'kernel_share_of_step': round(kernel_ms / total_ms_local, 4),
+            'note': 'FP32 CUDA-core bound path (north_star: no tensor cores; SURVEY.md 8d). '
+                    'achieved = (10 N log2 N + (30 n_sersic + 16) N) FLOP/eval x evals per '
+                    'launch / mean launch duration of the dominant kernel (CUDA events on the '
+                    'launching stream inside the timed region); peak = FP32 FMA throughput '
+                    'probed in this run (MEASURED_PEAKS.json has no FP32 entry). FFT '
+                    'butterflies are mostly adds, so the practical ceiling of this path is '
+                    'about half of the FMA peak (DESIGN.md).',
             'fft_stage_achieved': round(fft_achieved, 3),
             'fft_stage_frac': round(fft_achieved / peak_probe, 4),
             'flops_per_eval': info['flops_per_eval'],
-            'hbm': {'achieved': round(info['hbm_bytes_per_eval'] * evals_per_s_per_gpu / 1e9, 2),
+            'hbm': {'achieved': round(info['hbm_bytes_per_eval'] * evals_per_launch
+                                      / (kernel_us * 1e-6) / 1e9, 2),
                     'peak': hbm_peak, 'unit': 'GB/s',
                     'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
                     'bytes_per_eval': info['hbm_bytes_per_eval']},
-            'engine_path': 'fused' if info['path'] == 1 else 'staged',
+            'engine_path': 'fused' if fused else 'staged',
         }
         result = {
             'metric': METRIC, 'value': round(value, 1), 'unit': UNIT,

@@ -161,6 +161,15 @@ typedef struct psfmc_info {
 } psfmc_info;
 int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info);
 
+/* Device-side timing of the dominant kernel of the lnL path (the fused kernel, or
+ * the three staged row/column kernels together): when enabled, every launch is
+ * bracketed by CUDA events on the stream it is launched on. psfmc_engine_profile_read
+ * synchronises, returns the summed duration (ms) and the number of launches since
+ * the last read, and resets both. For bench.py's roofline; off by default. */
+int psfmc_engine_profile(psfmc_engine *engine, int32_t enable);
+int psfmc_engine_profile_read(psfmc_engine *engine, double *kernel_ms_out,
+                              int64_t *kernel_launches_out);
+
 /* Measured FP32 FMA throughput of one device (TFLOP/s, FMA = 2 FLOP): the
  * denominator of the FP32 roofline (MEASURED_PEAKS.json has no FP32 entry). */
 int psfmc_fp32_peak_probe(int32_t device, double *tflops_out, double *ms_out);

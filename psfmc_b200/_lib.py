@@ -72,6 +72,7 @@ class Info(ctypes.Structure):
 EXPORTED_SYMBOLS = (
     'psfmc_engine_create', 'psfmc_engine_destroy', 'psfmc_lnlike_batch',
     'psfmc_lnlike_batch_device', 'psfmc_render_batch', 'psfmc_engine_info',
+    'psfmc_engine_profile', 'psfmc_engine_profile_read',
     'psfmc_fp32_peak_probe', 'psfmc_last_error', 'psfmc_abi_version',
 )
 
@@ -124,6 +125,11 @@ def load(path=None):
                                        ctypes.c_int64, ctypes.c_uint32, dbl_p]
     lib.psfmc_engine_info.restype = ctypes.c_int
     lib.psfmc_engine_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(Info)]
+    lib.psfmc_engine_profile.restype = ctypes.c_int
+    lib.psfmc_engine_profile.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    lib.psfmc_engine_profile_read.restype = ctypes.c_int
+    lib.psfmc_engine_profile_read.argtypes = [ctypes.c_void_p, dbl_p,
+                                              ctypes.POINTER(ctypes.c_int64)]
     lib.psfmc_fp32_peak_probe.restype = ctypes.c_int
     lib.psfmc_fp32_peak_probe.argtypes = [ctypes.c_int32, dbl_p, dbl_p]
     if lib.psfmc_abi_version() != ABI_VERSION:

@@ -12,7 +12,7 @@
 #define PSFMC_HD
 #else
 #include <cuda_runtime.h>
-#define PSFMC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define PSFMC_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #define PSFMC_HD __host__ __device__
 #endif
 
@@ -60,6 +60,109 @@ template <typename T>
 __device__ __forceinline__ cplx<T> mul_pos_i(cplx<T> a) {
   return mk<T>(-a.y, a.x);
 }
+
+// Generic conjugate multiply a * conj(w) and constant rotations a * (c -+ i s);
+// float32 has packed implementations below.
+template <typename T>
+__device__ __forceinline__ cplx<T> cmul_conj(cplx<T> a, cplx<T> w) {
+  return mk<T>(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+}
+template <typename T, bool INV>
+__device__ __forceinline__ cplx<T> crot(cplx<T> a, T c, T s) {   // a * (c - i s), inverse: (c + i s)
+  return INV ? mk<T>(a.x * c - a.y * s, a.y * c + a.x * s)
+             : mk<T>(a.x * c + a.y * s, a.y * c - a.x * s);
+}
+template <typename T>
+__device__ __forceinline__ cplx<T> cscale(cplx<T> a, T f) {
+  return mk<T>(a.x * f, a.y * f);
+}
+
+// Element-wise pair arithmetic (a cplx<T> used as a plain pair of values).
+template <typename T>
+__device__ __forceinline__ cplx<T> pmul(cplx<T> a, cplx<T> b) {
+  return mk<T>(a.x * b.x, a.y * b.y);
+}
+template <typename T>
+__device__ __forceinline__ cplx<T> pfma(cplx<T> a, cplx<T> b, cplx<T> c) {
+  return mk<T>(a.x * b.x + c.x, a.y * b.y + c.y);
+}
+template <typename T>
+__device__ __forceinline__ cplx<T> bcast(T a) {
+  return mk<T>(a, a);
+}
+
+#ifndef PSFMC_EMU
+// ---- packed float32 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2) ----------------
+// A complex64 value is one 64-bit register pair, so complex add/sub is ONE packed
+// instruction and a complex multiply is two (ptxas folds the pack/unpack moves,
+// swaps and per-half sign flips into operand modifiers). The packed forms issue at
+// half the rate of the scalar ones (same FLOP/s) but take half the issue slots,
+// which is what this issue-bound path needs (profiles/microbench/pipe_probe.cu).
+typedef unsigned long long u64_t;
+__device__ __forceinline__ u64_t pk2(float a, float b) {
+  u64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ cplx<float> upk2(u64_t v) {
+  cplx<float> r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ u64_t add2(u64_t a, u64_t b) {
+  u64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64_t mul2(u64_t a, u64_t b) {
+  u64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64_t fma2(u64_t a, u64_t b, u64_t c) {
+  u64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ cplx<float> operator+(cplx<float> a, cplx<float> b) {
+  return upk2(add2(pk2(a.x, a.y), pk2(b.x, b.y)));
+}
+__device__ __forceinline__ cplx<float> operator-(cplx<float> a, cplx<float> b) {
+  return upk2(add2(pk2(a.x, a.y), pk2(-b.x, -b.y)));
+}
+__device__ __forceinline__ cplx<float> operator*(cplx<float> a, cplx<float> w) {
+  const cplx<float> r = upk2(mul2(pk2(a.y, a.y), pk2(w.y, w.x)));   // (a.y w.y, a.y w.x)
+  return upk2(fma2(pk2(a.x, a.x), pk2(w.x, w.y), pk2(-r.x, r.y)));
+}
+template <>
+__device__ __forceinline__ cplx<float> cmul_conj<float>(cplx<float> a, cplx<float> w) {
+  const cplx<float> r = upk2(mul2(pk2(a.x, a.x), pk2(w.x, w.y)));   // (a.x w.x, a.x w.y)
+  return upk2(fma2(pk2(a.y, a.y), pk2(w.y, w.x), pk2(r.x, -r.y)));
+}
+template <>
+__device__ __forceinline__ cplx<float> crot<float, false>(cplx<float> a, float c, float s) {
+  const cplx<float> r = upk2(mul2(pk2(a.x, a.x), pk2(c, s)));       // (a.x c, a.x s)
+  return upk2(fma2(pk2(a.y, a.y), pk2(s, c), pk2(r.x, -r.y)));
+}
+template <>
+__device__ __forceinline__ cplx<float> crot<float, true>(cplx<float> a, float c, float s) {
+  const cplx<float> r = upk2(mul2(pk2(a.y, a.y), pk2(s, c)));       // (a.y s, a.y c)
+  return upk2(fma2(pk2(a.x, a.x), pk2(c, s), pk2(-r.x, r.y)));
+}
+template <>
+__device__ __forceinline__ cplx<float> cscale<float>(cplx<float> a, float f) {
+  return upk2(mul2(pk2(a.x, a.y), pk2(f, f)));
+}
+template <>
+__device__ __forceinline__ cplx<float> pmul<float>(cplx<float> a, cplx<float> b) {
+  return upk2(mul2(pk2(a.x, a.y), pk2(b.x, b.y)));
+}
+template <>
+__device__ __forceinline__ cplx<float> pfma<float>(cplx<float> a, cplx<float> b,
+                                                   cplx<float> c) {
+  return upk2(fma2(pk2(a.x, a.y), pk2(b.x, b.y), pk2(c.x, c.y)));
+}
+#endif
 
 // --------------------------------------------------------- derived params --
 // Per-walker, per-component constants produced by the prepare kernel (always in

@@ -102,6 +102,9 @@ struct DeviceState {
   cplx<float> *fspec = nullptr, *fspecx = nullptr;
   float2 *fow = nullptr;
   int n_sms = 148;
+  // optional event pairs around the dominant kernel(s) of every lnL call
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
   DevBuf<cplx<T>> scratch;
   DevBuf<T> img[4];
   PinBuf<double> theta_pin, lnl_pin;
@@ -112,6 +115,8 @@ struct DeviceState {
 
 struct EngineBase {
   virtual ~EngineBase() {}
+  virtual int profile_read(double *ms, long long *count) = 0;
+  bool profiling = false;
   virtual int lnlike_host(const double *theta, long long B, long long ld, double *out) = 0;
   virtual int lnlike_device(int slot, const double *theta, long long B, long long ld,
                             double *lnl, void *stream) = 0;
@@ -157,8 +162,45 @@ struct Engine : EngineBase {
       d.theta_pin.release();
       d.lnl_pin.release();
       d.img_pin.release();
+      for (auto &ev : d.prof_events) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+      }
       if (d.stream) cudaStreamDestroy(d.stream);
     }
+  }
+
+  // next free event pair of the device (grows on demand)
+  int prof_pair(DeviceState<T> &d, cudaEvent_t *e0, cudaEvent_t *e1) {
+    if (d.prof_used == d.prof_events.size()) {
+      cudaEvent_t a, b;
+      CUDA_TRY(cudaEventCreate(&a));
+      CUDA_TRY(cudaEventCreate(&b));
+      d.prof_events.push_back(std::make_pair(a, b));
+    }
+    *e0 = d.prof_events[d.prof_used].first;
+    *e1 = d.prof_events[d.prof_used].second;
+    ++d.prof_used;
+    return 0;
+  }
+
+  int profile_read(double *ms, long long *count) override {
+    double total = 0.0;
+    long long n = 0;
+    for (auto &d : devs) {
+      CUDA_TRY(cudaSetDevice(d.ordinal));
+      for (size_t k = 0; k < d.prof_used; ++k) {
+        float one = 0.f;
+        CUDA_TRY(cudaEventSynchronize(d.prof_events[k].second));
+        CUDA_TRY(cudaEventElapsedTime(&one, d.prof_events[k].first, d.prof_events[k].second));
+        total += one;
+        ++n;
+      }
+      d.prof_used = 0;
+    }
+    *ms = total;
+    *count = n;
+    return 0;
   }
 
   StagedBuffers<T> buffers(DeviceState<T> &d) {
@@ -212,14 +254,18 @@ struct Engine : EngineBase {
       fb.specx = d.fspecx;
       fb.ow = d.fow;
       fb.n_sms = d.n_sms;
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (profiling && (rc = prof_pair(d, &e0, &e1))) return rc;
       launches += launch_fused_lnlike<T>(plan, buf, fb, prog_h, theta_dev, B, ld, lnl_dev,
-                                         stream);
+                                         stream, e0, e1);
       CUDA_TRY(cudaGetLastError());
       return 0;
     }
 #endif
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (profiling && (rc = prof_pair(d, &e0, &e1))) return rc;
     launch_staged_lnlike<T>(plan, buf, prog_h.n_components, precision, theta_dev, B, ld,
-                            lnl_dev, stream);
+                            lnl_dev, stream, false, nullptr, -1, e0, e1);
     launches += count_launches<T>(plan, B);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -613,8 +659,12 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       }
       cudaDeviceGetAttribute(&ds.n_sms, cudaDevAttrMultiProcessorCount, ds.ordinal);
       if (ds.n_sms < 1) ds.n_sms = 148;
+      if (const char *env = getenv("PSFMC_FUSED_CTAS")) {   // tests: force walker loops
+        int v = atoi(env);
+        if (v > 0) ds.n_sms = v;
+      }
       const size_t N = PSFMC_FUSED_N;
-      std::vector<cplx<float>> fspec((size_t)d->n_psf * N * N), fspecx((size_t)d->n_psf * 2 * N);
+      std::vector<cplx<float>> fspec((size_t)d->n_psf * N * N), fspecx((size_t)d->n_psf * 4 * N);
       std::vector<double> vs(d->n_psf);
       for (int k = 0; k < d->n_psf; ++k) vs[k] = 1.0 / vscale_inv[k];
       fused_spectrum_layout(spec64.data(), d->n_psf, vs.data(), fspec.data(), fspecx.data());
@@ -757,6 +807,27 @@ int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info) {
   info->kernels_per_call = e->path == 1 ? 2 : 5;
   info->launches_total = e->launches;
   return 0;
+}
+
+int psfmc_engine_profile(psfmc_engine *engine, int32_t enable) {
+  if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
+  engine->impl->profiling = enable != 0;
+  return 0;
+}
+
+int psfmc_engine_profile_read(psfmc_engine *engine, double *kernel_ms_out,
+                              int64_t *kernel_launches_out) {
+  if (!engine || !engine->impl || !kernel_ms_out || !kernel_launches_out)
+    return fail(PSFMC_ERR_INVALID_ARG, "null argument");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  double ms = 0.0;
+  long long n = 0;
+  int rc = engine->impl->profile_read(&ms, &n);
+  cudaSetDevice(prev);
+  *kernel_ms_out = ms;
+  *kernel_launches_out = n;
+  return rc;
 }
 
 int psfmc_fp32_peak_probe(int32_t device, double *tflops_out, double *ms_out) {

@@ -46,15 +46,10 @@ __device__ __forceinline__ void dft8(cplx<T> *v) {
   cplx<T> a1 = v[1] + v[5], b1 = v[1] - v[5];
   cplx<T> a2 = v[2] + v[6], b2 = v[2] - v[6];
   cplx<T> a3 = v[3] + v[7], b3 = v[3] - v[7];
-  if (!INV) {
-    b1 = mk<T>(h * (b1.x + b1.y), h * (b1.y - b1.x));    // * (1 - i)/sqrt2
-    b2 = mul_neg_i(b2);                                   // * -i
-    b3 = mk<T>(h * (b3.y - b3.x), -h * (b3.x + b3.y));   // * (-1 - i)/sqrt2
-  } else {
-    b1 = mk<T>(h * (b1.x - b1.y), h * (b1.x + b1.y));    // * (1 + i)/sqrt2
-    b2 = mul_pos_i(b2);                                   // * +i
-    b3 = mk<T>(-h * (b3.x + b3.y), h * (b3.x - b3.y));   // * (-1 + i)/sqrt2
-  }
+  // W8^1, W8^2, W8^3 (conjugated for the inverse)
+  b1 = crot<T, INV>(b1, h, h);
+  b2 = INV ? mul_pos_i(b2) : mul_neg_i(b2);
+  b3 = crot<T, INV>(b3, -h, h);
   dft4<T, INV>(a0, a1, a2, a3);
   dft4<T, INV>(b0, b1, b2, b3);
   v[0] = a0; v[1] = b0; v[2] = a1; v[3] = b1;

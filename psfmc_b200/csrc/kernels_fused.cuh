@@ -47,7 +47,8 @@ struct FusedParams {
   const int *psf_sel;        // [B]
   const double *vscale_inv;  // [K]
   const cplx<float> *spec;   // [K][ky=128][c=128], see fused_spectrum_layout()
-  const cplx<float> *specx;  // [K][2][ky=128]: P[ky][kx=64], V[ky][kx=64]
+  const cplx<float> *specx;  // [K][2 (P,V)][2][ky=128]: (S0+S64)/2 and (S0-S64)/2 of the
+                             // packed DC/Nyquist columns (S0 = kx 0, S64 = kx 64)
   const float2 *ow;          // [128*128]: (obs, bad ? -ovar : +ovar)
   double *lnl;               // [B]
   long long n_batch;
@@ -76,22 +77,16 @@ __device__ __forceinline__ void dft16(cplx<float> *v) {
   const float h = 0.70710678118654752440f;
 #pragma unroll
   for (int n2 = 0; n2 < 4; ++n2) dft4<float, INV>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
-  // v[4*k1 + n2] *= W16^(n2*k1)  (conjugated for the inverse)
-  const float sg = INV ? -1.0f : 1.0f;
-  auto rot = [&](cplx<float> &a, float c, float s) {   // a *= (c, -sg*s)
-    float x = a.x * c + sg * a.y * s, y = a.y * c - sg * a.x * s;
-    a.x = x;
-    a.y = y;
-  };
-  rot(v[4 * 1 + 1], C, S);        // e = 1
-  rot(v[4 * 1 + 2], h, h);        // e = 2
-  rot(v[4 * 1 + 3], S, C);        // e = 3
-  rot(v[4 * 2 + 1], h, h);        // e = 2
+  // v[4*k1 + n2] *= W16^(n2*k1) = (cos, -sin)(pi e / 8), conjugated for the inverse
+  v[4 * 1 + 1] = crot<float, INV>(v[4 * 1 + 1], C, S);     // e = 1
+  v[4 * 1 + 2] = crot<float, INV>(v[4 * 1 + 2], h, h);     // e = 2
+  v[4 * 1 + 3] = crot<float, INV>(v[4 * 1 + 3], S, C);     // e = 3
+  v[4 * 2 + 1] = crot<float, INV>(v[4 * 2 + 1], h, h);     // e = 2
   v[4 * 2 + 2] = INV ? mul_pos_i(v[4 * 2 + 2]) : mul_neg_i(v[4 * 2 + 2]);  // e = 4
-  rot(v[4 * 2 + 3], -h, h);       // e = 6
-  rot(v[4 * 3 + 1], S, C);        // e = 3
-  rot(v[4 * 3 + 2], -h, h);       // e = 6
-  rot(v[4 * 3 + 3], -C, -S);      // e = 9
+  v[4 * 2 + 3] = crot<float, INV>(v[4 * 2 + 3], -h, h);    // e = 6
+  v[4 * 3 + 1] = crot<float, INV>(v[4 * 3 + 1], S, C);     // e = 3
+  v[4 * 3 + 2] = crot<float, INV>(v[4 * 3 + 2], -h, h);    // e = 6
+  v[4 * 3 + 3] = crot<float, INV>(v[4 * 3 + 3], -C, -S);   // e = 9
 #pragma unroll
   for (int k1 = 0; k1 < 4; ++k1)
     dft4<float, INV>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
@@ -103,28 +98,60 @@ __device__ __forceinline__ void dft16(cplx<float> *v) {
   for (int k = 0; k < 16; ++k) v[k] = t[4 * (k & 3) + (k >> 2)];
 }
 
-// position (in complex elements) of exchange element (k1, n2) inside a row:
-// rotate n2 by k1 inside each block of 8 so that both the radix-16 side (fixed k1,
-// lanes over n2) and the radix-8 side (fixed n2, lanes over k1) are free of bank
-// conflicts; `swz` = 8 * (row parity) keeps two rows of a half-warp apart.
-__device__ __forceinline__ int xpos(int k1, int n2, int swz) {
-  return (k1 * 8 + ((n2 + k1) & 7)) ^ swz;
+// Shared-memory tile access by BYTE offset (32-bit address arithmetic; XOR swizzles
+// act directly on the address). Exchange layout of a row between its radix-16 and
+// radix-8 sides: element (k1, n2) of row y sits at complex position
+//     8 * (k1 ^ s) + (n2 ^ (k1 & 7)),   s = y & 1,
+// which is free of bank conflicts on both sides (fixed k1 / lanes over n2, and fixed
+// n2 / lanes over k1) and keeps the two rows of a half-warp on different banks.
+// All its fields are bit-disjoint, so the byte offset is (thread constant) XOR
+// (compile-time constant): one LOP3 per access.
+// The tile is 1024-byte aligned, so a row base plus a thread constant below 1024
+// can be XOR-ed with compile-time constants on the final address.
+#ifdef PSFMC_EMU
+typedef uintptr_t smem_addr_t;
+#else
+typedef unsigned smem_addr_t;
+#endif
+
+__device__ __forceinline__ cplx<float> lds64(smem_addr_t addr) {
+#ifdef PSFMC_EMU
+  return *reinterpret_cast<const cplx<float> *>(addr);
+#else
+  cplx<float> v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ void sts64(smem_addr_t addr, cplx<float> v) {
+#ifdef PSFMC_EMU
+  *reinterpret_cast<cplx<float> *>(addr) = v;
+#else
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+#endif
+}
+__device__ __forceinline__ smem_addr_t smem_base(unsigned char *ptr) {
+#ifdef PSFMC_EMU
+  return (smem_addr_t)ptr;
+#else
+  return (smem_addr_t)__cvta_generic_to_shared(ptr);
+#endif
 }
 
 // Raw model at the 16 pixels x = l + 8*j of row y -> packed z = raw + i*wsc*raw^2.
+// Pixels are rendered in pairs (j, j+1) with element-wise pair arithmetic.
 __device__ __forceinline__ void fused_render16(const FusedParams &P, long long b, int y,
                                                int l, float wsc, cplx<float> *v) {
-  float acc[16];
+  cplx<float> acc[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
-  const float fy = (float)y;
+  for (int i = 0; i < 8; ++i) acc[i] = mk<float>(0.0f, 0.0f);
   for (int c = 0; c < P.ncomp; ++c) {
     const int kind = P.kind[c];
     const float *rc = P.rconst + (b * P.ncomp + c) * PSFMC_RC_STRIDE;
     if (kind == PSFMC_SKY) {
-      const float adu = __ldg(rc);
+      const cplx<float> adu = bcast(__ldg(rc));
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] += adu;
+      for (int i = 0; i < 8; ++i) acc[i] = acc[i] + adu;
     } else if (kind == PSFMC_SERSIC) {
       SersicF32 s;
       const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rc));
@@ -133,128 +160,256 @@ __device__ __forceinline__ void fused_render16(const FusedParams &P, long long b
       s.xi = q0.x; s.xf = q0.y; s.yi = q0.z; s.yf = q0.w;
       s.a00 = q1.x; s.a01 = q1.y; s.a10 = q1.z; s.a11 = q1.w;
       s.p = q2.x; s.c0 = q2.y; s.c1 = q2.z; s.kq = q2.w;
+      const float dy = ((float)y - s.yi) - s.yf;
+      const float cu = s.a01 * dy, cv = s.a11 * dy, dy2 = dy * dy;
+      // (l - xi) and 8*j are exact in float32, so dx0 + 8*j == (x - xi) - xf to 1 ulp
+      const float dx0 = ((float)l - s.xi) - s.xf;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] += sersic_pixel_f32(s, (float)(l + 8 * j), fy);
+      for (int i = 0; i < 8; ++i) {
+        const cplx<float> dx = mk<float>(dx0 + (float)(16 * i), dx0 + (float)(16 * i + 8));
+        acc[i] = acc[i] + sersic_pair_f32(s, dx, cu, cv, dy2);
+      }
     } else {  // point source: at most 7 x 7 pixels of the frame, float64 taps
       const double *d = P.derived + (b * P.ncomp + c) * PSFMC_DERIVED_STRIDE;
       const int ymin = (int)__ldg(d + D_PS_YMIN), ymax = (int)__ldg(d + D_PS_YMAX);
       if (y >= ymin && y <= ymax) {
         const int xmin = (int)__ldg(d + D_PS_XMIN), xmax = (int)__ldg(d + D_PS_XMAX);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int x = l + 8 * j;
-          if (x >= xmin && x <= xmax) acc[j] += (float)point_pixel(d, x, y);
+        for (int i = 0; i < 8; ++i) {
+          const int x = l + 16 * i;
+          if (x >= xmin && x <= xmax) acc[i].x += (float)point_pixel(d, x, y);
+          if (x + 8 >= xmin && x + 8 <= xmax) acc[i].y += (float)point_pixel(d, x + 8, y);
         }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = mk<float>(acc[j], acc[j] * acc[j] * wsc);
+  for (int i = 0; i < 8; ++i) {
+    const cplx<float> sq = pmul(pmul(acc[i], acc[i]), bcast(wsc));
+    v[2 * i] = mk<float>(acc[i].x, sq.x);
+    v[2 * i + 1] = mk<float>(acc[i].y, sq.y);
+  }
 }
 
 // Special (packed DC/Nyquist) columns: U = FFT(p + i q) of two real sequences that
 // are multiplied by different spectra S0 (for p) and S64 (for q):
 //   U'[ky] = U[ky] (S0+S64)/2 + conj(U[-ky]) (S0-S64)/2, spectra taken at ky.
+// sx points at the host-prepared half-sum / half-difference tables [2][128].
 __device__ __forceinline__ void special_pair(cplx<float> &u, cplx<float> &um,
-                                             cplx<float> s0u, cplx<float> s64u,
-                                             cplx<float> s0m, cplx<float> s64m) {
-  const cplx<float> pu = mk<float>(0.5f * (s0u.x + s64u.x), 0.5f * (s0u.y + s64u.y));
-  const cplx<float> du = mk<float>(0.5f * (s0u.x - s64u.x), 0.5f * (s0u.y - s64u.y));
-  const cplx<float> pm = mk<float>(0.5f * (s0m.x + s64m.x), 0.5f * (s0m.y + s64m.y));
-  const cplx<float> dm = mk<float>(0.5f * (s0m.x - s64m.x), 0.5f * (s0m.y - s64m.y));
-  const cplx<float> nu = u * pu + cconj(um) * du;
-  const cplx<float> nm = um * pm + cconj(u) * dm;
+                                             const cplx<float> *sx, int ky, int kym) {
+  const cplx<float> nu = u * sx[ky] + cmul_conj(sx[PSFMC_FUSED_N + ky], um);
+  const cplx<float> nm = um * sx[kym] + cmul_conj(sx[PSFMC_FUSED_N + kym], u);
   u = nu;
   um = nm;
+}
+
+// Per-thread constants of the row passes (4 rows per warp, 8 threads per row).
+struct RowRole {
+  int w, rr, l;
+  bool l0;
+  unsigned t16;     // radix-16 side of the exchange layout: (8 l) ^ (64 s)
+  unsigned qa, qb;  // radix-8 side, for k1 = kA / kB: 64 (k ^ s) + 8 (k & 7)
+  unsigned fa, fb;  // column layout: 8 (k ^ 8 s)
+};
+
+// render + forward row transform + real-pair split of row batch `it` of walker b
+__device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_addr_t tile,
+                                                   const RowRole &R, const cplx<float> *tw,
+                                                   long long b, int it, float wsc) {
+  const int y = it * 64 + R.w * 4 + R.rr;
+  const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
+  {
+    cplx<float> v[16];
+    fused_render16(P, b, y, R.l, wsc, v);
+    dft16<false>(v);
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * tw[k1];
+    __syncwarp();   // every lane is done reading this row (previous walker)
+    const smem_addr_t rt = rb + R.t16;
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) sts64(rt ^ (unsigned)(64 * k1 + 8 * (k1 & 7)), v[k1]);
+  }
+  __syncwarp();
+  cplx<float> a[8], bb[8];
+  {
+    const smem_addr_t ra = rb + R.qa, rq = rb + R.qb;
+#pragma unroll
+    for (int n2 = 0; n2 < 8; ++n2) {
+      a[n2] = lds64(ra ^ (unsigned)(8 * n2));
+      bb[n2] = lds64(rq ^ (unsigned)(8 * n2));
+    }
+  }
+  __syncwarp();
+  dft8<float, false>(a);    // a[k2]  = Z[kA + 16 k2]
+  dft8<float, false>(bb);   // bb[k2] = Z[kB + 16 k2]
+  const bool l0 = R.l0;
+#pragma unroll
+  for (int k2 = 0; k2 < 4; ++k2) {
+    // row spectra of the two real images (the factor 1/2 of the split is folded
+    // into the PSF spectra):  A = Z[kx] + conj Z[-kx],  B = -i (Z[kx] - conj Z[-kx])
+    {  // kx = kA + 16 k2, partner -kx
+      const cplx<float> zk = a[k2];
+      const cplx<float> zp = l0 ? a[(8 - k2) & 7] : bb[7 - k2];
+      cplx<float> oa = zk + mk<float>(zp.x, -zp.y);
+      cplx<float> ob = mk<float>(zk.y, -zk.x) + mk<float>(zp.y, zp.x);
+      if (k2 == 0 && l0) {   // real DC / Nyquist columns, packed in pairs
+        oa = mk<float>(a[0].x, a[4].x);
+        ob = mk<float>(a[0].y, a[4].y);
+      }
+      sts64(rb + R.fa + 8 * 16 * k2, oa);
+      sts64(rb + R.fa + 8 * (64 + 16 * k2), ob);
+    }
+    {  // kx = kB + 16 k2
+      const cplx<float> zk = bb[k2];
+      const cplx<float> zp = l0 ? bb[7 - k2] : a[7 - k2];
+      sts64(rb + R.fb + 8 * 16 * k2, zk + mk<float>(zp.x, -zp.y));
+      sts64(rb + R.fb + 8 * (64 + 16 * k2), mk<float>(zk.y, -zk.x) + mk<float>(zp.y, zp.x));
+    }
+  }
+}
+
+// Hermitian rebuild + inverse row transform + chi-square terms of row batch `it`;
+// returns this thread's float64 partial sum over its 16 pixels.
+__device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_addr_t tile,
+                                                     const RowRole &R, const cplx<float> *tw,
+                                                     int it, float unscale) {
+  const int y = it * 64 + R.w * 4 + R.rr;
+  const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
+  const bool l0 = R.l0;
+  cplx<float> a[8], bb[8];
+  {
+    cplx<float> yd1[4], ym1[4], yd2[4], ym2[4];
+    cplx<float> a10, b10;
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      const cplx<float> a1 = lds64(rb + R.fa + 8 * 16 * k2);
+      const cplx<float> b1 = lds64(rb + R.fa + 8 * (64 + 16 * k2));
+      const cplx<float> a2 = lds64(rb + R.fb + 8 * 16 * k2);
+      const cplx<float> b2 = lds64(rb + R.fb + 8 * (64 + 16 * k2));
+      if (k2 == 0) {
+        a10 = a1;
+        b10 = b1;
+      }
+      // Y[kx] = A' + i B',  Y[-kx] = conj(A') + i conj(B')
+      yd1[k2] = a1 + mk<float>(-b1.y, b1.x);
+      ym1[k2] = mk<float>(a1.x, -a1.y) + mk<float>(b1.y, b1.x);
+      yd2[k2] = a2 + mk<float>(-b2.y, b2.x);
+      ym2[k2] = mk<float>(a2.x, -a2.y) + mk<float>(b2.y, b2.x);
+    }
+    // a[k2] = Y[kA + 16 k2], bb[k2] = Y[kB + 16 k2]; the upper halves are mirrored
+    // entries of the other set (of the same set for l = 0, where kA = 0, kB = 8)
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      a[k2] = yd1[k2];
+      bb[k2] = yd2[k2];
+      a[4 + k2] = l0 ? ym1[(4 - k2) & 3] : ym2[3 - k2];
+      bb[4 + k2] = l0 ? ym2[3 - k2] : ym1[3 - k2];
+    }
+    if (l0) {   // packed DC / Nyquist columns
+      a[0] = mk<float>(a10.x, b10.x);
+      a[4] = mk<float>(a10.y, b10.y);
+    }
+  }
+  __syncwarp();
+  dft8<float, true>(a);     // a[n2]
+  dft8<float, true>(bb);
+  {
+    const smem_addr_t ra = rb + R.qa, rq = rb + R.qb;
+#pragma unroll
+    for (int n2 = 0; n2 < 8; ++n2) {
+      sts64(ra ^ (unsigned)(8 * n2), a[n2]);
+      sts64(rq ^ (unsigned)(8 * n2), bb[n2]);
+    }
+  }
+  __syncwarp();
+  cplx<float> v[16];
+  {
+    const smem_addr_t rt = rb + R.t16;
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(rt ^ (unsigned)(64 * k1 + 8 * (k1 & 7)));
+  }
+  // observation + signed variance of this thread's 16 pixels
+  float2 o[16];
+  const float2 *owr = P.ow + y * PSFMC_FUSED_N + R.l;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], tw[k1]);
+  dft16<true>(v);           // v[j] = (convolved model, scaled model variance)
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float resid, ivm;
+    const double t = Epilogue<float>::term(v[j].x, v[j].y * unscale, o[j].x,
+                                           fabsf(o[j].y), &resid, &ivm);
+    if (__float_as_int(o[j].y) >= 0) acc += t;
+  }
+  return acc;
 }
 
 __global__ void __launch_bounds__(PSFMC_FUSED_THREADS, 1)
 fused_lnlike_kernel(const FusedParams P) {
   PSFMC_DYN_SMEM(smem_raw);
-  cplx<float> *tile = reinterpret_cast<cplx<float> *>(smem_raw);
+  const smem_addr_t tile = smem_base(smem_raw);
   __shared__ double red_s[PSFMC_FUSED_THREADS / 32];
   __shared__ int cnt_s;
   constexpr int N = PSFMC_FUSED_N;
+  constexpr unsigned ROWB = N * 8;   // bytes per tile row
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) cnt_s = 0;
-  __syncthreads();
 
-  // row-phase role: 4 rows per warp, 8 threads per row
-  const int rr = lane >> 3, l = lane & 7;
-  const bool l0 = (l == 0);
-  const int kA = l, kB = l0 ? 8 : 16 - l;
-  // column-phase role: column c, two of the eight n2 residues
+  // row-pass role
+  RowRole R;
+  R.w = w;
+  R.rr = lane >> 3;
+  R.l = lane & 7;
+  R.l0 = (R.l == 0);
+  {
+    const unsigned s = R.rr & 1;
+    const unsigned kA = R.l, kB = R.l0 ? 8 : 16 - R.l;
+    R.t16 = (8u * R.l) ^ (64u * s);
+    R.qa = 64u * (kA ^ s) + 8u * (kA & 7);
+    R.qb = 64u * (kB ^ s) + 8u * (kB & 7);
+    R.fa = 8u * (kA ^ (8u * s));
+    R.fb = 8u * (kB ^ (8u * s));
+  }
+  // per-thread twiddles of the row passes: W128^(l*k1)
+  cplx<float> tw[16];
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) tw[k1] = tw128(R.l, k1);
+
+  // column-pass role: column c, two of the eight n2 residues
   const int cg = w & 3, m = w >> 2;
   const int c = cg * 32 + lane;
   const bool special = (c == 0) || (c == 64);
   // radix-8 side of the columns: four k1 values closed under k1 -> -k1 (mod 16)
   const int ck1[4] = {m == 0 ? 0 : m, m == 0 ? 8 : 16 - m, m == 0 ? 4 : 8 - m,
                       m == 0 ? 12 : 8 + m};
+  // byte offsets of column c in even / odd rows (row swizzle = 8 * parity)
+  const unsigned cev = 8u * c, cod = 8u * (c ^ 8);
 
-  for (long long b = blockIdx.x; b < P.n_batch; b += gridDim.x) {
-    int sel = P.psf_sel[b];
+  // Order of the row work between two column passes. Every warp owns two row
+  // batches; per batch the inverse pass of walker b must precede the forward pass
+  // of the next walker (same rows). Half of the warps of each scheduler interleave
+  // (inv 0, fwd 0, inv 1, fwd 1), the other half run (inv 0, inv 1, fwd 0, fwd 1),
+  // so the SFU-bound render of some warps overlaps the FMA/LSU-bound inverse
+  // transforms of the others.
+  const bool interleave = ((w >> 2) & 1) != 0;
+
+  // The first pass through the loop (b < 0) only renders and forward-transforms the
+  // CTA's first walker; every later pass runs the column passes of walker b, then
+  // its inverse rows interleaved with the forward rows of the CTA's next walker.
+#pragma unroll 1
+  for (long long b = (long long)blockIdx.x - (long long)gridDim.x; b < P.n_batch;
+       b += gridDim.x) {
+    const bool cur = b >= 0;
+    int sel = cur ? P.psf_sel[b] : 0;
     const bool invalid = sel < 0;
     if (invalid) sel = 0;
-    const double wscale_b = P.wscale[b];
-    const float wsc = (float)wscale_b;
+    const double wscale_b = cur ? P.wscale[b] : 1.0;
     const float unscale = (float)(P.vscale_inv[sel] / wscale_b);
     const cplx<float> *sp = P.spec + (size_t)sel * N * N;
-
-    // per-thread twiddles of the row phases: W128^(l*k1)
-    cplx<float> tw[16];
-#pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) tw[k1] = tw128(l, k1);
-
-    // ---------------------------------------------------------- rows fwd --
-#pragma unroll 1
-    for (int it = 0; it < 2; ++it) {
-      const int y = it * 64 + w * 4 + rr;
-      cplx<float> *row = tile + y * N;
-      const int swz = (y & 1) << 3;
-      {
-        cplx<float> v[16];
-        fused_render16(P, b, y, l, wsc, v);
-        dft16<false>(v);
-#pragma unroll
-        for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * tw[k1];
-        __syncwarp();   // the previous walker's last reads of this row are done
-#pragma unroll
-        for (int k1 = 0; k1 < 16; ++k1) row[xpos(k1, l, swz)] = v[k1];
-      }
-      __syncwarp();
-      cplx<float> a[8], bb[8];
-#pragma unroll
-      for (int n2 = 0; n2 < 8; ++n2) {
-        a[n2] = row[xpos(kA, n2, swz)];
-        bb[n2] = row[xpos(kB, n2, swz)];
-      }
-      __syncwarp();
-      dft8<float, false>(a);    // a[k2]  = Z[kA + 16 k2]
-      dft8<float, false>(bb);   // bb[k2] = Z[kB + 16 k2]
-#pragma unroll
-      for (int k2 = 0; k2 < 4; ++k2) {
-        {  // kx = kA + 16 k2, partner -kx
-          const cplx<float> zk = a[k2];
-          const cplx<float> zp = l0 ? a[(8 - k2) & 7] : bb[7 - k2];
-          cplx<float> oa = mk<float>(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
-          cplx<float> ob = mk<float>(0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x));
-          if (k2 == 0 && l0) {   // real DC / Nyquist columns, packed in pairs
-            oa = mk<float>(a[0].x, a[4].x);
-            ob = mk<float>(a[0].y, a[4].y);
-          }
-          row[(kA + 16 * k2) ^ swz] = oa;
-          row[(64 + kA + 16 * k2) ^ swz] = ob;
-        }
-        {  // kx = kB + 16 k2
-          const cplx<float> zk = bb[k2];
-          const cplx<float> zp = l0 ? bb[7 - k2] : a[7 - k2];
-          row[(kB + 16 * k2) ^ swz] =
-              mk<float>(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
-          row[(64 + kB + 16 * k2) ^ swz] =
-              mk<float>(0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x));
-        }
-      }
-    }
+    if (cur) {
 
     // spectrum values of the first half of the column multiply (latency is hidden
     // behind the first column pass)
@@ -270,15 +425,15 @@ fused_lnlike_kernel(const FusedParams P) {
 #pragma unroll 1
     for (int hh = 0; hh < 2; ++hh) {
       const int n2 = m + 4 * hh;
-      cplx<float> *col = tile + n2 * N + (c ^ ((n2 & 1) << 3));
+      const smem_addr_t cb = tile + (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
       cplx<float> v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = col[8 * j * N];
+      for (int j = 0; j < 16; ++j) v[j] = lds64(cb + 8 * j * ROWB);
       dft16<false>(v);
 #pragma unroll
       for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * tw128(n2, k1);
 #pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) col[8 * k1 * N] = v[k1];
+      for (int k1 = 0; k1 < 16; ++k1) sts64(cb + 8 * k1 * ROWB, v[k1]);
     }
     group_barrier(1 + cg, 128);
 
@@ -286,12 +441,13 @@ fused_lnlike_kernel(const FusedParams P) {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int k1a = ck1[2 * half], k1b = ck1[2 * half + 1];
+      const smem_addr_t ba = tile + 8u * k1a * ROWB, bq = tile + 8u * k1b * ROWB;
       cplx<float> a[8], bb[8];
 #pragma unroll
       for (int n2 = 0; n2 < 8; ++n2) {
-        const int cc = c ^ ((n2 & 1) << 3);
-        a[n2] = tile[(n2 + 8 * k1a) * N + cc];
-        bb[n2] = tile[(n2 + 8 * k1b) * N + cc];
+        const unsigned cc = (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
+        a[n2] = lds64(ba + cc);
+        bb[n2] = lds64(bq + cc);
       }
       dft8<float, false>(a);    // a[k2]  = U[k1a + 16 k2][c]
       dft8<float, false>(bb);
@@ -302,23 +458,20 @@ fused_lnlike_kernel(const FusedParams P) {
           bb[k2] = bb[k2] * sb[k2];
         }
       } else {
-        const cplx<float> *sx = P.specx + ((size_t)sel * 2 + (c == 64 ? 1 : 0)) * N;
+        const cplx<float> *sx = P.specx + ((size_t)sel * 2 + (c == 64 ? 1 : 0)) * 2 * N;
         if (m == 0 && half == 0) {   // k1a = 0: ky <-> (128 - ky); k1b = 8: k2 <-> 7-k2
-          special_pair(a[0], a[0], sa[0], sx[0], sa[0], sx[0]);
-          special_pair(a[4], a[4], sa[4], sx[64], sa[4], sx[64]);
+          special_pair(a[0], a[0], sx, 0, 0);
+          special_pair(a[4], a[4], sx, 64, 64);
 #pragma unroll
           for (int k2 = 1; k2 < 4; ++k2)
-            special_pair(a[k2], a[8 - k2], sa[k2], sx[16 * k2], sa[8 - k2],
-                         sx[16 * (8 - k2)]);
+            special_pair(a[k2], a[8 - k2], sx, 16 * k2, 16 * (8 - k2));
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2)
-            special_pair(bb[k2], bb[7 - k2], sb[k2], sx[8 + 16 * k2], sb[7 - k2],
-                         sx[8 + 16 * (7 - k2)]);
+            special_pair(bb[k2], bb[7 - k2], sx, 8 + 16 * k2, 8 + 16 * (7 - k2));
         } else {                     // a[k2] <-> bb[7 - k2]
 #pragma unroll
           for (int k2 = 0; k2 < 8; ++k2)
-            special_pair(a[k2], bb[7 - k2], sa[k2], sx[k1a + 16 * k2], sb[7 - k2],
-                         sx[k1b + 16 * (7 - k2)]);
+            special_pair(a[k2], bb[7 - k2], sx, k1a + 16 * k2, k1b + 16 * (7 - k2));
         }
       }
       if (half == 0) {   // prefetch the second half's spectrum values
@@ -332,9 +485,9 @@ fused_lnlike_kernel(const FusedParams P) {
       dft8<float, true>(bb);
 #pragma unroll
       for (int n2 = 0; n2 < 8; ++n2) {
-        const int cc = c ^ ((n2 & 1) << 3);
-        tile[(n2 + 8 * k1a) * N + cc] = a[n2];
-        tile[(n2 + 8 * k1b) * N + cc] = bb[n2];
+        const unsigned cc = (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
+        sts64(ba + cc, a[n2]);
+        sts64(bq + cc, bb[n2]);
       }
     }
     group_barrier(1 + cg, 128);
@@ -343,105 +496,56 @@ fused_lnlike_kernel(const FusedParams P) {
 #pragma unroll 1
     for (int hh = 0; hh < 2; ++hh) {
       const int n2 = m + 4 * hh;
-      cplx<float> *col = tile + n2 * N + (c ^ ((n2 & 1) << 3));
+      const smem_addr_t cb = tile + (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
       cplx<float> v[16];
 #pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) v[k1] = col[8 * k1 * N];
+      for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(cb + 8 * k1 * ROWB);
 #pragma unroll
-      for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * cconj(tw128(n2, k1));
+      for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], tw128(n2, k1));
       dft16<true>(v);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) col[8 * j * N] = v[j];
+      for (int j = 0; j < 16; ++j) sts64(cb + 8 * j * ROWB, v[j]);
     }
     __syncthreads();
+    }  // if (cur)
 
-    // ------------------------------------------------ rows inv + epilogue --
+    // ------ rows: inverse + chi-square of walker b, render + forward of the next --
+    const long long bn = b + gridDim.x;
+    const bool has_next = bn < P.n_batch;
+    const float wsc_next = has_next ? (float)P.wscale[bn] : 0.0f;
     double acc = 0.0;
 #pragma unroll 1
-    for (int it = 0; it < 2; ++it) {
-      const int y = it * 64 + w * 4 + rr;
-      cplx<float> *row = tile + y * N;
-      const int swz = (y & 1) << 3;
-      cplx<float> a[8], bb[8];
-      {
-        cplx<float> yd1[4], ym1[4], yd2[4], ym2[4];
-        cplx<float> a10, b10;
+    for (int step = 0; step < 4; ++step) {
+      // interleave: I0 F0 I1 F1 ; otherwise: I0 I1 F0 F1
+      const bool fwd = interleave ? (step & 1) : (step >= 2);
+      const int it = interleave ? (step >> 1) : (step & 1);
+      if (!fwd) {
+        if (cur) acc += fused_rows_inverse(P, tile, R, tw, it, unscale);
+      } else if (has_next) {
+        fused_rows_forward(P, tile, R, tw, bn, it, wsc_next);
+      }
+      if (cur && ((interleave && step == 2) || (!interleave && step == 1))) {
+        // both inverse batches of this warp are done: float64 reduction. Warp
+        // shuffles, then the last warp to arrive sums the per-warp partials in
+        // fixed order (deterministic) and writes lnL.
 #pragma unroll
-        for (int k2 = 0; k2 < 4; ++k2) {
-          const cplx<float> a1 = row[(kA + 16 * k2) ^ swz];
-          const cplx<float> b1 = row[(64 + kA + 16 * k2) ^ swz];
-          const cplx<float> a2 = row[(kB + 16 * k2) ^ swz];
-          const cplx<float> b2 = row[(64 + kB + 16 * k2) ^ swz];
-          if (k2 == 0) {
-            a10 = a1;
-            b10 = b1;
+        for (int off = 16; off > 0; off >>= 1)
+          acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if (lane == 0) {
+          volatile double *red = red_s;
+          red[w] = acc;
+          __threadfence_block();
+          const int prev = atomicAdd(&cnt_s, 1);
+          if (prev == PSFMC_FUSED_THREADS / 32 - 1) {
+            __threadfence_block();
+            double tot = 0.0;
+            for (int k = 0; k < PSFMC_FUSED_THREADS / 32; ++k) tot += red[k];
+            double val = -0.5 * tot;
+            if (!isfinite(val) || invalid) val = -INFINITY;
+            P.lnl[b] = val;
+            cnt_s = 0;
           }
-          // Y[kx] = A' + i B',  Y[-kx] = conj(A') + i conj(B')
-          yd1[k2] = mk<float>(a1.x - b1.y, a1.y + b1.x);
-          ym1[k2] = mk<float>(a1.x + b1.y, b1.x - a1.y);
-          yd2[k2] = mk<float>(a2.x - b2.y, a2.y + b2.x);
-          ym2[k2] = mk<float>(a2.x + b2.y, b2.x - a2.y);
         }
-#pragma unroll
-        for (int k2 = 0; k2 < 4; ++k2) {
-          a[k2] = yd1[k2];
-          bb[k2] = yd2[k2];
-          a[4 + k2] = l0 ? ym1[(4 - k2) & 3] : ym2[3 - k2];
-          bb[4 + k2] = l0 ? ym2[3 - k2] : ym1[3 - k2];
-        }
-        if (l0) {   // packed DC / Nyquist columns
-          a[0] = mk<float>(a10.x, b10.x);
-          a[4] = mk<float>(a10.y, b10.y);
-        }
-      }
-      __syncwarp();
-      dft8<float, true>(a);     // a[n2]
-      dft8<float, true>(bb);
-#pragma unroll
-      for (int n2 = 0; n2 < 8; ++n2) {
-        row[xpos(kA, n2, swz)] = a[n2];
-        row[xpos(kB, n2, swz)] = bb[n2];
-      }
-      __syncwarp();
-      cplx<float> v[16];
-#pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) v[k1] = row[xpos(k1, l, swz)];
-      // observation + signed variance of this thread's 16 pixels
-      float2 o[16];
-      const float2 *owr = P.ow + y * N + l;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
-#pragma unroll
-      for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * cconj(tw[k1]);
-      dft16<true>(v);           // v[j] = (convolved model, scaled model variance)
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float resid, ivm;
-        const double t = Epilogue<float>::term(v[j].x, v[j].y * unscale, o[j].x,
-                                               fabsf(o[j].y), &resid, &ivm);
-        if (__float_as_int(o[j].y) >= 0) acc += t;
-      }
-    }
-    // a[4 + k2] for l0 uses ym1[8 - (4 + k2)] = ym1[4 - k2], k2 = 1..3 (k2 = 0 is
-    // overwritten by the packed Nyquist value above)
-
-    // float64 reduction: warp shuffles, then the last warp to arrive sums the
-    // per-warp partials in fixed order (deterministic) and writes lnL.
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
-      volatile double *red = red_s;
-      red[w] = acc;
-      __threadfence_block();
-      const int prev = atomicAdd(&cnt_s, 1);
-      if (prev == PSFMC_FUSED_THREADS / 32 - 1) {
-        __threadfence_block();
-        double tot = 0.0;
-        for (int k = 0; k < PSFMC_FUSED_THREADS / 32; ++k) tot += red[k];
-        double val = -0.5 * tot;
-        if (!isfinite(val) || invalid) val = -INFINITY;
-        P.lnl[b] = val;
-        cnt_s = 0;
       }
     }
   }
@@ -468,7 +572,8 @@ inline int fused_prepare_device(const StagedPlan &) {
 // kernels_staged.cuh) for the fused kernel:
 //   spec [K][ky][c]: c in 1..63 -> P[ky][kx=c]; c in 65..127 -> V[ky][kx=c-64];
 //                    c = 0 -> P[ky][0]; c = 64 -> V[ky][0]
-//   specx[K][0][ky] = P[ky][64], specx[K][1][ky] = V[ky][64]
+//   specx[K][t][0][ky] = (S[ky][0] + S[ky][64]) / 2, specx[K][t][1][ky] = (S[ky][0] -
+//                    S[ky][64]) / 2 for S = P (t = 0) and S = V (t = 1)
 // `vscale[k]` multiplies the V channel (power of two, undone in the epilogue).
 inline void fused_spectrum_layout(const cplx<double> *spec64, int n_psf,
                                   const double *vscale, cplx<float> *spec,
@@ -476,9 +581,11 @@ inline void fused_spectrum_layout(const cplx<double> *spec64, int n_psf,
   constexpr int N = PSFMC_FUSED_N, Wc = N / 2 + 1;
   for (int k = 0; k < n_psf; ++k) {
     const cplx<double> *src = spec64 + (size_t)k * 2 * Wc * N;
-    auto at = [&](int chan, int kx, int ky) {
+    // `split`: the factor 1/2 of the real-pair split of the row spectra, folded in
+    // for the regular columns; the packed DC/Nyquist columns carry exact values
+    auto at = [&](int chan, int kx, int ky, double split) {
       const cplx<double> &s = src[((size_t)chan * Wc + kx) * N + ky];
-      const double f = chan ? vscale[k] : 1.0;
+      const double f = (chan ? vscale[k] : 1.0) * split;
       cplx<float> o;
       o.x = (float)(s.x * f);
       o.y = (float)(s.y * f);
@@ -487,10 +594,18 @@ inline void fused_spectrum_layout(const cplx<double> *spec64, int n_psf,
     for (int ky = 0; ky < N; ++ky) {
       for (int c = 0; c < N; ++c) {
         const int chan = c >= 64 ? 1 : 0, kx = c & 63;
-        spec[((size_t)k * N + ky) * N + c] = at(chan, kx, ky);
+        spec[((size_t)k * N + ky) * N + c] = at(chan, kx, ky, kx == 0 ? 1.0 : 0.5);
       }
-      specx[((size_t)k * 2 + 0) * N + ky] = at(0, 64, ky);
-      specx[((size_t)k * 2 + 1) * N + ky] = at(1, 64, ky);
+      for (int t = 0; t < 2; ++t) {
+        const cplx<double> &s0 = src[((size_t)t * Wc + 0) * N + ky];
+        const cplx<double> &s64 = src[((size_t)t * Wc + 64) * N + ky];
+        const double f = t ? vscale[k] : 1.0;
+        cplx<float> *dst = specx + ((size_t)k * 2 + t) * 2 * N;
+        dst[ky].x = (float)(0.5 * f * (s0.x + s64.x));
+        dst[ky].y = (float)(0.5 * f * (s0.y + s64.y));
+        dst[N + ky].x = (float)(0.5 * f * (s0.x - s64.x));
+        dst[N + ky].y = (float)(0.5 * f * (s0.y - s64.y));
+      }
     }
   }
 }
@@ -508,11 +623,12 @@ template <typename T>
 inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &buf,
                                const FusedBuffers &fb, const Program &prog_h,
                                const double *theta, long long n_batch, long long ld,
-                               double *lnl, cudaStream_t stream) {
+                               double *lnl, cudaStream_t stream,
+                               cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr) {
   if (n_batch <= 0) return 0;
   const int ncomp = prog_h.n_components;
   {
-    long long nthreads = n_batch * (ncomp > 0 ? ncomp : 1);
+    long long nthreads = 32 * n_batch * (ncomp > 0 ? ncomp : 1);   // warp per component
     int block = 128;
     unsigned grid = (unsigned)((nthreads + block - 1) / block);
     launch_kernel(prepare_kernel, dim3(grid), dim3(block), 0, stream, buf.prog, theta,
@@ -534,8 +650,10 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
   for (int c = 0; c < PSFMC_MAX_COMPONENTS; ++c)
     P.kind[c] = (signed char)(c < ncomp ? prog_h.kind[c] : 0);
   unsigned grid = (unsigned)(n_batch < fb.n_sms ? n_batch : fb.n_sms);
+  if (ev_begin) cudaEventRecord(ev_begin, stream);
   launch_kernel(fused_lnlike_kernel, dim3(grid), dim3(PSFMC_FUSED_THREADS),
                 (size_t)PSFMC_FUSED_SMEM, stream, P);
+  if (ev_end) cudaEventRecord(ev_end, stream);
   return 2;
 }
 

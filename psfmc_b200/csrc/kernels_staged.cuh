@@ -225,16 +225,13 @@ template <>
 struct Epilogue<float> {
   static __device__ __forceinline__ double term(float conv, float mvar, float obs,
                                                 float ovar, float *resid, float *ivm) {
+    // -log(ivm / 2pi) = ln2 * log2(tot) + ln(2 pi): the logarithm does not wait
+    // for the reciprocal
     *resid = obs - conv;
-    float tot = mvar + ovar;
-#ifdef PSFMC_EMU
-    *ivm = 1.0f / tot;
-    float lg = logf(0.15915494309189535f * (*ivm));
-#else
-    *ivm = __frcp_rn(tot);
-    float lg = __logf(0.15915494309189535f * (*ivm));
-#endif
-    return (double)((*resid) * (*resid) * (*ivm) - lg);
+    const float tot = mvar + ovar;
+    *ivm = fast_rcp(tot);
+    const float lg = fmaf(0.69314718055994530942f, fast_lg2(tot), 1.8378770664093454836f);
+    return (double)fmaf((*resid) * (*resid), *ivm, lg);
   }
 };
 

@@ -118,17 +118,20 @@ inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
                                  long long n_batch, long long ld, double *lnl,
                                  cudaStream_t stream, bool ps_only = false,
                                  const ImageOutputs<T> *images = nullptr,
-                                 long long images_chunk_offset = -1) {
+                                 long long images_chunk_offset = -1,
+                                 cudaEvent_t ev_begin = nullptr,
+                                 cudaEvent_t ev_end = nullptr) {
   if (n_batch <= 0) return;
   const Frame fr = plan.fr;
   {
-    long long nthreads = n_batch * n_components;
+    long long nthreads = 32 * n_batch * n_components;   // one warp per component
     int block = 128;
     unsigned grid = (unsigned)((nthreads + block - 1) / block);
     launch_kernel(prepare_kernel, dim3(grid), dim3(block), 0, stream, buf.prog, theta,
                   n_batch, ld, fr.H, fr.W, buf.derived, buf.psf_sel, buf.wscale,
                   (float *)nullptr);
   }
+  if (ev_begin) cudaEventRecord(ev_begin, stream);   // the three row/column kernels
   for (long long start = 0; start < n_batch; start += plan.chunk) {
     long long nb = n_batch - start < plan.chunk ? n_batch - start : plan.chunk;
     const double *der = buf.derived + start * n_components * PSFMC_DERIVED_STRIDE;
@@ -156,6 +159,7 @@ inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
                   (const int *)(buf.psf_sel + start), buf.vscale_inv,
                   buf.partials + start * plan.n_rowblk, img.conv, img.resid, img.ivm);
   }
+  if (ev_end) cudaEventRecord(ev_end, stream);
   {
     int block = 128;
     unsigned grid = (unsigned)((n_batch + block - 1) / block);

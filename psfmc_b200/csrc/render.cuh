@@ -80,8 +80,10 @@ __device__ __forceinline__ float sersic_pixel_f32(const SersicF32 &s, float x, f
   return sb * (1.0f + s.kq * (t * t) * fast_rcp(r2));
 }
 
-// One thread per (walker, component): theta -> derived constants, float64.
-//   grid = ceil(B * n_components / blockDim)
+// One WARP per (walker, component): theta -> derived constants, float64. The lanes
+// share the scalar work and split the incomplete-gamma series of the Sersic kappa
+// (devmath.cuh) and the point-source stamp taps.
+//   grid = ceil(32 * B * n_components / blockDim), blockDim a multiple of 32
 // wscale[b] receives the packing scale of the walker (see below);
 // psf_sel[b] receives the rint-ed PSF index (psfMC/distributions.py:130-138), or
 // -1 when it is out of range (the prior is -inf there; the walker gets -inf).
@@ -91,15 +93,17 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
                                int *__restrict__ psf_sel, double *__restrict__ wscale,
                                float *__restrict__ rconst) {
   const int ncomp = prog->n_components;
-  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= n_batch * ncomp) return;
+  const int lane = threadIdx.x & 31;
+  long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gid >= n_batch * ncomp) return;     // whole warps leave together
+  const bool writer = (lane == 0);
   long long b = gid / ncomp;
   int c = (int)(gid - b * ncomp);
   const double *th = theta + b * ld;
   double *out = derived + (b * ncomp + c) * PSFMC_DERIVED_STRIDE;
   const int kind = prog->kind[c];
   const int flags = prog->flags[c];
-  if (c == 0) {
+  if (c == 0 && writer) {
     int sel = 0;
     if (prog->psf_theta_index >= 0) {
       double v = rint(th[prog->psf_theta_index]);
@@ -113,12 +117,14 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
     // (z = raw + i * wscale * raw^2): with wscale ~ 1/flux both channels have
     // comparable magnitude, so rounding errors of the large one do not swamp
     // the small one. Exact (power of two), undone in the epilogue.
+    // (only the binary exponent of the total flux matters: float32 exp2 is enough)
     double ftot = 0.0;
     for (int k = 0; k < ncomp; ++k) {
       if (prog->kind[k] == PSFMC_SKY)
         ftot += fabs(slot_value(prog, k, PSFMC_P_ADU, th));
       else
-        ftot += mag_to_flux(slot_value(prog, k, PSFMC_P_MAG, th), prog->mag_zp);
+        ftot += (double)exp2f((float)(-0.4 * 3.3219280948873623 *
+                                      (slot_value(prog, k, PSFMC_P_MAG, th) - prog->mag_zp)));
     }
     double sc = 1.0;
     if (isfinite(ftot) && ftot > 1e-300) {
@@ -131,28 +137,37 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
     wscale[b] = sc;
   }
   if (kind == PSFMC_SKY) {
-    out[D_SKY_ADU] = slot_value(prog, c, PSFMC_P_ADU, th);
+    if (writer) out[D_SKY_ADU] = slot_value(prog, c, PSFMC_P_ADU, th);
   } else if (kind == PSFMC_POINT) {
     double x = slot_value(prog, c, PSFMC_P_X, th);
     double y = slot_value(prog, c, PSFMC_P_Y, th);
     double mag = slot_value(prog, c, PSFMC_P_MAG, th);
     double radius = (flags & PSFMC_FLAG_BILINEAR) ? 0.5 : 3.0;
-    out[D_PS_X] = x;
-    out[D_PS_Y] = y;
-    out[D_PS_FLUX] = mag_to_flux(mag, prog->mag_zp);
-    stamp_bounds(y, radius, H, &out[D_PS_YMIN], &out[D_PS_YMAX]);
-    stamp_bounds(x, radius, W, &out[D_PS_XMIN], &out[D_PS_XMAX]);
+    double ymin, ymax, xmin, xmax;
+    stamp_bounds(y, radius, H, &ymin, &ymax);
+    stamp_bounds(x, radius, W, &xmin, &xmax);
+    if (writer) {
+      out[D_PS_X] = x;
+      out[D_PS_Y] = y;
+      out[D_PS_FLUX] = mag_to_flux(mag, prog->mag_zp);
+      out[D_PS_YMIN] = ymin;
+      out[D_PS_YMAX] = ymax;
+      out[D_PS_XMIN] = xmin;
+      out[D_PS_XMAX] = xmax;
+    }
     // separable stamp weights (PointSource.py:40-56: kern = prod over (x, y) of
-    // lanczos(diff) or 1 - |diff|), measured from the UNCLIPPED position
-    for (int i = 0; i < 7; ++i) {
-      double px = out[D_PS_XMIN] + (double)i, py = out[D_PS_YMIN] + (double)i;
-      double wx = 0.0, wy = 0.0;
-      if (px <= out[D_PS_XMAX])
-        wx = (flags & PSFMC_FLAG_BILINEAR) ? 1.0 - fabs(px - x) : lanczos3_ref(px - x);
-      if (py <= out[D_PS_YMAX])
-        wy = (flags & PSFMC_FLAG_BILINEAR) ? 1.0 - fabs(py - y) : lanczos3_ref(py - y);
-      out[D_PS_WX + i] = wx;
-      out[D_PS_WY + i] = wy;
+    // lanczos(diff) or 1 - |diff|), measured from the UNCLIPPED position; lane i
+    // computes tap i of the x axis, lane 7 + i tap i of the y axis
+    if (lane < 14) {
+      const bool along_y = lane >= 7;
+      const int i = along_y ? lane - 7 : lane;
+      const double pos = (along_y ? ymin : xmin) + (double)i;
+      const double centre = along_y ? y : x;
+      double wgt = 0.0;
+      if (pos <= (along_y ? ymax : xmax))
+        wgt = (flags & PSFMC_FLAG_BILINEAR) ? 1.0 - fabs(pos - centre)
+                                            : lanczos3_ref(pos - centre);
+      out[(along_y ? D_PS_WY : D_PS_WX) + i] = wgt;
     }
   } else {  // PSFMC_SERSIC: Sersic.py:73-96 (transform), :47-71 (kappa, sb_eff)
     double x0 = slot_value(prog, c, PSFMC_P_X, th);
@@ -165,19 +180,26 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
     if (flags & PSFMC_FLAG_ANGLE_DEGREES) angle = angle * (PSFMC_PI / 180.0);  // np.deg2rad
     angle += 0.5 * PSFMC_PI;
     double sn = sin(angle), cs = cos(angle);
-    double kappa = gammaincinv_half(2.0 * n);
+    double lgam_a1;
+    double kappa = gammaincinv_half_warp(2.0 * n, lane, &lgam_a1);
+    // Gamma(2n) = exp(lgamma(2n + 1)) / (2n); overflows to inf for n >= 86 like
+    // scipy.special.gamma (-> NaN -> lnL = -inf, as in the reference)
+    double gamma_2n = exp(lgam_a1) / (2.0 * n);
     double flux = mag_to_flux(mag, prog->mag_zp);
-    out[D_SER_X0] = x0;
-    out[D_SER_Y0] = y0;
-    out[D_SER_A00] = cs / reff;
-    out[D_SER_A01] = sn / reff;
-    out[D_SER_A10] = -sn / reff_b;
-    out[D_SER_A11] = cs / reff_b;
-    out[D_SER_P] = 0.5 / n;
-    out[D_SER_KAPPA] = kappa;
-    out[D_SER_SBEFF] = sersic_sb_eff(flux, n, reff, reff_b, kappa);
+    if (writer) {
+      out[D_SER_X0] = x0;
+      out[D_SER_Y0] = y0;
+      out[D_SER_A00] = cs / reff;
+      out[D_SER_A01] = sn / reff;
+      out[D_SER_A10] = -sn / reff_b;
+      out[D_SER_A11] = cs / reff_b;
+      out[D_SER_P] = 0.5 / n;
+      out[D_SER_KAPPA] = kappa;
+      out[D_SER_SBEFF] = sersic_sb_eff(flux, n, reff, reff_b, kappa, gamma_2n);
+    }
   }
-  if (rconst) {
+  __syncwarp();
+  if (rconst && writer) {
     float *rc = rconst + (b * ncomp + c) * PSFMC_RC_STRIDE;
     if (kind == PSFMC_SKY) {
       rc[0] = (float)out[D_SKY_ADU];
@@ -243,6 +265,40 @@ __device__ __forceinline__ double raw_pixel_f64(const Program *prog, const doubl
     if (round_f32) acc = (double)(float)acc;
   }
   return acc;
+}
+
+// 1/x for a pair on the FMA pipe (the render is bound by the SFU, which already
+// carries three transcendentals per pixel): integer seed (12 % error), three
+// Newton steps -> ~1e-7 relative. x > 0; x = 0 gives a huge finite value times the
+// zero it multiplies where the reference has 0/0 = NaN -- handled by the caller.
+__device__ __forceinline__ cplx<float> rcp_pair_fma(cplx<float> x) {
+#ifdef PSFMC_EMU
+  return mk<float>(1.0f / x.x, 1.0f / x.y);
+#else
+  cplx<float> y = mk<float>(__int_as_float(0x7EF311C7 - __float_as_int(x.x)),
+                            __int_as_float(0x7EF311C7 - __float_as_int(x.y)));
+  const cplx<float> nx = mk<float>(-x.x, -x.y);
+#pragma unroll
+  for (int it = 0; it < 3; ++it) y = pfma(y, pfma(nx, y, bcast(1.0f)), y);
+  return y;
+#endif
+}
+
+// Two pixels of one row at once (x offsets dx.x, dx.y from the centre), element-wise
+// pair arithmetic (packed FFMA2/FMUL2 on the device): same formula as
+// sersic_pixel_f32. cu = a01*dy, cv = a11*dy, dy2 = dy*dy are per-row constants.
+__device__ __forceinline__ cplx<float> sersic_pair_f32(const SersicF32 &s, cplx<float> dx,
+                                                       float cu, float cv, float dy2) {
+  const cplx<float> u = pfma(bcast(s.a00), dx, bcast(cu));
+  const cplx<float> v = pfma(bcast(s.a10), dx, bcast(cv));
+  const cplx<float> sq = pfma(v, v, pmul(u, u));
+  const cplx<float> r2 = pfma(dx, dx, bcast(dy2));
+  const cplx<float> e = pmul(bcast(s.p), mk<float>(fast_lg2(sq.x), fast_lg2(sq.y)));
+  const cplx<float> t = mk<float>(fminf(fast_ex2(e.x), 1.0e18f), fminf(fast_ex2(e.y), 1.0e18f));
+  const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0));
+  const cplx<float> sb = mk<float>(fast_ex2(arg.x), fast_ex2(arg.y));
+  const cplx<float> q = pmul(pmul(bcast(s.kq), pmul(t, t)), rcp_pair_fma(r2));
+  return pfma(sb, q, sb);    // sb * (1 + q)
 }
 
 }  // namespace psfmc

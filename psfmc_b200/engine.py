@@ -178,6 +178,18 @@ class LikelihoodEngine(object):
             out.ctypes.data_as(dbl_p)))
         return {name: out[num] for num, name in enumerate(ordered)}
 
+    def profile(self, enable=True):
+        """Bracket the dominant kernel of every lnL call with CUDA events."""
+        _lib.check(self._lib, self._lib.psfmc_engine_profile(self._handle,
+                                                             1 if enable else 0))
+
+    def profile_read(self):
+        """(summed kernel milliseconds, launches) since the last read."""
+        ms, count = ctypes.c_double(), ctypes.c_int64()
+        _lib.check(self._lib, self._lib.psfmc_engine_profile_read(
+            self._handle, ctypes.byref(ms), ctypes.byref(count)))
+        return ms.value, count.value
+
     def info(self):
         info = _lib.Info()
         _lib.check(self._lib, self._lib.psfmc_engine_info(self._handle,

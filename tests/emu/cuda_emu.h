@@ -177,7 +177,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F &&body) {
   st.block = block;
   st.body = body;
   int nthreads = block.x * block.y * block.z;
-  st.smem.assign(smem_bytes + 64, 0);
+  st.smem.assign(smem_bytes + 2048, 0);
   if ((int)st.fibers.size() < nthreads) st.fibers.resize(nthreads);
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
@@ -228,7 +228,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F &&body) {
 
 inline unsigned char *dyn_smem() {
   uintptr_t p = (uintptr_t)S().smem.data();
-  p = (p + 15) & ~(uintptr_t)15;
+  p = (p + 1023) & ~(uintptr_t)1023;   // PSFMC_DYN_SMEM asks for 1024-byte alignment
   return (unsigned char *)p;
 }
 

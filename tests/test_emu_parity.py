@@ -40,6 +40,24 @@ def test_emu_c1_fp32_tolerance(emu_library, c1_golden, path, monkeypatch):
                      fp32_bounds(model, thetas))
 
 
+def test_emu_fused_persistent_loop(emu_library, c1_golden, monkeypatch):
+    """More walkers than CTAs: every CTA of the fused kernel walks over several
+    walkers (next walker's render overlapped with this walker's inverse rows); the
+    result must not depend on the grid size."""
+    thetas = np.array(c1_golden['theta'][:11])
+    monkeypatch.setenv('PSFMC_FUSED_CTAS', '148')
+    wide = model_from_file('j0005/model_c1.py', 'fp32', library=emu_library,
+                           obs_dtype=np.float64).log_likelihood_batch(thetas)
+    monkeypatch.setenv('PSFMC_FUSED_CTAS', '3')
+    model = model_from_file('j0005/model_c1.py', 'fp32', library=emu_library,
+                            obs_dtype=np.float64)
+    assert model.engine.info()['path'] == 1
+    narrow = model.log_likelihood_batch(thetas)
+    assert np.array_equal(wide, narrow)
+    assert_lnl_close(narrow, c1_golden['lnl']['M3'][:11], 'fp32',
+                     fp32_bounds(model, thetas))
+
+
 def test_emu_rawf32_tracks_m2(emu_library, c1_golden):
     model = model_from_file('j0005/model_c1.py', 'fp64_rawf32', library=emu_library)
     thetas = np.array(c1_golden['theta'][:6])

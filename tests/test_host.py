@@ -302,3 +302,44 @@ def test_accumulate_images_running_mean(tiny_model):
     # the IVM is averaged in variance space (models.py:81-82,96-97)
     assert np.allclose(model.posterior_images['composite_ivm'], 1 / ((0.25 + 1.0) / 2))
     model.reset_images()
+
+
+# ------------------------------------------- drop-in for the unmodified reference --
+
+_BRIDGE_CHECK = r"""
+import json, os, sys
+import numpy as np
+root, emu_lib = sys.argv[1], sys.argv[2]
+sys.path.insert(0, root)
+from oracle import refshim
+golden = json.load(open(os.path.join(root, 'tests/golden/c1_golden.json')))
+model = refshim.build_reference_model(
+    os.path.join(root, 'tests/golden/j0005/model_c1.py'), 'M3')
+from psfmc_b200.bridge import pool_for_reference_model
+pool = pool_for_reference_model(model, precision='fp64', library=emu_lib)
+rows = [0, 1, 2, 3, 4, 8, 9, 10]
+thetas = [np.array(golden['theta'][r]) for r in rows]
+batched = pool.map(None, thetas)
+for r, theta, (lnpost, blob) in zip(rows, thetas, batched):
+    want, _ = type(model).log_posterior(theta, model=model)     # the reference itself
+    assert blob == {}
+    if np.isfinite(want):
+        assert abs(lnpost - want) <= 1e-10 * abs(want), (r, lnpost, want)
+    else:
+        assert lnpost == -np.inf, (r, lnpost, want)
+print('BRIDGE-OK')
+"""
+
+
+def test_bridge_is_a_drop_in_for_the_unmodified_reference(emu_library):
+    """The reference's OWN MultiComponentModel + our pool object (kernels emulated on
+    the CPU here) reproduce the reference's log_posterior to 1e-10."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if not os.path.isdir('/root/reference/psfMC'):
+        pytest.skip('/root/reference not present (GPU box)')
+    proc = subprocess.run([sys.executable, '-c', _BRIDGE_CHECK, ROOT, emu_library],
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                          universal_newlines=True, timeout=600)
+    assert proc.returncode == 0 and 'BRIDGE-OK' in proc.stdout, proc.stdout[-3000:]
