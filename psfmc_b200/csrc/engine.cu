@@ -664,7 +664,7 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
         if (v > 0) ds.n_sms = v;
       }
       const size_t N = PSFMC_FUSED_N;
-      std::vector<cplx<float>> fspec((size_t)d->n_psf * N * N), fspecx((size_t)d->n_psf * 4 * N);
+      std::vector<cplx<float>> fspec((size_t)d->n_psf * N * N), fspecx((size_t)d->n_psf * 2 * N);
       std::vector<double> vs(d->n_psf);
       for (int k = 0; k < d->n_psf; ++k) vs[k] = 1.0 / vscale_inv[k];
       fused_spectrum_layout(spec64.data(), d->n_psf, vs.data(), fspec.data(), fspecx.data());

@@ -47,8 +47,8 @@ struct FusedParams {
   const int *psf_sel;        // [B]
   const double *vscale_inv;  // [K]
   const cplx<float> *spec;   // [K][ky=128][c=128], see fused_spectrum_layout()
-  const cplx<float> *specx;  // [K][2 (P,V)][2][ky=128]: (S0+S64)/2 and (S0-S64)/2 of the
-                             // packed DC/Nyquist columns (S0 = kx 0, S64 = kx 64)
+  const cplx<float> *specx;  // [K][2 (P,V)][ky=128]: (S0-S64)/2 of the packed DC/Nyquist
+                             // columns (S0 = kx 0, S64 = kx 64); (S0+S64)/2 is in spec
   const float2 *ow;          // [128*128]: (obs, bad ? -ovar : +ovar)
   double *lnl;               // [B]
   long long n_batch;
@@ -191,14 +191,25 @@ __device__ __forceinline__ void fused_render16(const FusedParams &P, long long b
   }
 }
 
+__device__ __forceinline__ cplx<float> ldc2(const cplx<float> *p) {
+#ifdef PSFMC_EMU
+  return *p;
+#else
+  const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+  return mk<float>(v.x, v.y);
+#endif
+}
+
 // Special (packed DC/Nyquist) columns: U = FFT(p + i q) of two real sequences that
 // are multiplied by different spectra S0 (for p) and S64 (for q):
 //   U'[ky] = U[ky] (S0+S64)/2 + conj(U[-ky]) (S0-S64)/2, spectra taken at ky.
-// sx points at the host-prepared half-sum / half-difference tables [2][128].
+// pu / pm: half-sums at ky / -ky (they sit in the `spec` table at c = 0 and c = 64),
+// du / dm: half-differences (from `specx`), all prefetched by the caller.
 __device__ __forceinline__ void special_pair(cplx<float> &u, cplx<float> &um,
-                                             const cplx<float> *sx, int ky, int kym) {
-  const cplx<float> nu = u * sx[ky] + cmul_conj(sx[PSFMC_FUSED_N + ky], um);
-  const cplx<float> nm = um * sx[kym] + cmul_conj(sx[PSFMC_FUSED_N + kym], u);
+                                             cplx<float> pu, cplx<float> du,
+                                             cplx<float> pm, cplx<float> dm) {
+  const cplx<float> nu = u * pu + cmul_conj(du, um);
+  const cplx<float> nm = um * pm + cmul_conj(dm, u);
   u = nu;
   um = nm;
 }
@@ -214,7 +225,7 @@ struct RowRole {
 
 // render + forward row transform + real-pair split of row batch `it` of walker b
 __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_addr_t tile,
-                                                   const RowRole &R, const cplx<float> *tw,
+                                                   const RowRole &R, smem_addr_t twl,
                                                    long long b, int it, float wsc) {
   const int y = it * 64 + R.w * 4 + R.rr;
   const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
@@ -223,7 +234,7 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
     fused_render16(P, b, y, R.l, wsc, v);
     dft16<false>(v);
 #pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * tw[k1];
+    for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * lds64(twl + 64 * k1);
     __syncwarp();   // every lane is done reading this row (previous walker)
     const smem_addr_t rt = rb + R.t16;
 #pragma unroll
@@ -271,11 +282,17 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
 // Hermitian rebuild + inverse row transform + chi-square terms of row batch `it`;
 // returns this thread's float64 partial sum over its 16 pixels.
 __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_addr_t tile,
-                                                     const RowRole &R, const cplx<float> *tw,
+                                                     const RowRole &R, smem_addr_t twl,
                                                      int it, float unscale) {
   const int y = it * 64 + R.w * 4 + R.rr;
   const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
   const bool l0 = R.l0;
+  // observation + signed variance of this thread's 16 pixels: issued first, used
+  // last (L2 latency hidden behind the whole inverse transform)
+  float2 o[16];
+  const float2 *owr = P.ow + y * PSFMC_FUSED_N + R.l;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
   cplx<float> a[8], bb[8];
   {
     cplx<float> yd1[4], ym1[4], yd2[4], ym2[4];
@@ -328,13 +345,8 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(rt ^ (unsigned)(64 * k1 + 8 * (k1 & 7)));
   }
-  // observation + signed variance of this thread's 16 pixels
-  float2 o[16];
-  const float2 *owr = P.ow + y * PSFMC_FUSED_N + R.l;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
-#pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], tw[k1]);
+  for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], lds64(twl + 64 * k1));
   dft16<true>(v);           // v[j] = (convolved model, scaled model variance)
   double acc = 0.0;
 #pragma unroll
@@ -373,10 +385,17 @@ fused_lnlike_kernel(const FusedParams P) {
     R.fa = 8u * (kA ^ (8u * s));
     R.fb = 8u * (kB ^ (8u * s));
   }
-  // per-thread twiddles of the row passes: W128^(l*k1)
-  cplx<float> tw[16];
-#pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) tw[k1] = tw128(R.l, k1);
+  // twiddles of the row passes W128^(l*k1) in shared memory as [k1][l]: the eight
+  // threads of a row read eight consecutive entries (no bank conflicts, 4 rows
+  // broadcast); this thread's entries are twl + 64 * k1
+  __shared__ __align__(16) float tw_s[128][2];
+  if (tid < 128) {
+    const int k1 = tid >> 3, ll = tid & 7;
+    tw_s[tid][0] = c_tw128[ll * 16 + k1][0];
+    tw_s[tid][1] = c_tw128[ll * 16 + k1][1];
+  }
+  const smem_addr_t twl = smem_base(reinterpret_cast<unsigned char *>(&tw_s[0][0])) + 8u * R.l;
+  __syncthreads();
 
   // column-pass role: column c, two of the eight n2 residues
   const int cg = w & 3, m = w >> 2;
@@ -426,15 +445,20 @@ fused_lnlike_kernel(const FusedParams P) {
     for (int hh = 0; hh < 2; ++hh) {
       const int n2 = m + 4 * hh;
       const smem_addr_t cb = tile + (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
-      cplx<float> v[16];
+      cplx<float> v[16], tc[16];
+#pragma unroll
+      for (int k1 = 1; k1 < 16; ++k1) tc[k1] = tw128(n2, k1);   // ahead of their use
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = lds64(cb + 8 * j * ROWB);
       dft16<false>(v);
 #pragma unroll
-      for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * tw128(n2, k1);
+      for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * tc[k1];
 #pragma unroll
       for (int k1 = 0; k1 < 16; ++k1) sts64(cb + 8 * k1 * ROWB, v[k1]);
     }
+    // half-difference table of the two special columns (one lane in 8 of 16 warps;
+    // 1 KB per PSF, L1-resident across walkers)
+    const cplx<float> *sx = P.specx + ((size_t)sel * 2 + (c == 64 ? 1 : 0)) * N;
     group_barrier(1 + cg, 128);
 
     // --------------- columns: radix-8, spectrum multiply, inverse radix-8 --
@@ -458,20 +482,22 @@ fused_lnlike_kernel(const FusedParams P) {
           bb[k2] = bb[k2] * sb[k2];
         }
       } else {
-        const cplx<float> *sx = P.specx + ((size_t)sel * 2 + (c == 64 ? 1 : 0)) * 2 * N;
         if (m == 0 && half == 0) {   // k1a = 0: ky <-> (128 - ky); k1b = 8: k2 <-> 7-k2
-          special_pair(a[0], a[0], sx, 0, 0);
-          special_pair(a[4], a[4], sx, 64, 64);
+          special_pair(a[0], a[0], sa[0], ldc2(sx), sa[0], ldc2(sx));
+          special_pair(a[4], a[4], sa[4], ldc2(sx + 64), sa[4], ldc2(sx + 64));
 #pragma unroll
           for (int k2 = 1; k2 < 4; ++k2)
-            special_pair(a[k2], a[8 - k2], sx, 16 * k2, 16 * (8 - k2));
+            special_pair(a[k2], a[8 - k2], sa[k2], ldc2(sx + 16 * k2), sa[8 - k2],
+                         ldc2(sx + 16 * (8 - k2)));
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2)
-            special_pair(bb[k2], bb[7 - k2], sx, 8 + 16 * k2, 8 + 16 * (7 - k2));
+            special_pair(bb[k2], bb[7 - k2], sb[k2], ldc2(sx + 8 + 16 * k2), sb[7 - k2],
+                         ldc2(sx + 8 + 16 * (7 - k2)));
         } else {                     // a[k2] <-> bb[7 - k2]
 #pragma unroll
           for (int k2 = 0; k2 < 8; ++k2)
-            special_pair(a[k2], bb[7 - k2], sx, k1a + 16 * k2, k1b + 16 * (7 - k2));
+            special_pair(a[k2], bb[7 - k2], sa[k2], ldc2(sx + k1a + 16 * k2), sb[7 - k2],
+                         ldc2(sx + k1b + 16 * (7 - k2)));
         }
       }
       if (half == 0) {   // prefetch the second half's spectrum values
@@ -497,11 +523,13 @@ fused_lnlike_kernel(const FusedParams P) {
     for (int hh = 0; hh < 2; ++hh) {
       const int n2 = m + 4 * hh;
       const smem_addr_t cb = tile + (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
-      cplx<float> v[16];
+      cplx<float> v[16], tc[16];
+#pragma unroll
+      for (int k1 = 1; k1 < 16; ++k1) tc[k1] = tw128(n2, k1);
 #pragma unroll
       for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(cb + 8 * k1 * ROWB);
 #pragma unroll
-      for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], tw128(n2, k1));
+      for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], tc[k1]);
       dft16<true>(v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) sts64(cb + 8 * j * ROWB, v[j]);
@@ -520,9 +548,9 @@ fused_lnlike_kernel(const FusedParams P) {
       const bool fwd = interleave ? (step & 1) : (step >= 2);
       const int it = interleave ? (step >> 1) : (step & 1);
       if (!fwd) {
-        if (cur) acc += fused_rows_inverse(P, tile, R, tw, it, unscale);
+        if (cur) acc += fused_rows_inverse(P, tile, R, twl, it, unscale);
       } else if (has_next) {
-        fused_rows_forward(P, tile, R, tw, bn, it, wsc_next);
+        fused_rows_forward(P, tile, R, twl, bn, it, wsc_next);
       }
       if (cur && ((interleave && step == 2) || (!interleave && step == 1))) {
         // both inverse batches of this warp are done: float64 reduction. Warp
@@ -571,9 +599,8 @@ inline int fused_prepare_device(const StagedPlan &) {
 // Re-layout of the float64 spectra [K][2*Wc][H] (column-major, see
 // kernels_staged.cuh) for the fused kernel:
 //   spec [K][ky][c]: c in 1..63 -> P[ky][kx=c]; c in 65..127 -> V[ky][kx=c-64];
-//                    c = 0 -> P[ky][0]; c = 64 -> V[ky][0]
-//   specx[K][t][0][ky] = (S[ky][0] + S[ky][64]) / 2, specx[K][t][1][ky] = (S[ky][0] -
-//                    S[ky][64]) / 2 for S = P (t = 0) and S = V (t = 1)
+//                    c = 0 -> (P[ky][0] + P[ky][64]) / 2; c = 64 -> same for V
+//   specx[K][t][ky] = (S[ky][0] - S[ky][64]) / 2 for S = P (t = 0) and S = V (t = 1)
 // `vscale[k]` multiplies the V channel (power of two, undone in the epilogue).
 inline void fused_spectrum_layout(const cplx<double> *spec64, int n_psf,
                                   const double *vscale, cplx<float> *spec,
@@ -594,17 +621,18 @@ inline void fused_spectrum_layout(const cplx<double> *spec64, int n_psf,
     for (int ky = 0; ky < N; ++ky) {
       for (int c = 0; c < N; ++c) {
         const int chan = c >= 64 ? 1 : 0, kx = c & 63;
-        spec[((size_t)k * N + ky) * N + c] = at(chan, kx, ky, kx == 0 ? 1.0 : 0.5);
+        if (kx != 0) spec[((size_t)k * N + ky) * N + c] = at(chan, kx, ky, 0.5);
       }
       for (int t = 0; t < 2; ++t) {
         const cplx<double> &s0 = src[((size_t)t * Wc + 0) * N + ky];
         const cplx<double> &s64 = src[((size_t)t * Wc + 64) * N + ky];
         const double f = t ? vscale[k] : 1.0;
-        cplx<float> *dst = specx + ((size_t)k * 2 + t) * 2 * N;
-        dst[ky].x = (float)(0.5 * f * (s0.x + s64.x));
-        dst[ky].y = (float)(0.5 * f * (s0.y + s64.y));
-        dst[N + ky].x = (float)(0.5 * f * (s0.x - s64.x));
-        dst[N + ky].y = (float)(0.5 * f * (s0.y - s64.y));
+        cplx<float> &sum = spec[((size_t)k * N + ky) * N + 64 * t];
+        cplx<float> &dif = specx[((size_t)k * 2 + t) * N + ky];
+        sum.x = (float)(0.5 * f * (s0.x + s64.x));
+        sum.y = (float)(0.5 * f * (s0.y + s64.y));
+        dif.x = (float)(0.5 * f * (s0.x - s64.x));
+        dif.y = (float)(0.5 * f * (s0.y - s64.y));
       }
     }
   }
