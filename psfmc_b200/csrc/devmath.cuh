@@ -14,28 +14,49 @@ namespace psfmc {
 //   P(a,x) = x^a e^-x / Gamma(a+1) * sum_k x^k / ((a+1)...(a+k)),
 // used only for x <= a + 1 (the median of Gamma(a) is always below a), where
 // every term is positive and the sum converges after O(sqrt(a)) terms.
-// Warp-cooperative: ALL 32 lanes call it with identical (a, x); each chunk of 32
-// terms costs one division per lane, a product scan and a sum reduction instead
-// of 32 dependent divisions. Every lane returns the same value.
-__device__ __forceinline__ double gamma_p_series_warp(double a, double x, double lgam_a1,
-                                                      int lane) {
+// Group-cooperative: the 8 lanes of a group call it with identical (a, x) (four
+// independent groups per warp, every lane of the warp takes part in the shuffles);
+// each chunk of 8 terms costs one division per lane, a product scan and a sum
+// reduction instead of 8 dependent divisions. Every lane of the group returns the
+// same value. Loop trip counts are made warp-uniform with __all_sync: the extra
+// chunks a faster group runs only add terms below 1e-17 of its sum.
+#define PSFMC_GROUP 8
+
+// 1/y for y >= 1 to ~1 ulp: hardware seed (2^-23) + two Newton steps; a full IEEE
+// division costs several times as many float64 instructions, and the prepare
+// kernel is bound by the float64 pipe.
+__device__ __forceinline__ double fast_drcp(double y) {
+#ifdef PSFMC_EMU
+  return 1.0 / y;
+#else
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+  r = fma(r, fma(-y, r, 1.0), r);
+  r = fma(r, fma(-y, r, 1.0), r);
+  return r;
+#endif
+}
+
+// Returns the series sum S; P(a, x) = exp(a log x - x - lgamma(a + 1)) * S.
+__device__ __forceinline__ double gamma_p_series_group(double a, double x, int glane) {
   double sum = 1.0, tbase = 1.0;
-  for (int chunk = 0; chunk < 64; ++chunk) {
-    double p = x / (a + (double)(chunk * 32 + lane + 1));
+  for (int chunk = 0; chunk < 256; ++chunk) {
+    double p = x * fast_drcp(a + (double)(chunk * PSFMC_GROUP + glane + 1));
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      double q = __shfl_up_sync(0xffffffffu, p, off);
-      if (lane >= off) p *= q;
+    for (int off = 1; off < PSFMC_GROUP; off <<= 1) {
+      double q = __shfl_up_sync(0xffffffffu, p, off, PSFMC_GROUP);
+      if (glane >= off) p *= q;
     }
-    const double term = tbase * p;          // term number chunk*32 + lane + 1
+    const double term = tbase * p;          // term number chunk*8 + glane + 1
     double part = term;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    for (int off = PSFMC_GROUP / 2; off > 0; off >>= 1)
+      part += __shfl_xor_sync(0xffffffffu, part, off, PSFMC_GROUP);
     sum += part;
-    tbase = __shfl_sync(0xffffffffu, term, 31);
-    if (tbase < sum * 1.0e-17) break;
+    tbase = __shfl_sync(0xffffffffu, term, PSFMC_GROUP - 1, PSFMC_GROUP);
+    if (__all_sync(0xffffffffu, !(tbase >= sum * 1.0e-17))) break;
   }
-  return exp(a * log(x) - x - lgam_a1) * sum;
+  return sum;
 }
 
 // kappa = gammaincinv(a, 0.5): the reference's exact Sersic b_n
@@ -44,12 +65,14 @@ __device__ __forceinline__ double gamma_p_series_warp(double a, double x, double
 // (1999) asymptotic seed (large a) or the small-x inversion (small a) converge
 // to double precision in 2-3 steps. Warp-cooperative like the series.
 // *lgam_a1_out receives lgamma(a + 1) (reused for Gamma(2n) by the caller).
-__device__ __forceinline__ double gammaincinv_half_warp(double a, int lane,
-                                                        double *lgam_a1_out) {
-  *lgam_a1_out = NAN;
-  if (!(a > 0.0) || !isfinite(a)) return NAN;
+// `active`: false for groups that have no Sersic to work on; they still walk through
+// the shuffles (with a harmless a = 1) so that the warp stays convergent.
+__device__ __forceinline__ double gammaincinv_half_group(double a, int glane, bool active,
+                                                         double *lgam_a1_out) {
+  const bool valid = active && (a > 0.0) && isfinite(a);
+  if (!valid) a = 1.0;
   const double lgam_a1 = lgamma(a + 1.0);
-  *lgam_a1_out = lgam_a1;
+  *lgam_a1_out = valid ? lgam_a1 : NAN;
   double x;
   if (a >= 0.8) {
     const double ia = 1.0 / a;   // b_n series in 1/n with n = a/2
@@ -61,27 +84,35 @@ __device__ __forceinline__ double gammaincinv_half_warp(double a, int lane,
     if (a > 0.3) x = fmax(x, 0.5 * (a - 1.0 / 3.0 + 8.0 / (405.0 * a)));
   }
   if (!(x > 0.0)) x = 1.0e-300;
-  const double lgam_a = lgam_a1 - log(a);
   double prev_dx = INFINITY;
+  bool done = false;
   for (int it = 0; it < 16; ++it) {
-    double f = gamma_p_series_warp(a, x, lgam_a1, lane) - 0.5;
-    double dens = exp((a - 1.0) * log(x) - x - lgam_a);  // dP/dx
-    if (!(dens > 0.0)) break;
-    double step = f / dens;
-    double curv = (a - 1.0) / x - 1.0;                   // P'' / P'
-    double denom = 1.0 - 0.5 * step * curv;
-    if (denom > 0.25) step /= denom;
-    double xn = x - step;
-    if (!(xn > 0.0)) xn = 0.5 * x;
-    if (xn > a + 1.0) xn = 0.5 * (x + a + 1.0);
-    double dx = fabs(xn - x);
-    x = xn;
-    // Halley's iteration converges cubically: a step below 1e-6 relative leaves an
-    // error below 1e-17. (Second test: bouncing between neighbouring doubles.)
-    if (dx <= 1.0e-6 * x || (dx <= 1.0e-13 * x && dx >= prev_dx)) break;
-    prev_dx = dx;
+    const double series = gamma_p_series_group(a, x, glane);
+    if (!done) {
+      const double pref = exp(a * log(x) - x - lgam_a1);  // x^a e^-x / Gamma(a+1)
+      const double f = pref * series - 0.5;
+      const double dens = pref * a / x;                   // dP/dx = x^(a-1) e^-x / Gamma(a)
+      if (!(dens > 0.0)) {
+        done = true;
+      } else {
+        double step = f / dens;
+        double curv = (a - 1.0) / x - 1.0;                   // P'' / P'
+        double denom = 1.0 - 0.5 * step * curv;
+        if (denom > 0.25) step /= denom;
+        double xn = x - step;
+        if (!(xn > 0.0)) xn = 0.5 * x;
+        if (xn > a + 1.0) xn = 0.5 * (x + a + 1.0);
+        double dx = fabs(xn - x);
+        x = xn;
+        // Halley's iteration converges cubically: a step below 1e-6 relative leaves
+        // an error below 1e-17. (Second test: bouncing between neighbouring doubles.)
+        if (dx <= 1.0e-6 * x || (dx <= 1.0e-13 * x && dx >= prev_dx)) done = true;
+        prev_dx = dx;
+      }
+    }
+    if (__all_sync(0xffffffffu, done)) break;
   }
-  return x;
+  return valid ? x : NAN;
 }
 
 // psfMC/utils.py:160-164

@@ -430,31 +430,36 @@ fused_lnlike_kernel(const FusedParams P) {
     const cplx<float> *sp = P.spec + (size_t)sel * N * N;
     if (cur) {
 
-    // spectrum values of the first half of the column multiply (latency is hidden
-    // behind the first column pass)
+    __syncthreads();
+
+    // ------------------------------------------------- columns: radix-16 --
+    // both residues n2 = m and m + 4 of this thread in flight at once (ILP)
+    {
+      const smem_addr_t cb0 = tile + (unsigned)m * ROWB + ((m & 1) ? cod : cev);
+      const smem_addr_t cb1 = cb0 + 4 * ROWB;
+      cplx<float> v0[16], v1[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v0[j] = lds64(cb0 + 8 * j * ROWB);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v1[j] = lds64(cb1 + 8 * j * ROWB);
+      dft16<false>(v0);
+#pragma unroll
+      for (int k1 = 1; k1 < 16; ++k1) v0[k1] = v0[k1] * tw128(m, k1);
+      dft16<false>(v1);
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) sts64(cb0 + 8 * k1 * ROWB, v0[k1]);
+#pragma unroll
+      for (int k1 = 1; k1 < 16; ++k1) v1[k1] = v1[k1] * tw128(m + 4, k1);
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) sts64(cb1 + 8 * k1 * ROWB, v1[k1]);
+    }
+    // spectrum values of the first half of the column multiply, issued before the
+    // group barrier so that their L2 latency overlaps the wait
     cplx<float> sa[8], sb[8];
 #pragma unroll
     for (int k2 = 0; k2 < 8; ++k2) {
       sa[k2] = sp[(ck1[0] + 16 * k2) * N + c];
       sb[k2] = sp[(ck1[1] + 16 * k2) * N + c];
-    }
-    __syncthreads();
-
-    // ------------------------------------------------- columns: radix-16 --
-#pragma unroll 1
-    for (int hh = 0; hh < 2; ++hh) {
-      const int n2 = m + 4 * hh;
-      const smem_addr_t cb = tile + (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
-      cplx<float> v[16], tc[16];
-#pragma unroll
-      for (int k1 = 1; k1 < 16; ++k1) tc[k1] = tw128(n2, k1);   // ahead of their use
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = lds64(cb + 8 * j * ROWB);
-      dft16<false>(v);
-#pragma unroll
-      for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * tc[k1];
-#pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) sts64(cb + 8 * k1 * ROWB, v[k1]);
     }
     // half-difference table of the two special columns (one lane in 8 of 16 warps;
     // 1 KB per PSF, L1-resident across walkers)
@@ -519,20 +524,24 @@ fused_lnlike_kernel(const FusedParams P) {
     group_barrier(1 + cg, 128);
 
     // ----------------------------------------- columns: inverse radix-16 --
-#pragma unroll 1
-    for (int hh = 0; hh < 2; ++hh) {
-      const int n2 = m + 4 * hh;
-      const smem_addr_t cb = tile + (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
-      cplx<float> v[16], tc[16];
+    {
+      const smem_addr_t cb0 = tile + (unsigned)m * ROWB + ((m & 1) ? cod : cev);
+      const smem_addr_t cb1 = cb0 + 4 * ROWB;
+      cplx<float> v0[16], v1[16];
 #pragma unroll
-      for (int k1 = 1; k1 < 16; ++k1) tc[k1] = tw128(n2, k1);
+      for (int k1 = 0; k1 < 16; ++k1) v0[k1] = lds64(cb0 + 8 * k1 * ROWB);
 #pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(cb + 8 * k1 * ROWB);
+      for (int k1 = 0; k1 < 16; ++k1) v1[k1] = lds64(cb1 + 8 * k1 * ROWB);
 #pragma unroll
-      for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], tc[k1]);
-      dft16<true>(v);
+      for (int k1 = 1; k1 < 16; ++k1) v0[k1] = cmul_conj(v0[k1], tw128(m, k1));
+      dft16<true>(v0);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) sts64(cb + 8 * j * ROWB, v[j]);
+      for (int k1 = 1; k1 < 16; ++k1) v1[k1] = cmul_conj(v1[k1], tw128(m + 4, k1));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sts64(cb0 + 8 * j * ROWB, v0[j]);
+      dft16<true>(v1);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sts64(cb1 + 8 * j * ROWB, v1[j]);
     }
     __syncthreads();
     }  // if (cur)
@@ -656,7 +665,7 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
   if (n_batch <= 0) return 0;
   const int ncomp = prog_h.n_components;
   {
-    long long nthreads = 32 * n_batch * (ncomp > 0 ? ncomp : 1);   // warp per component
+    long long nthreads = PSFMC_GROUP * n_batch * (ncomp > 0 ? ncomp : 1);   // 8 lanes each
     int block = 128;
     unsigned grid = (unsigned)((nthreads + block - 1) / block);
     launch_kernel(prepare_kernel, dim3(grid), dim3(block), 0, stream, buf.prog, theta,

@@ -124,7 +124,7 @@ inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
   if (n_batch <= 0) return;
   const Frame fr = plan.fr;
   {
-    long long nthreads = 32 * n_batch * n_components;   // one warp per component
+    long long nthreads = PSFMC_GROUP * n_batch * (n_components > 0 ? n_components : 1);
     int block = 128;
     unsigned grid = (unsigned)((nthreads + block - 1) / block);
     launch_kernel(prepare_kernel, dim3(grid), dim3(block), 0, stream, buf.prog, theta,

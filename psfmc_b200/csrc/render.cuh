@@ -80,10 +80,11 @@ __device__ __forceinline__ float sersic_pixel_f32(const SersicF32 &s, float x, f
   return sb * (1.0f + s.kq * (t * t) * fast_rcp(r2));
 }
 
-// One WARP per (walker, component): theta -> derived constants, float64. The lanes
-// share the scalar work and split the incomplete-gamma series of the Sersic kappa
-// (devmath.cuh) and the point-source stamp taps.
-//   grid = ceil(32 * B * n_components / blockDim), blockDim a multiple of 32
+// One 8-lane GROUP per (walker, component): theta -> derived constants, float64.
+// The lanes of a group share the scalar work and split the incomplete-gamma series
+// of the Sersic kappa (devmath.cuh) and the point-source stamp taps; the four
+// groups of a warp walk through the same shuffles (groups without a Sersic idle).
+//   grid = ceil(8 * B * n_components / blockDim), blockDim a multiple of 32
 // wscale[b] receives the packing scale of the walker (see below);
 // psf_sel[b] receives the rint-ed PSF index (psfMC/distributions.py:130-138), or
 // -1 when it is out of range (the prior is -inf there; the walker gets -inf).
@@ -92,17 +93,20 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
                                long long ld, int H, int W, double *__restrict__ derived,
                                int *__restrict__ psf_sel, double *__restrict__ wscale,
                                float *__restrict__ rconst) {
-  const int ncomp = prog->n_components;
-  const int lane = threadIdx.x & 31;
-  long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (gid >= n_batch * ncomp) return;     // whole warps leave together
-  const bool writer = (lane == 0);
+  const int ncomp_prog = prog->n_components;
+  const int ncomp = ncomp_prog > 0 ? ncomp_prog : 1;   // an empty model still gets its
+                                                       // per-walker PSF index and scale
+  const int glane = threadIdx.x & (PSFMC_GROUP - 1);
+  long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / PSFMC_GROUP;
+  const bool live = gid < n_batch * ncomp;
+  if (!live) gid = 0;                       // idle groups shadow group 0, write nothing
+  const bool writer = live && (glane == 0);
   long long b = gid / ncomp;
   int c = (int)(gid - b * ncomp);
   const double *th = theta + b * ld;
   double *out = derived + (b * ncomp + c) * PSFMC_DERIVED_STRIDE;
-  const int kind = prog->kind[c];
-  const int flags = prog->flags[c];
+  const int kind = c < ncomp_prog ? prog->kind[c] : -1;
+  const int flags = c < ncomp_prog ? prog->flags[c] : 0;
   if (c == 0 && writer) {
     int sel = 0;
     if (prog->psf_theta_index >= 0) {
@@ -119,7 +123,7 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
     // the small one. Exact (power of two), undone in the epilogue.
     // (only the binary exponent of the total flux matters: float32 exp2 is enough)
     double ftot = 0.0;
-    for (int k = 0; k < ncomp; ++k) {
+    for (int k = 0; k < ncomp_prog; ++k) {
       if (prog->kind[k] == PSFMC_SKY)
         ftot += fabs(slot_value(prog, k, PSFMC_P_ADU, th));
       else
@@ -136,6 +140,12 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
     }
     wscale[b] = sc;
   }
+  // every group of the warp takes part in the kappa iteration (shuffles)
+  const bool is_sersic = live && kind == PSFMC_SERSIC;
+  const double n_index = is_sersic ? slot_value(prog, c, PSFMC_P_INDEX, th) : 0.5;
+  double lgam_a1;
+  const double kappa = gammaincinv_half_group(2.0 * n_index, glane, is_sersic, &lgam_a1);
+  if (!live) return;
   if (kind == PSFMC_SKY) {
     if (writer) out[D_SKY_ADU] = slot_value(prog, c, PSFMC_P_ADU, th);
   } else if (kind == PSFMC_POINT) {
@@ -157,48 +167,45 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
     }
     // separable stamp weights (PointSource.py:40-56: kern = prod over (x, y) of
     // lanczos(diff) or 1 - |diff|), measured from the UNCLIPPED position; lane i
-    // computes tap i of the x axis, lane 7 + i tap i of the y axis
-    if (lane < 14) {
-      const bool along_y = lane >= 7;
-      const int i = along_y ? lane - 7 : lane;
-      const double pos = (along_y ? ymin : xmin) + (double)i;
-      const double centre = along_y ? y : x;
-      double wgt = 0.0;
-      if (pos <= (along_y ? ymax : xmax))
-        wgt = (flags & PSFMC_FLAG_BILINEAR) ? 1.0 - fabs(pos - centre)
-                                            : lanczos3_ref(pos - centre);
-      out[(along_y ? D_PS_WY : D_PS_WX) + i] = wgt;
+    // of the group computes tap i of the x axis, then tap i of the y axis
+    if (glane < 7) {
+#pragma unroll
+      for (int axis = 0; axis < 2; ++axis) {
+        const bool along_y = axis == 1;
+        const double pos = (along_y ? ymin : xmin) + (double)glane;
+        const double centre = along_y ? y : x;
+        double wgt = 0.0;
+        if (pos <= (along_y ? ymax : xmax))
+          wgt = (flags & PSFMC_FLAG_BILINEAR) ? 1.0 - fabs(pos - centre)
+                                              : lanczos3_ref(pos - centre);
+        out[(along_y ? D_PS_WY : D_PS_WX) + glane] = wgt;
+      }
     }
-  } else {  // PSFMC_SERSIC: Sersic.py:73-96 (transform), :47-71 (kappa, sb_eff)
+  } else if (kind == PSFMC_SERSIC && writer) {  // Sersic.py:73-96 (transform), :47-71 (kappa, sb_eff)
     double x0 = slot_value(prog, c, PSFMC_P_X, th);
     double y0 = slot_value(prog, c, PSFMC_P_Y, th);
     double mag = slot_value(prog, c, PSFMC_P_MAG, th);
     double reff = slot_value(prog, c, PSFMC_P_REFF, th);
     double reff_b = slot_value(prog, c, PSFMC_P_REFF_B, th);
-    double n = slot_value(prog, c, PSFMC_P_INDEX, th);
+    double n = n_index;
     double angle = slot_value(prog, c, PSFMC_P_ANGLE, th);
     if (flags & PSFMC_FLAG_ANGLE_DEGREES) angle = angle * (PSFMC_PI / 180.0);  // np.deg2rad
     angle += 0.5 * PSFMC_PI;
     double sn = sin(angle), cs = cos(angle);
-    double lgam_a1;
-    double kappa = gammaincinv_half_warp(2.0 * n, lane, &lgam_a1);
     // Gamma(2n) = exp(lgamma(2n + 1)) / (2n); overflows to inf for n >= 86 like
     // scipy.special.gamma (-> NaN -> lnL = -inf, as in the reference)
     double gamma_2n = exp(lgam_a1) / (2.0 * n);
     double flux = mag_to_flux(mag, prog->mag_zp);
-    if (writer) {
-      out[D_SER_X0] = x0;
-      out[D_SER_Y0] = y0;
-      out[D_SER_A00] = cs / reff;
-      out[D_SER_A01] = sn / reff;
-      out[D_SER_A10] = -sn / reff_b;
-      out[D_SER_A11] = cs / reff_b;
-      out[D_SER_P] = 0.5 / n;
-      out[D_SER_KAPPA] = kappa;
-      out[D_SER_SBEFF] = sersic_sb_eff(flux, n, reff, reff_b, kappa, gamma_2n);
-    }
+    out[D_SER_X0] = x0;
+    out[D_SER_Y0] = y0;
+    out[D_SER_A00] = cs / reff;
+    out[D_SER_A01] = sn / reff;
+    out[D_SER_A10] = -sn / reff_b;
+    out[D_SER_A11] = cs / reff_b;
+    out[D_SER_P] = 0.5 / n;
+    out[D_SER_KAPPA] = kappa;
+    out[D_SER_SBEFF] = sersic_sb_eff(flux, n, reff, reff_b, kappa, gamma_2n);
   }
-  __syncwarp();
   if (rconst && writer) {
     float *rc = rconst + (b * ncomp + c) * PSFMC_RC_STRIDE;
     if (kind == PSFMC_SKY) {

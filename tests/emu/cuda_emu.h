@@ -276,6 +276,18 @@ inline T __shfl_up_sync(unsigned, T v, int delta, int width = 32) {
   return out;
 }
 
+inline int __all_sync(unsigned, int pred) {
+  int all = 1;
+  for (int src = 0; src < 32; ++src) {   // one exchange per source lane keeps it simple
+    int got = 0;
+    int mine = pred ? 1 : 0;
+    emu::warp_exchange(&mine, &got, sizeof(int), src);
+    int lane_alive = src < emu::S().warps[emu::S().cur->linear / 32].live ? 1 : 1;
+    (void)lane_alive;
+    all &= got;
+  }
+  return all;
+}
 template <typename T>
 inline T __ldg(const T *p) { return *p; }
 inline double atomicAdd(double *p, double v) { double o = *p; *p += v; return o; }
