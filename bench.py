@@ -251,6 +251,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must
+        # carry the one JSON line only
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
 
     walkers = args.walkers or default_walkers(args.workload)
@@ -491,7 +495,9 @@ def run_reference(args):
         'ms_per_step': round(1e3 * elapsed / args.steps, 3), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 (numpy, float32 storage)',
         'data': 'synthetic walkers drawn from the model priors (seeded)',
-        'config': {'workload': workload_description(args.workload, walkers)},
+        'config': {'workload': workload_description(args.workload, walkers),
+                   'walkers_per_gpu': walkers, 'batch_per_launch': walkers // 2,
+                   'ndim': ndim, 'frame': list(config.obs_data.shape)},
         'cpu_baseline': {'value': round(rate, 1), 'unit': UNIT, 'cores': port.cores,
                          'kind': 'port', 'sample': sample_text},
         'e2e': {'value': round(rate, 1), 'unit': UNIT, 'h2d_bytes_per_step': 0,
