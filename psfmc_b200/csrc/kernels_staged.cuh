@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "fft.cuh"
 #include "render.cuh"
+#include "tma.cuh"
 
 namespace psfmc {
 
@@ -173,8 +174,23 @@ __global__ void cols_kernel(Frame fr, int CB, const cplx<T> *__restrict__ tw_h,
   cplx<T> *base = scratch + (b * ncol + c0) * (long long)H;
   const int nel = CB * H;
   const int nvalid = (ncol - c0 < CB ? ncol - c0 : CB) * H;
+#ifndef PSFMC_EMU
+  // The CTA's columns are one contiguous run of the column-major scratch: fetch
+  // them with a single bulk asynchronous copy (TMA) while the twiddles load.
+  __shared__ __align__(8) unsigned long long tile_bar;
+  const unsigned tile_bytes = (unsigned)nvalid * (unsigned)sizeof(cplx<T>);
+  if (tid == 0) mbar_init(&tile_bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&tile_bar, tile_bytes);
+    bulk_load(tile, base, tile_bytes, &tile_bar);
+  }
+  for (int e = nvalid + tid; e < nel; e += nthreads) tile[e] = mk<T>((T)0, (T)0);
+  mbar_wait(&tile_bar, 0);
+#else
   for (int e = tid; e < nel; e += nthreads)
     tile[e] = (e < nvalid) ? base[e] : mk<T>((T)0, (T)0);
+#endif
   __syncthreads();
 
   const int tpc = H >> 3;
@@ -202,7 +218,14 @@ __global__ void cols_kernel(Frame fr, int CB, const cplx<T> *__restrict__ tw_h,
 
   fft_line_smem<T, true>(tile + col * H, H, fr.logH, tl, tw_s);
 
+#ifndef PSFMC_EMU
+  // (fft_line_smem ends with a CTA barrier after its last stores) one bulk store
+  bulk_store_fence();
+  __syncthreads();
+  if (tid == 0) bulk_store_and_wait(base, tile, tile_bytes);
+#else
   for (int e = tid; e < nvalid; e += nthreads) base[e] = tile[e];
+#endif
 }
 
 // ------------------------------------------------------------- rows_inv --
