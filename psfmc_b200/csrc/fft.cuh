@@ -62,10 +62,19 @@ __device__ __forceinline__ cplx<T> twiddle(const cplx<T> *tw, int idx) {
   return INV ? cconj(w) : w;
 }
 
+// Bank-conflict-free exchange layout between the passes of fft_line_smem: element i
+// of a line sits at i ^ ((i >> 3) & 15). The strided stores of a Stockham pass
+// (lane stride 8 elements) and its contiguous loads are then both conflict-free for
+// 8- and 16-byte elements. Only the intermediate passes use it: the first pass reads
+// and the last pass writes the plain layout, so callers never see the swizzle.
+__device__ __forceinline__ int fft_swz(int i, bool on) {
+  return on ? (i ^ ((i >> 3) & 15)) : i;
+}
+
 // In-place length-L FFT of one contiguous shared-memory line, executed by the
 // L/8 threads with local indices tl = 0..L/8-1 (each owns 8 points per stage).
 // ALL threads of the CTA must call this together (it contains __syncthreads).
-// `tw` holds exp(-2 pi i k / L), k = 0..L-1. L is a power of two >= 8.
+// `tw` holds exp(-2 pi i k / L), k = 0..L-1. L is a power of two >= 16.
 template <typename T, bool INV>
 __device__ __forceinline__ void fft_line_smem(cplx<T> *line, int L, int logL, int tl,
                                               const cplx<T> *tw) {
@@ -74,9 +83,10 @@ __device__ __forceinline__ void fft_line_smem(cplx<T> *line, int L, int logL, in
   int Ns = 1, logNs = 0;
   cplx<T> v[8];
   for (int s = 0; s < n8; ++s) {
+    const bool in_swz = s > 0, out_swz = !(s == n8 - 1 && rem == 0);
     const int j = tl;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = line[j + r * L8];
+    for (int r = 0; r < 8; ++r) v[r] = line[fft_swz(j + r * L8, in_swz)];
     const int k = j & (Ns - 1);
     const int tstep = k << (logL - logNs - 3);   // k * L / (Ns * 8)
     if (Ns > 1) {
@@ -87,18 +97,20 @@ __device__ __forceinline__ void fft_line_smem(cplx<T> *line, int L, int logL, in
     __syncthreads();
     const int j0 = ((j - k) << 3) + k;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) line[j0 + r * Ns] = v[r];
+    for (int r = 0; r < 8; ++r) line[fft_swz(j0 + r * Ns, out_swz)] = v[r];
     __syncthreads();
     Ns <<= 3;
     logNs += 3;
   }
+  // remainder pass (radix 4 or 2): always the last one, after at least one radix-8
+  // pass: reads the swizzled layout, writes the plain one
   if (rem == 2) {
     const int L4 = L >> 2;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int j = tl + q * L8;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) v[q * 4 + r] = line[j + r * L4];
+      for (int r = 0; r < 4; ++r) v[q * 4 + r] = line[fft_swz(j + r * L4, true)];
       const int k = j & (Ns - 1);
       const int tstep = k << (logL - logNs - 2);
 #pragma unroll
@@ -121,8 +133,8 @@ __device__ __forceinline__ void fft_line_smem(cplx<T> *line, int L, int logL, in
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int j = tl + q * L8;
-      v[q * 2] = line[j];
-      v[q * 2 + 1] = line[j + L2];
+      v[q * 2] = line[fft_swz(j, true)];
+      v[q * 2 + 1] = line[fft_swz(j + L2, true)];
       const int k = j & (Ns - 1);
       const int tstep = k << (logL - logNs - 1);
       v[q * 2 + 1] = v[q * 2 + 1] * twiddle<T, INV>(tw, tstep);

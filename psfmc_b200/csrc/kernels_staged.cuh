@@ -25,6 +25,9 @@
 
 namespace psfmc {
 
+// padding between the rows of a row-kernel tile, in elements (32 bytes)
+#define PSFMC_ROW_PAD(T) (32 / (int)sizeof(cplx<T>))
+
 #define PSFMC_SRC_RENDER 0      // rows come from the model renderer
 #define PSFMC_SRC_PSFPAD 1      // rows come from padded PSF / variance frames (setup)
 #define PSFMC_SRC_RENDER_PS 2   // renderer, point sources only
@@ -52,8 +55,11 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const long long b = blockIdx.y;
   const int y0 = blockIdx.x * RB;
+  // rows are PITCH elements apart (32 bytes of padding): the transposed accesses
+  // below (lanes over the RB rows of one kx) then hit different banks
+  const int PITCH = W + PSFMC_ROW_PAD(T);
   cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
-  cplx<T> *tw_s = tile + RB * W;
+  cplx<T> *tw_s = tile + RB * PITCH;
   double *der_s = reinterpret_cast<double *>(tw_s + W);
 
   load_twiddles<T>(tw_s, tw_w, W, tid, nthreads);
@@ -72,7 +78,7 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
     for (int e = tid; e < npx; e += nthreads) {
       int r = e / W, x = e - r * W;
       long long g = (b * H + (y0 + r)) * (long long)W + x;
-      tile[e] = mk<T>((T)pad_a[g], (T)pad_b[g]);
+      tile[r * PITCH + x] = mk<T>((T)pad_a[g], (T)pad_b[g]);
     }
   } else if (sizeof(T) == 8 || SRC == PSFMC_SRC_RENDER_PS) {
     const bool round_f32 = (precision == PSFMC_PREC_FP64_RAWF32);
@@ -81,7 +87,7 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
       double val = raw_pixel_f64(prog, der_s, x, y0 + r, round_f32,
                                  SRC == PSFMC_SRC_RENDER_PS);
       T a = (T)val;
-      tile[e] = mk<T>(a, a * a * wsc);
+      tile[r * PITCH + x] = mk<T>(a, a * a * wsc);
       if (raw_out) raw_out[(b * H + (y0 + r)) * (long long)W + x] = a;
     }
   } else {
@@ -118,7 +124,7 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
     for (int i = 0; i < 8; ++i) {
       int e = tid + i * nthreads;
       int r = e / W, x = e - r * W;
-      tile[e] = mk<T>((T)acc[i], (T)(acc[i] * acc[i]) * wsc);
+      tile[r * PITCH + x] = mk<T>((T)acc[i], (T)(acc[i] * acc[i]) * wsc);
       if (raw_out) raw_out[(b * H + (y0 + r)) * (long long)W + x] = (T)acc[i];
     }
   }
@@ -128,7 +134,7 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
   {
     const int tpr = W >> 3;  // threads per row
     const int r = tid / tpr, tl = tid - r * tpr;
-    fft_line_smem<T, false>(tile + r * W, W, fr.logW, tl, tw_s);
+    fft_line_smem<T, false>(tile + r * PITCH, W, fr.logW, tl, tw_s);
   }
 
   // ---- split z-spectrum into the spectra of the two real rows and store
@@ -138,8 +144,8 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
   for (int e = tid; e < nout; e += nthreads) {
     int r = e % RB, c = e / RB;
     int kx = (c < Wc) ? c : c - Wc;
-    cplx<T> zk = tile[r * W + kx];
-    cplx<T> zm = cconj(tile[r * W + ((W - kx) & (W - 1))]);
+    cplx<T> zk = tile[r * PITCH + kx];
+    cplx<T> zm = cconj(tile[r * PITCH + ((W - kx) & (W - 1))]);
     cplx<T> o;
     if (c < Wc) {
       o = mk<T>(half * (zk.x + zm.x), half * (zk.y + zm.y));
@@ -276,8 +282,9 @@ __global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const long long b = blockIdx.y;
   const int y0 = blockIdx.x * RB;
+  const int PITCH = W + PSFMC_ROW_PAD(T);   // see rows_fwd_kernel
   cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
-  cplx<T> *tw_s = tile + RB * W;
+  cplx<T> *tw_s = tile + RB * PITCH;
   double *red_s = reinterpret_cast<double *>(tw_s + W);
   load_twiddles<T>(tw_s, tw_w, W, tid, nthreads);
 
@@ -290,12 +297,12 @@ __global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw
     cplx<T> a = sa[(long long)kx * H + y0 + r];
     cplx<T> bb = sb[(long long)kx * H + y0 + r];
     if (kx > 0 && kx < W - kx) {
-      tile[r * W + kx] = mk<T>(a.x - bb.y, a.y + bb.x);
-      tile[r * W + (W - kx)] = mk<T>(a.x + bb.y, bb.x - a.y);
+      tile[r * PITCH + kx] = mk<T>(a.x - bb.y, a.y + bb.x);
+      tile[r * PITCH + (W - kx)] = mk<T>(a.x + bb.y, bb.x - a.y);
     } else {
       // DC and Nyquist terms of a real row are real: a c2r transform ignores
       // their imaginary parts (numpy.fft.irfft does the same)
-      tile[r * W + kx] = mk<T>(a.x, bb.x);
+      tile[r * PITCH + kx] = mk<T>(a.x, bb.x);
     }
   }
   __syncthreads();
@@ -303,7 +310,7 @@ __global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw
   {
     const int tpr = W >> 3;
     const int r = tid / tpr, tl = tid - r * tpr;
-    fft_line_smem<T, true>(tile + r * W, W, fr.logW, tl, tw_s);
+    fft_line_smem<T, true>(tile + r * PITCH, W, fr.logW, tl, tw_s);
   }
 
   // undo the (exact, power-of-two) channel scalings of the variance image
@@ -315,7 +322,7 @@ __global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw
   for (int e = tid; e < npx; e += nthreads) {
     int r = e / W, x = e - r * W;
     long long g = (long long)(y0 + r) * W + x;
-    cplx<T> yv = tile[e];
+    cplx<T> yv = tile[r * PITCH + x];
     yv.y *= unscale;
     T resid, ivm;
     double t = Epilogue<T>::term(yv.x, yv.y, obs[g], ovar[g], &resid, &ivm);

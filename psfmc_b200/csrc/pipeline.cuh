@@ -71,7 +71,7 @@ inline StagedPlan make_staged_plan(int H, int W, int n_components, size_t sizeof
   p.n_colblk = (ncol + best - 1) / best;
   p.threads_cols = best * (H / 8);
   size_t csz = 2 * sizeof_real;
-  p.smem_rows = (size_t)(rb * W + W) * csz +
+  p.smem_rows = (size_t)(rb * (W + 4) + W) * csz +
                 (size_t)(n_components * PSFMC_DERIVED_STRIDE + 64) * sizeof(double);
   p.smem_cols = (size_t)(best * H + H) * csz;
   p.scratch_elems_per_walker = (size_t)ncol * H;
