@@ -58,6 +58,7 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
   // rows are PITCH elements apart (32 bytes of padding): the transposed accesses
   // below (lanes over the RB rows of one kx) then hit different banks
   const int PITCH = W + PSFMC_ROW_PAD(T);
+  const int logRB = 31 - __clz(RB);          // RB is a power of two
   cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
   cplx<T> *tw_s = tile + RB * PITCH;
   double *der_s = reinterpret_cast<double *>(tw_s + W);
@@ -76,14 +77,14 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
   const T wsc = (SRC != PSFMC_SRC_PSFPAD) ? (T)wscale[b] : (T)1;
   if (SRC == PSFMC_SRC_PSFPAD) {
     for (int e = tid; e < npx; e += nthreads) {
-      int r = e / W, x = e - r * W;
+      int r = e >> fr.logW, x = e & (W - 1);
       long long g = (b * H + (y0 + r)) * (long long)W + x;
       tile[r * PITCH + x] = mk<T>((T)pad_a[g], (T)pad_b[g]);
     }
   } else if (sizeof(T) == 8 || SRC == PSFMC_SRC_RENDER_PS) {
     const bool round_f32 = (precision == PSFMC_PREC_FP64_RAWF32);
     for (int e = tid; e < npx; e += nthreads) {
-      int r = e / W, x = e - r * W;
+      int r = e >> fr.logW, x = e & (W - 1);
       double val = raw_pixel_f64(prog, der_s, x, y0 + r, round_f32,
                                  SRC == PSFMC_SRC_RENDER_PS);
       T a = (T)val;
@@ -107,7 +108,7 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           int e = tid + i * nthreads;
-          int r = e / W, x = e - r * W;
+          int r = e >> fr.logW, x = e & (W - 1);
           acc[i] += (float)point_pixel(d, x, y0 + r);
         }
       } else {
@@ -115,7 +116,7 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           int e = tid + i * nthreads;
-          int r = e / W, x = e - r * W;
+          int r = e >> fr.logW, x = e & (W - 1);
           acc[i] += sersic_pixel_f32(s, (float)x, (float)(y0 + r));
         }
       }
@@ -123,7 +124,7 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       int e = tid + i * nthreads;
-      int r = e / W, x = e - r * W;
+      int r = e >> fr.logW, x = e & (W - 1);
       tile[r * PITCH + x] = mk<T>((T)acc[i], (T)(acc[i] * acc[i]) * wsc);
       if (raw_out) raw_out[(b * H + (y0 + r)) * (long long)W + x] = (T)acc[i];
     }
@@ -133,7 +134,7 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
   // ---- FFT along x of every row of the tile
   {
     const int tpr = W >> 3;  // threads per row
-    const int r = tid / tpr, tl = tid - r * tpr;
+    const int r = tid >> (fr.logW - 3), tl = tid & (tpr - 1);
     fft_line_smem<T, false>(tile + r * PITCH, W, fr.logW, tl, tw_s);
   }
 
@@ -142,7 +143,7 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
   const int nout = RB * 2 * Wc;
   const T half = (T)0.5;
   for (int e = tid; e < nout; e += nthreads) {
-    int r = e % RB, c = e / RB;
+    int r = e & (RB - 1), c = e >> logRB;
     int kx = (c < Wc) ? c : c - Wc;
     cplx<T> zk = tile[r * PITCH + kx];
     cplx<T> zm = cconj(tile[r * PITCH + ((W - kx) & (W - 1))]);
@@ -200,7 +201,7 @@ __global__ void cols_kernel(Frame fr, int CB, const cplx<T> *__restrict__ tw_h,
   __syncthreads();
 
   const int tpc = H >> 3;
-  const int col = tid / tpc, tl = tid - col * tpc;
+  const int col = tid >> (fr.logH - 3), tl = tid & (tpc - 1);
   fft_line_smem<T, false>(tile + col * H, H, fr.logH, tl, tw_s);
 
   if (MODE == PSFMC_COLS_SETUP) {
@@ -208,7 +209,7 @@ __global__ void cols_kernel(Frame fr, int CB, const cplx<T> *__restrict__ tw_h,
     const T scale = (T)(1.0 / ((double)fr.H * (double)fr.W));
     cplx<T> *obase = spec_out + (b * ncol + c0) * (long long)H;
     for (int e = tid; e < nvalid; e += nthreads) {
-      int cc = c0 + e / H, ky = e % H;
+      int cc = c0 + (e >> fr.logH), ky = e & (H - 1);
       int kx = cc < Wc ? cc : cc - Wc;
       T sgn = ((kx + ky) & 1) ? -scale : scale;
       obase[e] = mk<T>(tile[e].x * sgn, tile[e].y * sgn);
@@ -283,6 +284,7 @@ __global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw
   const long long b = blockIdx.y;
   const int y0 = blockIdx.x * RB;
   const int PITCH = W + PSFMC_ROW_PAD(T);   // see rows_fwd_kernel
+  const int logRB = 31 - __clz(RB);
   cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
   cplx<T> *tw_s = tile + RB * PITCH;
   double *red_s = reinterpret_cast<double *>(tw_s + W);
@@ -293,7 +295,7 @@ __global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw
   const cplx<T> *sb = sa + (long long)Wc * H;
   const int nin = RB * Wc;
   for (int e = tid; e < nin; e += nthreads) {
-    int r = e % RB, kx = e / RB;
+    int r = e & (RB - 1), kx = e >> logRB;
     cplx<T> a = sa[(long long)kx * H + y0 + r];
     cplx<T> bb = sb[(long long)kx * H + y0 + r];
     if (kx > 0 && kx < W - kx) {
@@ -309,7 +311,7 @@ __global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw
 
   {
     const int tpr = W >> 3;
-    const int r = tid / tpr, tl = tid - r * tpr;
+    const int r = tid >> (fr.logW - 3), tl = tid & (tpr - 1);
     fft_line_smem<T, true>(tile + r * PITCH, W, fr.logW, tl, tw_s);
   }
 
@@ -320,7 +322,7 @@ __global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw
   double acc = 0.0;
   const int npx = RB * W;
   for (int e = tid; e < npx; e += nthreads) {
-    int r = e / W, x = e - r * W;
+    int r = e >> fr.logW, x = e & (W - 1);
     long long g = (long long)(y0 + r) * W + x;
     cplx<T> yv = tile[r * PITCH + x];
     yv.y *= unscale;

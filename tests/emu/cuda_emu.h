@@ -294,6 +294,7 @@ inline double atomicAdd(double *p, double v) { double o = *p; *p += v; return o;
 inline float atomicAdd(float *p, float v) { float o = *p; *p += v; return o; }
 inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p += v; return o; }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
 
