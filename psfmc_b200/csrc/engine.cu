@@ -610,6 +610,10 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       rc = fail(PSFMC_ERR_CUDA, "cudaStreamCreate failed");
       break;
     }
+    if (staged_prepare_device<T>()) {
+      rc = fail(PSFMC_ERR_CUDA, "cannot raise the shared-memory limit of the staged kernels");
+      break;
+    }
     std::vector<cplx<double>> spec64;
     if ((rc = compute_spectra(d, eng->plan, &spec64))) break;
     // Balance the two channels of the packed inverse transform: scale the

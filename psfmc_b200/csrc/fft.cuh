@@ -62,6 +62,23 @@ __device__ __forceinline__ cplx<T> twiddle(const cplx<T> *tw, int idx) {
   return INV ? cconj(w) : w;
 }
 
+// Twiddle table of fft_line_smem, ordered by pass so that the lanes of a warp read
+// consecutive entries (no bank conflicts): for every pass after the first, with
+// sub-transform length Ns and radix R, entry [(r - 1) * Ns + k] = exp(-2 pi i r k /
+// (R Ns)), r = 1..R-1, k = 0..Ns-1; passes are stored back to back (fewer than L
+// entries in total). Filled on the host by fill_twiddles (pipeline.cuh).
+PSFMC_HD inline int twiddle_table_entries(int logL) {
+  const int n8 = logL / 3, rem = logL - 3 * n8;
+  int total = 0, Ns = 1;
+  for (int s = 0; s < n8; ++s) {
+    if (s > 0) total += 7 * Ns;
+    Ns <<= 3;
+  }
+  if (rem == 2) total += 3 * Ns;
+  if (rem == 1) total += Ns;
+  return total;
+}
+
 // Bank-conflict-free exchange layout between the passes of fft_line_smem: element i
 // of a line sits at i ^ ((i >> 3) & 15). The strided stores of a Stockham pass
 // (lane stride 8 elements) and its contiguous loads are then both conflict-free for
@@ -74,13 +91,14 @@ __device__ __forceinline__ int fft_swz(int i, bool on) {
 // In-place length-L FFT of one contiguous shared-memory line, executed by the
 // L/8 threads with local indices tl = 0..L/8-1 (each owns 8 points per stage).
 // ALL threads of the CTA must call this together (it contains __syncthreads).
-// `tw` holds exp(-2 pi i k / L), k = 0..L-1. L is a power of two >= 16.
+// `tw` is the pass-ordered twiddle table described above. L is a power of two >= 16.
 template <typename T, bool INV>
 __device__ __forceinline__ void fft_line_smem(cplx<T> *line, int L, int logL, int tl,
                                               const cplx<T> *tw) {
   const int n8 = logL / 3, rem = logL - 3 * n8;
   const int L8 = L >> 3;
   int Ns = 1, logNs = 0;
+  const cplx<T> *twp = tw;     // table of the current pass
   cplx<T> v[8];
   for (int s = 0; s < n8; ++s) {
     const bool in_swz = s > 0, out_swz = !(s == n8 - 1 && rem == 0);
@@ -88,10 +106,10 @@ __device__ __forceinline__ void fft_line_smem(cplx<T> *line, int L, int logL, in
 #pragma unroll
     for (int r = 0; r < 8; ++r) v[r] = line[fft_swz(j + r * L8, in_swz)];
     const int k = j & (Ns - 1);
-    const int tstep = k << (logL - logNs - 3);   // k * L / (Ns * 8)
     if (Ns > 1) {
 #pragma unroll
-      for (int r = 1; r < 8; ++r) v[r] = v[r] * twiddle<T, INV>(tw, r * tstep);
+      for (int r = 1; r < 8; ++r) v[r] = v[r] * twiddle<T, INV>(twp, (r - 1) * Ns + k);
+      twp += 7 * Ns;
     }
     dft8<T, INV>(v);
     __syncthreads();
@@ -112,10 +130,9 @@ __device__ __forceinline__ void fft_line_smem(cplx<T> *line, int L, int logL, in
 #pragma unroll
       for (int r = 0; r < 4; ++r) v[q * 4 + r] = line[fft_swz(j + r * L4, true)];
       const int k = j & (Ns - 1);
-      const int tstep = k << (logL - logNs - 2);
 #pragma unroll
       for (int r = 1; r < 4; ++r)
-        v[q * 4 + r] = v[q * 4 + r] * twiddle<T, INV>(tw, r * tstep);
+        v[q * 4 + r] = v[q * 4 + r] * twiddle<T, INV>(twp, (r - 1) * Ns + k);
       dft4<T, INV>(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
     }
     __syncthreads();
@@ -136,8 +153,7 @@ __device__ __forceinline__ void fft_line_smem(cplx<T> *line, int L, int logL, in
       v[q * 2] = line[fft_swz(j, true)];
       v[q * 2 + 1] = line[fft_swz(j + L2, true)];
       const int k = j & (Ns - 1);
-      const int tstep = k << (logL - logNs - 1);
-      v[q * 2 + 1] = v[q * 2 + 1] * twiddle<T, INV>(tw, tstep);
+      v[q * 2 + 1] = v[q * 2 + 1] * twiddle<T, INV>(twp, k);
       dft2<T, INV>(v[q * 2], v[q * 2 + 1]);
     }
     __syncthreads();

@@ -114,10 +114,16 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
       } else {
         const SersicF32 s = make_sersic_f32(d);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int e = tid + i * nthreads;
-          int r = e >> fr.logW, x = e & (W - 1);
-          acc[i] += sersic_pixel_f32(s, (float)x, (float)(y0 + r));
+        for (int i = 0; i < 8; i += 2) {   // two pixels per packed instruction
+          const int e0 = tid + i * nthreads, e1 = e0 + nthreads;
+          const int r0 = e0 >> fr.logW, x0 = e0 & (W - 1);
+          const int r1 = e1 >> fr.logW, x1 = e1 & (W - 1);
+          const cplx<float> dx = mk<float>(((float)x0 - s.xi) - s.xf, ((float)x1 - s.xi) - s.xf);
+          const cplx<float> dy = mk<float>(((float)(y0 + r0) - s.yi) - s.yf,
+                                           ((float)(y0 + r1) - s.yi) - s.yf);
+          const cplx<float> val = sersic_pair2_f32(s, dx, dy);
+          acc[i] += val.x;
+          acc[i + 1] += val.y;
         }
       }
     }

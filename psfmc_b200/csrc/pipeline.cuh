@@ -169,6 +169,27 @@ inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
   }
 }
 
+// Frames of 1024 columns/rows need a little more than the default 48 KB of dynamic
+// shared memory: raise the limit of every staged kernel of real type T (and of the
+// float64 setup kernels) once per device.
+template <typename T>
+inline int staged_prepare_device() {
+  const int limit = 96 * 1024;
+  cudaError_t err = cudaSuccess;
+  auto raise = [&](auto kernel) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         limit);
+    if (e != cudaSuccess) err = e;
+  };
+  raise(rows_fwd_kernel<T, PSFMC_SRC_RENDER>);
+  raise(rows_fwd_kernel<T, PSFMC_SRC_RENDER_PS>);
+  raise(rows_fwd_kernel<double, PSFMC_SRC_PSFPAD>);
+  raise(cols_kernel<T, PSFMC_COLS_CONV>);
+  raise(cols_kernel<double, PSFMC_COLS_SETUP>);
+  raise(rows_inv_kernel<T>);
+  return err == cudaSuccess ? 0 : 1;
+}
+
 // Setup: spectra of the K padded PSF / variance frames, always float64.
 //   pad_psf, pad_var: [K][H][W] doubles on the device; spec_out: [K][2*Wc][H]
 inline void launch_staged_setup(const StagedPlan &plan, const cplx<double> *tw_w,
@@ -187,21 +208,44 @@ inline void launch_staged_setup(const StagedPlan &plan, const cplx<double> *tw_w
                 (const int *)nullptr, scratch, spec_out);
 }
 
-// exp(-2 pi i k / L), k = 0..L-1, computed in long double on the host.
+// Pass-ordered twiddle table of fft_line_smem (fft.cuh), computed in long double on
+// the host; `tw` has room for L entries, of which twiddle_table_entries() are used.
 template <typename T>
 inline void fill_twiddles(cplx<T> *tw, int L) {
+  const long double pi = 3.14159265358979323846264338327950288L;
+  auto put = [&](int pos, long long num, long long den) {   // exp(-2 pi i num / den)
+    num %= den;
+    long double ang = -2.0L * pi * (long double)num / (long double)den;
+    long double c = cosl(ang), sn = sinl(ang);
+    if ((4 * num) % den == 0) {   // exact values at the quadrant points
+      const int q = (int)((4 * num) / den);
+      const long double cq[4] = {1, 0, -1, 0}, sq[4] = {0, -1, 0, 1};
+      c = cq[q];
+      sn = sq[q];
+    }
+    tw[pos].x = (T)c;
+    tw[pos].y = (T)sn;
+  };
   for (int k = 0; k < L; ++k) {
-    long double ang = -2.0L * 3.14159265358979323846264338327950288L * k / L;
-    tw[k].x = (T)cosl(ang);
-    tw[k].y = (T)sinl(ang);
+    tw[k].x = (T)1;
+    tw[k].y = (T)0;
   }
-  // exact values at the quadrant points
-  tw[0].x = (T)1; tw[0].y = (T)0;
-  if (L >= 4) {
-    tw[L / 4].x = (T)0; tw[L / 4].y = (T)-1;
-    tw[L / 2].x = (T)-1; tw[L / 2].y = (T)0;
-    tw[3 * L / 4].x = (T)0; tw[3 * L / 4].y = (T)1;
+  const int logL = ilog2(L);
+  const int n8 = logL / 3, rem = logL - 3 * n8;
+  int pos = 0, Ns = 1;
+  for (int s = 0; s < n8; ++s) {
+    if (s > 0) {
+      for (int r = 1; r < 8; ++r)
+        for (int k = 0; k < Ns; ++k) put(pos + (r - 1) * Ns + k, (long long)r * k, 8LL * Ns);
+      pos += 7 * Ns;
+    }
+    Ns <<= 3;
   }
+  if (rem == 2)
+    for (int r = 1; r < 4; ++r)
+      for (int k = 0; k < Ns; ++k) put(pos + (r - 1) * Ns + k, (long long)r * k, 4LL * Ns);
+  if (rem == 1)
+    for (int k = 0; k < Ns; ++k) put(pos + k, k, 2LL * Ns);
 }
 
 }  // namespace psfmc

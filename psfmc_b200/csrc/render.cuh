@@ -308,4 +308,19 @@ __device__ __forceinline__ cplx<float> sersic_pair_f32(const SersicF32 &s, cplx<
   return pfma(sb, q, sb);    // sb * (1 + q)
 }
 
+// Two arbitrary pixels at once (offsets (dx.x, dy.x) and (dx.y, dy.y) from the centre).
+__device__ __forceinline__ cplx<float> sersic_pair2_f32(const SersicF32 &s, cplx<float> dx,
+                                                        cplx<float> dy) {
+  const cplx<float> u = pfma(bcast(s.a00), dx, pmul(bcast(s.a01), dy));
+  const cplx<float> v = pfma(bcast(s.a10), dx, pmul(bcast(s.a11), dy));
+  const cplx<float> sq = pfma(v, v, pmul(u, u));
+  const cplx<float> r2 = pfma(dx, dx, pmul(dy, dy));
+  const cplx<float> e = pmul(bcast(s.p), mk<float>(fast_lg2(sq.x), fast_lg2(sq.y)));
+  const cplx<float> t = mk<float>(fminf(fast_ex2(e.x), 1.0e18f), fminf(fast_ex2(e.y), 1.0e18f));
+  const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0));
+  const cplx<float> sb = mk<float>(fast_ex2(arg.x), fast_ex2(arg.y));
+  const cplx<float> q = pmul(pmul(bcast(s.kq), pmul(t, t)), rcp_pair_fma(r2));
+  return pfma(sb, q, sb);    // sb * (1 + q)
+}
+
 }  // namespace psfmc

@@ -97,7 +97,7 @@ def test_emu_c2_galfit(emu_library, index):
                      'fp32', fp32_bounds(model32, thetas))
 
 
-@pytest.mark.parametrize('size,n_sersic', [(32, 1), (64, 1), (256, 2)])
+@pytest.mark.parametrize('size,n_sersic', [(16, 1), (32, 1), (64, 1), (256, 2)])
 def test_emu_synthetic_frames(emu_library, size, n_sersic):
     from psfmc_b200 import MultiComponentModel
     from psfmc_b200.synthetic import draw_walkers_fast, synthetic_components

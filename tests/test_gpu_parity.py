@@ -129,7 +129,8 @@ def test_c1_images_match_reference_pixels(cuda_library, c1_golden):
     assert np.allclose(imgs['point_source_subtracted'][0], ref, rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize('size,n_sersic', [(256, 2), (512, 3), (64, 1), (32, 1)])
+@pytest.mark.parametrize('size,n_sersic', [(256, 2), (512, 3), (64, 1), (32, 1), (16, 1),
+                                           (1024, 1)])
 def test_synthetic_frames_against_oracle(cuda_library, size, n_sersic):
     """C3 / C4 frame sizes (and small ones) on seeded synthetic inputs."""
     from psfmc_b200 import MultiComponentModel
@@ -137,7 +138,7 @@ def test_synthetic_frames_against_oracle(cuda_library, size, n_sersic):
     comps = synthetic_components(size, n_sersic, dtype=np.float64,
                                  psf_size=min(64, size // 2))
     model = MultiComponentModel(comps, precision='fp64')
-    thetas = draw_walkers_fast(model, 6, seed=size)
+    thetas = draw_walkers_fast(model, 3 if size >= 1024 else 6, seed=size)
     expect = oracle_from_model(model).lnlike_batch(thetas)
     assert_lnl_close(model.log_likelihood_batch(thetas), expect, 'fp64')
     comps = synthetic_components(size, n_sersic, dtype=np.float64,
