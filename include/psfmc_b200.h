@@ -147,6 +147,16 @@ int psfmc_lnlike_batch_device(psfmc_engine *engine, int32_t device_slot,
 int psfmc_render_batch(psfmc_engine *engine, const double *theta, int64_t n_batch,
                        int64_t ld, uint32_t which, double *out);
 
+/* Posterior-image accumulation on the device (psfMC/models.py:74-97 averages five
+ * images per sample; psfMC/analysis/images.py:74-83 re-renders every database row):
+ * for every image selected in `which` (ascending bit order) sums_out receives
+ * [n_selected][height*width] doubles = the SUM over the B parameter vectors, added
+ * up in float64 on the device. The composite IVM is summed as 1/ivm, i.e. in
+ * variance space, exactly like the reference's running mean. Only the sums cross
+ * the bus (not B images). */
+int psfmc_accumulate_batch(psfmc_engine *engine, const double *theta, int64_t n_batch,
+                           int64_t ld, uint32_t which, double *sums_out);
+
 /* Introspection (roofline bookkeeping for bench.py). */
 typedef struct psfmc_info {
   int32_t height, width, n_components, n_sersic, n_point, n_psf, precision;

@@ -71,7 +71,8 @@ class Info(ctypes.Structure):
 # every symbol include/psfmc_b200.h declares
 EXPORTED_SYMBOLS = (
     'psfmc_engine_create', 'psfmc_engine_destroy', 'psfmc_lnlike_batch',
-    'psfmc_lnlike_batch_device', 'psfmc_render_batch', 'psfmc_engine_info',
+    'psfmc_lnlike_batch_device', 'psfmc_render_batch', 'psfmc_accumulate_batch',
+    'psfmc_engine_info',
     'psfmc_engine_profile', 'psfmc_engine_profile_read',
     'psfmc_fp32_peak_probe', 'psfmc_last_error', 'psfmc_abi_version',
 )
@@ -123,6 +124,9 @@ def load(path=None):
     lib.psfmc_render_batch.restype = ctypes.c_int
     lib.psfmc_render_batch.argtypes = [ctypes.c_void_p, dbl_p, ctypes.c_int64,
                                        ctypes.c_int64, ctypes.c_uint32, dbl_p]
+    lib.psfmc_accumulate_batch.restype = ctypes.c_int
+    lib.psfmc_accumulate_batch.argtypes = [ctypes.c_void_p, dbl_p, ctypes.c_int64,
+                                           ctypes.c_int64, ctypes.c_uint32, dbl_p]
     lib.psfmc_engine_info.restype = ctypes.c_int
     lib.psfmc_engine_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(Info)]
     lib.psfmc_engine_profile.restype = ctypes.c_int

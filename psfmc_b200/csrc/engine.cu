@@ -107,6 +107,7 @@ struct DeviceState {
   size_t prof_used = 0;
   DevBuf<cplx<T>> scratch;
   DevBuf<T> img[4];
+  DevBuf<double> img_acc;
   PinBuf<double> theta_pin, lnl_pin;
   PinBuf<T> img_pin;
   // rows of the current host call
@@ -121,7 +122,7 @@ struct EngineBase {
   virtual int lnlike_device(int slot, const double *theta, long long B, long long ld,
                             double *lnl, void *stream) = 0;
   virtual int render(const double *theta, long long B, long long ld, unsigned which,
-                     double *out) = 0;
+                     double *out, bool accumulate) = 0;
   int H = 0, W = 0, precision = 0;
   Program prog_h;
   int n_sersic = 0, n_point = 0;
@@ -159,6 +160,7 @@ struct Engine : EngineBase {
       d.psf_sel.release();
       d.scratch.release();
       for (auto &im : d.img) im.release();
+      d.img_acc.release();
       d.theta_pin.release();
       d.lnl_pin.release();
       d.img_pin.release();
@@ -340,9 +342,11 @@ struct Engine : EngineBase {
     return 0;
   }
 
-  // Blob images (psfMC/models.py:213-226); device 0 only, chunked.
-  int render(const double *theta, long long B, long long ld, unsigned which,
-             double *out) override {
+  // Blob images (psfMC/models.py:213-226); device 0 only, chunked. With
+  // `accumulate` the images are summed over the batch on the device (float64) and
+  // only the sums come back: out[n_selected][H*W].
+  int render(const double *theta, long long B, long long ld, unsigned which, double *out,
+             bool accumulate) override {
     if (B <= 0 || which == 0) return 0;
     DeviceState<T> &d = devs[0];
     CUDA_TRY(cudaSetDevice(d.ordinal));
@@ -355,9 +359,15 @@ struct Engine : EngineBase {
     for (int k = 0; k < 4; ++k)
       if (d.img[k].ensure((size_t)chunk * npx))
         return fail(PSFMC_ERR_CUDA, "device allocation failed (images)");
-    if (d.img_pin.ensure((size_t)chunk * npx) || d.theta.ensure((size_t)chunk * ld) ||
-        d.lnl.ensure((size_t)chunk))
+    if (d.theta.ensure((size_t)chunk * ld) || d.lnl.ensure((size_t)chunk))
       return fail(PSFMC_ERR_CUDA, "allocation failed (image staging)");
+    if (accumulate) {
+      if (d.img_acc.ensure((size_t)nsel * npx))
+        return fail(PSFMC_ERR_CUDA, "device allocation failed (image sums)");
+      CUDA_TRY(cudaMemsetAsync(d.img_acc.ptr, 0, (size_t)nsel * npx * sizeof(double), d.stream));
+    } else if (d.img_pin.ensure((size_t)chunk * npx)) {
+      return fail(PSFMC_ERR_CUDA, "allocation failed (image staging)");
+    }
     for (long long start = 0; start < B; start += chunk) {
       long long nb = B - start < chunk ? B - start : chunk;
       int rc = ensure_batch(d, nb, true);
@@ -391,15 +401,28 @@ struct Engine : EngineBase {
           CUDA_TRY(cudaGetLastError());
           src = d.img[0].ptr;
         }
-        CUDA_TRY(cudaMemcpyAsync(d.img_pin.ptr, src, (size_t)nb * npx * sizeof(T),
-                                 cudaMemcpyDeviceToHost, d.stream));
-        CUDA_TRY(cudaStreamSynchronize(d.stream));
-        double *dst = out + ((size_t)sel * B + start) * npx;
-        for (size_t e = 0; e < (size_t)nb * npx; ++e) dst[e] = (double)d.img_pin.ptr[e];
+        if (accumulate) {
+          const int block = 256;
+          launch_kernel(accumulate_kernel<T>, dim3((unsigned)((npx + block - 1) / block)),
+                        dim3(block), 0, d.stream, (const T *)src, (int)nb, (long long)npx,
+                        k == 3 ? 1 : 0, d.img_acc.ptr + (size_t)sel * npx);
+          ++launches;
+          CUDA_TRY(cudaGetLastError());
+        } else {
+          CUDA_TRY(cudaMemcpyAsync(d.img_pin.ptr, src, (size_t)nb * npx * sizeof(T),
+                                   cudaMemcpyDeviceToHost, d.stream));
+          CUDA_TRY(cudaStreamSynchronize(d.stream));
+          double *dst = out + ((size_t)sel * B + start) * npx;
+          for (size_t e = 0; e < (size_t)nb * npx; ++e) dst[e] = (double)d.img_pin.ptr[e];
+        }
         ++sel;
       }
     }
-    (void)nsel;
+    if (accumulate) {
+      CUDA_TRY(cudaMemcpyAsync(out, d.img_acc.ptr, (size_t)nsel * npx * sizeof(double),
+                               cudaMemcpyDeviceToHost, d.stream));
+      CUDA_TRY(cudaStreamSynchronize(d.stream));
+    }
     return 0;
   }
 };
@@ -777,7 +800,29 @@ int psfmc_render_batch(psfmc_engine *engine, const double *theta, int64_t n_batc
   if (which >= 32u) return fail(PSFMC_ERR_INVALID_ARG, "unknown image bits in `which`");
   int prev = 0;
   cudaGetDevice(&prev);
-  int rc = engine->impl->render(theta, n_batch, ld, which, out);
+  int rc = engine->impl->render(theta, n_batch, ld, which, out, false);
+  cudaSetDevice(prev);
+  return rc;
+}
+
+int psfmc_accumulate_batch(psfmc_engine *engine, const double *theta, int64_t n_batch,
+                           int64_t ld, uint32_t which, double *sums_out) {
+  if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
+  if (n_batch < 0 || ld < 0) return fail(PSFMC_ERR_INVALID_ARG, "negative batch or ld");
+  if (which == 0) return 0;
+  if (which >= 32u) return fail(PSFMC_ERR_INVALID_ARG, "unknown image bits in `which`");
+  if (!sums_out) return fail(PSFMC_ERR_INVALID_ARG, "null sums_out");
+  if (n_batch == 0) {
+    int nsel = 0;
+    for (unsigned bit = 1; bit <= PSFMC_IMG_POINT_SOURCE_SUBTRACTED; bit <<= 1)
+      if (which & bit) ++nsel;
+    memset(sums_out, 0, sizeof(double) * (size_t)nsel * engine->impl->H * engine->impl->W);
+    return 0;
+  }
+  if (!theta) return fail(PSFMC_ERR_INVALID_ARG, "null theta");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int rc = engine->impl->render(theta, n_batch, ld, which, sums_out, true);
   cudaSetDevice(prev);
   return rc;
 }

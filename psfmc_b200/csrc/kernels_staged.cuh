@@ -352,6 +352,22 @@ __global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw
   }
 }
 
+// Posterior-image accumulation: one thread per pixel adds the nb images of a chunk
+// ([nb][npx], walker-major) to a float64 sum; `invert` sums 1/value (the composite
+// IVM is averaged in variance space, psfMC/models.py:81-82,96-97).
+template <typename T>
+__global__ void accumulate_kernel(const T *__restrict__ img, int nb, long long npx,
+                                  int invert, double *__restrict__ acc) {
+  const long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= npx) return;
+  double sum = 0.0;
+  for (int b = 0; b < nb; ++b) {
+    const double v = (double)img[(long long)b * npx + px];
+    sum += invert ? 1.0 / v : v;
+  }
+  acc[px] += sum;
+}
+
 // one thread per walker: lnL = -0.5 * sum(partials); non-finite => -inf
 // (psfMC/models.py:235-241); invalid PSF index => -inf.
 __global__ void finalize_kernel(const double *__restrict__ partials, int nblk,

@@ -178,6 +178,26 @@ class LikelihoodEngine(object):
             out.ctypes.data_as(dbl_p)))
         return {name: out[num] for num, name in enumerate(ordered)}
 
+    def accumulate(self, thetas, which=('raw_model', 'convolved_model', 'residual',
+                                        'composite_ivm', 'point_source_subtracted')):
+        """Per-pixel SUMS of the blob images over all rows of ``thetas`` (float64,
+        added up on the device) as dict name -> (H, W); 'composite_ivm' is the sum
+        of 1/ivm (variance space), as the reference's running mean uses it."""
+        thetas = np.ascontiguousarray(np.atleast_2d(thetas), dtype=np.float64)
+        n_batch, ld = thetas.shape
+        bits = 0
+        for name in which:
+            bits |= _lib.IMAGE_BITS[name]
+        ordered = [name for name, bit in sorted(_lib.IMAGE_BITS.items(),
+                                                key=lambda kv: kv[1])
+                   if bits & bit]
+        out = np.zeros((len(ordered),) + tuple(self.shape), dtype=np.float64)
+        dbl_p = ctypes.POINTER(ctypes.c_double)
+        _lib.check(self._lib, self._lib.psfmc_accumulate_batch(
+            self._handle, thetas.ctypes.data_as(dbl_p), n_batch, ld, bits,
+            out.ctypes.data_as(dbl_p)))
+        return {name: out[num] for num, name in enumerate(ordered)}
+
     def profile(self, enable=True):
         """Bracket the dominant kernel of every lnL call with CUDA events."""
         _lib.check(self._lib, self._lib.psfmc_engine_profile(self._handle,

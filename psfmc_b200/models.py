@@ -220,12 +220,25 @@ class MultiComponentModel(object):
             self.posterior_images['composite_ivm'] = \
                 1 / self.posterior_images['composite_ivm']
 
-    def accumulate_from_chain(self, thetas, which=IMAGE_TYPES, batch=64):
-        """Render every row of ``thetas`` on the GPU and fold the images into the
-        running means (the reference's re-render path, analysis/images.py:74-83)."""
+    def accumulate_from_chain(self, thetas, which=IMAGE_TYPES, batch=4096):
+        """Fold the images of every row of ``thetas`` into the running means (the
+        reference's re-render path, analysis/images.py:74-83). The images are
+        rendered AND summed on the GPU (psfmc_accumulate_batch); only per-pixel
+        sums come back, so this costs a few seconds for a whole trace database."""
         thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
-        for start in range(0, thetas.shape[0], batch):
-            imgs = self.engine.render(thetas[start:start + batch], which)
-            nrows = min(batch, thetas.shape[0] - start)
-            self.accumulate_images([{name: imgs[name][row] for name in imgs}
-                                    for row in range(nrows)])
+        with np.errstate(divide='ignore', invalid='ignore'):
+            for start in range(0, thetas.shape[0], batch):
+                block = thetas[start:start + batch]
+                sums = self.engine.accumulate(block, which)
+                old, new = self.accumulated_samples, self.accumulated_samples + len(block)
+                for name, total in sums.items():
+                    mean = self.posterior_images[name]
+                    if name == 'composite_ivm':      # averaged as a variance
+                        mean = 1 / mean if old else np.zeros_like(mean)
+                        mean = (mean * old + total) / new
+                        self.posterior_images[name] = 1 / mean
+                    else:
+                        if not old:
+                            mean = np.zeros_like(mean)
+                        self.posterior_images[name] = (mean * old + total) / new
+                self.accumulated_samples = new

@@ -172,3 +172,31 @@ def test_emu_device_kappa_matches_scipy(emu_library):
         grad = -kappa / n          # normed_grad at sq_radii = 1
         want = sbeff * (1 + grad * (1 / 36.0 / 12 * grad))
         assert abs(img[16, 16] / want - 1) < 1e-12, (n, img[16, 16], want)
+
+
+def test_emu_accumulate_matches_rendered_images(emu_library, c1_golden):
+    """psfmc_accumulate_batch (images summed on the device, the IVM in variance
+    space) against the same images rendered one by one, and the running-mean
+    bookkeeping of MultiComponentModel.accumulate_from_chain against the
+    reference-style accumulate_images."""
+    model = model_from_file('j0005/model_c1.py', 'fp64', library=emu_library,
+                            obs_dtype=np.float64)
+    thetas = np.array(c1_golden['theta'][:3] + c1_golden['theta'][6:8])
+    imgs = model.engine.render(thetas)
+    sums = model.engine.accumulate(thetas)
+    for name in imgs:
+        want = (1 / imgs[name]).sum(axis=0) if name == 'composite_ivm' \
+            else imgs[name].sum(axis=0)
+        assert np.allclose(sums[name], want, rtol=1e-12, atol=0), name
+    model.reset_images()
+    model.accumulate_from_chain(thetas[:2])
+    model.accumulate_from_chain(thetas[2:])
+    fast = {k: v.copy() for k, v in model.posterior_images.items()}
+    model.reset_images()
+    model.accumulate_images([{name: imgs[name][row] for name in imgs}
+                             for row in range(len(thetas))])
+    assert model.accumulated_samples == len(thetas)
+    for name in imgs:
+        assert np.allclose(fast[name], model.posterior_images[name], rtol=1e-11), name
+    empty = model.engine.accumulate(thetas[:0].reshape(0, 18), ('residual',))
+    assert np.all(empty['residual'] == 0)

@@ -316,3 +316,17 @@ def test_seeded_run_posterior_medians_within_mc_error(cuda_library):
     assert np.all(np.abs(med_gpu - med_ref) < 5.0 * spread / np.sqrt(n_eff) + 1e-9), \
         (np.abs(med_gpu - med_ref) / spread)
     assert np.all(np.abs(med_ref - truth) < 6.0 * spread + 1e-9)
+
+
+def test_accumulate_on_device_matches_rendered_images(cuda_library, c1_golden):
+    """Posterior-image sums accumulated on the device (float32 engine) against the
+    individually rendered images; the IVM is summed in variance space."""
+    model = model_from_file('j0005/model_c1.py', 'fp32')
+    thetas = np.array(c1_golden['theta'][:3] + c1_golden['theta'][6:16])
+    imgs = model.engine.render(thetas)
+    sums = model.engine.accumulate(thetas)
+    for name in imgs:
+        want = (1 / imgs[name]).sum(axis=0) if name == 'composite_ivm' \
+            else imgs[name].sum(axis=0)
+        scale = np.abs(want[np.isfinite(want)]).max()
+        assert np.allclose(sums[name], want, rtol=1e-6, atol=1e-9 * scale, equal_nan=True), name
