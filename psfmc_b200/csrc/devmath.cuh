@@ -14,13 +14,14 @@ namespace psfmc {
 //   P(a,x) = x^a e^-x / Gamma(a+1) * sum_k x^k / ((a+1)...(a+k)),
 // used only for x <= a + 1 (the median of Gamma(a) is always below a), where
 // every term is positive and the sum converges after O(sqrt(a)) terms.
-// Group-cooperative: the 8 lanes of a group call it with identical (a, x) (four
+// Group-cooperative: the G lanes of a group call it with identical (a, x) (32/G
 // independent groups per warp, every lane of the warp takes part in the shuffles);
-// each chunk of 8 terms costs one division per lane, a product scan and a sum
-// reduction instead of 8 dependent divisions. Every lane of the group returns the
+// each chunk of G terms costs one division per lane, a product scan and a sum
+// reduction instead of G dependent divisions. Every lane of the group returns the
 // same value. Loop trip counts are made warp-uniform with __all_sync: the extra
 // chunks a faster group runs only add terms below 1e-17 of its sum.
-#define PSFMC_GROUP 8
+// (G = lanes per group: 8 for large batches, where the float64 pipe is the limit;
+//  32 for small ones, where the length of the dependent chain is)
 
 // 1/y for y >= 1 to ~1 ulp: hardware seed (2^-23) + two Newton steps; a full IEEE
 // division costs several times as many float64 instructions, and the prepare
@@ -38,22 +39,23 @@ __device__ __forceinline__ double fast_drcp(double y) {
 }
 
 // Returns the series sum S; P(a, x) = exp(a log x - x - lgamma(a + 1)) * S.
+template <int G>
 __device__ __forceinline__ double gamma_p_series_group(double a, double x, int glane) {
   double sum = 1.0, tbase = 1.0;
   for (int chunk = 0; chunk < 256; ++chunk) {
-    double p = x * fast_drcp(a + (double)(chunk * PSFMC_GROUP + glane + 1));
+    double p = x * fast_drcp(a + (double)(chunk * G + glane + 1));
 #pragma unroll
-    for (int off = 1; off < PSFMC_GROUP; off <<= 1) {
-      double q = __shfl_up_sync(0xffffffffu, p, off, PSFMC_GROUP);
+    for (int off = 1; off < G; off <<= 1) {
+      double q = __shfl_up_sync(0xffffffffu, p, off, G);
       if (glane >= off) p *= q;
     }
-    const double term = tbase * p;          // term number chunk*8 + glane + 1
+    const double term = tbase * p;          // term number chunk*G + glane + 1
     double part = term;
 #pragma unroll
-    for (int off = PSFMC_GROUP / 2; off > 0; off >>= 1)
-      part += __shfl_xor_sync(0xffffffffu, part, off, PSFMC_GROUP);
+    for (int off = G / 2; off > 0; off >>= 1)
+      part += __shfl_xor_sync(0xffffffffu, part, off, G);
     sum += part;
-    tbase = __shfl_sync(0xffffffffu, term, PSFMC_GROUP - 1, PSFMC_GROUP);
+    tbase = __shfl_sync(0xffffffffu, term, G - 1, G);
     if (__all_sync(0xffffffffu, !(tbase >= sum * 1.0e-17))) break;
   }
   return sum;
@@ -67,6 +69,7 @@ __device__ __forceinline__ double gamma_p_series_group(double a, double x, int g
 // *lgam_a1_out receives lgamma(a + 1) (reused for Gamma(2n) by the caller).
 // `active`: false for groups that have no Sersic to work on; they still walk through
 // the shuffles (with a harmless a = 1) so that the warp stays convergent.
+template <int G>
 __device__ __forceinline__ double gammaincinv_half_group(double a, int glane, bool active,
                                                          double *lgam_a1_out) {
   const bool valid = active && (a > 0.0) && isfinite(a);
@@ -87,7 +90,7 @@ __device__ __forceinline__ double gammaincinv_half_group(double a, int glane, bo
   double prev_dx = INFINITY;
   bool done = false;
   for (int it = 0; it < 16; ++it) {
-    const double series = gamma_p_series_group(a, x, glane);
+    const double series = gamma_p_series_group<G>(a, x, glane);
     if (!done) {
       const double pref = exp(a * log(x) - x - lgam_a1);  // x^a e^-x / Gamma(a+1)
       const double f = pref * series - 0.5;

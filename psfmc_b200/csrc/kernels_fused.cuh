@@ -664,14 +664,8 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
                                cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr) {
   if (n_batch <= 0) return 0;
   const int ncomp = prog_h.n_components;
-  {
-    long long nthreads = PSFMC_GROUP * n_batch * (ncomp > 0 ? ncomp : 1);   // 8 lanes each
-    int block = 128;
-    unsigned grid = (unsigned)((nthreads + block - 1) / block);
-    launch_kernel(prepare_kernel, dim3(grid), dim3(block), 0, stream, buf.prog, theta,
-                  n_batch, ld, plan.fr.H, plan.fr.W, buf.derived, buf.psf_sel, buf.wscale,
-                  fb.rconst);
-  }
+  launch_prepare(buf.prog, theta, n_batch, ld, plan.fr.H, plan.fr.W, ncomp, buf.derived, buf.psf_sel,
+                 buf.wscale, fb.rconst, stream);
   FusedParams P;
   P.rconst = fb.rconst;
   P.derived = buf.derived;

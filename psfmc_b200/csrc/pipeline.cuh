@@ -3,6 +3,8 @@
 // non-GPU test tier (tests/emu/, -DPSFMC_EMU), so that what is tested locally is
 // the launch sequence that runs on the B200.
 #pragma once
+#include <stdlib.h>
+
 #include <utility>
 
 #include "kernels_staged.cuh"
@@ -82,6 +84,28 @@ inline StagedPlan make_staged_plan(int H, int W, int n_components, size_t sizeof
   return p;
 }
 
+// theta -> per-walker constants. Small batches use 32 lanes per component (the
+// kernel is then bound by the length of its dependent float64 chain), large ones 8
+// (bound by the float64 pipe).
+inline void launch_prepare(const Program *prog, const double *theta, long long n_batch,
+                           long long ld, int H, int W, int n_components, double *derived,
+                           int *psf_sel, double *wscale, float *rconst, cudaStream_t stream) {
+  const long long ngroups = n_batch * (n_components > 0 ? n_components : 1);
+  const int block = 128;
+  const char *env = getenv("PSFMC_PREPARE_GROUP");   // tests: 8 | 32 pins the variant
+  const int forced = env ? atoi(env) : 0;
+  const bool wide = forced ? forced == 32 : ngroups <= 4096;
+  if (wide) {
+    unsigned grid = (unsigned)((32 * ngroups + block - 1) / block);
+    launch_kernel(prepare_kernel<32>, dim3(grid), dim3(block), 0, stream, prog, theta, n_batch,
+                  ld, H, W, derived, psf_sel, wscale, rconst);
+  } else {
+    unsigned grid = (unsigned)((8 * ngroups + block - 1) / block);
+    launch_kernel(prepare_kernel<8>, dim3(grid), dim3(block), 0, stream, prog, theta, n_batch,
+                  ld, H, W, derived, psf_sel, wscale, rconst);
+  }
+}
+
 // Device-resident state the launch sequence needs (one per device per precision).
 template <typename T>
 struct StagedBuffers {
@@ -123,14 +147,8 @@ inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
                                  cudaEvent_t ev_end = nullptr) {
   if (n_batch <= 0) return;
   const Frame fr = plan.fr;
-  {
-    long long nthreads = PSFMC_GROUP * n_batch * (n_components > 0 ? n_components : 1);
-    int block = 128;
-    unsigned grid = (unsigned)((nthreads + block - 1) / block);
-    launch_kernel(prepare_kernel, dim3(grid), dim3(block), 0, stream, buf.prog, theta,
-                  n_batch, ld, fr.H, fr.W, buf.derived, buf.psf_sel, buf.wscale,
-                  (float *)nullptr);
-  }
+  launch_prepare(buf.prog, theta, n_batch, ld, fr.H, fr.W, n_components, buf.derived, buf.psf_sel,
+                 buf.wscale, (float *)nullptr, stream);
   if (ev_begin) cudaEventRecord(ev_begin, stream);   // the three row/column kernels
   for (long long start = 0; start < n_batch; start += plan.chunk) {
     long long nb = n_batch - start < plan.chunk ? n_batch - start : plan.chunk;

@@ -80,14 +80,15 @@ __device__ __forceinline__ float sersic_pixel_f32(const SersicF32 &s, float x, f
   return sb * (1.0f + s.kq * (t * t) * fast_rcp(r2));
 }
 
-// One 8-lane GROUP per (walker, component): theta -> derived constants, float64.
+// One G-lane GROUP per (walker, component): theta -> derived constants, float64.
 // The lanes of a group share the scalar work and split the incomplete-gamma series
 // of the Sersic kappa (devmath.cuh) and the point-source stamp taps; the four
 // groups of a warp walk through the same shuffles (groups without a Sersic idle).
-//   grid = ceil(8 * B * n_components / blockDim), blockDim a multiple of 32
+//   grid = ceil(G * B * n_components / blockDim), blockDim a multiple of 32
 // wscale[b] receives the packing scale of the walker (see below);
 // psf_sel[b] receives the rint-ed PSF index (psfMC/distributions.py:130-138), or
 // -1 when it is out of range (the prior is -inf there; the walker gets -inf).
+template <int G>
 __global__ void prepare_kernel(const Program *__restrict__ prog,
                                const double *__restrict__ theta, long long n_batch,
                                long long ld, int H, int W, double *__restrict__ derived,
@@ -96,8 +97,8 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
   const int ncomp_prog = prog->n_components;
   const int ncomp = ncomp_prog > 0 ? ncomp_prog : 1;   // an empty model still gets its
                                                        // per-walker PSF index and scale
-  const int glane = threadIdx.x & (PSFMC_GROUP - 1);
-  long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / PSFMC_GROUP;
+  const int glane = threadIdx.x & (G - 1);
+  long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const bool live = gid < n_batch * ncomp;
   if (!live) gid = 0;                       // idle groups shadow group 0, write nothing
   const bool writer = live && (glane == 0);
@@ -144,7 +145,7 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
   const bool is_sersic = live && kind == PSFMC_SERSIC;
   const double n_index = is_sersic ? slot_value(prog, c, PSFMC_P_INDEX, th) : 0.5;
   double lgam_a1;
-  const double kappa = gammaincinv_half_group(2.0 * n_index, glane, is_sersic, &lgam_a1);
+  const double kappa = gammaincinv_half_group<G>(2.0 * n_index, glane, is_sersic, &lgam_a1);
   if (!live) return;
   if (kind == PSFMC_SKY) {
     if (writer) out[D_SKY_ADU] = slot_value(prog, c, PSFMC_P_ADU, th);

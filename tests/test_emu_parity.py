@@ -145,10 +145,12 @@ def test_emu_batch_edges_and_determinism(emu_library, c1_golden):
     assert np.array_equal(pieces, full)
 
 
-def test_emu_device_kappa_matches_scipy(emu_library):
-    """kappa = gammaincinv(2n, 0.5) on the device (float64 Halley iteration) against
-    scipy over the whole prior range, through a one-Sersic model whose raw image
-    at the effective radius equals sb_eff."""
+@pytest.mark.parametrize('group', ['8', '32'])
+def test_emu_device_kappa_matches_scipy(emu_library, group, monkeypatch):
+    """kappa = gammaincinv(2n, 0.5) on the device (float64 Halley iteration, 8 or 32
+    cooperating lanes) against scipy over the whole prior range, through a one-Sersic
+    model whose raw image at the effective radius equals sb_eff."""
+    monkeypatch.setenv('PSFMC_PREPARE_GROUP', group)
     from scipy.special import gammaincinv
     from psfmc_b200 import MultiComponentModel
     from psfmc_b200.components import Configuration, Sersic
