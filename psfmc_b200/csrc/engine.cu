@@ -128,6 +128,7 @@ struct EngineBase {
   int n_sersic = 0, n_point = 0;
   StagedPlan plan;
   int path = 0;
+  bool fused_wide = false;   // PSFMC_FUSED_VARIANT=1024 selects the 1024-thread kernel
   long long launches = 0;
   int n_devices = 0;
 };
@@ -256,6 +257,7 @@ struct Engine : EngineBase {
       fb.specx = d.fspecx;
       fb.ow = d.fow;
       fb.n_sms = d.n_sms;
+      fb.wide = fused_wide;
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (profiling && (rc = prof_pair(d, &e0, &e1))) return rc;
       launches += launch_fused_lnlike<T>(plan, buf, fb, prog_h, theta_dev, B, ld, lnl_dev,
@@ -678,6 +680,8 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       eng->path = fused_path_available<T>(eng->plan, eng->prog_h) ? 1 : 0;
       const char *force = getenv("PSFMC_FORCE_STAGED");
       if (force && force[0] == '1') eng->path = 0;
+      const char *variant = getenv("PSFMC_FUSED_VARIANT");
+      eng->fused_wide = variant && atoi(variant) == 1024;
     }
     if (eng->path == 1) {
       if (fused_prepare_device<T>(eng->plan)) {

@@ -280,7 +280,9 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
 }
 
 // Hermitian rebuild + inverse row transform + chi-square terms of row batch `it`;
-// returns this thread's float64 partial sum over its 16 pixels.
+// returns this thread's float64 partial sum over its 16 pixels. PREFETCH: issue the
+// observation loads before the transform (needs 32 registers for its duration).
+template <bool PREFETCH>
 __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_addr_t tile,
                                                      const RowRole &R, smem_addr_t twl,
                                                      int it, float unscale) {
@@ -291,8 +293,10 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   // last (L2 latency hidden behind the whole inverse transform)
   float2 o[16];
   const float2 *owr = P.ow + y * PSFMC_FUSED_N + R.l;
+  if (PREFETCH) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
+    for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
+  }
   cplx<float> a[8], bb[8];
   {
     cplx<float> yd1[4], ym1[4], yd2[4], ym2[4];
@@ -348,6 +352,10 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
 #pragma unroll
   for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], lds64(twl + 64 * k1));
   dft16<true>(v);           // v[j] = (convolved model, scaled model variance)
+  if (!PREFETCH) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
+  }
   double acc = 0.0;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -557,7 +565,7 @@ fused_lnlike_kernel(const FusedParams P) {
       const bool fwd = interleave ? (step & 1) : (step >= 2);
       const int it = interleave ? (step >> 1) : (step & 1);
       if (!fwd) {
-        if (cur) acc += fused_rows_inverse(P, tile, R, twl, it, unscale);
+        if (cur) acc += fused_rows_inverse<true>(P, tile, R, twl, it, unscale);
       } else if (has_next) {
         fused_rows_forward(P, tile, R, twl, bn, it, wsc_next);
       }
@@ -588,6 +596,197 @@ fused_lnlike_kernel(const FusedParams P) {
   }
 }
 
+// --------------------------------------------------------------------------
+// 1024-thread variant: the same passes with ONE 16-point unit per thread and pass
+// (32 warps, 64 registers): twice the resident warps per scheduler to hide the
+// latencies the 512-thread kernel is bound by. Rows: warp w owns rows 4w..4w+3.
+// Columns: thread (c, m), m = 0..7: radix-16 of residue n2 = m, then the radix-8
+// pair k1 in {m, 16 - m} ({0, 8} for m = 0), closed under k1 -> -k1.
+#define PSFMC_FUSED_THREADS_WIDE 1024
+
+// Thread roles are recomputed from an opaque copy of the thread index at the start of
+// every phase, so that the compiler cannot keep them alive across phases (64
+// registers per thread leave no room for loop-invariant luggage).
+__device__ __forceinline__ int opaque_tid() {
+  int t = threadIdx.x;
+#ifndef PSFMC_EMU
+  asm volatile("" : "+r"(t));
+#endif
+  return t;
+}
+
+__device__ __forceinline__ RowRole make_row_role(int tid) {
+  RowRole R;
+  const int lane = tid & 31;
+  R.w = tid >> 5;
+  R.rr = lane >> 3;
+  R.l = lane & 7;
+  R.l0 = (R.l == 0);
+  const unsigned s = R.rr & 1;
+  const unsigned kA = R.l, kB = R.l0 ? 8 : 16 - R.l;
+  R.t16 = (8u * R.l) ^ (64u * s);
+  R.qa = 64u * (kA ^ s) + 8u * (kA & 7);
+  R.qb = 64u * (kB ^ s) + 8u * (kB & 7);
+  R.fa = 8u * (kA ^ (8u * s));
+  R.fb = 8u * (kB ^ (8u * s));
+  return R;
+}
+
+__global__ void __launch_bounds__(PSFMC_FUSED_THREADS_WIDE, 1)
+fused_lnlike_kernel_wide(const FusedParams P) {
+  PSFMC_DYN_SMEM(smem_raw);
+  const smem_addr_t tile = smem_base(smem_raw);
+  constexpr int NW = PSFMC_FUSED_THREADS_WIDE / 32;
+  __shared__ double red_s[NW];
+  __shared__ int cnt_s;
+  constexpr int N = PSFMC_FUSED_N;
+  constexpr unsigned ROWB = N * 8;
+  __shared__ __align__(16) float tw_s[128][2];
+  {
+    const int tid = threadIdx.x;
+    if (tid == 0) cnt_s = 0;
+    if (tid < 128) {
+      const int k1 = tid >> 3, ll = tid & 7;
+      tw_s[tid][0] = c_tw128[ll * 16 + k1][0];
+      tw_s[tid][1] = c_tw128[ll * 16 + k1][1];
+    }
+  }
+  const smem_addr_t tw_base = smem_base(reinterpret_cast<unsigned char *>(&tw_s[0][0]));
+  __syncthreads();
+
+#pragma unroll 1
+  for (long long b = (long long)blockIdx.x - (long long)gridDim.x; b < P.n_batch;
+       b += gridDim.x) {
+    const bool cur = b >= 0;
+    if (cur) {
+      int sel = P.psf_sel[b];
+      const bool invalid = sel < 0;
+      if (invalid) sel = 0;
+      const cplx<float> *sp = P.spec + (size_t)sel * N * N;
+      __syncthreads();
+      // ---- columns: radix-16 of residue n2 = m
+      {
+        const int tid = opaque_tid();
+        const int w = tid >> 5, m = w >> 2, c = (w & 3) * 32 + (tid & 31);
+        const smem_addr_t cb = tile + (unsigned)m * ROWB + 8u * ((m & 1) ? (c ^ 8) : c);
+        cplx<float> v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = lds64(cb + 8 * j * ROWB);
+        dft16<false>(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * tw128(m, k1);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) sts64(cb + 8 * k1 * ROWB, v[k1]);
+        group_barrier(1 + (w & 3), 256);
+      }
+
+      // ---- columns: radix-8 pair, spectrum multiply, inverse radix-8
+      {
+        const int tid = opaque_tid();
+        const int w = tid >> 5, m = w >> 2, c = (w & 3) * 32 + (tid & 31);
+        const bool special = (c == 0) || (c == 64);
+        const int k1a = m, k1b = (m == 0) ? 8 : 16 - m;
+        const unsigned cev = 8u * c, cod = 8u * (c ^ 8);
+        const smem_addr_t ba = tile + 8u * k1a * ROWB, bq = tile + 8u * k1b * ROWB;
+        const cplx<float> *spa = sp + k1a * N + c, *spb = sp + k1b * N + c;
+        cplx<float> a[8], bb[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) {
+          const unsigned cc = (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
+          a[n2] = lds64(ba + cc);
+          bb[n2] = lds64(bq + cc);
+        }
+        dft8<float, false>(a);    // a[k2]  = U[k1a + 16 k2][c]
+        dft8<float, false>(bb);
+        if (!special) {
+#pragma unroll
+          for (int k2 = 0; k2 < 8; ++k2) a[k2] = a[k2] * ldc2(spa + 16 * k2 * N);
+#pragma unroll
+          for (int k2 = 0; k2 < 8; ++k2) bb[k2] = bb[k2] * ldc2(spb + 16 * k2 * N);
+        } else {
+          const cplx<float> *sx = P.specx + ((size_t)sel * 2 + (c == 64 ? 1 : 0)) * N;
+          if (m == 0) {   // k1a = 0: ky <-> (128 - ky); k1b = 8: k2 <-> 7 - k2
+            special_pair(a[0], a[0], ldc2(spa), ldc2(sx), ldc2(spa), ldc2(sx));
+            special_pair(a[4], a[4], ldc2(spa + 64 * N), ldc2(sx + 64), ldc2(spa + 64 * N),
+                         ldc2(sx + 64));
+#pragma unroll
+            for (int k2 = 1; k2 < 4; ++k2)
+              special_pair(a[k2], a[8 - k2], ldc2(spa + 16 * k2 * N), ldc2(sx + 16 * k2),
+                           ldc2(spa + 16 * (8 - k2) * N), ldc2(sx + 16 * (8 - k2)));
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2)
+              special_pair(bb[k2], bb[7 - k2], ldc2(spb + 16 * k2 * N),
+                           ldc2(sx + 8 + 16 * k2), ldc2(spb + 16 * (7 - k2) * N),
+                           ldc2(sx + 8 + 16 * (7 - k2)));
+          } else {        // a[k2] <-> bb[7 - k2]
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2)
+              special_pair(a[k2], bb[7 - k2], ldc2(spa + 16 * k2 * N),
+                           ldc2(sx + k1a + 16 * k2), ldc2(spb + 16 * (7 - k2) * N),
+                           ldc2(sx + k1b + 16 * (7 - k2)));
+          }
+        }
+        dft8<float, true>(a);     // a[n2]: inverse over k2
+        dft8<float, true>(bb);
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) {
+          const unsigned cc = (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
+          sts64(ba + cc, a[n2]);
+          sts64(bq + cc, bb[n2]);
+        }
+        group_barrier(1 + (w & 3), 256);
+      }
+
+      // ---- columns: inverse radix-16 of residue n2 = m
+      {
+        const int tid = opaque_tid();
+        const int w = tid >> 5, m = w >> 2, c = (w & 3) * 32 + (tid & 31);
+        const smem_addr_t cb = tile + (unsigned)m * ROWB + 8u * ((m & 1) ? (c ^ 8) : c);
+        cplx<float> v[16];
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(cb + 8 * k1 * ROWB);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], tw128(m, k1));
+        dft16<true>(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sts64(cb + 8 * j * ROWB, v[j]);
+      }
+      __syncthreads();
+
+      // ---- rows: inverse + chi-square of walker b
+      {
+        const int tid = opaque_tid();
+        const RowRole R = make_row_role(tid);
+        const float unscale = (float)(P.vscale_inv[sel] / P.wscale[b]);
+        double acc = fused_rows_inverse<false>(P, tile, R, tw_base + 8u * R.l, 0, unscale);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if ((tid & 31) == 0) {
+          volatile double *red = red_s;
+          red[tid >> 5] = acc;
+          __threadfence_block();
+          const int prev = atomicAdd(&cnt_s, 1);
+          if (prev == NW - 1) {
+            __threadfence_block();
+            double tot = 0.0;
+            for (int k = 0; k < NW; ++k) tot += red[k];
+            double val = -0.5 * tot;
+            if (!isfinite(val) || invalid) val = -INFINITY;
+            P.lnl[b] = val;
+            cnt_s = 0;
+          }
+        }
+      }
+    }
+    // ---- rows: render + forward of the CTA's next walker
+    const long long bn = b + gridDim.x;
+    if (bn < P.n_batch) {
+      const RowRole R = make_row_role(opaque_tid());
+      fused_rows_forward(P, tile, R, tw_base + 8u * R.l, bn, 0, (float)P.wscale[bn]);
+    }
+  }
+}
+
 // -------------------------------------------------------------- host side --
 
 template <typename T>
@@ -599,6 +798,9 @@ template <typename T>
 inline int fused_prepare_device(const StagedPlan &) {
 #ifndef PSFMC_EMU
   if (cudaFuncSetAttribute(fused_lnlike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           PSFMC_FUSED_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(fused_lnlike_kernel_wide,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                            PSFMC_FUSED_SMEM) != cudaSuccess)
     return 1;
 #endif
@@ -652,6 +854,7 @@ struct FusedBuffers {
   const cplx<float> *spec = nullptr, *specx = nullptr;
   const float2 *ow = nullptr;
   int n_sms = 148;
+  bool wide = false;   // 1024-thread variant
 };
 
 // theta -> lnL for n_batch walkers: prepare kernel + one persistent fused kernel.
@@ -682,8 +885,12 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
     P.kind[c] = (signed char)(c < ncomp ? prog_h.kind[c] : 0);
   unsigned grid = (unsigned)(n_batch < fb.n_sms ? n_batch : fb.n_sms);
   if (ev_begin) cudaEventRecord(ev_begin, stream);
-  launch_kernel(fused_lnlike_kernel, dim3(grid), dim3(PSFMC_FUSED_THREADS),
-                (size_t)PSFMC_FUSED_SMEM, stream, P);
+  if (fb.wide)
+    launch_kernel(fused_lnlike_kernel_wide, dim3(grid), dim3(PSFMC_FUSED_THREADS_WIDE),
+                  (size_t)PSFMC_FUSED_SMEM, stream, P);
+  else
+    launch_kernel(fused_lnlike_kernel, dim3(grid), dim3(PSFMC_FUSED_THREADS),
+                  (size_t)PSFMC_FUSED_SMEM, stream, P);
   if (ev_end) cudaEventRecord(ev_end, stream);
   return 2;
 }
