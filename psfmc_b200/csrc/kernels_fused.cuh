@@ -405,8 +405,11 @@ fused_lnlike_kernel(const FusedParams P) {
   const smem_addr_t twl = smem_base(reinterpret_cast<unsigned char *>(&tw_s[0][0])) + 8u * R.l;
   __syncthreads();
 
-  // column-pass role: column c, two of the eight n2 residues
-  const int cg = w & 3, m = w >> 2;
+  // column-pass role: column c, two of the eight n2 residues. The four warps of a
+  // column group (which meet at the named barriers) sit on four DIFFERENT
+  // schedulers (warp w runs on scheduler w & 3), so every scheduler hosts one warp
+  // of each group and its warps are not phase-locked to each other.
+  const int cg = w >> 2, m = w & 3;
   const int c = cg * 32 + lane;
   const bool special = (c == 0) || (c == 64);
   // radix-8 side of the columns: four k1 values closed under k1 -> -k1 (mod 16)
@@ -601,7 +604,8 @@ fused_lnlike_kernel(const FusedParams P) {
 // (32 warps, 64 registers): twice the resident warps per scheduler to hide the
 // latencies the 512-thread kernel is bound by. Rows: warp w owns rows 4w..4w+3.
 // Columns: thread (c, m), m = 0..7: radix-16 of residue n2 = m, then the radix-8
-// pair k1 in {m, 16 - m} ({0, 8} for m = 0), closed under k1 -> -k1.
+// pair k1 in {m, 16 - m} ({0, 8} for m = 0), closed under k1 -> -k1. The eight warps of
+// a column group are spread over the four schedulers (see fused_lnlike_kernel).
 #define PSFMC_FUSED_THREADS_WIDE 1024
 
 // Thread roles are recomputed from an opaque copy of the thread index at the start of
@@ -667,7 +671,7 @@ fused_lnlike_kernel_wide(const FusedParams P) {
       // ---- columns: radix-16 of residue n2 = m
       {
         const int tid = opaque_tid();
-        const int w = tid >> 5, m = w >> 2, c = (w & 3) * 32 + (tid & 31);
+        const int w = tid >> 5, m = w & 7, cg = w >> 3, c = cg * 32 + (tid & 31);
         const smem_addr_t cb = tile + (unsigned)m * ROWB + 8u * ((m & 1) ? (c ^ 8) : c);
         cplx<float> v[16];
 #pragma unroll
@@ -677,13 +681,13 @@ fused_lnlike_kernel_wide(const FusedParams P) {
         for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * tw128(m, k1);
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) sts64(cb + 8 * k1 * ROWB, v[k1]);
-        group_barrier(1 + (w & 3), 256);
+        group_barrier(1 + cg, 256);
       }
 
       // ---- columns: radix-8 pair, spectrum multiply, inverse radix-8
       {
         const int tid = opaque_tid();
-        const int w = tid >> 5, m = w >> 2, c = (w & 3) * 32 + (tid & 31);
+        const int w = tid >> 5, m = w & 7, cg = w >> 3, c = cg * 32 + (tid & 31);
         const bool special = (c == 0) || (c == 64);
         const int k1a = m, k1b = (m == 0) ? 8 : 16 - m;
         const unsigned cev = 8u * c, cod = 8u * (c ^ 8);
@@ -734,13 +738,13 @@ fused_lnlike_kernel_wide(const FusedParams P) {
           sts64(ba + cc, a[n2]);
           sts64(bq + cc, bb[n2]);
         }
-        group_barrier(1 + (w & 3), 256);
+        group_barrier(1 + cg, 256);
       }
 
       // ---- columns: inverse radix-16 of residue n2 = m
       {
         const int tid = opaque_tid();
-        const int w = tid >> 5, m = w >> 2, c = (w & 3) * 32 + (tid & 31);
+        const int w = tid >> 5, m = w & 7, cg = w >> 3, c = cg * 32 + (tid & 31);
         const smem_addr_t cb = tile + (unsigned)m * ROWB + 8u * ((m & 1) ? (c ^ 8) : c);
         cplx<float> v[16];
 #pragma unroll
