@@ -168,6 +168,9 @@ typedef struct psfmc_info {
   double fft_flops_per_eval;   /* 10 N log2 N                                     */
   double hbm_bytes_per_eval;   /* algorithmic bytes through L2/HBM per walker     */
   int64_t launches_total;   /* kernels launched by this engine since creation     */
+  int32_t kappa_table;      /* 1: the Sersic kappa comes from the Chebyshev table built
+                               and verified at creation; 0: from the iteration       */
+  int32_t reserved;
 } psfmc_info;
 int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info);
 

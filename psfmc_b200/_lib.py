@@ -65,6 +65,7 @@ class Info(ctypes.Structure):
         ('fft_flops_per_eval', ctypes.c_double),
         ('hbm_bytes_per_eval', ctypes.c_double),
         ('launches_total', ctypes.c_int64),
+        ('kappa_table', ctypes.c_int32), ('reserved', ctypes.c_int32),
     ]
 
 

@@ -206,7 +206,17 @@ struct Program {
   double psf_value;
   int32_t n_psf;
   double mag_zp;
+  // Piecewise Chebyshev table of log(kappa) over u = log2(2n) (devmath.cuh), built
+  // at engine creation from the device's own Halley iteration; null = not available
+  const double *kappa_coef;   // [kappa_nint][PSFMC_KAPPA_DEG]
+  int32_t kappa_nint;
+  double kappa_u0, kappa_inv_du;
 };
+
+#define PSFMC_KAPPA_DEG 16      // Chebyshev coefficients per interval
+#define PSFMC_KAPPA_U0 (-3.5)   // log2(a) range of the table: a = 2n in [0.088, 64]
+#define PSFMC_KAPPA_U1 6.0
+#define PSFMC_KAPPA_NINT 19     // intervals of width 0.5 in log2(a)
 
 // Frame geometry shared by all kernels of the staged path.
 struct Frame {

@@ -118,6 +118,29 @@ __device__ __forceinline__ double gammaincinv_half_group(double a, int glane, bo
   return valid ? x : NAN;
 }
 
+// kappa(a) from the piecewise Chebyshev table of log(kappa) over u = log2(a)
+// (Clenshaw recurrence); `*ok` is false when a is outside the table (the caller then
+// falls back to the iteration).
+__device__ __forceinline__ double kappa_from_table(const double *coef, int n_int, double u0,
+                                                   double inv_du, double a, bool *ok) {
+  *ok = false;
+  if (!coef || !(a > 0.0) || !isfinite(a)) return NAN;
+  const double pos = (log2(a) - u0) * inv_du;
+  if (!(pos >= 0.0) || !(pos < (double)n_int)) return NAN;
+  const int k = (int)pos;
+  const double t = 2.0 * (pos - (double)k) - 1.0;      // in [-1, 1)
+  const double *c = coef + k * PSFMC_KAPPA_DEG;
+  double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+  for (int j = PSFMC_KAPPA_DEG - 1; j >= 1; --j) {
+    const double b0 = fma(2.0 * t, b1, c[j] - b2);
+    b2 = b1;
+    b1 = b0;
+  }
+  *ok = true;
+  return exp(fma(t, b1, c[0] - b2));
+}
+
 // psfMC/utils.py:160-164
 __device__ __forceinline__ double mag_to_flux(double mag, double mag_zp) {
   return pow(10.0, -0.4 * (mag - mag_zp));

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -92,7 +93,9 @@ struct DeviceState {
   int ordinal = 0;
   cudaStream_t stream = nullptr;
   Program *prog = nullptr;
+  Program prog_host;   // = *prog, host copy (kernel parameter of the prepare kernel)
   cplx<T> *tw_w = nullptr, *tw_h = nullptr, *spec = nullptr;
+  double *kappa_coef = nullptr;
   T *obs = nullptr, *ovar = nullptr;
   unsigned char *bad = nullptr;
   DevBuf<double> derived, partials, theta, lnl, wscale;
@@ -129,6 +132,7 @@ struct EngineBase {
   StagedPlan plan;
   int path = 0;
   bool fused_wide = false;   // PSFMC_FUSED_VARIANT=1024 selects the 1024-thread kernel
+  bool kappa_table = false;  // Chebyshev table of the Sersic kappa accepted
   long long launches = 0;
   int n_devices = 0;
 };
@@ -149,6 +153,7 @@ struct Engine : EngineBase {
       cudaFree(d.ovar);
       cudaFree(d.bad);
       cudaFree(d.vscale_inv);
+      cudaFree(d.kappa_coef);
       cudaFree(d.fspec);
       cudaFree(d.fspecx);
       cudaFree(d.fow);
@@ -209,6 +214,7 @@ struct Engine : EngineBase {
   StagedBuffers<T> buffers(DeviceState<T> &d) {
     StagedBuffers<T> b;
     b.prog = d.prog;
+    b.prog_host = &d.prog_host;
     b.tw_w = d.tw_w;
     b.tw_h = d.tw_h;
     b.spec = d.spec;
@@ -484,6 +490,79 @@ void build_program(const psfmc_desc *d, Program *p, int *n_sersic, int *n_point)
 }
 
 template <typename T>
+int upload(T **dst, const std::vector<T> &src);
+
+// Chebyshev table of log(kappa(a)) over u = log2(a), a = 2n (common.cuh): the nodes
+// are evaluated by the device's own iteration (kappa_nodes_kernel), the coefficients
+// by a discrete Chebyshev transform in long double; the table is accepted only if it
+// reproduces the iteration to 2e-14 at the interval mid-grid. Empty coef = rejected.
+int build_kappa_table(std::vector<double> *coef) {
+  coef->clear();
+  if (const char *env = getenv("PSFMC_NO_KAPPA_TABLE"))
+    if (env[0] == '1') return 0;
+  // device-independent data: built once per process
+  static std::vector<double> cached;
+  static bool cached_valid = false;
+  if (cached_valid) {
+    *coef = cached;
+    return 0;
+  }
+  const int NI = PSFMC_KAPPA_NINT, ND = PSFMC_KAPPA_DEG, NT = 7;
+  const double du = (PSFMC_KAPPA_U1 - PSFMC_KAPPA_U0) / NI;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  std::vector<double> a_nodes;
+  for (int k = 0; k < NI; ++k) {
+    for (int j = 0; j < ND; ++j) {       // Chebyshev nodes of the first kind
+      long double t = cosl(pi * (j + 0.5L) / ND);
+      a_nodes.push_back(exp2(PSFMC_KAPPA_U0 + du * (k + 0.5 * (1.0 + (double)t))));
+    }
+    for (int j = 0; j < NT; ++j)          // test points
+      a_nodes.push_back(exp2(PSFMC_KAPPA_U0 + du * (k + (j + 0.5) / NT)));
+  }
+  const int n = (int)a_nodes.size();
+  double *a_dev = nullptr, *k_dev = nullptr;
+  int rc = upload(&a_dev, a_nodes);
+  if (rc) return rc;
+  CUDA_TRY(cudaMalloc(&k_dev, n * sizeof(double)));
+  launch_kernel(kappa_nodes_kernel, dim3((unsigned)((32 * n + 127) / 128)), dim3(128), 0,
+                (cudaStream_t)0, (const double *)a_dev, n, k_dev);
+  CUDA_TRY(cudaGetLastError());
+  std::vector<double> kap(n);
+  CUDA_TRY(cudaMemcpy(kap.data(), k_dev, n * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(a_dev);
+  cudaFree(k_dev);
+  std::vector<double> out((size_t)NI * ND);
+  double worst = 0.0;
+  for (int k = 0; k < NI; ++k) {
+    const double *vals = kap.data() + (size_t)k * (ND + NT);
+    for (int m = 0; m < ND; ++m) {
+      long double acc = 0.0L;
+      for (int j = 0; j < ND; ++j) {
+        if (!(vals[j] > 0.0) || !std::isfinite(vals[j])) return 0;   // reject the table
+        acc += logl((long double)vals[j]) * cosl(pi * m * (j + 0.5L) / ND);
+      }
+      out[(size_t)k * ND + m] = (double)(acc * (m == 0 ? 1.0L : 2.0L) / ND);
+    }
+    for (int j = 0; j < NT; ++j) {        // Clenshaw, as on the device
+      const double t = 2.0 * ((j + 0.5) / NT) - 1.0;
+      double b1 = 0.0, b2 = 0.0;
+      for (int m = ND - 1; m >= 1; --m) {
+        double b0 = fma(2.0 * t, b1, out[(size_t)k * ND + m] - b2);
+        b2 = b1;
+        b1 = b0;
+      }
+      const double got = exp(fma(t, b1, out[(size_t)k * ND] - b2));
+      const double err = fabs(got / vals[ND + j] - 1.0);
+      if (!(err <= worst)) worst = err;
+    }
+  }
+  if (worst <= 2.0e-14) coef->swap(out);
+  cached = *coef;
+  cached_valid = true;
+  return 0;
+}
+
+template <typename T>
 int upload(T **dst, const std::vector<T> &src) {
   CUDA_TRY(cudaMalloc(dst, src.size() * sizeof(T)));
   CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -670,6 +749,21 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
         }
       }
     }
+    {
+      std::vector<double> kcoef;
+      if ((rc = build_kappa_table(&kcoef))) break;
+      progv[0].kappa_coef = nullptr;
+      progv[0].kappa_nint = 0;
+      if (!kcoef.empty()) {
+        if ((rc = upload(&ds.kappa_coef, kcoef))) break;
+        progv[0].kappa_coef = ds.kappa_coef;
+        progv[0].kappa_nint = PSFMC_KAPPA_NINT;
+        progv[0].kappa_u0 = PSFMC_KAPPA_U0;
+        progv[0].kappa_inv_du = PSFMC_KAPPA_NINT / (PSFMC_KAPPA_U1 - PSFMC_KAPPA_U0);
+        eng->kappa_table = true;
+      }
+    }
+    ds.prog_host = progv[0];
     if ((rc = upload(&ds.prog, progv)) || (rc = upload(&ds.tw_w, tww)) ||
         (rc = upload(&ds.tw_h, twh)) || (rc = upload(&ds.spec, spec)) ||
         (rc = upload(&ds.obs, obs)) || (rc = upload(&ds.ovar, ovar)) ||
@@ -859,6 +953,7 @@ int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info) {
                    : 4.0 * (double)e->plan.scratch_elems_per_walker * csz;
   info->kernels_per_call = e->path == 1 ? 2 : 5;
   info->launches_total = e->launches;
+  info->kappa_table = e->kappa_table ? 1 : 0;
   return 0;
 }
 

@@ -871,7 +871,7 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
                                cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr) {
   if (n_batch <= 0) return 0;
   const int ncomp = prog_h.n_components;
-  launch_prepare(buf.prog, theta, n_batch, ld, plan.fr.H, plan.fr.W, ncomp, buf.derived, buf.psf_sel,
+  launch_prepare(*buf.prog_host, theta, n_batch, ld, plan.fr.H, plan.fr.W, ncomp, buf.derived, buf.psf_sel,
                  buf.wscale, fb.rconst, stream);
   FusedParams P;
   P.rconst = fb.rconst;

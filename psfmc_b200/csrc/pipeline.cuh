@@ -87,7 +87,7 @@ inline StagedPlan make_staged_plan(int H, int W, int n_components, size_t sizeof
 // theta -> per-walker constants. Small batches use 32 lanes per component (the
 // kernel is then bound by the length of its dependent float64 chain), large ones 8
 // (bound by the float64 pipe).
-inline void launch_prepare(const Program *prog, const double *theta, long long n_batch,
+inline void launch_prepare(const Program &prog, const double *theta, long long n_batch,
                            long long ld, int H, int W, int n_components, double *derived,
                            int *psf_sel, double *wscale, float *rconst, cudaStream_t stream) {
   const long long ngroups = n_batch * (n_components > 0 ? n_components : 1);
@@ -109,7 +109,8 @@ inline void launch_prepare(const Program *prog, const double *theta, long long n
 // Device-resident state the launch sequence needs (one per device per precision).
 template <typename T>
 struct StagedBuffers {
-  const Program *prog;
+  const Program *prog;        // device copy (row kernels)
+  const Program *prog_host;   // host copy with the device's table pointers (prepare)
   const cplx<T> *tw_w, *tw_h;
   const cplx<T> *spec;        // [K][2*Wc][H]
   const T *obs, *ovar;        // [H*W]
@@ -147,7 +148,7 @@ inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
                                  cudaEvent_t ev_end = nullptr) {
   if (n_batch <= 0) return;
   const Frame fr = plan.fr;
-  launch_prepare(buf.prog, theta, n_batch, ld, fr.H, fr.W, n_components, buf.derived, buf.psf_sel,
+  launch_prepare(*buf.prog_host, theta, n_batch, ld, fr.H, fr.W, n_components, buf.derived, buf.psf_sel,
                  buf.wscale, (float *)nullptr, stream);
   if (ev_begin) cudaEventRecord(ev_begin, stream);   // the three row/column kernels
   for (long long start = 0; start < n_batch; start += plan.chunk) {

@@ -88,12 +88,15 @@ __device__ __forceinline__ float sersic_pixel_f32(const SersicF32 &s, float x, f
 // wscale[b] receives the packing scale of the walker (see below);
 // psf_sel[b] receives the rint-ed PSF index (psfMC/distributions.py:130-138), or
 // -1 when it is out of range (the prior is -inf there; the walker gets -inf).
+// The program travels as a kernel parameter (constant bank): its per-slot lookups
+// are then constant loads instead of dependent global loads.
 template <int G>
-__global__ void prepare_kernel(const Program *__restrict__ prog,
+__global__ void prepare_kernel(const __grid_constant__ Program prog_c,
                                const double *__restrict__ theta, long long n_batch,
                                long long ld, int H, int W, double *__restrict__ derived,
                                int *__restrict__ psf_sel, double *__restrict__ wscale,
                                float *__restrict__ rconst) {
+  const Program *prog = &prog_c;
   const int ncomp_prog = prog->n_components;
   const int ncomp = ncomp_prog > 0 ? ncomp_prog : 1;   // an empty model still gets its
                                                        // per-walker PSF index and scale
@@ -141,11 +144,21 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
     }
     wscale[b] = sc;
   }
-  // every group of the warp takes part in the kappa iteration (shuffles)
+  // kappa = gammaincinv(2n, 1/2): from the engine's Chebyshev table when 2n is inside
+  // it, else by the group-cooperative iteration, in which every group of the warp has
+  // to take part (shuffles) -- so the iteration runs only if some lane needs it
   const bool is_sersic = live && kind == PSFMC_SERSIC;
   const double n_index = is_sersic ? slot_value(prog, c, PSFMC_P_INDEX, th) : 0.5;
-  double lgam_a1;
-  const double kappa = gammaincinv_half_group<G>(2.0 * n_index, glane, is_sersic, &lgam_a1);
+  double lgam_a1 = NAN;
+  bool tabulated = false;
+  double kappa = kappa_from_table(prog->kappa_coef, prog->kappa_nint, prog->kappa_u0,
+                                  prog->kappa_inv_du, 2.0 * n_index, &tabulated);
+  if (__any_sync(0xffffffffu, is_sersic && !tabulated)) {
+    const double slow = gammaincinv_half_group<G>(2.0 * n_index, glane,
+                                                  is_sersic && !tabulated, &lgam_a1);
+    if (!tabulated) kappa = slow;
+  }
+  if (is_sersic && tabulated) lgam_a1 = lgamma(2.0 * n_index + 1.0);
   if (!live) return;
   if (kind == PSFMC_SKY) {
     if (writer) out[D_SKY_ADU] = slot_value(prog, c, PSFMC_P_ADU, th);
@@ -218,6 +231,18 @@ __global__ void prepare_kernel(const Program *__restrict__ prog,
       rc[8] = s.p; rc[9] = s.c0; rc[10] = s.c1; rc[11] = s.kq;
     }
   }
+}
+
+// kappa at n_nodes values of a = 2n by the iteration (one warp per node): used once at
+// engine creation to build and to verify the Chebyshev table.
+__global__ void kappa_nodes_kernel(const double *__restrict__ a_nodes, int n_nodes,
+                                   double *__restrict__ kappa_out) {
+  const int node = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  const bool live = node < n_nodes;
+  double lgam;
+  const double k = gammaincinv_half_group<32>(live ? a_nodes[node] : 1.0, lane, live, &lgam);
+  if (live && lane == 0) kappa_out[node] = k;
 }
 
 // ------------------------------------------------------------ pixel math --

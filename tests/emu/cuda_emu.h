@@ -23,6 +23,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 #define __constant__ static
@@ -288,6 +289,7 @@ inline int __all_sync(unsigned, int pred) {
   }
   return all;
 }
+inline int __any_sync(unsigned mask, int pred) { return !__all_sync(mask, !pred); }
 template <typename T>
 inline T __ldg(const T *p) { return *p; }
 inline double atomicAdd(double *p, double v) { double o = *p; *p += v; return o; }

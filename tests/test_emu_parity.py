@@ -168,6 +168,8 @@ def test_emu_device_kappa_matches_scipy(emu_library, group, monkeypatch):
     cooperating lanes) against scipy over the whole prior range, through a one-Sersic
     model whose raw image at the effective radius equals sb_eff."""
     monkeypatch.setenv('PSFMC_PREPARE_GROUP', group)
+    # group '8' also switches the Chebyshev table off: the iteration itself is tested
+    monkeypatch.setenv('PSFMC_NO_KAPPA_TABLE', '1' if group == '8' else '0')
     from scipy.special import gammaincinv
     from psfmc_b200 import MultiComponentModel
     from psfmc_b200.components import Configuration, Sersic
@@ -179,9 +181,12 @@ def test_emu_device_kappa_matches_scipy(emu_library, group, monkeypatch):
     psf[4, 4] = 1.0
     comps = [Configuration(obs, ivm, psf, np.full((8, 8), 1e12), mag_zeropoint=25.0),
              Sersic(xy=(10.0, 16.0), mag=20.0, reff=6.0, reff_b=6.0,
-                    index=Uniform(loc=0.05, scale=20), angle=0.0)]
+                    index=Uniform(loc=0.01, scale=50), angle=0.0)]
     model = MultiComponentModel(comps, precision='fp64', library=emu_library)
-    ns = np.array([0.06, 0.13, 0.2, 0.36, 0.5, 0.75, 1.0, 1.7, 2.5, 4.0, 6.5, 9.9, 15.0])
+    assert model.engine.info()['kappa_table'] == (0 if group == '8' else 1)
+    # 0.03 and 40 lie outside the table (2n in [0.088, 64]): iteration fallback
+    ns = np.array([0.03, 0.06, 0.13, 0.2, 0.36, 0.5, 0.75, 1.0, 1.7, 2.5, 4.0, 6.5, 9.9,
+                   15.0, 31.9, 40.0])
     raw = model.engine.render(ns[:, None], which=('raw_model',))['raw_model']
     # pixel (x=16, y=16) is exactly at r = reff (circular): value = sbeff * (1 + corr)
     from oracle import psfmc_oracle as orc

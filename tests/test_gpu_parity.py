@@ -228,10 +228,13 @@ def test_multi_device_sharding(cuda_library):
                           multi.log_likelihood_batch(thetas))
 
 
-def test_device_kappa_matches_scipy(cuda_library):
+@pytest.mark.parametrize('table', ['1', '0'])
+def test_device_kappa_matches_scipy(cuda_library, table, monkeypatch):
     """kappa = gammaincinv(2n, 0.5), Gamma(2n) and sb_eff computed on the device
-    (group-cooperative Halley iteration, approximate float64 reciprocals) against
-    scipy over the whole prior range: the raw model at r = reff is sb_eff * (1 + corr)."""
+    (Chebyshev table built at engine creation, or the group-cooperative Halley
+    iteration with approximate float64 reciprocals) against scipy over the whole
+    prior range: the raw model at r = reff is sb_eff * (1 + corr)."""
+    monkeypatch.setenv('PSFMC_NO_KAPPA_TABLE', '0' if table == '1' else '1')
     from scipy.special import gammaincinv
     from oracle import psfmc_oracle as orc
     from psfmc_b200 import MultiComponentModel
@@ -243,10 +246,12 @@ def test_device_kappa_matches_scipy(cuda_library):
     comps = [Configuration(np.zeros((size, size)), np.ones((size, size)), psf,
                            np.full((8, 8), 1e12), mag_zeropoint=25.0),
              Sersic(xy=(10.0, 16.0), mag=20.0, reff=6.0, reff_b=6.0,
-                    index=Uniform(loc=0.05, scale=20), angle=0.0)]
+                    index=Uniform(loc=0.01, scale=50), angle=0.0)]
     model = MultiComponentModel(comps, precision='fp64')
-    ns = np.concatenate([[0.06, 0.13, 0.2, 0.36, 0.5, 0.75, 1.0, 1.7, 2.5, 4.0, 6.5, 9.9,
-                          15.0, 19.5], np.random.RandomState(4).uniform(0.1, 12, 500)])
+    assert model.engine.info()['kappa_table'] == int(table)
+    ns = np.concatenate([[0.03, 0.06, 0.13, 0.2, 0.36, 0.5, 0.75, 1.0, 1.7, 2.5, 4.0, 6.5,
+                          9.9, 15.0, 19.5, 31.9, 40.0],
+                         np.random.RandomState(4).uniform(0.1, 12, 500)])
     raw = model.engine.render(ns[:, None], which=('raw_model',))['raw_model']
     kappa = gammaincinv(2 * ns, 0.5)
     sbeff = orc.sersic_sb_eff(orc.mag_to_flux(20.0, 25.0), ns, 6.0, 6.0, kappa)
