@@ -251,10 +251,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must
-        # carry the one JSON line only
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # NCCL prints its version banner on stdout at NCCL_DEBUG >= VERSION; stdout must
+        # carry the one JSON line only: send NCCL's log to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            del os.environ['NCCL_DEBUG']
         dist.init_process_group('nccl', device_id=dev)
 
     walkers = args.walkers or default_walkers(args.workload)
