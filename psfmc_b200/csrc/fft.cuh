@@ -92,14 +92,19 @@ __device__ __forceinline__ int fft_swz(int i, bool on) {
 // L/8 threads with local indices tl = 0..L/8-1 (each owns 8 points per stage).
 // ALL threads of the CTA must call this together (it contains __syncthreads).
 // `tw` is the pass-ordered twiddle table described above. L is a power of two >= 16.
-template <typename T, bool INV>
-__device__ __forceinline__ void fft_line_smem(cplx<T> *line, int L, int logL, int tl,
+// LOGL != 0 fixes the length at compile time (L = 2^LOGL: all index arithmetic folds
+// into immediates and the pass loop unrolls); LOGL = 0 takes L, logL at run time.
+template <typename T, bool INV, int LOGL = 0>
+__device__ __forceinline__ void fft_line_smem(cplx<T> *line, int L_rt, int logL_rt, int tl,
                                               const cplx<T> *tw) {
+  const int logL = LOGL ? LOGL : logL_rt;
+  const int L = LOGL ? (1 << LOGL) : L_rt;
   const int n8 = logL / 3, rem = logL - 3 * n8;
   const int L8 = L >> 3;
   int Ns = 1, logNs = 0;
   const cplx<T> *twp = tw;     // table of the current pass
   cplx<T> v[8];
+#pragma unroll
   for (int s = 0; s < n8; ++s) {
     const bool in_swz = s > 0, out_swz = !(s == n8 - 1 && rem == 0);
     const int j = tl;

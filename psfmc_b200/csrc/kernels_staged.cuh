@@ -41,8 +41,10 @@ __device__ __forceinline__ void load_twiddles(cplx<T> *tw_s, const cplx<T> *tw_g
 // ------------------------------------------------------------- rows_fwd --
 // grid = (H / RB, B), block = RB * (W / 8)
 // dynamic smem: (RB*W + W) cplx<T> + n_components*STRIDE doubles
-template <typename T, int SRC>
-__global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ prog,
+// LOGW != 0: row length fixed at compile time (specialised instances for the
+// throughput path at 256 and 512 columns), 0: taken from `fr`.
+template <typename T, int SRC, int LOGW = 0>
+__global__ void rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__ prog,
                                 const double *__restrict__ derived,
                                 const double *__restrict__ wscale, int precision,
                                 const double *__restrict__ pad_a,
@@ -51,6 +53,12 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
                                 cplx<T> *__restrict__ scratch,
                                 T *__restrict__ raw_out) {
   PSFMC_DYN_SMEM(smem_raw);
+  Frame fr = fr_rt;
+  if (LOGW) {
+    fr.logW = LOGW;
+    fr.W = 1 << LOGW;
+    fr.Wc = (1 << LOGW) / 2 + 1;
+  }
   const int W = fr.W, H = fr.H, Wc = fr.Wc;
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const long long b = blockIdx.y;
@@ -141,7 +149,7 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
   {
     const int tpr = W >> 3;  // threads per row
     const int r = tid >> (fr.logW - 3), tl = tid & (tpr - 1);
-    fft_line_smem<T, false>(tile + r * PITCH, W, fr.logW, tl, tw_s);
+    fft_line_smem<T, false, LOGW>(tile + r * PITCH, W, fr.logW, tl, tw_s);
   }
 
   // ---- split z-spectrum into the spectra of the two real rows and store
@@ -169,13 +177,18 @@ __global__ void rows_fwd_kernel(Frame fr, int RB, const Program *__restrict__ pr
 #define PSFMC_COLS_SETUP 1  // forward only, scaled: produces the spectra themselves
 
 // grid = (ceil(2*Wc / CB), B), block = CB * (H / 8); smem (CB*H + H) cplx<T>
-template <typename T, int MODE>
-__global__ void cols_kernel(Frame fr, int CB, const cplx<T> *__restrict__ tw_h,
+template <typename T, int MODE, int LOGH = 0>
+__global__ void cols_kernel(Frame fr_rt, int CB, const cplx<T> *__restrict__ tw_h,
                             const cplx<T> *__restrict__ spec,
                             const int *__restrict__ psf_sel,
                             cplx<T> *__restrict__ scratch,
                             cplx<T> *__restrict__ spec_out) {
   PSFMC_DYN_SMEM(smem_raw);
+  Frame fr = fr_rt;
+  if (LOGH) {
+    fr.logH = LOGH;
+    fr.H = 1 << LOGH;
+  }
   const int H = fr.H, Wc = fr.Wc, ncol = 2 * Wc;
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const long long b = blockIdx.y;
@@ -208,7 +221,7 @@ __global__ void cols_kernel(Frame fr, int CB, const cplx<T> *__restrict__ tw_h,
 
   const int tpc = H >> 3;
   const int col = tid >> (fr.logH - 3), tl = tid & (tpc - 1);
-  fft_line_smem<T, false>(tile + col * H, H, fr.logH, tl, tw_s);
+  fft_line_smem<T, false, LOGH>(tile + col * H, H, fr.logH, tl, tw_s);
 
   if (MODE == PSFMC_COLS_SETUP) {
     // spec_out[b][c][ky] = F * (-1)^(kx+ky) / (H*W)
@@ -229,7 +242,7 @@ __global__ void cols_kernel(Frame fr, int CB, const cplx<T> *__restrict__ tw_h,
   for (int e = tid; e < nvalid; e += nthreads) tile[e] = tile[e] * sp[e];
   __syncthreads();
 
-  fft_line_smem<T, true>(tile + col * H, H, fr.logH, tl, tw_s);
+  fft_line_smem<T, true, LOGH>(tile + col * H, H, fr.logH, tl, tw_s);
 
 #ifndef PSFMC_EMU
   // (fft_line_smem ends with a CTA barrier after its last stores) one bulk store
@@ -273,8 +286,8 @@ struct Epilogue<float> {
 
 // grid = (H / RB, B), block = RB * (W / 8); smem (RB*W + W) cplx<T> + 32 doubles
 // img_* (optional, may be null): residual / composite IVM / convolved images.
-template <typename T>
-__global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw_w,
+template <typename T, int LOGW = 0>
+__global__ void rows_inv_kernel(Frame fr_rt, int RB, const cplx<T> *__restrict__ tw_w,
                                 const cplx<T> *__restrict__ scratch,
                                 const T *__restrict__ obs, const T *__restrict__ ovar,
                                 const unsigned char *__restrict__ bad,
@@ -285,6 +298,12 @@ __global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw
                                 T *__restrict__ img_conv, T *__restrict__ img_resid,
                                 T *__restrict__ img_ivm) {
   PSFMC_DYN_SMEM(smem_raw);
+  Frame fr = fr_rt;
+  if (LOGW) {
+    fr.logW = LOGW;
+    fr.W = 1 << LOGW;
+    fr.Wc = (1 << LOGW) / 2 + 1;
+  }
   const int W = fr.W, H = fr.H, Wc = fr.Wc;
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const long long b = blockIdx.y;
@@ -318,7 +337,7 @@ __global__ void rows_inv_kernel(Frame fr, int RB, const cplx<T> *__restrict__ tw
   {
     const int tpr = W >> 3;
     const int r = tid >> (fr.logW - 3), tl = tid & (tpr - 1);
-    fft_line_smem<T, true>(tile + r * PITCH, W, fr.logW, tl, tw_s);
+    fft_line_smem<T, true, LOGW>(tile + r * PITCH, W, fr.logW, tl, tw_s);
   }
 
   // undo the (exact, power-of-two) channel scalings of the variance image

@@ -157,26 +157,47 @@ inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
     ImageOutputs<T> img;
     if (images && (images_chunk_offset < 0 || images_chunk_offset == start)) img = *images;
     dim3 grid_rows(plan.n_rowblk, (unsigned)nb), grid_cols(plan.n_colblk, (unsigned)nb);
+    // float32 lnL path at 256 / 512 columns or rows: instances with the transform
+    // length fixed at compile time (the generic passes are bound by index arithmetic)
+    const bool fast32 = sizeof(T) == 4 && !ps_only;
+    const int lw = fast32 ? fr.logW : 0, lh = fast32 ? fr.logH : 0;
+    const double *wsc = (const double *)(buf.wscale + start);
+    const int *sel = (const int *)(buf.psf_sel + start);
+    double *part = buf.partials + start * plan.n_rowblk;
+#define PSFMC_ROWS_FWD(KERNEL)                                                               \
+  launch_kernel(KERNEL, grid_rows, dim3(plan.threads_rows), plan.smem_rows, stream, fr,      \
+                plan.RB, buf.prog, der, wsc, precision, (const double *)nullptr,             \
+                (const double *)nullptr, buf.tw_w, buf.scratch, img.raw)
+#define PSFMC_COLS(KERNEL)                                                                   \
+  launch_kernel(KERNEL, grid_cols, dim3(plan.threads_cols), plan.smem_cols, stream, fr,      \
+                plan.CB, buf.tw_h, buf.spec, sel, buf.scratch, (cplx<T> *)nullptr)
+#define PSFMC_ROWS_INV(KERNEL)                                                               \
+  launch_kernel(KERNEL, grid_rows, dim3(plan.threads_rows), plan.smem_rows, stream, fr,      \
+                plan.RB, buf.tw_w, (const cplx<T> *)buf.scratch, buf.obs, buf.ovar, buf.bad, \
+                wsc, sel, buf.vscale_inv, part, img.conv, img.resid, img.ivm)
     if (ps_only)
-      launch_kernel(rows_fwd_kernel<T, PSFMC_SRC_RENDER_PS>, grid_rows,
-                    dim3(plan.threads_rows), plan.smem_rows, stream, fr, plan.RB, buf.prog,
-                    der, (const double *)(buf.wscale + start), precision,
-                    (const double *)nullptr, (const double *)nullptr, buf.tw_w, buf.scratch,
-                    img.raw);
+      PSFMC_ROWS_FWD((rows_fwd_kernel<T, PSFMC_SRC_RENDER_PS>));
+    else if (lw == 8)
+      PSFMC_ROWS_FWD((rows_fwd_kernel<T, PSFMC_SRC_RENDER, 8>));
+    else if (lw == 9)
+      PSFMC_ROWS_FWD((rows_fwd_kernel<T, PSFMC_SRC_RENDER, 9>));
     else
-      launch_kernel(rows_fwd_kernel<T, PSFMC_SRC_RENDER>, grid_rows,
-                    dim3(plan.threads_rows), plan.smem_rows, stream, fr, plan.RB, buf.prog,
-                    der, (const double *)(buf.wscale + start), precision,
-                    (const double *)nullptr, (const double *)nullptr, buf.tw_w, buf.scratch,
-                    img.raw);
-    launch_kernel(cols_kernel<T, PSFMC_COLS_CONV>, grid_cols, dim3(plan.threads_cols),
-                  plan.smem_cols, stream, fr, plan.CB, buf.tw_h, buf.spec,
-                  (const int *)(buf.psf_sel + start), buf.scratch, (cplx<T> *)nullptr);
-    launch_kernel(rows_inv_kernel<T>, grid_rows, dim3(plan.threads_rows), plan.smem_rows,
-                  stream, fr, plan.RB, buf.tw_w, (const cplx<T> *)buf.scratch, buf.obs,
-                  buf.ovar, buf.bad, (const double *)(buf.wscale + start),
-                  (const int *)(buf.psf_sel + start), buf.vscale_inv,
-                  buf.partials + start * plan.n_rowblk, img.conv, img.resid, img.ivm);
+      PSFMC_ROWS_FWD((rows_fwd_kernel<T, PSFMC_SRC_RENDER>));
+    if (lh == 8)
+      PSFMC_COLS((cols_kernel<T, PSFMC_COLS_CONV, 8>));
+    else if (lh == 9)
+      PSFMC_COLS((cols_kernel<T, PSFMC_COLS_CONV, 9>));
+    else
+      PSFMC_COLS((cols_kernel<T, PSFMC_COLS_CONV>));
+    if (lw == 8)
+      PSFMC_ROWS_INV((rows_inv_kernel<T, 8>));
+    else if (lw == 9)
+      PSFMC_ROWS_INV((rows_inv_kernel<T, 9>));
+    else
+      PSFMC_ROWS_INV((rows_inv_kernel<T>));
+#undef PSFMC_ROWS_FWD
+#undef PSFMC_COLS
+#undef PSFMC_ROWS_INV
   }
   if (ev_end) cudaEventRecord(ev_end, stream);
   {
