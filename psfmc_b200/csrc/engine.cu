@@ -293,6 +293,14 @@ struct Engine : EngineBase {
 
   int lnlike_host(const double *theta, long long B, long long ld, double *out) override {
     if (B <= 0) return 0;
+#ifdef PSFMC_EMU
+    const bool zero_copy_out = true;    // "device" memory is host memory
+#else
+    static const bool zero_copy_out = [] {
+      const char *env = getenv("PSFMC_NO_ZERO_COPY");
+      return !(env && env[0] == '1');
+    }();
+#endif
     const int D = (int)ld;
     const int nd = (int)devs.size();
     long long base = B / nd, extra = B % nd, row = 0;
@@ -328,16 +336,21 @@ struct Engine : EngineBase {
       }
       CUDA_TRY(cudaMemcpyAsync(d.theta.ptr, src, nel * sizeof(double),
                                cudaMemcpyHostToDevice, d.stream));
-      int rc = enqueue(d, d.theta.ptr, d.nrows, ld, d.lnl.ptr, d.stream);
-      if (rc) return rc;
+      // lnL is written by the kernels straight into page-locked host memory (the
+      // caller's buffer if it is pinned, else the engine's staging buffer): under
+      // unified addressing the pointer is valid on the device, and the few bytes per
+      // walker do not need a separate device-to-host copy after the kernel
       double *dst = out + d.row0;
       if (!out_pinned) {
         if (d.lnl_pin.ensure((size_t)d.nrows))
           return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
         dst = d.lnl_pin.ptr;
       }
-      CUDA_TRY(cudaMemcpyAsync(dst, d.lnl.ptr, (size_t)d.nrows * sizeof(double),
-                               cudaMemcpyDeviceToHost, d.stream));
+      int rc = enqueue(d, d.theta.ptr, d.nrows, ld, zero_copy_out ? dst : d.lnl.ptr, d.stream);
+      if (rc) return rc;
+      if (!zero_copy_out)
+        CUDA_TRY(cudaMemcpyAsync(dst, d.lnl.ptr, (size_t)d.nrows * sizeof(double),
+                                 cudaMemcpyDeviceToHost, d.stream));
     }
     for (int i = 0; i < nd; ++i) {
       DeviceState<T> &d = devs[i];
