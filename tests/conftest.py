@@ -150,3 +150,34 @@ def assert_lnl_close(got, expect, precision, bounds=None):
     worst = np.argmax(err / bound)
     assert np.all(err <= bound), 'worst |dlnL| {} (bound {}) at lnL {}'.format(
         err[worst], bound[worst], expect[finite][worst])
+
+
+def mixed_model_128(precision, library=None):
+    """128 x 128 model exercising the fused kernel's less common render paths: two
+    point sources (bilinear and Lanczos, one clipped at the frame edge), a Sersic with
+    fixed shape parameters and its angle in radians, a fixed sky, bad pixels."""
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.components import Configuration, PointSource, Sersic, Sky
+    from psfmc_b200.distributions import Normal, Uniform
+    rng = np.random.RandomState(12)
+    obs = 0.05 * rng.standard_normal((128, 128))
+    ivm = np.full((128, 128), 400.0)
+    ivm[5, 7] = 0.0
+    ivm[100:104, 20:30] = -1.0
+    obs[9, 100] = np.nan
+    psf = np.zeros((32, 32))
+    yy, xx = np.mgrid[0:32, 0:32]
+    psf += np.exp(-0.5 * ((xx - 16) ** 2 + (yy - 16) ** 2) / 2.0 ** 2)
+    psf_ivm = 1.0 / (psf / 200.0 + 1e-4)
+    comps = [Configuration(obs, ivm, psf, psf_ivm, mag_zeropoint=25.0),
+             Sky(adu=0.003),
+             PointSource(xy=Uniform(loc=np.array((60.0, 60.0)), scale=np.array((8.0, 8.0))),
+                         mag=Uniform(loc=18, scale=2), shift_method='bilinear'),
+             PointSource(xy=Uniform(loc=np.array((0.0, 120.0)), scale=np.array((4.0, 7.9))),
+                         mag=19.5),
+             Sersic(xy=Uniform(loc=np.array((58.0, 58.0)), scale=np.array((10.0, 10.0))),
+                    mag=Uniform(loc=19, scale=3), reff=7.0, reff_b=3.0,
+                    index=Normal(loc=2.0, scale=0.3), angle=0.4),
+             Sersic(xy=(70.25, 61.5), mag=21.0, reff=Uniform(loc=3, scale=4), reff_b=2.5,
+                    index=1.0, angle=Uniform(loc=0, scale=3.1), angle_degrees=False)]
+    return MultiComponentModel(comps, precision=precision, library=library)

@@ -8,7 +8,7 @@ it says nothing about speed. The product library is never built this way.
 import numpy as np
 import pytest
 
-from conftest import (assert_lnl_close, fp32_bounds, load_golden, model_from_file,
+from conftest import (assert_lnl_close, mixed_model_128, fp32_bounds, load_golden, model_from_file,
                       oracle_from_model)
 
 
@@ -224,3 +224,19 @@ def test_emu_accumulate_matches_rendered_images(emu_library, c1_golden):
         assert np.allclose(fast[name], model.posterior_images[name], rtol=1e-11), name
     empty = model.engine.accumulate(thetas[:0].reshape(0, 18), ('residual',))
     assert np.all(empty['residual'] == 0)
+
+
+def test_emu_mixed_components_fused_and_fp64(emu_library):
+    """Bilinear + edge-clipped Lanczos point sources, fixed and free Sersic parameters,
+    angle in radians, fixed sky, bad pixels: fused float32 kernel and float64 staged
+    kernels against the oracle."""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model64 = mixed_model_128('fp64', library=emu_library)
+    thetas = draw_walkers_fast(model64, 5, seed=8)
+    expect = oracle_from_model(model64).lnlike_batch(thetas)
+    assert np.all(np.isfinite(expect))
+    assert_lnl_close(model64.log_likelihood_batch(thetas), expect, 'fp64')
+    model32 = mixed_model_128('fp32', library=emu_library)
+    assert model32.engine.info()['path'] == 1
+    assert_lnl_close(model32.log_likelihood_batch(thetas), expect, 'fp32',
+                     fp32_bounds(model32, thetas))

@@ -6,7 +6,8 @@ reference (tests/golden/make_golden.py) and against the oracle on seeded inputs.
 import numpy as np
 import pytest
 
-from conftest import (assert_lnl_close, fp32_bounds, load_golden, model_from_file,
+from conftest import (assert_lnl_close, fp32_bounds, load_golden, mixed_model_128,
+                      model_from_file,
                       oracle_from_model)
 
 pytestmark = pytest.mark.gpu
@@ -335,3 +336,19 @@ def test_accumulate_on_device_matches_rendered_images(cuda_library, c1_golden):
             else imgs[name].sum(axis=0)
         scale = np.abs(want[np.isfinite(want)]).max()
         assert np.allclose(sums[name], want, rtol=1e-6, atol=1e-9 * scale, equal_nan=True), name
+
+
+def test_gpu_mixed_components_fused_and_fp64(cuda_library):
+    """Bilinear + edge-clipped Lanczos point sources, fixed and free Sersic parameters,
+    angle in radians, fixed sky, bad pixels: fused float32 kernel and float64 staged
+    kernels against the oracle."""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model64 = mixed_model_128('fp64')
+    thetas = draw_walkers_fast(model64, 64, seed=8)
+    expect = oracle_from_model(model64).lnlike_batch(thetas)
+    assert np.all(np.isfinite(expect))
+    assert_lnl_close(model64.log_likelihood_batch(thetas), expect, 'fp64')
+    model32 = mixed_model_128('fp32')
+    assert model32.engine.info()['path'] == 1
+    assert_lnl_close(model32.log_likelihood_batch(thetas), expect, 'fp32',
+                     fp32_bounds(model32, thetas))
