@@ -72,6 +72,13 @@ extern "C" {
                              reference does for float32 FITS inputs on numpy 1.x
                              (oracle mode M2; psfMC/models.py:249)                  */
 
+/* descriptor flags */
+#define PSFMC_DESC_NO_FP64_RESCUE 1 /* PSFMC_PREC_FP32 only: psfmc_lnlike_batch normally
+                             repeats every walker whose float32 result is non-finite in
+                             float64 on the GPU (a model whose dynamic range exceeds what
+                             a float32 transform resolves gives a negative variance, where
+                             the float64 reference is finite); this flag turns that off */
+
 /* images psfmc_render_batch can return: the blobs of psfMC/models.py:222-226 */
 #define PSFMC_IMG_RAW_MODEL 1u
 #define PSFMC_IMG_CONVOLVED_MODEL 2u
@@ -115,7 +122,7 @@ typedef struct psfmc_desc {
   int32_t n_devices;       /* 0: use the current CUDA device only                */
   const int32_t *devices;  /* CUDA ordinals; batches are split contiguously       */
   int32_t max_batch;       /* hint: largest B per call (0 = grow on demand)      */
-  int32_t flags;           /* reserved, 0                                         */
+  int32_t flags;           /* PSFMC_DESC_*                                        */
 } psfmc_desc;
 
 typedef struct psfmc_engine psfmc_engine;
@@ -129,7 +136,9 @@ void psfmc_engine_destroy(psfmc_engine *engine);
 /* lnL for B parameter vectors held in HOST memory (theta[b*ld + j], ld >= D).
  * Blocking. Rows are split over the engine's devices; the only cross-device
  * traffic is the per-walker lnL copied back. lnl_out[b] = -inf for non-finite
- * results. This is what the pool-like map object calls for emcee. */
+ * results. In PSFMC_PREC_FP32 a non-finite float32 result is first repeated in
+ * float64 on the engine's first device (PSFMC_DESC_NO_FP64_RESCUE turns that off).
+ * This is what the pool-like map object calls for emcee. */
 int psfmc_lnlike_batch(psfmc_engine *engine, const double *theta, int64_t n_batch,
                        int64_t ld, double *lnl_out);
 
@@ -170,7 +179,8 @@ typedef struct psfmc_info {
   int64_t launches_total;   /* kernels launched by this engine since creation     */
   int32_t kappa_table;      /* 1: the Sersic kappa comes from the Chebyshev table built
                                and verified at creation; 0: from the iteration       */
-  int32_t reserved;
+  int32_t rescued_total;    /* walkers re-evaluated in float64 by psfmc_lnlike_batch
+                               (PSFMC_PREC_FP32, see PSFMC_DESC_NO_FP64_RESCUE)      */
 } psfmc_info;
 int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info);
 

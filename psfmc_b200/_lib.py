@@ -16,6 +16,7 @@ P_ADU, P_X, P_Y, P_MAG, P_REFF, P_REFF_B, P_INDEX, P_ANGLE = 0, 0, 1, 2, 3, 4, 5
 NSLOTS = 7
 MAX_COMPONENTS = 32
 PREC_FP64, PREC_FP32, PREC_FP64_RAWF32 = 0, 1, 2
+DESC_NO_FP64_RESCUE = 1
 PRECISIONS = {'fp64': PREC_FP64, 'fp32': PREC_FP32, 'fp64_rawf32': PREC_FP64_RAWF32}
 IMAGE_BITS = {'raw_model': 1, 'convolved_model': 2, 'residual': 4,
               'composite_ivm': 8, 'point_source_subtracted': 16}
@@ -65,7 +66,7 @@ class Info(ctypes.Structure):
         ('fft_flops_per_eval', ctypes.c_double),
         ('hbm_bytes_per_eval', ctypes.c_double),
         ('launches_total', ctypes.c_int64),
-        ('kappa_table', ctypes.c_int32), ('reserved', ctypes.c_int32),
+        ('kappa_table', ctypes.c_int32), ('rescued_total', ctypes.c_int32),
     ]
 
 

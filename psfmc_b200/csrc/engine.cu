@@ -135,6 +135,7 @@ struct EngineBase {
   bool kappa_table = false;  // Chebyshev table of the Sersic kappa accepted
   long long launches = 0;
   int n_devices = 0;
+  int first_ordinal = 0;     // CUDA ordinal of the engine's first device
 };
 
 template <typename T>
@@ -704,6 +705,7 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
 
   eng->devs.resize(ordinals.size());
   eng->n_devices = (int)ordinals.size();
+  eng->first_ordinal = ordinals[0];
   int rc = 0;
   for (size_t i = 0; i < ordinals.size() && !rc; ++i) {
     DeviceState<T> &ds = eng->devs[i];
@@ -841,9 +843,78 @@ __global__ void fma_probe_kernel(float *out, int iters, float a, float b) {
 
 }  // namespace
 
-struct psfmc_engine {
-  EngineBase *impl;
+// Deep copy of a descriptor (the engine keeps no caller pointer): what the float32
+// engine needs to build its float64 rescue engine later.
+struct SavedDesc {
+  psfmc_desc d;
+  std::vector<double> obs, var, psf, psf_var;
+  std::vector<uint8_t> bad;
+  std::vector<psfmc_component> comps;
+  int32_t device = 0;
+  explicit SavedDesc(const psfmc_desc *src, int ordinal) : d(*src), device(ordinal) {
+    const size_t npx = (size_t)src->height * src->width;
+    const size_t nps = (size_t)src->n_psf * src->psf_height * src->psf_width;
+    obs.assign(src->obs_data, src->obs_data + npx);
+    var.assign(src->obs_var, src->obs_var + npx);
+    bad.assign(src->bad_px, src->bad_px + npx);
+    psf.assign(src->psf, src->psf + nps);
+    psf_var.assign(src->psf_var, src->psf_var + nps);
+    if (src->n_components > 0)
+      comps.assign(src->components, src->components + src->n_components);
+    d.obs_data = obs.data();
+    d.obs_var = var.data();
+    d.bad_px = bad.data();
+    d.psf = psf.data();
+    d.psf_var = psf_var.data();
+    d.components = comps.data();
+    d.precision = PSFMC_PREC_FP64;
+    d.n_devices = 1;
+    d.devices = &device;
+    d.max_batch = 0;
+  }
 };
+
+struct psfmc_engine {
+  EngineBase *impl = nullptr;
+  // float64 rescue of the float32 mode (see psfmc_lnlike_batch)
+  SavedDesc *saved = nullptr;
+  EngineBase *rescue = nullptr;
+  long long rescued = 0;
+  std::vector<double> r_theta, r_lnl;
+  std::vector<long long> r_rows;
+};
+
+// A float32 evaluation that came back non-finite is repeated in float64 on the GPU:
+// the float32 transform of a model with a huge dynamic range (a Sersic centre within
+// ~1e-2 px of a pixel centre at a high index: raw peaks ~1e5 x the rest) leaves
+// rounding noise in the convolved variance that exceeds the observation variance at
+// far pixels -> negative IVM -> NaN -> -inf, where the reference in float64 is finite.
+// (The reference run on float32 arrays under numpy >= 2 fails the same way.) Walkers
+// that are -inf for a real reason (PSF index out of range, a Sersic centre exactly on
+// a pixel) stay -inf. Rare: ~5e-4 of prior-drawn walkers of the example model, none
+// in a converged chain.
+static int rescue_nonfinite(psfmc_engine *engine, const double *theta, int64_t n_batch,
+                            int64_t ld, double *lnl_out) {
+  engine->r_rows.clear();
+  for (int64_t b = 0; b < n_batch; ++b)
+    if (!(lnl_out[b] > -INFINITY)) engine->r_rows.push_back(b);
+  if (engine->r_rows.empty()) return 0;
+  if (!engine->rescue) {
+    int rc = create_engine<double>(&engine->saved->d, &engine->rescue);
+    if (rc) return rc;
+  }
+  const size_t nr = engine->r_rows.size();
+  engine->r_theta.resize(nr * (size_t)ld);
+  engine->r_lnl.resize(nr);
+  for (size_t k = 0; k < nr; ++k)
+    memcpy(&engine->r_theta[k * ld], theta + engine->r_rows[k] * ld, sizeof(double) * ld);
+  int rc = engine->rescue->lnlike_host(engine->r_theta.data(), (long long)nr, ld,
+                                       engine->r_lnl.data());
+  if (rc) return rc;
+  for (size_t k = 0; k < nr; ++k) lnl_out[engine->r_rows[k]] = engine->r_lnl[k];
+  engine->rescued += (long long)nr;
+  return 0;
+}
 
 extern "C" {
 
@@ -867,6 +938,11 @@ int psfmc_engine_create(const psfmc_desc *desc, psfmc_engine **out) {
   if (rc) return rc;
   psfmc_engine *eng = new psfmc_engine();
   eng->impl = impl;
+  bool want_rescue = desc->precision == PSFMC_PREC_FP32 &&
+                     !(desc->flags & PSFMC_DESC_NO_FP64_RESCUE);
+  if (const char *env = getenv("PSFMC_NO_FP64_RESCUE"))
+    if (env[0] == '1') want_rescue = false;
+  if (want_rescue) eng->saved = new SavedDesc(desc, impl->first_ordinal);
   *out = eng;
   return 0;
 }
@@ -876,6 +952,8 @@ void psfmc_engine_destroy(psfmc_engine *engine) {
   int prev = 0;
   cudaGetDevice(&prev);
   delete engine->impl;
+  delete engine->rescue;
+  delete engine->saved;
   delete engine;
   cudaSetDevice(prev);
 }
@@ -889,6 +967,7 @@ int psfmc_lnlike_batch(psfmc_engine *engine, const double *theta, int64_t n_batc
   int prev = 0;
   cudaGetDevice(&prev);
   int rc = engine->impl->lnlike_host(theta, n_batch, ld, lnl_out);
+  if (!rc && engine->saved) rc = rescue_nonfinite(engine, theta, n_batch, ld, lnl_out);
   cudaSetDevice(prev);
   return rc;
 }
@@ -967,6 +1046,8 @@ int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info) {
   info->kernels_per_call = e->path == 1 ? 2 : 5;
   info->launches_total = e->launches;
   info->kappa_table = e->kappa_table ? 1 : 0;
+  info->rescued_total =
+      (int32_t)(engine->rescued > 0x7fffffffLL ? 0x7fffffffLL : engine->rescued);
   return 0;
 }
 

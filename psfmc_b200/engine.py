@@ -49,11 +49,13 @@ class LikelihoodEngine(object):
     :param precision: 'fp32' (float32 render/FFT, float64 accumulation; default),
         'fp64' (everything float64) or 'fp64_rawf32'
     :param devices: CUDA ordinals to shard batches over (default: current device)
+    :param fp64_rescue: 'fp32' only: walkers whose float32 result is non-finite are
+        repeated in float64 on the GPU (default); False = raw float32 behaviour
     """
 
     def __init__(self, obs_data, obs_var, bad_px, psfs, psf_vars, mag_zeropoint,
                  program, psf_index_slot=('const', 0), precision='fp32',
-                 devices=None, max_batch=0, library=None):
+                 devices=None, max_batch=0, library=None, fp64_rescue=True):
         self._lib = _lib.load(library)
         self._handle = ctypes.c_void_p()
         obs = np.ascontiguousarray(obs_data, dtype=np.float64)
@@ -112,6 +114,7 @@ class LikelihoodEngine(object):
             desc.n_devices = len(devices)
             desc.devices = devs
         desc.max_batch = int(max_batch)
+        desc.flags = 0 if fp64_rescue else _lib.DESC_NO_FP64_RESCUE
         _lib.check(self._lib, self._lib.psfmc_engine_create(
             ctypes.byref(desc), ctypes.byref(self._handle)))
         self.shape = obs.shape

@@ -24,13 +24,15 @@ class MultiComponentModel(object):
         name of a model file
     :param precision: engine precision ('fp32' default, 'fp64', 'fp64_rawf32')
     :param devices: CUDA ordinals to shard walker batches over
+    :param fp64_rescue: 'fp32' only: repeat non-finite float32 evaluations in float64
+        on the GPU (default True; see include/psfmc_b200.h PSFMC_DESC_NO_FP64_RESCUE)
     :param with_blobs: if True, ``log_posterior`` returns the five images per
         evaluation like the reference (slow: they travel to the host); the default
         returns empty blobs and posterior images are re-rendered from the chain
     """
 
     def __init__(self, components, precision='fp32', devices=None,
-                 with_blobs=False, library=None):
+                 with_blobs=False, library=None, fp64_rescue=True):
         if isinstance(components, str):
             components = component_list_from_file(components)
         components = list(components)
@@ -61,7 +63,7 @@ class MultiComponentModel(object):
             config.obs_data, config.obs_var, config.bad_px,
             selector.psf_images, selector.var_images, config.mag_zeropoint,
             self.program, self.psf_index_slot, precision=precision,
-            devices=devices, library=library)
+            devices=devices, library=library, fp64_rescue=fp64_rescue)
 
         self._param_vector = np.zeros(self.num_params)
         self.posterior_images = {}

@@ -181,3 +181,41 @@ def mixed_model_128(precision, library=None):
              Sersic(xy=(70.25, 61.5), mag=21.0, reff=Uniform(loc=3, scale=4), reff_b=2.5,
                     index=1.0, angle=Uniform(loc=0, scale=3.1), angle_degrees=False)]
     return MultiComponentModel(comps, precision=precision, library=library)
+
+# Two prior-drawn walkers of the C1 model (seed 77, rows 2200 and 2217 of 4096) whose
+# Sersic centre lies ~3e-3 px from a pixel centre at index 8.8 / 7.6: the raw model
+# peaks at 5e5 and the float32 transform leaves negative variances at far pixels.
+# The float64 reference is finite (-7.8e5); the reference on float32 arrays under
+# numpy >= 2 (oracle mode M1) gives -inf, like the raw float32 kernels.
+HIGH_DYNAMIC_RANGE_THETAS = [
+    [-1.50520e-02, 2.17831e+01, 7.05861e+01, 6.06020e+01, 2.31439e+01, 8.82537e+00,
+     2.17054e+01, 8.19306e+00, 3.16874e+00, 7.20025e+01, 6.90073e+01, 8.57218e+01,
+     1.98887e+00, 2.36680e+01, 6.90261e+00, 3.29286e+00, 4.66194e+01, 8.50845e+01],
+    [-7.72354e-03, 2.07897e+01, 6.65900e+01, 6.20912e+01, 1.16326e+02, 3.09299e+00,
+     2.18998e+01, 1.12871e+01, 4.28030e+00, 6.94145e+01, 7.14683e+01, 1.70829e+02,
+     7.63948e+00, 2.47298e+01, 5.87249e+00, 3.92618e+00, 4.20018e+01, 8.49977e+01]]
+
+
+def check_fp64_rescue(library, c1_golden):
+    """float32 mode: non-finite float32 results are repeated in float64 on the device
+    (psfmc_lnlike_batch); really infinite walkers stay -inf; the flag turns it off."""
+    exact = c1_golden['names'].index('C_exact_centre')
+    thetas = np.array(HIGH_DYNAMIC_RANGE_THETAS + [c1_golden['theta'][exact],
+                                                   c1_golden['theta'][0]])
+    model = model_from_file('j0005/model_c1.py', 'fp32', library=library,
+                            obs_dtype=np.float64)
+    oracle = oracle_from_model(model)
+    expect = oracle.lnlike_batch(thetas)
+    assert np.all(np.isfinite(expect[[0, 1, 3]])) and expect[2] == -np.inf
+    m1 = oracle_from_model(model, fft_upcast=False).lnlike_batch(thetas[:2].astype(np.float64))
+    got = model.log_likelihood_batch(thetas)
+    assert got[2] == -np.inf
+    assert_lnl_close(got[[0, 1]], expect[[0, 1]], 'fp64')       # came from the float64 kernels
+    assert_lnl_close(got[[3]], expect[[3]], 'fp32', fp32_bounds(model, thetas[[3]]))
+    assert model.engine.info()['rescued_total'] == 3
+    raw = model_from_file('j0005/model_c1.py', 'fp32', library=library,
+                          obs_dtype=np.float64, fp64_rescue=False)
+    got_raw = raw.log_likelihood_batch(thetas)
+    assert np.all(got_raw[:3] == -np.inf) and got_raw[3] == got[3]
+    assert raw.engine.info()['rescued_total'] == 0
+    return m1

@@ -352,3 +352,9 @@ def test_gpu_mixed_components_fused_and_fp64(cuda_library):
     assert model32.engine.info()['path'] == 1
     assert_lnl_close(model32.log_likelihood_batch(thetas), expect, 'fp32',
                      fp32_bounds(model32, thetas))
+
+
+@pytest.mark.gpu
+def test_gpu_fp64_rescue_of_high_dynamic_range_walkers(cuda_library, c1_golden):
+    from conftest import check_fp64_rescue
+    check_fp64_rescue(cuda_library, c1_golden)
