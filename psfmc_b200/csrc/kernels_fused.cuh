@@ -162,11 +162,13 @@ __device__ __forceinline__ void fused_render16(const FusedParams &P, long long b
       s.p = q2.x; s.c0 = q2.y; s.c1 = q2.z; s.kq = q2.w;
       const float dy = ((float)y - s.yi) - s.yf;
       const float cu = s.a01 * dy, cv = s.a11 * dy, dy2 = dy * dy;
-      // (l - xi) and 8*j are exact in float32, so dx0 + 8*j == (x - xi) - xf to 1 ulp
-      const float dx0 = ((float)l - s.xi) - s.xf;
+      // (x - xi) is an exact small integer; subtracting the fraction LAST keeps dx
+      // accurate to an ulp of dx itself next to the centre (where the profile and its
+      // centroid correction vary as a power of the distance)
+      const cplx<float> dxi = bcast((float)l - s.xi), nxf = bcast(-s.xf);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const cplx<float> dx = mk<float>(dx0 + (float)(16 * i), dx0 + (float)(16 * i + 8));
+        const cplx<float> dx = (dxi + mk<float>((float)(16 * i), (float)(16 * i + 8))) + nxf;
         acc[i] = acc[i] + sersic_pair_f32(s, dx, cu, cv, dy2);
       }
     } else {  // point source: at most 7 x 7 pixels of the frame, float64 taps

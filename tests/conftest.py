@@ -219,3 +219,17 @@ def check_fp64_rescue(library, c1_golden):
     assert np.all(got_raw[:3] == -np.inf) and got_raw[3] == got[3]
     assert raw.engine.info()['rescued_total'] == 0
     return m1
+
+
+def check_near_centre_walkers(library):
+    """Sersic centres within ~0.1 px of a pixel centre (steep central pixel): float32
+    fused kernel against the oracle within the stated bound."""
+    data = load_golden('c1_near_centre.json')
+    thetas = np.array(data['theta'])
+    model = model_from_file('j0005/model_c1.py', 'fp32', library=library, fp64_rescue=False)
+    assert model.engine.info()['path'] == 1
+    oracle = oracle_from_model(model)
+    expect = oracle.lnlike_batch(thetas)
+    assert np.allclose(expect, data['lnl_fp64'], rtol=1e-7)   # same walkers, same model
+    assert_lnl_close(model.log_likelihood_batch(thetas), expect, 'fp32',
+                     0.25 * fp32_bounds(model, thetas, oracle))

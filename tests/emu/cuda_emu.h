@@ -3,11 +3,12 @@
 // (this container has no GPU). It is never part of the product: libpsfmc_b200.so
 // is built by nvcc without this header, and nothing in psfmc_b200/ includes it.
 //
-// Model: one CTA at a time; every CUDA thread is a ucontext fiber. __syncthreads
+// Model: one CTA (or one thread-block cluster) at a time; every CUDA thread is a ucontext fiber. __syncthreads
 // and the warp shuffles are cooperative yield points; the scheduler runs fibers
 // round-robin and aborts on deadlock (a barrier not reached by all live threads),
 // which catches divergent-barrier bugs. No attempt is made to model timing.
 #pragma once
+#include <sys/mman.h>
 #include <ucontext.h>
 
 #include <cmath>
@@ -43,25 +44,31 @@ typedef void *cudaStream_t;
 
 namespace emu {
 
+// Fiber stacks: mmap-ed and committed lazily (a 4-CTA cluster of 512-thread CTAs is
+// 2048 fibers).
+constexpr size_t kStackBytes = 256 * 1024;
+
 struct Fiber {
   ucontext_t ctx;
-  std::vector<unsigned char> stack;
+  unsigned char *stack = nullptr;
   uint3 tid;
   int linear;
   bool done = false;
   // barrier bookkeeping
-  int wait_kind = 0;        // 0 none, 1 block barrier, 2 warp exchange
+  int wait_kind = 0;        // 0 none, 1 block barrier, 2 warp exchange, 3 named, 4 cluster
   unsigned long long wait_gen = 0;
+  unsigned long long cluster_gen = 0;   // generation seen at barrier.cluster.arrive
 };
 
+// One CTA. A launch runs one CLUSTER of CTAs at a time (cluster size 1 = the classic
+// one-CTA-at-a-time model); all fibers of the cluster are scheduled round-robin.
 struct State {
-  ucontext_t sched;
   std::vector<Fiber> fibers;
   Fiber *cur = nullptr;
   dim3 grid, block;
   uint3 bid;
+  unsigned cta_rank = 0;
   std::vector<unsigned char> smem;
-  std::function<void()> body;
   // block barrier
   int bar_count = 0;
   unsigned long long bar_gen = 0;
@@ -83,24 +90,36 @@ struct State {
   };
   std::vector<Named> named;
   int live = 0;
-  unsigned long long progress = 0;
 };
 
-inline State &S() {
-  static State st;
-  return st;
+struct Global {
+  ucontext_t sched;
+  State *cur = nullptr;                 // CTA of the running fiber
+  std::vector<State *> cluster;         // CTAs of the running cluster (by rank)
+  std::function<void()> body;
+  unsigned long long progress = 0;
+  // barrier.cluster
+  int cl_count = 0;
+  unsigned long long cl_gen = 0;
+};
+
+inline Global &G() {
+  static Global g;
+  return g;
 }
 
-inline void yield_to_sched() { swapcontext(&S().cur->ctx, &S().sched); }
+inline State &S() { return *G().cur; }
+
+inline void yield_to_sched() { swapcontext(&S().cur->ctx, &G().sched); }
 
 inline void fiber_entry() {
+  G().body();
   State &st = S();
-  st.body();
   st.cur->done = true;
-  st.progress++;
+  G().progress++;
   st.live--;
   st.warps[st.cur->linear / 32].live--;
-  swapcontext(&st.cur->ctx, &st.sched);
+  swapcontext(&st.cur->ctx, &G().sched);
 }
 
 inline void syncthreads() {
@@ -110,7 +129,7 @@ inline void syncthreads() {
   if (st.bar_count >= st.live) {  // last arrival releases everybody
     st.bar_count = 0;
     st.bar_gen++;
-    st.progress++;
+    G().progress++;
     return;
   }
   st.cur->wait_kind = 1;
@@ -125,7 +144,7 @@ inline void warp_barrier(State::Warp &w, int &count, unsigned long long &gen) {
   if (count >= w.live) {
     count = 0;
     gen++;
-    st.progress++;
+    G().progress++;
     return;
   }
   st.cur->wait_kind = 2;
@@ -150,13 +169,36 @@ inline void named_barrier(int id, int nthreads) {
   if (nb.count >= nthreads) {
     nb.count = 0;
     nb.gen++;
-    st.progress++;
+    G().progress++;
     return;
   }
   st.cur->wait_kind = 3;
   while (nb.gen == gen) yield_to_sched();
   st.cur->wait_kind = 0;
 }
+
+// barrier.cluster.arrive / .wait over all live threads of the cluster (split phase:
+// work between the two overlaps the other CTAs' arrival)
+inline void cluster_arrive() {
+  Global &g = G();
+  S().cur->cluster_gen = g.cl_gen;
+  int live = 0;
+  for (State *c : g.cluster) live += c->live;
+  g.cl_count++;
+  if (g.cl_count >= live) {
+    g.cl_count = 0;
+    g.cl_gen++;
+    g.progress++;
+  }
+}
+inline void cluster_wait() {
+  State &st = S();
+  st.cur->wait_kind = 4;
+  while (G().cl_gen == st.cur->cluster_gen) yield_to_sched();
+  st.cur->wait_kind = 0;
+}
+inline unsigned cluster_ctarank() { return S().cta_rank; }
+inline unsigned cluster_nctarank() { return (unsigned)G().cluster.size(); }
 
 // all live lanes of the warp publish `bytes` of data, then read lane `src`
 // (two warp-wide barriers per exchange: publish, then consume).
@@ -171,66 +213,111 @@ inline void warp_exchange(const void *mine, void *out, int bytes, int src_lane) 
   warp_barrier(w, w.departed, w.gen2);
 }
 
+inline unsigned char *dyn_smem_of(State &st) {
+  uintptr_t p = (uintptr_t)st.smem.data();
+  p = (p + 1023) & ~(uintptr_t)1023;   // PSFMC_DYN_SMEM asks for 1024-byte alignment
+  return (unsigned char *)p;
+}
+inline unsigned char *dyn_smem() { return dyn_smem_of(S()); }
+
+// mapa: the address of the same dynamic-shared-memory location in CTA `rank` of the
+// cluster (static __shared__ variables are plain statics here, shared by all CTAs:
+// cluster kernels must keep everything in dynamic shared memory)
+inline uintptr_t map_shared_rank(uintptr_t addr, unsigned rank) {
+  Global &g = G();
+  return addr - (uintptr_t)dyn_smem_of(S()) + (uintptr_t)dyn_smem_of(*g.cluster[rank]);
+}
+
+inline State *pooled_state(size_t k) {
+  static std::vector<State *> pool;
+  while (pool.size() <= k) pool.push_back(new State());
+  return pool[k];
+}
+
 template <typename F>
-void launch(dim3 grid, dim3 block, size_t smem_bytes, F &&body) {
-  State &st = S();
-  st.grid = grid;
-  st.block = block;
-  st.body = body;
-  int nthreads = block.x * block.y * block.z;
-  st.smem.assign(smem_bytes + 2048, 0);
-  if ((int)st.fibers.size() < nthreads) st.fibers.resize(nthreads);
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F &&body, unsigned cluster_x = 1) {
+  Global &g = G();
+  g.body = body;
+  const int nthreads = block.x * block.y * block.z;
+  if (cluster_x < 1 || grid.x % cluster_x) {
+    std::fprintf(stderr, "cuda_emu: grid.x is not a multiple of the cluster size\n");
+    std::abort();
+  }
+  g.cluster.clear();
+  for (unsigned k = 0; k < cluster_x; ++k) g.cluster.push_back(pooled_state(k));
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        st.bid = uint3{bx, by, bz};
-        st.live = nthreads;
-        st.bar_count = 0;
-        st.named.clear();
-        st.warps.assign((nthreads + 31) / 32, State::Warp());
-        // poison shared memory so that reads of unwritten smem show up as NaNs
-        std::memset(st.smem.data(), 0xFF, st.smem.size());
-        for (int t = 0; t < nthreads; ++t) {
-          Fiber &f = st.fibers[t];
-          if (f.stack.empty()) f.stack.resize(256 * 1024);
-          f.done = false;
-          f.wait_kind = 0;
-          f.linear = t;
-          f.tid = uint3{(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y),
-                        (unsigned)(t / (block.x * block.y))};
-          st.warps[t / 32].live++;
-          getcontext(&f.ctx);
-          f.ctx.uc_stack.ss_sp = f.stack.data();
-          f.ctx.uc_stack.ss_size = f.stack.size();
-          f.ctx.uc_link = &st.sched;
-          makecontext(&f.ctx, (void (*)())fiber_entry, 0);
-        }
-        int idle_rounds = 0;
-        while (st.live > 0) {
-          unsigned long long before = st.progress;
+      for (unsigned bx0 = 0; bx0 < grid.x; bx0 += cluster_x) {
+        g.cl_count = 0;
+        for (unsigned k = 0; k < cluster_x; ++k) {
+          State &st = *g.cluster[k];
+          st.grid = grid;
+          st.block = block;
+          st.bid = uint3{bx0 + k, by, bz};
+          st.cta_rank = k;
+          st.live = nthreads;
+          st.bar_count = 0;
+          st.named.clear();
+          st.warps.assign((nthreads + 31) / 32, State::Warp());
+          // poison shared memory so that reads of unwritten smem show up as NaNs
+          st.smem.assign(smem_bytes + 2048, 0xFF);
+          if ((int)st.fibers.size() < nthreads) st.fibers.resize(nthreads);
           for (int t = 0; t < nthreads; ++t) {
             Fiber &f = st.fibers[t];
-            if (f.done) continue;
-            st.cur = &f;
-            swapcontext(&st.sched, &f.ctx);
+            if (!f.stack) {
+              void *mem = mmap(nullptr, kStackBytes, PROT_READ | PROT_WRITE,
+                               MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+              if (mem == MAP_FAILED) {
+                std::fprintf(stderr, "cuda_emu: cannot map a fiber stack\n");
+                std::abort();
+              }
+              f.stack = (unsigned char *)mem;
+            }
+            f.done = false;
+            f.wait_kind = 0;
+            f.linear = t;
+            f.tid = uint3{(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y),
+                          (unsigned)(t / (block.x * block.y))};
+            st.warps[t / 32].live++;
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack;
+            f.ctx.uc_stack.ss_size = kStackBytes;
+            f.ctx.uc_link = &g.sched;
+            makecontext(&f.ctx, (void (*)())fiber_entry, 0);
           }
-          bool progress = st.progress != before;
+        }
+        int idle_rounds = 0;
+        for (;;) {
+          int live = 0;
+          for (State *c : g.cluster) live += c->live;
+          if (live <= 0) break;
+          unsigned long long before = g.progress;
+          for (State *c : g.cluster) {
+            for (int t = 0; t < nthreads; ++t) {
+              Fiber &f = c->fibers[t];
+              if (f.done) continue;
+              g.cur = c;
+              c->cur = &f;
+              swapcontext(&g.sched, &f.ctx);
+            }
+          }
+          bool progress = g.progress != before;
           idle_rounds = progress ? 0 : idle_rounds + 1;
           if (idle_rounds > 4) {
+            int kinds[5] = {0, 0, 0, 0, 0};
+            for (State *c : g.cluster)
+              for (int t = 0; t < nthreads; ++t)
+                if (!c->fibers[t].done) kinds[c->fibers[t].wait_kind]++;
             std::fprintf(stderr,
-                         "cuda_emu: DEADLOCK in block (%u,%u,%u): %d threads alive, "
-                         "%d at __syncthreads -- divergent barrier or shuffle\n",
-                         bx, by, bz, st.live, st.bar_count);
+                         "cuda_emu: DEADLOCK in block (%u,%u,%u) (cluster of %u): %d threads "
+                         "alive; waiting at __syncthreads %d, warp %d, named %d, cluster %d "
+                         "-- divergent barrier or shuffle\n",
+                         bx0, by, bz, cluster_x, live, kinds[1], kinds[2], kinds[3], kinds[4]);
             std::abort();
           }
         }
       }
-}
-
-inline unsigned char *dyn_smem() {
-  uintptr_t p = (uintptr_t)S().smem.data();
-  p = (p + 1023) & ~(uintptr_t)1023;   // PSFMC_DYN_SMEM asks for 1024-byte alignment
-  return (unsigned char *)p;
+  g.cur = g.cluster[0];
 }
 
 }  // namespace emu

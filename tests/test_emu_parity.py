@@ -8,7 +8,7 @@ it says nothing about speed. The product library is never built this way.
 import numpy as np
 import pytest
 
-from conftest import (assert_lnl_close, check_fp64_rescue, mixed_model_128, fp32_bounds, load_golden, model_from_file,
+from conftest import (assert_lnl_close, check_fp64_rescue, check_near_centre_walkers, mixed_model_128, fp32_bounds, load_golden, model_from_file,
                       oracle_from_model)
 
 
@@ -244,3 +244,7 @@ def test_emu_mixed_components_fused_and_fp64(emu_library):
 
 def test_emu_fp64_rescue_of_high_dynamic_range_walkers(emu_library, c1_golden):
     check_fp64_rescue(emu_library, c1_golden)
+
+
+def test_emu_fused_near_centre_walkers(emu_library):
+    check_near_centre_walkers(emu_library)

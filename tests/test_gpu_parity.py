@@ -358,3 +358,9 @@ def test_gpu_mixed_components_fused_and_fp64(cuda_library):
 def test_gpu_fp64_rescue_of_high_dynamic_range_walkers(cuda_library, c1_golden):
     from conftest import check_fp64_rescue
     check_fp64_rescue(cuda_library, c1_golden)
+
+
+@pytest.mark.gpu
+def test_gpu_fused_near_centre_walkers(cuda_library):
+    from conftest import check_near_centre_walkers
+    check_near_centre_walkers(cuda_library)
