@@ -138,8 +138,10 @@ __device__ __forceinline__ smem_addr_t smem_base(unsigned char *ptr) {
 #endif
 }
 
-// Raw model at the 16 pixels x = l + 8*j of row y -> packed z = raw + i*wsc*raw^2.
+// Raw model at the 16 pixels x = l + XS*j of row y -> packed z = raw + i*wsc*raw^2
+// (XS = 8: 128-wide rows, XS = 16: 256-wide rows of the cluster kernel).
 // Pixels are rendered in pairs (j, j+1) with element-wise pair arithmetic.
+template <int XS>
 __device__ __forceinline__ void fused_render16(const FusedParams &P, long long b, int y,
                                                int l, float wsc, cplx<float> *v) {
   cplx<float> acc[8];
@@ -168,7 +170,8 @@ __device__ __forceinline__ void fused_render16(const FusedParams &P, long long b
       const cplx<float> dxi = bcast((float)l - s.xi), nxf = bcast(-s.xf);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const cplx<float> dx = (dxi + mk<float>((float)(16 * i), (float)(16 * i + 8))) + nxf;
+        const cplx<float> dx =
+            (dxi + mk<float>((float)(2 * XS * i), (float)(2 * XS * i + XS))) + nxf;
         acc[i] = acc[i] + sersic_pair_f32(s, dx, cu, cv, dy2);
       }
     } else {  // point source: at most 7 x 7 pixels of the frame, float64 taps
@@ -178,9 +181,9 @@ __device__ __forceinline__ void fused_render16(const FusedParams &P, long long b
         const int xmin = (int)__ldg(d + D_PS_XMIN), xmax = (int)__ldg(d + D_PS_XMAX);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int x = l + 16 * i;
+          const int x = l + 2 * XS * i;
           if (x >= xmin && x <= xmax) acc[i].x += (float)point_pixel(d, x, y);
-          if (x + 8 >= xmin && x + 8 <= xmax) acc[i].y += (float)point_pixel(d, x + 8, y);
+          if (x + XS >= xmin && x + XS <= xmax) acc[i].y += (float)point_pixel(d, x + XS, y);
         }
       }
     }
@@ -233,7 +236,7 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
   const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
   {
     cplx<float> v[16];
-    fused_render16(P, b, y, R.l, wsc, v);
+    fused_render16<8>(P, b, y, R.l, wsc, v);
     dft16<false>(v);
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * lds64(twl + 64 * k1);

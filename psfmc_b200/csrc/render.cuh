@@ -37,10 +37,14 @@ __device__ __forceinline__ float fast_rcp(float x) {
 #endif
 
 // Per-walker Sersic constants of the float32 path, derived from the float64 ones:
-//   value = 2^(c0 - c1 * t) * (1 + kq * t^2 / |d|^2),  t = sq^p = 2^(p * log2 sq)
+//   value = 2^(c0 - c1 * t) * (1 + (kq * t)^2 / |d|^2),  t = sq^p = 2^(p * log2 sq)
 // which is Sersic.py:124-133 with sbeff*exp(kappa) folded into c0 and
 // normed_grad * cent_offset = (2 p kappa)^2 / 12 * t^2 / |d|^2 (algebraically
-// identical to the reference's g * (sq_delta_r / 12 * g)).
+// identical to the reference's g * (sq_delta_r / 12 * g)); kq = 2 p kappa / sqrt(12).
+// Range: for a very small index (n ~ 0.006: p = 86, kappa ~ 1e-26) the profile only
+// decays where t ~ 1/kappa, so t must keep float32's whole range (clamped at 1e38
+// against inf * 0); kq * t is clamped at 1e18 so that its square stays finite -- the
+// profile is exactly 0 long before (c1 * t = 5 n * kq * t).
 struct SersicF32 {
   float xi, xf, yi, yf;  // centre split into integer + fraction (keeps dx exact)
   float a00, a01, a10, a11;
@@ -63,7 +67,7 @@ __device__ __forceinline__ SersicF32 make_sersic_f32(const double *d) {
   s.p = (float)p;
   s.c1 = (float)(kappa * log2e);
   s.c0 = (float)(log2(d[D_SER_SBEFF]) + kappa * log2e);
-  s.kq = (float)((2.0 * p * kappa) * (2.0 * p * kappa) / 12.0);
+  s.kq = (float)(2.0 * p * kappa * 0.28867513459481288225);   // / sqrt(12)
   return s;
 }
 
@@ -73,11 +77,10 @@ __device__ __forceinline__ float sersic_pixel_f32(const SersicF32 &s, float x, f
   float v = s.a10 * dx + s.a11 * dy;
   float sq = u * u + v * v;
   float r2 = dx * dx + dy * dy;
-  // t is clamped so that t*t stays finite in float32 for very small Sersic
-  // indices (p = 0.5/n large): beyond the clamp the profile is exactly 0 anyway
-  float t = fminf(fast_ex2(s.p * fast_lg2(sq)), 1.0e18f);
+  float t = fminf(fast_ex2(s.p * fast_lg2(sq)), 1.0e38f);
   float sb = fast_ex2(s.c0 - s.c1 * t);
-  return sb * (1.0f + s.kq * (t * t) * fast_rcp(r2));
+  float g = fminf(s.kq * t, 1.0e18f);
+  return sb * (1.0f + (g * g) * fast_rcp(r2));
 }
 
 // One G-lane GROUP per (walker, component): theta -> derived constants, float64.
@@ -327,10 +330,12 @@ __device__ __forceinline__ cplx<float> sersic_pair_f32(const SersicF32 &s, cplx<
   const cplx<float> sq = pfma(v, v, pmul(u, u));
   const cplx<float> r2 = pfma(dx, dx, bcast(dy2));
   const cplx<float> e = pmul(bcast(s.p), mk<float>(fast_lg2(sq.x), fast_lg2(sq.y)));
-  const cplx<float> t = mk<float>(fminf(fast_ex2(e.x), 1.0e18f), fminf(fast_ex2(e.y), 1.0e18f));
+  const cplx<float> t = mk<float>(fminf(fast_ex2(e.x), 1.0e38f), fminf(fast_ex2(e.y), 1.0e38f));
   const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0));
   const cplx<float> sb = mk<float>(fast_ex2(arg.x), fast_ex2(arg.y));
-  const cplx<float> q = pmul(pmul(bcast(s.kq), pmul(t, t)), rcp_pair_fma(r2));
+  const cplx<float> gu = pmul(bcast(s.kq), t);
+  const cplx<float> g = mk<float>(fminf(gu.x, 1.0e18f), fminf(gu.y, 1.0e18f));
+  const cplx<float> q = pmul(pmul(g, g), rcp_pair_fma(r2));
   return pfma(sb, q, sb);    // sb * (1 + q)
 }
 
@@ -342,10 +347,12 @@ __device__ __forceinline__ cplx<float> sersic_pair2_f32(const SersicF32 &s, cplx
   const cplx<float> sq = pfma(v, v, pmul(u, u));
   const cplx<float> r2 = pfma(dx, dx, pmul(dy, dy));
   const cplx<float> e = pmul(bcast(s.p), mk<float>(fast_lg2(sq.x), fast_lg2(sq.y)));
-  const cplx<float> t = mk<float>(fminf(fast_ex2(e.x), 1.0e18f), fminf(fast_ex2(e.y), 1.0e18f));
+  const cplx<float> t = mk<float>(fminf(fast_ex2(e.x), 1.0e38f), fminf(fast_ex2(e.y), 1.0e38f));
   const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0));
   const cplx<float> sb = mk<float>(fast_ex2(arg.x), fast_ex2(arg.y));
-  const cplx<float> q = pmul(pmul(bcast(s.kq), pmul(t, t)), rcp_pair_fma(r2));
+  const cplx<float> gu = pmul(bcast(s.kq), t);
+  const cplx<float> g = mk<float>(fminf(gu.x, 1.0e18f), fminf(gu.y, 1.0e18f));
+  const cplx<float> q = pmul(pmul(g, g), rcp_pair_fma(r2));
   return pfma(sb, q, sb);    // sb * (1 + q)
 }
 
