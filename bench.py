@@ -376,7 +376,8 @@ def run_ours(args):
             'achieved': round(achieved, 3), 'peak': round(peak_probe, 2),
             'unit': 'TFLOP/s', 'frac': round(achieved / peak_probe, 4),
             'traffic': traffic,
-            'kernel': 'fused_lnlike_kernel' if fused else 'rows_fwd + cols + rows_inv',
+            'kernel': {1: 'fused_lnlike_kernel', 2: 'cluster256_lnlike_kernel'}.get(
+                info['path'], 'rows_fwd + cols + rows_inv'),
             'kernel_us_per_launch': round(kernel_us, 2),
             'kernel_launches_timed': int(kernel_launches),
             'evals_per_launch': evals_per_launch,
@@ -396,7 +397,7 @@ def run_ours(args):
                     'peak': hbm_peak, 'unit': 'GB/s',
                     'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
                     'bytes_per_eval': info['hbm_bytes_per_eval']},
-            'engine_path': 'fused' if fused else 'staged',
+            'engine_path': {1: 'fused', 2: 'fused-cluster4'}.get(info['path'], 'staged'),
         }
         result = {
             'metric': METRIC, 'value': round(value, 1), 'unit': UNIT,

@@ -171,7 +171,9 @@ typedef struct psfmc_info {
   int32_t height, width, n_components, n_sersic, n_point, n_psf, precision;
   int32_t n_devices;
   int32_t path;             /* 0 = staged row/column passes through L2/HBM,
-                               1 = fused single-kernel shared-memory path          */
+                               1 = fused single-kernel shared-memory path (128 x 128),
+                               2 = fused four-CTA-cluster path, frame split over the
+                                   shared memory of four SMs (256 x 256)            */
   int32_t kernels_per_call; /* kernels launched per lnlike call per device        */
   double flops_per_eval;    /* 10 N log2 N + (30 n_sersic + 16) N     */
   double fft_flops_per_eval;   /* 10 N log2 N                                     */

@@ -17,6 +17,7 @@
 #include "pipeline.cuh"
 #ifndef PSFMC_NO_FUSED
 #include "kernels_fused.cuh"
+#include "kernels_cluster.cuh"
 #endif
 
 using namespace psfmc;
@@ -104,6 +105,9 @@ struct DeviceState {
   DevBuf<float> rconst;
   cplx<float> *fspec = nullptr, *fspecx = nullptr;
   float2 *fow = nullptr;
+  float4 *cspec = nullptr, *cspecx = nullptr;   // cluster kernel (256 x 256)
+  float2 *ctw = nullptr;
+  int n_clusters = 0;
   int n_sms = 148;
   // optional event pairs around the dominant kernel(s) of every lnL call
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -158,6 +162,9 @@ struct Engine : EngineBase {
       cudaFree(d.fspec);
       cudaFree(d.fspecx);
       cudaFree(d.fow);
+      cudaFree(d.cspec);
+      cudaFree(d.cspecx);
+      cudaFree(d.ctw);
       d.rconst.release();
       d.wscale.release();
       d.derived.release();
@@ -238,7 +245,7 @@ struct Engine : EngineBase {
     if (d.derived.ensure(nb * ncomp * PSFMC_DERIVED_STRIDE) || d.psf_sel.ensure(nb) ||
         d.wscale.ensure(nb))
       return fail(PSFMC_ERR_CUDA, "device allocation failed while sizing the batch buffers");
-    if (path == 1 && !for_images) {
+    if (path >= 1 && !for_images) {
       if (d.rconst.ensure(nb * ncomp * PSFMC_RC_STRIDE))
         return fail(PSFMC_ERR_CUDA, "device allocation failed (render constants)");
       return 0;
@@ -269,6 +276,21 @@ struct Engine : EngineBase {
       if (profiling && (rc = prof_pair(d, &e0, &e1))) return rc;
       launches += launch_fused_lnlike<T>(plan, buf, fb, prog_h, theta_dev, B, ld, lnl_dev,
                                          stream, e0, e1);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
+    if (path == 2) {
+      ClusterBuffers cb;
+      cb.rconst = d.rconst.ptr;
+      cb.spec4 = d.cspec;
+      cb.specx4 = d.cspecx;
+      cb.ow = d.fow;
+      cb.tw = d.ctw;
+      cb.n_clusters = d.n_clusters;
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (profiling && (rc = prof_pair(d, &e0, &e1))) return rc;
+      launches += launch_cluster_lnlike<T>(plan, buf, cb, prog_h, theta_dev, B, ld, lnl_dev,
+                                           stream, e0, e1);
       CUDA_TRY(cudaGetLastError());
       return 0;
     }
@@ -787,6 +809,7 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
 #ifndef PSFMC_NO_FUSED
     if (i == 0) {
       eng->path = fused_path_available<T>(eng->plan, eng->prog_h) ? 1 : 0;
+      if (cluster_path_available<T>(eng->plan)) eng->path = 2;
       const char *force = getenv("PSFMC_FORCE_STAGED");
       if (force && force[0] == '1') eng->path = 0;
       const char *variant = getenv("PSFMC_FUSED_VARIANT");
@@ -816,6 +839,33 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       }
       if ((rc = upload(&ds.fspec, fspec)) || (rc = upload(&ds.fspecx, fspecx)) ||
           (rc = upload(&ds.fow, ow)))
+        break;
+    }
+    if (eng->path == 2) {
+      if (cluster_prepare_device(&ds.n_clusters)) {
+        rc = fail(PSFMC_ERR_CUDA, "cannot reserve shared memory / clusters for the 256 x 256 "
+                                  "cluster kernel");
+        break;
+      }
+      if (const char *env = getenv("PSFMC_FUSED_CTAS")) {   // tests: force walker loops
+        int v = atoi(env);
+        if (v > 0 && v < ds.n_clusters) ds.n_clusters = v;
+      }
+      const size_t N = PSFMC_CL_N;
+      std::vector<float4> cspec((size_t)d->n_psf * PSFMC_CL_CTAS * N * 32),
+          cspecx((size_t)d->n_psf * 2 * N);
+      std::vector<double> vs(d->n_psf);
+      for (int k = 0; k < d->n_psf; ++k) vs[k] = 1.0 / vscale_inv[k];
+      cluster_spectrum_layout(spec64.data(), d->n_psf, vs.data(), cspec.data(), cspecx.data());
+      std::vector<float2> ow(npx), ctw(256);
+      for (size_t e = 0; e < npx; ++e) {
+        float v = fabsf((float)d->obs_var[e]);
+        ow[e].x = (float)d->obs_data[e];
+        ow[e].y = bad[e] ? -v : v;
+      }
+      cluster_twiddles(ctw.data());
+      if ((rc = upload(&ds.cspec, cspec)) || (rc = upload(&ds.cspecx, cspecx)) ||
+          (rc = upload(&ds.fow, ow)) || (rc = upload(&ds.ctw, ctw)))
         break;
     }
 #endif
@@ -1039,11 +1089,11 @@ int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info) {
   // fused path: theta in, render constants out+in, lnL out; spectra and observation
   // (2 x 128 KB) are shared by all walkers and stay in L2
   info->hbm_bytes_per_eval =
-      e->path == 1 ? (double)(8 * 32 + 8 + e->prog_h.n_components *
+      e->path >= 1 ? (double)(8 * 32 + 8 + e->prog_h.n_components *
                                                (2 * 4 * PSFMC_RC_STRIDE +
                                                 2 * 8 * PSFMC_DERIVED_STRIDE))
                    : 4.0 * (double)e->plan.scratch_elems_per_walker * csz;
-  info->kernels_per_call = e->path == 1 ? 2 : 5;
+  info->kernels_per_call = e->path >= 1 ? 2 : 5;
   info->launches_total = e->launches;
   info->kappa_table = e->kappa_table ? 1 : 0;
   info->rescued_total =

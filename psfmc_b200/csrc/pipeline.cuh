@@ -22,6 +22,30 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
 #endif
 }
 
+// Launch with a thread-block cluster of `cluster` CTAs along x.
+template <typename... KArgs, typename... Args>
+inline void launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                  cudaStream_t stream, unsigned cluster, Args &&...args) {
+#ifdef PSFMC_EMU
+  (void)stream;
+  emu::launch(grid, block, smem, [&] { kernel(args...); }, cluster);
+#else
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+#endif
+}
+
 inline int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;

@@ -25,6 +25,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __grid_constant__
+#define __cluster_dims__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 #define __constant__ static

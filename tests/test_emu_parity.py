@@ -8,7 +8,8 @@ it says nothing about speed. The product library is never built this way.
 import numpy as np
 import pytest
 
-from conftest import (assert_lnl_close, check_fp64_rescue, check_near_centre_walkers, mixed_model_128, fp32_bounds, load_golden, model_from_file,
+from conftest import (assert_lnl_close, check_cluster_path_256, check_fp64_rescue,
+                      check_near_centre_walkers, mixed_model_128, fp32_bounds, load_golden, model_from_file,
                       oracle_from_model)
 
 
@@ -248,3 +249,9 @@ def test_emu_fp64_rescue_of_high_dynamic_range_walkers(emu_library, c1_golden):
 
 def test_emu_fused_near_centre_walkers(emu_library):
     check_near_centre_walkers(emu_library)
+
+
+def test_emu_cluster_kernel_256(emu_library, monkeypatch):
+    """256 x 256 frame split over a four-CTA cluster (distributed shared memory,
+    barrier.cluster emulated): two clusters walking over five walkers."""
+    check_cluster_path_256(emu_library, 5, monkeypatch)

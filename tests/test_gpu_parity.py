@@ -364,3 +364,27 @@ def test_gpu_fp64_rescue_of_high_dynamic_range_walkers(cuda_library, c1_golden):
 def test_gpu_fused_near_centre_walkers(cuda_library):
     from conftest import check_near_centre_walkers
     check_near_centre_walkers(cuda_library)
+
+
+@pytest.mark.gpu
+def test_gpu_cluster_kernel_256(cuda_library, monkeypatch):
+    from conftest import check_cluster_path_256
+    check_cluster_path_256(cuda_library, 300, monkeypatch)
+
+
+@pytest.mark.gpu
+def test_gpu_cluster_kernel_256_properties(cuda_library):
+    """Full C3 ensemble through the cluster kernel: determinism, permutation
+    equivariance, batch-composition independence."""
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.synthetic import draw_walkers_fast, synthetic_components
+    model = MultiComponentModel(synthetic_components(256, 2), precision='fp32',
+                                fp64_rescue=False)
+    assert model.engine.info()['path'] == 2
+    thetas = draw_walkers_fast(model, 1024, seed=3)
+    first = model.log_likelihood_batch(thetas)
+    assert np.array_equal(first, model.log_likelihood_batch(thetas))
+    perm = np.random.RandomState(0).permutation(len(thetas))
+    assert np.array_equal(model.log_likelihood_batch(thetas[perm]), first[perm])
+    assert np.array_equal(model.log_likelihood_batch(thetas[:37]), first[:37])
+    assert np.all(np.isfinite(first))

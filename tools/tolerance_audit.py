@@ -41,7 +41,8 @@ def main():
                     'rescued_in_fp64': int(m32.engine.info()['rescued_total']),
                     'raw_fp32_nonfinite_where_fp64_finite':
                         int(np.sum(finite & ~np.isfinite(raw))),
-                    'engine_path': 'fused' if m32.engine.info()['path'] == 1 else 'staged',
+                    'engine_path': {1: 'fused', 2: 'fused-cluster4'}.get(
+                        m32.engine.info()['path'], 'staged'),
                     'max_abs_dlnl': float(err.max()), 'median_abs_dlnl': float(np.median(err)),
                     'max_rel_dlnl': float((err / np.abs(l64[finite])).max()),
                     'bound_checked_on': int(len(rows)),
