@@ -50,7 +50,12 @@ namespace psfmc {
 #define PSFMC_CL_X_OFF PSFMC_CL_TILE_BYTES           // row exchange scratch: 32 rows x 2 KB
 #define PSFMC_CL_TW_OFF (PSFMC_CL_X_OFF + 32 * 2048)  // W256^(j k1) as [k1][j], 2 KB
 #define PSFMC_CL_RED_OFF (PSFMC_CL_TW_OFF + 2048)     // 16 warp partials + 4 CTA partials
-#define PSFMC_CL_SMEM (PSFMC_CL_RED_OFF + 256)
+// per-walker parameters staged one walker ahead: header (PSF index, packing scale),
+// float32 render constants, float64 constants (point-source taps)
+#define PSFMC_CL_PAR_OFF (PSFMC_CL_RED_OFF + 256)
+#define PSFMC_CL_PAR_RC (PSFMC_CL_PAR_OFF + 64)
+#define PSFMC_CL_PAR_DER (PSFMC_CL_PAR_RC + PSFMC_MAX_COMPONENTS * PSFMC_RC_STRIDE * 4)
+#define PSFMC_CL_SMEM (PSFMC_CL_PAR_DER + PSFMC_MAX_COMPONENTS * PSFMC_DERIVED_STRIDE * 8)
 
 struct ClusterParams {
   FusedParams f;          // render constants, observation, outputs (spec/specx unused)
@@ -156,12 +161,29 @@ __device__ __forceinline__ smem_addr_t cl_row_addr(const smem_addr_t *ra, const 
   return l0 ? rm[((m + 1) >> 1) & 3] + 8 * 32 : rm[m >> 1] + 8 * 64;
 }
 
+// owner CTA of element kx = l + 16 k2
+template <int K2>
+__device__ __forceinline__ int cl_row_owner(bool l0) {
+  if (K2 < 8) return K2 >> 1;
+  constexpr int m = 15 - K2;
+  if ((m & 1) == 0) return m >> 1;
+  return l0 ? (((m + 1) >> 1) & 3) : (m >> 1);
+}
+
+// push: ra / rm are addresses in the OWNERS' tiles (mapa); the quarter that stays in
+// this CTA (rank) goes through the ordinary shared-memory path (own_delta = mapped -
+// local address of this CTA's tile), the rest through st.shared::cluster
 template <int K2>
 struct ClRowLoop {
   static __device__ __forceinline__ void push(const smem_addr_t *ra, const smem_addr_t *rm,
-                                              bool l0, const cplx<float> *u) {
-    sts64_cluster(cl_row_addr<K2>(ra, rm, l0), u[K2]);
-    ClRowLoop<K2 + 1>::push(ra, rm, l0, u);
+                                              bool l0, int rank, smem_addr_t own_delta,
+                                              const cplx<float> *u) {
+    const smem_addr_t addr = cl_row_addr<K2>(ra, rm, l0);
+    if (cl_row_owner<K2>(l0) == rank)
+      sts64(addr - own_delta, u[K2]);
+    else
+      sts64_cluster(addr, u[K2]);
+    ClRowLoop<K2 + 1>::push(ra, rm, l0, rank, own_delta, u);
   }
   static __device__ __forceinline__ void gather(const smem_addr_t *ra, const smem_addr_t *rm,
                                                 bool l0, cplx<float> *u) {
@@ -172,18 +194,18 @@ struct ClRowLoop {
 template <>
 struct ClRowLoop<16> {
   static __device__ __forceinline__ void push(const smem_addr_t *, const smem_addr_t *, bool,
-                                              const cplx<float> *) {}
+                                              int, smem_addr_t, const cplx<float> *) {}
   static __device__ __forceinline__ void gather(const smem_addr_t *, const smem_addr_t *, bool,
                                                 cplx<float> *) {}
 };
 
 // render + forward row transform of row batch `it` of walker b; u[k2] = Z[y][l + 16 k2]
 __device__ __forceinline__ void cl_rows_forward(const FusedParams &P, const ClRowRole &R,
-                                                long long b, int y, float wsc,
-                                                cplx<float> *u) {
+                                                const float *rc_s, const double *der_s, int y,
+                                                float wsc, cplx<float> *u) {
   {
     cplx<float> v[16];
-    fused_render16<16>(P, b, y, R.l, wsc, v);
+    fused_render16<16, true>(P, rc_s, der_s, y, R.l, wsc, v);
     dft16<false>(v);
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * lds64(R.twl + 128 * k1);
@@ -245,10 +267,28 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
     const float2 t = CP.tw[tid];
     sts64(twb + 8u * tid, mk<float>(t.x, t.y));
   }
+  // staged parameters of the walker the next forward pass renders
+  int *par_sel = reinterpret_cast<int *>(smem_raw + PSFMC_CL_PAR_OFF);
+  double *par_wsc = reinterpret_cast<double *>(smem_raw + PSFMC_CL_PAR_OFF + 8);
+  float *rc_s = reinterpret_cast<float *>(smem_raw + PSFMC_CL_PAR_RC);
+  double *der_s = reinterpret_cast<double *>(smem_raw + PSFMC_CL_PAR_DER);
+  auto stage_params = [&](long long bs) {
+    if (bs >= P.n_batch) return;
+    if (tid < P.ncomp * PSFMC_RC_STRIDE)
+      rc_s[tid] = __ldg(P.rconst + bs * P.ncomp * PSFMC_RC_STRIDE + tid);
+    for (int k = tid; k < P.ncomp * PSFMC_DERIVED_STRIDE; k += PSFMC_CL_THREADS)
+      der_s[k] = __ldg(P.derived + bs * P.ncomp * PSFMC_DERIVED_STRIDE + k);
+    if (tid == PSFMC_CL_THREADS - 1) {
+      *par_sel = P.psf_sel[bs];
+      *par_wsc = P.wscale[bs];
+    }
+  };
+  stage_params(cluster_id);
   // this CTA's tile as seen by each CTA of the cluster (index = owner rank)
   smem_addr_t mb[PSFMC_CL_CTAS];
 #pragma unroll
   for (int q = 0; q < PSFMC_CL_CTAS; ++q) mb[q] = cl_map(tile, q);
+  const smem_addr_t own_delta = cl_map(tile, rank) - tile;
   const smem_addr_t red0 = cl_map(tile + PSFMC_CL_RED_OFF + 8 * 16, 0);   // CTA 0's [4]
 
   ClRowRole R;
@@ -279,13 +319,29 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
   const bool rule0 = (k1A == 0) && !special;   // partner of a[k2] is b[(16 - k2) & 15]
   const bool special0 = special && (j8 == 0);  // pairs inside a and inside b
 
-  bool first = true;
+  // The last cluster barrier of a walker (all inverse rows done, CTA partials delivered
+  // to CTA 0) is only ARRIVED at; the wait is taken after the next walker's render and
+  // forward transform, right before its first push -- `pending` is the walker whose
+  // lnL CTA 0 still has to assemble then.
+  long long pending = -1;
+  bool pending_invalid = false;
+  auto finish_pending = [&]() {
+    cl_wait();
+    if (rank == 0 && tid == 0) {
+      double tot = 0.0;
+      for (int k = 0; k < PSFMC_CL_CTAS; ++k) tot += red_s[16 + k];
+      double val = -0.5 * tot;
+      if (!isfinite(val) || pending_invalid) val = -INFINITY;
+      P.lnl[pending] = val;
+    }
+    pending = -1;
+  };
 #pragma unroll 1
   for (long long b = cluster_id; b < P.n_batch; b += n_clusters) {
-    int sel = P.psf_sel[b];
+    int sel = *par_sel;
     const bool invalid = sel < 0;
     if (invalid) sel = 0;
-    const double wscale_b = P.wscale[b];
+    const double wscale_b = *par_wsc;
     const float unscale = (float)(P.vscale_inv[sel] / wscale_b);
 
     // ------------------------------------------ rows: render + forward + push --
@@ -294,8 +350,9 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
       const int yl = yl0 + 32 * it;
       const int y = 64 * (int)rank + yl;
       cplx<float> u[16];
-      cl_rows_forward(P, R, b, y, (float)wscale_b, u);
-      if (it == 0 && !first) cl_wait();   // the other CTAs are done with the last walker's rows
+      cl_rows_forward(P, R, rc_s, der_s, y, (float)wscale_b, u);
+      if (it == 0 && pending >= 0) finish_pending();   // the other CTAs are done with
+                                                       // the last walker's rows
       smem_addr_t ra[PSFMC_CL_CTAS], rm[PSFMC_CL_CTAS];
 #pragma unroll
       for (int q = 0; q < PSFMC_CL_CTAS; ++q) {
@@ -303,11 +360,25 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
         ra[q] = rowb + R.lx;
         rm[q] = rowb - R.lx;
       }
-      ClRowLoop<0>::push(ra, rm, R.l0, u);
+      ClRowLoop<0>::push(ra, rm, R.l0, (int)rank, own_delta, u);
     }
-    first = false;
     cl_arrive();
     cl_wait();
+    // every thread of the CTA is past its forward rows: stage the next walker's
+    // parameters (read again after the CTA barrier of this walker's reduction)
+    stage_params(b + n_clusters);
+
+    // spectra of unit A of the multiply pass at ky = k1A + 16 k2 (of unit B for the
+    // second half of special0)
+    const float4 *sp;
+    int sstride;
+    if (special) {
+      sp = CP.specx4 + ((size_t)sel * 2 + (w < 8 ? 0 : 1)) * 256 + k1A;
+      sstride = 16;
+    } else {
+      sp = CP.spec4 + (((size_t)sel * PSFMC_CL_CTAS + rank) * 256 + k1A) * 32 + lane;
+      sstride = 16 * 32;
+    }
 
     // ------------------------------------------------- columns: radix-16 (n1) --
 #pragma unroll
@@ -322,6 +393,10 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
 #pragma unroll
       for (int k1 = 0; k1 < 16; ++k1) sts64(base + 8192 * k1, v[k1]);
     }
+    // first half of the spectrum values: their L2 latency overlaps the CTA barrier
+    float4 f[8];
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) f[k2] = ldg128(sp + k2 * sstride);
     __syncthreads();
 
     // -------------- columns: radix-16 (n2), spectrum multiply, inverse radix-16 --
@@ -333,16 +408,6 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
       for (int n2 = 0; n2 < 16; ++n2) {
         a[n2] = lds64(baseA + 512 * n2);
         bb[n2] = lds64(baseB + 512 * n2);
-      }
-      // spectra of unit A at ky = k1A + 16 k2 (of unit B for the second half of special0)
-      const float4 *sp;
-      int sstride;
-      if (special) {
-        sp = CP.specx4 + ((size_t)sel * 2 + (w < 8 ? 0 : 1)) * 256 + k1A;
-        sstride = 16;
-      } else {
-        sp = CP.spec4 + (((size_t)sel * PSFMC_CL_CTAS + rank) * 256 + k1A) * 32 + lane;
-        sstride = 16 * 32;
       }
       dft16<false>(a);    // a[k2]  = Z[k1A + 16 k2][colA]
       dft16<false>(bb);   // bb[k2] = Z[k1B + 16 k2][colB]
@@ -356,12 +421,16 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
           cl_pair_mul(bb[k2], bb[15 - k2], ldg128(sp + 8 + k2 * sstride));
       } else if (rule0) {
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2)
-          cl_pair_mul(a[k2], bb[(16 - k2) & 15], ldg128(sp + k2 * sstride));
+        for (int k2 = 0; k2 < 16; ++k2) {
+          cl_pair_mul(a[k2], bb[(16 - k2) & 15], f[k2 & 7]);
+          if (k2 < 8) f[k2] = ldg128(sp + (k2 + 8) * sstride);
+        }
       } else {
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2)
-          cl_pair_mul(a[k2], bb[15 - k2], ldg128(sp + k2 * sstride));
+        for (int k2 = 0; k2 < 16; ++k2) {
+          cl_pair_mul(a[k2], bb[15 - k2], f[k2 & 7]);
+          if (k2 < 8) f[k2] = ldg128(sp + (k2 + 8) * sstride);
+        }
       }
       dft16<true>(a);     // over k2 -> n2
       dft16<true>(bb);
@@ -395,8 +464,13 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
         const smem_addr_t dst = mb[n1 >> 2] + off + 8192 * (n1 & 3);
-        sts64_cluster(dst, v0[n1]);
-        sts64_cluster(dst + 256, v1[n1]);
+        if ((n1 >> 2) == (int)rank) {
+          sts64(dst - own_delta, v0[n1]);
+          sts64(dst - own_delta + 256, v1[n1]);
+        } else {
+          sts64_cluster(dst, v0[n1]);
+          sts64_cluster(dst + 256, v1[n1]);
+        }
       }
     }
     cl_arrive();
@@ -433,22 +507,12 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
       for (int k = 0; k < PSFMC_CL_THREADS / 32; ++k) tot += red_s[k];
       std64_cluster(red0 + 8u * rank, tot);
     }
-    // this CTA is done with its tile (rows) and has delivered its partial; the wait
-    // is taken before the next walker's first push (or below for the last walker)
+    // this CTA is done with its tile (rows) and has delivered its partial
     cl_arrive();
-    const bool last = b + n_clusters >= P.n_batch;
-    if (rank == 0 || last) {
-      cl_wait();
-      first = true;       // the wait of this phase has been consumed
-      if (rank == 0 && tid == 0) {
-        double tot = 0.0;
-        for (int k = 0; k < PSFMC_CL_CTAS; ++k) tot += red_s[16 + k];
-        double val = -0.5 * tot;
-        if (!isfinite(val) || invalid) val = -INFINITY;
-        P.lnl[b] = val;
-      }
-    }
+    pending = b;
+    pending_invalid = invalid;
   }
+  if (pending >= 0) finish_pending();
 }
 
 // -------------------------------------------------------------- host side --

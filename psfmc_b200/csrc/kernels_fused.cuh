@@ -141,24 +141,28 @@ __device__ __forceinline__ smem_addr_t smem_base(unsigned char *ptr) {
 // Raw model at the 16 pixels x = l + XS*j of row y -> packed z = raw + i*wsc*raw^2
 // (XS = 8: 128-wide rows, XS = 16: 256-wide rows of the cluster kernel).
 // Pixels are rendered in pairs (j, j+1) with element-wise pair arithmetic.
-template <int XS>
-__device__ __forceinline__ void fused_render16(const FusedParams &P, long long b, int y,
-                                               int l, float wsc, cplx<float> *v) {
+template <int XS, bool STAGED>
+__device__ __forceinline__ void fused_render16(const FusedParams &P, const float *rc0,
+                                               const double *der0, int y, int l, float wsc,
+                                               cplx<float> *v) {
+  // rc0 / der0: this walker's render constants / float64 constants; STAGED = they were
+  // copied to shared memory beforehand (plain loads), else read-only global loads
   cplx<float> acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = mk<float>(0.0f, 0.0f);
   for (int c = 0; c < P.ncomp; ++c) {
     const int kind = P.kind[c];
-    const float *rc = P.rconst + (b * P.ncomp + c) * PSFMC_RC_STRIDE;
+    const float *rc = rc0 + c * PSFMC_RC_STRIDE;
     if (kind == PSFMC_SKY) {
-      const cplx<float> adu = bcast(__ldg(rc));
+      const cplx<float> adu = bcast(STAGED ? *rc : __ldg(rc));
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = acc[i] + adu;
     } else if (kind == PSFMC_SERSIC) {
       SersicF32 s;
-      const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rc));
-      const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rc) + 1);
-      const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rc) + 2);
+      const float4 *rc4 = reinterpret_cast<const float4 *>(rc);
+      const float4 q0 = STAGED ? rc4[0] : __ldg(rc4);
+      const float4 q1 = STAGED ? rc4[1] : __ldg(rc4 + 1);
+      const float4 q2 = STAGED ? rc4[2] : __ldg(rc4 + 2);
       s.xi = q0.x; s.xf = q0.y; s.yi = q0.z; s.yf = q0.w;
       s.a00 = q1.x; s.a01 = q1.y; s.a10 = q1.z; s.a11 = q1.w;
       s.p = q2.x; s.c0 = q2.y; s.c1 = q2.z; s.kq = q2.w;
@@ -175,10 +179,12 @@ __device__ __forceinline__ void fused_render16(const FusedParams &P, long long b
         acc[i] = acc[i] + sersic_pair_f32(s, dx, cu, cv, dy2);
       }
     } else {  // point source: at most 7 x 7 pixels of the frame, float64 taps
-      const double *d = P.derived + (b * P.ncomp + c) * PSFMC_DERIVED_STRIDE;
-      const int ymin = (int)__ldg(d + D_PS_YMIN), ymax = (int)__ldg(d + D_PS_YMAX);
+      const double *d = der0 + c * PSFMC_DERIVED_STRIDE;
+      const int ymin = (int)(STAGED ? d[D_PS_YMIN] : __ldg(d + D_PS_YMIN));
+      const int ymax = (int)(STAGED ? d[D_PS_YMAX] : __ldg(d + D_PS_YMAX));
       if (y >= ymin && y <= ymax) {
-        const int xmin = (int)__ldg(d + D_PS_XMIN), xmax = (int)__ldg(d + D_PS_XMAX);
+        const int xmin = (int)(STAGED ? d[D_PS_XMIN] : __ldg(d + D_PS_XMIN));
+        const int xmax = (int)(STAGED ? d[D_PS_XMAX] : __ldg(d + D_PS_XMAX));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int x = l + 2 * XS * i;
@@ -236,7 +242,8 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
   const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
   {
     cplx<float> v[16];
-    fused_render16<8>(P, b, y, R.l, wsc, v);
+    fused_render16<8, false>(P, P.rconst + b * P.ncomp * PSFMC_RC_STRIDE,
+                             P.derived + b * P.ncomp * PSFMC_DERIVED_STRIDE, y, R.l, wsc, v);
     dft16<false>(v);
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * lds64(twl + 64 * k1);
