@@ -458,22 +458,35 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
         v1[k1] = cmul_conj(v1[k1], tw);
       }
       dft16<true>(v0);    // v[n1]: row y = w + 16 n1
-      dft16<true>(v1);
       cl_wait();          // every CTA has read its tile: the tiles may be overwritten
       const unsigned off = 512u * (64u * rank + w) + 8u * lane;
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
         const smem_addr_t dst = mb[n1 >> 2] + off + 8192 * (n1 & 3);
-        if ((n1 >> 2) == (int)rank) {
+        if ((n1 >> 2) == (int)rank)
           sts64(dst - own_delta, v0[n1]);
-          sts64(dst - own_delta + 256, v1[n1]);
-        } else {
+        else
           sts64_cluster(dst, v0[n1]);
-          sts64_cluster(dst + 256, v1[n1]);
-        }
+      }
+      dft16<true>(v1);    // overlaps the first unit's stores in flight
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const smem_addr_t dst = mb[n1 >> 2] + off + 256 + 8192 * (n1 & 3);
+        if ((n1 >> 2) == (int)rank)
+          sts64(dst - own_delta, v1[n1]);
+        else
+          sts64_cluster(dst, v1[n1]);
       }
     }
     cl_arrive();
+    // observation + signed variance of the first row batch: their L2 latency overlaps
+    // the cluster barrier
+    float2 o[16];
+    {
+      const float2 *owr = P.ow + (64 * (int)rank + yl0) * PSFMC_CL_N + R.l;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 16 * j);
+    }
     cl_wait();
 
     // ------------------------------------------- rows: inverse + chi-square --
@@ -482,10 +495,11 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
     for (int it = 0; it < 2; ++it) {
       const int yl = yl0 + 32 * it;
       const int y = 64 * (int)rank + yl;
-      float2 o[16];
-      const float2 *owr = P.ow + y * PSFMC_CL_N + R.l;
+      if (it) {
+        const float2 *owr = P.ow + y * PSFMC_CL_N + R.l;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 16 * j);
+        for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 16 * j);
+      }
       smem_addr_t ra[PSFMC_CL_CTAS], rm[PSFMC_CL_CTAS];
 #pragma unroll
       for (int q = 0; q < PSFMC_CL_CTAS; ++q) {
