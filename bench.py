@@ -363,14 +363,19 @@ def run_ours(args):
         evals_per_launch = half
         achieved = info['flops_per_eval'] * evals_per_launch / (kernel_us * 1e-6) / 1e12
         fft_achieved = info['fft_flops_per_eval'] * evals_per_launch / (kernel_us * 1e-6) / 1e12
+        # dram__bytes of one launch of the dominant kernel from the committed ncu capture
+        # of the same workload (profiles/), when there is one
         ncu = {}
-        try:
-            with open(os.path.join(ROOT, 'profiles', 'r1_fused_ncu_summary.json')) as fobj:
-                ncu = json.load(fobj)
-        except (OSError, ValueError):
-            pass
-        fused = info['path'] == 1
-        traffic = ncu.get('dram_bytes_per_launch') if (fused and args.workload == 'c1') else None
+        ncu_file = {('c1', 1): 'r1_fused_ncu_summary.json',
+                    ('c3', 2): 'r1_cluster256_ncu_summary.json'}.get(
+                        (args.workload, info['path']))
+        if ncu_file and args.walkers == 0:
+            try:
+                with open(os.path.join(ROOT, 'profiles', ncu_file)) as fobj:
+                    ncu = json.load(fobj)
+            except (OSError, ValueError):
+                pass
+        traffic = ncu.get('dram_bytes_per_launch')
         roofline = {
             'bound': 'fp32',
             'achieved': round(achieved, 3), 'peak': round(peak_probe, 2),

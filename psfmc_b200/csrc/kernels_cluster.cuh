@@ -259,6 +259,7 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
   const smem_addr_t tile = smem_base(smem_raw);
   const smem_addr_t twb = tile + PSFMC_CL_TW_OFF;
   double *red_s = reinterpret_cast<double *>(smem_raw + PSFMC_CL_RED_OFF);   // [16] + [4]
+  int *cnt_s = reinterpret_cast<int *>(smem_raw + PSFMC_CL_RED_OFF + 8 * 20);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const unsigned rank = cl_rank();
   const long long cluster_id = blockIdx.x / PSFMC_CL_CTAS;
@@ -267,6 +268,7 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
     const float2 t = CP.tw[tid];
     sts64(twb + 8u * tid, mk<float>(t.x, t.y));
   }
+  if (tid == 0) *cnt_s = 0;
   // staged parameters of the walker the next forward pass renders
   int *par_sel = reinterpret_cast<int *>(smem_raw + PSFMC_CL_PAR_OFF);
   double *par_wsc = reinterpret_cast<double *>(smem_raw + PSFMC_CL_PAR_OFF + 8);
@@ -511,15 +513,23 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
       ClRowLoop<0>::gather(ra, rm, R.l0, u);
       acc += cl_rows_inverse(P, R, y, unscale, u, o);
     }
-    // float64 reduction: warp shuffles, 16 warp partials, 4 CTA partials in CTA 0
+    // float64 reduction: warp shuffles; the last warp to arrive sums the 16 warp
+    // partials in fixed order (deterministic) and delivers the CTA partial to CTA 0
+    // -- before its own barrier arrival below, which publishes it
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-    if (lane == 0) red_s[w] = acc;
-    __syncthreads();
-    if (tid == 0) {
-      double tot = 0.0;
-      for (int k = 0; k < PSFMC_CL_THREADS / 32; ++k) tot += red_s[k];
-      std64_cluster(red0 + 8u * rank, tot);
+    if (lane == 0) {
+      volatile double *red = red_s;
+      red[w] = acc;
+      __threadfence_block();
+      const int prev = atomicAdd(cnt_s, 1);
+      if (prev == PSFMC_CL_THREADS / 32 - 1) {
+        __threadfence_block();
+        double tot = 0.0;
+        for (int k = 0; k < PSFMC_CL_THREADS / 32; ++k) tot += red[k];
+        std64_cluster(red0 + 8u * rank, tot);
+        *cnt_s = 0;
+      }
     }
     // this CTA is done with its tile (rows) and has delivered its partial
     cl_arrive();
