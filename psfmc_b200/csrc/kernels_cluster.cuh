@@ -74,29 +74,20 @@ __device__ __forceinline__ unsigned cl_rank() {
   return r;
 #endif
 }
-__device__ __forceinline__ smem_addr_t cl_map(smem_addr_t addr, unsigned rank) {
+// Generic pointer to the same shared-memory location in CTA `rank` of the cluster.
+// Remote stores go through these 64-bit pointers (plain generic stores): a
+// st.shared::cluster on a 32-bit address costs one S2R (shared-window base) PER STORE.
+__device__ __forceinline__ unsigned char *cl_map(unsigned char *ptr, unsigned rank) {
 #ifdef PSFMC_EMU
-  return emu::map_shared_rank(addr, rank);
+  return reinterpret_cast<unsigned char *>(emu::map_shared_rank((uintptr_t)ptr, rank));
 #else
-  smem_addr_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
+  unsigned long long in = reinterpret_cast<unsigned long long>(ptr), out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(in), "r"(rank));
+  return reinterpret_cast<unsigned char *>(out);
 #endif
 }
-__device__ __forceinline__ void sts64_cluster(smem_addr_t addr, cplx<float> v) {
-#ifdef PSFMC_EMU
-  *reinterpret_cast<cplx<float> *>(addr) = v;
-#else
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y)
-               : "memory");
-#endif
-}
-__device__ __forceinline__ void std64_cluster(smem_addr_t addr, double v) {
-#ifdef PSFMC_EMU
-  *reinterpret_cast<double *>(addr) = v;
-#else
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
-#endif
+__device__ __forceinline__ void stg64(unsigned char *ptr, cplx<float> v) {
+  *reinterpret_cast<float2 *>(ptr) = make_float2(v.x, v.y);
 }
 __device__ __forceinline__ void cl_arrive() {
 #ifdef PSFMC_EMU
@@ -161,29 +152,40 @@ __device__ __forceinline__ smem_addr_t cl_row_addr(const smem_addr_t *ra, const 
   return l0 ? rm[((m + 1) >> 1) & 3] + 8 * 32 : rm[m >> 1] + 8 * 64;
 }
 
-// owner CTA of element kx = l + 16 k2
+// Destination of element kx = l + 16 k2 of a row: owner CTA q, base (row start + 8 l
+// or row start - 8 l) and a compile-time byte offset; lane l = 0 of the odd mirrored
+// blocks goes to the first mirrored slot of the NEXT owner (see cl_row_addr).
 template <int K2>
-__device__ __forceinline__ int cl_row_owner(bool l0) {
-  if (K2 < 8) return K2 >> 1;
-  constexpr int m = 15 - K2;
-  if ((m & 1) == 0) return m >> 1;
-  return l0 ? (((m + 1) >> 1) & 3) : (m >> 1);
-}
+struct ClRowMap {
+  static constexpr int m = 15 - K2;
+  static constexpr bool minus = K2 >= 8;
+  static constexpr int q = K2 < 8 ? (K2 >> 1) : (m >> 1);
+  static constexpr int imm = K2 < 8 ? 128 * (K2 & 1) : ((m & 1) ? 8 * 64 : 8 * 48);
+  static constexpr bool l0_special = (K2 >= 8) && ((m & 1) != 0);
+  static constexpr int q0 = ((m + 1) >> 1) & 3;
+  static constexpr int imm0 = 8 * 32;
+};
 
-// push: ra / rm are addresses in the OWNERS' tiles (mapa); the quarter that stays in
-// this CTA (rank) goes through the ordinary shared-memory path (own_delta = mapped -
-// local address of this CTA's tile), the rest through st.shared::cluster
+// push: ga[q] / gm[q] = generic pointers into the OWNERS' tiles (row start +- 8 l), la /
+// lm the same row in this CTA's tile: the quarter that stays here goes through the
+// ordinary shared-memory path, the rest through distributed shared memory
 template <int K2>
 struct ClRowLoop {
-  static __device__ __forceinline__ void push(const smem_addr_t *ra, const smem_addr_t *rm,
-                                              bool l0, int rank, smem_addr_t own_delta,
-                                              const cplx<float> *u) {
-    const smem_addr_t addr = cl_row_addr<K2>(ra, rm, l0);
-    if (cl_row_owner<K2>(l0) == rank)
-      sts64(addr - own_delta, u[K2]);
-    else
-      sts64_cluster(addr, u[K2]);
-    ClRowLoop<K2 + 1>::push(ra, rm, l0, rank, own_delta, u);
+  static __device__ __forceinline__ void push(unsigned char *const *ga, unsigned char *const *gm,
+                                              smem_addr_t la, smem_addr_t lm, bool l0,
+                                              int rank, const cplx<float> *u) {
+    typedef ClRowMap<K2> M;
+    if (M::l0_special && l0) {
+      if (M::q0 == rank)
+        sts64(lm + M::imm0, u[K2]);
+      else
+        stg64(gm[M::q0] + M::imm0, u[K2]);
+    } else if (M::q == rank) {
+      sts64((M::minus ? lm : la) + M::imm, u[K2]);
+    } else {
+      stg64((M::minus ? gm[M::q] : ga[M::q]) + M::imm, u[K2]);
+    }
+    ClRowLoop<K2 + 1>::push(ga, gm, la, lm, l0, rank, u);
   }
   static __device__ __forceinline__ void gather(const smem_addr_t *ra, const smem_addr_t *rm,
                                                 bool l0, cplx<float> *u) {
@@ -193,8 +195,9 @@ struct ClRowLoop {
 };
 template <>
 struct ClRowLoop<16> {
-  static __device__ __forceinline__ void push(const smem_addr_t *, const smem_addr_t *, bool,
-                                              int, smem_addr_t, const cplx<float> *) {}
+  static __device__ __forceinline__ void push(unsigned char *const *, unsigned char *const *,
+                                              smem_addr_t, smem_addr_t, bool, int,
+                                              const cplx<float> *) {}
   static __device__ __forceinline__ void gather(const smem_addr_t *, const smem_addr_t *, bool,
                                                 cplx<float> *) {}
 };
@@ -287,11 +290,10 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
   };
   stage_params(cluster_id);
   // this CTA's tile as seen by each CTA of the cluster (index = owner rank)
-  smem_addr_t mb[PSFMC_CL_CTAS];
+  unsigned char *mb[PSFMC_CL_CTAS];
 #pragma unroll
-  for (int q = 0; q < PSFMC_CL_CTAS; ++q) mb[q] = cl_map(tile, q);
-  const smem_addr_t own_delta = cl_map(tile, rank) - tile;
-  const smem_addr_t red0 = cl_map(tile + PSFMC_CL_RED_OFF + 8 * 16, 0);   // CTA 0's [4]
+  for (int q = 0; q < PSFMC_CL_CTAS; ++q) mb[q] = cl_map(smem_raw, q);
+  double *red0 = reinterpret_cast<double *>(cl_map(smem_raw + PSFMC_CL_RED_OFF + 8 * 16, 0));
 
   ClRowRole R;
   R.w = w;
@@ -355,14 +357,15 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
       cl_rows_forward(P, R, rc_s, der_s, y, (float)wscale_b, u);
       if (it == 0 && pending >= 0) finish_pending();   // the other CTAs are done with
                                                        // the last walker's rows
-      smem_addr_t ra[PSFMC_CL_CTAS], rm[PSFMC_CL_CTAS];
+      unsigned char *ga[PSFMC_CL_CTAS], *gm[PSFMC_CL_CTAS];
 #pragma unroll
       for (int q = 0; q < PSFMC_CL_CTAS; ++q) {
-        const smem_addr_t rowb = mb[q] + 512u * (unsigned)y;
-        ra[q] = rowb + R.lx;
-        rm[q] = rowb - R.lx;
+        unsigned char *rowb = mb[q] + 512 * y;
+        ga[q] = rowb + R.lx;
+        gm[q] = rowb - R.lx;
       }
-      ClRowLoop<0>::push(ra, rm, R.l0, (int)rank, own_delta, u);
+      const smem_addr_t lrow = tile + 512u * (unsigned)y;
+      ClRowLoop<0>::push(ga, gm, lrow + R.lx, lrow - R.lx, R.l0, (int)rank, u);
     }
     cl_arrive();
     cl_wait();
@@ -462,22 +465,24 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
       dft16<true>(v0);    // v[n1]: row y = w + 16 n1
       cl_wait();          // every CTA has read its tile: the tiles may be overwritten
       const unsigned off = 512u * (64u * rank + w) + 8u * lane;
+      unsigned char *pb[PSFMC_CL_CTAS];
+#pragma unroll
+      for (int q = 0; q < PSFMC_CL_CTAS; ++q) pb[q] = mb[q] + off;
+      const smem_addr_t lb = tile + off;
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
-        const smem_addr_t dst = mb[n1 >> 2] + off + 8192 * (n1 & 3);
         if ((n1 >> 2) == (int)rank)
-          sts64(dst - own_delta, v0[n1]);
+          sts64(lb + 8192 * (n1 & 3), v0[n1]);
         else
-          sts64_cluster(dst, v0[n1]);
+          stg64(pb[n1 >> 2] + 8192 * (n1 & 3), v0[n1]);
       }
       dft16<true>(v1);    // overlaps the first unit's stores in flight
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
-        const smem_addr_t dst = mb[n1 >> 2] + off + 256 + 8192 * (n1 & 3);
         if ((n1 >> 2) == (int)rank)
-          sts64(dst - own_delta, v1[n1]);
+          sts64(lb + 256 + 8192 * (n1 & 3), v1[n1]);
         else
-          sts64_cluster(dst, v1[n1]);
+          stg64(pb[n1 >> 2] + 256 + 8192 * (n1 & 3), v1[n1]);
       }
     }
     cl_arrive();
@@ -527,7 +532,7 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
         __threadfence_block();
         double tot = 0.0;
         for (int k = 0; k < PSFMC_CL_THREADS / 32; ++k) tot += red[k];
-        std64_cluster(red0 + 8u * rank, tot);
+        red0[rank] = tot;
         *cnt_s = 0;
       }
     }
