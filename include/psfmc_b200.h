@@ -35,7 +35,7 @@ extern "C" {
 /* error codes */
 #define PSFMC_OK 0
 #define PSFMC_ERR_INVALID_ARG 1   /* bad descriptor / shapes / slot indices        */
-#define PSFMC_ERR_UNSUPPORTED 2   /* frame size the kernels do not cover             */
+#define PSFMC_ERR_UNSUPPORTED 2   /* odd width, frame too large, PSF larger than frame */
 #define PSFMC_ERR_CUDA 3          /* a CUDA runtime call failed (message has detail) */
 #define PSFMC_ERR_NO_DEVICE 4     /* no usable sm_100 device                          */
 
@@ -104,8 +104,15 @@ typedef struct psfmc_component {
  * (Configuration.py:38-52, PSFSelector.py:16-43), plus the component program. */
 typedef struct psfmc_desc {
   int32_t abi_version; /* PSFMC_ABI_VERSION */
-  int32_t height;      /* observation frame, rows    (power of two, 16..1024) */
-  int32_t width;       /* observation frame, columns (power of two, 16..1024) */
+  int32_t height;      /* observation frame, rows                            */
+  int32_t width;       /* observation frame, columns: EVEN, like the reference
+                          (psfMC/models.py:276). Powers of two 16..1024 are
+                          transformed directly; any other size goes through a
+                          zero-padded power-of-two transform frame (needs
+                          height + psf_height - 1 <= 1024, same for the width)
+                          whose linear convolution is folded back modulo
+                          (height, width): the reference's circular convolution at
+                          the image size (psfMC/utils.py:25-32), exactly           */
   const double *obs_data;  /* [height*width] row-major                          */
   const double *obs_var;   /* [height*width] 1/ivm, +inf at data-bad pixels      */
   const uint8_t *bad_px;   /* [height*width] nonzero = excluded from the sum     */

@@ -220,9 +220,19 @@ struct Program {
 
 // Frame geometry shared by all kernels of the staged path.
 struct Frame {
-  int32_t H, W;        // rows, columns
+  int32_t H, W;        // rows, columns of the TRANSFORM frame (powers of two)
   int32_t Wc;          // W/2 + 1 retained row frequencies
   int32_t logH, logW;
+  // Observation frame Hr x Wr. padded = 0: identical to the transform frame. padded = 1
+  // (frames that are not powers of two): the observation sits in the corner of a larger
+  // transform frame (H >= Hr + psf_h - 1, W >= Wr + psf_w - 1), rendered pixels outside it
+  // are zero, so the transform yields the LINEAR convolution, which is then folded back
+  // modulo (Hr, Wr) into the reference's circular one (psfMC/utils.py:25-32): output p of
+  // an axis adds c[p + N] for p <= f?_hi and c[M + p - N] for p >= f?_lo (N = real,
+  // M = transform length; the bounds follow from the PSF extent and its origin).
+  int32_t Hr, Wr;
+  int32_t padded;
+  int32_t fy_hi, fy_lo, fx_hi, fx_lo;
 };
 
 }  // namespace psfmc

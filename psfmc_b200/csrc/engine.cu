@@ -130,7 +130,7 @@ struct EngineBase {
                             double *lnl, void *stream) = 0;
   virtual int render(const double *theta, long long B, long long ld, unsigned which,
                      double *out, bool accumulate) = 0;
-  int H = 0, W = 0, precision = 0;
+  int H = 0, W = 0, precision = 0;   // observation frame (plan.fr: the transform frame)
   Program prog_h;
   int n_sersic = 0, n_point = 0;
   StagedPlan plan;
@@ -394,7 +394,10 @@ struct Engine : EngineBase {
     if (B <= 0 || which == 0) return 0;
     DeviceState<T> &d = devs[0];
     CUDA_TRY(cudaSetDevice(d.ordinal));
-    const size_t npx = (size_t)H * W;
+    // device images cover the transform frame (FH x FW); the caller gets the H x W
+    // observation frame (identical unless the frame is padded)
+    const int FH = plan.fr.H, FW = plan.fr.W;
+    const size_t npx = (size_t)FH * FW, npx_out = (size_t)H * W;
     int nsel = 0;
     for (unsigned bit = 1; bit <= PSFMC_IMG_POINT_SOURCE_SUBTRACTED; bit <<= 1)
       if (which & bit) ++nsel;
@@ -456,16 +459,32 @@ struct Engine : EngineBase {
           CUDA_TRY(cudaMemcpyAsync(d.img_pin.ptr, src, (size_t)nb * npx * sizeof(T),
                                    cudaMemcpyDeviceToHost, d.stream));
           CUDA_TRY(cudaStreamSynchronize(d.stream));
-          double *dst = out + ((size_t)sel * B + start) * npx;
-          for (size_t e = 0; e < (size_t)nb * npx; ++e) dst[e] = (double)d.img_pin.ptr[e];
+          double *dst = out + ((size_t)sel * B + start) * npx_out;
+          for (long long i = 0; i < nb; ++i)
+            for (int y = 0; y < H; ++y)
+              for (int x = 0; x < W; ++x)
+                dst[(size_t)i * npx_out + (size_t)y * W + x] =
+                    (double)d.img_pin.ptr[(size_t)i * npx + (size_t)y * FW + x];
         }
         ++sel;
       }
     }
     if (accumulate) {
-      CUDA_TRY(cudaMemcpyAsync(out, d.img_acc.ptr, (size_t)nsel * npx * sizeof(double),
+      std::vector<double> sums;
+      double *dst = out;
+      if (plan.fr.padded) {
+        sums.resize((size_t)nsel * npx);
+        dst = sums.data();
+      }
+      CUDA_TRY(cudaMemcpyAsync(dst, d.img_acc.ptr, (size_t)nsel * npx * sizeof(double),
                                cudaMemcpyDeviceToHost, d.stream));
       CUDA_TRY(cudaStreamSynchronize(d.stream));
+      if (plan.fr.padded)
+        for (int k = 0; k < nsel; ++k)
+          for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x)
+              out[(size_t)k * npx_out + (size_t)y * W + x] =
+                  sums[(size_t)k * npx + (size_t)y * FW + x];
     }
     return 0;
   }
@@ -475,10 +494,12 @@ int validate_desc(const psfmc_desc *d) {
   if (!d) return fail(PSFMC_ERR_INVALID_ARG, "descriptor is null");
   if (d->abi_version != PSFMC_ABI_VERSION)
     return fail(PSFMC_ERR_INVALID_ARG, "psfmc_desc.abi_version does not match the library");
-  if (!frame_supported(d->height, d->width))
+  if (d->height < 1 || d->width < 1)
+    return fail(PSFMC_ERR_INVALID_ARG, "frame height/width must be positive");
+  if (d->width & 1)
     return fail(PSFMC_ERR_UNSUPPORTED,
-                "frame height/width must be powers of two between 16 and 1024 "
-                "(the reference itself requires an even width, psfMC/models.py:276)");
+                "odd frame widths are not supported (the reference itself requires an even "
+                "width: irfft2 without s= returns W - 1 columns, psfMC/models.py:276)");
   if (!d->obs_data || !d->obs_var || !d->bad_px || !d->psf || !d->psf_var)
     return fail(PSFMC_ERR_INVALID_ARG, "null image pointer in descriptor");
   if (d->n_psf < 1) return fail(PSFMC_ERR_INVALID_ARG, "n_psf must be >= 1");
@@ -487,6 +508,11 @@ int validate_desc(const psfmc_desc *d) {
     return fail(PSFMC_ERR_UNSUPPORTED,
                 "PSF images larger than observation images are not supported "
                 "(psfMC/utils.py:16-18)");
+  if (!frame_supported(d->height, d->width, d->psf_height, d->psf_width))
+    return fail(PSFMC_ERR_UNSUPPORTED,
+                "frame too large: powers of two up to 1024 x 1024 are transformed directly, "
+                "other sizes need height + psf_height - 1 <= 1024 and width + psf_width - 1 "
+                "<= 1024");
   if (d->n_components < 0 || d->n_components > PSFMC_MAX_COMPONENTS)
     return fail(PSFMC_ERR_INVALID_ARG, "n_components out of range");
   if (d->n_components > 0 && !d->components)
@@ -608,15 +634,21 @@ int upload(T **dst, const std::vector<T> &src) {
 // Spectra of the padded PSFs / variance maps, float64, on the current device.
 int compute_spectra(const psfmc_desc *d, const StagedPlan &plan,
                     std::vector<cplx<double>> *spec_host) {
-  const int H = d->height, W = d->width, K = d->n_psf;
+  const int H = plan.fr.H, W = plan.fr.W, K = d->n_psf;
   const size_t npx = (size_t)H * W, nps = (size_t)d->psf_height * d->psf_width;
-  // zero-pad at offset pad//2 (psfMC/utils.py:15-21)
+  // zero-pad at offset pad//2 (psfMC/utils.py:15-21); the ifftshift of utils.py:32 is
+  // folded into the spectra by the setup kernel. Padded frames (see Frame): the stamp
+  // is laid out circularly with the reference's kernel origin at lag 0 instead.
   std::vector<double> pad_psf(K * npx, 0.0), pad_var(K * npx, 0.0);
-  const int oy = (H - d->psf_height) / 2, ox = (W - d->psf_width) / 2;
+  int oy = (H - d->psf_height) / 2, ox = (W - d->psf_width) / 2;
+  if (plan.fr.padded) {
+    oy = H - kernel_origin(plan.fr.Hr, d->psf_height);
+    ox = W - kernel_origin(plan.fr.Wr, d->psf_width);
+  }
   for (int k = 0; k < K; ++k)
     for (int y = 0; y < d->psf_height; ++y)
       for (int x = 0; x < d->psf_width; ++x) {
-        size_t dst = k * npx + (size_t)(y + oy) * W + (x + ox);
+        size_t dst = k * npx + (size_t)((y + oy) % H) * W + ((x + ox) % W);
         size_t src = k * nps + (size_t)y * d->psf_width + x;
         pad_psf[dst] = d->psf[src];
         pad_var[dst] = d->psf_var[src];
@@ -653,6 +685,7 @@ int compute_spectra(const psfmc_desc *d, const StagedPlan &plan,
   CUDA_TRY(cudaMalloc(&scratch, nspec * sizeof(cplx<double>)));
   CUDA_TRY(cudaMalloc(&spec, nspec * sizeof(cplx<double>)));
   StagedPlan dplan = make_staged_plan(H, W, 0, sizeof(double), 1.0);
+  dplan.fr.padded = plan.fr.padded;
   launch_staged_setup(dplan, tw_w, tw_h, pp, pv, K, scratch, spec, (cudaStream_t)0);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaDeviceSynchronize());
@@ -694,8 +727,11 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
   eng->W = d->width;
   eng->precision = d->precision;
   build_program(d, &eng->prog_h, &eng->n_sersic, &eng->n_point);
-  eng->plan = make_staged_plan(d->height, d->width, d->n_components, sizeof(T),
-                               chunk_mbytes_from_env());
+  const bool direct = frame_is_pow2(d->height, d->width);
+  eng->plan = direct ? make_staged_plan(d->height, d->width, d->n_components, sizeof(T),
+                                        chunk_mbytes_from_env())
+                     : make_padded_plan(d->height, d->width, d->psf_height, d->psf_width,
+                                        d->n_components, sizeof(T), chunk_mbytes_from_env());
   eng->path = 0;
   std::vector<int> ordinals;
   if (d->n_devices == 0) {
@@ -713,16 +749,22 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
     delete eng;
     return fail(PSFMC_ERR_NO_DEVICE, "no CUDA device available (cudaGetDeviceCount)");
   }
-  const size_t npx = (size_t)d->height * d->width;
-  std::vector<T> obs(npx), ovar(npx);
-  for (size_t e = 0; e < npx; ++e) {
-    obs[e] = (T)d->obs_data[e];
-    ovar[e] = (T)d->obs_var[e];
-  }
-  std::vector<unsigned char> bad(d->bad_px, d->bad_px + npx);
-  std::vector<cplx<T>> tww(d->width), twh(d->height);
-  fill_twiddles<T>(tww.data(), d->width);
-  fill_twiddles<T>(twh.data(), d->height);
+  // observation arrays over the TRANSFORM frame: outside the observation frame (padded
+  // frames only) every pixel is excluded (bad, infinite variance)
+  const int FH = eng->plan.fr.H, FW = eng->plan.fr.W;
+  const size_t npx = (size_t)FH * FW;
+  std::vector<T> obs(npx, (T)0), ovar(npx, (T)INFINITY);
+  std::vector<unsigned char> bad(npx, 1);
+  for (int y = 0; y < d->height; ++y)
+    for (int x = 0; x < d->width; ++x) {
+      const size_t src = (size_t)y * d->width + x, dst = (size_t)y * FW + x;
+      obs[dst] = (T)d->obs_data[src];
+      ovar[dst] = (T)d->obs_var[src];
+      bad[dst] = d->bad_px[src];
+    }
+  std::vector<cplx<T>> tww(FW), twh(FH);
+  fill_twiddles<T>(tww.data(), FW);
+  fill_twiddles<T>(twh.data(), FH);
   std::vector<Program> progv(1, eng->prog_h);
 
   eng->devs.resize(ordinals.size());
@@ -808,8 +850,8 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       break;
 #ifndef PSFMC_NO_FUSED
     if (i == 0) {
-      eng->path = fused_path_available<T>(eng->plan, eng->prog_h) ? 1 : 0;
-      if (cluster_path_available<T>(eng->plan)) eng->path = 2;
+      eng->path = (direct && fused_path_available<T>(eng->plan, eng->prog_h)) ? 1 : 0;
+      if (direct && cluster_path_available<T>(eng->plan)) eng->path = 2;
       const char *force = getenv("PSFMC_FORCE_STAGED");
       if (force && force[0] == '1') eng->path = 0;
       const char *variant = getenv("PSFMC_FUSED_VARIANT");

@@ -1,5 +1,5 @@
-// Staged row/column path: works for every supported frame (16..1024, powers of
-// two) in both precisions; the row spectra of each walker are staged through a
+// Staged row/column path: works for every supported frame (powers of two 16..1024
+// directly, other sizes through a padded transform frame, see Frame) in both precisions; the row spectra of each walker are staged through a
 // global scratch buffer that stays L2-resident for the batch chunk in flight.
 //
 //   rows_fwd : render RB rows -> z = raw + i raw^2 -> FFT_W -> split into the row
@@ -93,8 +93,11 @@ __global__ void rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__
     const bool round_f32 = (precision == PSFMC_PREC_FP64_RAWF32);
     for (int e = tid; e < npx; e += nthreads) {
       int r = e >> fr.logW, x = e & (W - 1);
-      double val = raw_pixel_f64(prog, der_s, x, y0 + r, round_f32,
-                                 SRC == PSFMC_SRC_RENDER_PS);
+      // (padded frames: nothing is rendered outside the observation frame)
+      double val = (x < fr.Wr && y0 + r < fr.Hr)
+                       ? raw_pixel_f64(prog, der_s, x, y0 + r, round_f32,
+                                       SRC == PSFMC_SRC_RENDER_PS)
+                       : 0.0;
       T a = (T)val;
       tile[r * PITCH + x] = mk<T>(a, a * a * wsc);
       if (raw_out) raw_out[(b * H + (y0 + r)) * (long long)W + x] = a;
@@ -139,6 +142,7 @@ __global__ void rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__
     for (int i = 0; i < 8; ++i) {
       int e = tid + i * nthreads;
       int r = e >> fr.logW, x = e & (W - 1);
+      if (x >= fr.Wr || y0 + r >= fr.Hr) acc[i] = 0.0f;   // padded frames
       tile[r * PITCH + x] = mk<T>((T)acc[i], (T)(acc[i] * acc[i]) * wsc);
       if (raw_out) raw_out[(b * H + (y0 + r)) * (long long)W + x] = (T)acc[i];
     }
@@ -230,7 +234,8 @@ __global__ void cols_kernel(Frame fr_rt, int CB, const cplx<T> *__restrict__ tw_
     for (int e = tid; e < nvalid; e += nthreads) {
       int cc = c0 + (e >> fr.logH), ky = e & (H - 1);
       int kx = cc < Wc ? cc : cc - Wc;
-      T sgn = ((kx + ky) & 1) ? -scale : scale;
+      // (padded frames: the kernel is laid out with its origin at lag 0, no shift)
+      T sgn = (((kx + ky) & 1) && !fr.padded) ? -scale : scale;
       obase[e] = mk<T>(tile[e].x * sgn, tile[e].y * sgn);
     }
     return;
@@ -243,6 +248,20 @@ __global__ void cols_kernel(Frame fr_rt, int CB, const cplx<T> *__restrict__ tw_
   __syncthreads();
 
   fft_line_smem<T, true, LOGH>(tile + col * H, H, fr.logH, tl, tw_s);
+
+  if (fr.padded) {
+    // fold the linear convolution back modulo Hr (see Frame); reads touch rows >= Hr
+    // only, writes rows < Hr only. (fft_line_smem ends with a CTA barrier.)
+    const int Hr = fr.Hr, ncols = nvalid / H;
+    for (int e = tid; e < ncols * Hr; e += nthreads) {
+      const int cc = e / Hr, p = e - cc * Hr;
+      cplx<T> v = tile[cc * H + p];
+      if (p <= fr.fy_hi) v = v + tile[cc * H + p + Hr];
+      if (p >= fr.fy_lo) v = v + tile[cc * H + H + p - Hr];
+      tile[cc * H + p] = v;
+    }
+    __syncthreads();
+  }
 
 #ifndef PSFMC_EMU
   // (fft_line_smem ends with a CTA barrier after its last stores) one bulk store
@@ -338,6 +357,19 @@ __global__ void rows_inv_kernel(Frame fr_rt, int RB, const cplx<T> *__restrict__
     const int tpr = W >> 3;
     const int r = tid >> (fr.logW - 3), tl = tid & (tpr - 1);
     fft_line_smem<T, true, LOGW>(tile + r * PITCH, W, fr.logW, tl, tw_s);
+  }
+
+  if (fr.padded) {
+    // fold modulo Wr (see Frame); reads touch columns >= Wr only, writes columns < Wr
+    const int Wr = fr.Wr;
+    for (int e = tid; e < RB * Wr; e += nthreads) {
+      const int r = e / Wr, p = e - r * Wr;
+      cplx<T> v = tile[r * PITCH + p];
+      if (p <= fr.fx_hi) v = v + tile[r * PITCH + p + Wr];
+      if (p >= fr.fx_lo) v = v + tile[r * PITCH + W + p - Wr];
+      tile[r * PITCH + p] = v;
+    }
+    __syncthreads();
   }
 
   // undo the (exact, power-of-two) channel scalings of the variance image

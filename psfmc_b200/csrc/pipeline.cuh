@@ -62,9 +62,26 @@ struct StagedPlan {
   long long chunk;          // walkers whose scratch is in flight at once
 };
 
-inline bool frame_supported(int H, int W) {
+inline bool frame_is_pow2(int H, int W) {
   auto ok = [](int v) { return v >= 16 && v <= 1024 && (v & (v - 1)) == 0; };
   return ok(H) && ok(W);
+}
+
+// Transform frame of an observation frame that is not a power of two: the smallest
+// powers of two that hold the linear convolution with the PSF stamp.
+inline int padded_length(int n, int psf_n) {
+  int m = 16;
+  while (m < n + psf_n - 1) m <<= 1;
+  return m;
+}
+
+// Frames the engine covers: powers of two 16..1024 directly; any other height and any
+// other EVEN width (the reference needs an even width, psfMC/models.py:276) through a
+// padded transform frame of at most 1024 x 1024.
+inline bool frame_supported(int H, int W, int psf_h, int psf_w) {
+  if (frame_is_pow2(H, W)) return true;
+  if (H < 1 || W < 2 || (W & 1)) return false;
+  return padded_length(H, psf_h) <= 1024 && padded_length(W, psf_w) <= 1024;
 }
 
 inline StagedPlan make_staged_plan(int H, int W, int n_components, size_t sizeof_real,
@@ -75,6 +92,11 @@ inline StagedPlan make_staged_plan(int H, int W, int n_components, size_t sizeof
   p.fr.Wc = W / 2 + 1;
   p.fr.logH = ilog2(H);
   p.fr.logW = ilog2(W);
+  p.fr.Hr = H;
+  p.fr.Wr = W;
+  p.fr.padded = 0;
+  p.fr.fy_hi = p.fr.fx_hi = -1;
+  p.fr.fy_lo = p.fr.fx_lo = 1 << 30;
   int rb = 2048 / W;
   if (rb < 1) rb = 1;
   if (rb > H) rb = H;
@@ -105,6 +127,28 @@ inline StagedPlan make_staged_plan(int H, int W, int n_components, size_t sizeof
   long long chunk = (long long)(chunk_mbytes * 1048576.0 / per_walker);
   if (chunk < 1) chunk = 1;
   p.chunk = chunk;
+  return p;
+}
+
+// Origin of the reference's convolution kernel inside the PSF stamp along one axis:
+// conv = ifftshift(irfft2(rfft2(img) * rfft2(psf padded at offset (n - psf_n) // 2)))
+// (psfMC/utils.py:9-32) is the circular convolution with the stamp pixel
+// n // 2 - (n - psf_n) // 2 at lag 0.
+inline int kernel_origin(int n, int psf_n) { return n / 2 - (n - psf_n) / 2; }
+
+// Plan for an observation frame Hr x Wr that is not a power of two (see Frame).
+inline StagedPlan make_padded_plan(int Hr, int Wr, int psf_h, int psf_w, int n_components,
+                                   size_t sizeof_real, double chunk_mbytes) {
+  StagedPlan p = make_staged_plan(padded_length(Hr, psf_h), padded_length(Wr, psf_w),
+                                  n_components, sizeof_real, chunk_mbytes);
+  p.fr.Hr = Hr;
+  p.fr.Wr = Wr;
+  p.fr.padded = 1;
+  const int oy = kernel_origin(Hr, psf_h), ox = kernel_origin(Wr, psf_w);
+  p.fr.fy_hi = psf_h - 2 - oy;
+  p.fr.fy_lo = Hr - oy;
+  p.fr.fx_hi = psf_w - 2 - ox;
+  p.fr.fx_lo = Wr - ox;
   return p;
 }
 
@@ -172,8 +216,8 @@ inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
                                  cudaEvent_t ev_end = nullptr) {
   if (n_batch <= 0) return;
   const Frame fr = plan.fr;
-  launch_prepare(*buf.prog_host, theta, n_batch, ld, fr.H, fr.W, n_components, buf.derived, buf.psf_sel,
-                 buf.wscale, (float *)nullptr, stream);
+  launch_prepare(*buf.prog_host, theta, n_batch, ld, fr.Hr, fr.Wr, n_components, buf.derived,
+                 buf.psf_sel, buf.wscale, (float *)nullptr, stream);
   if (ev_begin) cudaEventRecord(ev_begin, stream);   // the three row/column kernels
   for (long long start = 0; start < n_batch; start += plan.chunk) {
     long long nb = n_batch - start < plan.chunk ? n_batch - start : plan.chunk;

@@ -301,3 +301,70 @@ def check_cluster_path_256(library, n_walkers, monkeypatch=None):
         assert staged.engine.info()['path'] == 0
         assert_lnl_close(staged.log_likelihood_batch(thetas), expect, 'fp32', bounds)
     return got
+
+
+ARBITRARY_FRAMES = ((100, 100, 64, 64), (75, 100, 31, 17), (50, 36, 21, 36),
+                    (128, 100, 32, 32), (33, 64, 8, 9))
+
+
+def arbitrary_frame_model(height, width, psf_h, psf_w, precision, library=None):
+    """A frame that is not a power of two (odd heights, odd PSF stamps, a PSF as wide as
+    the frame): asymmetric PSF (pins the kernel origin), a point source in the frame
+    corner whose PSF wings wrap around (the reference's convolution is circular at the
+    image size, psfMC/utils.py:25-32), bad pixels, a NaN observation."""
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.components import Configuration, PointSource, Sersic, Sky
+    from psfmc_b200.distributions import Normal, Uniform
+    rng = np.random.RandomState(height * 1000 + width)
+    obs = 0.05 * rng.standard_normal((height, width))
+    ivm = np.full((height, width), 400.0)
+    ivm[height // 3, width // 4] = 0.0
+    obs[height // 2, width // 5] = np.nan
+    yy, xx = np.mgrid[0:psf_h, 0:psf_w]
+    psf = np.exp(-0.5 * (((xx - psf_w // 2) / 1.7) ** 2 + ((yy - psf_h // 2) / 2.3) ** 2))
+    psf += 0.02 * rng.random_sample((psf_h, psf_w))
+    psf_ivm = 1.0 / (psf / 200.0 + 1e-4)
+    cx, cy = width / 2.0, height / 2.0
+    comps = [Configuration(obs, ivm, psf, psf_ivm, mag_zeropoint=25.0),
+             Sky(adu=Normal(loc=0, scale=0.01)),
+             PointSource(xy=Uniform(loc=np.array((cx - 3, cy - 3)), scale=np.array((6.0, 6.0))),
+                         mag=Uniform(loc=18, scale=2)),
+             PointSource(xy=Uniform(loc=np.array((0.5, height - 4.0)),
+                                    scale=np.array((3.0, 3.0))),
+                         mag=Uniform(loc=17, scale=1), shift_method='bilinear'),
+             Sersic(xy=Uniform(loc=np.array((cx - 4, cy - 4)), scale=np.array((8.0, 8.0))),
+                    mag=Uniform(loc=18, scale=3), reff=Uniform(loc=4, scale=8),
+                    reff_b=Uniform(loc=2, scale=2), index=Uniform(loc=0.5, scale=4),
+                    angle=Uniform(loc=0, scale=180), angle_degrees=True)]
+    return MultiComponentModel(comps, precision=precision, library=library,
+                               fp64_rescue=False)
+
+
+def check_arbitrary_frame(library, dims, n_walkers=3):
+    """Frames that are not powers of two (padded transform frame + fold): lnL in float64
+    and float32 and all five blob images against the oracle."""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model64 = arbitrary_frame_model(*dims, precision='fp64', library=library)
+    assert model64.engine.info()['height'] == dims[0]
+    assert model64.engine.info()['width'] == dims[1]
+    thetas = draw_walkers_fast(model64, n_walkers, seed=dims[0])
+    oracle = oracle_from_model(model64)
+    expect = oracle.lnlike_batch(thetas)
+    assert np.all(np.isfinite(expect))
+    assert_lnl_close(model64.log_likelihood_batch(thetas), expect, 'fp64')
+    model32 = arbitrary_frame_model(*dims, precision='fp32', library=library)
+    assert_lnl_close(model32.log_likelihood_batch(thetas), expect, 'fp32',
+                     fp32_bounds(model32, thetas, oracle))
+    images = model64.engine.render(thetas[:1])
+    reference = oracle.images(thetas[0])
+    for key, got in images.items():
+        want = np.asarray(reference[key], dtype=np.float64)
+        assert got[0].shape == want.shape == tuple(dims[:2])
+        finite = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got[0]), finite), key
+        scale = np.abs(want[finite]).max()
+        assert np.allclose(got[0][finite], want[finite], rtol=1e-9, atol=1e-12 * scale), key
+    sums = model64.engine.accumulate(thetas, ('convolved_model',))
+    full = model64.engine.render(thetas, ('convolved_model',))
+    assert np.allclose(sums['convolved_model'], full['convolved_model'].sum(axis=0),
+                       rtol=1e-12, atol=1e-12)

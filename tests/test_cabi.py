@@ -81,8 +81,22 @@ def test_invalid_arguments_are_reported_not_thrown(cuda_library):
     assert lib.psfmc_engine_create(ctypes.byref(desc), ctypes.byref(handle)) == 1
     assert b'abi_version' in lib.psfmc_last_error()
     desc.abi_version = _lib.ABI_VERSION
-    desc.height, desc.width = 100, 128          # not a power of two
+    desc.height, desc.width = 100, 101          # odd width: the reference rejects it too
     assert lib.psfmc_engine_create(ctypes.byref(desc), ctypes.byref(handle)) == 2
+    assert b'odd' in lib.psfmc_last_error()
+    assert handle.value is None
+    # too large for the padded transform frame (1000 + 64 - 1 > 1024)
+    px = np.zeros(1000 * 1000)
+    stamp = np.zeros(64 * 64)
+    bad = np.zeros(1000 * 1000, dtype=np.uint8)
+    dbl = ctypes.POINTER(ctypes.c_double)
+    desc.height, desc.width = 1000, 1000
+    desc.obs_data = desc.obs_var = px.ctypes.data_as(dbl)
+    desc.bad_px = bad.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+    desc.n_psf, desc.psf_height, desc.psf_width = 1, 64, 64
+    desc.psf = desc.psf_var = stamp.ctypes.data_as(dbl)
+    assert lib.psfmc_engine_create(ctypes.byref(desc), ctypes.byref(handle)) == 2
+    assert b'too large' in lib.psfmc_last_error()
     assert handle.value is None
     out = np.zeros(1)
     dbl_p = ctypes.POINTER(ctypes.c_double)

@@ -8,7 +8,8 @@ it says nothing about speed. The product library is never built this way.
 import numpy as np
 import pytest
 
-from conftest import (assert_lnl_close, check_cluster_path_256, check_fp64_rescue,
+from conftest import (ARBITRARY_FRAMES, assert_lnl_close, check_arbitrary_frame,
+                      check_cluster_path_256, check_fp64_rescue,
                       check_near_centre_walkers, mixed_model_128, fp32_bounds, load_golden, model_from_file,
                       oracle_from_model)
 
@@ -255,3 +256,8 @@ def test_emu_cluster_kernel_256(emu_library, monkeypatch):
     """256 x 256 frame split over a four-CTA cluster (distributed shared memory,
     barrier.cluster emulated): two clusters walking over five walkers."""
     check_cluster_path_256(emu_library, 5, monkeypatch)
+
+
+@pytest.mark.parametrize('dims', ARBITRARY_FRAMES[:3] + ARBITRARY_FRAMES[4:])
+def test_emu_arbitrary_frame_sizes(emu_library, dims):
+    check_arbitrary_frame(emu_library, dims, n_walkers=2)

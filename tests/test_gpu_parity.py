@@ -388,3 +388,12 @@ def test_gpu_cluster_kernel_256_properties(cuda_library):
     assert np.array_equal(model.log_likelihood_batch(thetas[perm]), first[perm])
     assert np.array_equal(model.log_likelihood_batch(thetas[:37]), first[:37])
     assert np.all(np.isfinite(first))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dims', [(100, 100, 64, 64), (75, 100, 31, 17), (50, 36, 21, 36),
+                                  (128, 100, 32, 32), (33, 64, 8, 9), (150, 150, 64, 64),
+                                  (301, 300, 65, 64), (600, 500, 101, 99)])
+def test_gpu_arbitrary_frame_sizes(cuda_library, dims):
+    from conftest import check_arbitrary_frame
+    check_arbitrary_frame(cuda_library, dims, n_walkers=5 if dims[0] < 400 else 2)
