@@ -125,20 +125,28 @@ class ComponentBase(object):
             total += np.sum(prior.logp(prior.value))
         return total
 
-    def log_priors_batch(self, block):
+    def log_priors_batch(self, block, column_logp=None):
         """
         Joint log-prior for every row of ``block`` (B, num_stochastics()):
         one vectorised ``logp`` call per prior instead of B scalar calls.
+        ``column_logp`` (same shape): per-column log-densities somebody already
+        evaluated (the model groups priors of one family, models.py); only the
+        summation -- in the same order -- is done here then.
         """
         block = np.asarray(block, dtype=np.float64)
         total = np.zeros(block.shape[0])
         start = 0
         for _, prior, length in self.free_parameters():
+            if column_logp is not None:
+                total = total + np.sum(column_logp[:, start:start + length], axis=1)
+                start += length
+                continue
             cols = block[:, start:start + length]
             if getattr(prior, 'discrete', False):
                 cols = np.rint(cols).astype(int)
+            batched = getattr(prior, 'logp_batch', prior.logp)
             with np.errstate(all='ignore'):
-                total = total + np.sum(prior.logp(cols), axis=1)
+                total = total + np.sum(batched(cols), axis=1)
             start += length
         return total
 
@@ -207,9 +215,9 @@ class Sersic(ComponentBase):
         logp = super(Sersic, self).log_priors()
         return logp + (-np.inf if self.reff_b > self.reff else 0)
 
-    def log_priors_batch(self, block):
+    def log_priors_batch(self, block, column_logp=None):
         block = np.asarray(block, dtype=np.float64)
-        logp = super(Sersic, self).log_priors_batch(block)
+        logp = super(Sersic, self).log_priors_batch(block, column_logp)
         swapped = self.column_of('reff_b', block) > self.column_of('reff', block)
         return np.where(swapped, -np.inf, logp)
 

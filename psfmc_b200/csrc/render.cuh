@@ -42,9 +42,12 @@ __device__ __forceinline__ float fast_rcp(float x) {
 // normed_grad * cent_offset = (2 p kappa)^2 / 12 * t^2 / |d|^2 (algebraically
 // identical to the reference's g * (sq_delta_r / 12 * g)); kq = 2 p kappa / sqrt(12).
 // Range: for a very small index (n ~ 0.006: p = 86, kappa ~ 1e-26) the profile only
-// decays where t ~ 1/kappa, so t must keep float32's whole range (clamped at 1e38
-// against inf * 0); kq * t is clamped at 1e18 so that its square stays finite -- the
-// profile is exactly 0 long before (c1 * t = 5 n * kq * t).
+// decays where t ~ 1/kappa, so t keeps float32's whole range (an overflow to +inf gives
+// 2^-inf = 0, which is what the reference has there); kq * t is clamped at 1e18 so that
+// its square stays finite -- the profile is exactly 0 long before (c1 * t = 5 n * kq * t).
+// NaN / overflow: nothing on the way from sq to the value may swallow a NaN (fminf
+// returns its other operand), and an infinite sq (reff ~ 0) must give NaN like the
+// reference's inf * 0 in its gradient term: (sq - sq) is 0 for finite sq, NaN otherwise.
 struct SersicF32 {
   float xi, xf, yi, yf;  // centre split into integer + fraction (keeps dx exact)
   float a00, a01, a10, a11;
@@ -77,8 +80,8 @@ __device__ __forceinline__ float sersic_pixel_f32(const SersicF32 &s, float x, f
   float v = s.a10 * dx + s.a11 * dy;
   float sq = u * u + v * v;
   float r2 = dx * dx + dy * dy;
-  float t = fminf(fast_ex2(s.p * fast_lg2(sq)), 1.0e38f);
-  float sb = fast_ex2(s.c0 - s.c1 * t);
+  float t = fast_ex2(s.p * fast_lg2(sq));
+  float sb = fast_ex2((s.c0 + (sq - sq)) - s.c1 * t);
   float g = fminf(s.kq * t, 1.0e18f);
   return sb * (1.0f + (g * g) * fast_rcp(r2));
 }
@@ -173,10 +176,19 @@ __global__ void prepare_kernel(const __grid_constant__ Program prog_c,
     double ymin, ymax, xmin, xmax;
     stamp_bounds(y, radius, H, &ymin, &ymax);
     stamp_bounds(x, radius, W, &xmin, &xmax);
+    double flux = mag_to_flux(mag, prog->mag_zp);
+    // a position that is not finite has no stamp (the reference's weights are NaN for
+    // an infinite offset and its slice arithmetic raises for NaN): poison one pixel so
+    // that the walker comes out as -inf instead of silently losing the component
+    const bool lost = !(isfinite(x) && isfinite(y));
+    if (lost) {
+      ymin = ymax = xmin = xmax = 0.0;
+      flux = NAN;
+    }
     if (writer) {
       out[D_PS_X] = x;
       out[D_PS_Y] = y;
-      out[D_PS_FLUX] = mag_to_flux(mag, prog->mag_zp);
+      out[D_PS_FLUX] = flux;
       out[D_PS_YMIN] = ymin;
       out[D_PS_YMAX] = ymax;
       out[D_PS_XMIN] = xmin;
@@ -195,6 +207,7 @@ __global__ void prepare_kernel(const __grid_constant__ Program prog_c,
         if (pos <= (along_y ? ymax : xmax))
           wgt = (flags & PSFMC_FLAG_BILINEAR) ? 1.0 - fabs(pos - centre)
                                               : lanczos3_ref(pos - centre);
+        if (lost) wgt = 1.0;
         out[(along_y ? D_PS_WY : D_PS_WX) + glane] = wgt;
       }
     }
@@ -330,8 +343,8 @@ __device__ __forceinline__ cplx<float> sersic_pair_f32(const SersicF32 &s, cplx<
   const cplx<float> sq = pfma(v, v, pmul(u, u));
   const cplx<float> r2 = pfma(dx, dx, bcast(dy2));
   const cplx<float> e = pmul(bcast(s.p), mk<float>(fast_lg2(sq.x), fast_lg2(sq.y)));
-  const cplx<float> t = mk<float>(fminf(fast_ex2(e.x), 1.0e38f), fminf(fast_ex2(e.y), 1.0e38f));
-  const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0));
+  const cplx<float> t = mk<float>(fast_ex2(e.x), fast_ex2(e.y));
+  const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0) + (sq - sq));
   const cplx<float> sb = mk<float>(fast_ex2(arg.x), fast_ex2(arg.y));
   const cplx<float> gu = pmul(bcast(s.kq), t);
   const cplx<float> g = mk<float>(fminf(gu.x, 1.0e18f), fminf(gu.y, 1.0e18f));
@@ -347,8 +360,8 @@ __device__ __forceinline__ cplx<float> sersic_pair2_f32(const SersicF32 &s, cplx
   const cplx<float> sq = pfma(v, v, pmul(u, u));
   const cplx<float> r2 = pfma(dx, dx, pmul(dy, dy));
   const cplx<float> e = pmul(bcast(s.p), mk<float>(fast_lg2(sq.x), fast_lg2(sq.y)));
-  const cplx<float> t = mk<float>(fminf(fast_ex2(e.x), 1.0e38f), fminf(fast_ex2(e.y), 1.0e38f));
-  const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0));
+  const cplx<float> t = mk<float>(fast_ex2(e.x), fast_ex2(e.y));
+  const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0) + (sq - sq));
   const cplx<float> sb = mk<float>(fast_ex2(arg.x), fast_ex2(arg.y));
   const cplx<float> gu = pmul(bcast(s.kq), t);
   const cplx<float> g = mk<float>(fminf(gu.x, 1.0e18f), fminf(gu.y, 1.0e18f));

@@ -368,3 +368,27 @@ def check_arbitrary_frame(library, dims, n_walkers=3):
     full = model64.engine.render(thetas, ('convolved_model',))
     assert np.allclose(sums['convolved_model'], full['convolved_model'].sum(axis=0),
                        rtol=1e-12, atol=1e-12)
+
+
+def check_nan_propagation(library, monkeypatch):
+    """Parameters that make the reference's model NaN (-> lnL = -inf, models.py:238-241)
+    must not be swallowed by the float32 fast paths (a clamp with fminf once returned a
+    finite lnL with the component silently missing)."""
+    golden = load_golden('c1_golden.json')
+    base = np.array(golden['theta'][0])
+    # theta order: sky | ps mag x y | sersic: angle index mag reff reff_b x y | sersic ...
+    poison = [(4, np.nan), (4, np.inf), (5, -np.inf), (5, np.nan), (6, np.nan),
+              (7, 1e-300), (7, np.nan), (8, 1e-300), (9, np.nan), (10, np.inf),
+              (11, -np.inf), (14, 1e-300), (15, 1e-300), (0, np.nan), (1, np.nan),
+              (2, np.nan)]
+    rows = np.array([base] * (len(poison) + 1))
+    for num, (col, val) in enumerate(poison):
+        rows[num + 1, col] = val
+    for staged in ('0', '1'):
+        monkeypatch.setenv('PSFMC_FORCE_STAGED', staged)
+        for precision in ('fp32', 'fp64'):
+            model = model_from_file('j0005/model_c1.py', precision, library=library,
+                                    fp64_rescue=False)
+            got = model.log_likelihood_batch(rows)
+            assert np.isfinite(got[0])
+            assert np.all(got[1:] == -np.inf), (staged, precision, got)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import (ARBITRARY_FRAMES, assert_lnl_close, check_arbitrary_frame,
-                      check_cluster_path_256, check_fp64_rescue,
+                      check_cluster_path_256, check_nan_propagation, check_fp64_rescue,
                       check_near_centre_walkers, mixed_model_128, fp32_bounds, load_golden, model_from_file,
                       oracle_from_model)
 
@@ -261,3 +261,7 @@ def test_emu_cluster_kernel_256(emu_library, monkeypatch):
 @pytest.mark.parametrize('dims', ARBITRARY_FRAMES[:3] + ARBITRARY_FRAMES[4:])
 def test_emu_arbitrary_frame_sizes(emu_library, dims):
     check_arbitrary_frame(emu_library, dims, n_walkers=2)
+
+
+def test_emu_nan_parameters_give_minus_inf(emu_library, monkeypatch):
+    check_nan_propagation(emu_library, monkeypatch)

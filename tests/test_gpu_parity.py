@@ -397,3 +397,9 @@ def test_gpu_cluster_kernel_256_properties(cuda_library):
 def test_gpu_arbitrary_frame_sizes(cuda_library, dims):
     from conftest import check_arbitrary_frame
     check_arbitrary_frame(cuda_library, dims, n_walkers=5 if dims[0] < 400 else 2)
+
+
+@pytest.mark.gpu
+def test_gpu_nan_parameters_give_minus_inf(cuda_library, monkeypatch):
+    from conftest import check_nan_propagation
+    check_nan_propagation(cuda_library, monkeypatch)
