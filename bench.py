@@ -339,6 +339,28 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * walkers * args.steps / e2e_s
+    rescued_per_step = engine.info()['rescued_total'] / float(
+        args.steps + max(args.warmup, 3))
+    # the same loop with the float64 rescue of non-finite float32 results switched
+    # off (for information: prior-drawn ensembles contain a few such walkers, the
+    # walkers of a converged chain do not)
+    e2e_raw = None
+    if args.precision == 'fp32':
+        raw_engine = MultiComponentModel(build_components(args.workload), precision='fp32',
+                                         devices=[local], fp64_rescue=False).engine
+        out = lnl_pin.numpy()
+        for s in range(3):
+            raw_engine.lnlike(th_pin[0].numpy()[:half], out=out[:half])
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            th = th_pin[s % nsets].numpy()
+            for h in range(2):
+                raw_engine.lnlike(th[h * half:(h + 1) * half],
+                                  out=out[h * half:(h + 1) * half])
+        torch.cuda.synchronize()
+        e2e_raw = world * walkers * args.steps / max_over_ranks(time.perf_counter() - t0)
+        raw_engine.close()
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
@@ -422,7 +444,9 @@ def run_ours(args):
                     'd2h_bytes_per_step': walkers * 8,
                     'timer': 'host perf_counter around blocking C-ABI calls '
                              '(psfmc_lnlike_batch), max over ranks',
-                    'with_python_priors': round(world * walkers * args.steps / post_s, 1)},
+                    'with_python_priors': round(world * walkers * args.steps / post_s, 1),
+                    'fp64_rescued_walkers_per_step': round(rescued_per_step, 2),
+                    'without_fp64_rescue': None if e2e_raw is None else round(e2e_raw, 1)},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': roofline,

@@ -79,6 +79,11 @@ extern "C" {
                              a float32 transform resolves gives a negative variance, where
                              the float64 reference is finite); this flag turns that off */
 
+#define PSFMC_DESC_LOW_LATENCY 2 /* the engine will see batches of a few walkers: the
+                             row/column kernels are planned with many small CTAs per
+                             walker instead of few large ones (the float64 rescue
+                             engine is built this way)                               */
+
 /* images psfmc_render_batch can return: the blobs of psfMC/models.py:222-226 */
 #define PSFMC_IMG_RAW_MODEL 1u
 #define PSFMC_IMG_CONVOLVED_MODEL 2u

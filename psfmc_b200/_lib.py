@@ -17,6 +17,7 @@ NSLOTS = 7
 MAX_COMPONENTS = 32
 PREC_FP64, PREC_FP32, PREC_FP64_RAWF32 = 0, 1, 2
 DESC_NO_FP64_RESCUE = 1
+DESC_LOW_LATENCY = 2
 PRECISIONS = {'fp64': PREC_FP64, 'fp32': PREC_FP32, 'fp64_rawf32': PREC_FP64_RAWF32}
 IMAGE_BITS = {'raw_model': 1, 'convolved_model': 2, 'residual': 4,
               'composite_ivm': 8, 'point_source_subtracted': 16}

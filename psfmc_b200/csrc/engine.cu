@@ -728,10 +728,12 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
   eng->precision = d->precision;
   build_program(d, &eng->prog_h, &eng->n_sersic, &eng->n_point);
   const bool direct = frame_is_pow2(d->height, d->width);
+  const bool low_latency = (d->flags & PSFMC_DESC_LOW_LATENCY) != 0;
   eng->plan = direct ? make_staged_plan(d->height, d->width, d->n_components, sizeof(T),
-                                        chunk_mbytes_from_env())
+                                        chunk_mbytes_from_env(), low_latency)
                      : make_padded_plan(d->height, d->width, d->psf_height, d->psf_width,
-                                        d->n_components, sizeof(T), chunk_mbytes_from_env());
+                                        d->n_components, sizeof(T), chunk_mbytes_from_env(),
+                                        low_latency);
   eng->path = 0;
   std::vector<int> ordinals;
   if (d->n_devices == 0) {
@@ -960,6 +962,7 @@ struct SavedDesc {
     d.psf_var = psf_var.data();
     d.components = comps.data();
     d.precision = PSFMC_PREC_FP64;
+    d.flags |= PSFMC_DESC_LOW_LATENCY;   // a handful of walkers per call
     d.n_devices = 1;
     d.devices = &device;
     d.max_batch = 0;

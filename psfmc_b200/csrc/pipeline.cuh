@@ -84,8 +84,10 @@ inline bool frame_supported(int H, int W, int psf_h, int psf_w) {
   return padded_length(H, psf_h) <= 1024 && padded_length(W, psf_w) <= 1024;
 }
 
+// low_latency: plans for batches of a few walkers (the float64 rescue engine): many
+// small CTAs per walker instead of few large ones
 inline StagedPlan make_staged_plan(int H, int W, int n_components, size_t sizeof_real,
-                                   double chunk_mbytes) {
+                                   double chunk_mbytes, bool low_latency = false) {
   StagedPlan p;
   p.fr.H = H;
   p.fr.W = W;
@@ -97,7 +99,7 @@ inline StagedPlan make_staged_plan(int H, int W, int n_components, size_t sizeof
   p.fr.padded = 0;
   p.fr.fy_hi = p.fr.fx_hi = -1;
   p.fr.fy_lo = p.fr.fx_lo = 1 << 30;
-  int rb = 2048 / W;
+  int rb = (low_latency ? 256 : 2048) / W;
   if (rb < 1) rb = 1;
   if (rb > H) rb = H;
   p.RB = rb;
@@ -105,7 +107,7 @@ inline StagedPlan make_staged_plan(int H, int W, int n_components, size_t sizeof
   p.threads_rows = rb * (W / 8);
   // columns per CTA: at most 2048/H, chosen to minimise padding of the 2*Wc columns
   int ncol = 2 * p.fr.Wc;
-  int cbmax = 2048 / H;
+  int cbmax = (low_latency ? 256 : 2048) / H;
   if (cbmax < 1) cbmax = 1;
   int best = cbmax, best_waste = 1 << 30;
   for (int cb = cbmax; cb >= (cbmax + 1) / 2 && cb >= 1; --cb) {
@@ -138,9 +140,10 @@ inline int kernel_origin(int n, int psf_n) { return n / 2 - (n - psf_n) / 2; }
 
 // Plan for an observation frame Hr x Wr that is not a power of two (see Frame).
 inline StagedPlan make_padded_plan(int Hr, int Wr, int psf_h, int psf_w, int n_components,
-                                   size_t sizeof_real, double chunk_mbytes) {
+                                   size_t sizeof_real, double chunk_mbytes,
+                                   bool low_latency = false) {
   StagedPlan p = make_staged_plan(padded_length(Hr, psf_h), padded_length(Wr, psf_w),
-                                  n_components, sizeof_real, chunk_mbytes);
+                                  n_components, sizeof_real, chunk_mbytes, low_latency);
   p.fr.Hr = Hr;
   p.fr.Wr = Wr;
   p.fr.padded = 1;
