@@ -235,15 +235,17 @@ struct RowRole {
 };
 
 // render + forward row transform + real-pair split of row batch `it` of walker b
+// (rc0 / der0: the walker's constants, STAGED = in shared memory, see fused_render16)
+template <bool STAGED>
 __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_addr_t tile,
                                                    const RowRole &R, smem_addr_t twl,
-                                                   long long b, int it, float wsc) {
+                                                   const float *rc0, const double *der0,
+                                                   int it, float wsc) {
   const int y = it * 64 + R.w * 4 + R.rr;
   const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
   {
     cplx<float> v[16];
-    fused_render16<8, false>(P, P.rconst + b * P.ncomp * PSFMC_RC_STRIDE,
-                             P.derived + b * P.ncomp * PSFMC_DERIVED_STRIDE, y, R.l, wsc, v);
+    fused_render16<8, STAGED>(P, rc0, der0, y, R.l, wsc, v);
     dft16<false>(v);
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * lds64(twl + 64 * k1);
@@ -415,6 +417,20 @@ fused_lnlike_kernel(const FusedParams P) {
     tw_s[tid][1] = c_tw128[ll * 16 + k1][1];
   }
   const smem_addr_t twl = smem_base(reinterpret_cast<unsigned char *>(&tw_s[0][0])) + 8u * R.l;
+  // constants of the walker the next forward pass renders, staged one walker ahead
+  // (during the column passes) so that the render does not wait for L2
+  __shared__ __align__(16) float rc_s[PSFMC_MAX_COMPONENTS * PSFMC_RC_STRIDE];
+  __shared__ double der_s[PSFMC_MAX_COMPONENTS * PSFMC_DERIVED_STRIDE];
+  __shared__ float wsc_s;
+  auto stage_params = [&](long long bs) {
+    if (bs >= P.n_batch) return;
+    if (tid < P.ncomp * PSFMC_RC_STRIDE)
+      rc_s[tid] = __ldg(P.rconst + bs * P.ncomp * PSFMC_RC_STRIDE + tid);
+    for (int k = tid; k < P.ncomp * PSFMC_DERIVED_STRIDE; k += PSFMC_FUSED_THREADS)
+      der_s[k] = __ldg(P.derived + bs * P.ncomp * PSFMC_DERIVED_STRIDE + k);
+    if (tid == PSFMC_FUSED_THREADS - 1) wsc_s = (float)P.wscale[bs];
+  };
+  stage_params(blockIdx.x);
   __syncthreads();
 
   // column-pass role: column c, two of the eight n2 residues. The four warps of a
@@ -454,6 +470,8 @@ fused_lnlike_kernel(const FusedParams P) {
     if (cur) {
 
     __syncthreads();
+    // every warp is past the forward rows of walker b: stage walker b + grid
+    stage_params(b + gridDim.x);
 
     // ------------------------------------------------- columns: radix-16 --
     // both residues n2 = m and m + 4 of this thread in flight at once (ILP)
@@ -572,7 +590,7 @@ fused_lnlike_kernel(const FusedParams P) {
     // ------ rows: inverse + chi-square of walker b, render + forward of the next --
     const long long bn = b + gridDim.x;
     const bool has_next = bn < P.n_batch;
-    const float wsc_next = has_next ? (float)P.wscale[bn] : 0.0f;
+    const float wsc_next = has_next ? wsc_s : 0.0f;
     double acc = 0.0;
 #pragma unroll 1
     for (int step = 0; step < 4; ++step) {
@@ -582,7 +600,7 @@ fused_lnlike_kernel(const FusedParams P) {
       if (!fwd) {
         if (cur) acc += fused_rows_inverse<true>(P, tile, R, twl, it, unscale);
       } else if (has_next) {
-        fused_rows_forward(P, tile, R, twl, bn, it, wsc_next);
+        fused_rows_forward<true>(P, tile, R, twl, rc_s, der_s, it, wsc_next);
       }
       if (cur && ((interleave && step == 2) || (!interleave && step == 1))) {
         // both inverse batches of this warp are done: float64 reduction. Warp
@@ -798,7 +816,10 @@ fused_lnlike_kernel_wide(const FusedParams P) {
     const long long bn = b + gridDim.x;
     if (bn < P.n_batch) {
       const RowRole R = make_row_role(opaque_tid());
-      fused_rows_forward(P, tile, R, tw_base + 8u * R.l, bn, 0, (float)P.wscale[bn]);
+      fused_rows_forward<false>(P, tile, R, tw_base + 8u * R.l,
+                                P.rconst + bn * P.ncomp * PSFMC_RC_STRIDE,
+                                P.derived + bn * P.ncomp * PSFMC_DERIVED_STRIDE, 0,
+                                (float)P.wscale[bn]);
     }
   }
 }
