@@ -392,3 +392,31 @@ def check_nan_propagation(library, monkeypatch):
             got = model.log_likelihood_batch(rows)
             assert np.isfinite(got[0])
             assert np.all(got[1:] == -np.inf), (staged, precision, got)
+
+
+def check_cropped_golden(library, tag):
+    """The engine on a frame that is not a power of two against the REFERENCE's lnL
+    (golden vectors of the cropped J0005-0006 frames, mode M3)."""
+    case = load_golden('c1_cropped_golden.json')['cases'][tag]
+    from psfmc_b200 import MultiComponentModel, fitsio
+    from psfmc_b200.components import Configuration
+    from psfmc_b200.model_parser import component_list_from_file
+    jdir = os.path.join(GOLDEN, 'j0005')
+    thetas = np.array(case['theta'])
+    expect = np.array(case['lnl']['M3'])
+    models = {}
+    for precision in ('fp64', 'fp32'):
+        comps = component_list_from_file(os.path.join(GOLDEN, case['model_file']))
+        old = [c for c in comps if isinstance(c, Configuration)][0]
+        obs = fitsio.getdata(os.path.join(jdir, 'sci_{}.fits'.format(tag))).astype(np.float64)
+        ivm = fitsio.getdata(os.path.join(jdir, 'ivm_{}.fits'.format(tag))).astype(np.float64)
+        mask = fitsio.getdata(os.path.join(jdir, 'mask_{}.fits'.format(tag))) != 0
+        config = Configuration(obs, ivm, [os.path.join(jdir, 'sci_psf.fits')],
+                               [os.path.join(jdir, 'ivm_psf.fits')], mask_file=mask,
+                               mag_zeropoint=old.mag_zeropoint)
+        models[precision] = MultiComponentModel([config] + [c for c in comps if c is not old],
+                                                precision=precision, library=library)
+    assert list(models['fp64'].engine.shape) == case['setup']['shape']
+    assert_lnl_close(models['fp64'].log_likelihood_batch(thetas), expect, 'fp64')
+    assert_lnl_close(models['fp32'].log_likelihood_batch(thetas), expect, 'fp32',
+                     fp32_bounds(models['fp32'], thetas))

@@ -10,7 +10,9 @@ Outputs (all committed):
   galfit/ivm_const.fits, galfit/psf_delta.fits, galfit/psfivm_delta.fits,
   galfit/model_n*.py                          C2 single-Sersic models on the
                                               reference's GALFIT fixtures
-  c1_golden.json, c1_2psf_golden.json, c2_golden.json
+  j0005/{sci,ivm,mask}_crop*.fits, j0005/model_c1_crop*.py
+                                              C1 cropped to 100 x 100 and 75 x 100
+  c1_golden.json, c1_2psf_golden.json, c1_cropped_golden.json, c2_golden.json
       theta vectors, the reference's lnL in precision modes M1/M2/M3 (SURVEY.md
       section 8c), its lnprior, setup checksums and sampled image pixels
   pointsource_golden.json                     the reference's own known-answer
@@ -259,6 +261,66 @@ def main():
     c1b['sample_px'] = sample_px
     c1b['model_file'] = 'j0005/model_c1_2psf.py'
     dump('c1_2psf_golden.json', c1b)
+
+    # ---- C1 cropped to frames that are not powers of two ------------------------
+    # (the reference convolves circularly at the image size, whatever it is:
+    # psfMC/utils.py:25-32; odd heights work, odd widths do not, models.py:276)
+    crops = {'crop100': (slice(14, 114), slice(14, 114)),      # 100 x 100
+             'crop75x100': (slice(30, 105), slice(10, 110))}   # 75 x 100 (odd height)
+    cropped = {'cases': {}}
+    for tag, (rows, cols) in crops.items():
+        obs, ivm, exclude, psfs, ivms, zp = raw_inputs_j0005(False)
+        y0, x0 = rows.start, cols.start
+        fitsio.writeto(os.path.join(HERE, 'j0005', 'sci_{}.fits'.format(tag)),
+                       np.ascontiguousarray(obs[rows, cols]))
+        fitsio.writeto(os.path.join(HERE, 'j0005', 'ivm_{}.fits'.format(tag)),
+                       np.ascontiguousarray(ivm[rows, cols]))
+        fitsio.writeto(os.path.join(HERE, 'j0005', 'mask_{}.fits'.format(tag)),
+                       np.ascontiguousarray(exclude[rows, cols]).astype(np.int16))
+        mfile = os.path.join(HERE, 'j0005', 'model_c1_{}.py'.format(tag))
+        with open(mfile, 'w') as fobj:
+            fobj.write(
+                "# C1 (model_c1.py) on the J0005-0006 frames cropped to rows {r0}:{r1},\n"
+                "# columns {c0}:{c1} -- a frame that is not a power of two; the mask is\n"
+                "# the cropped region mask as a FITS image (nonzero = excluded).\n"
+                "from numpy import array\n\n"
+                "qso_mag = 20.66\n"
+                "qso_xy, qso_box = array((64.5 - {c0}, 64.5 - {r0})), array((8, 8))\n"
+                "blob_xy, blob_box = array((46 - {c0}, 85.6 - {r0})), array((5, 5))\n\n"
+                "Configuration(obs_file='sci_{t}.fits', obsivm_file='ivm_{t}.fits',\n"
+                "              psf_files='sci_psf.fits', psfivm_files='ivm_psf.fits',\n"
+                "              mask_file='mask_{t}.fits', mag_zeropoint=25.9463)\n"
+                "Sky(adu=Normal(loc=0, scale=0.01))\n"
+                "PointSource(xy=Uniform(loc=qso_xy - qso_box, scale=2 * qso_box),\n"
+                "            mag=Uniform(loc=qso_mag - 0.2, scale=0.2 + 1.5))\n"
+                "Sersic(xy=Uniform(loc=qso_xy - qso_box, scale=2 * qso_box),\n"
+                "       mag=Uniform(loc=qso_mag, scale=27.5 - qso_mag),\n"
+                "       reff=Uniform(loc=2.0, scale=10.0), reff_b=Uniform(loc=2.0, scale=10.0),\n"
+                "       index=WeibullMinimum(c=1.5, scale=4),\n"
+                "       angle=Uniform(loc=0, scale=180), angle_degrees=True)\n"
+                "Sersic(xy=Uniform(loc=blob_xy - blob_box, scale=2 * blob_box),\n"
+                "       mag=Uniform(loc=23.5, scale=2.0),\n"
+                "       reff=Uniform(loc=2.0, scale=6.0), reff_b=Uniform(loc=2.0, scale=6.0),\n"
+                "       index=WeibullMinimum(c=1.5, scale=4),\n"
+                "       angle=Uniform(loc=0, scale=180), angle_degrees=True)\n".format(
+                    r0=rows.start, r1=rows.stop, c0=cols.start, c1=cols.stop, t=tag))
+        draws = prior_draws(mfile, 10, seed=4242 + y0)
+        thetas = [list(map(float, row)) for row in draws]
+        # a bright point source next to the frame corner: its PSF wings wrap around
+        thetas[0][1:4] = [19.5, 1.25, 2.5]
+        thetas[1][1:4] = [19.5, (cols.stop - cols.start) - 1.75,
+                          (rows.stop - rows.start) - 2.25]
+        npx = (rows.stop - rows.start) * (cols.stop - cols.start)
+        crop_px = [0, 99, 100, 1234, npx // 2, npx // 2 + 37, npx - 101, npx - 1]
+        raw = (np.ascontiguousarray(obs[rows, cols]), np.ascontiguousarray(ivm[rows, cols]),
+               np.ascontiguousarray(exclude[rows, cols]), psfs, ivms, zp)
+        print('C1/{}:'.format(tag), len(thetas), 'thetas')
+        case = pin_and_collect(mfile, raw, thetas, crop_px)
+        case['theta'] = thetas
+        case['sample_px'] = crop_px
+        case['model_file'] = 'j0005/model_c1_{}.py'.format(tag)
+        cropped['cases'][tag] = case
+    dump('c1_cropped_golden.json', cropped)
 
     # ---- C2: GALFIT single-Sersic sweep ------------------------------------------
     gdir = os.path.join(HERE, 'galfit')

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import (ARBITRARY_FRAMES, assert_lnl_close, check_arbitrary_frame,
-                      check_cluster_path_256, check_nan_propagation, check_fp64_rescue,
+                      check_cluster_path_256, check_cropped_golden, check_nan_propagation, check_fp64_rescue,
                       check_near_centre_walkers, mixed_model_128, fp32_bounds, load_golden, model_from_file,
                       oracle_from_model)
 
@@ -265,3 +265,8 @@ def test_emu_arbitrary_frame_sizes(emu_library, dims):
 
 def test_emu_nan_parameters_give_minus_inf(emu_library, monkeypatch):
     check_nan_propagation(emu_library, monkeypatch)
+
+
+@pytest.mark.parametrize('tag', ['crop100', 'crop75x100'])
+def test_emu_cropped_frames_match_the_reference(emu_library, tag):
+    check_cropped_golden(emu_library, tag)

@@ -403,3 +403,10 @@ def test_gpu_arbitrary_frame_sizes(cuda_library, dims):
 def test_gpu_nan_parameters_give_minus_inf(cuda_library, monkeypatch):
     from conftest import check_nan_propagation
     check_nan_propagation(cuda_library, monkeypatch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', ['crop100', 'crop75x100'])
+def test_gpu_cropped_frames_match_the_reference(cuda_library, tag):
+    from conftest import check_cropped_golden
+    check_cropped_golden(cuda_library, tag)

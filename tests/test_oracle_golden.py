@@ -179,3 +179,34 @@ def test_live_against_reference_when_present():
                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                           universal_newlines=True, timeout=300)
     assert proc.returncode == 0 and 'LIVE-OK' in proc.stdout, proc.stdout
+
+
+@pytest.mark.parametrize('tag', ['crop100', 'crop75x100'])
+@pytest.mark.parametrize('mode', MODES)
+def test_cropped_frames_oracle_reproduces_reference_bitwise(tag, mode):
+    """Frames that are not powers of two (100 x 100, 75 x 100): the reference convolves
+    circularly at the image size; golden vectors from the unmodified reference."""
+    case = load_golden('c1_cropped_golden.json')['cases'][tag]
+    program, psf_slot, ndim, _ = _program(case['model_file'])
+    jdir = os.path.join(GOLDEN, 'j0005')
+    obs = fitsio.getdata(os.path.join(jdir, 'sci_{}.fits'.format(tag)))
+    ivm = fitsio.getdata(os.path.join(jdir, 'ivm_{}.fits'.format(tag)))
+    mask = fitsio.getdata(os.path.join(jdir, 'mask_{}.fits'.format(tag))) != 0
+    assert list(obs.shape) == case['setup']['shape']
+    if mode == 'M3':
+        obs, ivm = obs.astype(np.float64), ivm.astype(np.float64)
+    psfs = [fitsio.getdata(os.path.join(jdir, 'sci_psf.fits'))]
+    ivms = [fitsio.getdata(os.path.join(jdir, 'ivm_psf.fits'))]
+    oracle = orc.build_from_raw_inputs(obs, ivm, mask, psfs, ivms, 25.9463, program,
+                                       psf_slot, fft_upcast=(mode != 'M1'))
+    good = np.flatnonzero(~oracle.bad_px)
+    assert len(good) == case['setup']['n_good']
+    assert int(good.sum()) == case['setup']['good_index_sum']
+    thetas = np.array(case['theta'])
+    px = np.array(case['sample_px'])
+    for row in range(len(thetas)):
+        assert oracle.lnlike(thetas[row]) == case['lnl'][mode][row], (mode, row)
+        if row < 3:
+            imgs = oracle.images(thetas[row], with_point_source_subtracted=False)
+            for key, want in case['pixels'][mode][row].items():
+                assert _same(imgs[key].ravel()[px], want), (mode, row, key)
