@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """
 Ensemble-size sweep (BASELINE.json configs[4]): lnL evaluations/s for ensembles of
-200 ... 65536 walkers on the 128^2 (C1 model) and 512^2 (C4 synthetic) frames, one GPU,
+200 ... 65536 walkers on the 128^2 (C1 model), 256^2 (C3) and 512^2 (C4) frames, one GPU,
 device-resident (CUDA events) and end to end through the C ABI with host buffers.
 Each emcee iteration is two half-ensemble batches, as in bench.py.
 
@@ -71,14 +71,15 @@ def measure(workload, walkers, seconds=1.0):
     return {'workload': workload, 'frame': list(engine.shape), 'walkers': walkers,
             'batch_per_launch': half, 'steps': steps,
             'device_evals_per_s': round(dev_rate, 1), 'e2e_evals_per_s': round(host_rate, 1),
-            'engine_path': 'fused' if info['path'] == 1 else 'staged'}
+            'engine_path': {1: 'fused', 2: 'fused-cluster4'}.get(info['path'], 'staged'),
+            'fp64_rescued_walkers': int(info['rescued_total'])}
 
 
 def main():
     import __graft_entry__ as entry
     entry.build()
     rows = []
-    for workload in ('c1', 'c4'):
+    for workload in ('c1', 'c3', 'c4'):
         for walkers in (200, 512, 1024, 4096, 16384, 65536):
             rows.append(measure(workload, walkers))
             print(json.dumps(rows[-1]), file=sys.stderr)
