@@ -853,7 +853,7 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       break;
 #ifndef PSFMC_NO_FUSED
     if (i == 0) {
-      eng->path = (direct && fused_path_available<T>(eng->plan, eng->prog_h)) ? 1 : 0;
+      eng->path = fused_path_available<T>(eng->plan, eng->prog_h) ? 1 : 0;
       if (direct && cluster_path_available<T>(eng->plan)) eng->path = 2;
       const char *force = getenv("PSFMC_FORCE_STAGED");
       if (force && force[0] == '1') eng->path = 0;
@@ -876,10 +876,10 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       std::vector<double> vs(d->n_psf);
       for (int k = 0; k < d->n_psf; ++k) vs[k] = 1.0 / vscale_inv[k];
       fused_spectrum_layout(spec64.data(), d->n_psf, vs.data(), fspec.data(), fspecx.data());
-      std::vector<float2> ow(npx);
+      std::vector<float2> ow(npx);   // over the transform frame (padding: excluded)
       for (size_t e = 0; e < npx; ++e) {
-        float v = fabsf((float)d->obs_var[e]);
-        ow[e].x = (float)d->obs_data[e];
+        float v = fabsf((float)ovar[e]);
+        ow[e].x = (float)obs[e];
         ow[e].y = bad[e] ? -v : v;
       }
       if ((rc = upload(&ds.fspec, fspec)) || (rc = upload(&ds.fspecx, fspecx)) ||

@@ -56,6 +56,11 @@ struct FusedParams {
   signed char kind[PSFMC_MAX_COMPONENTS];
 };
 
+// padded frames (see Frame in common.cuh): observation frame and fold bounds
+struct FoldParams {
+  int Hr, Wr, fy_hi, fy_lo, fx_hi, fx_lo;
+};
+
 __device__ __forceinline__ void group_barrier(int id, int nthreads) {
 #ifdef PSFMC_EMU
   emu::named_barrier(id, nthreads);
@@ -236,16 +241,29 @@ struct RowRole {
 
 // render + forward row transform + real-pair split of row batch `it` of walker b
 // (rc0 / der0: the walker's constants, STAGED = in shared memory, see fused_render16)
-template <bool STAGED>
+// PADDED: the observation frame is P.Hr x P.Wr in the corner of the 128 x 128 transform
+// frame; nothing is rendered outside it.
+template <bool STAGED, bool PADDED = false>
 __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_addr_t tile,
                                                    const RowRole &R, smem_addr_t twl,
                                                    const float *rc0, const double *der0,
-                                                   int it, float wsc) {
+                                                   int it, float wsc,
+                                                   const FoldParams *F = nullptr) {
   const int y = it * 64 + R.w * 4 + R.rr;
   const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
   {
     cplx<float> v[16];
-    fused_render16<8, STAGED>(P, rc0, der0, y, R.l, wsc, v);
+    if (!PADDED || y < F->Hr) {
+      fused_render16<8, STAGED>(P, rc0, der0, y, R.l, wsc, v);
+      if (PADDED) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (R.l + 8 * j >= F->Wr) v[j] = mk<float>(0.0f, 0.0f);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = mk<float>(0.0f, 0.0f);
+    }
     dft16<false>(v);
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * lds64(twl + 64 * k1);
@@ -296,10 +314,11 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
 // Hermitian rebuild + inverse row transform + chi-square terms of row batch `it`;
 // returns this thread's float64 partial sum over its 16 pixels. PREFETCH: issue the
 // observation loads before the transform (needs 32 registers for its duration).
-template <bool PREFETCH>
+template <bool PREFETCH, bool PADDED = false>
 __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_addr_t tile,
                                                      const RowRole &R, smem_addr_t twl,
-                                                     int it, float unscale) {
+                                                     int it, float unscale,
+                                                     const FoldParams *F = nullptr) {
   const int y = it * 64 + R.w * 4 + R.rr;
   const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
   const bool l0 = R.l0;
@@ -366,6 +385,23 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
 #pragma unroll
   for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], lds64(twl + 64 * k1));
   dft16<true>(v);           // v[j] = (convolved model, scaled model variance)
+  if (PADDED) {
+    // fold the linear convolution back modulo Wr (see Frame): through the row's own
+    // 1 KB of the tile (free once every lane has taken its exchange values), pixel x at
+    // position x
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sts64(rb + 8u * (R.l + 8 * j), v[j]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int x = R.l + 8 * j;
+      if (x <= F->fx_hi) v[j] = v[j] + lds64(rb + 8u * (x + F->Wr));
+      if (x >= F->fx_lo && x < F->Wr)
+        v[j] = v[j] + lds64(rb + 8u * (PSFMC_FUSED_N + x - F->Wr));
+    }
+    __syncwarp();
+  }
   if (!PREFETCH) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
@@ -381,8 +417,9 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   return acc;
 }
 
+template <bool PADDED>
 __global__ void __launch_bounds__(PSFMC_FUSED_THREADS, 1)
-fused_lnlike_kernel(const FusedParams P) {
+fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   PSFMC_DYN_SMEM(smem_raw);
   const smem_addr_t tile = smem_base(smem_raw);
   __shared__ double red_s[PSFMC_FUSED_THREADS / 32];
@@ -585,6 +622,29 @@ fused_lnlike_kernel(const FusedParams P) {
       for (int j = 0; j < 16; ++j) sts64(cb1 + 8 * j * ROWB, v1[j]);
     }
     __syncthreads();
+    if (PADDED) {
+      // fold the linear convolution back modulo Hr (see Frame): row p receives rows
+      // p + Hr (p <= fy_hi) and 128 + p - Hr (p >= fy_lo); the sources lie at or beyond
+      // row Hr, the targets below it. Column c of row y sits at c ^ (8 * (y & 1)).
+      for (int e = tid; e < F.Hr * N; e += PSFMC_FUSED_THREADS) {
+        const int p = e >> 7, cc = e & (N - 1);
+        const bool hi = p <= F.fy_hi, lo = p >= F.fy_lo;
+        if (hi || lo) {
+          const smem_addr_t dst = tile + (unsigned)p * ROWB + 8u * (cc ^ (8 * (p & 1)));
+          cplx<float> acc = lds64(dst);
+          if (hi) {
+            const int q = p + F.Hr;
+            acc = acc + lds64(tile + (unsigned)q * ROWB + 8u * (cc ^ (8 * (q & 1))));
+          }
+          if (lo) {
+            const int q = N + p - F.Hr;
+            acc = acc + lds64(tile + (unsigned)q * ROWB + 8u * (cc ^ (8 * (q & 1))));
+          }
+          sts64(dst, acc);
+        }
+      }
+      __syncthreads();
+    }
     }  // if (cur)
 
     // ------ rows: inverse + chi-square of walker b, render + forward of the next --
@@ -598,9 +658,9 @@ fused_lnlike_kernel(const FusedParams P) {
       const bool fwd = interleave ? (step & 1) : (step >= 2);
       const int it = interleave ? (step >> 1) : (step & 1);
       if (!fwd) {
-        if (cur) acc += fused_rows_inverse<true>(P, tile, R, twl, it, unscale);
+        if (cur) acc += fused_rows_inverse<true, PADDED>(P, tile, R, twl, it, unscale, &F);
       } else if (has_next) {
-        fused_rows_forward<true>(P, tile, R, twl, rc_s, der_s, it, wsc_next);
+        fused_rows_forward<true, PADDED>(P, tile, R, twl, rc_s, der_s, it, wsc_next, &F);
       }
       if (cur && ((interleave && step == 2) || (!interleave && step == 1))) {
         // both inverse batches of this warp are done: float64 reduction. Warp
@@ -826,6 +886,9 @@ fused_lnlike_kernel_wide(const FusedParams P) {
 
 // -------------------------------------------------------------- host side --
 
+// (the TRANSFORM frame must be 128 x 128: the observation frame itself, or any smaller
+// frame whose padded transform frame is -- every frame with height + psf_height - 1 <=
+// 128 and width + psf_width - 1 <= 128 that is not a power of two)
 template <typename T>
 inline bool fused_path_available(const StagedPlan &plan, const Program &) {
   return sizeof(T) == 4 && plan.fr.H == PSFMC_FUSED_N && plan.fr.W == PSFMC_FUSED_N;
@@ -834,7 +897,11 @@ inline bool fused_path_available(const StagedPlan &plan, const Program &) {
 template <typename T>
 inline int fused_prepare_device(const StagedPlan &) {
 #ifndef PSFMC_EMU
-  if (cudaFuncSetAttribute(fused_lnlike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(fused_lnlike_kernel<false>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           PSFMC_FUSED_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(fused_lnlike_kernel<true>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                            PSFMC_FUSED_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(fused_lnlike_kernel_wide,
                            cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -904,9 +971,16 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
                                cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr) {
   if (n_batch <= 0) return 0;
   const int ncomp = prog_h.n_components;
-  launch_prepare(*buf.prog_host, theta, n_batch, ld, plan.fr.H, plan.fr.W, ncomp, buf.derived, buf.psf_sel,
-                 buf.wscale, fb.rconst, stream);
+  launch_prepare(*buf.prog_host, theta, n_batch, ld, plan.fr.Hr, plan.fr.Wr, ncomp, buf.derived,
+                 buf.psf_sel, buf.wscale, fb.rconst, stream);
   FusedParams P;
+  FoldParams F;
+  F.Hr = plan.fr.Hr;
+  F.Wr = plan.fr.Wr;
+  F.fy_hi = plan.fr.fy_hi;
+  F.fy_lo = plan.fr.fy_lo;
+  F.fx_hi = plan.fr.fx_hi;
+  F.fx_lo = plan.fr.fx_lo;
   P.rconst = fb.rconst;
   P.derived = buf.derived;
   P.wscale = buf.wscale;
@@ -922,12 +996,15 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
     P.kind[c] = (signed char)(c < ncomp ? prog_h.kind[c] : 0);
   unsigned grid = (unsigned)(n_batch < fb.n_sms ? n_batch : fb.n_sms);
   if (ev_begin) cudaEventRecord(ev_begin, stream);
-  if (fb.wide)
+  if (fb.wide && !plan.fr.padded)
     launch_kernel(fused_lnlike_kernel_wide, dim3(grid), dim3(PSFMC_FUSED_THREADS_WIDE),
                   (size_t)PSFMC_FUSED_SMEM, stream, P);
+  else if (plan.fr.padded)
+    launch_kernel(fused_lnlike_kernel<true>, dim3(grid), dim3(PSFMC_FUSED_THREADS),
+                  (size_t)PSFMC_FUSED_SMEM, stream, P, F);
   else
-    launch_kernel(fused_lnlike_kernel, dim3(grid), dim3(PSFMC_FUSED_THREADS),
-                  (size_t)PSFMC_FUSED_SMEM, stream, P);
+    launch_kernel(fused_lnlike_kernel<false>, dim3(grid), dim3(PSFMC_FUSED_THREADS),
+                  (size_t)PSFMC_FUSED_SMEM, stream, P, F);
   if (ev_end) cudaEventRecord(ev_end, stream);
   return 2;
 }

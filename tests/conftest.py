@@ -303,8 +303,10 @@ def check_cluster_path_256(library, n_walkers, monkeypatch=None):
     return got
 
 
+# (the third, sixth and seventh have a 128 x 128 transform frame: fused kernel, padded)
 ARBITRARY_FRAMES = ((100, 100, 64, 64), (75, 100, 31, 17), (50, 36, 21, 36),
-                    (128, 100, 32, 32), (33, 64, 8, 9))
+                    (128, 100, 32, 32), (33, 64, 8, 9), (100, 100, 25, 25),
+                    (65, 64, 64, 64))
 
 
 def arbitrary_frame_model(height, width, psf_h, psf_w, precision, library=None):

@@ -258,7 +258,7 @@ def test_emu_cluster_kernel_256(emu_library, monkeypatch):
     check_cluster_path_256(emu_library, 5, monkeypatch)
 
 
-@pytest.mark.parametrize('dims', ARBITRARY_FRAMES[:3] + ARBITRARY_FRAMES[4:])
+@pytest.mark.parametrize('dims', ARBITRARY_FRAMES[:3] + ARBITRARY_FRAMES[4:6])
 def test_emu_arbitrary_frame_sizes(emu_library, dims):
     check_arbitrary_frame(emu_library, dims, n_walkers=2)
 
