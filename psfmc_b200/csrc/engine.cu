@@ -854,7 +854,7 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
 #ifndef PSFMC_NO_FUSED
     if (i == 0) {
       eng->path = fused_path_available<T>(eng->plan, eng->prog_h) ? 1 : 0;
-      if (direct && cluster_path_available<T>(eng->plan)) eng->path = 2;
+      if (cluster_path_available<T>(eng->plan)) eng->path = 2;
       const char *force = getenv("PSFMC_FORCE_STAGED");
       if (force && force[0] == '1') eng->path = 0;
       const char *variant = getenv("PSFMC_FUSED_VARIANT");
@@ -903,9 +903,9 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       for (int k = 0; k < d->n_psf; ++k) vs[k] = 1.0 / vscale_inv[k];
       cluster_spectrum_layout(spec64.data(), d->n_psf, vs.data(), cspec.data(), cspecx.data());
       std::vector<float2> ow(npx), ctw(256);
-      for (size_t e = 0; e < npx; ++e) {
-        float v = fabsf((float)d->obs_var[e]);
-        ow[e].x = (float)d->obs_data[e];
+      for (size_t e = 0; e < npx; ++e) {   // over the transform frame (padding: excluded)
+        float v = fabsf((float)ovar[e]);
+        ow[e].x = (float)obs[e];
         ow[e].y = bad[e] ? -v : v;
       }
       cluster_twiddles(ctw.data());

@@ -141,9 +141,8 @@ struct ClRowRole {
 // Tile address of element kx = l + 16 k2 of a row whose four 64-slot blocks start at
 // base[q] (C layout of the column owners for the pushes, R layout of the local tile
 // for the gathers): ra[q] = base[q] + 8 l, rm[q] = base[q] - 8 l.
-template <int K2>
-__device__ __forceinline__ smem_addr_t cl_row_addr(const smem_addr_t *ra, const smem_addr_t *rm,
-                                                   bool l0) {
+template <int K2, typename A = smem_addr_t>
+__device__ __forceinline__ A cl_row_addr(const A *ra, const A *rm, bool l0) {
   if (K2 < 8) return ra[K2 >> 1] + 128 * (K2 & 1);          // kx < 128: slot 16 (k2 & 1) + l
   constexpr int m = 15 - K2;                                 // kx' = 256 - kx = 16 m + 16 - l
   if ((m & 1) == 0) return rm[m >> 1] + 8 * 48;              // slot 48 - l
@@ -192,6 +191,15 @@ struct ClRowLoop {
     u[K2] = lds64(cl_row_addr<K2>(ra, rm, l0));
     ClRowLoop<K2 + 1>::gather(ra, rm, l0, u);
   }
+  // u += the same row elements of a row in ANOTHER CTA's tile (generic mapped pointers)
+  static __device__ __forceinline__ void gather_add(unsigned char *const *ga,
+                                                    unsigned char *const *gm, bool l0,
+                                                    cplx<float> *u) {
+    const float2 v = *reinterpret_cast<const float2 *>(
+        cl_row_addr<K2, unsigned char *>(ga, gm, l0));
+    u[K2] = u[K2] + mk<float>(v.x, v.y);
+    ClRowLoop<K2 + 1>::gather_add(ga, gm, l0, u);
+  }
 };
 template <>
 struct ClRowLoop<16> {
@@ -200,15 +208,30 @@ struct ClRowLoop<16> {
                                               const cplx<float> *) {}
   static __device__ __forceinline__ void gather(const smem_addr_t *, const smem_addr_t *, bool,
                                                 cplx<float> *) {}
+  static __device__ __forceinline__ void gather_add(unsigned char *const *,
+                                                    unsigned char *const *, bool,
+                                                    cplx<float> *) {}
 };
 
 // render + forward row transform of row batch `it` of walker b; u[k2] = Z[y][l + 16 k2]
+template <bool PADDED>
 __device__ __forceinline__ void cl_rows_forward(const FusedParams &P, const ClRowRole &R,
                                                 const float *rc_s, const double *der_s, int y,
-                                                float wsc, cplx<float> *u) {
+                                                float wsc, cplx<float> *u,
+                                                const FoldParams &F) {
   {
     cplx<float> v[16];
-    fused_render16<16, true>(P, rc_s, der_s, y, R.l, wsc, v);
+    if (!PADDED || y < F.Hr) {
+      fused_render16<16, true>(P, rc_s, der_s, y, R.l, wsc, v);
+      if (PADDED) {   // nothing is rendered outside the observation frame
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (R.l + 16 * j >= F.Wr) v[j] = mk<float>(0.0f, 0.0f);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = mk<float>(0.0f, 0.0f);
+    }
     dft16<false>(v);
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * lds64(R.twl + 128 * k1);
@@ -226,9 +249,10 @@ __device__ __forceinline__ void cl_rows_forward(const FusedParams &P, const ClRo
 
 // inverse row transform + chi-square terms of one row; u[k2] = Y[y][l + 16 k2] on entry.
 // Returns this thread's float64 partial sum over its 16 pixels.
+template <bool PADDED>
 __device__ __forceinline__ double cl_rows_inverse(const FusedParams &P, const ClRowRole &R,
                                                   int y, float unscale, cplx<float> *u,
-                                                  const float2 *o) {
+                                                  const float2 *o, const FoldParams &F) {
   dft16<true>(u);   // over k2 -> n2
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2)
@@ -242,6 +266,20 @@ __device__ __forceinline__ double cl_rows_inverse(const FusedParams &P, const Cl
 #pragma unroll
   for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], lds64(R.twl + 128 * k1));
   dft16<true>(v);   // v[j]: pixel x = l + 16 j = (convolved model, scaled model variance)
+  if (PADDED) {
+    // fold the linear convolution back modulo Wr (see Frame) through the row's exchange
+    // scratch (free: the barrier above), pixel x at position x
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sts64(R.xrow + 8u * (R.l + 16 * j), v[j]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int x = R.l + 16 * j;
+      if (x <= F.fx_hi) v[j] = v[j] + lds64(R.xrow + 8u * (x + F.Wr));
+      if (x >= F.fx_lo && x < F.Wr) v[j] = v[j] + lds64(R.xrow + 8u * (PSFMC_CL_N + x - F.Wr));
+    }
+    __syncwarp();
+  }
   double acc = 0.0;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -255,8 +293,9 @@ __device__ __forceinline__ double cl_rows_inverse(const FusedParams &P, const Cl
   return acc;
 }
 
+template <bool PADDED>
 __global__ void __launch_bounds__(PSFMC_CL_THREADS, 1)
-cluster256_lnlike_kernel(const ClusterParams CP) {
+cluster256_lnlike_kernel(const ClusterParams CP, const FoldParams F) {
   PSFMC_DYN_SMEM(smem_raw);
   const FusedParams &P = CP.f;
   const smem_addr_t tile = smem_base(smem_raw);
@@ -354,7 +393,7 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
       const int yl = yl0 + 32 * it;
       const int y = 64 * (int)rank + yl;
       cplx<float> u[16];
-      cl_rows_forward(P, R, rc_s, der_s, y, (float)wscale_b, u);
+      cl_rows_forward<PADDED>(P, R, rc_s, der_s, y, (float)wscale_b, u, F);
       if (it == 0 && pending >= 0) finish_pending();   // the other CTAs are done with
                                                        // the last walker's rows
       unsigned char *ga[PSFMC_CL_CTAS], *gm[PSFMC_CL_CTAS];
@@ -516,7 +555,29 @@ cluster256_lnlike_kernel(const ClusterParams CP) {
       }
       cplx<float> u[16];
       ClRowLoop<0>::gather(ra, rm, R.l0, u);
-      acc += cl_rows_inverse(P, R, y, unscale, u, o);
+      if (PADDED && y < F.Hr) {
+        // fold the linear convolution back modulo Hr (see Frame): row y also receives
+        // rows y + Hr and 256 + y - Hr, which other CTAs of the cluster own -- read
+        // straight from their tiles (final since the last cluster barrier, overwritten
+        // only after the next one)
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          const bool take = which == 0 ? (y <= F.fy_hi) : (y >= F.fy_lo);
+          if (!take) continue;
+          const int yq = which == 0 ? y + F.Hr : PSFMC_CL_N + y - F.Hr;
+          const int oq = yq >> 6;   // owner of row yq (selects keep mb[] in registers)
+          unsigned char *ob = oq == 0 ? mb[0] : oq == 1 ? mb[1] : oq == 2 ? mb[2] : mb[3];
+          unsigned char *ga[PSFMC_CL_CTAS], *gm[PSFMC_CL_CTAS];
+#pragma unroll
+          for (int q = 0; q < PSFMC_CL_CTAS; ++q) {
+            unsigned char *rowb = ob + 512 * (64 * q + (yq & 63));
+            ga[q] = rowb + R.lx;
+            gm[q] = rowb - R.lx;
+          }
+          ClRowLoop<0>::gather_add(ga, gm, R.l0, u);
+        }
+      }
+      acc += cl_rows_inverse<PADDED>(P, R, y, unscale, u, o, F);
     }
     // float64 reduction: warp shuffles; the last warp to arrive sums the 16 warp
     // partials in fixed order (deterministic) and delivers the CTA partial to CTA 0
@@ -601,7 +662,11 @@ inline int cluster_prepare_device(int *n_clusters_out) {
   *n_clusters_out = 2;
   return 0;
 #else
-  if (cudaFuncSetAttribute(cluster256_lnlike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(cluster256_lnlike_kernel<false>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           PSFMC_CL_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(cluster256_lnlike_kernel<true>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                            PSFMC_CL_SMEM) != cudaSuccess)
     return 1;
   cudaLaunchConfig_t cfg = {};
@@ -616,7 +681,8 @@ inline int cluster_prepare_device(int *n_clusters_out) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, cluster256_lnlike_kernel, &cfg) != cudaSuccess || n < 1)
+  if (cudaOccupancyMaxActiveClusters(&n, cluster256_lnlike_kernel<false>, &cfg) != cudaSuccess ||
+      n < 1)
     return 1;
   *n_clusters_out = n;
   return 0;
@@ -632,9 +698,16 @@ inline int launch_cluster_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
                                  cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr) {
   if (n_batch <= 0) return 0;
   const int ncomp = prog_h.n_components;
-  launch_prepare(*buf.prog_host, theta, n_batch, ld, plan.fr.H, plan.fr.W, ncomp, buf.derived,
+  launch_prepare(*buf.prog_host, theta, n_batch, ld, plan.fr.Hr, plan.fr.Wr, ncomp, buf.derived,
                  buf.psf_sel, buf.wscale, cb.rconst, stream);
   ClusterParams CP;
+  FoldParams F;
+  F.Hr = plan.fr.Hr;
+  F.Wr = plan.fr.Wr;
+  F.fy_hi = plan.fr.fy_hi;
+  F.fy_lo = plan.fr.fy_lo;
+  F.fx_hi = plan.fr.fx_hi;
+  F.fx_lo = plan.fr.fx_lo;
   FusedParams &P = CP.f;
   P.rconst = cb.rconst;
   P.derived = buf.derived;
@@ -654,8 +727,14 @@ inline int launch_cluster_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
   CP.tw = cb.tw;
   const unsigned nclus = (unsigned)(n_batch < cb.n_clusters ? n_batch : cb.n_clusters);
   if (ev_begin) cudaEventRecord(ev_begin, stream);
-  launch_kernel_cluster(cluster256_lnlike_kernel, dim3(nclus * PSFMC_CL_CTAS),
-                        dim3(PSFMC_CL_THREADS), (size_t)PSFMC_CL_SMEM, stream, PSFMC_CL_CTAS, CP);
+  if (plan.fr.padded)
+    launch_kernel_cluster(cluster256_lnlike_kernel<true>, dim3(nclus * PSFMC_CL_CTAS),
+                          dim3(PSFMC_CL_THREADS), (size_t)PSFMC_CL_SMEM, stream, PSFMC_CL_CTAS,
+                          CP, F);
+  else
+    launch_kernel_cluster(cluster256_lnlike_kernel<false>, dim3(nclus * PSFMC_CL_CTAS),
+                          dim3(PSFMC_CL_THREADS), (size_t)PSFMC_CL_SMEM, stream, PSFMC_CL_CTAS,
+                          CP, F);
   if (ev_end) cudaEventRecord(ev_end, stream);
   return 2;
 }

@@ -394,6 +394,7 @@ def test_gpu_cluster_kernel_256_properties(cuda_library):
 @pytest.mark.parametrize('dims', [(100, 100, 64, 64), (75, 100, 31, 17), (50, 36, 21, 36),
                                   (128, 100, 32, 32), (33, 64, 8, 9), (100, 100, 25, 25),
                                   (65, 64, 64, 64), (97, 120, 32, 9), (150, 150, 64, 64),
+                                  (150, 130, 31, 64), (193, 192, 64, 64),
                                   (301, 300, 65, 64), (600, 500, 101, 99)])
 def test_gpu_arbitrary_frame_sizes(cuda_library, dims):
     from conftest import check_arbitrary_frame
