@@ -393,7 +393,14 @@ cluster256_lnlike_kernel(const ClusterParams CP, const FoldParams F) {
       const int yl = yl0 + 32 * it;
       const int y = 64 * (int)rank + yl;
       cplx<float> u[16];
-      cl_rows_forward<PADDED>(P, R, rc_s, der_s, y, (float)wscale_b, u, F);
+      // (padded frames: a warp whose two rows lie outside the observation frame has
+      // nothing to render or transform -- it only delivers the zeros)
+      if (PADDED && y - R.rr >= F.Hr) {
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) u[k2] = mk<float>(0.0f, 0.0f);
+      } else {
+        cl_rows_forward<PADDED>(P, R, rc_s, der_s, y, (float)wscale_b, u, F);
+      }
       if (it == 0 && pending >= 0) finish_pending();   // the other CTAs are done with
                                                        // the last walker's rows
       unsigned char *ga[PSFMC_CL_CTAS], *gm[PSFMC_CL_CTAS];
@@ -541,6 +548,7 @@ cluster256_lnlike_kernel(const ClusterParams CP, const FoldParams F) {
     for (int it = 0; it < 2; ++it) {
       const int yl = yl0 + 32 * it;
       const int y = 64 * (int)rank + yl;
+      if (PADDED && y - R.rr >= F.Hr) continue;   // both rows of the warp are padding
       if (it) {
         const float2 *owr = P.ow + y * PSFMC_CL_N + R.l;
 #pragma unroll

@@ -251,6 +251,20 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
                                                    const FoldParams *F = nullptr) {
   const int y = it * 64 + R.w * 4 + R.rr;
   const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
+  if (PADDED && y - R.rr >= F->Hr) {
+    // all four rows of the warp lie outside the observation frame: their row spectra
+    // are zero (the tile still holds the previous walker's values there)
+    __syncwarp();
+    const cplx<float> zero = mk<float>(0.0f, 0.0f);
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      sts64(rb + R.fa + 8 * 16 * k2, zero);
+      sts64(rb + R.fa + 8 * (64 + 16 * k2), zero);
+      sts64(rb + R.fb + 8 * 16 * k2, zero);
+      sts64(rb + R.fb + 8 * (64 + 16 * k2), zero);
+    }
+    return;
+  }
   {
     cplx<float> v[16];
     if (!PADDED || y < F->Hr) {
@@ -320,6 +334,7 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
                                                      int it, float unscale,
                                                      const FoldParams *F = nullptr) {
   const int y = it * 64 + R.w * 4 + R.rr;
+  if (PADDED && y - R.rr >= F->Hr) return 0.0;   // the warp's four rows are padding
   const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
   const bool l0 = R.l0;
   // observation + signed variance of this thread's 16 pixels: issued first, used
