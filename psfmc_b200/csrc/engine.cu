@@ -235,6 +235,7 @@ struct Engine : EngineBase {
     b.vscale_inv = d.vscale_inv;
     b.scratch = d.scratch.ptr;
     b.partials = d.partials.ptr;
+    b.rconst = sizeof(T) == 4 ? d.rconst.ptr : nullptr;
     return b;
   }
 
@@ -251,6 +252,8 @@ struct Engine : EngineBase {
       return 0;
     }
     long long chunk = B < plan.chunk ? B : plan.chunk;
+    if (sizeof(T) == 4 && d.rconst.ensure(nb * ncomp * PSFMC_RC_STRIDE))
+      return fail(PSFMC_ERR_CUDA, "device allocation failed (render constants)");
     if (d.partials.ensure(nb * plan.n_rowblk) ||
         d.scratch.ensure((size_t)chunk * plan.scratch_elems_per_walker))
       return fail(PSFMC_ERR_CUDA, "device allocation failed while sizing the batch buffers");

@@ -51,7 +51,11 @@ __global__ void rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__
                                 const double *__restrict__ pad_b,
                                 const cplx<T> *__restrict__ tw_w,
                                 cplx<T> *__restrict__ scratch,
-                                T *__restrict__ raw_out) {
+                                T *__restrict__ raw_out,
+                                const float *__restrict__ rconst = nullptr) {
+  // rconst (optional, float32 render): the per-walker float32 Sersic constants the
+  // prepare kernel wrote ([B][ncomp][PSFMC_RC_STRIDE]); without them every thread
+  // derives them from the float64 ones (a float64 log2 per Sersic)
   PSFMC_DYN_SMEM(smem_raw);
   Frame fr = fr_rt;
   if (LOGW) {
@@ -70,6 +74,9 @@ __global__ void rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__
   cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
   cplx<T> *tw_s = tile + RB * PITCH;
   double *der_s = reinterpret_cast<double *>(tw_s + W);
+  // float32 constants behind the float64 ones (16-byte aligned: the stride is even)
+  float *rc_s = reinterpret_cast<float *>(
+      der_s + (prog ? prog->n_components : 0) * PSFMC_DERIVED_STRIDE);
 
   load_twiddles<T>(tw_s, tw_w, W, tid, nthreads);
   int ncomp = 0;
@@ -77,6 +84,9 @@ __global__ void rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__
     ncomp = prog->n_components;
     const double *der_b = derived + b * ncomp * PSFMC_DERIVED_STRIDE;
     for (int k = tid; k < ncomp * PSFMC_DERIVED_STRIDE; k += nthreads) der_s[k] = der_b[k];
+    if (rconst)
+      for (int k = tid; k < ncomp * PSFMC_RC_STRIDE; k += nthreads)
+        rc_s[k] = rconst[b * ncomp * PSFMC_RC_STRIDE + k];
     __syncthreads();
   }
 
@@ -123,7 +133,16 @@ __global__ void rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__
           acc[i] += (float)point_pixel(d, x, y0 + r);
         }
       } else {
-        const SersicF32 s = make_sersic_f32(d);
+        SersicF32 s;
+        if (rconst) {
+          const float4 *rc4 = reinterpret_cast<const float4 *>(rc_s + c * PSFMC_RC_STRIDE);
+          const float4 q0 = rc4[0], q1 = rc4[1], q2 = rc4[2];
+          s.xi = q0.x; s.xf = q0.y; s.yi = q0.z; s.yf = q0.w;
+          s.a00 = q1.x; s.a01 = q1.y; s.a10 = q1.z; s.a11 = q1.w;
+          s.p = q2.x; s.c0 = q2.y; s.c1 = q2.z; s.kq = q2.w;
+        } else {
+          s = make_sersic_f32(d);
+        }
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {   // two pixels per packed instruction
           const int e0 = tid + i * nthreads, e1 = e0 + nthreads;

@@ -122,7 +122,8 @@ inline StagedPlan make_staged_plan(int H, int W, int n_components, size_t sizeof
   p.threads_cols = best * (H / 8);
   size_t csz = 2 * sizeof_real;
   p.smem_rows = (size_t)(rb * (W + 4) + W) * csz +
-                (size_t)(n_components * PSFMC_DERIVED_STRIDE + 64) * sizeof(double);
+                (size_t)(n_components * PSFMC_DERIVED_STRIDE + 64) * sizeof(double) +
+                (size_t)(n_components * PSFMC_RC_STRIDE) * sizeof(float);
   p.smem_cols = (size_t)(best * H + H) * csz;
   p.scratch_elems_per_walker = (size_t)ncol * H;
   double per_walker = (double)p.scratch_elems_per_walker * csz;
@@ -192,6 +193,7 @@ struct StagedBuffers {
   const double *vscale_inv;   // [K] inverse of the scale folded into the V spectra
   cplx<T> *scratch;           // [chunk][2*Wc][H]
   double *partials;           // [B][n_rowblk]
+  float *rconst = nullptr;    // [B][ncomp][PSFMC_RC_STRIDE], float32 engines only
 };
 
 // Optional image outputs of one chunk (null = not wanted), [chunk][H*W] each.
@@ -220,7 +222,7 @@ inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
   if (n_batch <= 0) return;
   const Frame fr = plan.fr;
   launch_prepare(*buf.prog_host, theta, n_batch, ld, fr.Hr, fr.Wr, n_components, buf.derived,
-                 buf.psf_sel, buf.wscale, (float *)nullptr, stream);
+                 buf.psf_sel, buf.wscale, buf.rconst, stream);
   if (ev_begin) cudaEventRecord(ev_begin, stream);   // the three row/column kernels
   for (long long start = 0; start < n_batch; start += plan.chunk) {
     long long nb = n_batch - start < plan.chunk ? n_batch - start : plan.chunk;
@@ -235,10 +237,12 @@ inline void launch_staged_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
     const double *wsc = (const double *)(buf.wscale + start);
     const int *sel = (const int *)(buf.psf_sel + start);
     double *part = buf.partials + start * plan.n_rowblk;
+    const float *rcs = buf.rconst ? buf.rconst + start * n_components * PSFMC_RC_STRIDE
+                                  : (const float *)nullptr;
 #define PSFMC_ROWS_FWD(KERNEL)                                                               \
   launch_kernel(KERNEL, grid_rows, dim3(plan.threads_rows), plan.smem_rows, stream, fr,      \
                 plan.RB, buf.prog, der, wsc, precision, (const double *)nullptr,             \
-                (const double *)nullptr, buf.tw_w, buf.scratch, img.raw)
+                (const double *)nullptr, buf.tw_w, buf.scratch, img.raw, rcs)
 #define PSFMC_COLS(KERNEL)                                                                   \
   launch_kernel(KERNEL, grid_cols, dim3(plan.threads_cols), plan.smem_cols, stream, fr,      \
                 plan.CB, buf.tw_h, buf.spec, sel, buf.scratch, (cplx<T> *)nullptr)
@@ -313,7 +317,7 @@ inline void launch_staged_setup(const StagedPlan &plan, const cplx<double> *tw_w
   launch_kernel(rows_fwd_kernel<double, PSFMC_SRC_PSFPAD>, grid_rows,
                 dim3(plan.threads_rows), plan.smem_rows, stream, fr, plan.RB,
                 (const Program *)nullptr, (const double *)nullptr, (const double *)nullptr, 0,
-                pad_psf, pad_var, tw_w, scratch, (double *)nullptr);
+                pad_psf, pad_var, tw_w, scratch, (double *)nullptr, (const float *)nullptr);
   launch_kernel(cols_kernel<double, PSFMC_COLS_SETUP>, grid_cols, dim3(plan.threads_cols),
                 plan.smem_cols, stream, fr, plan.CB, tw_h, (const cplx<double> *)nullptr,
                 (const int *)nullptr, scratch, spec_out);
