@@ -178,6 +178,46 @@ int psfmc_render_batch(psfmc_engine *engine, const double *theta, int64_t n_batc
 int psfmc_accumulate_batch(psfmc_engine *engine, const double *theta, int64_t n_batch,
                            int64_t ld, uint32_t which, double *sums_out);
 
+/* ---- batched log-priors on the host --------------------
+ * The priors stay scipy.stats objects on the Python side (psfMC/distributions.py:
+ * 115-128); what crosses this boundary is, per theta column, a closed-form family with
+ * constants the caller computed with numpy/scipy, so that only IEEE-exact operations
+ * run here and the result is bit-identical to rv_frozen.logpdf (the caller checks that
+ * on its first batch). Replaces the per-walker scipy calls of
+ * ComponentBase.log_priors (psfMC/ModelComponents/ComponentBase.py:121-129),
+ * Sersic.log_priors (Sersic.py:41-45) and MultiComponentModel.log_priors
+ * (psfMC/models.py:187-191). No GPU involved. */
+#define PSFMC_PRIOR_OTHER 0   /* column evaluated by the caller (any other scipy family) */
+#define PSFMC_PRIOR_UNIFORM 1 /* scipy.stats.uniform(loc, scale)                        */
+#define PSFMC_PRIOR_NORMAL 2  /* scipy.stats.norm(loc, scale)                           */
+typedef struct psfmc_prior_column {
+  int32_t family;      /* PSFMC_PRIOR_*                                                 */
+  int32_t theta_index; /* column of theta                                               */
+  int32_t valid;       /* scipy's _argcheck(...) & (scale > 0)                          */
+  int32_t reserved;
+  double loc, scale;
+  double log_scale;    /* numpy.log(scale)                                              */
+  double log_norm;     /* NORMAL: scipy's log(sqrt(2 pi)) constant                      */
+} psfmc_prior_column;
+/* logp_out[b*ld_out + c] for every column c whose family is not PSFMC_PRIOR_OTHER. */
+int psfmc_prior_columns(const psfmc_prior_column *columns, int32_t n_columns,
+                        const double *theta, int64_t n_batch, int64_t ld, double *logp_out,
+                        int64_t ld_out);
+typedef struct psfmc_prior_term {   /* one prior: n_columns consecutive columns of logp */
+  int32_t component, first_column, n_columns, reserved;
+} psfmc_prior_term;
+typedef struct psfmc_prior_rule {   /* component's joint prior is -inf where b > a      */
+  int32_t component, a_index, b_index, reserved;   /* theta columns, or -1: the constant */
+  double a_value, b_value;
+} psfmc_prior_rule;
+/* lnprior_out[b] = sum over components (model order) of the sum over the component's
+ * terms (given in evaluation order, grouped by ascending component), in exactly the
+ * order the reference adds them. */
+int psfmc_prior_sum(const double *logp, int64_t n_batch, int64_t ld_logp, const double *theta,
+                    int64_t ld, const psfmc_prior_term *terms, int32_t n_terms,
+                    const psfmc_prior_rule *rules, int32_t n_rules, int32_t n_components,
+                    double *lnprior_out);
+
 /* Introspection (roofline bookkeeping for bench.py). */
 typedef struct psfmc_info {
   int32_t height, width, n_components, n_sersic, n_point, n_psf, precision;
@@ -195,6 +235,10 @@ typedef struct psfmc_info {
                                and verified at creation; 0: from the iteration       */
   int32_t rescued_total;    /* walkers re-evaluated in float64 by psfmc_lnlike_batch
                                (PSFMC_PREC_FP32, see PSFMC_DESC_NO_FP64_RESCUE)      */
+  int32_t graph_replays;    /* psfmc_lnlike_batch calls served by replaying a captured
+                               CUDA graph (single-device float32 engines)            */
+  int32_t rescued_on_device;   /* of rescued_total: repeated inside such a graph by its
+                               conditional node, without a host round trip           */
 } psfmc_info;
 int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info);
 

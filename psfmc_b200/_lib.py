@@ -68,14 +68,36 @@ class Info(ctypes.Structure):
         ('hbm_bytes_per_eval', ctypes.c_double),
         ('launches_total', ctypes.c_int64),
         ('kappa_table', ctypes.c_int32), ('rescued_total', ctypes.c_int32),
+        ('graph_replays', ctypes.c_int32), ('rescued_on_device', ctypes.c_int32),
     ]
+
+
+PRIOR_OTHER, PRIOR_UNIFORM, PRIOR_NORMAL = 0, 1, 2
+
+
+class PriorColumn(ctypes.Structure):
+    _fields_ = [('family', ctypes.c_int32), ('theta_index', ctypes.c_int32),
+                ('valid', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('loc', ctypes.c_double), ('scale', ctypes.c_double),
+                ('log_scale', ctypes.c_double), ('log_norm', ctypes.c_double)]
+
+
+class PriorTerm(ctypes.Structure):
+    _fields_ = [('component', ctypes.c_int32), ('first_column', ctypes.c_int32),
+                ('n_columns', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+class PriorRule(ctypes.Structure):
+    _fields_ = [('component', ctypes.c_int32), ('a_index', ctypes.c_int32),
+                ('b_index', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('a_value', ctypes.c_double), ('b_value', ctypes.c_double)]
 
 
 # every symbol include/psfmc_b200.h declares
 EXPORTED_SYMBOLS = (
     'psfmc_engine_create', 'psfmc_engine_destroy', 'psfmc_lnlike_batch',
     'psfmc_lnlike_batch_device', 'psfmc_render_batch', 'psfmc_accumulate_batch',
-    'psfmc_engine_info',
+    'psfmc_engine_info', 'psfmc_prior_columns', 'psfmc_prior_sum',
     'psfmc_engine_profile', 'psfmc_engine_profile_read',
     'psfmc_fp32_peak_probe', 'psfmc_last_error', 'psfmc_abi_version',
 )
@@ -132,6 +154,15 @@ def load(path=None):
                                            ctypes.c_int64, ctypes.c_uint32, dbl_p]
     lib.psfmc_engine_info.restype = ctypes.c_int
     lib.psfmc_engine_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(Info)]
+    lib.psfmc_prior_columns.restype = ctypes.c_int
+    lib.psfmc_prior_columns.argtypes = [
+        ctypes.POINTER(PriorColumn), ctypes.c_int32, dbl_p, ctypes.c_int64,
+        ctypes.c_int64, dbl_p, ctypes.c_int64]
+    lib.psfmc_prior_sum.restype = ctypes.c_int
+    lib.psfmc_prior_sum.argtypes = [
+        dbl_p, ctypes.c_int64, ctypes.c_int64, dbl_p, ctypes.c_int64,
+        ctypes.POINTER(PriorTerm), ctypes.c_int32, ctypes.POINTER(PriorRule),
+        ctypes.c_int32, ctypes.c_int32, dbl_p]
     lib.psfmc_engine_profile.restype = ctypes.c_int
     lib.psfmc_engine_profile.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.psfmc_engine_profile_read.restype = ctypes.c_int

@@ -10,11 +10,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <cmath>
 #include <string>
 #include <vector>
 
 #include "pipeline.cuh"
+#include "priors_host.cuh"
 #ifndef PSFMC_NO_FUSED
 #include "kernels_fused.cuh"
 #include "kernels_cluster.cuh"
@@ -42,12 +44,17 @@ int fail(int code, const std::string &msg) {
     }                                                                               \
   } while (0)
 
+// Bumped whenever a batch buffer is reallocated: captured graphs hold raw pointers
+// into these buffers and are rebuilt when the epoch they were captured in is over.
+std::atomic<long long> g_alloc_epoch{0};
+
 template <typename T>
 struct DevBuf {
   T *ptr = nullptr;
   size_t count = 0;
   int ensure(size_t n) {
     if (n <= count) return 0;
+    ++g_alloc_epoch;
     if (ptr) cudaFree(ptr);
     ptr = nullptr;
     count = 0;
@@ -73,6 +80,7 @@ struct PinBuf {
   size_t count = 0;
   int ensure(size_t n) {
     if (n <= count) return 0;
+    ++g_alloc_epoch;
     if (ptr) cudaFreeHost(ptr);
     ptr = nullptr;
     count = 0;
@@ -119,12 +127,44 @@ struct DeviceState {
   PinBuf<T> img_pin;
   // rows of the current host call
   long long row0 = 0, nrows = 0;
+#ifndef PSFMC_EMU
+  // host calls replayed as CUDA graphs (lnlike_host_graph)
+  struct GraphEntry {
+    long long B = 0, ld = 0, epoch = 0;
+    const void *src = nullptr;
+    void *dst = nullptr;
+    bool has_body = false;
+    int n_launches = 0;
+    cudaGraphExec_t exec = nullptr;
+  };
+  std::vector<GraphEntry> graphs;
+  bool graph_ok = true;
+  cudaStream_t stream2 = nullptr;      // captures the conditional body
+  DevBuf<int> r_flags;                 // [0] = non-finite count, [1..] = their rows
+  PinBuf<int> r_flags_host;            // the same, written by the scan kernel
+  DevBuf<double> r_theta, r_lnl;       // [PSFMC_RESCUE_MAX][ld], [PSFMC_RESCUE_MAX]
+  void drop_graphs() {
+    for (auto &g : graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
+#endif
 };
 
 struct EngineBase {
   virtual ~EngineBase() {}
   virtual int profile_read(double *ms, long long *count) = 0;
+  virtual int reserve(long long B) = 0;   // size device 0's batch buffers for B walkers
   bool profiling = false;
+  // float64 rescue on the device (float32 engines, see lnlike_host_graph): the owner
+  // sets scan_wanted and, once it exists, the float64 engine; every host call reports
+  // whether the device looked for non-finite results, how many it found and whether it
+  // already repeated them
+  bool scan_wanted = false;
+  EngineBase *rescue_peer = nullptr;
+  bool scan_valid = false, scan_rescued = false;
+  int scan_flagged = 0;
+  long long graph_replays = 0;
   virtual int lnlike_host(const double *theta, long long B, long long ld, double *out) = 0;
   virtual int lnlike_device(int slot, const double *theta, long long B, long long ld,
                             double *lnl, void *stream) = 0;
@@ -142,6 +182,68 @@ struct EngineBase {
   int first_ordinal = 0;     // CUDA ordinal of the engine's first device
 };
 
+#ifndef PSFMC_EMU
+// ------------------------------------------- float64 rescue on the device --
+// A host call of a float32 engine is replayed as ONE CUDA graph: theta H2D -> prepare
+// -> lnL kernel(s) -> rescue_scan_kernel -> IF node { gather theta rows -> the float64
+// engine's kernels -> scatter }. The scan kernel copies lnL to the caller's page-locked
+// buffer, lists the non-finite walkers and arms the conditional node; the float64
+// repeat then costs no host round trip, and nothing at all when no walker needs it.
+#define PSFMC_RESCUE_MAX 8   // more non-finite walkers than this: the host path repeats them
+
+__global__ void rescue_scan_kernel(const double *__restrict__ lnl, long long n_batch,
+                                   double *__restrict__ out_host, int *__restrict__ flags,
+                                   int *__restrict__ flags_host,
+                                   cudaGraphConditionalHandle handle, int armed) {
+  __shared__ int count;
+  __shared__ int rows[PSFMC_RESCUE_MAX];
+  if (threadIdx.x == 0) count = 0;
+  __syncthreads();
+  for (long long b = threadIdx.x; b < n_batch; b += blockDim.x) {
+    const double v = lnl[b];
+    out_host[b] = v;
+    if (!(v > -INFINITY)) {
+      const int k = atomicAdd(&count, 1);
+      if (k < PSFMC_RESCUE_MAX) rows[k] = (int)b;
+    }
+  }
+  __syncthreads();
+  const int n = count;
+  // the order atomicAdd handed out is arbitrary: sort the (few) rows
+  if (threadIdx.x == 0) {
+    const int m = n < PSFMC_RESCUE_MAX ? n : PSFMC_RESCUE_MAX;
+    for (int i = 1; i < m; ++i) {
+      const int v = rows[i];
+      int j = i - 1;
+      for (; j >= 0 && rows[j] > v; --j) rows[j + 1] = rows[j];
+      rows[j + 1] = v;
+    }
+    flags[0] = flags_host[0] = n;
+    for (int i = 0; i < m; ++i) flags[1 + i] = flags_host[1 + i] = rows[i];
+    if (armed) cudaGraphSetConditional(handle, (n > 0 && n <= PSFMC_RESCUE_MAX) ? 1u : 0u);
+  }
+}
+
+// theta rows of the listed walkers -> [PSFMC_RESCUE_MAX][ld]; unused slots repeat the first
+__global__ void rescue_gather_kernel(const double *__restrict__ theta, long long ld,
+                                     const int *__restrict__ flags,
+                                     double *__restrict__ r_theta) {
+  const int n = flags[0];
+  for (long long e = threadIdx.x; e < PSFMC_RESCUE_MAX * ld; e += blockDim.x) {
+    const int k = (int)(e / ld);
+    const int row = flags[1 + (k < n ? k : 0)];
+    r_theta[e] = theta[(long long)row * ld + (e - k * ld)];
+  }
+}
+
+__global__ void rescue_scatter_kernel(const double *__restrict__ r_lnl,
+                                      const int *__restrict__ flags,
+                                      double *__restrict__ out_host) {
+  const int k = threadIdx.x;
+  if (k < flags[0] && k < PSFMC_RESCUE_MAX) out_host[flags[1 + k]] = r_lnl[k];
+}
+#endif
+
 template <typename T>
 struct Engine : EngineBase {
   std::vector<DeviceState<T>> devs;
@@ -150,6 +252,14 @@ struct Engine : EngineBase {
     for (auto &d : devs) {
       cudaSetDevice(d.ordinal);
       if (d.stream) cudaStreamSynchronize(d.stream);
+#ifndef PSFMC_EMU
+      d.drop_graphs();
+      if (d.stream2) cudaStreamDestroy(d.stream2);
+      d.r_flags.release();
+      d.r_flags_host.release();
+      d.r_theta.release();
+      d.r_lnl.release();
+#endif
       cudaFree(d.prog);
       cudaFree(d.tw_w);
       cudaFree(d.tw_h);
@@ -317,7 +427,162 @@ struct Engine : EngineBase {
     return enqueue(d, theta, B, ld, lnl, (cudaStream_t)stream);
   }
 
+  int reserve(long long B) override {
+    DeviceState<T> &d = devs[0];
+    CUDA_TRY(cudaSetDevice(d.ordinal));
+    return ensure_batch(d, B);
+  }
+
+#ifndef PSFMC_EMU
+  // Capture one host call (single device) into a graph; see rescue_scan_kernel.
+  // Returns 0 and leaves *out null when capturing is not possible (the caller then
+  // takes the ordinary launch path for good).
+  int capture_call(DeviceState<T> &d, const double *src, long long B, long long ld,
+                   double *dst, typename DeviceState<T>::GraphEntry *out) {
+    const size_t nel = (size_t)B * ld;
+    if (d.theta.ensure(nel) || d.lnl.ensure((size_t)B) || d.r_flags.ensure(1 + PSFMC_RESCUE_MAX) ||
+        d.r_flags_host.ensure(1 + PSFMC_RESCUE_MAX) ||
+        d.r_theta.ensure((size_t)PSFMC_RESCUE_MAX * ld) || d.r_lnl.ensure(PSFMC_RESCUE_MAX))
+      return fail(PSFMC_ERR_CUDA, "device allocation failed (graph path)");
+    int rc = ensure_batch(d, B);
+    if (rc) return rc;
+    if (rescue_peer && (rc = rescue_peer->reserve(PSFMC_RESCUE_MAX))) return rc;
+    CUDA_TRY(cudaSetDevice(d.ordinal));
+    if (!d.stream2)
+      CUDA_TRY(cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking));
+    const long long launches0 = launches;
+    bool ok = cudaStreamBeginCapture(d.stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      return 0;
+    }
+    cudaGraph_t graph = nullptr;
+    cudaGraphConditionalHandle handle = 0;
+    const bool body = rescue_peer != nullptr;
+    ok = cudaMemcpyAsync(d.theta.ptr, src, nel * sizeof(double), cudaMemcpyHostToDevice,
+                         d.stream) == cudaSuccess;
+    ok = ok && enqueue(d, d.theta.ptr, B, ld, d.lnl.ptr, d.stream) == 0;
+    cudaStreamCaptureStatus st;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t ndeps = 0;
+    ok = ok && cudaStreamGetCaptureInfo_v2(d.stream, &st, nullptr, &graph, &deps, &ndeps) ==
+                   cudaSuccess;
+    if (ok && body)
+      ok = cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault) ==
+           cudaSuccess;
+    if (ok) {
+      rescue_scan_kernel<<<1, 1024, 0, d.stream>>>(d.lnl.ptr, B, dst, d.r_flags.ptr,
+                                                   d.r_flags_host.ptr, handle, body ? 1 : 0);
+      ++launches;
+    }
+    if (ok && body) {
+      ok = cudaStreamGetCaptureInfo_v2(d.stream, &st, nullptr, &graph, &deps, &ndeps) ==
+           cudaSuccess;
+      cudaGraphNodeParams cp = {};
+      cp.type = cudaGraphNodeTypeConditional;
+      cp.conditional.handle = handle;
+      cp.conditional.type = cudaGraphCondTypeIf;
+      cp.conditional.size = 1;
+      cudaGraphNode_t cnode = nullptr;
+      ok = ok && cudaGraphAddNode(&cnode, graph, deps, ndeps, &cp) == cudaSuccess;
+      if (ok) {
+        cudaGraph_t bgraph = cp.conditional.phGraph_out[0];
+        ok = cudaStreamBeginCaptureToGraph(d.stream2, bgraph, nullptr, nullptr, 0,
+                                           cudaStreamCaptureModeRelaxed) == cudaSuccess;
+        if (ok) {
+          const long long keep = launches;   // body launches are counted when they run
+          rescue_gather_kernel<<<1, 256, 0, d.stream2>>>(d.theta.ptr, ld, d.r_flags.ptr,
+                                                         d.r_theta.ptr);
+          const bool inner = rescue_peer->lnlike_device(0, d.r_theta.ptr, PSFMC_RESCUE_MAX, ld,
+                                                        d.r_lnl.ptr, d.stream2) == 0;
+          rescue_scatter_kernel<<<1, 32, 0, d.stream2>>>(d.r_lnl.ptr, d.r_flags.ptr, dst);
+          launches = keep;
+          ok = cudaStreamEndCapture(d.stream2, nullptr) == cudaSuccess && inner;
+        }
+        ok = ok && cudaStreamUpdateCaptureDependencies(d.stream, &cnode, 1,
+                                                       cudaStreamSetCaptureDependencies) ==
+                       cudaSuccess;
+      }
+    }
+    cudaGraph_t done = nullptr;
+    const bool ended = cudaStreamEndCapture(d.stream, &done) == cudaSuccess;
+    cudaGraphExec_t exec = nullptr;
+    if (ok && ended && done) ok = cudaGraphInstantiate(&exec, done, 0) == cudaSuccess;
+    if (done) cudaGraphDestroy(done);
+    if (!ok || !ended || !exec) {
+      cudaGetLastError();
+      launches = launches0;
+      return 0;
+    }
+    out->B = B;
+    out->ld = ld;
+    out->src = src;
+    out->dst = dst;
+    out->has_body = body;
+    out->n_launches = (int)(launches - launches0);
+    out->exec = exec;
+    launches = launches0;
+    return 0;
+  }
+
+  // One host call on a single device as a graph replay. *done = false: not taken.
+  int lnlike_host_graph(const double *theta, long long B, long long ld, double *out,
+                        bool theta_pinned, bool out_pinned, bool *done) {
+    *done = false;
+    DeviceState<T> &d = devs[0];
+    if (!d.graph_ok) return 0;
+    CUDA_TRY(cudaSetDevice(d.ordinal));
+    const size_t nel = (size_t)B * ld;
+    const double *src = theta;
+    double *dst = out;
+    if (!theta_pinned) {
+      if (d.theta_pin.ensure(nel)) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
+      src = d.theta_pin.ptr;
+    }
+    if (!out_pinned) {
+      if (d.lnl_pin.ensure((size_t)B)) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
+      dst = d.lnl_pin.ptr;
+    }
+    const bool body = rescue_peer != nullptr;
+    typename DeviceState<T>::GraphEntry *hit = nullptr;
+    for (int attempt = 0; attempt < 2 && !hit; ++attempt) {
+      if (!d.graphs.empty() && d.graphs[0].epoch != g_alloc_epoch.load()) d.drop_graphs();
+      for (auto &g : d.graphs)
+        if (g.B == B && g.ld == ld && g.src == src && g.dst == dst && g.has_body == body)
+          hit = &g;
+      if (hit) break;
+      if (d.graphs.size() >= 32) d.drop_graphs();
+      typename DeviceState<T>::GraphEntry e;
+      int rc = capture_call(d, src, B, ld, dst, &e);
+      if (rc) return rc;
+      if (!e.exec) {
+        d.graph_ok = false;
+        d.drop_graphs();
+        return 0;
+      }
+      // the allocations of the capture may have ended the epoch of older entries
+      const long long now = g_alloc_epoch.load();
+      if (!d.graphs.empty() && d.graphs[0].epoch != now) d.drop_graphs();
+      e.epoch = now;
+      d.graphs.push_back(e);
+      hit = &d.graphs.back();
+    }
+    if (!theta_pinned) memcpy(d.theta_pin.ptr, theta, nel * sizeof(double));
+    CUDA_TRY(cudaGraphLaunch(hit->exec, d.stream));
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    launches += hit->n_launches;
+    ++graph_replays;
+    if (!out_pinned) memcpy(out, d.lnl_pin.ptr, (size_t)B * sizeof(double));
+    scan_valid = true;
+    scan_flagged = d.r_flags_host.ptr[0];
+    scan_rescued = hit->has_body && scan_flagged > 0 && scan_flagged <= PSFMC_RESCUE_MAX;
+    *done = true;
+    return 0;
+  }
+#endif
+
   int lnlike_host(const double *theta, long long B, long long ld, double *out) override {
+    scan_valid = false;
     if (B <= 0) return 0;
 #ifdef PSFMC_EMU
     const bool zero_copy_out = true;    // "device" memory is host memory
@@ -343,6 +608,15 @@ struct Engine : EngineBase {
       else
         cudaGetLastError();
     }
+#ifndef PSFMC_EMU
+    const char *no_graph = getenv("PSFMC_NO_GRAPH");
+    const bool use_graphs = !(no_graph && no_graph[0] == '1');
+    if (use_graphs && scan_wanted && nd == 1 && !profiling && zero_copy_out) {
+      bool done = false;
+      int rc = lnlike_host_graph(theta, B, ld, out, theta_pinned, out_pinned, &done);
+      if (rc || done) return rc;
+    }
+#endif
     for (int i = 0; i < nd; ++i) {
       DeviceState<T> &d = devs[i];
       d.row0 = row;
@@ -978,7 +1252,10 @@ struct psfmc_engine {
   // float64 rescue of the float32 mode (see psfmc_lnlike_batch)
   SavedDesc *saved = nullptr;
   EngineBase *rescue = nullptr;
-  long long rescued = 0;
+  long long rescued = 0, rescued_device = 0;
+  // calls left on the graph path (device-side repeat): re-armed by every call that
+  // had to repeat a walker, so ensembles that never need it keep the plain launches
+  int rescue_heat = 0;
   std::vector<double> r_theta, r_lnl;
   std::vector<long long> r_rows;
 };
@@ -1001,6 +1278,7 @@ static int rescue_nonfinite(psfmc_engine *engine, const double *theta, int64_t n
   if (!engine->rescue) {
     int rc = create_engine<double>(&engine->saved->d, &engine->rescue);
     if (rc) return rc;
+    engine->impl->rescue_peer = engine->rescue;   // later calls repeat them on the device
   }
   const size_t nr = engine->r_rows.size();
   engine->r_theta.resize(nr * (size_t)ld);
@@ -1065,8 +1343,24 @@ int psfmc_lnlike_batch(psfmc_engine *engine, const double *theta, int64_t n_batc
   if (!theta || !lnl_out) return fail(PSFMC_ERR_INVALID_ARG, "null theta / lnl_out");
   int prev = 0;
   cudaGetDevice(&prev);
+  engine->impl->scan_wanted = engine->saved && engine->rescue_heat > 0;
   int rc = engine->impl->lnlike_host(theta, n_batch, ld, lnl_out);
-  if (!rc && engine->saved) rc = rescue_nonfinite(engine, theta, n_batch, ld, lnl_out);
+  if (!rc && engine->saved) {
+    EngineBase *impl = engine->impl;
+    const long long before = engine->rescued;
+    if (impl->scan_valid && impl->scan_flagged == 0) {
+      // the device looked: every result is finite
+    } else if (impl->scan_valid && impl->scan_rescued) {
+      engine->rescued += impl->scan_flagged;     // repeated in float64 inside the graph
+      engine->rescued_device += impl->scan_flagged;
+    } else {
+      rc = rescue_nonfinite(engine, theta, n_batch, ld, lnl_out);
+    }
+    if (engine->rescued != before)
+      engine->rescue_heat = 64;
+    else if (engine->rescue_heat > 0)
+      --engine->rescue_heat;
+  }
   cudaSetDevice(prev);
   return rc;
 }
@@ -1147,6 +1441,54 @@ int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info) {
   info->kappa_table = e->kappa_table ? 1 : 0;
   info->rescued_total =
       (int32_t)(engine->rescued > 0x7fffffffLL ? 0x7fffffffLL : engine->rescued);
+  info->graph_replays =
+      (int32_t)(e->graph_replays > 0x7fffffffLL ? 0x7fffffffLL : e->graph_replays);
+  info->rescued_on_device = (int32_t)(engine->rescued_device > 0x7fffffffLL
+                                          ? 0x7fffffffLL
+                                          : engine->rescued_device);
+  return 0;
+}
+
+int psfmc_prior_columns(const psfmc_prior_column *columns, int32_t n_columns,
+                        const double *theta, int64_t n_batch, int64_t ld, double *logp_out,
+                        int64_t ld_out) {
+  if (n_batch < 0 || n_columns < 0 || ld < 0 || ld_out < n_columns)
+    return fail(PSFMC_ERR_INVALID_ARG, "negative size / ld_out < n_columns");
+  if (n_batch == 0 || n_columns == 0) return 0;
+  if (!columns || !theta || !logp_out) return fail(PSFMC_ERR_INVALID_ARG, "null pointer");
+  for (int c = 0; c < n_columns; ++c) {
+    if (columns[c].family < PSFMC_PRIOR_OTHER || columns[c].family > PSFMC_PRIOR_NORMAL)
+      return fail(PSFMC_ERR_INVALID_ARG, "unknown prior family");
+    if (columns[c].family != PSFMC_PRIOR_OTHER &&
+        (columns[c].theta_index < 0 || columns[c].theta_index >= ld))
+      return fail(PSFMC_ERR_INVALID_ARG, "prior column outside theta");
+  }
+  prior_columns_host(columns, n_columns, theta, n_batch, ld, logp_out, ld_out);
+  return 0;
+}
+
+int psfmc_prior_sum(const double *logp, int64_t n_batch, int64_t ld_logp, const double *theta,
+                    int64_t ld, const psfmc_prior_term *terms, int32_t n_terms,
+                    const psfmc_prior_rule *rules, int32_t n_rules, int32_t n_components,
+                    double *lnprior_out) {
+  if (n_batch < 0 || n_terms < 0 || n_rules < 0 || n_components < 0)
+    return fail(PSFMC_ERR_INVALID_ARG, "negative size");
+  if (n_batch == 0) return 0;
+  if (!logp || !theta || !lnprior_out || (n_terms && !terms) || (n_rules && !rules))
+    return fail(PSFMC_ERR_INVALID_ARG, "null pointer");
+  for (int t = 0; t < n_terms; ++t) {
+    if (terms[t].n_columns < 1 || terms[t].first_column < 0 ||
+        terms[t].first_column + terms[t].n_columns > ld_logp)
+      return fail(PSFMC_ERR_INVALID_ARG, "prior term outside the logp matrix");
+    if (terms[t].component < 0 || terms[t].component >= n_components ||
+        (t > 0 && terms[t].component < terms[t - 1].component))
+      return fail(PSFMC_ERR_INVALID_ARG, "prior terms must be grouped by ascending component");
+  }
+  for (int r = 0; r < n_rules; ++r)
+    if (rules[r].a_index >= ld || rules[r].b_index >= ld)
+      return fail(PSFMC_ERR_INVALID_ARG, "prior rule outside theta");
+  prior_sum_host(logp, n_batch, ld_logp, theta, ld, terms, n_terms, rules, n_rules,
+                 n_components, lnprior_out);
   return 0;
 }
 

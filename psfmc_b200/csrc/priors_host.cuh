@@ -1,0 +1,105 @@
+// Host-side batched log-priors: the priors stay the
+// reference's scipy.stats objects (psfMC/distributions.py) and the Python side decides
+// what is evaluated here -- per theta column one of the closed-form families below, with
+// every constant (loc, scale, log(scale), the family's normalisation) computed by numpy /
+// scipy on the Python side, so that only IEEE-exact operations (+ - * / and comparisons)
+// happen here and the result is bit-identical to rv_frozen.logpdf. The Python caller
+// verifies that on the first batch and falls back to scipy otherwise
+// (psfmc_b200/models.py:_column_logp). No CUDA in this file.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/psfmc_b200.h"
+
+namespace psfmc {
+
+// rv_continuous.logpdf (scipy/stats/_distn_infrastructure.py): std = (x - loc) / scale;
+// inside the support and for valid arguments dist._logpdf(std) - log(scale), outside
+// -inf, NaN for NaN input or invalid arguments.
+inline void prior_columns_host(const psfmc_prior_column *cols, int n_cols, const double *theta,
+                               long long n_batch, long long ld, double *logp,
+                               long long ld_out) {
+  // column by column: the family switch and the constants stay out of the inner loop
+  for (int c = 0; c < n_cols; ++c) {
+    const psfmc_prior_column &pc = cols[c];
+    if (pc.family == PSFMC_PRIOR_OTHER) continue;   // the caller fills this column
+    const double *x = theta + pc.theta_index;
+    double *out = logp + c;
+    const double loc = pc.loc, scale = pc.scale;
+    if (!pc.valid) {                                 // rv_continuous.badvalue
+      for (long long b = 0; b < n_batch; ++b) out[b * ld_out] = NAN;
+      continue;
+    }
+    if (pc.family == PSFMC_PRIOR_UNIFORM) {
+      // uniform_gen._pdf = 1.0 * (x == x); _logpdf = log(_pdf) = 0.0; support [0, 1]
+      const double value = 0.0 - pc.log_scale;
+      for (long long b = 0; b < n_batch; ++b) {
+        const double std_ = (x[b * ld] - loc) / scale;
+        double v = (std_ >= 0.0 && std_ <= 1.0) ? value : -INFINITY;
+        if (std_ != std_) v = NAN;
+        out[b * ld_out] = v;
+      }
+    } else {
+      // norm_gen._logpdf = -x**2 / 2.0 - log(sqrt(2 pi)); support (-inf, inf)
+      const double log_norm = pc.log_norm, log_scale = pc.log_scale;
+      for (long long b = 0; b < n_batch; ++b) {
+        const double std_ = (x[b * ld] - loc) / scale;
+        volatile double sq = std_ * std_;            // no contraction into an FMA
+        double v = (-sq / 2.0 - log_norm) - log_scale;
+        if (std_ != std_) v = NAN;
+        out[b * ld_out] = v;
+      }
+    }
+  }
+}
+
+// Joint log-prior per walker from the per-column log-densities, added in the order the
+// reference adds them: per component `total += sum(prior.logp(value))` over its priors
+// (ComponentBase.py:121-129), a rule "-inf if b > a" per component where one is given
+// (Sersic.py:41-45: reff_b > reff), then the components in model order (models.py:187-191).
+inline void prior_sum_host(const double *logp, long long n_batch, long long ld_logp,
+                           const double *theta, long long ld, const psfmc_prior_term *terms,
+                           int n_terms, const psfmc_prior_rule *rules, int n_rules,
+                           int n_components, double *lnprior) {
+  // per component: its run of terms and its rules (rules sorted by component here)
+  std::vector<int> term_end(n_components, 0), rule_begin(n_components + 1, 0), order;
+  for (int comp = 0, t = 0; comp < n_components; ++comp) {
+    while (t < n_terms && terms[t].component == comp) ++t;
+    term_end[comp] = t;
+  }
+  for (int comp = 0; comp < n_components; ++comp) {
+    rule_begin[comp] = (int)order.size();
+    for (int r = 0; r < n_rules; ++r)
+      if (rules[r].component == comp) order.push_back(r);
+  }
+  rule_begin[n_components] = (int)order.size();
+  for (long long b = 0; b < n_batch; ++b) {
+    const double *lp = logp + b * ld_logp;
+    const double *row = theta + b * ld;
+    double total = 0.0;
+    int t = 0;
+    for (int comp = 0; comp < n_components; ++comp) {
+      double ctotal = 0.0;
+      for (; t < term_end[comp]; ++t) {
+        // np.sum over the prior's own columns (sequential below 8 elements)
+        const int first = terms[t].first_column, n = terms[t].n_columns;
+        double s = lp[first];
+        for (int k = 1; k < n; ++k) s += lp[first + k];
+        ctotal = ctotal + s;
+      }
+      for (int q = rule_begin[comp]; q < rule_begin[comp + 1]; ++q) {
+        const psfmc_prior_rule &ru = rules[order[q]];
+        const double a = ru.a_index >= 0 ? row[ru.a_index] : ru.a_value;
+        const double bb = ru.b_index >= 0 ? row[ru.b_index] : ru.b_value;
+        if (bb > a) ctotal = -INFINITY;
+      }
+      total = total + ctotal;
+    }
+    lnprior[b] = total;
+  }
+}
+
+}  // namespace psfmc

@@ -7,9 +7,11 @@ return value ``(lnL + lnprior, blobs)`` so it can still be handed to emcee as is
 the fast path is :meth:`log_posterior_batch`, which :class:`psfmc_b200.pool.BatchPool`
 calls once per emcee ``map`` with the whole (half-)ensemble.
 """
+import os
+
 import numpy as np
 
-from .components import Configuration, PointSource
+from .components import Configuration, PointSource, Sersic
 from .engine import LikelihoodEngine
 from .model_parser import component_list_from_file
 from .program import compile_program
@@ -175,18 +177,19 @@ class MultiComponentModel(object):
             group['args'] = tuple(np.concatenate(arg) for arg in group['args'])
         return list(groups.values()), others
 
-    def _column_logp(self, thetas):
+    def _column_logp(self, thetas, groups=None, others=None, out=None):
         """Per-column log-densities (B, D): rv_continuous.logpdf's own operations
         (cf. ScipyDistribution._logpdf_direct), one pass per distribution family."""
-        groups, others = self._prior_plan
+        if groups is None:
+            groups, others = self._prior_plan
         # parameter-major working layout: the columns of one family are contiguous rows
-        theta_t = np.ascontiguousarray(thetas.T)
-        out = np.empty_like(theta_t)
+        out_t = np.empty((thetas.shape[1], thetas.shape[0]), dtype=np.float64)
         with np.errstate(all='ignore'):
             for group in groups:
                 dist, scale = group['dist'], group['scale'][:, None]
                 args = tuple(arg[:, None] for arg in group['args'])
-                std = (theta_t[group['cols']] - group['loc'][:, None]) / scale
+                theta_g = np.ascontiguousarray(thetas[:, group['cols']].T)
+                std = (theta_g - group['loc'][:, None]) / scale
                 cond0 = dist._argcheck(*args) & (scale > 0)
                 cond = cond0 & dist._support_mask(std, *args) & (scale > 0)
                 values = dist._logpdf(std, *args) - np.log(scale)
@@ -194,37 +197,143 @@ class MultiComponentModel(object):
                 bad = (1 - cond0) + np.isnan(std)
                 if np.any(bad):
                     logp = np.where(bad, dist.badvalue, logp)
-                out[group['cols']] = logp
+                out_t[group['cols']] = logp
             for prior, cols in others:
                 block = thetas[:, cols]
                 if getattr(prior, 'discrete', False):
                     block = np.rint(block).astype(int)
-                out[cols] = np.asarray(getattr(prior, 'logp_batch', prior.logp)(block)).T
-        return out.T
+                out_t[cols] = np.asarray(getattr(prior, 'logp_batch', prior.logp)(block)).T
+        if out is None:
+            return out_t.T
+        for group in groups:
+            out[:, group['cols']] = out_t[group['cols']].T
+        for _, cols in others:
+            out[:, cols] = out_t[cols].T
+        return out
+
+    # -- native evaluation (include/psfmc_b200.h: psfmc_prior_columns / _sum) ------
+    def _native_prior_plan(self):
+        """Tables for the library's host-side prior evaluation: Uniform and Normal
+        columns are evaluated there (closed forms whose constants -- log(scale), the
+        normal's log sqrt(2 pi) -- are computed HERE by numpy/scipy, so only IEEE-exact
+        operations run in C), every other family stays with ``_column_logp``; the
+        summation over priors and components runs in C in the reference's order."""
+        import ctypes
+        from . import _lib
+        from scipy.stats import _continuous_distns as _cd
+        groups, others = self._prior_plan
+        ndim = self.num_params
+        columns = (_lib.PriorColumn * max(ndim, 1))()
+        families = {'uniform_gen': _lib.PRIOR_UNIFORM, 'norm_gen': _lib.PRIOR_NORMAL}
+        rest = []
+        for group in groups:
+            family = families.get(type(group['dist']).__name__)
+            if family is None or len(group['args']) != 0:
+                rest.append(group)
+                continue
+            dist, scale = group['dist'], group['scale'][:, None]
+            with np.errstate(all='ignore'):
+                cond0 = np.broadcast_to(dist._argcheck() & (scale > 0), scale.shape)
+                log_scale = np.log(scale)
+            for k, col in enumerate(group['cols']):
+                entry = columns[int(col)]
+                entry.family = family
+                entry.theta_index = int(col)
+                entry.valid = int(bool(cond0[k, 0]))
+                entry.loc = float(group['loc'][k])
+                entry.scale = float(group['scale'][k])
+                entry.log_scale = float(log_scale[k, 0])
+                entry.log_norm = float(_cd._norm_pdf_logC)
+        terms, rules, start = [], [], 0
+        for num, comp in enumerate(self.components):
+            where = {}
+            for name, _, length in comp.free_parameters():
+                terms.append((num, start, length))
+                where[name] = start
+                start += length
+            if isinstance(comp, Sersic):
+                rule = _lib.PriorRule()
+                rule.component = num
+                for tag, attr in (('a', 'reff'), ('b', 'reff_b')):
+                    if attr in where:
+                        setattr(rule, tag + '_index', where[attr])
+                    else:
+                        setattr(rule, tag + '_index', -1)
+                        setattr(rule, tag + '_value',
+                                float(np.ravel(comp._constants[attr])[0]))
+                rules.append(rule)
+        term_arr = (_lib.PriorTerm * max(len(terms), 1))()
+        for k, (num, first, length) in enumerate(terms):
+            term_arr[k].component, term_arr[k].first_column = num, first
+            term_arr[k].n_columns = length
+        rule_arr = (_lib.PriorRule * max(len(rules), 1))(*rules)
+        return {'columns': columns, 'terms': term_arr, 'n_terms': len(terms),
+                'rules': rule_arr, 'n_rules': len(rules), 'rest': rest, 'others': others,
+                'n_components': len(self.components), 'ndim': ndim,
+                'lib': self.engine._lib}
+
+    def _log_priors_native(self, thetas):
+        import ctypes
+        from . import _lib
+        plan = self._native_plan
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+        n_batch, ld = thetas.shape
+        ndim = plan['ndim']
+        if ld < ndim:
+            raise ValueError('theta has too few columns')
+        dbl_p = ctypes.POINTER(ctypes.c_double)
+        logp = np.empty((n_batch, max(ndim, 1)), dtype=np.float64)
+        lib = plan['lib']
+        _lib.check(lib, lib.psfmc_prior_columns(
+            plan['columns'], ndim, thetas.ctypes.data_as(dbl_p), n_batch, ld,
+            logp.ctypes.data_as(dbl_p), logp.shape[1]))
+        if plan['rest'] or plan['others']:
+            self._column_logp(thetas, plan['rest'], plan['others'], out=logp)
+        lnprior = np.empty(n_batch, dtype=np.float64)
+        _lib.check(lib, lib.psfmc_prior_sum(
+            logp.ctypes.data_as(dbl_p), n_batch, logp.shape[1],
+            thetas.ctypes.data_as(dbl_p), ld, plan['terms'], plan['n_terms'],
+            plan['rules'], plan['n_rules'], plan['n_components'],
+            lnprior.ctypes.data_as(dbl_p)))
+        return lnprior
 
     def log_priors_batch(self, thetas):
-        """Joint log-prior of every row of ``thetas`` (B, D). Priors of the same
-        scipy family are evaluated together (one array operation per family instead
-        of one scipy call per prior: the reference's 11 scalar scipy calls per walker,
-        SURVEY.md section 0.7, become ~3 array operations per BATCH); the grouped path is
-        used only after it has reproduced the per-prior ``rv_frozen.logpdf`` sums bit
-        for bit on the first batch."""
+        """Joint log-prior of every row of ``thetas`` (B, D). Three implementations,
+        tried in this order on the first batch and kept only if they reproduce the
+        per-prior ``rv_frozen.logpdf`` sums BIT FOR BIT on it: 'native' (Uniform and
+        Normal columns and all sums in the library's host code, other families as in
+        'grouped'), 'grouped' (priors of one scipy family in one array operation: the
+        reference's 11 scalar scipy calls per walker, SURVEY.md section 0.7, become ~3
+        array operations per BATCH), 'scipy' (one ``logpdf`` call per prior)."""
         thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
-        state = getattr(self, '_prior_plan_ok', None)
-        if state is False or thetas.shape[0] == 0:
+        mode = getattr(self, '_prior_mode', None)
+        if mode == 'scipy' or thetas.shape[0] == 0:
             return self._log_priors_per_component(thetas)
+        if mode == 'native':
+            return self._log_priors_native(thetas)
+        if mode == 'grouped':
+            return self._log_priors_per_component(thetas, self._column_logp(thetas))
+        slow = self._log_priors_per_component(thetas)
+        self._prior_mode = 'scipy'
         try:
-            if state is None:
-                self._prior_plan = self._prior_groups()
-            fast = self._log_priors_per_component(thetas, self._column_logp(thetas))
+            self._prior_plan = self._prior_groups()
         except Exception:
-            self._prior_plan_ok = False
-            return self._log_priors_per_component(thetas)
-        if state is None:
-            slow = self._log_priors_per_component(thetas)
-            self._prior_plan_ok = bool(np.array_equal(fast, slow, equal_nan=True))
             return slow
-        return fast
+        for candidate in ('native', 'grouped'):
+            if os.environ.get('PSFMC_PRIORS', candidate) != candidate:
+                continue
+            try:
+                if candidate == 'native':
+                    self._native_plan = self._native_prior_plan()
+                    fast = self._log_priors_native(thetas)
+                else:
+                    fast = self._log_priors_per_component(thetas, self._column_logp(thetas))
+            except Exception:
+                continue
+            if np.array_equal(fast, slow, equal_nan=True):
+                self._prior_mode = candidate
+                break
+        return slow
 
     # -- posterior ---------------------------------------------------------------
     def log_likelihood_batch(self, thetas):

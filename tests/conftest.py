@@ -221,6 +221,71 @@ def check_fp64_rescue(library, c1_golden):
     return m1
 
 
+def check_fp64_rescue_on_device(library, c1_golden, monkeypatch):
+    """Host calls of a single-device float32 engine are replayed as CUDA graphs whose
+    conditional node repeats non-finite walkers in float64 without a host round trip
+    (engine.cu: lnlike_host_graph). Same numbers as the host-side repeat, bit for bit;
+    more than 8 non-finite walkers fall back to the host-side repeat."""
+    exact = c1_golden['names'].index('C_exact_centre')
+    base = np.array(c1_golden['theta'][:48])
+    base = base[np.all(np.isfinite(base), axis=1)]
+    finite = [k for k in range(len(base)) if k != exact]
+    batch = np.array(base[finite][:40])
+    hdr = np.array(HIGH_DYNAMIC_RANGE_THETAS)
+    batch[5] = hdr[0]
+    batch[17] = hdr[1]
+    batch[33] = c1_golden['theta'][exact]
+
+    monkeypatch.setenv('PSFMC_NO_GRAPH', '1')
+    plain = model_from_file('j0005/model_c1.py', 'fp32', library=library,
+                            obs_dtype=np.float64)
+    want = plain.log_likelihood_batch(batch)
+    assert plain.engine.info()['graph_replays'] == 0
+    assert want[33] == -np.inf and np.all(np.isfinite(np.delete(want, 33)))
+    monkeypatch.delenv('PSFMC_NO_GRAPH')
+
+    model = model_from_file('j0005/model_c1.py', 'fp32', library=library,
+                            obs_dtype=np.float64)
+    first = model.log_likelihood_batch(batch)     # plain launches + host-side repeat
+    info = model.engine.info()
+    assert info['graph_replays'] == 0 and info['rescued_total'] == 3
+    assert info['rescued_on_device'] == 0
+    assert np.array_equal(first, want)
+    for k in range(3):                             # graph with the conditional body
+        again = model.log_likelihood_batch(batch)
+        assert np.array_equal(again, want)
+    info = model.engine.info()
+    assert info['graph_replays'] == 3 and info['rescued_on_device'] == 9
+    assert info['rescued_total'] == 12
+    # nothing to repeat: the body is skipped
+    clean = np.delete(batch, [5, 17, 33], axis=0)
+    assert np.array_equal(model.log_likelihood_batch(clean), np.delete(want, [5, 17, 33]))
+    assert model.engine.info()['rescued_total'] == 12
+    # other batch sizes / another row order / a strided view (copied by the wrapper)
+    perm = np.random.RandomState(3).permutation(len(batch))
+    assert np.array_equal(model.log_likelihood_batch(batch[perm]), want[perm])
+    assert np.array_equal(model.log_likelihood_batch(batch[:7]), want[:7])
+    assert np.array_equal(model.log_likelihood_batch(batch[30:]), want[30:])
+    # more non-finite walkers than the device list holds: host-side repeat of all
+    many = np.concatenate([batch, np.repeat(hdr, 6, axis=0)])
+    got = model.log_likelihood_batch(many)
+    assert np.array_equal(got[:len(batch)], want)
+    assert np.array_equal(got[len(batch):], np.repeat(want[[5, 17]], 6))
+    before = model.engine.info()['rescued_on_device']
+    assert np.array_equal(model.log_likelihood_batch(many), got)
+    assert model.engine.info()['rescued_on_device'] == before
+    # and a large batch after the small ones (buffers regrow, graphs are re-captured)
+    big = np.concatenate([batch] * 60)
+    got = model.log_likelihood_batch(big)
+    assert np.array_equal(got, np.concatenate([want] * 60))
+    assert np.array_equal(model.log_likelihood_batch(batch), want)
+    # 64 calls without a repeat later the engine is back on the plain launch path
+    before = model.engine.info()['graph_replays']
+    for _ in range(70):
+        model.log_likelihood_batch(clean[:16])
+    assert model.engine.info()['graph_replays'] - before == 64
+
+
 def check_near_centre_walkers(library):
     """Sersic centres within ~0.1 px of a pixel centre (steep central pixel): float32
     fused kernel against the oracle within the stated bound."""

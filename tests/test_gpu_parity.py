@@ -361,6 +361,12 @@ def test_gpu_fp64_rescue_of_high_dynamic_range_walkers(cuda_library, c1_golden):
 
 
 @pytest.mark.gpu
+def test_gpu_fp64_rescue_inside_the_graph(cuda_library, c1_golden, monkeypatch):
+    from conftest import check_fp64_rescue_on_device
+    check_fp64_rescue_on_device(cuda_library, c1_golden, monkeypatch)
+
+
+@pytest.mark.gpu
 def test_gpu_fused_near_centre_walkers(cuda_library):
     from conftest import check_near_centre_walkers
     check_near_centre_walkers(cuda_library)

@@ -57,6 +57,102 @@ def test_batched_priors_equal_reference_lnprior(emu_library):
     assert model.log_priors_batch(bad[None, :])[0] == -np.inf
 
 
+def test_native_priors_are_bit_identical_to_scipy(emu_library, monkeypatch):
+    """Uniform / Normal columns and all sums in the library's host code
+    (psfmc_prior_columns / psfmc_prior_sum), other families (Weibull) in numpy: the same
+    bits as one rv_frozen.logpdf call per prior, including values outside the support,
+    NaN, +-inf and the reff_b > reff rule; every slower mode gives the same numbers."""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model = model_from_file('j0005/model_c1.py', 'fp32', library=emu_library)
+    thetas = draw_walkers_fast(model, 700, seed=11)
+    rng = np.random.RandomState(5)
+    for k in range(120):                       # knock single values out of the support
+        thetas[rng.randint(700), rng.randint(model.num_params)] += rng.choice([-1, 1]) * \
+            10.0 ** rng.uniform(-1, 3)
+    thetas[3, 2] = np.nan
+    thetas[5, 0] = np.inf
+    thetas[6, 0] = -np.inf
+    thetas[8, 7], thetas[8, 8] = 3.0, 5.0      # reff_b > reff
+    want = model._log_priors_per_component(thetas)
+    assert np.isnan(want[3]) and want[5] == -np.inf and want[8] == -np.inf
+    first = model.log_priors_batch(thetas)     # the verifying call returns scipy's
+    assert model._prior_mode == 'native'
+    assert np.array_equal(first, want, equal_nan=True)
+    for rows in (slice(None), slice(0, 1), slice(10, 331)):
+        assert np.array_equal(model.log_priors_batch(thetas[rows]), want[rows],
+                              equal_nan=True)
+    # wider theta rows than the program needs (ld > D)
+    wide = np.concatenate([thetas, np.zeros((700, 3))], axis=1)
+    assert np.array_equal(model.log_priors_batch(wide), want, equal_nan=True)
+    for mode in ('grouped', 'scipy'):
+        monkeypatch.setenv('PSFMC_PRIORS', mode)
+        other = model_from_file('j0005/model_c1.py', 'fp32', library=emu_library)
+        other.log_priors_batch(thetas)
+        assert other._prior_mode == mode
+        assert np.array_equal(other.log_priors_batch(thetas), want, equal_nan=True)
+
+
+def test_native_priors_with_constants_and_two_psfs(emu_library):
+    """Fixed reff (the rule compares against the constant), a discrete PSF index
+    (stays with scipy's logpmf) and a Normal prior."""
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.components import Configuration, Sersic, Sky
+    from psfmc_b200.distributions import Normal, Uniform
+    two = model_from_file('j0005/model_c1_2psf.py', 'fp32', library=emu_library)
+    rng = np.random.RandomState(2)
+    thetas = np.array([two.init_params_from_priors(1)[0] for _ in range(40)])
+    thetas[:, -1] = rng.uniform(-0.7, 2.7, size=40)       # PSF index incl. out of range
+    want = two._log_priors_per_component(thetas)
+    two.log_priors_batch(thetas)
+    assert two._prior_mode == 'native'
+    assert np.array_equal(two.log_priors_batch(thetas), want, equal_nan=True)
+    assert np.any(want == -np.inf) and np.any(np.isfinite(want))
+
+    obs = np.zeros((16, 16))
+    psf = np.zeros((5, 5))
+    psf[2, 2] = 1.0
+    config = Configuration(obs, np.ones_like(obs), psf, np.ones_like(psf),
+                           mag_zeropoint=25.0)
+    comps = [config, Sky(adu=Normal(loc=0.0, scale=0.1)),
+             Sersic(xy=Normal(loc=(8.0, 8.0), scale=(1.0, 2.0)), mag=20.0, reff=4.0,
+                    reff_b=Uniform(loc=1.0, scale=6.0), index=Uniform(loc=0.5, scale=4.0),
+                    angle=0.3)]
+    model = MultiComponentModel(comps, precision='fp32', library=emu_library)
+    thetas = rng.uniform(-1.0, 9.0, size=(300, model.num_params))
+    want = model._log_priors_per_component(thetas)
+    model.log_priors_batch(thetas)
+    assert model._prior_mode == 'native'
+    got = model.log_priors_batch(thetas)
+    assert np.array_equal(got, want, equal_nan=True)
+    reff_b = thetas[:, model.param_names.index('1_Sersic_reff_b')]
+    assert np.all(got[reff_b > 4.0] == -np.inf) and np.any(np.isfinite(got))
+
+
+def test_prior_entry_points_reject_bad_tables(emu_library):
+    import ctypes
+    from psfmc_b200 import _lib
+    lib = _lib.load(emu_library)
+    dbl_p = ctypes.POINTER(ctypes.c_double)
+    theta = np.zeros((4, 3))
+    logp = np.zeros((4, 3))
+    cols = (_lib.PriorColumn * 3)()
+    cols[0].family = 7
+    call = lambda: lib.psfmc_prior_columns(cols, 3, theta.ctypes.data_as(dbl_p), 4, 3,
+                                           logp.ctypes.data_as(dbl_p), 3)
+    assert call() != 0 and b'family' in lib.psfmc_last_error()
+    cols[0].family, cols[0].theta_index = _lib.PRIOR_UNIFORM, 3
+    assert call() != 0
+    cols[0].theta_index, cols[0].scale, cols[0].valid = 0, 1.0, 1
+    assert call() == 0 and logp[0, 0] == 0.0
+    terms = (_lib.PriorTerm * 2)()
+    terms[0].component, terms[0].first_column, terms[0].n_columns = 1, 0, 1
+    terms[1].component, terms[1].first_column, terms[1].n_columns = 0, 1, 1
+    out = np.zeros(4)
+    rc = lib.psfmc_prior_sum(logp.ctypes.data_as(dbl_p), 4, 3, theta.ctypes.data_as(dbl_p), 3,
+                             terms, 2, None, 0, 2, out.ctypes.data_as(dbl_p))
+    assert rc != 0 and b'ascending' in lib.psfmc_last_error()
+
+
 def test_discrete_prior_rounds_half_to_even():
     from psfmc_b200.distributions import DiscreteUniform, Normal
     prior = DiscreteUniform(low=0, high=2)
