@@ -154,6 +154,15 @@ void psfmc_engine_destroy(psfmc_engine *engine);
 int psfmc_lnlike_batch(psfmc_engine *engine, const double *theta, int64_t n_batch,
                        int64_t ld, double *lnl_out);
 
+/* The same call in two halves, so that the caller's own per-batch host work (the
+ * priors, psfMC/models.py:205-211) runs while the GPU computes: _begin copies / enqueues
+ * and returns, _end waits and finishes (including the float64 repeat). theta and
+ * lnl_out must stay valid and untouched until _end has returned; one batch in flight
+ * per engine. psfmc_lnlike_batch(...) == _begin(...) followed by _end(). */
+int psfmc_lnlike_batch_begin(psfmc_engine *engine, const double *theta, int64_t n_batch,
+                             int64_t ld, double *lnl_out);
+int psfmc_lnlike_batch_end(psfmc_engine *engine);
+
 /* Same computation with DEVICE-resident theta and lnL on device `device_slot`
  * (index into the engine's device list), enqueued on `cuda_stream` (a
  * cudaStream_t passed as void*; NULL = the legacy default stream). Asynchronous:

@@ -96,6 +96,7 @@ class PriorRule(ctypes.Structure):
 # every symbol include/psfmc_b200.h declares
 EXPORTED_SYMBOLS = (
     'psfmc_engine_create', 'psfmc_engine_destroy', 'psfmc_lnlike_batch',
+    'psfmc_lnlike_batch_begin', 'psfmc_lnlike_batch_end',
     'psfmc_lnlike_batch_device', 'psfmc_render_batch', 'psfmc_accumulate_batch',
     'psfmc_engine_info', 'psfmc_prior_columns', 'psfmc_prior_sum',
     'psfmc_engine_profile', 'psfmc_engine_profile_read',
@@ -142,6 +143,11 @@ def load(path=None):
     lib.psfmc_lnlike_batch.restype = ctypes.c_int
     lib.psfmc_lnlike_batch.argtypes = [ctypes.c_void_p, dbl_p, ctypes.c_int64,
                                        ctypes.c_int64, dbl_p]
+    lib.psfmc_lnlike_batch_begin.restype = ctypes.c_int
+    lib.psfmc_lnlike_batch_begin.argtypes = [ctypes.c_void_p, dbl_p, ctypes.c_int64,
+                                             ctypes.c_int64, dbl_p]
+    lib.psfmc_lnlike_batch_end.restype = ctypes.c_int
+    lib.psfmc_lnlike_batch_end.argtypes = [ctypes.c_void_p]
     lib.psfmc_lnlike_batch_device.restype = ctypes.c_int
     lib.psfmc_lnlike_batch_device.argtypes = [
         ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64,

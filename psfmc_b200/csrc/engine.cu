@@ -166,6 +166,9 @@ struct EngineBase {
   int scan_flagged = 0;
   long long graph_replays = 0;
   virtual int lnlike_host(const double *theta, long long B, long long ld, double *out) = 0;
+  virtual int lnlike_host_begin(const double *theta, long long B, long long ld,
+                                double *out) = 0;
+  virtual int lnlike_host_end() = 0;
   virtual int lnlike_device(int slot, const double *theta, long long B, long long ld,
                             double *lnl, void *stream) = 0;
   virtual int render(const double *theta, long long B, long long ld, unsigned which,
@@ -569,20 +572,49 @@ struct Engine : EngineBase {
     }
     if (!theta_pinned) memcpy(d.theta_pin.ptr, theta, nel * sizeof(double));
     CUDA_TRY(cudaGraphLaunch(hit->exec, d.stream));
-    CUDA_TRY(cudaStreamSynchronize(d.stream));
     launches += hit->n_launches;
     ++graph_replays;
-    if (!out_pinned) memcpy(out, d.lnl_pin.ptr, (size_t)B * sizeof(double));
+    pend_graph = true;
+    pend_graph_body = hit->has_body;
+    *done = true;
+    return 0;
+  }
+
+  int lnlike_host_graph_end() {
+    DeviceState<T> &d = devs[0];
+    CUDA_TRY(cudaSetDevice(d.ordinal));
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    if (!pend_out_pinned) memcpy(pend_out, d.lnl_pin.ptr, (size_t)pend_B * sizeof(double));
     scan_valid = true;
     scan_flagged = d.r_flags_host.ptr[0];
-    scan_rescued = hit->has_body && scan_flagged > 0 && scan_flagged <= PSFMC_RESCUE_MAX;
-    *done = true;
+    scan_rescued = pend_graph_body && scan_flagged > 0 && scan_flagged <= PSFMC_RESCUE_MAX;
     return 0;
   }
 #endif
 
+  // state of the host call in flight (lnlike_host_begin ... lnlike_host_end)
+  bool pend_active = false, pend_graph = false, pend_graph_body = false;
+  bool pend_out_pinned = false;
+  long long pend_B = 0;
+  double *pend_out = nullptr;
+
   int lnlike_host(const double *theta, long long B, long long ld, double *out) override {
+    int rc = lnlike_host_begin(theta, B, ld, out);
+    if (rc) {
+      pend_active = false;
+      return rc;
+    }
+    return lnlike_host_end();
+  }
+
+  // Enqueue a host call on every device; theta and out must stay valid until
+  // lnlike_host_end() has returned.
+  int lnlike_host_begin(const double *theta, long long B, long long ld, double *out) override {
+    if (pend_active) return fail(PSFMC_ERR_INVALID_ARG, "a batch is already in flight");
     scan_valid = false;
+    pend_graph = false;
+    pend_B = B;
+    pend_out = out;
     if (B <= 0) return 0;
 #ifdef PSFMC_EMU
     const bool zero_copy_out = true;    // "device" memory is host memory
@@ -613,10 +645,16 @@ struct Engine : EngineBase {
     const bool use_graphs = !(no_graph && no_graph[0] == '1');
     if (use_graphs && scan_wanted && nd == 1 && !profiling && zero_copy_out) {
       bool done = false;
+      pend_out_pinned = out_pinned;
       int rc = lnlike_host_graph(theta, B, ld, out, theta_pinned, out_pinned, &done);
-      if (rc || done) return rc;
+      if (rc) return rc;
+      if (done) {
+        pend_active = true;
+        return 0;
+      }
     }
 #endif
+    pend_out_pinned = out_pinned;
     for (int i = 0; i < nd; ++i) {
       DeviceState<T> &d = devs[i];
       d.row0 = row;
@@ -652,13 +690,25 @@ struct Engine : EngineBase {
         CUDA_TRY(cudaMemcpyAsync(dst, d.lnl.ptr, (size_t)d.nrows * sizeof(double),
                                  cudaMemcpyDeviceToHost, d.stream));
     }
+    pend_active = true;
+    return 0;
+  }
+
+  int lnlike_host_end() override {
+    if (pend_B <= 0) return 0;
+    if (!pend_active) return fail(PSFMC_ERR_INVALID_ARG, "no batch in flight");
+    pend_active = false;
+#ifndef PSFMC_EMU
+    if (pend_graph) return lnlike_host_graph_end();
+#endif
+    const int nd = (int)devs.size();
     for (int i = 0; i < nd; ++i) {
       DeviceState<T> &d = devs[i];
       if (d.nrows == 0) continue;
       CUDA_TRY(cudaSetDevice(d.ordinal));
       CUDA_TRY(cudaStreamSynchronize(d.stream));
-      if (!out_pinned)
-        memcpy(out + d.row0, d.lnl_pin.ptr, (size_t)d.nrows * sizeof(double));
+      if (!pend_out_pinned)
+        memcpy(pend_out + d.row0, d.lnl_pin.ptr, (size_t)d.nrows * sizeof(double));
     }
     return 0;
   }
@@ -1256,6 +1306,11 @@ struct psfmc_engine {
   // calls left on the graph path (device-side repeat): re-armed by every call that
   // had to repeat a walker, so ensembles that never need it keep the plain launches
   int rescue_heat = 0;
+  // host batch in flight (psfmc_lnlike_batch_begin ... _end)
+  bool in_flight = false;
+  const double *f_theta = nullptr;
+  double *f_lnl = nullptr;
+  int64_t f_batch = 0, f_ld = 0;
   std::vector<double> r_theta, r_lnl;
   std::vector<long long> r_rows;
 };
@@ -1335,16 +1390,35 @@ void psfmc_engine_destroy(psfmc_engine *engine) {
   cudaSetDevice(prev);
 }
 
-int psfmc_lnlike_batch(psfmc_engine *engine, const double *theta, int64_t n_batch, int64_t ld,
-                       double *lnl_out) {
+int psfmc_lnlike_batch_begin(psfmc_engine *engine, const double *theta, int64_t n_batch,
+                             int64_t ld, double *lnl_out) {
   if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
   if (n_batch < 0 || ld < 0) return fail(PSFMC_ERR_INVALID_ARG, "negative batch or ld");
-  if (n_batch == 0) return 0;
-  if (!theta || !lnl_out) return fail(PSFMC_ERR_INVALID_ARG, "null theta / lnl_out");
+  if (engine->in_flight) return fail(PSFMC_ERR_INVALID_ARG, "a batch is already in flight");
+  if (n_batch > 0 && (!theta || !lnl_out))
+    return fail(PSFMC_ERR_INVALID_ARG, "null theta / lnl_out");
   int prev = 0;
   cudaGetDevice(&prev);
   engine->impl->scan_wanted = engine->saved && engine->rescue_heat > 0;
-  int rc = engine->impl->lnlike_host(theta, n_batch, ld, lnl_out);
+  int rc = engine->impl->lnlike_host_begin(theta, n_batch, ld, lnl_out);
+  cudaSetDevice(prev);
+  if (rc) return rc;
+  engine->in_flight = true;
+  engine->f_theta = theta;
+  engine->f_lnl = lnl_out;
+  engine->f_batch = n_batch;
+  engine->f_ld = ld;
+  return 0;
+}
+
+int psfmc_lnlike_batch_end(psfmc_engine *engine) {
+  if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
+  if (!engine->in_flight) return fail(PSFMC_ERR_INVALID_ARG, "no batch in flight");
+  engine->in_flight = false;
+  if (engine->f_batch == 0) return 0;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int rc = engine->impl->lnlike_host_end();
   if (!rc && engine->saved) {
     EngineBase *impl = engine->impl;
     const long long before = engine->rescued;
@@ -1354,7 +1428,8 @@ int psfmc_lnlike_batch(psfmc_engine *engine, const double *theta, int64_t n_batc
       engine->rescued += impl->scan_flagged;     // repeated in float64 inside the graph
       engine->rescued_device += impl->scan_flagged;
     } else {
-      rc = rescue_nonfinite(engine, theta, n_batch, ld, lnl_out);
+      rc = rescue_nonfinite(engine, engine->f_theta, engine->f_batch, engine->f_ld,
+                            engine->f_lnl);
     }
     if (engine->rescued != before)
       engine->rescue_heat = 64;
@@ -1363,6 +1438,13 @@ int psfmc_lnlike_batch(psfmc_engine *engine, const double *theta, int64_t n_batc
   }
   cudaSetDevice(prev);
   return rc;
+}
+
+int psfmc_lnlike_batch(psfmc_engine *engine, const double *theta, int64_t n_batch, int64_t ld,
+                       double *lnl_out) {
+  int rc = psfmc_lnlike_batch_begin(engine, theta, n_batch, ld, lnl_out);
+  if (rc) return rc;
+  return psfmc_lnlike_batch_end(engine);
 }
 
 int psfmc_lnlike_batch_device(psfmc_engine *engine, int32_t device_slot, const double *theta_dev,

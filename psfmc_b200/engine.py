@@ -155,6 +155,31 @@ class LikelihoodEngine(object):
             out.ctypes.data_as(dbl_p)))
         return out
 
+    def lnlike_begin(self, thetas, out=None):
+        """First half of :meth:`lnlike`: copy / enqueue and return at once, so the
+        caller can evaluate the priors while the GPU works. Finish with
+        :meth:`lnlike_end`, which returns the lnL array."""
+        thetas = np.ascontiguousarray(np.atleast_2d(thetas), dtype=np.float64)
+        n_batch, ld = thetas.shape
+        if ld < self.num_params:
+            raise ValueError('theta has {} columns, the program needs {}'.format(
+                ld, self.num_params))
+        if out is None:
+            out = np.empty(n_batch, dtype=np.float64)
+        dbl_p = ctypes.POINTER(ctypes.c_double)
+        _lib.check(self._lib, self._lib.psfmc_lnlike_batch_begin(
+            self._handle, thetas.ctypes.data_as(dbl_p), n_batch, ld,
+            out.ctypes.data_as(dbl_p)))
+        self._in_flight = (thetas, out)      # keep both buffers alive until _end
+
+    def lnlike_end(self):
+        thetas, out = self._in_flight
+        try:
+            _lib.check(self._lib, self._lib.psfmc_lnlike_batch_end(self._handle))
+        finally:
+            self._in_flight = None
+        return out
+
     def lnlike_device(self, theta_ptr, n_batch, ld, lnl_ptr, stream=0,
                       device_slot=0):
         """Asynchronous evaluation on device-resident buffers (raw addresses,

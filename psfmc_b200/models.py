@@ -63,7 +63,6 @@ class MultiComponentModel(object):
         selector = config.psf_selector
         # batches of at least this many rows overlap the priors with the GPU call
         self.overlap_min_batch = 512
-        self._lnl_worker = None
         self.engine = LikelihoodEngine(
             config.obs_data, config.obs_var, config.bad_px,
             selector.psf_images, selector.var_images, config.mag_zeropoint,
@@ -346,15 +345,14 @@ class MultiComponentModel(object):
         """
         thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
         if thetas.shape[0] >= self.overlap_min_batch:
-            # large batches: the GPU call (ctypes drops the GIL) runs on a helper
-            # thread over ALL rows while the priors are evaluated here; rows with a
+            # large batches: the GPU works on ALL rows (psfmc_lnlike_batch_begin returns
+            # once they are enqueued) while the priors are evaluated here; rows with a
             # dead prior are evaluated for nothing and discarded
-            if self._lnl_worker is None:
-                from concurrent.futures import ThreadPoolExecutor
-                self._lnl_worker = ThreadPoolExecutor(max_workers=1)
-            pending = self._lnl_worker.submit(self.engine.lnlike, thetas)
-            lnprior = self.log_priors_batch(thetas)
-            lnl = pending.result()
+            self.engine.lnlike_begin(thetas)
+            try:
+                lnprior = self.log_priors_batch(thetas)
+            finally:
+                lnl = self.engine.lnlike_end()
             ok = np.isfinite(lnprior) & np.isfinite(lnl)
             with np.errstate(invalid='ignore'):
                 return np.where(ok, lnl + lnprior, -np.inf)

@@ -37,15 +37,22 @@ class BatchPool(object):
             if hasattr(func, 'kwargs') else self.model
         if target is not self.model:
             raise ValueError('BatchPool was built for a different model')
-        thetas = [np.asarray(p, dtype=np.float64) for p in iterable]
+        thetas = iterable if isinstance(iterable, list) else list(iterable)
         if not thetas:
             return []
-        block = np.stack(thetas)
+        try:
+            # emcee hands over the rows of one (B, D) array: one concatenation is 3-5x
+            # cheaper than stacking B one-row arrays
+            block = np.concatenate(thetas).reshape(len(thetas), -1)
+            if block.dtype != np.float64 or thetas[0].ndim != 1:
+                raise ValueError
+        except (ValueError, TypeError, AttributeError):
+            block = np.stack([np.asarray(p, dtype=np.float64) for p in thetas])
         lnpost = self.model.log_posterior_batch(block)
         self.calls += 1
         self.evaluations += len(thetas)
         if not self.with_blobs:
-            return [(float(v), {}) for v in lnpost]
+            return [(v, {}) for v in lnpost.tolist()]
         out = []
         alive = np.isfinite(self.model.log_priors_batch(block))
         imgs = self.model.engine.render(block[alive]) if alive.any() else {}
@@ -57,6 +64,24 @@ class BatchPool(object):
             out.append((float(value), {name: arr[cursor] for name, arr in imgs.items()}))
             cursor += 1
         return out
+
+    def map_batch(self, func, block):
+        """The same evaluation without the per-walker lists of emcee's protocol:
+        ``block`` (B, D) -> ``(lnpost (B,), blobs)`` with ``blobs`` None unless
+        ``with_blobs``. Used by this package's own sampler (sampler.py)."""
+        if not self.with_blobs:
+            target = getattr(func, 'kwargs', {}).get('model', self.model) \
+                if hasattr(func, 'kwargs') else self.model
+            if target is not self.model:
+                raise ValueError('BatchPool was built for a different model')
+            block = np.ascontiguousarray(block, dtype=np.float64)
+            lnpost = self.model.log_posterior_batch(block)
+            self.calls += 1
+            self.evaluations += len(block)
+            return lnpost, None
+        results = self.map(func, [block[i] for i in range(len(block))])
+        return (np.array([r[0] for r in results], dtype=np.float64),
+                [r[1] for r in results])
 
     # multiprocessing.Pool look-alikes some callers use
     def close(self):

@@ -154,6 +154,14 @@ class EnsembleSampler(object):
             raise ValueError('At least one parameter value was infinite.')
         if np.any(np.isnan(pos)):
             raise ValueError('At least one parameter value was NaN.')
+        if hasattr(self.pool, 'map_batch'):
+            # a pool that takes the ensemble as one array (BatchPool): no per-walker
+            # lists on the way in or out
+            lnprob, blob = self.pool.map_batch(self.lnprobfn, pos)
+            lnprob = np.array(lnprob, dtype=np.float64)
+            if np.any(np.isnan(lnprob)):
+                raise ValueError('lnprob returned NaN.')
+            return lnprob, blob
         mapper = self.pool.map if self.pool is not None else map
         results = list(mapper(self.lnprobfn, [pos[i] for i in range(len(pos))]))
         try:

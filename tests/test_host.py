@@ -318,6 +318,28 @@ def tiny_model(emu_library):
     return MultiComponentModel(comps, precision='fp32', library=emu_library)
 
 
+def test_split_host_call(tiny_model):
+    """psfmc_lnlike_batch_begin / _end: same numbers as the blocking call, one batch
+    in flight per engine, _end without _begin is an error."""
+    from psfmc_b200._lib import EngineError
+    engine = tiny_model.engine
+    thetas = tiny_model.init_params_from_priors(6)
+    want = engine.lnlike(thetas)
+    engine.lnlike_begin(thetas)
+    with pytest.raises(EngineError, match='in flight'):
+        engine.lnlike_begin(thetas)
+    assert np.array_equal(engine.lnlike_end(), want)
+    with pytest.raises(EngineError, match='no batch in flight'):
+        from psfmc_b200 import _lib
+        _lib.check(engine._lib, engine._lib.psfmc_lnlike_batch_end(engine._handle))
+    assert np.array_equal(engine.lnlike(thetas), want)
+    assert np.array_equal(tiny_model.log_posterior_batch(thetas[:1]),
+                          tiny_model.log_posterior_batch(thetas)[:1])
+    tiny_model.overlap_min_batch = 2          # overlapped priors on a small batch
+    lnpost = tiny_model.log_posterior_batch(thetas)
+    assert np.array_equal(lnpost, want + tiny_model.log_priors_batch(thetas))
+
+
 def test_batch_pool_is_a_drop_in_for_map(tiny_model):
     from psfmc_b200 import BatchPool
     from psfmc_b200.sampler import EnsembleSampler
@@ -339,6 +361,19 @@ def test_batch_pool_is_a_drop_in_for_map(tiny_model):
                                      'composite_ivm', 'point_source_subtracted'}
     assert with_blobs[2][1] == {}
     assert with_blobs[0][1]['raw_model'].shape == (32, 32)
+    # the array protocol of this package's own sampler: same numbers, no lists
+    lnpost, blobs = pool.map_batch(sampler.lnprobfn, thetas)
+    assert blobs is None and lnpost.tolist() == [b[0] for b in batched]
+    lnpost, blobs = BatchPool(model, with_blobs=True).map_batch(sampler.lnprobfn, thetas[:3])
+    assert lnpost.tolist() == [b[0] for b in batched[:3]] and blobs[2] == {}
+    assert np.array_equal(sampler._get_lnprob(thetas)[0], lnpost_all(batched))
+    # lists of Python lists / tuples still work (the slow stacking path)
+    assert [b[0] for b in pool.map(sampler.lnprobfn, [tuple(r) for r in thetas])] == \
+        [b[0] for b in batched]
+
+
+def lnpost_all(results):
+    return np.array([r[0] for r in results])
 
 
 def test_database_roundtrip(tmp_path, tiny_model):

@@ -44,6 +44,8 @@ def main():
     rows = [th[i] for i in range(len(th))]
     print('BatchPool.map (list in, list of tuples out) {:8.1f} us'.format(
         timed(lambda: bp.map(None, rows), calls)))
+    print('BatchPool.map_batch (array in, array out)   {:8.1f} us'.format(
+        timed(lambda: bp.map_batch(None, th), calls)))
 
 if __name__ == '__main__':
     main()
