@@ -117,6 +117,7 @@ struct DeviceState {
   float2 *ctw = nullptr;
   int n_clusters = 0;
   int n_sms = 148;
+  unsigned skip_quads = 0;   // fused 128 kernel: row quads without a good pixel
   // optional event pairs around the dominant kernel(s) of every lnL call
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
@@ -388,6 +389,7 @@ struct Engine : EngineBase {
       fb.ow = d.fow;
       fb.n_sms = d.n_sms;
       fb.wide = fused_wide;
+      fb.skip_quads = d.skip_quads;
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (profiling && (rc = prof_pair(d, &e0, &e1))) return rc;
       launches += launch_fused_lnlike<T>(plan, buf, fb, prog_h, theta_dev, B, ld, lnl_dev,
@@ -1212,6 +1214,16 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       if ((rc = upload(&ds.fspec, fspec)) || (rc = upload(&ds.fspecx, fspecx)) ||
           (rc = upload(&ds.fow, ow)))
         break;
+      // rows whose four-row group holds no good pixel never enter the sum
+      ds.skip_quads = 0;
+      const char *noskip = getenv("PSFMC_NO_ROW_SKIP");
+      if (!(noskip && noskip[0] == '1'))
+        for (int q = 0; q < 32; ++q) {
+          bool any_good = false;
+          for (size_t e = (size_t)q * 4 * N; e < (size_t)(q + 1) * 4 * N && !any_good; ++e)
+            any_good = !bad[e];
+          if (!any_good) ds.skip_quads |= 1u << q;
+        }
     }
     if (eng->path == 2) {
       if (cluster_prepare_device(&ds.n_clusters)) {

@@ -53,6 +53,8 @@ struct FusedParams {
   double *lnl;               // [B]
   long long n_batch;
   int ncomp;
+  unsigned skip_quads;       // bit q: rows 4q .. 4q+3 hold no good pixel (mask, bad pixels,
+                             // padding): their inverse row transform and epilogue are skipped
   signed char kind[PSFMC_MAX_COMPONENTS];
 };
 
@@ -335,6 +337,8 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
                                                      const FoldParams *F = nullptr) {
   const int y = it * 64 + R.w * 4 + R.rr;
   if (PADDED && y - R.rr >= F->Hr) return 0.0;   // the warp's four rows are padding
+  // ... or hold no unmasked pixel: nothing of them enters the sum (models.py:233-236)
+  if ((P.skip_quads >> (it * 16 + R.w)) & 1u) return 0.0;
   const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
   const bool l0 = R.l0;
   // observation + signed variance of this thread's 16 pixels: issued first, used
@@ -974,6 +978,7 @@ struct FusedBuffers {
   const float2 *ow = nullptr;
   int n_sms = 148;
   bool wide = false;   // 1024-thread variant
+  unsigned skip_quads = 0;   // see FusedParams
 };
 
 // theta -> lnL for n_batch walkers: prepare kernel + one persistent fused kernel.
@@ -1007,6 +1012,7 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
   P.lnl = lnl;
   P.n_batch = n_batch;
   P.ncomp = ncomp;
+  P.skip_quads = fb.skip_quads;
   for (int c = 0; c < PSFMC_MAX_COMPONENTS; ++c)
     P.kind[c] = (signed char)(c < ncomp ? prog_h.kind[c] : 0);
   unsigned grid = (unsigned)(n_batch < fb.n_sms ? n_batch : fb.n_sms);
