@@ -167,14 +167,19 @@ inline void launch_prepare(const Program &prog, const double *theta, long long n
   const char *env = getenv("PSFMC_PREPARE_GROUP");   // tests: 8 | 32 pins the variant
   const int forced = env ? atoi(env) : 0;
   const bool wide = forced ? forced == 32 : ngroups <= 4096;
+  // theta rows staged in shared memory: at most one row per group of the CTA
+  const size_t rows = (size_t)(block / (wide ? 32 : 8));
+  size_t smem = rows * (size_t)ld * sizeof(double);
+  const int stage = smem <= 40 * 1024 ? 1 : 0;
+  if (!stage) smem = 0;
   if (wide) {
     unsigned grid = (unsigned)((32 * ngroups + block - 1) / block);
-    launch_kernel(prepare_kernel<32>, dim3(grid), dim3(block), 0, stream, prog, theta, n_batch,
-                  ld, H, W, derived, psf_sel, wscale, rconst);
+    launch_kernel(prepare_kernel<32>, dim3(grid), dim3(block), smem, stream, prog, theta,
+                  n_batch, ld, H, W, derived, psf_sel, wscale, rconst, stage);
   } else {
     unsigned grid = (unsigned)((8 * ngroups + block - 1) / block);
-    launch_kernel(prepare_kernel<8>, dim3(grid), dim3(block), 0, stream, prog, theta, n_batch,
-                  ld, H, W, derived, psf_sel, wscale, rconst);
+    launch_kernel(prepare_kernel<8>, dim3(grid), dim3(block), smem, stream, prog, theta,
+                  n_batch, ld, H, W, derived, psf_sel, wscale, rconst, stage);
   }
 }
 
