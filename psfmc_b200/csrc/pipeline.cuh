@@ -162,25 +162,25 @@ inline StagedPlan make_padded_plan(int Hr, int Wr, int psf_h, int psf_w, int n_c
 inline void launch_prepare(const Program &prog, const double *theta, long long n_batch,
                            long long ld, int H, int W, int n_components, double *derived,
                            int *psf_sel, double *wscale, float *rconst, cudaStream_t stream) {
-  const long long ngroups = n_batch * (n_components > 0 ? n_components : 1);
+  const int ncomp = n_components > 0 ? n_components : 1;
+  const long long ngroups = n_batch * ncomp;
   const int block = 128;
   const char *env = getenv("PSFMC_PREPARE_GROUP");   // tests: 8 | 32 pins the variant
   const int forced = env ? atoi(env) : 0;
   const bool wide = forced ? forced == 32 : ngroups <= 4096;
-  // theta rows staged in shared memory: at most one row per group of the CTA
-  const size_t rows = (size_t)(block / (wide ? 32 : 8));
-  size_t smem = rows * (size_t)ld * sizeof(double);
+  // groups are numbered component-major, each component's run padded to whole CTAs
+  const int gpc = block / (wide ? 32 : 8);
+  const unsigned grid = (unsigned)(ncomp * ((n_batch + gpc - 1) / gpc));
+  // theta rows staged in shared memory: one row per group of the CTA
+  size_t smem = (size_t)gpc * (size_t)ld * sizeof(double);
   const int stage = smem <= 40 * 1024 ? 1 : 0;
   if (!stage) smem = 0;
-  if (wide) {
-    unsigned grid = (unsigned)((32 * ngroups + block - 1) / block);
+  if (wide)
     launch_kernel(prepare_kernel<32>, dim3(grid), dim3(block), smem, stream, prog, theta,
                   n_batch, ld, H, W, derived, psf_sel, wscale, rconst, stage);
-  } else {
-    unsigned grid = (unsigned)((8 * ngroups + block - 1) / block);
+  else
     launch_kernel(prepare_kernel<8>, dim3(grid), dim3(block), smem, stream, prog, theta,
                   n_batch, ld, H, W, derived, psf_sel, wscale, rconst, stage);
-  }
 }
 
 // Device-resident state the launch sequence needs (one per device per precision).

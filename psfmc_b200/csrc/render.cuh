@@ -112,21 +112,27 @@ __global__ void prepare_kernel(const __grid_constant__ Program prog_c,
   const int ncomp = ncomp_prog > 0 ? ncomp_prog : 1;   // an empty model still gets its
                                                        // per-walker PSF index and scale
   const int glane = threadIdx.x & (G - 1);
-  const long long gid0 = ((long long)blockIdx.x * blockDim.x) / G;   // always live
-  long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const bool live = gid < n_batch * ncomp;
-  if (!live) gid = gid0;                    // idle groups shadow the CTA's first group,
+  // Groups are numbered component-major, every component's run padded to whole CTAs:
+  // gid = c * n_pad + b. A warp then holds groups of ONE component kind (the Sky, point
+  // source and Sersic branches below no longer run one after the other in every warp)
+  // and a CTA the same component of consecutive walkers.
+  const int gpc = (int)blockDim.x / G;
+  const long long n_pad = (n_batch + gpc - 1) / gpc * gpc;
+  const long long gid0 = (long long)blockIdx.x * gpc;
+  const long long gid = gid0 + threadIdx.x / G;
+  const int c = (int)(gid / n_pad);
+  const long long b0 = gid0 - (long long)c * n_pad;   // the CTA's first walker: always live
+  long long b = gid - (long long)c * n_pad;
+  const bool live = b < n_batch;
+  if (!live) b = b0;                        // idle groups shadow the CTA's first group,
                                             // write nothing
   const bool writer = live && (glane == 0);
-  long long b = gid / ncomp;
-  int c = (int)(gid - b * ncomp);
   const double *th = theta + b * ld;
   if (stage) {
     double *th_s = reinterpret_cast<double *>(smem_raw);
-    const long long b0 = gid0 / ncomp;
-    long long gid1 = gid0 + (long long)blockDim.x / G - 1;
-    if (gid1 > n_batch * ncomp - 1) gid1 = n_batch * ncomp - 1;
-    const long long nel = (gid1 / ncomp - b0 + 1) * ld;
+    long long b1 = b0 + gpc;
+    if (b1 > n_batch) b1 = n_batch;
+    const long long nel = (b1 - b0) * ld;
     const double *src = theta + b0 * ld;
     for (long long e = threadIdx.x; e < nel; e += blockDim.x) th_s[e] = src[e];
     __syncthreads();
