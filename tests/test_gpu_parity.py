@@ -367,6 +367,39 @@ def test_gpu_fp64_rescue_inside_the_graph(cuda_library, c1_golden, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_gpu_split_host_call_and_overlapped_priors(cuda_library, c1_golden):
+    """psfmc_lnlike_batch_begin / _end on the GPU (plain launches and graph replay):
+    the numbers of the blocking call; log_posterior_batch with the priors evaluated
+    between the two halves equals lnL + lnprior of the separate calls."""
+    from conftest import HIGH_DYNAMIC_RANGE_THETAS, model_from_file
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model = model_from_file('j0005/model_c1.py', 'fp32', library=cuda_library,
+                            obs_dtype=np.float64)
+    engine = model.engine
+    thetas = draw_walkers_fast(model, 700, seed=9)
+    want = engine.lnlike(thetas)
+    engine.lnlike_begin(thetas)
+    lnprior = model.log_priors_batch(thetas)
+    assert np.array_equal(engine.lnlike_end(), want)
+    assert thetas.shape[0] >= model.overlap_min_batch
+    lnpost = model.log_posterior_batch(thetas)
+    ok = np.isfinite(lnprior) & np.isfinite(want)
+    assert np.array_equal(lnpost[ok], (want + lnprior)[ok]) and np.all(lnpost[~ok] == -np.inf)
+    # a walker that needs the float64 repeat arms the graph path for the next calls
+    thetas[11] = HIGH_DYNAMIC_RANGE_THETAS[0]
+    first = engine.lnlike(thetas)
+    assert np.isfinite(first[11]) and np.array_equal(np.delete(first, 11), np.delete(want, 11))
+    replays = engine.info()['graph_replays']
+    engine.lnlike_begin(thetas)
+    assert np.array_equal(engine.lnlike_end(), first)
+    lnprior = model.log_priors_batch(thetas)
+    ok = np.isfinite(lnprior) & np.isfinite(first)
+    assert np.array_equal(model.log_posterior_batch(thetas)[ok], (first + lnprior)[ok])
+    info = engine.info()
+    assert info['graph_replays'] == replays + 2 and info['rescued_on_device'] == 2
+
+
+@pytest.mark.gpu
 def test_gpu_fused_near_centre_walkers(cuda_library):
     from conftest import check_near_centre_walkers
     check_near_centre_walkers(cuda_library)
