@@ -104,8 +104,9 @@ __global__ void prepare_kernel(const __grid_constant__ Program prog_c,
                                float *__restrict__ rconst, int stage) {
   // stage: the theta rows of this CTA's walkers go through shared memory first, read
   // once with coalesced loads. (Tried on the B200: handing the kernel the caller's
-  // page-locked HOST rows instead of copying them first -- 304 us per 2048-walker call
-  // against 303 us with the H2D copy in front: the bus latency is the same either way.)
+  // page-locked HOST rows instead of copying them first -- per C-ABI call 70.6 us against
+  // 57.8 us with the H2D copy in front at 100 walkers, 120.6 / 113.4 us at 512, 304 / 303
+  // us at 2048: reads over the bus from inside a kernel cost more than the copy engine.)
   PSFMC_DYN_SMEM(smem_raw);
   const Program *prog = &prog_c;
   const int ncomp_prog = prog->n_components;

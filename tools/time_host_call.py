@@ -1,6 +1,7 @@
 """Host-timed anatomy of one 2048-walker C1 call: the blocking C-ABI call with pinned
 host buffers against the same kernels on device-resident theta (launch + sync only),
-and the device time of the kernels (CUDA events). Usage: python tools/time_host_call.py"""
+and the device time of the kernels (CUDA events).
+Usage: python tools/time_host_call.py [walkers per call = 2048]"""
 import os
 import sys
 import time
@@ -16,13 +17,14 @@ from psfmc_b200.synthetic import draw_walkers_fast  # noqa: E402
 
 
 def main():
-    calls = 300
-    half = 2048
+    half = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+    calls = 300 if half >= 1024 else 1000
     model = MultiComponentModel(build_components('c1'), precision='fp32', devices=[0],
                                 fp64_rescue=False)
     engine = model.engine
     th = draw_walkers_fast(model, half, seed=5)
     ndim = th.shape[1]
+    print('walkers per call', half)
     pin = torch.from_numpy(th).pin_memory()
     out = torch.empty(half, dtype=torch.float64).pin_memory()
     dev = torch.from_numpy(th).cuda()
