@@ -1411,7 +1411,14 @@ int psfmc_lnlike_batch_begin(psfmc_engine *engine, const double *theta, int64_t 
     return fail(PSFMC_ERR_INVALID_ARG, "null theta / lnl_out");
   int prev = 0;
   cudaGetDevice(&prev);
-  engine->impl->scan_wanted = engine->saved && engine->rescue_heat > 0;
+  // Graph replay (lnlike_host_graph): while a float64 repeat is likely, and always for
+  // batches of at most one walker per SM, where one graph launch instead of a copy and
+  // two kernel launches is worth more than the scan kernel costs (B200, C1, 100 walkers
+  // per call: 52.6 us against 57.6 us; 256 walkers: 78.4 against 76.9 us).
+  // PSFMC_GRAPH_ALWAYS=1 / 0 (experiments) forces / forbids the second rule.
+  const char *always = getenv("PSFMC_GRAPH_ALWAYS");
+  const bool small = always ? always[0] == '1' : n_batch <= 160;
+  engine->impl->scan_wanted = engine->saved && (engine->rescue_heat > 0 || small);
   int rc = engine->impl->lnlike_host_begin(theta, n_batch, ld, lnl_out);
   cudaSetDevice(prev);
   if (rc) return rc;

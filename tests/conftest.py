@@ -243,6 +243,9 @@ def check_fp64_rescue_on_device(library, c1_golden, monkeypatch):
     assert plain.engine.info()['graph_replays'] == 0
     assert want[33] == -np.inf and np.all(np.isfinite(np.delete(want, 33)))
     monkeypatch.delenv('PSFMC_NO_GRAPH')
+    # (batches of at most 160 walkers are replayed as graphs anyway: switch that rule
+    # off to see the arming by recent repeats on these small batches)
+    monkeypatch.setenv('PSFMC_GRAPH_ALWAYS', '0')
 
     model = model_from_file('j0005/model_c1.py', 'fp32', library=library,
                             obs_dtype=np.float64)
@@ -284,6 +287,13 @@ def check_fp64_rescue_on_device(library, c1_golden, monkeypatch):
     for _ in range(70):
         model.log_likelihood_batch(clean[:16])
     assert model.engine.info()['graph_replays'] - before == 64
+    # default rule: a batch of at most one walker per SM is always a graph replay
+    monkeypatch.delenv('PSFMC_GRAPH_ALWAYS')
+    before = model.engine.info()['graph_replays']
+    assert np.array_equal(model.log_likelihood_batch(batch), want)
+    assert np.array_equal(model.log_likelihood_batch(clean[:16]),
+                          np.delete(want, [5, 17, 33])[:16])
+    assert model.engine.info()['graph_replays'] - before == 2
 
 
 def check_near_centre_walkers(library):

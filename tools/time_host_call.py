@@ -20,7 +20,7 @@ def main():
     half = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
     calls = 300 if half >= 1024 else 1000
     model = MultiComponentModel(build_components('c1'), precision='fp32', devices=[0],
-                                fp64_rescue=False)
+                                fp64_rescue=os.environ.get('PSFMC_GRAPH_ALWAYS') == '1')
     engine = model.engine
     th = draw_walkers_fast(model, half, seed=5)
     ndim = th.shape[1]
