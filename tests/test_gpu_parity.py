@@ -3,6 +3,8 @@ Parity tests proper: the CUDA path on a real B200, called through the C ABI
 (ctypes -> libpsfmc_b200.so), against the golden vectors produced by the
 reference (tests/golden/make_golden.py) and against the oracle on seeded inputs.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -397,6 +399,43 @@ def test_gpu_split_host_call_and_overlapped_priors(cuda_library, c1_golden):
     assert np.array_equal(model.log_posterior_batch(thetas)[ok], (first + lnprior)[ok])
     info = engine.info()
     assert info['graph_replays'] == replays + 2 and info['rescued_on_device'] == 2
+
+
+@pytest.mark.gpu
+def test_gpu_masked_row_groups_are_skipped_exactly(cuda_library, monkeypatch):
+    """Fused 128 kernel: four-row groups without a good pixel skip their inverse
+    transform and epilogue -- bit-identical to transforming them (their pixels never
+    enter the sum), on the example's disc mask and on a mask that leaves one row group."""
+    from conftest import model_from_file
+    from psfmc_b200.synthetic import draw_walkers_fast
+    skipping = model_from_file('j0005/model_c1.py', 'fp32', library=cuda_library,
+                               fp64_rescue=False)
+    assert skipping.engine.info()['path'] == 1
+    thetas = draw_walkers_fast(skipping, 600, seed=4)
+    got = skipping.log_likelihood_batch(thetas)
+    monkeypatch.setenv('PSFMC_NO_ROW_SKIP', '1')
+    full = model_from_file('j0005/model_c1.py', 'fp32', library=cuda_library,
+                           fp64_rescue=False)
+    assert np.array_equal(full.log_likelihood_batch(thetas), got)
+    monkeypatch.delenv('PSFMC_NO_ROW_SKIP')
+    # everything masked except rows 60..63: 31 of the 32 groups drop out
+    from conftest import GOLDEN, j0005_arrays
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.components import Configuration
+    from psfmc_b200.model_parser import component_list_from_file
+    obs, ivm, _, psfs, ivms = j0005_arrays(np.float64)
+    mask = np.ones((128, 128), dtype=bool)
+    mask[60:64, 5:120] = False
+    comps = [c for c in component_list_from_file(os.path.join(GOLDEN, 'j0005/model_c1.py'))
+             if not isinstance(c, Configuration)]
+    config = Configuration(obs, ivm, psfs, ivms, mask_file=mask, mag_zeropoint=25.9463)
+    narrow = MultiComponentModel([config] + comps, precision='fp32', library=cuda_library,
+                                 fp64_rescue=False)
+    ref64 = MultiComponentModel([config] + comps, precision='fp64', library=cuda_library)
+    assert narrow.engine.info()['path'] == 1
+    assert int(np.sum(~np.asarray(narrow.config.bad_px, dtype=bool))) == 4 * 115
+    l32, l64 = narrow.log_likelihood_batch(thetas[:64]), ref64.log_likelihood_batch(thetas[:64])
+    assert_lnl_close(l32, l64, 'fp32', fp32_bounds(narrow, thetas[:64]))
 
 
 @pytest.mark.gpu
