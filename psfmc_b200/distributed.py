@@ -65,4 +65,10 @@ class ShardedPool(object):
             return []
         lnpost = sharded_lnlike(self.model.log_posterior_batch, np.stack(thetas),
                                 self.group)
-        return [(float(v), {}) for v in lnpost]
+        return [(v, {}) for v in lnpost.tolist()]
+
+    def map_batch(self, func, block):
+        """Array protocol of this package's sampler (cf. BatchPool.map_batch):
+        (B, D) -> ((B,) lnpost, None)."""
+        block = np.ascontiguousarray(block, dtype=np.float64)
+        return sharded_lnlike(self.model.log_posterior_batch, block, self.group), None
