@@ -115,22 +115,24 @@ __global__ void rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__
   } else {
     // float32 throughput path: Sky + Sersic in float, point-source taps in double.
     // RB*W == 8*nthreads, so every thread owns exactly 8 pixels.
-    float acc[8];
+    // Pixels are handled in pairs (packed FADD2 / FFMA2 arithmetic): pair j holds the
+    // thread's elements 2j and 2j+1.
+    cplx<float> acc[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    for (int j = 0; j < 4; ++j) acc[j] = mk<float>(0.0f, 0.0f);
     for (int c = 0; c < ncomp; ++c) {
       const double *d = der_s + c * PSFMC_DERIVED_STRIDE;
       const int kind = prog->kind[c];
       if (kind == PSFMC_SKY) {
-        const float adu = (float)d[D_SKY_ADU];
+        const cplx<float> adu = bcast((float)d[D_SKY_ADU]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += adu;
+        for (int j = 0; j < 4; ++j) acc[j] = acc[j] + adu;
       } else if (kind == PSFMC_POINT) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int e = tid + i * nthreads;
-          int r = e >> fr.logW, x = e & (W - 1);
-          acc[i] += (float)point_pixel(d, x, y0 + r);
+        for (int j = 0; j < 4; ++j) {
+          const int e0 = tid + 2 * j * nthreads, e1 = e0 + nthreads;
+          acc[j].x += (float)point_pixel(d, e0 & (W - 1), y0 + (e0 >> fr.logW));
+          acc[j].y += (float)point_pixel(d, e1 & (W - 1), y0 + (e1 >> fr.logW));
         }
       } else {
         SersicF32 s;
@@ -143,17 +145,18 @@ __global__ void rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__
         } else {
           s = make_sersic_f32(d);
         }
+        const cplx<float> xi = bcast(s.xi), xf = bcast(s.xf), yi = bcast(s.yi),
+                          yf = bcast(s.yf);
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) {   // two pixels per packed instruction
-          const int e0 = tid + i * nthreads, e1 = e0 + nthreads;
-          const int r0 = e0 >> fr.logW, x0 = e0 & (W - 1);
-          const int r1 = e1 >> fr.logW, x1 = e1 & (W - 1);
-          const cplx<float> dx = mk<float>(((float)x0 - s.xi) - s.xf, ((float)x1 - s.xi) - s.xf);
-          const cplx<float> dy = mk<float>(((float)(y0 + r0) - s.yi) - s.yf,
-                                           ((float)(y0 + r1) - s.yi) - s.yf);
-          const cplx<float> val = sersic_pair2_f32(s, dx, dy);
-          acc[i] += val.x;
-          acc[i + 1] += val.y;
+        for (int j = 0; j < 4; ++j) {
+          // (coordinate - integer part of the centre) is exact; its fraction goes last
+          const int e0 = tid + 2 * j * nthreads, e1 = e0 + nthreads;
+          const cplx<float> fx = mk<float>((float)(e0 & (W - 1)), (float)(e1 & (W - 1)));
+          const cplx<float> fy = mk<float>((float)(y0 + (e0 >> fr.logW)),
+                                           (float)(y0 + (e1 >> fr.logW)));
+          const cplx<float> dx = (fx - xi) - xf;
+          const cplx<float> dy = (fy - yi) - yf;
+          acc[j] = acc[j] + sersic_pair2_f32(s, dx, dy);
         }
       }
     }
@@ -161,9 +164,10 @@ __global__ void rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__
     for (int i = 0; i < 8; ++i) {
       int e = tid + i * nthreads;
       int r = e >> fr.logW, x = e & (W - 1);
-      if (x >= fr.Wr || y0 + r >= fr.Hr) acc[i] = 0.0f;   // padded frames
-      tile[r * PITCH + x] = mk<T>((T)acc[i], (T)(acc[i] * acc[i]) * wsc);
-      if (raw_out) raw_out[(b * H + (y0 + r)) * (long long)W + x] = (T)acc[i];
+      float a = (i & 1) ? acc[i >> 1].y : acc[i >> 1].x;
+      if (x >= fr.Wr || y0 + r >= fr.Hr) a = 0.0f;   // padded frames
+      tile[r * PITCH + x] = mk<T>((T)a, (T)(a * a) * wsc);
+      if (raw_out) raw_out[(b * H + (y0 + r)) * (long long)W + x] = (T)a;
     }
   }
   __syncthreads();
