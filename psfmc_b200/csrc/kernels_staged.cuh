@@ -43,8 +43,11 @@ __device__ __forceinline__ void load_twiddles(cplx<T> *tw_s, const cplx<T> *tw_g
 // dynamic smem: (RB*W + W) cplx<T> + n_components*STRIDE doubles
 // LOGW != 0: row length fixed at compile time (specialised instances for the
 // throughput path at 256 and 512 columns), 0: taken from `fr`.
+// (float32: at most 40 registers, six CTAs of 256 threads per SM -- the kernel is bound by
+// occupancy: 66 registers 543 us, 56 registers 537 us, 40 registers 520 us per 255-walker
+// chunk at 512 x 512; no spills)
 template <typename T, int SRC, int LOGW = 0>
-__global__ void rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__ prog,
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 6 : 1) rows_fwd_kernel(Frame fr_rt, int RB, const Program *__restrict__ prog,
                                 const double *__restrict__ derived,
                                 const double *__restrict__ wscale, int precision,
                                 const double *__restrict__ pad_a,
