@@ -1,3 +1,8 @@
+// Probe (not part of the product): do CUDA graph conditional IF nodes work on this
+// driver / toolkit without relocatable device code? A kernel arms the node with
+// cudaGraphSetConditional; the body graph is captured with cudaStreamBeginCaptureToGraph.
+// Expected output: "out" advances only on the launches whose flag is 1.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -o probe condgraph_probe.cu && ./probe
 #include <cuda_runtime.h>
 #include <cstdio>
 __global__ void setk(cudaGraphConditionalHandle h, const int *flag) {
