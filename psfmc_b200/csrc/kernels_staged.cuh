@@ -315,6 +315,7 @@ struct Epilogue<double> {
   }
 };
 // float32 arithmetic, float64 accumulation by the caller
+#define PSFMC_VAR_NOISE_TOL 0.00390625f   // 2^-8
 template <>
 struct Epilogue<float> {
   static __device__ __forceinline__ double term(float conv, float mvar, float obs,
@@ -324,7 +325,14 @@ struct Epilogue<float> {
     *resid = obs - conv;
     const float tot = mvar + ovar;
     *ivm = fast_rcp(tot);
-    const float lg = fmaf(0.69314718055994530942f, fast_lg2(tot), 1.8378770664093454836f);
+    float lg = fmaf(0.69314718055994530942f, fast_lg2(tot), 1.8378770664093454836f);
+    // The convolved model variance is non-negative in exact arithmetic. Where the
+    // float32 transform leaves it below -2^-8 of the pixel's own variance, its rounding
+    // noise (a model whose brightest pixel outshines the rest by ~1e5) is no longer small
+    // against the data: the walker is given up (NaN -> -inf -> repeated in float64 by
+    // psfmc_lnlike_batch) instead of returning an lnL tens to hundreds away from the
+    // reference's (audit of 65536 prior-drawn walkers).
+    if (fmaf(PSFMC_VAR_NOISE_TOL, ovar, mvar) < 0.0f) lg = NAN;
     return (double)fmaf((*resid) * (*resid), *ivm, lg);
   }
 };

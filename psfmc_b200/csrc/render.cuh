@@ -86,6 +86,8 @@ __device__ __forceinline__ float sersic_pixel_f32(const SersicF32 &s, float x, f
   return sb * (1.0f + (g * g) * fast_rcp(r2));
 }
 
+__device__ __forceinline__ double sersic_pixel(const double *d, double x, double y);
+
 // One G-lane GROUP per (walker, component): theta -> derived constants, float64.
 // The lanes of a group share the scalar work and split the incomplete-gamma series
 // of the Sersic kappa (devmath.cuh) and the point-source stamp taps; the four
@@ -267,6 +269,22 @@ __global__ void prepare_kernel(const __grid_constant__ Program prog_c,
       rc[0] = (float)out[D_SKY_ADU];
     } else if (kind == PSFMC_SERSIC) {
       SersicF32 s = make_sersic_f32(out);
+      // A very small index (n < 0.01: p = 1/(2n) > 50) overflows the reference's
+      // gradient term g * (sdr / 12 * g) in float64 at the far pixels of the frame:
+      // sb = 0 there, 0 * inf = NaN, and one NaN in the raw model makes the whole
+      // convolution NaN -> lnL = -inf (Sersic.py:129-133, models.py:238-241). The
+      // float32 formula clamps kq * t and would come out finite: evaluate the
+      // reference's own expression at the four frame corners (where sq, a convex
+      // quadratic, is largest) and poison the float32 constants if it is NaN there.
+      if (out[D_SER_P] > 20.0) {
+        bool poisoned = false;
+        for (int k = 0; k < 4; ++k) {
+          const double v = sersic_pixel(out, (k & 1) ? (double)(W - 1) : 0.0,
+                                        (k & 2) ? (double)(H - 1) : 0.0);
+          poisoned = poisoned || (v != v);
+        }
+        if (poisoned) s.c0 = NAN;
+      }
       rc[0] = s.xi; rc[1] = s.xf; rc[2] = s.yi; rc[3] = s.yf;
       rc[4] = s.a00; rc[5] = s.a01; rc[6] = s.a10; rc[7] = s.a11;
       rc[8] = s.p; rc[9] = s.c0; rc[10] = s.c1; rc[11] = s.kq;

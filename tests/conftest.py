@@ -296,6 +296,26 @@ def check_fp64_rescue_on_device(library, c1_golden, monkeypatch):
     assert model.engine.info()['graph_replays'] - before == 2
 
 
+def check_tiny_index_walkers(library):
+    """Sersic indices below 0.01: the reference's gradient term overflows in float64 at
+    the far pixels -> NaN -> lnL = -inf (golden values from the unmodified reference,
+    tests/golden/make_tiny_index_golden.py). The float32 kernels must not come out
+    finite there (their formula clamps the term); just above the overflow they agree
+    with the reference within the float32 bound."""
+    data = load_golden('c1_tiny_index.json')
+    thetas = np.array(data['theta'])
+    want = np.array([-np.inf if v is None else v for v in data['lnl_M3']])
+    dead = ~np.isfinite(want)
+    assert dead.sum() == 4 and (~dead).sum() == 2
+    for precision, kwargs in (('fp64', {}), ('fp32', {'fp64_rescue': False}), ('fp32', {})):
+        model = model_from_file('j0005/model_c1.py', precision, library=library,
+                                obs_dtype=np.float64, **kwargs)
+        got = model.log_likelihood_batch(thetas)
+        assert np.all(got[dead] == -np.inf), (precision, kwargs, got)
+        bounds = fp32_bounds(model, thetas[~dead]) if precision == 'fp32' else None
+        assert_lnl_close(got[~dead], want[~dead], precision, bounds)
+
+
 def check_near_centre_walkers(library):
     """Sersic centres within ~0.1 px of a pixel centre (steep central pixel): float32
     fused kernel against the oracle within the stated bound."""

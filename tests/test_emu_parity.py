@@ -252,6 +252,11 @@ def test_emu_fused_near_centre_walkers(emu_library):
     check_near_centre_walkers(emu_library)
 
 
+def test_emu_tiny_sersic_index_is_minus_inf_like_the_reference(emu_library):
+    from conftest import check_tiny_index_walkers
+    check_tiny_index_walkers(emu_library)
+
+
 def test_emu_cluster_kernel_256(emu_library, monkeypatch):
     """256 x 256 frame split over a four-CTA cluster (distributed shared memory,
     barrier.cluster emulated): two clusters walking over five walkers."""

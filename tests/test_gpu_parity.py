@@ -198,7 +198,13 @@ def test_full_size_properties(cuda_library):
     model.engine.lnlike_device(th_d.data_ptr(), len(thetas), thetas.shape[1],
                                out_d.data_ptr(), stream=stream)
     torch.cuda.synchronize()
-    assert np.array_equal(out_d.cpu().numpy(), full)
+    # (the device-pointer call returns the raw float32 results: the few walkers the
+    # float32 kernels give up on are repeated in float64 by the host call only)
+    got = out_d.cpu().numpy()
+    kept = np.isfinite(got)
+    assert np.array_equal(got[kept], full[kept])
+    assert np.all(got[~kept] == -np.inf) and (~kept).sum() <= 8
+    assert (~kept).sum() - (~np.isfinite(full)).sum() <= model.engine.info()['rescued_total']
     # a sample of the full batch against the oracle
     oracle = oracle_from_model(model)
     rows = np.arange(0, 4096, 256)
@@ -436,6 +442,12 @@ def test_gpu_masked_row_groups_are_skipped_exactly(cuda_library, monkeypatch):
     assert int(np.sum(~np.asarray(narrow.config.bad_px, dtype=bool))) == 4 * 115
     l32, l64 = narrow.log_likelihood_batch(thetas[:64]), ref64.log_likelihood_batch(thetas[:64])
     assert_lnl_close(l32, l64, 'fp32', fp32_bounds(narrow, thetas[:64]))
+
+
+@pytest.mark.gpu
+def test_gpu_tiny_sersic_index_is_minus_inf_like_the_reference(cuda_library):
+    from conftest import check_tiny_index_walkers
+    check_tiny_index_walkers(cuda_library)
 
 
 @pytest.mark.gpu

@@ -210,3 +210,18 @@ def test_cropped_frames_oracle_reproduces_reference_bitwise(tag, mode):
             imgs = oracle.images(thetas[row], with_point_source_subtracted=False)
             for key, want in case['pixels'][mode][row].items():
                 assert _same(imgs[key].ravel()[px], want), (mode, row, key)
+
+
+@pytest.mark.parametrize('mode', ['M2', 'M3'])
+def test_oracle_tiny_sersic_index_vectors(mode):
+    """Indices below 0.01: the reference's own -inf (overflow of its gradient term,
+    Sersic.py:129-133), frozen by tests/golden/make_tiny_index_golden.py; the oracle
+    reproduces them and the finite neighbours bit for bit."""
+    data = load_golden('c1_tiny_index.json')
+    thetas = np.array(data['theta'])
+    want = np.array([-np.inf if v is None else v for v in data['lnl_' + mode]])
+    assert np.sum(~np.isfinite(want)) == 4
+    oracle, _ = _oracle_j0005('j0005/model_c1.py', mode)
+    with np.errstate(all='ignore'):
+        got = oracle.lnlike_batch(thetas)
+    assert np.array_equal(got, want)
