@@ -66,7 +66,12 @@ extern "C" {
 #define PSFMC_PREC_FP64 0 /* everything in float64: parity mode, gated at 1e-10
                              relative against the all-float64 oracle (mode M3)     */
 #define PSFMC_PREC_FP32 1 /* float32 render + FFT, float64 chi-square accumulation:
-                             the throughput mode, gated at a stated |dlnL|          */
+                             the throughput mode, gated at a stated |dlnL|. A walker
+                             whose float32 transform is not trustworthy (a convolved
+                             model variance below -2^-8 of a pixel's own variance: the
+                             rounding noise of a model with a ~1e5 dynamic range) is
+                             returned as non-finite and, through psfmc_lnlike_batch,
+                             repeated in float64 (PSFMC_DESC_NO_FP64_RESCUE)        */
 #define PSFMC_PREC_FP64_RAWF32 2 /* as FP64 but the raw model is rounded to float32
                              after each component is added, which is what the
                              reference does for float32 FITS inputs on numpy 1.x
