@@ -5,18 +5,37 @@ bench.py -- model lnL evaluations per second (walkers x iterations).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c3|c4|s128]
                     [--walkers NW] [--impl ours|reference] [--precision fp32|fp64]
 
-One "step" is one emcee iteration of an NW-walker ensemble: the two sequentially
+One "step" is one emcee iteration of ONE NW-walker ensemble: the two sequentially
 dependent half-ensemble batches emcee 2.x maps per iteration (SURVEY.md section
 3.2), i.e. NW lnL evaluations through the hot path. The default workload is the
 J0005-0006 quasar+host model (C1 frame, 128^2, Sky + PointSource + 2 Sersic, D=18)
-for a 4096-walker ensemble per GPU -- the configuration BASELINE.json's north_star
-quotes its target on. Walkers shard over GPUs with no data-path collective
-(weak scaling: every rank evaluates its own NW-walker ensemble).
+for a 4096-walker ensemble -- the configuration BASELINE.json's north_star quotes
+its target on.
+
+Multi-GPU (torchrun, one rank per GPU): STRONG scaling. The one ensemble is sharded
+over the N ranks: every rank evaluates its contiguous rows of each half-ensemble
+on its own engine and the per-walker lnL is all-gathered (NCCL, B doubles) INSIDE
+the timed region, because the next half-ensemble's proposals depend on it. This
+is the pool.map of /root/reference/psfMC/fitting.py:55-58, timed as
+psfmc_b200.distributed.sharded_lnlike_device (device buffers, `value`) and
+ShardedPool.map_batch / .map (host buffers, `e2e`). The replica throughput (every
+rank its own ensemble, no gather; weak scaling) is reported beside it as
+`replicas_weak`.
 
 Prints ONE JSON line (rank 0). `value` = device-resident throughput (theta and
 lnL stay in HBM, CUDA events on the launching stream); `e2e` = the same metric
 through the C ABI with host buffers (pinned theta in, lnL out, copies inside the
-timed region).
+timed region); `e2e.pool_map` = through the emcee-facing list protocol
+(BatchPool.map / ShardedPool.map: row views in, (lnpost, blob) tuples out, priors
+included).
+
+`--impl reference` and the `cpu_baseline` leg run the UNMODIFIED reference
+(oracle/_ref/psfMC, placed there verbatim by oracle/make_ref.py; imported through
+oracle/refshim.py) on all host cores: its own MultiComponentModel.log_posterior
+(priors + the five blob images incl. point_source_subtracted, psfMC/models.py:193-243)
+in a multiprocessing pool with one model per worker, plus the lnL-only variant
+(priors and point_source_subtracted patched out) for a like-for-like comparison
+with the GPU arm. The oracle port is the fallback when oracle/_ref is missing.
 """
 import argparse
 import json
@@ -45,11 +64,15 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c1', choices=['c1', 'c3', 'c4', 's128'])
     ap.add_argument('--walkers', type=int, default=0,
-                    help='ensemble size per GPU (default: 4096 for c1/s128/c4, 1024 for c3)')
+                    help='size of THE ensemble, sharded over the GPUs '
+                         '(default: 4096 for c1/s128/c4, 1024 for c3)')
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp64'])
     ap.add_argument('--cpu-seconds', type=float, default=12.0,
                     help='budget of the cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-impl', default='auto', choices=['auto', 'reference', 'port'],
+                    help='CPU arm: the unmodified reference from oracle/_ref (default when '
+                         'present) or the oracle numpy port')
     return ap.parse_args()
 
 
@@ -63,7 +86,7 @@ def workload_description(name, walkers):
         'c4': 'C4 synthetic 512x512 PointSource + three Sersic, D=25',
         's128': 'synthetic 128x128, C1 component structure',
     }[name]
-    return '{}; {}-walker ensemble per GPU, 2 half-ensemble batches per step'.format(
+    return '{}; one {}-walker ensemble, 2 half-ensemble batches per step'.format(
         desc, walkers)
 
 
@@ -81,78 +104,170 @@ def build_components(name):
     return synthetic_components(size, n_sersic)
 
 
-def build_oracle(model_like):
-    """Oracle (CPU port of the reference path) over a model's arrays + program.
-    float32 inputs with float64 FFT/tail = the reference's pinned numpy-1.x
-    behaviour (mode M2)."""
-    from oracle import psfmc_oracle as orc
-    cfg = model_like['config']
-    return orc.OracleModel(cfg.obs_data, cfg.obs_var, cfg.bad_px,
-                           cfg.psf_selector.psf_images, cfg.psf_selector.var_images,
-                           cfg.mag_zeropoint, model_like['program'],
-                           model_like['psf_index_slot'], fft_upcast=True)
+def workload_model_file(name):
+    """The workload as a psfMC model file (what the reference's own model class
+    reads): C1 from tests/golden, the synthetic ones written to a scratch directory
+    with bit-identical arrays (psfmc_b200.synthetic.write_synthetic_files)."""
+    if name == 'c1':
+        return os.path.join(GOLDEN, 'j0005', 'model_c1.py')
+    import tempfile
+    from psfmc_b200.synthetic import WORKLOADS, write_synthetic_files
+    size, n_sersic, _ = WORKLOADS[name]
+    return write_synthetic_files(size, n_sersic, tempfile.mkdtemp(prefix='psfmc_bench_'))
 
 
-# ------------------------------------------------------- CPU baseline (port) --
+def host_model(name):
+    """Host-side pieces of the workload without an engine (components, number of
+    parameters, batched priors): draws the same walkers as the GPU arm on a box
+    whose GPU is not touched (reference arm)."""
+    from psfmc_b200.components import Configuration
+    from psfmc_b200.program import compile_program
+    comps = build_components(name)
+    config = [c for c in comps if isinstance(c, Configuration)][0]
+    rest = [c for c in comps if c is not config] + [config.psf_selector]
+    program, psf_slot, ndim = compile_program(rest)
+
+    class _Shim(object):
+        pass
+    shim = _Shim()
+    shim.components, shim.num_params, shim.config = rest, ndim, config
+    shim.program, shim.psf_index_slot = program, psf_slot
+
+    def log_priors_batch(thetas):
+        total, start = np.zeros(len(thetas)), 0
+        for comp in rest:
+            count = comp.num_stochastics()
+            total = total + comp.log_priors_batch(thetas[:, start:start + count])
+            start += count
+        return total
+    shim.log_priors_batch = log_priors_batch
+    return shim
+
+
+def ensemble(model, walkers, which):
+    """Seeded prior draws; ensemble `which` is the same on every rank and in both
+    arms (GPU and CPU)."""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    return draw_walkers_fast(model, walkers, seed=1000 + which)
+
+
+# ------------------------------------------------------------------ CPU arm --
+# The reference's CPU implementation of the path on the host cores: a
+# multiprocessing pool with one model per worker (the reference's own parallel hook
+# is emcee's pool.map; its model object is not picklable, psfMC/fitting.py:55,
+# hence one model per worker), OMP/MKL/OPENBLAS threads pinned to 1 per worker.
 
 _WORKER = {}
 
 
-def _worker_init(workload):
+def reference_available():
+    from oracle import refshim
+    return refshim.reference_available()
+
+
+def _worker_init(workload, kind, model_file):
     for var in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
         os.environ[var] = '1'
-    from psfmc_b200.components import Configuration
-    from psfmc_b200.program import compile_program
-    comps = build_components(workload)
-    config = [c for c in comps if isinstance(c, Configuration)][0]
-    rest = [c for c in comps if c is not config] + [config.psf_selector]
-    program, psf_slot, _ = compile_program(rest)
-    _WORKER['oracle'] = build_oracle({'config': config, 'program': program,
-                                      'psf_index_slot': psf_slot})
+    _WORKER['kind'] = kind
+    if kind == 'reference':
+        from oracle import refshim
+        # mode M1: what the unmodified reference computes under this box's numpy
+        # (float32 storage, complex64 FFT; SURVEY.md section 8c)
+        full = refshim.build_reference_model(model_file, 'M1')
+        lnl_only = refshim.build_reference_model(model_file, 'M1')
+        lnl_only.log_priors = lambda: 0.0               # psfMC/models.py:187-191
+        lnl_only.point_source_subtracted = lambda: None  # psfMC/models.py:296-306
+        _WORKER['full'], _WORKER['lnl_only'] = full, lnl_only
+        return
+    shim = host_model(workload)
+    from oracle import psfmc_oracle as orc
+    cfg = shim.config
+    # float32 inputs with float64 FFT/tail = the reference's pinned numpy-1.x
+    # behaviour (mode M2)
+    _WORKER['oracle'] = orc.OracleModel(
+        cfg.obs_data, cfg.obs_var, cfg.bad_px, cfg.psf_selector.psf_images,
+        cfg.psf_selector.var_images, cfg.mag_zeropoint, shim.program,
+        shim.psf_index_slot, fft_upcast=True)
 
 
-def _worker_eval(block):
+def _worker_eval(task):
+    variant, block = task
+    if _WORKER['kind'] == 'reference':
+        model = _WORKER[variant]
+        post = type(model).log_posterior
+        with np.errstate(all='ignore'):
+            return np.array([float(post(row, model=model)[0]) for row in block])
     return _WORKER['oracle'].lnlike_batch(block)
 
 
-class CpuPort(object):
-    """The oracle port on all host cores: a multiprocessing pool with one model per
-    worker (the reference's own parallel hook is emcee's pool.map; its model object
-    is not picklable, psfMC/fitting.py:55, hence one model per worker)."""
-
-    def __init__(self, workload):
+class CpuArm(object):
+    def __init__(self, workload, impl='auto'):
         import multiprocessing as mp
+        if impl == 'auto':
+            impl = 'reference' if reference_available() else 'port'
+        if impl == 'reference' and not reference_available():
+            raise SystemExit('bench.py: oracle/_ref is missing -- run oracle/make_ref.py '
+                             'where /root/reference exists')
+        self.kind = impl
         self.cores = os.cpu_count() or 1
+        model_file = workload_model_file(workload) if impl == 'reference' else None
         ctx = mp.get_context('fork')
         self.pool = ctx.Pool(self.cores, initializer=_worker_init,
-                             initargs=(workload,))
+                             initargs=(workload, impl, model_file))
 
-    def evaluate(self, thetas):
+    def evaluate(self, thetas, variant='full'):
         nblk = max(1, min(len(thetas), self.cores * 4))
-        blocks = np.array_split(thetas, nblk)
+        blocks = [(variant, blk) for blk in np.array_split(thetas, nblk)]
         return np.concatenate(self.pool.map(_worker_eval, blocks))
+
+    def rate(self, thetas, seconds, variant='full'):
+        """evaluations/s over about `seconds` of wall time, in calls of 4 walkers per
+        core (bounded sample of the ensemble)."""
+        self.evaluate(thetas[:self.cores], variant)            # warm the workers
+        per_call = min(len(thetas), max(self.cores * 4, 32))
+        done, start = 0, time.perf_counter()
+        while True:
+            lo = done % max(1, len(thetas) - per_call)
+            self.evaluate(thetas[lo:lo + per_call], variant)
+            done += per_call
+            elapsed = time.perf_counter() - start
+            if elapsed >= seconds:
+                return done / elapsed, done, elapsed
+
+    def describe(self):
+        if self.kind == 'reference':
+            return ('unmodified reference (oracle/_ref/psfMC via oracle/refshim.py, numpy '
+                    'branches: numexpr is not installed), MultiComponentModel.log_posterior '
+                    '= priors + 5 blob images + lnL, float32 storage / complex64 FFT (numpy '
+                    '{})'.format(np.__version__))
+        return 'oracle numpy port of the reference path, lnL only (oracle/_ref missing)'
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
 
-def time_cpu_port(workload, thetas, seconds):
-    port = CpuPort(workload)
+def cpu_baseline_block(workload, thetas, seconds, impl):
+    arm = CpuArm(workload, impl)
     try:
-        port.evaluate(thetas[:port.cores])            # warm the workers
-        per_call = max(port.cores * 4, 32)
-        done, start = 0, time.perf_counter()
-        while True:
-            lo = done % max(1, len(thetas) - per_call)
-            port.evaluate(thetas[lo:lo + per_call])
-            done += per_call
-            elapsed = time.perf_counter() - start
-            if elapsed >= seconds:
-                break
-        return done / elapsed, port.cores, done, elapsed
+        rate, count, elapsed = arm.rate(thetas, seconds * (0.6 if arm.kind == 'reference'
+                                                           else 1.0))
+        block = {
+            'value': round(rate, 1), 'unit': UNIT, 'cores': arm.cores,
+            'kind': arm.kind,
+            'sample': '{} evaluations of the same ensemble in {:.1f} s on {} worker '
+                      'processes; {}'.format(count, elapsed, arm.cores, arm.describe())}
+        if arm.kind == 'reference':
+            rate2, count2, elapsed2 = arm.rate(thetas, seconds * 0.4, 'lnl_only')
+            block['lnl_only'] = {
+                'value': round(rate2, 1), 'unit': UNIT,
+                'sample': '{} evaluations in {:.1f} s, log_priors and '
+                          'point_source_subtracted patched out (like-for-like with the '
+                          'GPU arm\'s lnL)'.format(count2, elapsed2)}
+            block['per_core'] = round(rate / arm.cores, 2)
+        return block
     finally:
-        port.close()
+        arm.close()
 
 
 # ------------------------------------------------------------------- clocks --
@@ -240,8 +355,9 @@ def run_ours(args):
     import torch.distributed as dist
     import __graft_entry__ as entry
     entry.build()
-    from psfmc_b200 import MultiComponentModel, fp32_peak_tflops
-    from psfmc_b200.synthetic import draw_walkers_fast
+    from psfmc_b200 import BatchPool, MultiComponentModel, fp32_peak_tflops
+    from psfmc_b200.distributed import (ShardedPool, shard_bounds,
+                                        sharded_lnlike_device)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -251,11 +367,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG >= VERSION; stdout must
-        # carry the one JSON line only: send NCCL's log to stderr
+        # stdout must carry the one JSON line only: NCCL's log (the version banner it
+        # prints at NCCL_DEBUG >= VERSION included) goes to stderr; NCCL_DEBUG itself
+        # is left as the launcher set it
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
-            del os.environ['NCCL_DEBUG']
         dist.init_process_group('nccl', device_id=dev)
 
     walkers = args.walkers or default_walkers(args.workload)
@@ -265,27 +380,73 @@ def run_ours(args):
     engine = model.engine
     ndim = model.num_params
     nsets = 4   # distinct ensembles cycled through, so no step repeats its input
-    thetas = [draw_walkers_fast(model, walkers, seed=1000 * rank + s) for s in range(nsets)]
+    thetas = [ensemble(model, walkers, s) for s in range(nsets)]   # same on every rank
     th_dev = [torch.from_numpy(t).to(dev) for t in thetas]
     th_pin = [torch.from_numpy(t).pin_memory() for t in thetas]
-    lnl_dev = torch.empty(walkers, dtype=torch.float64, device=dev)
+    bounds = shard_bounds(half, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    width = int(bounds[1] - bounds[0])
+    even = half % world == 0
+    lnl_dev = torch.zeros(2 * world * width, dtype=torch.float64, device=dev)
+    send = torch.zeros(width, dtype=torch.float64, device=dev)
+    lnl_own = torch.empty(walkers, dtype=torch.float64, device=dev)
     lnl_pin = torch.empty(walkers, dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def step_device(s):
+        """One emcee iteration of THE ensemble, device-resident: per half-ensemble this
+        rank's shard through the engine, then the lnL all-gather (NCCL) every rank needs
+        before it can propose the other half."""
         th = th_dev[s % nsets]
-        base = th.data_ptr()
         for h in range(2):     # two sequentially dependent half-ensembles
-            engine.lnlike_device(base + h * half * ndim * 8, half, ndim,
-                                 lnl_dev.data_ptr() + h * half * 8,
+            recv = lnl_dev[h * world * width:(h + 1) * world * width]
+            if world == 1:
+                engine.lnlike_device(th.data_ptr() + h * half * ndim * 8, half, ndim,
+                                     recv.data_ptr(), stream=stream.cuda_stream)
+            else:
+                sharded_lnlike_device(engine, th, half, ndim, send, recv, stream,
+                                      row_offset=h * half)
+
+    def step_replica(s):
+        """Weak-scaling companion: this rank evaluates a whole ensemble on its own."""
+        th = th_dev[s % nsets]
+        for h in range(2):
+            engine.lnlike_device(th.data_ptr() + h * half * ndim * 8, half, ndim,
+                                 lnl_own.data_ptr() + h * half * 8,
                                  stream=stream.cuda_stream)
 
+    pool = ShardedPool(model) if world > 1 else BatchPool(model)
+    lnlike_pool = None
+    if world > 1:
+        from psfmc_b200.distributed import ShardedEvaluator
+        lnlike_pool = ShardedEvaluator(lambda rows: engine.lnlike(rows))
+
     def step_host(s):
+        """The same iteration through the C ABI with host buffers: pinned theta in,
+        lnL out (N > 1: each rank its shard, then the gather to every rank's host)."""
         th = th_pin[s % nsets].numpy()
         out = lnl_pin.numpy()
         for h in range(2):
-            engine.lnlike(th[h * half:(h + 1) * half], out=out[h * half:(h + 1) * half])
+            rows = th[h * half:(h + 1) * half]
+            if world == 1:
+                engine.lnlike(rows, out=out[h * half:(h + 1) * half])
+            else:
+                out[h * half:(h + 1) * half] = lnlike_pool(rows)
+
+    def step_posterior(s):
+        th = thetas[s % nsets]
+        for h in range(2):
+            pool.map_batch(None, th[h * half:(h + 1) * half])
+
+    def step_pool_map(s):
+        """emcee 2.x's own protocol (EnsembleSampler._get_lnprob): a list of row views
+        in, a list of (lnpost, blob) out, the floats picked out again."""
+        th = thetas[s % nsets]
+        for h in range(2):
+            p = th[h * half:(h + 1) * half]
+            results = list(pool.map(None, [p[i] for i in range(len(p))]))
+            np.array([float(r[0]) for r in results])
 
     def barrier():
         if world > 1:
@@ -299,10 +460,21 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def host_timed(step, steps):
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(steps):
+            step(s)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0)
+
     sampler = ClockSampler(local)
-    for s in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for s in range(warm):
         step_device(s)
         step_host(s)
+        step_posterior(s)
+    step_pool_map(0)
     torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`) -------------------------------
@@ -329,45 +501,57 @@ def run_ours(args):
     total_ms_local = total_ms
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps
-    value = world * walkers / (ms_per_step * 1e-3)
+    value = walkers / (ms_per_step * 1e-3)
+
+    # ---- replicas (weak scaling, no gather) ---------------------------------
+    replicas = None
+    if world > 1:
+        rsteps = max(10, args.steps // 4)
+        for s in range(3):
+            step_replica(s)
+        barrier()
+        rep_ms = 0.0
+        for s in range(rsteps):
+            flush.fill_(s & 0xFF)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_replica(s)
+            e1.record(stream)
+            e1.synchronize()
+            rep_ms += e0.elapsed_time(e1)
+        rep_ms = max_over_ranks(rep_ms) / rsteps
+        replicas = {'value': round(world * walkers / (rep_ms * 1e-3), 1), 'unit': UNIT,
+                    'ms_per_step': round(rep_ms, 4), 'scaling': 'weak',
+                    'note': 'every rank evaluates its own {}-walker ensemble, no '
+                            'gather'.format(walkers)}
 
     # ---- end to end through the C ABI with host buffers (`e2e`) -------------
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        step_host(s)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * walkers * args.steps / e2e_s
-    rescued_per_step = engine.info()['rescued_total'] / float(
-        args.steps + max(args.warmup, 3))
+    rescued0 = engine.info()['rescued_total']
+    e2e_s = host_timed(step_host, args.steps)
+    e2e_value = walkers * args.steps / e2e_s
+    rescued_per_step = (engine.info()['rescued_total'] - rescued0) / float(args.steps)
     # the same loop with the float64 rescue of non-finite float32 results switched
     # off (for information: prior-drawn ensembles contain a few such walkers, the
     # walkers of a converged chain do not)
     e2e_raw = None
-    if args.precision == 'fp32':
+    if args.precision == 'fp32' and world == 1:
         raw_engine = MultiComponentModel(build_components(args.workload), precision='fp32',
                                          devices=[local], fp64_rescue=False).engine
         out = lnl_pin.numpy()
-        for s in range(3):
-            raw_engine.lnlike(th_pin[0].numpy()[:half], out=out[:half])
-        barrier()
-        t0 = time.perf_counter()
-        for s in range(args.steps):
+
+        def step_raw(s):
             th = th_pin[s % nsets].numpy()
             for h in range(2):
                 raw_engine.lnlike(th[h * half:(h + 1) * half],
                                   out=out[h * half:(h + 1) * half])
-        torch.cuda.synchronize()
-        e2e_raw = world * walkers * args.steps / max_over_ranks(time.perf_counter() - t0)
+        for s in range(3):
+            step_raw(s)
+        e2e_raw = walkers * args.steps / host_timed(step_raw, args.steps)
         raw_engine.close()
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        th = thetas[s % nsets]
-        for h in range(2):
-            model.log_posterior_batch(th[h * half:(h + 1) * half])
-    post_s = max_over_ranks(time.perf_counter() - t0)
+    post_s = host_timed(step_posterior, args.steps)
+    map_steps = max(10, args.steps // 3)
+    map_s = host_timed(step_pool_map, map_steps)
 
     info = engine.info()
     result = None
@@ -382,22 +566,26 @@ def run_ours(args):
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
         # dominant kernel: events around each launch on the launching stream
         kernel_us = 1e3 * kernel_ms / max(kernel_launches, 1)
-        evals_per_launch = half
+        evals_per_launch = hi - lo
         achieved = info['flops_per_eval'] * evals_per_launch / (kernel_us * 1e-6) / 1e12
         fft_achieved = info['fft_flops_per_eval'] * evals_per_launch / (kernel_us * 1e-6) / 1e12
-        # dram__bytes of one launch of the dominant kernel from the committed ncu capture
-        # of the same workload (profiles/), when there is one
+        # dram__bytes and the executed FP32 operation count of one launch of the dominant
+        # kernel, from the committed ncu capture of the same workload (profiles/)
         ncu = {}
-        ncu_file = {('c1', 1): 'r1_fused_ncu_summary.json',
-                    ('c3', 2): 'r1_cluster256_ncu_summary.json'}.get(
+        ncu_file = {('c1', 1): 'r2_fused_ncu_summary.json',
+                    ('c3', 2): 'r2_cluster256_ncu_summary.json'}.get(
                         (args.workload, info['path']))
-        if ncu_file and args.walkers == 0:
-            try:
-                with open(os.path.join(ROOT, 'profiles', ncu_file)) as fobj:
-                    ncu = json.load(fobj)
-            except (OSError, ValueError):
-                pass
+        if ncu_file and args.walkers == 0 and world == 1:
+            for name in (ncu_file, ncu_file.replace('r2_', 'r1_')):
+                try:
+                    with open(os.path.join(ROOT, 'profiles', name)) as fobj:
+                        ncu = json.load(fobj)
+                    ncu['file'] = 'profiles/' + name
+                    break
+                except (OSError, ValueError):
+                    continue
         traffic = ncu.get('dram_bytes_per_launch')
+        executed = ncu.get('executed_fp32_flop_per_launch')
         roofline = {
             'bound': 'fp32',
             'achieved': round(achieved, 3), 'peak': round(peak_probe, 2),
@@ -412,10 +600,13 @@ def run_ours(args):
             'note': 'FP32 CUDA-core bound path (north_star: no tensor cores; SURVEY.md 8d). '
                     'achieved = (10 N log2 N + (30 n_sersic + 16) N) FLOP/eval x evals per '
                     'launch / mean launch duration of the dominant kernel (CUDA events on the '
-                    'launching stream inside the timed region); peak = FP32 FMA throughput '
-                    'probed in this run (MEASURED_PEAKS.json has no FP32 entry). FFT '
-                    'butterflies are mostly adds, so the practical ceiling of this path is '
-                    'about half of the FMA peak (DESIGN.md).',
+                    'launching stream inside the timed region); this nominal count covers the '
+                    'full frame although row groups without an unmasked pixel skip their '
+                    'inverse transform. peak = FP32 FMA throughput probed in this run, the '
+                    'better of scalar FFMA and packed FFMA2 (MEASURED_PEAKS.json has no FP32 '
+                    'entry). FFT butterflies are mostly adds (1 FLOP per lane and clock), so '
+                    'the practical ceiling of this path is about half of the FMA peak '
+                    '(DESIGN.md).',
             'fft_stage_achieved': round(fft_achieved, 3),
             'fft_stage_frac': round(fft_achieved / peak_probe, 4),
             'flops_per_eval': info['flops_per_eval'],
@@ -426,42 +617,58 @@ def run_ours(args):
                     'bytes_per_eval': info['hbm_bytes_per_eval']},
             'engine_path': {1: 'fused', 2: 'fused-cluster4'}.get(info['path'], 'staged'),
         }
+        if executed:
+            # FP32 operations the kernel really executed (ncu op mix: FADD2/FMUL2 = 2,
+            # FFMA2 = 4, FADD/FMUL = 1, FFMA = 2 per thread) -- stated beside the nominal
+            # count above; scaled to this run's launch duration
+            ex_tflops = executed / (kernel_us * 1e-6) / 1e12 * (
+                evals_per_launch / float(ncu.get('evals_per_launch', evals_per_launch)))
+            roofline['executed'] = {'achieved': round(ex_tflops, 3),
+                                    'frac': round(ex_tflops / peak_probe, 4),
+                                    'flop_per_launch': executed, 'source': ncu.get('file')}
         result = {
             'metric': METRIC, 'value': round(value, 1), 'unit': UNIT,
-            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'n_gpus': world, 'steps': args.steps, 'warmup': warm,
             'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None,
+            'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f32 render+FFT / f64 accumulate' if args.precision == 'fp32' else 'f64',
             'data': 'synthetic walkers drawn from the model priors (seeded); '
                     + ('J0005-0006 example frames' if args.workload == 'c1'
                        else 'synthetic frames'),
             'config': {'workload': workload_description(args.workload, walkers),
-                       'walkers_per_gpu': walkers, 'batch_per_launch': half,
-                       'ndim': ndim, 'frame': list(engine.shape),
-                       'l2': 'flushed (256 MiB write) between timed steps'},
+                       'walkers': walkers, 'batch_per_launch': half,
+                       'ndim': ndim, 'frame': list(engine.shape)},
+            'l2': 'flushed (256 MiB write) between timed steps',
+            'sharding': {'ranks': world, 'rows_per_rank_per_half': hi - lo,
+                         'gather': 'none' if world == 1 else
+                                   'NCCL all_gather_into_tensor of {} doubles per '
+                                   'half-ensemble, inside the timed region'.format(half),
+                         'even': bool(even)},
             'e2e': {'value': round(e2e_value, 1), 'unit': UNIT,
-                    'h2d_bytes_per_step': walkers * ndim * 8,
+                    'h2d_bytes_per_step': (hi - lo) * 2 * ndim * 8,
                     'd2h_bytes_per_step': walkers * 8,
-                    'timer': 'host perf_counter around blocking C-ABI calls '
-                             '(psfmc_lnlike_batch), max over ranks',
-                    'with_python_priors': round(world * walkers * args.steps / post_s, 1),
+                    'timer': 'host perf_counter around blocking calls (psfmc_lnlike_batch; '
+                             'N > 1: + the gather to every rank\'s host), max over ranks',
+                    'with_python_priors': round(walkers * args.steps / post_s, 1),
+                    'pool_map': round(walkers * map_steps / map_s, 1),
+                    'pool_map_note': 'emcee 2.x list protocol through {}.map: row views in, '
+                                     '(lnpost, blob) tuples out, priors included'.format(
+                                         type(pool).__name__),
                     'fp64_rescued_walkers_per_step': round(rescued_per_step, 2),
                     'without_fp64_rescue': None if e2e_raw is None else round(e2e_raw, 1)},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': roofline,
         }
-    if rank == 0 and not args.no_cpu_baseline:
-        rate, cores, count, elapsed = time_cpu_port(args.workload, thetas[0],
-                                                    args.cpu_seconds)
-        result['cpu_baseline'] = {
-            'value': round(rate, 1), 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '{} evaluations of the same workload in {:.1f} s on {} worker '
-                      'processes (oracle numpy port of the reference path, lnL only: no '
-                      'priors, no point-source-subtracted blob)'.format(count, elapsed, cores)}
+        if replicas:
+            result['replicas_weak'] = replicas
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    model.engine.close()
+    if rank == 0 and not args.no_cpu_baseline:
+        result['cpu_baseline'] = cpu_baseline_block(args.workload, thetas[0],
+                                                    args.cpu_seconds, args.cpu_impl)
     if rank == 0:
         print(json.dumps(result))
 
@@ -469,68 +676,64 @@ def run_ours(args):
 # ------------------------------------------------------------ reference arm --
 
 def run_reference(args):
-    """The reference's CPU implementation of the path on the host cores. The
-    reference is pure Python and cannot travel to the GPU box, so this runs its
-    oracle port (oracle/psfmc_oracle.py, pinned bit-for-bit against the reference
-    by tests/golden/make_golden.py) on all host cores."""
+    """The reference's CPU implementation of the path on the host cores: the
+    UNMODIFIED reference's MultiComponentModel.log_posterior (oracle/_ref, see the
+    module docstring) on all host cores; the oracle port if oracle/_ref is absent.
+    Each step evaluates a bounded sample of the ensemble so that the whole run ends
+    within minutes. Rank 0 only."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from psfmc_b200.components import Configuration
-    from psfmc_b200.program import compile_program
     walkers = args.walkers or default_walkers(args.workload)
-    comps = build_components(args.workload)
-    config = [c for c in comps if isinstance(c, Configuration)][0]
-    rest = [c for c in comps if c is not config] + [config.psf_selector]
-    _, _, ndim = compile_program(rest)
+    shim = host_model(args.workload)
+    ndim = shim.num_params
+    thetas = ensemble(shim, walkers, 0)
 
-    class _Shim(object):     # priors only, to draw the same walkers as the GPU arm
-        pass
-    from psfmc_b200.synthetic import draw_walkers_fast
-    shim = _Shim()
-    shim.components = rest
-    shim.num_params = ndim
-
-    def log_priors_batch(thetas):
-        total, start = np.zeros(len(thetas)), 0
-        for comp in rest:
-            count = comp.num_stochastics()
-            total = total + comp.log_priors_batch(thetas[:, start:start + count])
-            start += count
-        return total
-    shim.log_priors_batch = log_priors_batch
-    thetas = draw_walkers_fast(shim, walkers, seed=0)
-
-    port = CpuPort(args.workload)
+    arm = CpuArm(args.workload, args.cpu_impl)
     # bounded sample per step so that the whole run ends within minutes
-    probe = port.cores * 4
+    probe = arm.cores * 2
+    arm.evaluate(thetas[:arm.cores])
     t0 = time.perf_counter()
-    port.evaluate(thetas[:probe])
+    arm.evaluate(thetas[:probe])
     per_eval = (time.perf_counter() - t0) / probe
     total_steps = args.steps + args.warmup
-    sample = int(min(walkers, max(port.cores * 4, 60.0 / max(total_steps, 1) / per_eval)))
+    sample = int(min(walkers, max(arm.cores * 4, 60.0 / max(total_steps, 1) / per_eval)))
     for s in range(args.warmup):
-        port.evaluate(thetas[:sample])
+        arm.evaluate(thetas[:sample])
     t0 = time.perf_counter()
     for s in range(args.steps):
         lo = (s * sample) % max(1, walkers - sample)
-        port.evaluate(thetas[lo:lo + sample])
+        arm.evaluate(thetas[lo:lo + sample])
     elapsed = time.perf_counter() - t0
-    port.close()
     rate = sample * args.steps / elapsed
-    sample_text = ('{} of the {} evaluations of a step, per step, on {} worker processes '
-                   '(oracle numpy port, lnL only)'.format(sample, walkers, port.cores))
+    extra = {}
+    if arm.kind == 'reference':
+        rate2, count2, elapsed2 = arm.rate(thetas, 8.0, 'lnl_only')
+        extra = {'lnl_only': {'value': round(rate2, 1), 'unit': UNIT,
+                              'sample': '{} evaluations in {:.1f} s, log_priors and '
+                                        'point_source_subtracted patched out'.format(
+                                            count2, elapsed2)},
+                 'per_core': round(rate / arm.cores, 2)}
+    arm.close()
+    sample_text = ('{} of the {} evaluations of a step, per step, on {} worker processes; '
+                   '{}'.format(sample, walkers, arm.cores, arm.describe()))
+    baseline = {'value': round(rate, 1), 'unit': UNIT, 'cores': arm.cores,
+                'kind': arm.kind, 'sample': sample_text}
+    baseline.update(extra)
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': round(rate, 1), 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': round(1e3 * elapsed / args.steps, 3), 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 (numpy, float32 storage)',
-        'data': 'synthetic walkers drawn from the model priors (seeded)',
+        'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32 storage / complex64 FFT (numpy {})'.format(np.__version__)
+                 if arm.kind == 'reference' else 'f64 (numpy, float32 storage)',
+        'data': 'synthetic walkers drawn from the model priors (seeded); '
+                + ('J0005-0006 example frames' if args.workload == 'c1'
+                   else 'synthetic frames'),
         'config': {'workload': workload_description(args.workload, walkers),
-                   'walkers_per_gpu': walkers, 'batch_per_launch': walkers // 2,
-                   'ndim': ndim, 'frame': list(config.obs_data.shape)},
-        'cpu_baseline': {'value': round(rate, 1), 'unit': UNIT, 'cores': port.cores,
-                         'kind': 'port', 'sample': sample_text},
+                   'walkers': walkers, 'batch_per_launch': walkers // 2,
+                   'ndim': ndim, 'frame': list(shim.config.obs_data.shape)},
+        'cpu_baseline': baseline,
         'e2e': {'value': round(rate, 1), 'unit': UNIT, 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }))

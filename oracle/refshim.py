@@ -12,9 +12,12 @@ numexpr, pyregion, matplotlib and corner are not installed, and numpy 2 / scipy
   * ``astropy.io.fits`` -> psfmc_b200.fitsio (getdata/getheader/writeto; raises
     IOError on non-FITS input, which psfMC/utils.py:87-90 relies on)
   * ``pyregion`` -> a stand-in over psfmc_b200.regions (image-frame shapes)
-and then imports ``psfMC`` from ``/root/reference``. Nothing under /root/reference
-is modified or copied. /root/reference does not exist on the GPU box, so nothing
-in the ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may import this module.
+and then imports ``psfMC`` from ``/root/reference`` -- or, where that does not exist
+(the GPU box), from the verbatim copy ``oracle/make_ref.py`` placed under
+``oracle/_ref`` (git-ignored). Nothing of the reference is modified. Importers: the CPU
+test tier, tests/golden/make_golden.py, and the CPU arm of bench.py (``--impl
+reference`` and the ``cpu_baseline`` leg) -- never the product, never the ``-m gpu``
+tests or ``smoke()``.
 
 Precision modes:
   M1  numpy-2 native: float32 storage, complex64 FFT, float32 reduce
@@ -29,8 +32,22 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get('PSFMC_REFERENCE_ROOT', '/root/reference')
 _REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reference_root():
+    """Where the unmodified reference package lives: $PSFMC_REFERENCE_ROOT, else
+    /root/reference (this container), else the verbatim copy oracle/make_ref.py
+    placed under oracle/_ref (the GPU box; git-ignored)."""
+    env = os.environ.get('PSFMC_REFERENCE_ROOT')
+    if env:
+        return env
+    if os.path.isdir('/root/reference/psfMC'):
+        return '/root/reference'
+    return os.path.join(_REPO_ROOT, 'oracle', '_ref')
+
+
+REFERENCE_ROOT = _reference_root()
 
 _state = {'mode': 'M1', 'loaded': False}
 
@@ -135,6 +152,13 @@ def load_reference():
         raise ImportError('reference not present at ' + REFERENCE_ROOT)
     if not _state['loaded']:
         _install_stubs()
+        # psfmc_b200.model_parser registers a stand-in ``psfMC`` module (so that model
+        # files importing from psfMC keep working where the package is not installed):
+        # drop it, the real package is wanted here
+        for name in [n for n in sys.modules if n == 'psfMC' or n.startswith('psfMC.')]:
+            origin = getattr(sys.modules[name], '__file__', None) or ''
+            if not origin.startswith(REFERENCE_ROOT):
+                del sys.modules[name]
         if REFERENCE_ROOT not in sys.path:
             sys.path.insert(0, REFERENCE_ROOT)
         import warnings

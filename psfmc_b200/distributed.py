@@ -5,8 +5,13 @@ group, every rank evaluates its rows on its own engine (constants replicated at
 engine creation), and the per-walker lnL is gathered back -- B doubles, the only
 cross-rank traffic. No collective touches the data path of the kernels.
 
-Backend: ``nccl`` on GPU boxes (tensors on the rank's device), ``gloo`` for the
-CPU test tier.
+This is the pool.map of /root/reference/psfMC/fitting.py:55-58 (the reference
+builds its sampler without a pool; emcee's hook for parallel evaluation is
+``pool.map``) for a job launched with torchrun: every rank runs the same seeded
+sampler and evaluates only its shard of every (half-)ensemble.
+
+Backend: ``nccl`` on GPU boxes (all_gather_into_tensor on the ranks' devices),
+``gloo`` for the CPU test tier.
 """
 import numpy as np
 
@@ -20,35 +25,100 @@ def shard_bounds(n_rows, world_size):
     return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
 
 
-def sharded_lnlike(evaluate, thetas, group=None):
-    """
-    :param evaluate: callable (rows, D) -> (rows,) lnL for this rank's rows
+class ShardedEvaluator(object):
+    """Sharded evaluation of (B, D) batches with reusable staging buffers.
+
+    :param evaluate: callable (rows, D) -> (rows,) for this rank's rows
         (e.g. ``model.log_likelihood_batch`` or ``model.log_posterior_batch``)
-    :param thetas: the FULL (B, D) batch, identical on every rank
-    :return: (B,) lnL on every rank
+    :param group: torch.distributed process group (default: the world)
     """
-    import torch
+
+    def __init__(self, evaluate, group=None):
+        self.evaluate = evaluate
+        self.group = group
+        self._width = 0
+        self._send = self._recv = self._send_host = self._recv_host = None
+
+    def _buffers(self, width, world, device):
+        import torch
+        if width > self._width or self._send is None or self._send.device != device:
+            self._width = max(width, 2 * self._width)
+            pin = device.type == 'cuda'
+            self._send = torch.zeros(self._width, dtype=torch.float64, device=device)
+            self._recv = torch.zeros(world * self._width, dtype=torch.float64, device=device)
+            self._send_host = torch.zeros(self._width, dtype=torch.float64, pin_memory=pin)
+            self._recv_host = torch.zeros(world * self._width, dtype=torch.float64,
+                                          pin_memory=pin)
+        return self._send, self._recv, self._send_host, self._recv_host
+
+    def __call__(self, thetas):
+        """:param thetas: the FULL (B, D) batch, identical on every rank
+        :return: (B,) results on every rank"""
+        import torch
+        import torch.distributed as dist
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        if not (dist.is_available() and dist.is_initialized()):
+            return np.asarray(self.evaluate(thetas), dtype=np.float64)
+        group = self.group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n_rows = len(thetas)
+        if world == 1 or n_rows == 0:
+            return np.asarray(self.evaluate(thetas), dtype=np.float64)
+        bounds = shard_bounds(n_rows, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        mine = np.asarray(self.evaluate(thetas[lo:hi]), dtype=np.float64) if hi > lo \
+            else np.zeros(0)
+        width = int(bounds[1] - bounds[0])          # the largest shard
+        nccl = dist.get_backend(group) == 'nccl'
+        device = torch.device('cuda', torch.cuda.current_device()) if nccl \
+            else torch.device('cpu')
+        send, recv, send_host, recv_host = self._buffers(width, world, device)
+        stride = self._width
+        if nccl:
+            send_host.numpy()[:hi - lo] = mine
+            send.copy_(send_host, non_blocking=True)
+            dist.all_gather_into_tensor(recv, send, group=group)
+            recv_host.copy_(recv, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            flat = recv_host.numpy()
+        else:
+            send.numpy()[:hi - lo] = mine
+            pieces = list(recv.view(world, stride).unbind(0))
+            dist.all_gather(pieces, send, group=group)
+            flat = recv.numpy()
+        out = np.empty(n_rows, dtype=np.float64)
+        for r in range(world):
+            count = int(bounds[r + 1] - bounds[r])
+            out[bounds[r]:bounds[r + 1]] = flat[r * stride:r * stride + count]
+        return out
+
+
+def sharded_lnlike(evaluate, thetas, group=None):
+    """One-shot form of :class:`ShardedEvaluator` (allocates its buffers per call)."""
+    return ShardedEvaluator(evaluate, group)(thetas)
+
+
+def sharded_lnlike_device(engine, theta_dev, n_rows, ld, send, recv, stream, group=None,
+                          row_offset=0):
+    """Device-resident form (NCCL): ``theta_dev`` is a float64 CUDA tensor holding the
+    FULL batch on every rank; this rank's engine evaluates its shard straight into
+    ``send`` and one ``all_gather_into_tensor`` fills ``recv`` -- laid out
+    [world][len(send)], i.e. the (B,) lnL vector itself when B divides evenly.
+    Everything is enqueued on ``stream`` (the current torch stream); nothing blocks.
+
+    :return: (bounds, width) of the split
+    """
     import torch.distributed as dist
-    thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
-    if not (dist.is_available() and dist.is_initialized()):
-        return np.asarray(evaluate(thetas), dtype=np.float64)
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    bounds = shard_bounds(len(thetas), world)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    bounds = shard_bounds(n_rows, world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    mine = np.asarray(evaluate(thetas[lo:hi]), dtype=np.float64) if hi > lo \
-        else np.zeros(0)
-    width = int(np.max(np.diff(bounds))) if len(thetas) else 0
-    device = torch.device('cuda', torch.cuda.current_device()) \
-        if dist.get_backend(group) == 'nccl' else torch.device('cpu')
-    send = torch.zeros(max(width, 1), dtype=torch.float64, device=device)
-    send[:hi - lo] = torch.from_numpy(mine).to(device)
-    gathered = [torch.empty_like(send) for _ in range(world)]
-    dist.all_gather(gathered, send, group=group)
-    out = np.empty(len(thetas), dtype=np.float64)
-    for r in range(world):
-        out[bounds[r]:bounds[r + 1]] = \
-            gathered[r][:bounds[r + 1] - bounds[r]].cpu().numpy()
-    return out
+    if hi > lo:
+        engine.lnlike_device(theta_dev.data_ptr() + (row_offset + lo) * ld * 8, hi - lo, ld,
+                             send.data_ptr(), stream=stream.cuda_stream)
+    if world > 1:
+        dist.all_gather_into_tensor(recv, send, group=group)
+    return bounds, int(bounds[1] - bounds[0])
 
 
 class ShardedPool(object):
@@ -58,17 +128,29 @@ class ShardedPool(object):
     def __init__(self, model, group=None):
         self.model = model
         self.group = group
+        self._evaluator = ShardedEvaluator(model.log_posterior_batch, group)
 
     def map(self, func, iterable):
-        thetas = [np.asarray(p, dtype=np.float64) for p in iterable]
+        thetas = iterable if isinstance(iterable, list) else list(iterable)
         if not thetas:
             return []
-        lnpost = sharded_lnlike(self.model.log_posterior_batch, np.stack(thetas),
-                                self.group)
+        try:
+            block = np.concatenate(thetas).reshape(len(thetas), -1)
+            if block.dtype != np.float64 or thetas[0].ndim != 1:
+                raise ValueError
+        except (ValueError, TypeError, AttributeError):
+            block = np.stack([np.asarray(p, dtype=np.float64) for p in thetas])
+        lnpost = self._evaluator(block)
         return [(v, {}) for v in lnpost.tolist()]
 
     def map_batch(self, func, block):
         """Array protocol of this package's sampler (cf. BatchPool.map_batch):
         (B, D) -> ((B,) lnpost, None)."""
         block = np.ascontiguousarray(block, dtype=np.float64)
-        return sharded_lnlike(self.model.log_posterior_batch, block, self.group), None
+        return self._evaluator(block), None
+
+    def close(self):
+        pass
+
+    def join(self):
+        pass

@@ -193,6 +193,9 @@ class LikelihoodEngine(object):
         """Blob images (psfMC/models.py:222-226) as dict name -> (B, H, W)."""
         thetas = np.ascontiguousarray(np.atleast_2d(thetas), dtype=np.float64)
         n_batch, ld = thetas.shape
+        if ld < self.num_params:
+            raise ValueError('theta has {} columns, the program needs {}'.format(
+                ld, self.num_params))
         bits = 0
         for name in which:
             bits |= _lib.IMAGE_BITS[name]
@@ -213,6 +216,9 @@ class LikelihoodEngine(object):
         of 1/ivm (variance space), as the reference's running mean uses it."""
         thetas = np.ascontiguousarray(np.atleast_2d(thetas), dtype=np.float64)
         n_batch, ld = thetas.shape
+        if ld < self.num_params:
+            raise ValueError('theta has {} columns, the program needs {}'.format(
+                ld, self.num_params))
         bits = 0
         for name in which:
             bits |= _lib.IMAGE_BITS[name]

@@ -88,3 +88,48 @@ def draw_walkers_fast(model, nwalkers, seed=0):
         ok = np.isfinite(model.log_priors_batch(block))
         out = np.concatenate([out, block[ok]], axis=0)
     return np.ascontiguousarray(out[:nwalkers])
+
+
+def write_synthetic_files(size, n_sersic, outdir, psf_size=64):
+    """The same synthetic workload as :func:`synthetic_components`, written out as
+    FITS files plus a model file in psfMC's model-file syntax, so that a model built
+    from files (e.g. the reference's own MultiComponentModel in the CPU arm of
+    bench.py) sees bit-identical inputs. Returns the model file's path."""
+    import os
+    from . import fitsio
+    comps = synthetic_components(size, n_sersic, psf_size=psf_size)
+    config = comps[0]
+    rng = np.random.RandomState(1234 + size)
+    obs = (0.02 * rng.standard_normal((size, size))).astype(np.float32)
+    ivm = np.full((size, size), 2500.0, dtype=np.float32)
+    yy, xx = np.mgrid[0:size, 0:size]
+    mask = ((xx - size / 2.0) ** 2 + (yy - size / 2.0) ** 2) > (0.43 * size) ** 2
+    psf, psf_ivm = synthetic_psf(min(psf_size, size))
+    assert np.array_equal(mask | ~np.isfinite(obs), config.bad_px)
+    os.makedirs(outdir, exist_ok=True)
+    fitsio.writeto(os.path.join(outdir, 'sci.fits'), obs)
+    fitsio.writeto(os.path.join(outdir, 'ivm.fits'), ivm)
+    fitsio.writeto(os.path.join(outdir, 'mask.fits'), mask.astype(np.int16))
+    fitsio.writeto(os.path.join(outdir, 'psf.fits'), psf)
+    fitsio.writeto(os.path.join(outdir, 'psf_ivm.fits'), psf_ivm)
+    lines = [
+        'from numpy import array',
+        'centre, box = array(({0}, {0})), array((4.0, 4.0))'.format(size / 2.0),
+        "Configuration(obs_file='sci.fits', obsivm_file='ivm.fits', psf_files='psf.fits',",
+        "              psfivm_files='psf_ivm.fits', mask_file='mask.fits',",
+        '              mag_zeropoint=25.9463)',
+        'Sky(adu=Normal(loc=0, scale=0.01))',
+        'PointSource(xy=Uniform(loc=centre - box, scale=2 * box),',
+        '            mag=Uniform(loc=20, scale=2))',
+    ]
+    for _ in range(n_sersic):
+        lines += [
+            'Sersic(xy=Uniform(loc=centre - box, scale=2 * box),',
+            '       mag=Uniform(loc=21, scale=4), reff=Uniform(loc=6, scale=10),',
+            '       reff_b=Uniform(loc=2, scale=4), index=Uniform(loc=0.5, scale=6.0),',
+            '       angle=Uniform(loc=0, scale=180), angle_degrees=True)',
+        ]
+    model_file = os.path.join(outdir, 'model_synthetic_{}.py'.format(size))
+    with open(model_file, 'w') as fobj:
+        fobj.write('\n'.join(lines) + '\n')
+    return model_file

@@ -17,6 +17,9 @@ Outputs (all committed):
       section 8c), its lnprior, setup checksums and sampled image pixels
   pointsource_golden.json                     the reference's own known-answer
                                               (tests/test_components.py:121-144)
+  c1_pssub_golden.json                        the reference's point_source_subtracted
+                                              image (psfMC/models.py:296-306), sampled
+                                              pixels + sums; `--pssub` regenerates only this
 
 The data files copied verbatim from the reference are inputs, not source code:
 j0005/{sci,ivm}_J0005-0006.fits, j0005/{sci,ivm}_psf.fits,
@@ -401,5 +404,51 @@ def main():
         'lanczos_xy': [7.3, 8.6], 'lanczos_16x16': lanc.tolist()})
 
 
+def make_pssub_golden():
+    """c1_pssub_golden.json: the reference's point_source_subtracted image
+    (psfMC/models.py:296-306) for 12 C1 and 8 two-PSF parameter vectors in all three
+    precision modes, after asserting that the oracle reproduces it BIT FOR BIT."""
+    if not refshim.reference_available():
+        raise SystemExit('the reference is not present; cannot regenerate')
+    with open(os.path.join(HERE, 'c1_golden.json')) as fobj:
+        c1 = json.load(fobj)
+    with open(os.path.join(HERE, 'c1_2psf_golden.json')) as fobj:
+        c1b = json.load(fobj)
+    rng = np.random.RandomState(99)
+    px = sorted(set(rng.randint(0, 128 * 128, size=96).tolist()
+                    + [0, 127, 8256, 8257, 8320, 8384, 16383]))
+    out = {'sample_px': px, 'cases': {}}
+    for tag, golden, two_psf, count in (('c1', c1, False, 12), ('c1_2psf', c1b, True, 8)):
+        model_file = os.path.join(HERE, golden['model_file'])
+        thetas = golden['theta'][:count]
+        case = {'model_file': golden['model_file'], 'theta': thetas, 'pixels': {},
+                'sum': {}, 'abs_sum': {}}
+        for mode in MODES:
+            model = refshim.build_reference_model(model_file, mode)
+            oracle = oracle_for(model, mode, raw_inputs_j0005(two_psf))
+            pixels, sums, abs_sums = [], [], []
+            for theta in thetas:
+                with np.errstate(all='ignore'):
+                    model.param_values = np.asarray(theta, dtype=np.float64)
+                    ref_px = model.point_source_subtracted()
+                mine = oracle.images(theta)['point_source_subtracted']
+                assert mine.dtype == ref_px.dtype, (mode, mine.dtype, ref_px.dtype)
+                assert np.array_equal(mine, ref_px, equal_nan=True), (tag, mode, theta)
+                flat = np.asarray(ref_px, dtype=np.float64).ravel()
+                pixels.append([float(v) for v in flat[px]])
+                sums.append(float(flat.sum()))
+                abs_sums.append(float(np.abs(flat).sum()))
+            case['pixels'][mode], case['sum'][mode] = pixels, sums
+            case['abs_sum'][mode] = abs_sums
+            print('  {} {}: point_source_subtracted pinned for {} thetas, oracle == '
+                  'reference bitwise'.format(tag, mode, len(thetas)))
+        out['cases'][tag] = case
+    dump('c1_pssub_golden.json', out)
+
+
 if __name__ == '__main__':
-    main()
+    if '--pssub' in sys.argv:
+        make_pssub_golden()
+    else:
+        main()
+        make_pssub_golden()

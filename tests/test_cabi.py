@@ -98,6 +98,22 @@ def test_invalid_arguments_are_reported_not_thrown(cuda_library):
     assert lib.psfmc_engine_create(ctypes.byref(desc), ctypes.byref(handle)) == 2
     assert b'too large' in lib.psfmc_last_error()
     assert handle.value is None
+    # a slot index below -1 (-1 = constant) is rejected before any device is touched
+    desc.height, desc.width = 128, 128
+    comps = (_lib.Component * 1)()
+    comps[0].kind = _lib.SKY
+    for sidx in range(_lib.NSLOTS):
+        comps[0].slot[sidx].theta_index = -1
+    comps[0].slot[_lib.P_ADU].theta_index = -2
+    desc.n_components, desc.components = 1, comps
+    desc.psf_index.theta_index = -1
+    assert lib.psfmc_engine_create(ctypes.byref(desc), ctypes.byref(handle)) == 1
+    assert b'theta_index' in lib.psfmc_last_error()
+    comps[0].slot[_lib.P_ADU].theta_index = 0
+    desc.psf_index.theta_index = -7
+    assert lib.psfmc_engine_create(ctypes.byref(desc), ctypes.byref(handle)) == 1
+    assert b'psf_index' in lib.psfmc_last_error()
+    assert handle.value is None
     out = np.zeros(1)
     dbl_p = ctypes.POINTER(ctypes.c_double)
     assert lib.psfmc_lnlike_batch(None, out.ctypes.data_as(dbl_p), 1, 1,

@@ -9,8 +9,9 @@ import numpy as np
 import pytest
 
 from conftest import (ARBITRARY_FRAMES, assert_lnl_close, check_arbitrary_frame,
-                      check_cluster_path_256, check_cropped_golden, check_nan_propagation, check_fp64_rescue,
-                      check_near_centre_walkers, mixed_model_128, fp32_bounds, load_golden, model_from_file,
+                      check_cluster_path_256, check_cropped_golden, check_nan_propagation,
+                      check_fp64_rescue, check_near_centre_walkers, check_pssub_golden,
+                      mixed_model_128, fp32_bounds, load_golden, model_from_file,
                       oracle_from_model)
 
 
@@ -148,6 +149,42 @@ def test_emu_images_and_point_source_subtracted(emu_library, c1_golden):
             assert np.allclose(got, ref[key], rtol=1e-9, atol=1e-12 * scale), key
     ref = oracle_from_model(model).images(thetas[0])['point_source_subtracted']
     assert np.allclose(imgs['point_source_subtracted'][0], ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_emu_point_source_subtracted_matches_the_reference(emu_library, precision):
+    check_pssub_golden(emu_library, precision, 'c1', rows=[0, 4, 5])
+    check_pssub_golden(emu_library, precision, 'c1_2psf', rows=[0, 1])
+
+
+def test_emu_short_theta_rows_are_rejected(emu_library, c1_golden):
+    """ld smaller than the number of theta columns the program reads: every C-ABI
+    entry point returns PSFMC_ERR_INVALID_ARG instead of reading past the rows."""
+    import ctypes
+    from psfmc_b200 import _lib
+    model = model_from_file('j0005/model_c1.py', 'fp64', library=emu_library)
+    eng = model.engine
+    short = np.ascontiguousarray(np.array(c1_golden['theta'][:2])[:, :17])
+    out = np.zeros(2)
+    dbl = ctypes.POINTER(ctypes.c_double)
+    args = (eng._handle, short.ctypes.data_as(dbl), 2, 17)
+    assert eng._lib.psfmc_lnlike_batch(*args, out.ctypes.data_as(dbl)) == 1
+    assert b'ld is smaller' in eng._lib.psfmc_last_error()
+    assert eng._lib.psfmc_lnlike_batch_begin(*args, out.ctypes.data_as(dbl)) == 1
+    assert eng._lib.psfmc_lnlike_batch_device(
+        eng._handle, 0, short.ctypes.data_as(dbl), 2, 17, out.ctypes.data_as(dbl),
+        None) == 1
+    img = np.zeros((2, 128, 128))
+    assert eng._lib.psfmc_render_batch(*args, 1, img.ctypes.data_as(dbl)) == 1
+    assert eng._lib.psfmc_accumulate_batch(*args, 1, img.ctypes.data_as(dbl)) == 1
+    with pytest.raises(ValueError):
+        eng.render(short)
+    with pytest.raises(ValueError):
+        eng.accumulate(short)
+    with pytest.raises(ValueError):
+        eng.lnlike(short)
+    # the engine is still usable
+    assert np.isfinite(eng.lnlike(np.array(c1_golden['theta'][:1]))).all()
 
 
 def test_emu_batch_edges_and_determinism(emu_library, c1_golden):

@@ -8,9 +8,8 @@ import os
 import numpy as np
 import pytest
 
-from conftest import (assert_lnl_close, fp32_bounds, load_golden, mixed_model_128,
-                      model_from_file,
-                      oracle_from_model)
+from conftest import (assert_lnl_close, check_pssub_golden, fp32_bounds, load_golden,
+                      mixed_model_128, model_from_file, oracle_from_model)
 
 pytestmark = pytest.mark.gpu
 
@@ -130,6 +129,14 @@ def test_c1_images_match_reference_pixels(cuda_library, c1_golden):
     oracle = oracle_from_model(model)
     ref = oracle.images(thetas[0])['point_source_subtracted']
     assert np.allclose(imgs['point_source_subtracted'][0], ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_point_source_subtracted_matches_the_reference(cuda_library, precision):
+    """Row a13 (psfMC/models.py:296-306) against the unmodified reference's image:
+    12 C1 + 8 two-PSF parameter vectors, fp64 (1e-9) and fp32 (2e-6 of the scale)."""
+    check_pssub_golden(cuda_library, precision, 'c1')
+    check_pssub_golden(cuda_library, precision, 'c1_2psf')
 
 
 @pytest.mark.parametrize('size,n_sersic', [(256, 2), (512, 3), (64, 1), (32, 1), (16, 1),

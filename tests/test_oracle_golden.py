@@ -68,6 +68,22 @@ def test_c1_oracle_reproduces_reference_bitwise(mode):
                 assert _same(imgs[key].ravel()[px], want), (mode, row, key)
 
 
+@pytest.mark.parametrize('mode', MODES)
+def test_point_source_subtracted_oracle_reproduces_reference_bitwise(mode):
+    """psfMC/models.py:296-306 (row a13): sampled pixels and sums of the reference's
+    image, frozen by make_golden.py --pssub."""
+    golden = load_golden('c1_pssub_golden.json')
+    px = np.array(golden['sample_px'])
+    for tag, two_psf in (('c1', False), ('c1_2psf', True)):
+        case = golden['cases'][tag]
+        oracle, _ = _oracle_j0005(case['model_file'], mode, two_psf)
+        for row, theta in enumerate(case['theta']):
+            img = oracle.images(np.array(theta))['point_source_subtracted']
+            flat = np.asarray(img, dtype=np.float64).ravel()
+            assert _same(flat[px], case['pixels'][mode][row]), (tag, mode, row)
+            assert float(flat.sum()) == case['sum'][mode][row], (tag, mode, row)
+
+
 def test_c1_named_edge_cases():
     golden = load_golden('c1_golden.json')
     names = golden['names']
