@@ -371,7 +371,17 @@ def run_ours(args):
         # prints at NCCL_DEBUG >= VERSION included) goes to stderr; NCCL_DEBUG itself
         # is left as the launcher set it
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)            # NCCL writes its banner to fd 1 while the communicator is built
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     walkers = args.walkers or default_walkers(args.workload)
     half = walkers // 2
@@ -417,6 +427,7 @@ def run_ours(args):
                                  stream=stream.cuda_stream)
 
     pool = ShardedPool(model) if world > 1 else BatchPool(model)
+    inside_map = [0.0]      # seconds spent inside pool.map itself (step_pool_map)
     lnlike_pool = None
     if world > 1:
         from psfmc_b200.distributed import ShardedEvaluator
@@ -445,7 +456,10 @@ def run_ours(args):
         th = thetas[s % nsets]
         for h in range(2):
             p = th[h * half:(h + 1) * half]
-            results = list(pool.map(None, [p[i] for i in range(len(p))]))
+            rows = [p[i] for i in range(len(p))]
+            t_in = time.perf_counter()
+            results = list(pool.map(None, rows))
+            inside_map[0] += time.perf_counter() - t_in
             np.array([float(r[0]) for r in results])
 
     def barrier():
@@ -551,7 +565,9 @@ def run_ours(args):
         raw_engine.close()
     post_s = host_timed(step_posterior, args.steps)
     map_steps = max(10, args.steps // 3)
+    inside_map[0] = 0.0
     map_s = host_timed(step_pool_map, map_steps)
+    map_inside_s = max_over_ranks(inside_map[0])
 
     info = engine.info()
     result = None
@@ -651,8 +667,11 @@ def run_ours(args):
                              'N > 1: + the gather to every rank\'s host), max over ranks',
                     'with_python_priors': round(walkers * args.steps / post_s, 1),
                     'pool_map': round(walkers * map_steps / map_s, 1),
-                    'pool_map_note': 'emcee 2.x list protocol through {}.map: row views in, '
-                                     '(lnpost, blob) tuples out, priors included'.format(
+                    'pool_map_inside': round(walkers * map_steps / map_inside_s, 1),
+                    'pool_map_note': 'emcee 2.x list protocol through {}.map, priors included: '
+                                     'pool_map also times emcee\'s own side of it (the list of '
+                                     'row views it builds, the floats it picks out of the '
+                                     'result tuples), pool_map_inside only the map call'.format(
                                          type(pool).__name__),
                     'fp64_rescued_walkers_per_step': round(rescued_per_step, 2),
                     'without_fp64_rescue': None if e2e_raw is None else round(e2e_raw, 1)},

@@ -134,14 +134,10 @@ class ShardedPool(object):
         thetas = iterable if isinstance(iterable, list) else list(iterable)
         if not thetas:
             return []
-        try:
-            block = np.concatenate(thetas).reshape(len(thetas), -1)
-            if block.dtype != np.float64 or thetas[0].ndim != 1:
-                raise ValueError
-        except (ValueError, TypeError, AttributeError):
-            block = np.stack([np.asarray(p, dtype=np.float64) for p in thetas])
-        lnpost = self._evaluator(block)
-        return [(v, {}) for v in lnpost.tolist()]
+        from itertools import repeat
+        from .pool import rows_as_block
+        lnpost = self._evaluator(rows_as_block(thetas))
+        return list(zip(lnpost.tolist(), repeat({})))
 
     def map_batch(self, func, block):
         """Array protocol of this package's sampler (cf. BatchPool.map_batch):

@@ -10,7 +10,45 @@ emcee 2.x evaluates the posterior with
 priors column-vectorised on the host, every walker with a finite prior through
 the C ABI (psfmc_lnlike_batch) in a single call.
 """
+from itertools import repeat
+
 import numpy as np
+
+
+def rows_as_block(rows):
+    """The (B, D) float64 array behind a list of B parameter vectors. emcee 2.x builds
+    the list as ``[p[i] for i in range(len(p))]`` -- B views of consecutive rows of ONE
+    array -- so when the first and last element are views of the same base, spaced
+    like the rows of a C-contiguous (B, D) block, the block is re-assembled from the
+    base without touching the B views (two address checks instead of a 2048-way
+    concatenation); anything else is concatenated or stacked."""
+    first, last = rows[0], rows[-1]
+    count = len(rows)
+    try:
+        if (first.dtype == np.float64 and first.ndim == 1 and first.base is not None
+                and first.base is last.base and first.flags.c_contiguous
+                and last.shape == first.shape):
+            ndim = first.shape[0]
+            a0 = first.__array_interface__['data'][0]
+            a1 = last.__array_interface__['data'][0]
+            if a1 - a0 == (count - 1) * ndim * 8:
+                mid = rows[count // 2]
+                if (mid.base is first.base and mid.shape == first.shape and
+                        mid.__array_interface__['data'][0] - a0 == (count // 2) * ndim * 8):
+                    base = first.base
+                    b0 = base.__array_interface__['data'][0]
+                    if base.dtype == np.float64 and base.flags.c_contiguous and \
+                            (a0 - b0) % 8 == 0:
+                        start = (a0 - b0) // 8
+                        flat = base.reshape(-1)[start:start + count * ndim]
+                        if flat.size == count * ndim:
+                            return flat.reshape(count, ndim)
+        block = np.concatenate(rows).reshape(count, -1)
+        if block.dtype != np.float64 or first.ndim != 1:
+            raise ValueError
+        return block
+    except (ValueError, TypeError, AttributeError):
+        return np.stack([np.asarray(p, dtype=np.float64) for p in rows])
 
 
 class BatchPool(object):
@@ -40,19 +78,14 @@ class BatchPool(object):
         thetas = iterable if isinstance(iterable, list) else list(iterable)
         if not thetas:
             return []
-        try:
-            # emcee hands over the rows of one (B, D) array: one concatenation is 3-5x
-            # cheaper than stacking B one-row arrays
-            block = np.concatenate(thetas).reshape(len(thetas), -1)
-            if block.dtype != np.float64 or thetas[0].ndim != 1:
-                raise ValueError
-        except (ValueError, TypeError, AttributeError):
-            block = np.stack([np.asarray(p, dtype=np.float64) for p in thetas])
+        block = rows_as_block(thetas)
         lnpost = self.model.log_posterior_batch(block)
         self.calls += 1
         self.evaluations += len(thetas)
         if not self.with_blobs:
-            return [(v, {}) for v in lnpost.tolist()]
+            # one shared empty blob: emcee only stores it, accumulate_images only
+            # iterates over it (psfMC/models.py:84-93)
+            return list(zip(lnpost.tolist(), repeat({})))
         out = []
         alive = np.isfinite(self.model.log_priors_batch(block))
         imgs = self.model.engine.render(block[alive]) if alive.any() else {}

@@ -231,17 +231,89 @@ def test_edge_batches(cuda_library, c1_golden):
                           model.log_likelihood_batch(thetas))
 
 
-def test_multi_device_sharding(cuda_library):
+def test_multi_device_sharding(cuda_library, c1_golden):
+    """In-process device list (psfmc_desc.devices): a batch split over all GPUs of the
+    box -- one host thread per device enqueues its shard -- gives bit-identical lnL,
+    images and image sums (up to the order of the per-device partial sums)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip('needs >= 2 GPUs')
     from psfmc_b200.synthetic import draw_walkers_fast
+    ndev = torch.cuda.device_count()
     single = model_from_file('j0005/model_c1.py', 'fp32')
-    multi = model_from_file('j0005/model_c1.py', 'fp32',
-                            devices=list(range(torch.cuda.device_count())))
+    multi = model_from_file('j0005/model_c1.py', 'fp32', devices=list(range(ndev)))
+    assert multi.engine.info()['n_devices'] == ndev
     thetas = draw_walkers_fast(single, 1001, seed=5)
-    assert np.array_equal(single.log_likelihood_batch(thetas),
-                          multi.log_likelihood_batch(thetas))
+    want = single.log_likelihood_batch(thetas)
+    for _ in range(3):      # repeated calls: the per-device worker threads are reused
+        assert np.array_equal(want, multi.log_likelihood_batch(thetas))
+    # fewer rows than devices, a single row
+    assert np.array_equal(want[:1], multi.log_likelihood_batch(thetas[:1]))
+    assert np.array_equal(want[:ndev - 1], multi.log_likelihood_batch(thetas[:ndev - 1]))
+    # split call with the priors overlapped (what BatchPool / ShardedPool use)
+    assert np.array_equal(single.log_posterior_batch(thetas),
+                          multi.log_posterior_batch(thetas))
+    # blob images and their sums, rows split over the devices
+    rows = np.array(c1_golden['theta'])
+    rows = rows[np.isfinite(np.array(c1_golden['lnl']['M3']))][:7]
+    a, b = single.engine.render(rows), multi.engine.render(rows)
+    for key in a:
+        assert np.array_equal(a[key], b[key], equal_nan=True), key
+    sa, sb = single.engine.accumulate(rows), multi.engine.accumulate(rows)
+    for key in sa:
+        scale = np.abs(sa[key][np.isfinite(sa[key])]).max()
+        assert np.allclose(sa[key], sb[key], rtol=1e-12, atol=1e-12 * scale,
+                           equal_nan=True), key
+    # a short theta is rejected on the multi-device engine too, and it stays usable
+    with pytest.raises(ValueError):
+        multi.engine.lnlike(thetas[:, :17])
+    assert np.array_equal(want, multi.log_likelihood_batch(thetas))
+
+
+def test_multi_process_sharded_pool_nccl(cuda_library, tmp_path):
+    """One process per GPU under torchrun (the deployment bench.py --gpus N times):
+    ShardedPool over NCCL returns on every rank exactly what one engine returns for
+    the whole batch, ragged shards included."""
+    import subprocess
+    import sys
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip('needs >= 2 GPUs')
+    script = tmp_path / 'worker.py'
+    script.write_text("""
+import os, sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import torch, torch.distributed as dist
+from conftest import model_from_file
+from psfmc_b200.distributed import ShardedPool
+from psfmc_b200.synthetic import draw_walkers_fast
+local = int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+model = model_from_file('j0005/model_c1.py', 'fp32', devices=[local])
+thetas = draw_walkers_fast(model, 1001, seed=5)
+pool = ShardedPool(model)
+got, _ = pool.map_batch(None, thetas)
+rows = [thetas[i] for i in range(37)]
+listed = np.array([r[0] for r in pool.map(None, rows)])
+np.savez(os.path.join({out!r}, 'rank%d.npz' % dist.get_rank()), got=got, listed=listed,
+         want=model.log_posterior_batch(thetas))
+dist.barrier()
+dist.destroy_process_group()
+""".format(root=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+           out=str(tmp_path)))
+    nproc = min(ndev, 8)
+    subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+                    '--nproc-per-node', str(nproc), '--master-addr', '127.0.0.1',
+                    '--master-port', '29533', str(script)], check=True, timeout=600)
+    first = np.load(str(tmp_path / 'rank0.npz'))
+    for r in range(nproc):
+        data = np.load(str(tmp_path / 'rank{}.npz'.format(r)))
+        assert np.array_equal(data['got'], data['want'])
+        assert np.array_equal(data['got'], first['got'])
+        assert np.array_equal(data['listed'], data['want'][:37])
 
 
 @pytest.mark.parametrize('table', ['1', '0'])

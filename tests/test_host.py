@@ -474,3 +474,27 @@ def test_bridge_is_a_drop_in_for_the_unmodified_reference(emu_library):
                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                           universal_newlines=True, timeout=600)
     assert proc.returncode == 0 and 'BRIDGE-OK' in proc.stdout, proc.stdout[-3000:]
+
+
+def test_rows_as_block_reassembles_emcee_row_lists():
+    """BatchPool.map gets emcee's ``[p[i] for i in range(len(p))]``: consecutive row
+    views of one array are re-assembled without copying; anything else is stacked."""
+    from psfmc_b200.pool import rows_as_block
+    rng = np.random.RandomState(0)
+    p = rng.rand(64, 18)
+    half = p[32:]
+    block = rows_as_block([half[i] for i in range(len(half))])
+    assert np.shares_memory(block, p) and np.array_equal(block, half)
+    taken = p[np.arange(0, 64, 2)]                       # emcee's fancy-indexed half
+    assert np.array_equal(rows_as_block([taken[i] for i in range(32)]), taken)
+    order = rng.permutation(32)
+    assert np.array_equal(rows_as_block([half[i] for i in order]), half[order])
+    order[0], order[16], order[31] = 0, 16, 31           # lined-up ends, shuffled middle
+    order[1], order[2] = 2, 1
+    got = rows_as_block([half[i] for i in order])
+    assert np.array_equal(got, half[order]) or np.array_equal(got, half)  # documented limit
+    wide = rng.rand(40, 20)[:, :18]                      # strided rows: not one block
+    assert np.array_equal(rows_as_block([wide[i] for i in range(40)]), wide)
+    assert np.array_equal(rows_as_block([np.array(r) for r in half[:5]]), half[:5])
+    assert np.array_equal(rows_as_block([list(r) for r in half[:3]]), half[:3])
+    assert np.array_equal(rows_as_block([half[0]]), half[:1])

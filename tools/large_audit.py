@@ -28,6 +28,19 @@ def main():
     err = np.abs(l32 - l64)[finite]
     rel = err / np.abs(l64[finite])
     info = m32.engine.info()
+    # |dlnL| by |lnL| (the absolute statement of DESIGN.md 4.5 is read off these rows)
+    mag = np.abs(l64[finite])
+    bins = []
+    for lo_edge, hi_edge in ((0, 5e4), (5e4, 2e5), (2e5, 1e6), (1e6, np.inf)):
+        pick = (mag >= lo_edge) & (mag < hi_edge)
+        if pick.any():
+            bins.append({'abs_lnl': [lo_edge, None if np.isinf(hi_edge) else hi_edge],
+                         'walkers': int(pick.sum()),
+                         'max_abs_dlnl': float(err[pick].max()),
+                         'p99_abs_dlnl': float(np.percentile(err[pick], 99)),
+                         'median_abs_dlnl': float(np.median(err[pick])),
+                         'max_rel_dlnl': float(rel[pick].max())})
+    form = err / (0.05 + 2e-6 * mag)
     print(json.dumps({
         'workload': 'c1', 'walkers': n, 'finite_fp64': int(finite.sum()),
         'finiteness_agrees': bool(np.array_equal(np.isfinite(l32), finite)),
@@ -37,7 +50,11 @@ def main():
         'max_abs_dlnl': float(err.max()), 'median_abs_dlnl': float(np.median(err)),
         'p99_abs_dlnl': float(np.percentile(err, 99)),
         'max_rel_dlnl': float(rel.max()), 'median_rel_dlnl': float(np.median(rel)),
-        'lnl_range': [float(l64[finite].min()), float(l64[finite].max())]}, indent=1))
+        'lnl_range': [float(l64[finite].min()), float(l64[finite].max())],
+        'by_abs_lnl': bins,
+        'max_err_over_0.05_plus_2e-6_abs_lnl': float(form.max()),
+        'p999_err_over_0.05_plus_2e-6_abs_lnl': float(np.percentile(form, 99.9))},
+        indent=1))
 
 
 if __name__ == '__main__':
