@@ -116,7 +116,7 @@ struct DeviceState {
   double *vscale_inv = nullptr;
   DevBuf<int> psf_sel;
   DevBuf<float> rconst;
-  cplx<float> *fspec = nullptr, *fspecx = nullptr;
+  float4 *fspec = nullptr, *fspecx = nullptr;   // fused kernel (128 x 128)
   float2 *fow = nullptr;
   float4 *cspec = nullptr, *cspecx = nullptr;   // cluster kernel (256 x 256)
   float2 *ctw = nullptr;
@@ -184,7 +184,6 @@ struct EngineBase {
   int n_sersic = 0, n_point = 0;
   StagedPlan plan;
   int path = 0;
-  bool fused_wide = false;   // PSFMC_FUSED_VARIANT=1024 selects the 1024-thread kernel
   bool kappa_table = false;  // Chebyshev table of the Sersic kappa accepted
   std::atomic<long long> launches{0};   // (device threads add to it concurrently)
   int n_devices = 0;
@@ -395,11 +394,10 @@ struct Engine : EngineBase {
     if (path == 1) {
       FusedBuffers fb;
       fb.rconst = d.rconst.ptr;
-      fb.spec = d.fspec;
-      fb.specx = d.fspecx;
+      fb.spec4 = d.fspec;
+      fb.specx4 = d.fspecx;
       fb.ow = d.fow;
       fb.n_sms = d.n_sms;
-      fb.wide = fused_wide;
       fb.skip_quads = d.skip_quads;
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (profiling && (rc = prof_pair(d, &e0, &e1))) return rc;
@@ -1381,8 +1379,6 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       if (cluster_path_available<T>(eng->plan)) eng->path = 2;
       const char *force = getenv("PSFMC_FORCE_STAGED");
       if (force && force[0] == '1') eng->path = 0;
-      const char *variant = getenv("PSFMC_FUSED_VARIANT");
-      eng->fused_wide = variant && atoi(variant) == 1024;
     }
     if (eng->path == 1) {
       if (fused_prepare_device<T>(eng->plan)) {
@@ -1396,7 +1392,7 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
         if (v > 0) ds.n_sms = v;
       }
       const size_t N = PSFMC_FUSED_N;
-      std::vector<cplx<float>> fspec((size_t)d->n_psf * N * N), fspecx((size_t)d->n_psf * 2 * N);
+      std::vector<float4> fspec((size_t)d->n_psf * N * 64), fspecx((size_t)d->n_psf * N);
       std::vector<double> vs(d->n_psf);
       for (int k = 0; k < d->n_psf; ++k) vs[k] = 1.0 / vscale_inv[k];
       fused_spectrum_layout(spec64.data(), d->n_psf, vs.data(), fspec.data(), fspecx.data());

@@ -722,8 +722,8 @@ inline int launch_cluster_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
   P.wscale = buf.wscale;
   P.psf_sel = buf.psf_sel;
   P.vscale_inv = buf.vscale_inv;
-  P.spec = nullptr;
-  P.specx = nullptr;
+  P.spec4 = nullptr;
+  P.specx4 = nullptr;
   P.ow = cb.ow;
   P.lnl = lnl;
   P.n_batch = n_batch;

@@ -11,18 +11,19 @@
 // butterfly in registers (index maps n = n2 + 8*n1, k = k1 + 16*k2).
 //
 //   rows fwd  (per warp, 4 rows at a time, no CTA barrier): render 16 px/thread
-//             -> radix-16 -> twiddle -> exchange (warp-private) -> radix-8 -> split
-//             the packed row spectrum into the row spectra of the two real images
-//             (A: raw, B: raw^2; partners kx <-> -kx are held by the same thread)
-//             -> 128 columns: c = kx (A, kx=1..63), c = 64+kx (B), c = 0 and c = 64
-//             carry the real DC/Nyquist columns of A and B packed in pairs
+//             -> radix-16 -> twiddle -> exchange (warp-private) -> radix-8 -> the row
+//             spectrum Z[kx], kx = 0..127, of the PACKED row goes to column kx as it is
 //   cols      radix-16 -> exchange inside a 4-warp column group -> radix-8 ->
-//             multiply by the PSF / PSF-variance spectrum (registers) -> inverse
-//             radix-8 -> exchange -> inverse radix-16
-//   rows inv  rebuild Y = A' + i B' (Hermitian extension), inverse radix-8 ->
-//             exchange -> inverse radix-16 -> Re = convolved model, Im = model
-//             variance -> residual, composite IVM, masked chi-square terms in
-//             registers -> float64 warp + CTA reduction -> lnL
+//             mirror-pair product with the PSF / PSF-variance spectra (registers):
+//                 Y[k] = Z[k] S+[k] + conj(Z[-k]) S-[k],   S+- = (P +- V) / 2
+//             (the two real images packed in z are multiplied by their own spectra
+//             without ever being separated: no real-pair split, no Hermitian rebuild,
+//             no packed DC/Nyquist columns; a thread owns the columns kx and -kx and
+//             the frequencies ky and -ky, so both partners sit in its registers)
+//             -> inverse radix-8 -> exchange -> inverse radix-16
+//   rows inv  inverse radix-8 -> exchange -> inverse radix-16 -> Re = convolved
+//             model, Im = model variance -> residual, composite IVM, masked
+//             chi-square terms in registers -> float64 warp + CTA reduction -> lnL
 //
 // Two CTA-wide barriers and two 128-thread named barriers per walker; warps drift
 // apart between them, which overlaps the SFU-bound render of one warp with the
@@ -46,9 +47,9 @@ struct FusedParams {
   const double *wscale;      // [B]
   const int *psf_sel;        // [B]
   const double *vscale_inv;  // [K]
-  const cplx<float> *spec;   // [K][ky=128][c=128], see fused_spectrum_layout()
-  const cplx<float> *specx;  // [K][2 (P,V)][ky=128]: (S0-S64)/2 of the packed DC/Nyquist
-                             // columns (S0 = kx 0, S64 = kx 64); (S0+S64)/2 is in spec
+  const float4 *spec4;       // [K][ky=128][slot=64]: (S+, S-) of column kx = slot, see
+                             // fused_spectrum_layout()
+  const float4 *specx4;      // [K][ky=128]: the same for the self-mirrored column kx = 64
   const float2 *ow;          // [128*128]: (obs, bad ? -ovar : +ovar)
   double *lnl;               // [B]
   long long n_batch;
@@ -218,18 +219,44 @@ __device__ __forceinline__ cplx<float> ldc2(const cplx<float> *p) {
 #endif
 }
 
-// Special (packed DC/Nyquist) columns: U = FFT(p + i q) of two real sequences that
-// are multiplied by different spectra S0 (for p) and S64 (for q):
-//   U'[ky] = U[ky] (S0+S64)/2 + conj(U[-ky]) (S0-S64)/2, spectra taken at ky.
-// pu / pm: half-sums at ky / -ky (they sit in the `spec` table at c = 0 and c = 64),
-// du / dm: half-differences (from `specx`), all prefetched by the caller.
-__device__ __forceinline__ void special_pair(cplx<float> &u, cplx<float> &um,
-                                             cplx<float> pu, cplx<float> du,
-                                             cplx<float> pm, cplx<float> dm) {
-  const cplx<float> nu = u * pu + cmul_conj(du, um);
-  const cplx<float> nm = um * pm + cmul_conj(dm, u);
-  u = nu;
-  um = nm;
+// Mirror-pair product. z = raw + i w raw^2 packs two real images; with Z = FFT2(z),
+// A = FFT2(raw) = (Z[k] + conj Z[-k]) / 2 and B = FFT2(w raw^2) = (Z[k] - conj Z[-k]) / 2i,
+// so the spectrum of (raw * psf) + i (w raw^2 * psf_var) is
+//     Y[k]  = A P + i B V = Z[k] S+ + conj(Z[-k]) S-,          S+- = (P +- V) / 2,
+//     Y[-k] = conj( conj(Z[-k]) S+ + Z[k] S- )                 (P, V Hermitian).
+// zu = Z[k], zm = Z[-k], s = (S+.re, S+.im, S-.re, S-.im) at k. Eight packed
+// instructions per pair: the per-half sign flips all sit on the accumulator operand
+// (FFMA2's .NP / .PN operand modifiers), the swaps and full negations on the others.
+__device__ __forceinline__ void mirror_pair(cplx<float> &zu, cplx<float> &zm, float4 s) {
+#ifdef PSFMC_EMU
+  const cplx<float> sp = mk<float>(s.x, s.y), sm = mk<float>(s.z, s.w);
+  const cplx<float> zc = mk<float>(zm.x, -zm.y);
+  const cplx<float> yu = zu * sp + zc * sm;
+  const cplx<float> w2 = zc * sp + zu * sm;
+  zu = yu;
+  zm = mk<float>(w2.x, -w2.y);
+#else
+  const u64_t SP = pk2(s.x, s.y), SPs = pk2(s.y, s.x), SM = pk2(s.z, s.w), SMs = pk2(s.w, s.z);
+  const u64_t zux = pk2(zu.x, zu.x), zuy = pk2(zu.y, zu.y);
+  const u64_t zmx = pk2(zm.x, zm.x), zmy = pk2(zm.y, zm.y);
+  // Y[k]: h = zu.y (py, px) - zm.y (my, mx);  yu = zu.x (px, py) + zm.x (mx, my) + (-h.x, h.y)
+  const cplx<float> h1 = upk2(mul2(zmy, SMs));
+  const cplx<float> h = upk2(fma2(zuy, SPs, pk2(-h1.x, -h1.y)));
+  const u64_t g = fma2(zmx, SM, pk2(-h.x, h.y));
+  const cplx<float> yu = upk2(fma2(zux, SP, g));
+  // Y[-k]: b = zm.x (px, py) + zu.x (mx, my);  ym = zm.y (py, px) - zu.y (my, mx) + (b.x, -b.y)
+  const cplx<float> b = upk2(fma2(zmx, SP, mul2(zux, SM)));
+  const cplx<float> nms = upk2(SMs);
+  const u64_t a1 = fma2(zuy, pk2(-nms.x, -nms.y), pk2(b.x, -b.y));
+  const cplx<float> ym = upk2(fma2(zmy, SPs, a1));
+  zu = yu;
+  zm = ym;
+#endif
+}
+// a self-mirrored element (k = -k: kx in {0, 64} and ky in {0, 64})
+__device__ __forceinline__ void mirror_self(cplx<float> &z, float4 s) {
+  cplx<float> zm = z;
+  mirror_pair(z, zm, s);
 }
 
 // Per-thread constants of the row passes (4 rows per warp, 8 threads per row).
@@ -238,10 +265,10 @@ struct RowRole {
   bool l0;
   unsigned t16;     // radix-16 side of the exchange layout: (8 l) ^ (64 s)
   unsigned qa, qb;  // radix-8 side, for k1 = kA / kB: 64 (k ^ s) + 8 (k & 7)
-  unsigned fa, fb;  // column layout: 8 (k ^ 8 s)
+  unsigned fa, fb;  // column layout: 8 (k ^ 8 s); column k + 16 k2 at + 128 k2
 };
 
-// render + forward row transform + real-pair split of row batch `it` of walker b
+// render + forward row transform of row batch `it` of walker b
 // (rc0 / der0: the walker's constants, STAGED = in shared memory, see fused_render16)
 // PADDED: the observation frame is P.Hr x P.Wr in the corner of the 128 x 128 transform
 // frame; nothing is rendered outside it.
@@ -259,11 +286,9 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
     __syncwarp();
     const cplx<float> zero = mk<float>(0.0f, 0.0f);
 #pragma unroll
-    for (int k2 = 0; k2 < 4; ++k2) {
+    for (int k2 = 0; k2 < 8; ++k2) {
       sts64(rb + R.fa + 8 * 16 * k2, zero);
-      sts64(rb + R.fa + 8 * (64 + 16 * k2), zero);
       sts64(rb + R.fb + 8 * 16 * k2, zero);
-      sts64(rb + R.fb + 8 * (64 + 16 * k2), zero);
     }
     return;
   }
@@ -301,33 +326,16 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
   __syncwarp();
   dft8<float, false>(a);    // a[k2]  = Z[kA + 16 k2]
   dft8<float, false>(bb);   // bb[k2] = Z[kB + 16 k2]
-  const bool l0 = R.l0;
+  // the row spectrum of the packed row goes to the columns as it is (column kx at
+  // kx ^ 8 (y & 1)); the two images are taken apart only implicitly, by mirror_pair
 #pragma unroll
-  for (int k2 = 0; k2 < 4; ++k2) {
-    // row spectra of the two real images (the factor 1/2 of the split is folded
-    // into the PSF spectra):  A = Z[kx] + conj Z[-kx],  B = -i (Z[kx] - conj Z[-kx])
-    {  // kx = kA + 16 k2, partner -kx
-      const cplx<float> zk = a[k2];
-      const cplx<float> zp = l0 ? a[(8 - k2) & 7] : bb[7 - k2];
-      cplx<float> oa = zk + mk<float>(zp.x, -zp.y);
-      cplx<float> ob = mk<float>(zk.y, -zk.x) + mk<float>(zp.y, zp.x);
-      if (k2 == 0 && l0) {   // real DC / Nyquist columns, packed in pairs
-        oa = mk<float>(a[0].x, a[4].x);
-        ob = mk<float>(a[0].y, a[4].y);
-      }
-      sts64(rb + R.fa + 8 * 16 * k2, oa);
-      sts64(rb + R.fa + 8 * (64 + 16 * k2), ob);
-    }
-    {  // kx = kB + 16 k2
-      const cplx<float> zk = bb[k2];
-      const cplx<float> zp = l0 ? bb[7 - k2] : a[7 - k2];
-      sts64(rb + R.fb + 8 * 16 * k2, zk + mk<float>(zp.x, -zp.y));
-      sts64(rb + R.fb + 8 * (64 + 16 * k2), mk<float>(zk.y, -zk.x) + mk<float>(zp.y, zp.x));
-    }
+  for (int k2 = 0; k2 < 8; ++k2) {
+    sts64(rb + R.fa + 8 * 16 * k2, a[k2]);
+    sts64(rb + R.fb + 8 * 16 * k2, bb[k2]);
   }
 }
 
-// Hermitian rebuild + inverse row transform + chi-square terms of row batch `it`;
+// inverse row transform + chi-square terms of row batch `it`;
 // returns this thread's float64 partial sum over its 16 pixels. PREFETCH: issue the
 // observation loads before the transform (needs 32 registers for its duration).
 template <bool PREFETCH, bool PADDED = false>
@@ -340,7 +348,6 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   // ... or hold no unmasked pixel: nothing of them enters the sum (models.py:233-236)
   if ((P.skip_quads >> (it * 16 + R.w)) & 1u) return 0.0;
   const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
-  const bool l0 = R.l0;
   // observation + signed variance of this thread's 16 pixels: issued first, used
   // last (L2 latency hidden behind the whole inverse transform)
   float2 o[16];
@@ -349,39 +356,11 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
   }
-  cplx<float> a[8], bb[8];
-  {
-    cplx<float> yd1[4], ym1[4], yd2[4], ym2[4];
-    cplx<float> a10, b10;
+  cplx<float> a[8], bb[8];   // a[k2] = Y[kA + 16 k2], bb[k2] = Y[kB + 16 k2]
 #pragma unroll
-    for (int k2 = 0; k2 < 4; ++k2) {
-      const cplx<float> a1 = lds64(rb + R.fa + 8 * 16 * k2);
-      const cplx<float> b1 = lds64(rb + R.fa + 8 * (64 + 16 * k2));
-      const cplx<float> a2 = lds64(rb + R.fb + 8 * 16 * k2);
-      const cplx<float> b2 = lds64(rb + R.fb + 8 * (64 + 16 * k2));
-      if (k2 == 0) {
-        a10 = a1;
-        b10 = b1;
-      }
-      // Y[kx] = A' + i B',  Y[-kx] = conj(A') + i conj(B')
-      yd1[k2] = a1 + mk<float>(-b1.y, b1.x);
-      ym1[k2] = mk<float>(a1.x, -a1.y) + mk<float>(b1.y, b1.x);
-      yd2[k2] = a2 + mk<float>(-b2.y, b2.x);
-      ym2[k2] = mk<float>(a2.x, -a2.y) + mk<float>(b2.y, b2.x);
-    }
-    // a[k2] = Y[kA + 16 k2], bb[k2] = Y[kB + 16 k2]; the upper halves are mirrored
-    // entries of the other set (of the same set for l = 0, where kA = 0, kB = 8)
-#pragma unroll
-    for (int k2 = 0; k2 < 4; ++k2) {
-      a[k2] = yd1[k2];
-      bb[k2] = yd2[k2];
-      a[4 + k2] = l0 ? ym1[(4 - k2) & 3] : ym2[3 - k2];
-      bb[4 + k2] = l0 ? ym2[3 - k2] : ym1[3 - k2];
-    }
-    if (l0) {   // packed DC / Nyquist columns
-      a[0] = mk<float>(a10.x, b10.x);
-      a[4] = mk<float>(a10.y, b10.y);
-    }
+  for (int k2 = 0; k2 < 8; ++k2) {
+    a[k2] = lds64(rb + R.fa + 8 * 16 * k2);
+    bb[k2] = lds64(rb + R.fb + 8 * 16 * k2);
   }
   __syncwarp();
   dft8<float, true>(a);     // a[n2]
@@ -489,18 +468,34 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   stage_params(blockIdx.x);
   __syncthreads();
 
-  // column-pass role: column c, two of the eight n2 residues. The four warps of a
-  // column group (which meet at the named barriers) sit on four DIFFERENT
-  // schedulers (warp w runs on scheduler w & 3), so every scheduler hosts one warp
-  // of each group and its warps are not phase-locked to each other.
+  // Column-pass roles. The four warps of a column group (which meet at the named
+  // barriers) sit on four DIFFERENT schedulers (warp w runs on scheduler w & 3), so
+  // every scheduler hosts one warp of each group and its warps are not phase-locked
+  // to each other. Group cg owns the 16 "slots" p = 16 cg .. 16 cg + 15: slot p is the
+  // mirror pair of columns (p, 128 - p); slot 0 is the two self-mirrored columns (0, 64).
+  //  * radix-16 sub-passes: thread = (column c, residues n2 = m and m + 4); lanes 0..15
+  //    run over the slots' first columns, lanes 16..31 over their mirrors (two
+  //    conflict-free half-warp wavefronts), m is warp-uniform (twiddles from the
+  //    constant bank).
+  //  * radix-8 sub-pass: thread = (slot p, m8 = 0..7), two rounds of two 8-point units
+  //    chosen so that every element and its mirror (-ky, -kx) are in the same thread:
+  //        m8 > 0:  round 0: a = (p, k1 = m8),      bb = (-p, k1 = 16 - m8)
+  //                 round 1: a = (p, k1 = 16 - m8), bb = (-p, k1 = m8)
+  //                 mirror of a[k2] (ky = k1 + 16 k2) is bb[7 - k2]
+  //        m8 = 0:  round 0: a = (p, 0), bb = (-p, 0): mirror of a[k2] is bb[(8 - k2) & 7]
+  //                 round 1: a = (p, 8), bb = (-p, 8): mirror of a[k2] is bb[7 - k2]
+  //        slot 0:  round 0 works on column 0, round 1 on column 64 (each its own
+  //                 mirror): a = (c, k1), bb = (c, -k1); for m8 = 0: a = (c, 0), bb = (c, 8)
+  //                 with the mirrors inside a (k2 <-> 8 - k2) and inside bb (k2 <-> 7 - k2).
   const int cg = w >> 2, m = w & 3;
-  const int c = cg * 32 + lane;
-  const bool special = (c == 0) || (c == 64);
-  // radix-8 side of the columns: four k1 values closed under k1 -> -k1 (mod 16)
-  const int ck1[4] = {m == 0 ? 0 : m, m == 0 ? 8 : 16 - m, m == 0 ? 4 : 8 - m,
-                      m == 0 ? 12 : 8 + m};
+  const int c = lane < 16 ? 16 * cg + lane
+                          : ((16 * cg + lane - 16) == 0 ? 64 : 128 - (16 * cg + lane - 16));
   // byte offsets of column c in even / odd rows (row swizzle = 8 * parity)
   const unsigned cev = 8u * c, cod = 8u * (c ^ 8);
+  const int slot = 16 * cg + (lane & 15), m8 = 2 * m + (lane >> 4);
+  const bool slot0 = slot == 0;
+  const bool zpat = slot0 && m8 == 0;          // one thread of the CTA
+  const bool xpat = !slot0 && m8 == 0;         // lanes 0..15 of the warps with m = 0
 
   // Order of the row work between two column passes. Every warp owns two row
   // batches; per batch the inverse pass of walker b must precede the forward pass
@@ -522,7 +517,6 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
     if (invalid) sel = 0;
     const double wscale_b = cur ? P.wscale[b] : 1.0;
     const float unscale = (float)(P.vscale_inv[sel] / wscale_b);
-    const cplx<float> *sp = P.spec + (size_t)sel * N * N;
     if (cur) {
 
     __syncthreads();
@@ -550,73 +544,70 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
 #pragma unroll
       for (int k1 = 0; k1 < 16; ++k1) sts64(cb1 + 8 * k1 * ROWB, v1[k1]);
     }
-    // spectrum values of the first half of the column multiply, issued before the
-    // group barrier so that their L2 latency overlaps the wait
-    cplx<float> sa[8], sb[8];
+    // spectrum values of round 0 of the mirror-pair product, issued before the group
+    // barrier so that their L2 latency overlaps the wait: one 16-byte load (S+, S-) per
+    // pair of elements
+    const float4 *sp4 = P.spec4 + (size_t)sel * N * 64 + slot;
+    const float4 *spx = P.specx4 + (size_t)sel * N;
+    int kA = m8, kB = (16 - m8) & 15;          // round 0 (m8 = 0: both 0)
+    if (zpat) kB = 8;
+    float4 S[8];
 #pragma unroll
-    for (int k2 = 0; k2 < 8; ++k2) {
-      sa[k2] = sp[(ck1[0] + 16 * k2) * N + c];
-      sb[k2] = sp[(ck1[1] + 16 * k2) * N + c];
-    }
-    // half-difference table of the two special columns (one lane in 8 of 16 warps;
-    // 1 KB per PSF, L1-resident across walkers)
-    const cplx<float> *sx = P.specx + ((size_t)sel * 2 + (c == 64 ? 1 : 0)) * N;
+    for (int k2 = 0; k2 < 8; ++k2) S[k2] = __ldg(sp4 + (kA + 16 * k2) * 64);
     group_barrier(1 + cg, 128);
 
-    // --------------- columns: radix-8, spectrum multiply, inverse radix-8 --
+    // ---------- columns: radix-8, mirror-pair spectrum product, inverse radix-8 --
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int k1a = ck1[2 * half], k1b = ck1[2 * half + 1];
-      const smem_addr_t ba = tile + 8u * k1a * ROWB, bq = tile + 8u * k1b * ROWB;
+    for (int round = 0; round < 2; ++round) {
+      // columns of the two units: (slot, mirror), slot 0: column 0, then column 64
+      const int ca = slot0 ? 64 * round : slot;
+      const int cb = slot0 ? 64 * round : 128 - slot;
+      const smem_addr_t ba = tile + 8u * kA * ROWB, bq = tile + 8u * kB * ROWB;
+      const unsigned aev = 8u * ca, aod = 8u * (ca ^ 8), bev = 8u * cb, bod = 8u * (cb ^ 8);
       cplx<float> a[8], bb[8];
 #pragma unroll
       for (int n2 = 0; n2 < 8; ++n2) {
-        const unsigned cc = (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
-        a[n2] = lds64(ba + cc);
-        bb[n2] = lds64(bq + cc);
+        a[n2] = lds64(ba + (unsigned)n2 * ROWB + ((n2 & 1) ? aod : aev));
+        bb[n2] = lds64(bq + (unsigned)n2 * ROWB + ((n2 & 1) ? bod : bev));
       }
-      dft8<float, false>(a);    // a[k2]  = U[k1a + 16 k2][c]
-      dft8<float, false>(bb);
-      if (!special) {
+      dft8<float, false>(a);    // a[k2]  = U[kA + 16 k2][ca]
+      dft8<float, false>(bb);   // bb[k2] = U[kB + 16 k2][cb]
+      if (zpat) {
+        // columns 0 / 64, k1 = 0 (a) and 8 (bb): every mirror is in the same array
+        mirror_self(a[0], S[0]);
+        mirror_self(a[4], S[4]);
 #pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2) {
-          a[k2] = a[k2] * sa[k2];
-          bb[k2] = bb[k2] * sb[k2];
-        }
+        for (int k2 = 1; k2 < 4; ++k2) mirror_pair(a[k2], a[8 - k2], S[k2]);
+        const float4 *s8 = round == 0 ? sp4 : spx;
+        const int st = round == 0 ? 64 : 1;
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2)
+          mirror_pair(bb[k2], bb[7 - k2], __ldg(s8 + (8 + 16 * k2) * st));
+      } else if (xpat && round == 0) {
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) mirror_pair(a[k2], bb[(8 - k2) & 7], S[k2]);
       } else {
-        if (m == 0 && half == 0) {   // k1a = 0: ky <-> (128 - ky); k1b = 8: k2 <-> 7-k2
-          special_pair(a[0], a[0], sa[0], ldc2(sx), sa[0], ldc2(sx));
-          special_pair(a[4], a[4], sa[4], ldc2(sx + 64), sa[4], ldc2(sx + 64));
 #pragma unroll
-          for (int k2 = 1; k2 < 4; ++k2)
-            special_pair(a[k2], a[8 - k2], sa[k2], ldc2(sx + 16 * k2), sa[8 - k2],
-                         ldc2(sx + 16 * (8 - k2)));
-#pragma unroll
-          for (int k2 = 0; k2 < 4; ++k2)
-            special_pair(bb[k2], bb[7 - k2], sb[k2], ldc2(sx + 8 + 16 * k2), sb[7 - k2],
-                         ldc2(sx + 8 + 16 * (7 - k2)));
-        } else {                     // a[k2] <-> bb[7 - k2]
-#pragma unroll
-          for (int k2 = 0; k2 < 8; ++k2)
-            special_pair(a[k2], bb[7 - k2], sa[k2], ldc2(sx + k1a + 16 * k2), sb[7 - k2],
-                         ldc2(sx + k1b + 16 * (7 - k2)));
-        }
+        for (int k2 = 0; k2 < 8; ++k2) mirror_pair(a[k2], bb[7 - k2], S[k2]);
       }
-      if (half == 0) {   // prefetch the second half's spectrum values
+      int kA1 = kB, kB1 = kA;                  // round 1
+      if (m8 == 0) kA1 = kB1 = 8;
+      if (zpat) kA1 = 0;
+      if (round == 0) {   // prefetch round 1's spectrum values
+        const float4 *s1 = slot0 ? spx : sp4;
+        const int st = slot0 ? 1 : 64;
 #pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2) {
-          sa[k2] = sp[(ck1[2] + 16 * k2) * N + c];
-          sb[k2] = sp[(ck1[3] + 16 * k2) * N + c];
-        }
+        for (int k2 = 0; k2 < 8; ++k2) S[k2] = __ldg(s1 + (kA1 + 16 * k2) * st);
       }
       dft8<float, true>(a);     // a[n2]: inverse over k2
       dft8<float, true>(bb);
 #pragma unroll
       for (int n2 = 0; n2 < 8; ++n2) {
-        const unsigned cc = (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
-        sts64(ba + cc, a[n2]);
-        sts64(bq + cc, bb[n2]);
+        sts64(ba + (unsigned)n2 * ROWB + ((n2 & 1) ? aod : aev), a[n2]);
+        sts64(bq + (unsigned)n2 * ROWB + ((n2 & 1) ? bod : bev), bb[n2]);
       }
+      kA = kA1;
+      kB = kB1;
     }
     group_barrier(1 + cg, 128);
 
@@ -708,201 +699,6 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   }
 }
 
-// --------------------------------------------------------------------------
-// 1024-thread variant: the same passes with ONE 16-point unit per thread and pass
-// (32 warps, 64 registers): twice the resident warps per scheduler to hide the
-// latencies the 512-thread kernel is bound by. Rows: warp w owns rows 4w..4w+3.
-// Columns: thread (c, m), m = 0..7: radix-16 of residue n2 = m, then the radix-8
-// pair k1 in {m, 16 - m} ({0, 8} for m = 0), closed under k1 -> -k1. The eight warps of
-// a column group are spread over the four schedulers (see fused_lnlike_kernel).
-#define PSFMC_FUSED_THREADS_WIDE 1024
-
-// Thread roles are recomputed from an opaque copy of the thread index at the start of
-// every phase, so that the compiler cannot keep them alive across phases (64
-// registers per thread leave no room for loop-invariant luggage).
-__device__ __forceinline__ int opaque_tid() {
-  int t = threadIdx.x;
-#ifndef PSFMC_EMU
-  asm volatile("" : "+r"(t));
-#endif
-  return t;
-}
-
-__device__ __forceinline__ RowRole make_row_role(int tid) {
-  RowRole R;
-  const int lane = tid & 31;
-  R.w = tid >> 5;
-  R.rr = lane >> 3;
-  R.l = lane & 7;
-  R.l0 = (R.l == 0);
-  const unsigned s = R.rr & 1;
-  const unsigned kA = R.l, kB = R.l0 ? 8 : 16 - R.l;
-  R.t16 = (8u * R.l) ^ (64u * s);
-  R.qa = 64u * (kA ^ s) + 8u * (kA & 7);
-  R.qb = 64u * (kB ^ s) + 8u * (kB & 7);
-  R.fa = 8u * (kA ^ (8u * s));
-  R.fb = 8u * (kB ^ (8u * s));
-  return R;
-}
-
-__global__ void __launch_bounds__(PSFMC_FUSED_THREADS_WIDE, 1)
-fused_lnlike_kernel_wide(const FusedParams P) {
-  PSFMC_DYN_SMEM(smem_raw);
-  const smem_addr_t tile = smem_base(smem_raw);
-  constexpr int NW = PSFMC_FUSED_THREADS_WIDE / 32;
-  __shared__ double red_s[NW];
-  __shared__ int cnt_s;
-  constexpr int N = PSFMC_FUSED_N;
-  constexpr unsigned ROWB = N * 8;
-  __shared__ __align__(16) float tw_s[128][2];
-  {
-    const int tid = threadIdx.x;
-    if (tid == 0) cnt_s = 0;
-    if (tid < 128) {
-      const int k1 = tid >> 3, ll = tid & 7;
-      tw_s[tid][0] = c_tw128[ll * 16 + k1][0];
-      tw_s[tid][1] = c_tw128[ll * 16 + k1][1];
-    }
-  }
-  const smem_addr_t tw_base = smem_base(reinterpret_cast<unsigned char *>(&tw_s[0][0]));
-  __syncthreads();
-
-#pragma unroll 1
-  for (long long b = (long long)blockIdx.x - (long long)gridDim.x; b < P.n_batch;
-       b += gridDim.x) {
-    const bool cur = b >= 0;
-    if (cur) {
-      int sel = P.psf_sel[b];
-      const bool invalid = sel < 0;
-      if (invalid) sel = 0;
-      const cplx<float> *sp = P.spec + (size_t)sel * N * N;
-      __syncthreads();
-      // ---- columns: radix-16 of residue n2 = m
-      {
-        const int tid = opaque_tid();
-        const int w = tid >> 5, m = w & 7, cg = w >> 3, c = cg * 32 + (tid & 31);
-        const smem_addr_t cb = tile + (unsigned)m * ROWB + 8u * ((m & 1) ? (c ^ 8) : c);
-        cplx<float> v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = lds64(cb + 8 * j * ROWB);
-        dft16<false>(v);
-#pragma unroll
-        for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * tw128(m, k1);
-#pragma unroll
-        for (int k1 = 0; k1 < 16; ++k1) sts64(cb + 8 * k1 * ROWB, v[k1]);
-        group_barrier(1 + cg, 256);
-      }
-
-      // ---- columns: radix-8 pair, spectrum multiply, inverse radix-8
-      {
-        const int tid = opaque_tid();
-        const int w = tid >> 5, m = w & 7, cg = w >> 3, c = cg * 32 + (tid & 31);
-        const bool special = (c == 0) || (c == 64);
-        const int k1a = m, k1b = (m == 0) ? 8 : 16 - m;
-        const unsigned cev = 8u * c, cod = 8u * (c ^ 8);
-        const smem_addr_t ba = tile + 8u * k1a * ROWB, bq = tile + 8u * k1b * ROWB;
-        const cplx<float> *spa = sp + k1a * N + c, *spb = sp + k1b * N + c;
-        cplx<float> a[8], bb[8];
-#pragma unroll
-        for (int n2 = 0; n2 < 8; ++n2) {
-          const unsigned cc = (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
-          a[n2] = lds64(ba + cc);
-          bb[n2] = lds64(bq + cc);
-        }
-        dft8<float, false>(a);    // a[k2]  = U[k1a + 16 k2][c]
-        dft8<float, false>(bb);
-        if (!special) {
-#pragma unroll
-          for (int k2 = 0; k2 < 8; ++k2) a[k2] = a[k2] * ldc2(spa + 16 * k2 * N);
-#pragma unroll
-          for (int k2 = 0; k2 < 8; ++k2) bb[k2] = bb[k2] * ldc2(spb + 16 * k2 * N);
-        } else {
-          const cplx<float> *sx = P.specx + ((size_t)sel * 2 + (c == 64 ? 1 : 0)) * N;
-          if (m == 0) {   // k1a = 0: ky <-> (128 - ky); k1b = 8: k2 <-> 7 - k2
-            special_pair(a[0], a[0], ldc2(spa), ldc2(sx), ldc2(spa), ldc2(sx));
-            special_pair(a[4], a[4], ldc2(spa + 64 * N), ldc2(sx + 64), ldc2(spa + 64 * N),
-                         ldc2(sx + 64));
-#pragma unroll
-            for (int k2 = 1; k2 < 4; ++k2)
-              special_pair(a[k2], a[8 - k2], ldc2(spa + 16 * k2 * N), ldc2(sx + 16 * k2),
-                           ldc2(spa + 16 * (8 - k2) * N), ldc2(sx + 16 * (8 - k2)));
-#pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2)
-              special_pair(bb[k2], bb[7 - k2], ldc2(spb + 16 * k2 * N),
-                           ldc2(sx + 8 + 16 * k2), ldc2(spb + 16 * (7 - k2) * N),
-                           ldc2(sx + 8 + 16 * (7 - k2)));
-          } else {        // a[k2] <-> bb[7 - k2]
-#pragma unroll
-            for (int k2 = 0; k2 < 8; ++k2)
-              special_pair(a[k2], bb[7 - k2], ldc2(spa + 16 * k2 * N),
-                           ldc2(sx + k1a + 16 * k2), ldc2(spb + 16 * (7 - k2) * N),
-                           ldc2(sx + k1b + 16 * (7 - k2)));
-          }
-        }
-        dft8<float, true>(a);     // a[n2]: inverse over k2
-        dft8<float, true>(bb);
-#pragma unroll
-        for (int n2 = 0; n2 < 8; ++n2) {
-          const unsigned cc = (unsigned)n2 * ROWB + ((n2 & 1) ? cod : cev);
-          sts64(ba + cc, a[n2]);
-          sts64(bq + cc, bb[n2]);
-        }
-        group_barrier(1 + cg, 256);
-      }
-
-      // ---- columns: inverse radix-16 of residue n2 = m
-      {
-        const int tid = opaque_tid();
-        const int w = tid >> 5, m = w & 7, cg = w >> 3, c = cg * 32 + (tid & 31);
-        const smem_addr_t cb = tile + (unsigned)m * ROWB + 8u * ((m & 1) ? (c ^ 8) : c);
-        cplx<float> v[16];
-#pragma unroll
-        for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(cb + 8 * k1 * ROWB);
-#pragma unroll
-        for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], tw128(m, k1));
-        dft16<true>(v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) sts64(cb + 8 * j * ROWB, v[j]);
-      }
-      __syncthreads();
-
-      // ---- rows: inverse + chi-square of walker b
-      {
-        const int tid = opaque_tid();
-        const RowRole R = make_row_role(tid);
-        const float unscale = (float)(P.vscale_inv[sel] / P.wscale[b]);
-        double acc = fused_rows_inverse<false>(P, tile, R, tw_base + 8u * R.l, 0, unscale);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-        if ((tid & 31) == 0) {
-          volatile double *red = red_s;
-          red[tid >> 5] = acc;
-          __threadfence_block();
-          const int prev = atomicAdd(&cnt_s, 1);
-          if (prev == NW - 1) {
-            __threadfence_block();
-            double tot = 0.0;
-            for (int k = 0; k < NW; ++k) tot += red[k];
-            double val = -0.5 * tot;
-            if (!isfinite(val) || invalid) val = -INFINITY;
-            P.lnl[b] = val;
-            cnt_s = 0;
-          }
-        }
-      }
-    }
-    // ---- rows: render + forward of the CTA's next walker
-    const long long bn = b + gridDim.x;
-    if (bn < P.n_batch) {
-      const RowRole R = make_row_role(opaque_tid());
-      fused_rows_forward<false>(P, tile, R, tw_base + 8u * R.l,
-                                P.rconst + bn * P.ncomp * PSFMC_RC_STRIDE,
-                                P.derived + bn * P.ncomp * PSFMC_DERIVED_STRIDE, 0,
-                                (float)P.wscale[bn]);
-    }
-  }
-}
-
 // -------------------------------------------------------------- host side --
 
 // (the TRANSFORM frame must be 128 x 128: the observation frame itself, or any smaller
@@ -921,9 +717,6 @@ inline int fused_prepare_device(const StagedPlan &) {
                            PSFMC_FUSED_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(fused_lnlike_kernel<true>,
                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           PSFMC_FUSED_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(fused_lnlike_kernel_wide,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                            PSFMC_FUSED_SMEM) != cudaSuccess)
     return 1;
 #endif
@@ -931,53 +724,43 @@ inline int fused_prepare_device(const StagedPlan &) {
 }
 
 // Re-layout of the float64 spectra [K][2*Wc][H] (column-major, see
-// kernels_staged.cuh) for the fused kernel:
-//   spec [K][ky][c]: c in 1..63 -> P[ky][kx=c]; c in 65..127 -> V[ky][kx=c-64];
-//                    c = 0 -> (P[ky][0] + P[ky][64]) / 2; c = 64 -> same for V
-//   specx[K][t][ky] = (S[ky][0] - S[ky][64]) / 2 for S = P (t = 0) and S = V (t = 1)
-// `vscale[k]` multiplies the V channel (power of two, undone in the epilogue).
+// kernels_staged.cuh; P = PSF, V = PSF variance, normalisation and ifftshift sign
+// folded in) for the mirror-pair product of the fused kernel:
+//   spec4 [K][ky][slot]: (S+, S-) = (P +- v V) / 2 at (ky, kx = slot), slot = 0..63
+//   specx4[K][ky]      : the same at kx = 64
+// `vscale[k]` = v multiplies the V channel (power of two, undone in the epilogue).
+// The mirrored element (-ky, -kx) uses the complex conjugates (P and V are spectra of
+// real images); at the four self-mirrored elements (kx, ky in {0, 64}) the spectra are
+// real, their imaginary rounding residue is dropped like a c2r transform drops it.
 inline void fused_spectrum_layout(const cplx<double> *spec64, int n_psf,
-                                  const double *vscale, cplx<float> *spec,
-                                  cplx<float> *specx) {
+                                  const double *vscale, float4 *spec4, float4 *specx4) {
   constexpr int N = PSFMC_FUSED_N, Wc = N / 2 + 1;
   for (int k = 0; k < n_psf; ++k) {
     const cplx<double> *src = spec64 + (size_t)k * 2 * Wc * N;
-    // `split`: the factor 1/2 of the real-pair split of the row spectra, folded in
-    // for the regular columns; the packed DC/Nyquist columns carry exact values
-    auto at = [&](int chan, int kx, int ky, double split) {
-      const cplx<double> &s = src[((size_t)chan * Wc + kx) * N + ky];
-      const double f = (chan ? vscale[k] : 1.0) * split;
-      cplx<float> o;
-      o.x = (float)(s.x * f);
-      o.y = (float)(s.y * f);
-      return o;
-    };
-    for (int ky = 0; ky < N; ++ky) {
-      for (int c = 0; c < N; ++c) {
-        const int chan = c >= 64 ? 1 : 0, kx = c & 63;
-        if (kx != 0) spec[((size_t)k * N + ky) * N + c] = at(chan, kx, ky, 0.5);
+    for (int ky = 0; ky < N; ++ky)
+      for (int kx = 0; kx <= 64; ++kx) {
+        const cplx<double> &pp = src[((size_t)0 * Wc + kx) * N + ky];
+        const cplx<double> &vv = src[((size_t)1 * Wc + kx) * N + ky];
+        const bool self = (kx == 0 || kx == 64) && (ky == 0 || ky == 64);
+        const double vy = self ? 0.0 : vv.y, py = self ? 0.0 : pp.y;
+        float4 o;
+        o.x = (float)(0.5 * (pp.x + vscale[k] * vv.x));
+        o.y = (float)(0.5 * (py + vscale[k] * vy));
+        o.z = (float)(0.5 * (pp.x - vscale[k] * vv.x));
+        o.w = (float)(0.5 * (py - vscale[k] * vy));
+        if (kx < 64)
+          spec4[((size_t)k * N + ky) * 64 + kx] = o;
+        else
+          specx4[(size_t)k * N + ky] = o;
       }
-      for (int t = 0; t < 2; ++t) {
-        const cplx<double> &s0 = src[((size_t)t * Wc + 0) * N + ky];
-        const cplx<double> &s64 = src[((size_t)t * Wc + 64) * N + ky];
-        const double f = t ? vscale[k] : 1.0;
-        cplx<float> &sum = spec[((size_t)k * N + ky) * N + 64 * t];
-        cplx<float> &dif = specx[((size_t)k * 2 + t) * N + ky];
-        sum.x = (float)(0.5 * f * (s0.x + s64.x));
-        sum.y = (float)(0.5 * f * (s0.y + s64.y));
-        dif.x = (float)(0.5 * f * (s0.x - s64.x));
-        dif.y = (float)(0.5 * f * (s0.y - s64.y));
-      }
-    }
   }
 }
 
 struct FusedBuffers {
   float *rconst = nullptr;
-  const cplx<float> *spec = nullptr, *specx = nullptr;
+  const float4 *spec4 = nullptr, *specx4 = nullptr;
   const float2 *ow = nullptr;
   int n_sms = 148;
-  bool wide = false;   // 1024-thread variant
   unsigned skip_quads = 0;   // see FusedParams
 };
 
@@ -1006,8 +789,8 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
   P.wscale = buf.wscale;
   P.psf_sel = buf.psf_sel;
   P.vscale_inv = buf.vscale_inv;
-  P.spec = fb.spec;
-  P.specx = fb.specx;
+  P.spec4 = fb.spec4;
+  P.specx4 = fb.specx4;
   P.ow = fb.ow;
   P.lnl = lnl;
   P.n_batch = n_batch;
@@ -1017,10 +800,7 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
     P.kind[c] = (signed char)(c < ncomp ? prog_h.kind[c] : 0);
   unsigned grid = (unsigned)(n_batch < fb.n_sms ? n_batch : fb.n_sms);
   if (ev_begin) cudaEventRecord(ev_begin, stream);
-  if (fb.wide && !plan.fr.padded)
-    launch_kernel(fused_lnlike_kernel_wide, dim3(grid), dim3(PSFMC_FUSED_THREADS_WIDE),
-                  (size_t)PSFMC_FUSED_SMEM, stream, P);
-  else if (plan.fr.padded)
+  if (plan.fr.padded)
     launch_kernel(fused_lnlike_kernel<true>, dim3(grid), dim3(PSFMC_FUSED_THREADS),
                   (size_t)PSFMC_FUSED_SMEM, stream, P, F);
   else

@@ -61,23 +61,6 @@ def test_emu_fused_persistent_loop(emu_library, c1_golden, monkeypatch):
                      fp32_bounds(model, thetas))
 
 
-def test_emu_fused_wide_variant(emu_library, c1_golden, monkeypatch):
-    """The 1024-thread variant of the fused kernel (one 16-point unit per thread and
-    pass) against the golden vectors, including a multi-walker CTA loop."""
-    monkeypatch.setenv('PSFMC_FUSED_VARIANT', '1024')
-    monkeypatch.setenv('PSFMC_FUSED_CTAS', '3')
-    model = model_from_file('j0005/model_c1.py', 'fp32', library=emu_library,
-                            obs_dtype=np.float64)
-    assert model.engine.info()['path'] == 1
-    thetas = np.array(c1_golden['theta'][:8])
-    got = model.log_likelihood_batch(thetas)
-    assert_lnl_close(got, c1_golden['lnl']['M3'][:8], 'fp32', fp32_bounds(model, thetas))
-    monkeypatch.setenv('PSFMC_FUSED_VARIANT', '512')
-    narrow = model_from_file('j0005/model_c1.py', 'fp32', library=emu_library,
-                             obs_dtype=np.float64).log_likelihood_batch(thetas)
-    assert_lnl_close(got, narrow, 'fp32', 2 * fp32_bounds(model, thetas))
-
-
 def test_emu_rawf32_tracks_m2(emu_library, c1_golden):
     model = model_from_file('j0005/model_c1.py', 'fp64_rawf32', library=emu_library)
     thetas = np.array(c1_golden['theta'][:6])
