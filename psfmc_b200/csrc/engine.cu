@@ -118,6 +118,8 @@ struct DeviceState {
   DevBuf<float> rconst;
   float4 *fspec = nullptr, *fspecx = nullptr;   // fused kernel (128 x 128)
   float2 *fow = nullptr;
+  unsigned short *fmaskw = nullptr;   // fused 128 kernel: good-pixel bits per row-pass thread
+  double lnl_const = 0.0;             // ln(2 pi) * number of good pixels
   float4 *cspec = nullptr, *cspecx = nullptr;   // cluster kernel (256 x 256)
   float2 *ctw = nullptr;
   int n_clusters = 0;
@@ -286,6 +288,7 @@ struct Engine : EngineBase {
       cudaFree(d.fspec);
       cudaFree(d.fspecx);
       cudaFree(d.fow);
+      cudaFree(d.fmaskw);
       cudaFree(d.cspec);
       cudaFree(d.cspecx);
       cudaFree(d.ctw);
@@ -397,6 +400,8 @@ struct Engine : EngineBase {
       fb.spec4 = d.fspec;
       fb.specx4 = d.fspecx;
       fb.ow = d.fow;
+      fb.maskw = d.fmaskw;
+      fb.lnl_const = d.lnl_const;
       fb.n_sms = d.n_sms;
       fb.skip_quads = d.skip_quads;
       cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1396,14 +1401,27 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       std::vector<double> vs(d->n_psf);
       for (int k = 0; k < d->n_psf; ++k) vs[k] = 1.0 / vscale_inv[k];
       fused_spectrum_layout(spec64.data(), d->n_psf, vs.data(), fspec.data(), fspecx.data());
-      std::vector<float2> ow(npx);   // over the transform frame (padding: excluded)
+      // (obs, ovar) over the transform frame; excluded pixels (mask, bad data, padding)
+      // carry (0, 1e30) -- finite, whatever the data there -- and a 0 in the mask words
+      // [row][l]: bit j <-> pixel x = l + 8 j (the 16 pixels of a row-pass thread)
+      std::vector<float2> ow(npx);
+      std::vector<unsigned short> maskw(N * 8, 0);
+      long long n_good = 0;
       for (size_t e = 0; e < npx; ++e) {
-        float v = fabsf((float)ovar[e]);
+        if (bad[e]) {
+          ow[e].x = 0.0f;
+          ow[e].y = 1.0e30f;
+          continue;
+        }
         ow[e].x = (float)obs[e];
-        ow[e].y = bad[e] ? -v : v;
+        ow[e].y = fabsf((float)ovar[e]);
+        const size_t y = e / N, x = e % N;
+        maskw[y * 8 + (x & 7)] |= (unsigned short)(1u << (x >> 3));
+        ++n_good;
       }
+      ds.lnl_const = 1.8378770664093454836 * (double)n_good;
       if ((rc = upload(&ds.fspec, fspec)) || (rc = upload(&ds.fspecx, fspecx)) ||
-          (rc = upload(&ds.fow, ow)))
+          (rc = upload(&ds.fow, ow)) || (rc = upload(&ds.fmaskw, maskw)))
         break;
       // rows whose four-row group holds no good pixel never enter the sum
       ds.skip_quads = 0;

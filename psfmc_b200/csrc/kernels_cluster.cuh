@@ -725,11 +725,13 @@ inline int launch_cluster_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
   P.spec4 = nullptr;
   P.specx4 = nullptr;
   P.ow = cb.ow;
+  P.maskw = nullptr;
+  P.lnl_const = 0.0;
   P.lnl = lnl;
   P.n_batch = n_batch;
   P.ncomp = ncomp;
-  for (int c = 0; c < PSFMC_MAX_COMPONENTS; ++c)
-    P.kind[c] = (signed char)(c < ncomp ? prog_h.kind[c] : 0);
+  P.kind_bits = 0;
+  for (int c = 0; c < ncomp; ++c) P.kind_bits |= (unsigned long long)(prog_h.kind[c] & 3) << (2 * c);
   CP.spec4 = cb.spec4;
   CP.specx4 = cb.specx4;
   CP.tw = cb.tw;

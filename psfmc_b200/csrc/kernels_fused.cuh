@@ -50,13 +50,16 @@ struct FusedParams {
   const float4 *spec4;       // [K][ky=128][slot=64]: (S+, S-) of column kx = slot, see
                              // fused_spectrum_layout()
   const float4 *specx4;      // [K][ky=128]: the same for the self-mirrored column kx = 64
-  const float2 *ow;          // [128*128]: (obs, bad ? -ovar : +ovar)
+  const float2 *ow;          // [128*128]: (obs, ovar); (0, 1e30) at excluded pixels
+  const unsigned short *maskw;  // [128 rows][8]: bit j of entry (y, l): pixel (y, l + 8 j) good
+  double lnl_const;          // ln(2 pi) * number of good pixels
   double *lnl;               // [B]
   long long n_batch;
   int ncomp;
   unsigned skip_quads;       // bit q: rows 4q .. 4q+3 hold no good pixel (mask, bad pixels,
                              // padding): their inverse row transform and epilogue are skipped
-  signed char kind[PSFMC_MAX_COMPONENTS];
+  unsigned long long kind_bits;   // 2 bits per component (a kernel-parameter ARRAY indexed
+                                  // by a loop variable is copied to local memory)
 };
 
 // padded frames (see Frame in common.cuh): observation frame and fold bounds
@@ -159,7 +162,7 @@ __device__ __forceinline__ void fused_render16(const FusedParams &P, const float
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = mk<float>(0.0f, 0.0f);
   for (int c = 0; c < P.ncomp; ++c) {
-    const int kind = P.kind[c];
+    const int kind = (int)((P.kind_bits >> (2 * c)) & 3ull);
     const float *rc = rc0 + c * PSFMC_RC_STRIDE;
     if (kind == PSFMC_SKY) {
       const cplx<float> adu = bcast(STAGED ? *rc : __ldg(rc));
@@ -184,7 +187,7 @@ __device__ __forceinline__ void fused_render16(const FusedParams &P, const float
       for (int i = 0; i < 8; ++i) {
         const cplx<float> dx =
             (dxi + mk<float>((float)(2 * XS * i), (float)(2 * XS * i + XS))) + nxf;
-        acc[i] = acc[i] + sersic_pair_f32(s, dx, cu, cv, dy2);
+        acc[i] = sersic_pair_f32(s, dx, cu, cv, dy2, acc[i]);
       }
     } else {  // point source: at most 7 x 7 pixels of the frame, float64 taps
       const double *d = der0 + c * PSFMC_DERIVED_STRIDE;
@@ -352,6 +355,7 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   // last (L2 latency hidden behind the whole inverse transform)
   float2 o[16];
   const float2 *owr = P.ow + y * PSFMC_FUSED_N + R.l;
+  const unsigned mw = __ldg(P.maskw + y * 8 + R.l);   // bit j: pixel x = l + 8 j is good
   if (PREFETCH) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
@@ -404,14 +408,35 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
   }
+  // Chi-square terms (psfMC/models.py:233-236) of the 16 pixels, float32, summed in
+  // float32 over 8 pixels before they enter the float64 sum:
+  //     resid^2 ivm - log(ivm / 2 pi) = resid^2 / tot + ln2 log2(tot) + ln(2 pi),
+  // tot = model variance + observation variance; ln(2 pi) times the number of good pixels
+  // is added once per walker (FusedParams::lnl_const). One packed FFMA2 gives (resid, tot);
+  // masked pixels are left out by predication (bit j of the thread's mask word; their
+  // table entry is (0, 1e30), so nothing non-finite arises from the observation there).
+  // The float32 transform must not leave the convolved model variance below -2^-8 of the
+  // pixel's own variance (see Epilogue<float>::term): the minimum of
+  // tot - (1 - 2^-8) ovar over the pixels is checked once per thread.
+  const cplx<float> cu = mk<float>(-1.0f, unscale);
   double acc = 0.0;
+  float s1 = 0.0f, s2 = 0.0f, mn = 3.0e38f;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    float resid, ivm;
-    const double t = Epilogue<float>::term(v[j].x, v[j].y * unscale, o[j].x,
-                                           fabsf(o[j].y), &resid, &ivm);
-    if (__float_as_int(o[j].y) >= 0) acc += t;
+    const cplx<float> rt = pfma(v[j], cu, mk<float>(o[j].x, o[j].y));   // (resid, tot)
+    const float ivm = fast_rcp(rt.y), l2 = fast_lg2(rt.y);
+    const float r2 = rt.x * rt.x;
+    mn = fminf(mn, fmaf(-(1.0f - PSFMC_VAR_NOISE_TOL), o[j].y, rt.y));
+    if ((mw >> j) & 1u) {
+      s1 = fmaf(r2, ivm, s1);
+      s2 += l2;
+    }
+    if ((j & 7) == 7) {
+      acc += (double)fmaf(0.69314718055994530942f, s2, s1);
+      s1 = s2 = 0.0f;
+    }
   }
+  if (mn < 0.0f) acc = NAN;
   return acc;
 }
 
@@ -688,7 +713,7 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
             __threadfence_block();
             double tot = 0.0;
             for (int k = 0; k < PSFMC_FUSED_THREADS / 32; ++k) tot += red[k];
-            double val = -0.5 * tot;
+            double val = -0.5 * (tot + P.lnl_const);
             if (!isfinite(val) || invalid) val = -INFINITY;
             P.lnl[b] = val;
             cnt_s = 0;
@@ -760,6 +785,8 @@ struct FusedBuffers {
   float *rconst = nullptr;
   const float4 *spec4 = nullptr, *specx4 = nullptr;
   const float2 *ow = nullptr;
+  const unsigned short *maskw = nullptr;
+  double lnl_const = 0.0;
   int n_sms = 148;
   unsigned skip_quads = 0;   // see FusedParams
 };
@@ -792,12 +819,14 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
   P.spec4 = fb.spec4;
   P.specx4 = fb.specx4;
   P.ow = fb.ow;
+  P.maskw = fb.maskw;
+  P.lnl_const = fb.lnl_const;
   P.lnl = lnl;
   P.n_batch = n_batch;
   P.ncomp = ncomp;
   P.skip_quads = fb.skip_quads;
-  for (int c = 0; c < PSFMC_MAX_COMPONENTS; ++c)
-    P.kind[c] = (signed char)(c < ncomp ? prog_h.kind[c] : 0);
+  P.kind_bits = 0;
+  for (int c = 0; c < ncomp; ++c) P.kind_bits |= (unsigned long long)(prog_h.kind[c] & 3) << (2 * c);
   unsigned grid = (unsigned)(n_batch < fb.n_sms ? n_batch : fb.n_sms);
   if (ev_begin) cudaEventRecord(ev_begin, stream);
   if (plan.fr.padded)

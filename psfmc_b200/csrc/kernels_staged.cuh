@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 6 : 1) rows_fwd_kernel(F
                                            (float)(y0 + (e1 >> fr.logW)));
           const cplx<float> dx = (fx - xi) - xf;
           const cplx<float> dy = (fy - yi) - yf;
-          acc[j] = acc[j] + sersic_pair2_f32(s, dx, dy);
+          acc[j] = sersic_pair2_f32(s, dx, dy, acc[j]);
         }
       }
     }

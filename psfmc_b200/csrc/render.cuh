@@ -376,40 +376,56 @@ __device__ __forceinline__ cplx<float> rcp_pair_fma(cplx<float> x) {
 #endif
 }
 
+// Reciprocal of a pixel pair for the centroid correction. Default: two MUFU.RCP (1 ulp).
+// The render was bound by the SFU in round 1 and took its reciprocals from the FMA pipe
+// (rcp_pair_fma: ~8 packed / integer instructions per pair); with the transforms now on
+// packed FP32 instructions the FMA pipe and the issue slots are the scarcer resources
+// (ncu r2: FMA pipe ~50 % busy, XU 27 %), so the two extra MUFU per pair are cheaper.
+// -DPSFMC_RCP_FMA restores the Newton form.
+__device__ __forceinline__ cplx<float> rcp_pair(cplx<float> x) {
+#if defined(PSFMC_RCP_FMA) && !defined(PSFMC_EMU)
+  return rcp_pair_fma(x);
+#else
+  return mk<float>(fast_rcp(x.x), fast_rcp(x.y));
+#endif
+}
+
 // Two pixels of one row at once (x offsets dx.x, dx.y from the centre), element-wise
 // pair arithmetic (packed FFMA2/FMUL2 on the device): same formula as
 // sersic_pixel_f32. cu = a01*dy, cv = a11*dy, dy2 = dy*dy are per-row constants.
+// Returns acc + value (the sum rides on the last multiply).
 __device__ __forceinline__ cplx<float> sersic_pair_f32(const SersicF32 &s, cplx<float> dx,
-                                                       float cu, float cv, float dy2) {
+                                                       float cu, float cv, float dy2,
+                                                       cplx<float> acc) {
   const cplx<float> u = pfma(bcast(s.a00), dx, bcast(cu));
   const cplx<float> v = pfma(bcast(s.a10), dx, bcast(cv));
   const cplx<float> sq = pfma(v, v, pmul(u, u));
   const cplx<float> r2 = pfma(dx, dx, bcast(dy2));
-  const cplx<float> e = pmul(bcast(s.p), mk<float>(fast_lg2(sq.x), fast_lg2(sq.y)));
+  // (sq - sq) = 0 for finite sq, NaN for an infinite one (see SersicF32): rides on the
+  // multiply by p as its addend
+  const cplx<float> e = pfma(bcast(s.p), mk<float>(fast_lg2(sq.x), fast_lg2(sq.y)), sq - sq);
   const cplx<float> t = mk<float>(fast_ex2(e.x), fast_ex2(e.y));
-  const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0) + (sq - sq));
+  const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0));
   const cplx<float> sb = mk<float>(fast_ex2(arg.x), fast_ex2(arg.y));
   const cplx<float> gu = pmul(bcast(s.kq), t);
   const cplx<float> g = mk<float>(fminf(gu.x, 1.0e18f), fminf(gu.y, 1.0e18f));
-  const cplx<float> q = pmul(pmul(g, g), rcp_pair_fma(r2));
-  return pfma(sb, q, sb);    // sb * (1 + q)
+  return pfma(sb, pfma(pmul(g, g), rcp_pair(r2), bcast(1.0f)), acc);    // + sb * (1 + q)
 }
 
 // Two arbitrary pixels at once (offsets (dx.x, dy.x) and (dx.y, dy.y) from the centre).
 __device__ __forceinline__ cplx<float> sersic_pair2_f32(const SersicF32 &s, cplx<float> dx,
-                                                        cplx<float> dy) {
+                                                        cplx<float> dy, cplx<float> acc) {
   const cplx<float> u = pfma(bcast(s.a00), dx, pmul(bcast(s.a01), dy));
   const cplx<float> v = pfma(bcast(s.a10), dx, pmul(bcast(s.a11), dy));
   const cplx<float> sq = pfma(v, v, pmul(u, u));
   const cplx<float> r2 = pfma(dx, dx, pmul(dy, dy));
-  const cplx<float> e = pmul(bcast(s.p), mk<float>(fast_lg2(sq.x), fast_lg2(sq.y)));
+  const cplx<float> e = pfma(bcast(s.p), mk<float>(fast_lg2(sq.x), fast_lg2(sq.y)), sq - sq);
   const cplx<float> t = mk<float>(fast_ex2(e.x), fast_ex2(e.y));
-  const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0) + (sq - sq));
+  const cplx<float> arg = pfma(bcast(-s.c1), t, bcast(s.c0));
   const cplx<float> sb = mk<float>(fast_ex2(arg.x), fast_ex2(arg.y));
   const cplx<float> gu = pmul(bcast(s.kq), t);
   const cplx<float> g = mk<float>(fminf(gu.x, 1.0e18f), fminf(gu.y, 1.0e18f));
-  const cplx<float> q = pmul(pmul(g, g), rcp_pair_fma(r2));
-  return pfma(sb, q, sb);    // sb * (1 + q)
+  return pfma(sb, pfma(pmul(g, g), rcp_pair(r2), bcast(1.0f)), acc);    // + sb * (1 + q)
 }
 
 }  // namespace psfmc
