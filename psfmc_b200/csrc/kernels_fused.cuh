@@ -39,7 +39,12 @@ namespace psfmc {
 
 #define PSFMC_FUSED_N 128
 #define PSFMC_FUSED_THREADS 512
-#define PSFMC_FUSED_SMEM (PSFMC_FUSED_N * PSFMC_FUSED_N * 8)
+// Bytes per tile row: 128 complex64 values (column layout: column kx at 8 kx) + room for
+// the row pass's exchange layout (16 x 10 complex positions, see lds64 below). The
+// pitch is an ODD multiple of 64 bytes, so the two rows of a half-warp fall on different
+// banks in the column layout without any swizzle.
+#define PSFMC_FUSED_ROWB 1344
+#define PSFMC_FUSED_SMEM (PSFMC_FUSED_N * PSFMC_FUSED_ROWB)
 
 struct FusedParams {
   const float *rconst;       // [B][ncomp][PSFMC_RC_STRIDE]
@@ -109,16 +114,19 @@ __device__ __forceinline__ void dft16(cplx<float> *v) {
   for (int k = 0; k < 16; ++k) v[k] = t[4 * (k & 3) + (k >> 2)];
 }
 
-// Shared-memory tile access by BYTE offset (32-bit address arithmetic; XOR swizzles
-// act directly on the address). Exchange layout of a row between its radix-16 and
-// radix-8 sides: element (k1, n2) of row y sits at complex position
-//     8 * (k1 ^ s) + (n2 ^ (k1 & 7)),   s = y & 1,
-// which is free of bank conflicts on both sides (fixed k1 / lanes over n2, and fixed
-// n2 / lanes over k1) and keeps the two rows of a half-warp on different banks.
-// All its fields are bit-disjoint, so the byte offset is (thread constant) XOR
-// (compile-time constant): one LOP3 per access.
-// The tile is 1024-byte aligned, so a row base plus a thread constant below 1024
-// can be XOR-ed with compile-time constants on the final address.
+// Shared-memory tile access by BYTE offset (32-bit address arithmetic). Exchange layout
+// of a row between its radix-16 and radix-8 sides: element (k1, n2) of row y sits at
+// complex position
+//     10 k1 + n2
+// inside the row's own 1344 bytes (an odd multiple of 64: consecutive rows are half a
+// bank cycle apart). Radix-16 side (one k1 per instruction, lanes over n2, two rows per
+// half-warp): 2 x 8 consecutive positions on opposite bank halves = one conflict-free
+// 128-byte wavefront. Radix-8 side: a thread's eight n2 values of one k1
+// are 64 contiguous, 16-byte aligned bytes = four 128-bit accesses, and the eight
+// threads of a row (k1 = 0..7 or 8..15, pitch 80 bytes) cover all eight 16-byte bank
+// groups (5 k1 mod 8 is a permutation). Every address is a per-thread base plus a
+// compile-time immediate: no address arithmetic per access (the XOR-swizzled layout of
+// round 1 cost one LOP3 per access and eight 64-bit accesses where four 128-bit ones do).
 #ifdef PSFMC_EMU
 typedef uintptr_t smem_addr_t;
 #else
@@ -139,6 +147,32 @@ __device__ __forceinline__ void sts64(smem_addr_t addr, cplx<float> v) {
   *reinterpret_cast<cplx<float> *>(addr) = v;
 #else
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+#endif
+}
+struct cplx2f {   // two adjacent complex64 values (one 128-bit shared-memory access)
+  cplx<float> lo, hi;
+};
+__device__ __forceinline__ cplx2f lds128(smem_addr_t addr) {
+  cplx2f v;
+#ifdef PSFMC_EMU
+  v.lo = reinterpret_cast<const cplx<float> *>(addr)[0];
+  v.hi = reinterpret_cast<const cplx<float> *>(addr)[1];
+#else
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.lo.x), "=f"(v.lo.y), "=f"(v.hi.x), "=f"(v.hi.y)
+               : "r"(addr)
+               : "memory");
+#endif
+  return v;
+}
+__device__ __forceinline__ void sts128(smem_addr_t addr, cplx<float> lo, cplx<float> hi) {
+#ifdef PSFMC_EMU
+  reinterpret_cast<cplx<float> *>(addr)[0] = lo;
+  reinterpret_cast<cplx<float> *>(addr)[1] = hi;
+#else
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(lo.x), "f"(lo.y),
+               "f"(hi.x), "f"(hi.y)
+               : "memory");
 #endif
 }
 __device__ __forceinline__ smem_addr_t smem_base(unsigned char *ptr) {
@@ -187,7 +221,10 @@ __device__ __forceinline__ void fused_render16(const FusedParams &P, const float
       for (int i = 0; i < 8; ++i) {
         const cplx<float> dx =
             (dxi + mk<float>((float)(2 * XS * i), (float)(2 * XS * i + XS))) + nxf;
-        acc[i] = sersic_pair_f32(s, dx, cu, cv, dy2, acc[i]);
+        if ((PSFMC_RCP_PATTERN >> i) & 1)
+          acc[i] = sersic_pair_f32<true>(s, dx, cu, cv, dy2, acc[i]);
+        else
+          acc[i] = sersic_pair_f32<false>(s, dx, cu, cv, dy2, acc[i]);
       }
     } else {  // point source: at most 7 x 7 pixels of the frame, float64 taps
       const double *d = der0 + c * PSFMC_DERIVED_STRIDE;
@@ -266,9 +303,9 @@ __device__ __forceinline__ void mirror_self(cplx<float> &z, float4 s) {
 struct RowRole {
   int w, rr, l;
   bool l0;
-  unsigned t16;     // radix-16 side of the exchange layout: (8 l) ^ (64 s)
-  unsigned qa, qb;  // radix-8 side, for k1 = kA / kB: 64 (k ^ s) + 8 (k & 7)
-  unsigned fa, fb;  // column layout: 8 (k ^ 8 s); column k + 16 k2 at + 128 k2
+  unsigned t16;     // radix-16 side of the exchange layout: 8 l, k1 at + 80 k1
+  unsigned qa, qb;  // radix-8 side, for k1 = kA / kB: 80 k, n2 at + 8 n2
+  unsigned fa, fb;  // column layout: 8 k; column k + 16 k2 at + 128 k2
 };
 
 // render + forward row transform of row batch `it` of walker b
@@ -282,7 +319,7 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
                                                    int it, float wsc,
                                                    const FoldParams *F = nullptr) {
   const int y = it * 64 + R.w * 4 + R.rr;
-  const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
+  const smem_addr_t rb = tile + (unsigned)y * PSFMC_FUSED_ROWB;
   if (PADDED && y - R.rr >= F->Hr) {
     // all four rows of the warp lie outside the observation frame: their row spectra
     // are zero (the tile still holds the previous walker's values there)
@@ -310,27 +347,34 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
     }
     dft16<false>(v);
 #pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) v[k1] = v[k1] * lds64(twl + 64 * k1);
+    for (int k1 = 0; k1 < 16; k1 += 2) {
+      const cplx2f w = lds128(twl + 16 * (k1 >> 1));
+      if (k1 > 0) v[k1] = v[k1] * w.lo;
+      v[k1 + 1] = v[k1 + 1] * w.hi;
+    }
     __syncwarp();   // every lane is done reading this row (previous walker)
     const smem_addr_t rt = rb + R.t16;
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) sts64(rt ^ (unsigned)(64 * k1 + 8 * (k1 & 7)), v[k1]);
+    for (int k1 = 0; k1 < 16; ++k1) sts64(rt + 80 * k1, v[k1]);
   }
   __syncwarp();
   cplx<float> a[8], bb[8];
   {
     const smem_addr_t ra = rb + R.qa, rq = rb + R.qb;
 #pragma unroll
-    for (int n2 = 0; n2 < 8; ++n2) {
-      a[n2] = lds64(ra ^ (unsigned)(8 * n2));
-      bb[n2] = lds64(rq ^ (unsigned)(8 * n2));
+    for (int n2 = 0; n2 < 8; n2 += 2) {
+      const cplx2f pa = lds128(ra + 8 * n2), pb = lds128(rq + 8 * n2);
+      a[n2] = pa.lo;
+      a[n2 + 1] = pa.hi;
+      bb[n2] = pb.lo;
+      bb[n2 + 1] = pb.hi;
     }
   }
   __syncwarp();
   dft8<float, false>(a);    // a[k2]  = Z[kA + 16 k2]
   dft8<float, false>(bb);   // bb[k2] = Z[kB + 16 k2]
-  // the row spectrum of the packed row goes to the columns as it is (column kx at
-  // kx ^ 8 (y & 1)); the two images are taken apart only implicitly, by mirror_pair
+  // the row spectrum of the packed row goes to the columns as it is (column kx at 8 kx);
+  // the two images are taken apart only implicitly, by mirror_pair
 #pragma unroll
   for (int k2 = 0; k2 < 8; ++k2) {
     sts64(rb + R.fa + 8 * 16 * k2, a[k2]);
@@ -350,7 +394,7 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   if (PADDED && y - R.rr >= F->Hr) return 0.0;   // the warp's four rows are padding
   // ... or hold no unmasked pixel: nothing of them enters the sum (models.py:233-236)
   if ((P.skip_quads >> (it * 16 + R.w)) & 1u) return 0.0;
-  const smem_addr_t rb = tile + (unsigned)y * (PSFMC_FUSED_N * 8);
+  const smem_addr_t rb = tile + (unsigned)y * PSFMC_FUSED_ROWB;
   // observation + signed variance of this thread's 16 pixels: issued first, used
   // last (L2 latency hidden behind the whole inverse transform)
   float2 o[16];
@@ -372,9 +416,9 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   {
     const smem_addr_t ra = rb + R.qa, rq = rb + R.qb;
 #pragma unroll
-    for (int n2 = 0; n2 < 8; ++n2) {
-      sts64(ra ^ (unsigned)(8 * n2), a[n2]);
-      sts64(rq ^ (unsigned)(8 * n2), bb[n2]);
+    for (int n2 = 0; n2 < 8; n2 += 2) {
+      sts128(ra + 8 * n2, a[n2], a[n2 + 1]);
+      sts128(rq + 8 * n2, bb[n2], bb[n2 + 1]);
     }
   }
   __syncwarp();
@@ -382,10 +426,14 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   {
     const smem_addr_t rt = rb + R.t16;
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(rt ^ (unsigned)(64 * k1 + 8 * (k1 & 7)));
+    for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(rt + 80 * k1);
   }
 #pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul_conj(v[k1], lds64(twl + 64 * k1));
+  for (int k1 = 0; k1 < 16; k1 += 2) {
+    const cplx2f w = lds128(twl + 16 * (k1 >> 1));
+    if (k1 > 0) v[k1] = cmul_conj(v[k1], w.lo);
+    v[k1 + 1] = cmul_conj(v[k1 + 1], w.hi);
+  }
   dft16<true>(v);           // v[j] = (convolved model, scaled model variance)
   if (PADDED) {
     // fold the linear convolution back modulo Wr (see Frame): through the row's own
@@ -448,7 +496,7 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   __shared__ double red_s[PSFMC_FUSED_THREADS / 32];
   __shared__ int cnt_s;
   constexpr int N = PSFMC_FUSED_N;
-  constexpr unsigned ROWB = N * 8;   // bytes per tile row
+  constexpr unsigned ROWB = PSFMC_FUSED_ROWB;   // bytes per tile row
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) cnt_s = 0;
 
@@ -461,22 +509,22 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   {
     const unsigned s = R.rr & 1;
     const unsigned kA = R.l, kB = R.l0 ? 8 : 16 - R.l;
-    R.t16 = (8u * R.l) ^ (64u * s);
-    R.qa = 64u * (kA ^ s) + 8u * (kA & 7);
-    R.qb = 64u * (kB ^ s) + 8u * (kB & 7);
-    R.fa = 8u * (kA ^ (8u * s));
-    R.fb = 8u * (kB ^ (8u * s));
+    R.t16 = 8u * R.l;
+    R.qa = 80u * kA;
+    R.qb = 80u * kB;
+    R.fa = 8u * kA;
+    R.fb = 8u * kB;
   }
-  // twiddles of the row passes W128^(l*k1) in shared memory as [k1][l]: the eight
-  // threads of a row read eight consecutive entries (no bank conflicts, 4 rows
-  // broadcast); this thread's entries are twl + 64 * k1
-  __shared__ __align__(16) float tw_s[128][2];
+  // twiddles of the row passes W128^(l*k1) in shared memory as [l][k1] with a pitch of
+  // 144 bytes: a thread takes its sixteen values with eight 128-bit loads (twl + 16 i =
+  // k1 2i, 2i+1); the eight threads of a row hit the eight 16-byte bank groups
+  __shared__ __align__(16) float tw_s[8][36];   // row l: 16 complex values + 16 bytes
   if (tid < 128) {
-    const int k1 = tid >> 3, ll = tid & 7;
-    tw_s[tid][0] = c_tw128[ll * 16 + k1][0];
-    tw_s[tid][1] = c_tw128[ll * 16 + k1][1];
+    const int k1 = tid & 15, ll = tid >> 4;
+    tw_s[ll][2 * k1] = c_tw128[ll * 16 + k1][0];
+    tw_s[ll][2 * k1 + 1] = c_tw128[ll * 16 + k1][1];
   }
-  const smem_addr_t twl = smem_base(reinterpret_cast<unsigned char *>(&tw_s[0][0])) + 8u * R.l;
+  const smem_addr_t twl = smem_base(reinterpret_cast<unsigned char *>(&tw_s[0][0])) + 144u * R.l;
   // constants of the walker the next forward pass renders, staged one walker ahead
   // (during the column passes) so that the render does not wait for L2
   __shared__ __align__(16) float rc_s[PSFMC_MAX_COMPONENTS * PSFMC_RC_STRIDE];
@@ -515,8 +563,7 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   const int cg = w >> 2, m = w & 3;
   const int c = lane < 16 ? 16 * cg + lane
                           : ((16 * cg + lane - 16) == 0 ? 64 : 128 - (16 * cg + lane - 16));
-  // byte offsets of column c in even / odd rows (row swizzle = 8 * parity)
-  const unsigned cev = 8u * c, cod = 8u * (c ^ 8);
+  const unsigned cev = 8u * c;   // byte offset of column c in a row
   const int slot = 16 * cg + (lane & 15), m8 = 2 * m + (lane >> 4);
   const bool slot0 = slot == 0;
   const bool zpat = slot0 && m8 == 0;          // one thread of the CTA
@@ -551,7 +598,7 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
     // ------------------------------------------------- columns: radix-16 --
     // both residues n2 = m and m + 4 of this thread in flight at once (ILP)
     {
-      const smem_addr_t cb0 = tile + (unsigned)m * ROWB + ((m & 1) ? cod : cev);
+      const smem_addr_t cb0 = tile + (unsigned)m * ROWB + cev;
       const smem_addr_t cb1 = cb0 + 4 * ROWB;
       cplx<float> v0[16], v1[16];
 #pragma unroll
@@ -588,12 +635,12 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
       const int ca = slot0 ? 64 * round : slot;
       const int cb = slot0 ? 64 * round : 128 - slot;
       const smem_addr_t ba = tile + 8u * kA * ROWB, bq = tile + 8u * kB * ROWB;
-      const unsigned aev = 8u * ca, aod = 8u * (ca ^ 8), bev = 8u * cb, bod = 8u * (cb ^ 8);
+      const unsigned aev = 8u * ca, bev = 8u * cb;
       cplx<float> a[8], bb[8];
 #pragma unroll
       for (int n2 = 0; n2 < 8; ++n2) {
-        a[n2] = lds64(ba + (unsigned)n2 * ROWB + ((n2 & 1) ? aod : aev));
-        bb[n2] = lds64(bq + (unsigned)n2 * ROWB + ((n2 & 1) ? bod : bev));
+        a[n2] = lds64(ba + (unsigned)n2 * ROWB + aev);
+        bb[n2] = lds64(bq + (unsigned)n2 * ROWB + bev);
       }
       dft8<float, false>(a);    // a[k2]  = U[kA + 16 k2][ca]
       dft8<float, false>(bb);   // bb[k2] = U[kB + 16 k2][cb]
@@ -628,8 +675,8 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
       dft8<float, true>(bb);
 #pragma unroll
       for (int n2 = 0; n2 < 8; ++n2) {
-        sts64(ba + (unsigned)n2 * ROWB + ((n2 & 1) ? aod : aev), a[n2]);
-        sts64(bq + (unsigned)n2 * ROWB + ((n2 & 1) ? bod : bev), bb[n2]);
+        sts64(ba + (unsigned)n2 * ROWB + aev, a[n2]);
+        sts64(bq + (unsigned)n2 * ROWB + bev, bb[n2]);
       }
       kA = kA1;
       kB = kB1;
@@ -638,7 +685,7 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
 
     // ----------------------------------------- columns: inverse radix-16 --
     {
-      const smem_addr_t cb0 = tile + (unsigned)m * ROWB + ((m & 1) ? cod : cev);
+      const smem_addr_t cb0 = tile + (unsigned)m * ROWB + cev;
       const smem_addr_t cb1 = cb0 + 4 * ROWB;
       cplx<float> v0[16], v1[16];
 #pragma unroll
@@ -660,20 +707,20 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
     if (PADDED) {
       // fold the linear convolution back modulo Hr (see Frame): row p receives rows
       // p + Hr (p <= fy_hi) and 128 + p - Hr (p >= fy_lo); the sources lie at or beyond
-      // row Hr, the targets below it. Column c of row y sits at c ^ (8 * (y & 1)).
+      // row Hr, the targets below it.
       for (int e = tid; e < F.Hr * N; e += PSFMC_FUSED_THREADS) {
         const int p = e >> 7, cc = e & (N - 1);
         const bool hi = p <= F.fy_hi, lo = p >= F.fy_lo;
         if (hi || lo) {
-          const smem_addr_t dst = tile + (unsigned)p * ROWB + 8u * (cc ^ (8 * (p & 1)));
+          const smem_addr_t dst = tile + (unsigned)p * ROWB + 8u * cc;
           cplx<float> acc = lds64(dst);
           if (hi) {
             const int q = p + F.Hr;
-            acc = acc + lds64(tile + (unsigned)q * ROWB + 8u * (cc ^ (8 * (q & 1))));
+            acc = acc + lds64(tile + (unsigned)q * ROWB + 8u * cc);
           }
           if (lo) {
             const int q = N + p - F.Hr;
-            acc = acc + lds64(tile + (unsigned)q * ROWB + 8u * (cc ^ (8 * (q & 1))));
+            acc = acc + lds64(tile + (unsigned)q * ROWB + 8u * cc);
           }
           sts64(dst, acc);
         }

@@ -376,24 +376,29 @@ __device__ __forceinline__ cplx<float> rcp_pair_fma(cplx<float> x) {
 #endif
 }
 
-// Reciprocal of a pixel pair for the centroid correction. Default: two MUFU.RCP (1 ulp).
-// The render was bound by the SFU in round 1 and took its reciprocals from the FMA pipe
-// (rcp_pair_fma: ~8 packed / integer instructions per pair); with the transforms now on
-// packed FP32 instructions the FMA pipe and the issue slots are the scarcer resources
-// (ncu r2: FMA pipe ~50 % busy, XU 27 %), so the two extra MUFU per pair are cheaper.
-// -DPSFMC_RCP_FMA restores the Newton form.
+// Reciprocal of a pixel pair for the centroid correction: from the FMA pipe (integer
+// seed + three Newton steps, rcp_pair_fma) or from the SFU (two MUFU.RCP, 1 ulp).
+template <bool MUFU = true>
 __device__ __forceinline__ cplx<float> rcp_pair(cplx<float> x) {
-#if defined(PSFMC_RCP_FMA) && !defined(PSFMC_EMU)
-  return rcp_pair_fma(x);
-#else
-  return mk<float>(fast_rcp(x.x), fast_rcp(x.y));
+#ifndef PSFMC_EMU
+  if (!MUFU) return rcp_pair_fma(x);
 #endif
+  return mk<float>(fast_rcp(x.x), fast_rcp(x.y));
 }
+// Which of the eight pixel pairs of a fused-render thread take their reciprocal from
+// the SFU (bit i set) and which from the FMA pipe. Measured on the B200 (r2, C1, 2048
+// walkers per launch): all SFU 241.8 us (the render phase becomes SFU-bound: XU 31 %,
+// MIO-queue stalls), half 240.3, three quarters 239.8, none 239.8 -- a wash, so the
+// Newton form stays (it is also the more accurate one: unbiased, ~0.5 ulp).
+#ifndef PSFMC_RCP_PATTERN
+#define PSFMC_RCP_PATTERN 0x00
+#endif
 
 // Two pixels of one row at once (x offsets dx.x, dx.y from the centre), element-wise
 // pair arithmetic (packed FFMA2/FMUL2 on the device): same formula as
 // sersic_pixel_f32. cu = a01*dy, cv = a11*dy, dy2 = dy*dy are per-row constants.
 // Returns acc + value (the sum rides on the last multiply).
+template <bool MUFU = true>
 __device__ __forceinline__ cplx<float> sersic_pair_f32(const SersicF32 &s, cplx<float> dx,
                                                        float cu, float cv, float dy2,
                                                        cplx<float> acc) {
@@ -409,7 +414,7 @@ __device__ __forceinline__ cplx<float> sersic_pair_f32(const SersicF32 &s, cplx<
   const cplx<float> sb = mk<float>(fast_ex2(arg.x), fast_ex2(arg.y));
   const cplx<float> gu = pmul(bcast(s.kq), t);
   const cplx<float> g = mk<float>(fminf(gu.x, 1.0e18f), fminf(gu.y, 1.0e18f));
-  return pfma(sb, pfma(pmul(g, g), rcp_pair(r2), bcast(1.0f)), acc);    // + sb * (1 + q)
+  return pfma(sb, pfma(pmul(g, g), rcp_pair<MUFU>(r2), bcast(1.0f)), acc);    // + sb * (1 + q)
 }
 
 // Two arbitrary pixels at once (offsets (dx.x, dy.x) and (dx.y, dy.y) from the centre).
@@ -425,7 +430,7 @@ __device__ __forceinline__ cplx<float> sersic_pair2_f32(const SersicF32 &s, cplx
   const cplx<float> sb = mk<float>(fast_ex2(arg.x), fast_ex2(arg.y));
   const cplx<float> gu = pmul(bcast(s.kq), t);
   const cplx<float> g = mk<float>(fminf(gu.x, 1.0e18f), fminf(gu.y, 1.0e18f));
-  return pfma(sb, pfma(pmul(g, g), rcp_pair(r2), bcast(1.0f)), acc);    // + sb * (1 + q)
+  return pfma(sb, pfma(pmul(g, g), rcp_pair<false>(r2), bcast(1.0f)), acc);    // + sb * (1 + q)
 }
 
 }  // namespace psfmc
