@@ -148,6 +148,19 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 6 : 1) rows_fwd_kernel(F
         } else {
           s = make_sersic_f32(d);
         }
+        if (W == 2 * nthreads) {
+          // 512-column frames (RB = 4): pair j is row y0 + j at x = tid and tid + W/2 --
+          // the x offsets are computed once per component, the row terms are scalars
+          // (same arithmetic as the fused kernel's render, see fused_render16)
+          const cplx<float> dx =
+              (mk<float>((float)tid, (float)(tid + nthreads)) - bcast(s.xi)) - bcast(s.xf);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float dy = ((float)(y0 + j) - s.yi) - s.yf;
+            acc[j] = sersic_pair_f32<false>(s, dx, s.a01 * dy, s.a11 * dy, dy * dy, acc[j]);
+          }
+          continue;
+        }
         const cplx<float> xi = bcast(s.xi), xf = bcast(s.xf), yi = bcast(s.yi),
                           yf = bcast(s.yf);
 #pragma unroll

@@ -163,7 +163,10 @@ inline void syncwarp() {
 // bar.sync id, nthreads: named barrier over `nthreads` threads of the CTA
 inline void named_barrier(int id, int nthreads) {
   State &st = S();
-  if ((int)st.named.size() <= id) st.named.resize(id + 1);
+  if (id < 0 || id >= (int)st.named.size()) {
+    std::fprintf(stderr, "cuda_emu: named barrier id %d out of range\n", id);
+    std::abort();
+  }
   State::Named &nb = st.named[id];
   unsigned long long gen = nb.gen;
   nb.count++;
@@ -258,7 +261,9 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F &&body, unsigned cluster
           st.cta_rank = k;
           st.live = nthreads;
           st.bar_count = 0;
-          st.named.clear();
+          // sixteen hardware barriers, sized once: fibers waiting in named_barrier() hold a
+          // reference into this vector, which must therefore never reallocate
+          st.named.assign(16, State::Named());
           st.warps.assign((nthreads + 31) / 32, State::Warp());
           // poison shared memory so that reads of unwritten smem show up as NaNs
           st.smem.assign(smem_bytes + 2048, 0xFF);
