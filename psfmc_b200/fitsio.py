@@ -121,7 +121,10 @@ def _parse_header(raw, offset):
             if key == 'END':
                 done = True
                 break
-            if card[8:10] == '= ':
+            if key == 'HIERARCH' and '=' in card:
+                long_key, _, rest = card[9:].partition('=')
+                hdr[long_key.strip()] = _parse_value(rest)
+            elif card[8:10] == '= ':
                 hdr[key] = _parse_value(card[10:])
                 comment = _split_comment(card[10:])
                 if comment:
@@ -207,6 +210,17 @@ def getdata(source, ext=None, header=False, **_ignored):
 # ---------------------------------------------------------------- writing --
 
 def _format_card(key, value, comment=None):
+    if len(str(key)) > 8:
+        # keywords longer than eight characters go into a HIERARCH card, like astropy
+        # writes them (e.g. the reference's '2SER_index' posterior summaries)
+        text = str(value).replace("'", "''") if not isinstance(
+            value, (bool, np.bool_, int, np.integer, float, np.floating)) else None
+        body = "'{}'".format(text) if text is not None else (
+            ('T' if value else 'F') if isinstance(value, (bool, np.bool_)) else repr(value))
+        card = 'HIERARCH {} = {}'.format(key, body)
+        if comment and len(card) + 3 + len(str(comment)) <= CARD:
+            card += ' / ' + str(comment)
+        return card[:CARD].ljust(CARD)
     key = str(key).upper()[:8]
     if isinstance(value, (bool, np.bool_)):
         body = '{:>20s}'.format('T' if value else 'F')

@@ -44,6 +44,41 @@ def check_convergence_autocorr(sampler, min_chain_to_tau_ratio=10, verbose=0):
     return bool(np.all(sampler.chain.shape[1] > min_chain_to_tau_ratio * acorr))
 
 
+def add_stats_to_header(header, model, database):
+    """Sampler metadata and the posterior summary of every stochastic parameter as
+    header cards (cf. analysis/images.py:104-143): the MC*/MAP* keywords of the trace
+    database, then per parameter, under its FITS abbreviation, 'mean +/- std' (tuple form
+    for vector parameters such as xy), then PSFIMG = the PSF file of the model."""
+    header.commentary.append(('COMMENT', 'psfMC MCMC SAMPLER PARAMETERS'))
+    for key, (value, comment) in annotate_metadata(
+            OrderedDict((k, database.meta[k]) for k in database.meta
+                        if k.startswith(('MC', 'MAP')))).items():
+        header.set(key, value, comment)
+    header.commentary.append(('COMMENT', 'psfMC POSTERIOR MODEL INFORMATION'))
+    stats = OrderedDict()
+    for col_name, fits_abbr in zip(model.param_names, model.param_fits_abbrs):
+        column = np.asarray(database[col_name], dtype=np.float64)
+        mean_post, std_post = np.mean(column, axis=0), np.std(column, axis=0)
+        if np.ndim(mean_post) == 0:
+            value = '{:0.4g} +/- {:0.4g}'.format(float(mean_post), float(std_post))
+        else:
+            value = '({}) +/- ({})'.format(
+                ','.join('{:0.4g}'.format(dim) for dim in mean_post),
+                ','.join('{:0.4g}'.format(dim) for dim in std_post))
+        stats[fits_abbr] = value
+    selector = model.config.psf_selector
+    index = 0
+    if len(selector.filenames) > 1 and 'PSF_Index' in getattr(database, 'colnames',
+                                                               list(database.keys())):
+        best_row = int(np.argmax(database['lnprobability']))
+        index = int(np.rint(np.asarray(database['PSF_Index'])[best_row]))
+        index = min(max(index, 0), len(selector.filenames) - 1)
+    name = selector.filenames[index]
+    stats['PSFIMG'] = name if isinstance(name, str) else 'array'
+    for key, (value, comment) in annotate_metadata(stats).items():
+        header.set(key, value, comment)
+
+
 def save_posterior_images(model, database, output_name='out_{}', mode='weighted',
                           filetypes=default_filetypes, bad_px_value=0,
                           walker_min_percentile=10):
@@ -74,10 +109,7 @@ def save_posterior_images(model, database, output_name='out_{}', mode='weighted'
         warn('Unknown posterior output mode ({}). Posterior model images will not '
              'be saved.'.format(mode))
         return None
-    for key, (value, comment) in annotate_metadata(
-            OrderedDict((k, database.meta[k]) for k in database.meta
-                        if k.startswith(('MC', 'MAP')))).items():
-        header.set(key, value, comment)
+    add_stats_to_header(header, model, database)
     written = []
     for ftype in filetypes:
         img = output[ftype]

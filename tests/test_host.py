@@ -416,6 +416,22 @@ def test_model_galaxy_mcmc_end_to_end(tmp_path, tiny_model):
     for ftype in ('raw_model', 'residual', 'composite_ivm'):
         img = fitsio.getdata('{}_{}.fits'.format(out, ftype))
         assert img.shape == (32, 32) and np.all(np.isfinite(img))
+    # fit summary in the image headers (cf. analysis/images.py:104-143): sampler metadata,
+    # 'mean +/- std' per parameter under its FITS abbreviation, the PSF image
+    hdr = fitsio.getheader('{}_raw_model.fits'.format(out))
+    assert hdr['MCCHAINS'] == nwalk and hdr['MCITER'] == 4
+    assert 'PSFIMG' in hdr
+    from psfmc_b200.database import filter_lowp_walkers
+    kept = filter_lowp_walkers(db, percentile=10)      # as save_posterior_images does
+    for name, abbr in zip(tiny_model.param_names, tiny_model.param_fits_abbrs):
+        column = np.asarray(kept[name], dtype=np.float64)
+        mean, std = np.mean(column, axis=0), np.std(column, axis=0)
+        key = abbr if len(abbr) > 8 else abbr.upper()     # long keys: HIERARCH cards
+        assert ' +/- ' in hdr[key], (key, hdr[key])
+        if np.ndim(mean) == 0:
+            assert hdr[key] == '{:0.4g} +/- {:0.4g}'.format(float(mean), float(std))
+        else:
+            assert hdr[key].startswith('(')
     # resume rule of the reference: an existing database is loaded, not re-sampled
     again = model_galaxy_mcmc(tiny_model, output_name=out, iterations=4, burn=2,
                               chains=nwalk, write_fits=(), verbose=False)
