@@ -117,17 +117,42 @@ class MultiComponentModel(object):
 
     def init_params_from_priors(self, nwalkers):
         """Starting positions drawn from the priors, redrawing per component until
-        its joint prior is finite (cf. models.py:108-130)."""
+        its joint prior is finite (cf. models.py:108-130). Same distribution as the
+        reference's per-walker loop, but every prior is drawn for all walkers in one
+        ``rvs`` call and the component's joint prior is evaluated once per block
+        (the scalar loop cost 0.4 s for 250 walkers -- half of the example run); the
+        draws come from numpy's global random state like the reference's."""
+        nwalkers = int(nwalkers)
         start_positions = np.zeros((nwalkers, self.num_params))
-        for walker in range(nwalkers):
-            pieces = []
-            for comp in self.components:
-                while True:
-                    values = comp.set_stochastic_values('random')
-                    if np.isfinite(comp.log_priors()):
-                        break
-                pieces.append(np.asarray(values, dtype=np.float64))
-            start_positions[walker] = np.concatenate(pieces) if pieces else []
+        column = 0
+        for comp in self.components:
+            free = comp.free_parameters()
+            width = comp.num_stochastics()
+            if width == 0:
+                continue
+            block = np.empty((nwalkers, width))
+            todo = np.arange(nwalkers)
+            for _ in range(1000):
+                cols = []
+                for _, prior, length in free:
+                    size = (len(todo), length) if length > 1 else len(todo)
+                    draw = np.asarray(prior.random(size=size), dtype=np.float64)
+                    cols.append(draw.reshape(len(todo), length))
+                drawn = np.concatenate(cols, axis=1)
+                block[todo] = drawn
+                with np.errstate(all='ignore'):
+                    ok = np.isfinite(comp.log_priors_batch(drawn))
+                todo = todo[~ok]
+                if len(todo) == 0:
+                    break
+            else:
+                raise RuntimeError('could not draw starting positions with a finite '
+                                   'prior for component {}'.format(type(comp).__name__))
+            start_positions[:, column:column + width] = block
+            column += width
+        # leave the components at the last walker's values, like the scalar loop did
+        if nwalkers:
+            self.param_values = start_positions[-1]
         return start_positions
 
     # -- priors ------------------------------------------------------------------
