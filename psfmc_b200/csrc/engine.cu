@@ -25,6 +25,7 @@
 #ifndef PSFMC_NO_FUSED
 #include "kernels_fused.cuh"
 #include "kernels_cluster.cuh"
+#include "kernels_tiled.cuh"
 #endif
 
 using namespace psfmc;
@@ -121,6 +122,12 @@ struct DeviceState {
   unsigned short *fmaskw = nullptr;   // fused 128 kernel: good-pixel bits per row-pass thread
   double lnl_const = 0.0;             // ln(2 pi) * number of good pixels
   float4 *cspec = nullptr, *cspecx = nullptr;   // cluster kernel (256 x 256)
+  // tiled path (512 x 512 as 4 x 4 sub-images, kernels_tiled.cuh)
+  float4 *tspec = nullptr;
+  float2 *ttw = nullptr;
+  unsigned *tskip = nullptr;
+  DevBuf<cplx<float>> tsub;
+  long long tchunk = 1;
   float2 *ctw = nullptr;
   int n_clusters = 0;
   int n_sms = 148;
@@ -291,6 +298,10 @@ struct Engine : EngineBase {
       cudaFree(d.fmaskw);
       cudaFree(d.cspec);
       cudaFree(d.cspecx);
+      cudaFree(d.tspec);
+      cudaFree(d.ttw);
+      cudaFree(d.tskip);
+      d.tsub.release();
       cudaFree(d.ctw);
       d.rconst.release();
       d.wscale.release();
@@ -376,6 +387,14 @@ struct Engine : EngineBase {
     if (path >= 1 && !for_images) {
       if (d.rconst.ensure(nb * ncomp * PSFMC_RC_STRIDE))
         return fail(PSFMC_ERR_CUDA, "device allocation failed (render constants)");
+#ifndef PSFMC_NO_FUSED
+      if (path == 3) {
+        const long long chunk = B < d.tchunk ? B : d.tchunk;
+        if (d.partials.ensure(nb * PSFMC_TILED_SUBS) ||
+            d.tsub.ensure((size_t)chunk * PSFMC_TILED_SUBS * PSFMC_FUSED_N * PSFMC_FUSED_N))
+          return fail(PSFMC_ERR_CUDA, "device allocation failed (sub-image spectra)");
+      }
+#endif
       return 0;
     }
     long long chunk = B < plan.chunk ? B : plan.chunk;
@@ -407,6 +426,26 @@ struct Engine : EngineBase {
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (profiling && (rc = prof_pair(d, &e0, &e1))) return rc;
       launches += launch_fused_lnlike<T>(plan, buf, fb, prog_h, theta_dev, B, ld, lnl_dev,
+                                         stream, e0, e1);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
+    if (path == 3) {
+      TiledBuffers tb;
+      tb.rconst = d.rconst.ptr;
+      tb.spec = d.tspec;
+      tb.tw512 = d.ttw;
+      tb.ow = d.fow;
+      tb.maskw = d.fmaskw;
+      tb.skip_tab = d.tskip;
+      tb.sub_spec = d.tsub.ptr;
+      tb.partials = d.partials.ptr;
+      tb.lnl_const = d.lnl_const;
+      tb.chunk = d.tchunk;
+      tb.n_sms = d.n_sms;
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (profiling && (rc = prof_pair(d, &e0, &e1))) return rc;
+      launches += launch_tiled_lnlike<T>(plan, buf, tb, prog_h, theta_dev, B, ld, lnl_dev,
                                          stream, e0, e1);
       CUDA_TRY(cudaGetLastError());
       return 0;
@@ -1382,6 +1421,7 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
     if (i == 0) {
       eng->path = fused_path_available<T>(eng->plan, eng->prog_h) ? 1 : 0;
       if (cluster_path_available<T>(eng->plan)) eng->path = 2;
+      if (tiled_path_available<T>(eng->plan)) eng->path = 3;
       const char *force = getenv("PSFMC_FORCE_STAGED");
       if (force && force[0] == '1') eng->path = 0;
     }
@@ -1433,6 +1473,77 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
             any_good = !bad[e];
           if (!any_good) ds.skip_quads |= 1u << q;
         }
+    }
+    if (eng->path == 3) {
+      if (tiled_prepare_device()) {
+        rc = fail(PSFMC_ERR_CUDA, "cannot reserve shared memory for the tiled 512 x 512 path");
+        break;
+      }
+      cudaDeviceGetAttribute(&ds.n_sms, cudaDevAttrMultiProcessorCount, ds.ordinal);
+      if (ds.n_sms < 1) ds.n_sms = 148;
+      if (const char *env = getenv("PSFMC_FUSED_CTAS")) {   // tests: force job loops
+        int v = atoi(env);
+        if (v > 0) ds.n_sms = v;
+      }
+      const size_t M = PSFMC_FUSED_N, NT = PSFMC_TILED_N;
+      std::vector<float4> tspec((size_t)d->n_psf * 16 * M * PSFMC_TILED_KX);
+      std::vector<double> vs(d->n_psf);
+      for (int k = 0; k < d->n_psf; ++k) vs[k] = 1.0 / vscale_inv[k];
+      tiled_spectrum_layout(spec64.data(), d->n_psf, vs.data(), tspec.data());
+      std::vector<float2> tw(NT);
+      {
+        const long double pi = 3.14159265358979323846264338327950288L;
+        for (size_t m = 0; m < NT; ++m) {
+          long double ang = -2.0L * pi * (long double)m / (long double)NT;
+          long double c = cosl(ang), sn = sinl(ang);
+          if ((4 * m) % NT == 0) {   // exact values at the quadrant points
+            const long double cq[4] = {1, 0, -1, 0}, sq[4] = {0, -1, 0, 1};
+            c = cq[(4 * m) / NT];
+            sn = sq[(4 * m) / NT];
+          }
+          tw[m].x = (float)c;
+          tw[m].y = (float)sn;
+        }
+      }
+      // observation tables in sub-image order: sub-image s = 4 ry + rx holds the frame
+      // pixels (4 y + ry, 4 x + rx); layout per sub-image as for the 128 x 128 kernel
+      std::vector<float2> ow((size_t)16 * M * M);
+      std::vector<unsigned short> maskw((size_t)16 * M * 8, 0);
+      std::vector<unsigned> skip(16, 0);
+      long long n_good = 0;
+      const char *noskip = getenv("PSFMC_NO_ROW_SKIP");
+      for (size_t sb = 0; sb < 16; ++sb) {
+        const size_t ry = sb >> 2, rx = sb & 3;
+        for (size_t y = 0; y < M; ++y)
+          for (size_t x = 0; x < M; ++x) {
+            const size_t e = (4 * y + ry) * NT + 4 * x + rx, o = (sb * M + y) * M + x;
+            if (bad[e]) {
+              ow[o].x = 0.0f;
+              ow[o].y = 1.0e30f;
+              continue;
+            }
+            ow[o].x = (float)obs[e];
+            ow[o].y = fabsf((float)ovar[e]);
+            maskw[(sb * M + y) * 8 + (x & 7)] |= (unsigned short)(1u << (x >> 3));
+            ++n_good;
+          }
+        if (!(noskip && noskip[0] == '1'))
+          for (int q = 0; q < 32; ++q) {
+            bool any_good = false;
+            for (size_t y = (size_t)q * 4; y < (size_t)(q + 1) * 4 && !any_good; ++y)
+              for (size_t l = 0; l < 8 && !any_good; ++l)
+                any_good = maskw[(sb * M + y) * 8 + l] != 0;
+            if (!any_good) skip[sb] |= 1u << q;
+          }
+      }
+      ds.lnl_const = 1.8378770664093454836 * (double)n_good;
+      ds.tchunk = (long long)(chunk_mbytes_from_env() * 1048576.0 /
+                              (16.0 * M * M * sizeof(cplx<float>)));
+      if (ds.tchunk < 1) ds.tchunk = 1;
+      if ((rc = upload(&ds.tspec, tspec)) || (rc = upload(&ds.ttw, tw)) ||
+          (rc = upload(&ds.fow, ow)) || (rc = upload(&ds.fmaskw, maskw)) ||
+          (rc = upload(&ds.tskip, skip)))
+        break;
     }
     if (eng->path == 2) {
       if (cluster_prepare_device(&ds.n_clusters)) {
@@ -1771,11 +1882,15 @@ int psfmc_engine_info(const psfmc_engine *engine, psfmc_info *info) {
   // fused path: theta in, render constants out+in, lnL out; spectra and observation
   // (2 x 128 KB) are shared by all walkers and stay in L2
   info->hbm_bytes_per_eval =
-      e->path >= 1 ? (double)(8 * 32 + 8 + e->prog_h.n_components *
-                                               (2 * 4 * PSFMC_RC_STRIDE +
-                                                2 * 8 * PSFMC_DERIVED_STRIDE))
-                   : 4.0 * (double)e->plan.scratch_elems_per_walker * csz;
-  info->kernels_per_call = e->path >= 1 ? 2 : 5;
+      e->path == 3
+          // tiled path: the sixteen 128 x 128 sub-spectra are written once, read and
+          // written by the combine kernel and read once: 4 x 2 MB
+          ? 4.0 * 16.0 * 128.0 * 128.0 * 8.0
+          : e->path >= 1 ? (double)(8 * 32 + 8 + e->prog_h.n_components *
+                                                     (2 * 4 * PSFMC_RC_STRIDE +
+                                                      2 * 8 * PSFMC_DERIVED_STRIDE))
+                         : 4.0 * (double)e->plan.scratch_elems_per_walker * csz;
+  info->kernels_per_call = e->path == 3 ? 5 : (e->path >= 1 ? 2 : 5);
   info->launches_total = e->launches.load();
   info->kappa_table = e->kappa_table ? 1 : 0;
   info->rescued_total =

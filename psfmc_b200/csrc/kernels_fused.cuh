@@ -63,6 +63,13 @@ struct FusedParams {
   int ncomp;
   unsigned skip_quads;       // bit q: rows 4q .. 4q+3 hold no good pixel (mask, bad pixels,
                              // padding): their inverse row transform and epilogue are skipped
+  // 512 x 512 frames as 4 x 4 interleaved 128 x 128 sub-images (kernels_tiled.cuh): the
+  // forward / inverse halves of this kernel exchange the sub-images' spectra through
+  // `sub_spec` [jobs][ky=128][kx=128] (job = 16 * walker + sub-image); the inverse half
+  // writes one partial sum per job; row-skip bits per sub-image
+  cplx<float> *sub_spec;
+  double *partials;
+  const unsigned *skip_tab;
   unsigned long long kind_bits;   // 2 bits per component (a kernel-parameter ARRAY indexed
                                   // by a loop variable is copied to local memory)
 };
@@ -312,12 +319,14 @@ struct RowRole {
 // (rc0 / der0: the walker's constants, STAGED = in shared memory, see fused_render16)
 // PADDED: the observation frame is P.Hr x P.Wr in the corner of the 128 x 128 transform
 // frame; nothing is rendered outside it.
-template <bool STAGED, bool PADDED = false>
+// TILED: the tile is sub-image `sub` = 4 ry + rx of a 512 x 512 frame: tile pixel (y, x)
+// is frame pixel (4 y + ry, 4 x + rx).
+template <bool STAGED, bool PADDED = false, bool TILED = false>
 __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_addr_t tile,
                                                    const RowRole &R, smem_addr_t twl,
                                                    const float *rc0, const double *der0,
                                                    int it, float wsc,
-                                                   const FoldParams *F = nullptr) {
+                                                   const FoldParams *F = nullptr, int sub = 0) {
   const int y = it * 64 + R.w * 4 + R.rr;
   const smem_addr_t rb = tile + (unsigned)y * PSFMC_FUSED_ROWB;
   if (PADDED && y - R.rr >= F->Hr) {
@@ -335,7 +344,11 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
   {
     cplx<float> v[16];
     if (!PADDED || y < F->Hr) {
-      fused_render16<8, STAGED>(P, rc0, der0, y, R.l, wsc, v);
+      if (TILED)
+        fused_render16<32, STAGED>(P, rc0, der0, 4 * y + (sub >> 2), 4 * R.l + (sub & 3), wsc,
+                                   v);
+      else
+        fused_render16<8, STAGED>(P, rc0, der0, y, R.l, wsc, v);
       if (PADDED) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -389,17 +402,20 @@ template <bool PREFETCH, bool PADDED = false>
 __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_addr_t tile,
                                                      const RowRole &R, smem_addr_t twl,
                                                      int it, float unscale,
-                                                     const FoldParams *F = nullptr) {
+                                                     const FoldParams *F = nullptr, int sub = 0,
+                                                     unsigned skip_quads = 0) {
   const int y = it * 64 + R.w * 4 + R.rr;
   if (PADDED && y - R.rr >= F->Hr) return 0.0;   // the warp's four rows are padding
   // ... or hold no unmasked pixel: nothing of them enters the sum (models.py:233-236)
-  if ((P.skip_quads >> (it * 16 + R.w)) & 1u) return 0.0;
+  if ((skip_quads >> (it * 16 + R.w)) & 1u) return 0.0;
   const smem_addr_t rb = tile + (unsigned)y * PSFMC_FUSED_ROWB;
   // observation + signed variance of this thread's 16 pixels: issued first, used
   // last (L2 latency hidden behind the whole inverse transform)
   float2 o[16];
-  const float2 *owr = P.ow + y * PSFMC_FUSED_N + R.l;
-  const unsigned mw = __ldg(P.maskw + y * 8 + R.l);   // bit j: pixel x = l + 8 j is good
+  // (sub-image tables of a tiled frame follow each other)
+  const float2 *owr = P.ow + (sub * PSFMC_FUSED_N + y) * PSFMC_FUSED_N + R.l;
+  const unsigned mw = __ldg(P.maskw + (sub * PSFMC_FUSED_N + y) * 8 + R.l);   // bit j: pixel
+                                                                         // x = l + 8 j is good
   if (PREFETCH) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
@@ -488,9 +504,18 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   return acc;
 }
 
-template <bool PADDED>
+// MODE 0: the whole lnL of a 128 x 128 frame. MODE 1 / 2: the forward / inverse half for
+// the 4 x 4 sub-images of a 512 x 512 frame (kernels_tiled.cuh): a "walker" of the loop
+// below is then a job = 16 * walker + sub-image; the forward half stops after the
+// columns' forward radix-8 (its results go to P.sub_spec instead of the spectrum
+// product), the inverse half starts there and ends with one partial sum per job.
+#define PSFMC_MODE_FULL 0
+#define PSFMC_MODE_FWD 1
+#define PSFMC_MODE_INV 2
+template <bool PADDED, int MODE = PSFMC_MODE_FULL>
 __global__ void __launch_bounds__(PSFMC_FUSED_THREADS, 1)
 fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
+  constexpr bool TILED = MODE != PSFMC_MODE_FULL;
   PSFMC_DYN_SMEM(smem_raw);
   const smem_addr_t tile = smem_base(smem_raw);
   __shared__ double red_s[PSFMC_FUSED_THREADS / 32];
@@ -531,7 +556,8 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   __shared__ double der_s[PSFMC_MAX_COMPONENTS * PSFMC_DERIVED_STRIDE];
   __shared__ float wsc_s;
   auto stage_params = [&](long long bs) {
-    if (bs >= P.n_batch) return;
+    if (bs >= P.n_batch || MODE == PSFMC_MODE_INV) return;
+    if (TILED) bs >>= 4;   // job -> walker
     if (tid < P.ncomp * PSFMC_RC_STRIDE)
       rc_s[tid] = __ldg(P.rconst + bs * P.ncomp * PSFMC_RC_STRIDE + tid);
     for (int k = tid; k < P.ncomp * PSFMC_DERIVED_STRIDE; k += PSFMC_FUSED_THREADS)
@@ -581,13 +607,16 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   // CTA's first walker; every later pass runs the column passes of walker b, then
   // its inverse rows interleaved with the forward rows of the CTA's next walker.
 #pragma unroll 1
-  for (long long b = (long long)blockIdx.x - (long long)gridDim.x; b < P.n_batch;
-       b += gridDim.x) {
+  for (long long b = (long long)blockIdx.x -
+                     (MODE == PSFMC_MODE_INV ? 0ll : (long long)gridDim.x);
+       b < P.n_batch; b += gridDim.x) {
     const bool cur = b >= 0;
-    int sel = cur ? P.psf_sel[b] : 0;
+    const long long wb = TILED ? (b >> 4) : b;        // walker of this job
+    const int sub = TILED ? (int)(b & 15) : 0;        // sub-image of this job
+    int sel = (cur && MODE != PSFMC_MODE_FWD) ? P.psf_sel[wb] : 0;
     const bool invalid = sel < 0;
     if (invalid) sel = 0;
-    const double wscale_b = cur ? P.wscale[b] : 1.0;
+    const double wscale_b = (cur && MODE != PSFMC_MODE_FWD) ? P.wscale[wb] : 1.0;
     const float unscale = (float)(P.vscale_inv[sel] / wscale_b);
     if (cur) {
 
@@ -597,7 +626,7 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
 
     // ------------------------------------------------- columns: radix-16 --
     // both residues n2 = m and m + 4 of this thread in flight at once (ILP)
-    {
+    if (MODE != PSFMC_MODE_INV) {
       const smem_addr_t cb0 = tile + (unsigned)m * ROWB + cev;
       const smem_addr_t cb1 = cb0 + 4 * ROWB;
       cplx<float> v0[16], v1[16];
@@ -624,9 +653,34 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
     int kA = m8, kB = (16 - m8) & 15;          // round 0 (m8 = 0: both 0)
     if (zpat) kB = 8;
     float4 S[8];
+    if (!TILED) {
 #pragma unroll
-    for (int k2 = 0; k2 < 8; ++k2) S[k2] = __ldg(sp4 + (kA + 16 * k2) * 64);
-    group_barrier(1 + cg, 128);
+      for (int k2 = 0; k2 < 8; ++k2) S[k2] = __ldg(sp4 + (kA + 16 * k2) * 64);
+    }
+    if (MODE != PSFMC_MODE_INV) group_barrier(1 + cg, 128);
+    // this job's spectrum tile in global memory (tiled frames)
+    cplx<float> *gsub = TILED ? P.sub_spec + (size_t)b * N * N : nullptr;
+    // inverse half: the values of BOTH rounds are requested up front (their L2 / HBM
+    // latency is the only thing this phase waits for)
+    cplx<float> ga[2][8], gb[2][8];
+    if (MODE == PSFMC_MODE_INV) {
+      int ka = kA, kb = kB;
+#pragma unroll
+      for (int round = 0; round < 2; ++round) {
+        const int ca = slot0 ? 64 * round : slot;
+        const int cb = slot0 ? 64 * round : 128 - slot;
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+          ga[round][k2] = gsub[(ka + 16 * k2) * N + ca];
+          gb[round][k2] = gsub[(kb + 16 * k2) * N + cb];
+        }
+        int ka1 = kb, kb1 = ka;
+        if (m8 == 0) ka1 = kb1 = 8;
+        if (zpat) ka1 = 0;
+        ka = ka1;
+        kb = kb1;
+      }
+    }
 
     // ---------- columns: radix-8, mirror-pair spectrum product, inverse radix-8 --
 #pragma unroll
@@ -637,14 +691,30 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
       const smem_addr_t ba = tile + 8u * kA * ROWB, bq = tile + 8u * kB * ROWB;
       const unsigned aev = 8u * ca, bev = 8u * cb;
       cplx<float> a[8], bb[8];
+      if (MODE != PSFMC_MODE_INV) {
 #pragma unroll
-      for (int n2 = 0; n2 < 8; ++n2) {
-        a[n2] = lds64(ba + (unsigned)n2 * ROWB + aev);
-        bb[n2] = lds64(bq + (unsigned)n2 * ROWB + bev);
+        for (int n2 = 0; n2 < 8; ++n2) {
+          a[n2] = lds64(ba + (unsigned)n2 * ROWB + aev);
+          bb[n2] = lds64(bq + (unsigned)n2 * ROWB + bev);
+        }
+        dft8<float, false>(a);    // a[k2]  = U[kA + 16 k2][ca]
+        dft8<float, false>(bb);   // bb[k2] = U[kB + 16 k2][cb]
       }
-      dft8<float, false>(a);    // a[k2]  = U[kA + 16 k2][ca]
-      dft8<float, false>(bb);   // bb[k2] = U[kB + 16 k2][cb]
-      if (zpat) {
+      if (MODE == PSFMC_MODE_FWD) {
+        // forward half: the column spectrum leaves for the 4 x 4 combine kernel
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+          gsub[(kA + 16 * k2) * N + ca] = a[k2];
+          gsub[(kB + 16 * k2) * N + cb] = bb[k2];
+        }
+      } else if (MODE == PSFMC_MODE_INV) {
+        // inverse half: ... and comes back multiplied by the PSF spectra
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+          a[k2] = ga[round][k2];
+          bb[k2] = gb[round][k2];
+        }
+      } else if (zpat) {
         // columns 0 / 64, k1 = 0 (a) and 8 (bb): every mirror is in the same array
         mirror_self(a[0], S[0]);
         mirror_self(a[4], S[4]);
@@ -665,26 +735,28 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
       int kA1 = kB, kB1 = kA;                  // round 1
       if (m8 == 0) kA1 = kB1 = 8;
       if (zpat) kA1 = 0;
-      if (round == 0) {   // prefetch round 1's spectrum values
+      if (round == 0 && !TILED) {   // prefetch round 1's spectrum values
         const float4 *s1 = slot0 ? spx : sp4;
         const int st = slot0 ? 1 : 64;
 #pragma unroll
         for (int k2 = 0; k2 < 8; ++k2) S[k2] = __ldg(s1 + (kA1 + 16 * k2) * st);
       }
-      dft8<float, true>(a);     // a[n2]: inverse over k2
-      dft8<float, true>(bb);
+      if (MODE != PSFMC_MODE_FWD) {
+        dft8<float, true>(a);     // a[n2]: inverse over k2
+        dft8<float, true>(bb);
 #pragma unroll
-      for (int n2 = 0; n2 < 8; ++n2) {
-        sts64(ba + (unsigned)n2 * ROWB + aev, a[n2]);
-        sts64(bq + (unsigned)n2 * ROWB + bev, bb[n2]);
+        for (int n2 = 0; n2 < 8; ++n2) {
+          sts64(ba + (unsigned)n2 * ROWB + aev, a[n2]);
+          sts64(bq + (unsigned)n2 * ROWB + bev, bb[n2]);
+        }
       }
       kA = kA1;
       kB = kB1;
     }
-    group_barrier(1 + cg, 128);
+    if (MODE != PSFMC_MODE_FWD) group_barrier(1 + cg, 128);
 
     // ----------------------------------------- columns: inverse radix-16 --
-    {
+    if (MODE != PSFMC_MODE_FWD) {
       const smem_addr_t cb0 = tile + (unsigned)m * ROWB + cev;
       const smem_addr_t cb1 = cb0 + 4 * ROWB;
       cplx<float> v0[16], v1[16];
@@ -740,11 +812,16 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
       const bool fwd = interleave ? (step & 1) : (step >= 2);
       const int it = interleave ? (step >> 1) : (step & 1);
       if (!fwd) {
-        if (cur) acc += fused_rows_inverse<true, PADDED>(P, tile, R, twl, it, unscale, &F);
-      } else if (has_next) {
-        fused_rows_forward<true, PADDED>(P, tile, R, twl, rc_s, der_s, it, wsc_next, &F);
+        if (cur && MODE != PSFMC_MODE_FWD)
+          acc += fused_rows_inverse<true, PADDED>(
+              P, tile, R, twl, it, unscale, &F, sub,
+              MODE == PSFMC_MODE_INV ? __ldg(P.skip_tab + sub) : P.skip_quads);
+      } else if (has_next && MODE != PSFMC_MODE_INV) {
+        fused_rows_forward<true, PADDED, TILED>(P, tile, R, twl, rc_s, der_s, it, wsc_next, &F,
+                                                TILED ? (int)(bn & 15) : 0);
       }
-      if (cur && ((interleave && step == 2) || (!interleave && step == 1))) {
+      if (cur && MODE != PSFMC_MODE_FWD &&
+          ((interleave && step == 2) || (!interleave && step == 1))) {
         // both inverse batches of this warp are done: float64 reduction. Warp
         // shuffles, then the last warp to arrive sums the per-warp partials in
         // fixed order (deterministic) and writes lnL.
@@ -760,9 +837,15 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
             __threadfence_block();
             double tot = 0.0;
             for (int k = 0; k < PSFMC_FUSED_THREADS / 32; ++k) tot += red[k];
-            double val = -0.5 * (tot + P.lnl_const);
-            if (!isfinite(val) || invalid) val = -INFINITY;
-            P.lnl[b] = val;
+            if (MODE == PSFMC_MODE_INV) {
+              // one partial per job; finalize_kernel sums the 16 of a walker in fixed
+              // order (the constant term rides on sub-image 0)
+              P.partials[b] = sub == 0 ? tot + P.lnl_const : tot;
+            } else {
+              double val = -0.5 * (tot + P.lnl_const);
+              if (!isfinite(val) || invalid) val = -INFINITY;
+              P.lnl[b] = val;
+            }
             cnt_s = 0;
           }
         }

@@ -374,8 +374,9 @@ def check_near_centre_walkers(library):
                      0.25 * fp32_bounds(model, thetas, oracle))
 
 
-def mixed_model_256(precision, library=None, **kwargs):
-    """256 x 256 model for the four-CTA cluster kernel: two PSFs (free PSF index), a
+def mixed_model_256(precision, library=None, n=256, **kwargs):
+    """256 x 256 model for the four-CTA cluster kernel (n = 512: the same scene, scaled,
+    for the tiled 512 x 512 path): two PSFs (free PSF index), a
     bilinear and an edge-clipped Lanczos point source, Sersics with fixed and free
     parameters (one angle in radians), fixed sky, bad pixels, a NaN observation and a
     disc mask -- everything the fused 256 x 256 path has to get right besides the FFT."""
@@ -383,14 +384,14 @@ def mixed_model_256(precision, library=None, **kwargs):
     from psfmc_b200.components import Configuration, PointSource, Sersic, Sky
     from psfmc_b200.distributions import Normal, Uniform
     rng = np.random.RandomState(21)
-    n = 256
+    f = n // 256
     obs = 0.05 * rng.standard_normal((n, n))
     ivm = np.full((n, n), 400.0)
     ivm[5, 7] = 0.0
     ivm[200:204, 20:30] = -1.0
     obs[9, 100] = np.nan
     yy, xx = np.mgrid[0:n, 0:n]
-    mask = ((xx - 120.0) ** 2 + (yy - 131.0) ** 2) > 118.0 ** 2
+    mask = ((xx - 120.0 * f) ** 2 + (yy - 131.0 * f) ** 2) > (118.0 * f) ** 2
     psfs, psf_ivms = [], []
     for sigma, size in ((2.0, 32), (3.1, 48)):
         gy, gx = np.mgrid[0:size, 0:size]
@@ -401,15 +402,18 @@ def mixed_model_256(precision, library=None, **kwargs):
         psf_ivms.append(1.0 / (psf / 200.0 + 1e-4))
     comps = [Configuration(obs, ivm, psfs, psf_ivms, mask_file=mask, mag_zeropoint=25.0),
              Sky(adu=0.003),
-             PointSource(xy=Uniform(loc=np.array((120.0, 124.0)), scale=np.array((8.0, 8.0))),
+             PointSource(xy=Uniform(loc=np.array((120.0 * f, 124.0 * f)),
+                                    scale=np.array((8.0, 8.0))),
                          mag=Uniform(loc=18, scale=2), shift_method='bilinear'),
-             PointSource(xy=Uniform(loc=np.array((0.0, 248.0)), scale=np.array((4.0, 7.9))),
+             PointSource(xy=Uniform(loc=np.array((0.0, n - 8.0)), scale=np.array((4.0, 7.9))),
                          mag=19.5),
-             Sersic(xy=Uniform(loc=np.array((118.0, 122.0)), scale=np.array((10.0, 10.0))),
+             Sersic(xy=Uniform(loc=np.array((118.0 * f, 122.0 * f)),
+                               scale=np.array((10.0, 10.0))),
                     mag=Uniform(loc=19, scale=3), reff=14.0, reff_b=6.0,
                     index=Normal(loc=2.0, scale=0.3), angle=0.4),
-             Sersic(xy=(140.25, 121.5), mag=21.0, reff=Uniform(loc=3, scale=8), reff_b=2.5,
-                    index=1.0, angle=Uniform(loc=0, scale=3.1), angle_degrees=False)]
+             Sersic(xy=(140.25 * f, 121.5 * f), mag=21.0, reff=Uniform(loc=3, scale=8),
+                    reff_b=2.5, index=1.0, angle=Uniform(loc=0, scale=3.1),
+                    angle_degrees=False)]
     return MultiComponentModel(comps, precision=precision, library=library, **kwargs)
 
 
@@ -437,6 +441,36 @@ def check_cluster_path_256(library, n_walkers, monkeypatch=None):
         assert np.array_equal(one.log_likelihood_batch(thetas), got)
         monkeypatch.setenv('PSFMC_FORCE_STAGED', '1')
         staged = mixed_model_256('fp32', library=library, fp64_rescue=False)
+        assert staged.engine.info()['path'] == 0
+        assert_lnl_close(staged.log_likelihood_batch(thetas), expect, 'fp32', bounds)
+    return got
+
+
+def check_tiled_path_512(library, n_walkers, monkeypatch=None):
+    """The tiled 512 x 512 path (4 x 4 sub-images through the fused kernel's halves + the
+    combine kernel, float32) against the oracle and against the staged float32 kernels;
+    results must not depend on the number of persistent CTAs or on the chunking."""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model = mixed_model_256('fp32', library=library, n=512, fp64_rescue=False)
+    assert model.engine.info()['path'] == 3
+    thetas = draw_walkers_fast(model, n_walkers, seed=5)
+    oracle = oracle_from_model(model)
+    expect = oracle.lnlike_batch(thetas)
+    assert np.all(np.isfinite(expect))
+    assert len(set(np.rint(thetas[:, -1]))) == 2      # both PSFs in use
+    bounds = fp32_bounds(model, thetas, oracle)
+    thetas[1, -1] = 7.4       # PSF index out of range: -inf
+    expect[1] = -np.inf
+    got = model.log_likelihood_batch(thetas)
+    assert_lnl_close(got, expect, 'fp32', bounds)
+    if monkeypatch is not None:
+        monkeypatch.setenv('PSFMC_FUSED_CTAS', '3')    # job loops, ragged last round
+        monkeypatch.setenv('PSFMC_CHUNK_MB', '3')      # one walker per chunk
+        one = mixed_model_256('fp32', library=library, n=512, fp64_rescue=False)
+        assert np.array_equal(one.log_likelihood_batch(thetas), got)
+        monkeypatch.delenv('PSFMC_CHUNK_MB')
+        monkeypatch.setenv('PSFMC_FORCE_STAGED', '1')
+        staged = mixed_model_256('fp32', library=library, n=512, fp64_rescue=False)
         assert staged.engine.info()['path'] == 0
         assert_lnl_close(staged.log_likelihood_batch(thetas), expect, 'fp32', bounds)
     return got

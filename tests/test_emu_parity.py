@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import (ARBITRARY_FRAMES, assert_lnl_close, check_arbitrary_frame,
-                      check_cluster_path_256, check_cropped_golden, check_nan_propagation,
+                      check_cluster_path_256, check_tiled_path_512, check_cropped_golden, check_nan_propagation,
                       check_fp64_rescue, check_near_centre_walkers, check_pssub_golden,
                       mixed_model_128, fp32_bounds, load_golden, model_from_file,
                       oracle_from_model)
@@ -281,6 +281,10 @@ def test_emu_cluster_kernel_256(emu_library, monkeypatch):
     """256 x 256 frame split over a four-CTA cluster (distributed shared memory,
     barrier.cluster emulated): two clusters walking over five walkers."""
     check_cluster_path_256(emu_library, 5, monkeypatch)
+
+
+def test_emu_tiled_path_512(emu_library, monkeypatch):
+    check_tiled_path_512(emu_library, 3, monkeypatch)
 
 
 @pytest.mark.parametrize('dims', ARBITRARY_FRAMES[:3] + ARBITRARY_FRAMES[4:6])

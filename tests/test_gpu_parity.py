@@ -588,6 +588,33 @@ def test_gpu_cluster_kernel_256(cuda_library, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_gpu_tiled_path_512(cuda_library, monkeypatch):
+    from conftest import check_tiled_path_512
+    check_tiled_path_512(cuda_library, 40, monkeypatch)
+
+
+def test_gpu_tiled_path_512_properties(cuda_library):
+    """C4 at full ensemble size: determinism, permutation equivariance, independence of the
+    batch composition, agreement with the float64 engine within the absolute statement."""
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.synthetic import draw_walkers_fast, synthetic_components
+    model = MultiComponentModel(synthetic_components(512, 3), precision='fp32',
+                                fp64_rescue=False)
+    assert model.engine.info()['path'] == 3
+    thetas = draw_walkers_fast(model, 600, seed=11)
+    full = model.log_likelihood_batch(thetas)
+    assert np.array_equal(full, model.log_likelihood_batch(thetas))
+    perm = np.random.RandomState(1).permutation(len(thetas))
+    assert np.array_equal(full[perm], model.log_likelihood_batch(thetas[perm]))
+    assert np.array_equal(full[100:137], model.log_likelihood_batch(thetas[100:137]))
+    m64 = MultiComponentModel(synthetic_components(512, 3), precision='fp64')
+    l64 = m64.log_likelihood_batch(thetas[:64])
+    finite = np.isfinite(l64)
+    assert np.array_equal(np.isfinite(full[:64]), finite)
+    err = np.abs(full[:64] - l64)[finite]
+    assert np.all(err <= np.maximum(0.3, 8e-6 * np.abs(l64[finite]))), err.max()
+
+
 def test_gpu_cluster_kernel_256_properties(cuda_library):
     """Full C3 ensemble through the cluster kernel: determinism, permutation
     equivariance, batch-composition independence."""
