@@ -418,6 +418,28 @@ def run_ours(args):
                 sharded_lnlike_device(engine, th, half, ndim, send, recv, stream,
                                       row_offset=h * half)
 
+    # lnL gather over peer memory (CUDA IPC mailboxes, psfmc_lnlike_batch_exchange) instead
+    # of NCCL: the default for N > 1; PSFMC_BENCH_GATHER=nccl keeps the all_gather
+    exchange = None
+    gather_mode = os.environ.get('PSFMC_BENCH_GATHER', 'peer')
+    if world > 1 and gather_mode == 'peer':
+        from psfmc_b200.distributed import PeerExchange
+        try:
+            exchange = PeerExchange(engine, half)
+        except Exception as exc:            # no peer access on this box: fall back, say so
+            print('bench.py: peer exchange unavailable ({}), using NCCL'.format(exc),
+                  file=sys.stderr)
+            exchange = None
+    lnl_gath = torch.zeros(2 * half, dtype=torch.float64, device=dev)
+
+    def step_peer(s, copy=False):
+        # (the gathered values stay in the mailbox, like NCCL's stay in its receive buffer)
+        th = th_dev[s % nsets]
+        for h in range(2):
+            exchange.lnlike(th, half, ndim,
+                            lnl_gath[h * half:(h + 1) * half] if copy else None, stream,
+                            row_offset=h * half)
+
     def step_replica(s):
         """Weak-scaling companion: this rank evaluates a whole ensemble on its own."""
         th = th_dev[s % nsets]
@@ -482,6 +504,17 @@ def run_ours(args):
         torch.cuda.synchronize()
         return max_over_ranks(time.perf_counter() - t0)
 
+    step_nccl = step_device
+    if exchange is not None:
+        # the two gathers must agree bit for bit before anything is timed
+        step_nccl(0)
+        step_peer(0, copy=True)
+        torch.cuda.synchronize()
+        a = torch.cat([lnl_dev[:half], lnl_dev[world * width:world * width + half]]) \
+            if even else None
+        if a is not None and not torch.equal(a.nan_to_num(), lnl_gath.nan_to_num()):
+            raise SystemExit('bench.py: peer exchange and NCCL gather disagree')
+        step_device = step_peer
     sampler = ClockSampler(local)
     warm = max(args.warmup, 3)
     for s in range(warm):
@@ -516,6 +549,31 @@ def run_ours(args):
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps
     value = walkers / (ms_per_step * 1e-3)
+
+    # ---- the same with the NCCL all_gather (secondary, when the peer exchange is used) --
+    nccl_line = None
+    if exchange is not None:
+        nsteps = max(10, args.steps // 2)
+        for s in range(3):
+            step_nccl(s)
+        engine.profile(True)        # same conditions as the headline loop
+        barrier()
+        nccl_ms = 0.0
+        for s in range(nsteps):
+            flush.fill_(s & 0xFF)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_nccl(s)
+            e1.record(stream)
+            e1.synchronize()
+            nccl_ms += e0.elapsed_time(e1)
+        engine.profile_read()
+        engine.profile(False)
+        nccl_ms = max_over_ranks(nccl_ms) / nsteps
+        nccl_line = {'value': round(walkers / (nccl_ms * 1e-3), 1), 'unit': UNIT,
+                     'ms_per_step': round(nccl_ms, 4),
+                     'gather': 'NCCL all_gather_into_tensor'}
 
     # ---- replicas (weak scaling, no gather) ---------------------------------
     replicas = None
@@ -656,9 +714,13 @@ def run_ours(args):
                        'ndim': ndim, 'frame': list(engine.shape)},
             'l2': 'flushed (256 MiB write) between timed steps',
             'sharding': {'ranks': world, 'rows_per_rank_per_half': hi - lo,
-                         'gather': 'none' if world == 1 else
-                                   'NCCL all_gather_into_tensor of {} doubles per '
-                                   'half-ensemble, inside the timed region'.format(half),
+                         'gather': 'none' if world == 1 else (
+                             'peer memory: every rank stores its lnL into all ranks\' '
+                             'mailboxes (CUDA IPC over NVLink) + one flag per peer, {} doubles '
+                             'per half-ensemble, inside the timed region'.format(half)
+                             if exchange is not None else
+                             'NCCL all_gather_into_tensor of {} doubles per '
+                             'half-ensemble, inside the timed region'.format(half)),
                          'even': bool(even)},
             'e2e': {'value': round(e2e_value, 1), 'unit': UNIT,
                     'h2d_bytes_per_step': (hi - lo) * 2 * ndim * 8,
@@ -681,6 +743,8 @@ def run_ours(args):
         }
         if replicas:
             result['replicas_weak'] = replicas
+        if nccl_line:
+            result['with_nccl_gather'] = nccl_line
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

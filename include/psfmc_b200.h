@@ -176,6 +176,39 @@ int psfmc_lnlike_batch_device(psfmc_engine *engine, int32_t device_slot,
                               const double *theta_dev, int64_t n_batch, int64_t ld,
                               double *lnl_dev, void *cuda_stream);
 
+/* ---- lnL gather over peer memory (one process per GPU, one node) -------------------
+ * The pool.map of psfMC/fitting.py:55-58 for a job launched with one rank per GPU:
+ * every rank evaluates its contiguous rows of a (half-)ensemble and needs ALL lnL
+ * values before it can propose the next one. Each rank owns a mailbox on its GPU
+ * ([2][capacity] doubles + one flag per rank); the ranks map one another's mailboxes
+ * through CUDA IPC (NVLink peer access), and a call publishes this rank's results with
+ * plain stores into EVERY rank's mailbox, signals with one system-scope flag per peer and
+ * waits for the peers' flags -- no NCCL, no host round trip. The fused 128 x 128 kernel
+ * stores its results in the peers' mailboxes itself (the gather is part of the lnL
+ * kernel; one 32-thread kernel behind it exchanges the flags), the other paths publish
+ * theirs from one small kernel. Mailboxes alternate between two halves from call to call, so a fast rank
+ * can never overwrite values a slow rank is still reading.
+ *   psfmc_peer_create   allocates the mailbox (same capacity on every rank) and returns
+ *                       its 64-byte IPC handle for the caller to all-gather
+ *   psfmc_peer_connect  maps the mailboxes of all `world` ranks (handles[world][64])
+ *   psfmc_lnlike_batch_exchange  evaluates this rank's n_rows rows (device-resident
+ *                       theta) on `cuda_stream`, publishes them at position row_offset of
+ *                       the gathered vector, waits for all ranks and copies the n_total
+ *                       gathered values to gathered_dev (device memory; may be null).
+ *                       Asynchronous; every rank must make the same sequence of calls. */
+#define PSFMC_PEER_HANDLE_BYTES 64
+#define PSFMC_PEER_MAX_RANKS 16
+int psfmc_peer_create(psfmc_engine *engine, int64_t capacity, void *handle_out);
+int psfmc_peer_connect(psfmc_engine *engine, int32_t rank, int32_t world,
+                       const void *handles);
+int psfmc_lnlike_batch_exchange(psfmc_engine *engine, const double *theta_dev,
+                                int64_t n_rows, int64_t ld, int64_t row_offset,
+                                int64_t n_total, double *gathered_dev, void *cuda_stream);
+/* Where the gathered vector of the LAST exchange sits in this rank's mailbox (device
+ * memory; valid until the exchange after the next one reuses that half). Saves the copy
+ * to gathered_dev when the consumer can read it in place. */
+int psfmc_peer_gathered(psfmc_engine *engine, double **gathered_dev_out);
+
 /* The blob images of psfMC/models.py:213-226 for B parameter vectors: for every
  * image selected in `which` (ascending bit order), out receives
  * [n_selected][B][height*width] doubles (host memory). */

@@ -8,6 +8,7 @@ missing or fails to load, importing this module's :func:`load` raises.
 import ctypes
 import os
 
+PEER_HANDLE_BYTES = 64
 ABI_VERSION = 1
 
 SKY, POINT, SERSIC = 0, 1, 2
@@ -101,6 +102,8 @@ EXPORTED_SYMBOLS = (
     'psfmc_engine_info', 'psfmc_prior_columns', 'psfmc_prior_sum',
     'psfmc_engine_profile', 'psfmc_engine_profile_read',
     'psfmc_fp32_peak_probe', 'psfmc_last_error', 'psfmc_abi_version',
+    'psfmc_peer_create', 'psfmc_peer_connect', 'psfmc_lnlike_batch_exchange',
+    'psfmc_peer_gathered',
 )
 
 _DEFAULT_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)),
@@ -174,6 +177,17 @@ def load(path=None):
     lib.psfmc_engine_profile_read.restype = ctypes.c_int
     lib.psfmc_engine_profile_read.argtypes = [ctypes.c_void_p, dbl_p,
                                               ctypes.POINTER(ctypes.c_int64)]
+    lib.psfmc_peer_create.restype = ctypes.c_int
+    lib.psfmc_peer_create.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    lib.psfmc_peer_connect.restype = ctypes.c_int
+    lib.psfmc_peer_connect.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_void_p]
+    lib.psfmc_lnlike_batch_exchange.restype = ctypes.c_int
+    lib.psfmc_lnlike_batch_exchange.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+        ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    lib.psfmc_peer_gathered.restype = ctypes.c_int
+    lib.psfmc_peer_gathered.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
     lib.psfmc_fp32_peak_probe.restype = ctypes.c_int
     lib.psfmc_fp32_peak_probe.argtypes = [ctypes.c_int32, dbl_p, dbl_p]
     if lib.psfmc_abi_version() != ABI_VERSION:

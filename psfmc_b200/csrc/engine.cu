@@ -170,6 +170,9 @@ struct EngineBase {
   virtual ~EngineBase() {}
   virtual int profile_read(double *ms, long long *count) = 0;
   virtual int reserve(long long B) = 0;   // size device 0's batch buffers for B walkers
+  // device 0: evaluate B device-resident rows into the engine's own lnL buffer
+  virtual int lnlike_local(const double *theta, long long B, long long ld, void *stream,
+                           double **lnl_out) = 0;
   bool profiling = false;
   // float64 rescue on the device (float32 engines, see lnlike_host_graph): the owner
   // sets scan_wanted and, once it exists, the float64 engine; every host call reports
@@ -197,6 +200,12 @@ struct EngineBase {
   std::atomic<long long> launches{0};   // (device threads add to it concurrently)
   int n_devices = 0;
   int first_ordinal = 0;     // CUDA ordinal of the engine's first device
+  // lnL gather over peer memory: destinations of the NEXT device-0 launch's results (one
+  // per rank, already offset to this rank's first row); honoured by the fused 128 x 128
+  // kernel, which then writes there instead of the local buffer (peer_direct = true)
+  double *peer_dst[PSFMC_PEER_MAX_RANKS] = {};
+  int peer_n = 0;
+  bool peer_direct = false;
   int n_theta = 0;           // 1 + the largest theta index the program reads: every
                              // entry point rejects ld < n_theta (rows would be read past
                              // their end by the prepare kernel)
@@ -423,6 +432,12 @@ struct Engine : EngineBase {
       fb.lnl_const = d.lnl_const;
       fb.n_sms = d.n_sms;
       fb.skip_quads = d.skip_quads;
+      peer_direct = false;
+      if (peer_n > 0 && &d == &devs[0]) {
+        fb.lnl_peer = peer_dst;
+        fb.n_peer = peer_n;
+        peer_direct = true;
+      }
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (profiling && (rc = prof_pair(d, &e0, &e1))) return rc;
       launches += launch_fused_lnlike<T>(plan, buf, fb, prog_h, theta_dev, B, ld, lnl_dev,
@@ -489,6 +504,17 @@ struct Engine : EngineBase {
     DeviceState<T> &d = devs[0];
     CUDA_TRY(cudaSetDevice(d.ordinal));
     return ensure_batch(d, B);
+  }
+
+  int lnlike_local(const double *theta, long long B, long long ld, void *stream,
+                   double **lnl_out) override {
+    DeviceState<T> &d = devs[0];
+    CUDA_TRY(cudaSetDevice(d.ordinal));
+    if (d.lnl.ensure((size_t)(B > 0 ? B : 1)))
+      return fail(PSFMC_ERR_CUDA, "device allocation failed (lnl)");
+    *lnl_out = d.lnl.ptr;
+    if (B <= 0) return 0;
+    return enqueue(d, theta, B, ld, d.lnl.ptr, (cudaStream_t)stream);
   }
 
 #ifndef PSFMC_EMU
@@ -1646,8 +1672,58 @@ struct SavedDesc {
   }
 };
 
+// ------------------------------------------- lnL gather over peer memory --
+struct PeerParams {
+  double *mail[PSFMC_PEER_MAX_RANKS];
+  unsigned long long *flags[PSFMC_PEER_MAX_RANKS];
+  int world, rank;
+};
+
+#ifndef PSFMC_EMU
+// One CTA: copy this rank's n results to position `offset` of every rank's mailbox
+// (coalesced 8-byte stores over NVLink), make them visible system-wide, raise this
+// rank's flag in every mailbox to `epoch` and wait until every rank's flag in the own
+// mailbox has reached it.
+__global__ void __launch_bounds__(512)
+peer_publish_kernel(const double *__restrict__ lnl, long long n, long long offset,
+                    const PeerParams pp, unsigned long long epoch) {
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = lnl[i];
+#pragma unroll
+    for (int p = 0; p < PSFMC_PEER_MAX_RANKS; ++p)
+      if (p < pp.world) pp.mail[p][offset + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < pp.world) {
+    const int p = threadIdx.x;
+    unsigned long long *theirs = pp.flags[p] + pp.rank;          // my flag, in p's mailbox
+    const unsigned long long *mine = pp.flags[pp.rank] + p;      // p's flag, in mine
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long seen;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+      if (seen >= epoch) break;
+      if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a rank died; fail loudly
+    }
+  }
+}
+#endif
+
+struct PeerState {
+  int rank = -1, world = 0;
+  long long capacity = 0;
+  unsigned char *base = nullptr;            // own mailbox allocation
+  void *opened[PSFMC_PEER_MAX_RANKS] = {};  // peers' mailboxes (IPC mappings)
+  PeerParams pp = {};
+  unsigned long long epoch = 0;
+  size_t bytes() const { return (size_t)capacity * 2 * sizeof(double) + 256; }
+};
+
 struct psfmc_engine {
   EngineBase *impl = nullptr;
+  PeerState peer;
   // float64 rescue of the float32 mode (see psfmc_lnlike_batch)
   SavedDesc *saved = nullptr;
   EngineBase *rescue = nullptr;
@@ -1732,6 +1808,15 @@ void psfmc_engine_destroy(psfmc_engine *engine) {
   if (!engine) return;
   int prev = 0;
   cudaGetDevice(&prev);
+#ifndef PSFMC_EMU
+  if (engine->peer.base && engine->impl) {
+    cudaSetDevice(engine->impl->first_ordinal);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < PSFMC_PEER_MAX_RANKS; ++p)
+      if (engine->peer.opened[p]) cudaIpcCloseMemHandle(engine->peer.opened[p]);
+    cudaFree(engine->peer.base);
+  }
+#endif
   delete engine->impl;
   delete engine->rescue;
   delete engine->saved;
@@ -1816,6 +1901,127 @@ int psfmc_lnlike_batch_device(psfmc_engine *engine, int32_t device_slot, const d
     return fail(PSFMC_ERR_INVALID_ARG,
                 "ld is smaller than the number of theta columns the component program reads");
   return engine->impl->lnlike_device(device_slot, theta_dev, n_batch, ld, lnl_dev, cuda_stream);
+}
+
+int psfmc_peer_create(psfmc_engine *engine, int64_t capacity, void *handle_out) {
+  if (!engine || !engine->impl || !handle_out)
+    return fail(PSFMC_ERR_INVALID_ARG, "null argument");
+  if (capacity < 1) return fail(PSFMC_ERR_INVALID_ARG, "capacity must be positive");
+#ifdef PSFMC_EMU
+  return fail(PSFMC_ERR_UNSUPPORTED, "peer exchange needs real devices");
+#else
+  static_assert(sizeof(cudaIpcMemHandle_t) == PSFMC_PEER_HANDLE_BYTES, "IPC handle size");
+  PeerState &ps = engine->peer;
+  if (ps.base) return fail(PSFMC_ERR_INVALID_ARG, "the engine already has a mailbox");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CUDA_TRY(cudaSetDevice(engine->impl->first_ordinal));
+  ps.capacity = capacity;
+  CUDA_TRY(cudaMalloc((void **)&ps.base, ps.bytes()));
+  CUDA_TRY(cudaMemset(ps.base, 0, ps.bytes()));
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t handle;
+  CUDA_TRY(cudaIpcGetMemHandle(&handle, ps.base));
+  memcpy(handle_out, &handle, sizeof(handle));
+  cudaSetDevice(prev);
+  return 0;
+#endif
+}
+
+int psfmc_peer_connect(psfmc_engine *engine, int32_t rank, int32_t world,
+                       const void *handles) {
+  if (!engine || !engine->impl || !handles)
+    return fail(PSFMC_ERR_INVALID_ARG, "null argument");
+  if (world < 1 || world > PSFMC_PEER_MAX_RANKS || rank < 0 || rank >= world)
+    return fail(PSFMC_ERR_INVALID_ARG, "bad rank / world size");
+#ifdef PSFMC_EMU
+  return fail(PSFMC_ERR_UNSUPPORTED, "peer exchange needs real devices");
+#else
+  PeerState &ps = engine->peer;
+  if (!ps.base) return fail(PSFMC_ERR_INVALID_ARG, "call psfmc_peer_create first");
+  if (ps.world) return fail(PSFMC_ERR_INVALID_ARG, "the mailboxes are already connected");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CUDA_TRY(cudaSetDevice(engine->impl->first_ordinal));
+  const size_t data_bytes = (size_t)ps.capacity * 2 * sizeof(double);
+  for (int p = 0; p < world; ++p) {
+    unsigned char *ptr = ps.base;
+    if (p != rank) {
+      cudaIpcMemHandle_t handle;
+      memcpy(&handle, (const unsigned char *)handles + (size_t)p * PSFMC_PEER_HANDLE_BYTES,
+             sizeof(handle));
+      void *mapped = nullptr;
+      CUDA_TRY(cudaIpcOpenMemHandle(&mapped, handle, cudaIpcMemLazyEnablePeerAccess));
+      ps.opened[p] = mapped;
+      ptr = (unsigned char *)mapped;
+    }
+    ps.pp.mail[p] = (double *)ptr;
+    ps.pp.flags[p] = (unsigned long long *)(ptr + data_bytes);
+  }
+  ps.pp.world = world;
+  ps.pp.rank = rank;
+  ps.rank = rank;
+  ps.world = world;
+  cudaSetDevice(prev);
+  return 0;
+#endif
+}
+
+int psfmc_lnlike_batch_exchange(psfmc_engine *engine, const double *theta_dev,
+                                int64_t n_rows, int64_t ld, int64_t row_offset,
+                                int64_t n_total, double *gathered_dev, void *cuda_stream) {
+  if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
+#ifdef PSFMC_EMU
+  return fail(PSFMC_ERR_UNSUPPORTED, "peer exchange needs real devices");
+#else
+  PeerState &ps = engine->peer;
+  if (!ps.world) return fail(PSFMC_ERR_INVALID_ARG, "call psfmc_peer_connect first");
+  if (n_rows < 0 || ld < 0 || row_offset < 0 || n_total < 0 ||
+      row_offset + n_rows > n_total || n_total > ps.capacity)
+    return fail(PSFMC_ERR_INVALID_ARG, "rows do not fit the gathered vector / the mailbox");
+  if (n_rows > 0 && !theta_dev) return fail(PSFMC_ERR_INVALID_ARG, "null theta");
+  if (n_rows > 0 && ld < engine->impl->n_theta)
+    return fail(PSFMC_ERR_INVALID_ARG,
+                "ld is smaller than the number of theta columns the component program reads");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  const unsigned long long epoch = ++ps.epoch;
+  const long long half = (long long)(epoch & 1ull) * ps.capacity;
+  EngineBase *impl = engine->impl;
+  for (int p = 0; p < ps.world; ++p) impl->peer_dst[p] = ps.pp.mail[p] + half + row_offset;
+  impl->peer_n = ps.world;
+  double *local = nullptr;
+  int rc = impl->lnlike_local(theta_dev, n_rows, ld, cuda_stream, &local);
+  impl->peer_n = 0;
+  if (rc) {
+    cudaSetDevice(prev);
+    return rc;
+  }
+  // the fused 128 x 128 kernel has already stored its results in every mailbox (a kernel's
+  // stores are performed system-wide when it completes): only the flags remain. Every
+  // other path publishes its local results here.
+  const bool direct = impl->peer_direct && n_rows > 0;
+  impl->peer_direct = false;
+  peer_publish_kernel<<<1, direct ? 32 : 512, 0, (cudaStream_t)cuda_stream>>>(
+      local, direct ? 0ll : (long long)n_rows, half + row_offset, ps.pp, epoch);
+  ++engine->impl->launches;
+  CUDA_TRY(cudaGetLastError());
+  if (gathered_dev && n_total > 0)
+    CUDA_TRY(cudaMemcpyAsync(gathered_dev, ps.pp.mail[ps.rank] + half,
+                             (size_t)n_total * sizeof(double), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)cuda_stream));
+  cudaSetDevice(prev);
+  return 0;
+#endif
+}
+
+int psfmc_peer_gathered(psfmc_engine *engine, double **gathered_dev_out) {
+  if (!engine || !gathered_dev_out) return fail(PSFMC_ERR_INVALID_ARG, "null argument");
+  PeerState &ps = engine->peer;
+  if (!ps.world || !ps.epoch)
+    return fail(PSFMC_ERR_INVALID_ARG, "no exchange has been made yet");
+  *gathered_dev_out = ps.pp.mail[ps.rank] + (long long)(ps.epoch & 1ull) * ps.capacity;
+  return 0;
 }
 
 int psfmc_render_batch(psfmc_engine *engine, const double *theta, int64_t n_batch, int64_t ld,

@@ -727,6 +727,7 @@ inline int launch_cluster_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
   P.ow = cb.ow;
   P.maskw = nullptr;
   P.lnl_const = 0.0;
+  P.n_peer = 0;
   P.lnl = lnl;
   P.n_batch = n_batch;
   P.ncomp = ncomp;

@@ -70,6 +70,11 @@ struct FusedParams {
   cplx<float> *sub_spec;
   double *partials;
   const unsigned *skip_tab;
+  // lnL gather over peer memory (engine.cu, psfmc_lnlike_batch_exchange): with n_peer > 0
+  // the result of walker b goes to lnl_peer[p][b] for every rank p (the ranks' mailboxes,
+  // mapped through CUDA IPC; plain stores over NVLink) instead of lnl[b]
+  double *lnl_peer[16];
+  int n_peer;
   unsigned long long kind_bits;   // 2 bits per component (a kernel-parameter ARRAY indexed
                                   // by a loop variable is copied to local memory)
 };
@@ -844,7 +849,13 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
             } else {
               double val = -0.5 * (tot + P.lnl_const);
               if (!isfinite(val) || invalid) val = -INFINITY;
-              P.lnl[b] = val;
+              if (P.n_peer > 0) {
+#pragma unroll
+                for (int p = 0; p < 16; ++p)
+                  if (p < P.n_peer) P.lnl_peer[p][b] = val;
+              } else {
+                P.lnl[b] = val;
+              }
             }
             cnt_s = 0;
           }
@@ -918,6 +929,8 @@ struct FusedBuffers {
   const unsigned short *maskw = nullptr;
   double lnl_const = 0.0;
   int n_sms = 148;
+  double *const *lnl_peer = nullptr;   // [n_peer] destinations of the results, or null
+  int n_peer = 0;
   unsigned skip_quads = 0;   // see FusedParams
 };
 
@@ -951,6 +964,8 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
   P.ow = fb.ow;
   P.maskw = fb.maskw;
   P.lnl_const = fb.lnl_const;
+  P.n_peer = fb.n_peer;
+  for (int p = 0; p < 16; ++p) P.lnl_peer[p] = p < fb.n_peer ? fb.lnl_peer[p] : nullptr;
   P.lnl = lnl;
   P.n_batch = n_batch;
   P.ncomp = ncomp;

@@ -121,6 +121,45 @@ def sharded_lnlike_device(engine, theta_dev, n_rows, ld, send, recv, stream, gro
     return bounds, int(bounds[1] - bounds[0])
 
 
+class PeerExchange(object):
+    """Device-resident sharded evaluation whose lnL gather goes over PEER MEMORY instead
+    of NCCL (include/psfmc_b200.h, psfmc_lnlike_batch_exchange): every rank's engine owns
+    a mailbox on its GPU, the ranks map one another's mailboxes through CUDA IPC (NVLink),
+    and a call publishes this rank's lnL with plain stores into every mailbox, raises one
+    flag per peer and waits for the peers' flags -- one small kernel behind the lnL
+    kernels. torch.distributed is used once, to all-gather the 64-byte IPC handles.
+
+    :param engine: this rank's LikelihoodEngine (one device)
+    :param capacity: the largest gathered vector (walkers per call over all ranks)
+    """
+
+    def __init__(self, engine, capacity, group=None):
+        import torch.distributed as dist
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        handle = engine.peer_create(int(capacity))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        engine.peer_connect(self.rank, handles)
+        dist.barrier(group=group)
+        self.capacity = int(capacity)
+
+    def lnlike(self, theta_dev, n_rows, ld, gathered, stream, row_offset=0):
+        """``theta_dev``: float64 CUDA tensor holding the FULL batch (identical on every
+        rank), rows ``row_offset .. row_offset + n_rows`` of it are the batch of this call;
+        ``gathered``: float64 CUDA tensor of at least ``n_rows`` elements that receives
+        the lnL of all rows, or None: the values then stay in this rank's mailbox
+        (``engine.peer_gathered()``). Everything is enqueued on ``stream``; nothing blocks."""
+        bounds = shard_bounds(n_rows, self.world)
+        lo, hi = int(bounds[self.rank]), int(bounds[self.rank + 1])
+        self.engine.lnlike_exchange(
+            theta_dev.data_ptr() + (row_offset + lo) * ld * 8, hi - lo, ld, lo, n_rows,
+            gathered.data_ptr() if gathered is not None else 0, stream=stream.cuda_stream)
+        return bounds
+
+
 class ShardedPool(object):
     """``pool.map`` for emcee where every rank runs the same sampler (same seed)
     and each evaluates only its shard of every (half-)ensemble."""

@@ -188,6 +188,38 @@ class LikelihoodEngine(object):
             self._handle, device_slot, ctypes.c_void_p(theta_ptr), n_batch, ld,
             ctypes.c_void_p(lnl_ptr), ctypes.c_void_p(stream)))
 
+    # -- lnL gather over peer memory (one process per GPU) ----------------------
+    def peer_create(self, capacity):
+        """Allocate this rank's mailbox for gathered vectors of up to ``capacity``
+        values; returns its 64-byte CUDA IPC handle (all-gather them, then
+        :meth:`peer_connect`)."""
+        handle = ctypes.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        _lib.check(self._lib, self._lib.psfmc_peer_create(self._handle, int(capacity), handle))
+        return handle.raw
+
+    def peer_connect(self, rank, handles):
+        """Map the mailboxes of all ranks (``handles``: list of the 64-byte handles in
+        rank order)."""
+        blob = b''.join(bytes(h) for h in handles)
+        _lib.check(self._lib, self._lib.psfmc_peer_connect(
+            self._handle, int(rank), len(handles), ctypes.c_char_p(blob)))
+
+    def lnlike_exchange(self, theta_ptr, n_rows, ld, row_offset, n_total, gathered_ptr,
+                        stream=0):
+        """Evaluate this rank's rows (device-resident, raw address) and gather the lnL of
+        all ranks through the peer mailboxes into ``gathered_ptr`` (device address of
+        ``n_total`` doubles). Asynchronous on ``stream``."""
+        _lib.check(self._lib, self._lib.psfmc_lnlike_batch_exchange(
+            self._handle, ctypes.c_void_p(theta_ptr), n_rows, ld, row_offset, n_total,
+            ctypes.c_void_p(gathered_ptr or None), ctypes.c_void_p(stream)))
+
+    def peer_gathered(self):
+        """Device address of the gathered vector of the last exchange (in this rank's
+        mailbox; valid until the exchange after the next one)."""
+        ptr = ctypes.c_void_p()
+        _lib.check(self._lib, self._lib.psfmc_peer_gathered(self._handle, ctypes.byref(ptr)))
+        return ptr.value
+
     def render(self, thetas, which=('raw_model', 'convolved_model', 'residual',
                                     'composite_ivm', 'point_source_subtracted')):
         """Blob images (psfMC/models.py:222-226) as dict name -> (B, H, W)."""

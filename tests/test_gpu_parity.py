@@ -319,8 +319,23 @@ pool = ShardedPool(model)
 got, _ = pool.map_batch(None, thetas)
 rows = [thetas[i] for i in range(37)]
 listed = np.array([r[0] for r in pool.map(None, rows)])
+# lnL gather over peer memory (CUDA IPC mailboxes): three calls (both mailbox halves),
+# ragged shards, against the same engine evaluating the whole batch alone
+from psfmc_b200.distributed import PeerExchange
+raw = model_from_file('j0005/model_c1.py', 'fp32', devices=[local], fp64_rescue=False)
+xch = PeerExchange(raw.engine, 1001)
+th_dev = torch.from_numpy(thetas).cuda()
+stream = torch.cuda.current_stream()
+peer = []
+for count in (1001, 64, 999):
+    gathered = torch.full((1001,), 7.0, dtype=torch.float64, device='cuda')
+    xch.lnlike(th_dev, count, thetas.shape[1], gathered, stream)
+    stream.synchronize()
+    peer.append(gathered.cpu().numpy()[:count])
+alone = raw.log_likelihood_batch(thetas)
 np.savez(os.path.join({out!r}, 'rank%d.npz' % dist.get_rank()), got=got, listed=listed,
-         want=model.log_posterior_batch(thetas))
+         want=model.log_posterior_batch(thetas), alone=alone, peer0=peer[0],
+         peer1=peer[1], peer2=peer[2])
 dist.barrier()
 dist.destroy_process_group()
 """.format(root=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
@@ -335,6 +350,9 @@ dist.destroy_process_group()
         assert np.array_equal(data['got'], data['want'])
         assert np.array_equal(data['got'], first['got'])
         assert np.array_equal(data['listed'], data['want'][:37])
+        assert np.array_equal(data['peer0'], data['alone'])
+        assert np.array_equal(data['peer1'], data['alone'][:64])
+        assert np.array_equal(data['peer2'], data['alone'][:999])
 
 
 @pytest.mark.parametrize('table', ['1', '0'])
