@@ -665,7 +665,9 @@ def run_ours(args):
             'achieved': round(achieved, 3), 'peak': round(peak_probe, 2),
             'unit': 'TFLOP/s', 'frac': round(achieved / peak_probe, 4),
             'traffic': traffic,
-            'kernel': {1: 'fused_lnlike_kernel', 2: 'cluster256_lnlike_kernel'}.get(
+            'kernel': {1: 'fused_lnlike_kernel', 2: 'cluster256_lnlike_kernel',
+                       3: 'fused_lnlike_kernel<FWD> + tiled_combine_kernel + '
+                          'fused_lnlike_kernel<INV>'}.get(
                 info['path'], 'rows_fwd + cols + rows_inv'),
             'kernel_us_per_launch': round(kernel_us, 2),
             'kernel_launches_timed': int(kernel_launches),
@@ -689,7 +691,8 @@ def run_ours(args):
                     'peak': hbm_peak, 'unit': 'GB/s',
                     'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
                     'bytes_per_eval': info['hbm_bytes_per_eval']},
-            'engine_path': {1: 'fused', 2: 'fused-cluster4'}.get(info['path'], 'staged'),
+            'engine_path': {1: 'fused', 2: 'fused-cluster4', 3: 'tiled-4x4'}.get(
+                info['path'], 'staged'),
         }
         if executed:
             # FP32 operations the kernel really executed (ncu op mix: FADD2/FMUL2 = 2,

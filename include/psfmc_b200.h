@@ -272,7 +272,10 @@ typedef struct psfmc_info {
   int32_t path;             /* 0 = staged row/column passes through L2/HBM,
                                1 = fused single-kernel shared-memory path (128 x 128),
                                2 = fused four-CTA-cluster path, frame split over the
-                                   shared memory of four SMs (256 x 256)            */
+                                   shared memory of four SMs (256 x 256),
+                               3 = tiled path: 512 x 512 as 4 x 4 interleaved 128 x 128
+                                   sub-images through the halves of the fused kernel
+                                   and a combine kernel                              */
   int32_t kernels_per_call; /* kernels launched per lnlike call per device        */
   double flops_per_eval;    /* 10 N log2 N + (30 n_sersic + 16) N     */
   double fft_flops_per_eval;   /* 10 N log2 N                                     */

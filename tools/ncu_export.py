@@ -2,7 +2,7 @@
 """Export the figures bench.py and DESIGN.md quote from an .ncu-rep into
 profiles/<name>.json and profiles/<name>.txt (read here, no GPU needed).
 
-    python tools/ncu_export.py gpurun_out/prof.ncu-rep profiles/r1_fused_ncu_summary
+    python tools/ncu_export.py gpurun_out/prof.ncu-rep profiles/r2_fused_ncu_summary [evals per launch]
 """
 import csv
 import io
@@ -61,6 +61,32 @@ stalls = {h.replace('smsp__pcsamp_warps_issue_stalled_', ''): float(row[i] or 0)
 total = sum(stalls.values()) or 1.0
 summary['stall_pct'] = {k: round(100 * v / total, 1)
                         for k, v in sorted(stalls.items(), key=lambda kv: -kv[1])[:10]}
+# Executed FP32 operations from the dynamic instruction mix (source page): per warp-level
+# instruction 32 lanes x (FADD/FMUL 1, FFMA 2, FADD2/FMUL2 2, FFMA2 4) FLOP. Transcendentals
+# (MUFU) and float64 are not counted; lanes switched off by predicates are (an upper bound
+# that is tight here: the kernels' warps run full).
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'],
+                     stdout=subprocess.PIPE, universal_newlines=True).stdout
+shdr, mix = None, {}
+for srow in csv.reader(io.StringIO(src)):
+    if 'Address' in srow and 'Source' in srow:
+        if shdr is not None:
+            break                      # first kernel of the report only
+        shdr = srow
+        continue
+    if not shdr or len(srow) != len(shdr):
+        continue
+    d = dict(zip(shdr, srow))
+    parts = d['Source'].split()
+    op = (parts[1] if parts[0].startswith('@') else parts[0]).split('.')[0]
+    mix[op] = mix.get(op, 0.0) + float(d['Instructions Executed'] or 0)
+weights = {'FADD': 1, 'FMUL': 1, 'FFMA': 2, 'FADD2': 2, 'FMUL2': 2, 'FFMA2': 4}
+summary['op_mix_warp_instructions'] = {k: v for k, v in sorted(
+    mix.items(), key=lambda kv: -kv[1])[:24]}
+summary['executed_fp32_flop_per_launch'] = 32.0 * sum(
+    mix.get(op, 0.0) * w for op, w in weights.items())
+if len(sys.argv) > 3:
+    summary['evals_per_launch'] = int(sys.argv[3])
 with open(out + '.json', 'w') as fobj:
     json.dump(summary, fobj, indent=1)
 with open(out + '.txt', 'w') as fobj:

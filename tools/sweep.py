@@ -71,7 +71,7 @@ def measure(workload, walkers, seconds=1.0):
     return {'workload': workload, 'frame': list(engine.shape), 'walkers': walkers,
             'batch_per_launch': half, 'steps': steps,
             'device_evals_per_s': round(dev_rate, 1), 'e2e_evals_per_s': round(host_rate, 1),
-            'engine_path': {1: 'fused', 2: 'fused-cluster4'}.get(info['path'], 'staged'),
+            'engine_path': {1: 'fused', 2: 'fused-cluster4', 3: 'tiled-4x4'}.get(info['path'], 'staged'),
             'fp64_rescued_walkers': int(info['rescued_total'])}
 
 

@@ -41,7 +41,7 @@ def main():
                     'rescued_in_fp64': int(m32.engine.info()['rescued_total']),
                     'raw_fp32_nonfinite_where_fp64_finite':
                         int(np.sum(finite & ~np.isfinite(raw))),
-                    'engine_path': {1: 'fused', 2: 'fused-cluster4'}.get(
+                    'engine_path': {1: 'fused', 2: 'fused-cluster4', 3: 'tiled-4x4'}.get(
                         m32.engine.info()['path'], 'staged'),
                     'max_abs_dlnl': float(err.max()), 'median_abs_dlnl': float(np.median(err)),
                     'max_rel_dlnl': float((err / np.abs(l64[finite])).max()),
@@ -49,8 +49,9 @@ def main():
                     'max_err_over_bound': float(ratio.max()),
                     'median_err_over_bound': float(np.median(ratio))})
         print(json.dumps(out[-1]), file=sys.stderr)
-    print(json.dumps({'audit': out, 'bound': '|dlnL| <= 0.01 + 128 * 2^-24 * sum_good |resid| '
-                      '* ivm * |model|'}, indent=1))
+    print(json.dumps({'audit': out, 'bound': '|dlnL| <= 0.01 + FP32_ULPS * 2^-24 * sum_good |resid| '
+                      '* ivm * |model| (FP32_ULPS of tests/conftest.py; err_over_bound is '
+                      'relative to it)', 'fp32_ulps': __import__('conftest').FP32_ULPS}, indent=1))
 
 
 if __name__ == '__main__':
