@@ -129,16 +129,18 @@ __device__ __forceinline__ void dft16(cplx<float> *v) {
 // Shared-memory tile access by BYTE offset (32-bit address arithmetic). Exchange layout
 // of a row between its radix-16 and radix-8 sides: element (k1, n2) of row y sits at
 // complex position
-//     10 k1 + n2
+//     18 (k1 >> 1) + 8 (k1 & 1) + n2
 // inside the row's own 1344 bytes (an odd multiple of 64: consecutive rows are half a
 // bank cycle apart). Radix-16 side (one k1 per instruction, lanes over n2, two rows per
 // half-warp): 2 x 8 consecutive positions on opposite bank halves = one conflict-free
-// 128-byte wavefront. Radix-8 side: a thread's eight n2 values of one k1
-// are 64 contiguous, 16-byte aligned bytes = four 128-bit accesses, and the eight
-// threads of a row (k1 = 0..7 or 8..15, pitch 80 bytes) cover all eight 16-byte bank
-// groups (5 k1 mod 8 is a permutation). Every address is a per-thread base plus a
-// compile-time immediate: no address arithmetic per access (the XOR-swizzled layout of
-// round 1 cost one LOP3 per access and eight 64-bit accesses where four 128-bit ones do).
+// 128-byte wavefront. Radix-8 side: thread l owns k1 = 2 l and 2 l + 1 -- with the
+// mirror-pair product no thread needs a frequency's Hermitian partner any more, so the
+// pairing is free -- i.e. 128 contiguous, 16-byte aligned bytes = eight 128-bit accesses,
+// and the eight threads of a row (pitch 144 bytes) cover all eight 16-byte bank groups
+// (9 l mod 8 is a permutation). Its results, the row frequencies kx = 2 l + 16 k2 and
+// kx + 1, are neighbours in the column layout too: 128-bit accesses there as well. Every
+// address is a per-thread base plus a compile-time immediate (the XOR-swizzled layout of
+// round 1 cost one LOP3 per access and twice the number of accesses).
 #ifdef PSFMC_EMU
 typedef uintptr_t smem_addr_t;
 #else
@@ -161,6 +163,24 @@ __device__ __forceinline__ void sts64(smem_addr_t addr, cplx<float> v) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 #endif
 }
+// Global accesses that are used exactly once (the sub-spectra of the tiled path):
+// streaming cache hints keep them from evicting the L1 / L2 lines the kernel reuses.
+__device__ __forceinline__ void stream_store(cplx<float> *p, cplx<float> v) {
+#if defined(PSFMC_EMU) || defined(PSFMC_NO_STREAM_HINTS)
+  *p = v;
+#else
+  __stcs(reinterpret_cast<float2 *>(p), make_float2(v.x, v.y));
+#endif
+}
+__device__ __forceinline__ cplx<float> stream_load(const cplx<float> *p) {
+#if defined(PSFMC_EMU) || defined(PSFMC_NO_STREAM_HINTS)
+  return *p;
+#else
+  const float2 v = __ldcs(reinterpret_cast<const float2 *>(p));
+  return mk<float>(v.x, v.y);
+#endif
+}
+
 struct cplx2f {   // two adjacent complex64 values (one 128-bit shared-memory access)
   cplx<float> lo, hi;
 };
@@ -314,10 +334,9 @@ __device__ __forceinline__ void mirror_self(cplx<float> &z, float4 s) {
 // Per-thread constants of the row passes (4 rows per warp, 8 threads per row).
 struct RowRole {
   int w, rr, l;
-  bool l0;
-  unsigned t16;     // radix-16 side of the exchange layout: 8 l, k1 at + 80 k1
-  unsigned qa, qb;  // radix-8 side, for k1 = kA / kB: 80 k, n2 at + 8 n2
-  unsigned fa, fb;  // column layout: 8 k; column k + 16 k2 at + 128 k2
+  unsigned t16;     // radix-16 side of the exchange layout: 8 l, k1 at + 144 (k1 >> 1) + 64 (k1 & 1)
+  unsigned qa;      // radix-8 side: 144 l; k1 = 2 l at + 8 n2, k1 = 2 l + 1 at + 64 + 8 n2
+  unsigned fa;      // column layout: 16 l; columns 2 l + 16 k2 and + 1 at + 128 k2
 };
 
 // render + forward row transform of row batch `it` of walker b
@@ -340,10 +359,7 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
     __syncwarp();
     const cplx<float> zero = mk<float>(0.0f, 0.0f);
 #pragma unroll
-    for (int k2 = 0; k2 < 8; ++k2) {
-      sts64(rb + R.fa + 8 * 16 * k2, zero);
-      sts64(rb + R.fb + 8 * 16 * k2, zero);
-    }
+    for (int k2 = 0; k2 < 8; ++k2) sts128(rb + R.fa + 8 * 16 * k2, zero, zero);
     return;
   }
   {
@@ -373,15 +389,15 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
     __syncwarp();   // every lane is done reading this row (previous walker)
     const smem_addr_t rt = rb + R.t16;
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) sts64(rt + 80 * k1, v[k1]);
+    for (int k1 = 0; k1 < 16; ++k1) sts64(rt + 144 * (k1 >> 1) + 64 * (k1 & 1), v[k1]);
   }
   __syncwarp();
   cplx<float> a[8], bb[8];
   {
-    const smem_addr_t ra = rb + R.qa, rq = rb + R.qb;
+    const smem_addr_t ra = rb + R.qa;
 #pragma unroll
     for (int n2 = 0; n2 < 8; n2 += 2) {
-      const cplx2f pa = lds128(ra + 8 * n2), pb = lds128(rq + 8 * n2);
+      const cplx2f pa = lds128(ra + 8 * n2), pb = lds128(ra + 64 + 8 * n2);
       a[n2] = pa.lo;
       a[n2 + 1] = pa.hi;
       bb[n2] = pb.lo;
@@ -389,15 +405,12 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
     }
   }
   __syncwarp();
-  dft8<float, false>(a);    // a[k2]  = Z[kA + 16 k2]
-  dft8<float, false>(bb);   // bb[k2] = Z[kB + 16 k2]
+  dft8<float, false>(a);    // a[k2]  = Z[2 l + 16 k2]
+  dft8<float, false>(bb);   // bb[k2] = Z[2 l + 1 + 16 k2]
   // the row spectrum of the packed row goes to the columns as it is (column kx at 8 kx);
   // the two images are taken apart only implicitly, by mirror_pair
 #pragma unroll
-  for (int k2 = 0; k2 < 8; ++k2) {
-    sts64(rb + R.fa + 8 * 16 * k2, a[k2]);
-    sts64(rb + R.fb + 8 * 16 * k2, bb[k2]);
-  }
+  for (int k2 = 0; k2 < 8; ++k2) sts128(rb + R.fa + 8 * 16 * k2, a[k2], bb[k2]);
 }
 
 // inverse row transform + chi-square terms of row batch `it`;
@@ -425,21 +438,22 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
   }
-  cplx<float> a[8], bb[8];   // a[k2] = Y[kA + 16 k2], bb[k2] = Y[kB + 16 k2]
+  cplx<float> a[8], bb[8];   // a[k2] = Y[2 l + 16 k2], bb[k2] = Y[2 l + 1 + 16 k2]
 #pragma unroll
   for (int k2 = 0; k2 < 8; ++k2) {
-    a[k2] = lds64(rb + R.fa + 8 * 16 * k2);
-    bb[k2] = lds64(rb + R.fb + 8 * 16 * k2);
+    const cplx2f pr = lds128(rb + R.fa + 8 * 16 * k2);
+    a[k2] = pr.lo;
+    bb[k2] = pr.hi;
   }
   __syncwarp();
   dft8<float, true>(a);     // a[n2]
   dft8<float, true>(bb);
   {
-    const smem_addr_t ra = rb + R.qa, rq = rb + R.qb;
+    const smem_addr_t ra = rb + R.qa;
 #pragma unroll
     for (int n2 = 0; n2 < 8; n2 += 2) {
       sts128(ra + 8 * n2, a[n2], a[n2 + 1]);
-      sts128(rq + 8 * n2, bb[n2], bb[n2 + 1]);
+      sts128(ra + 64 + 8 * n2, bb[n2], bb[n2 + 1]);
     }
   }
   __syncwarp();
@@ -447,7 +461,7 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   {
     const smem_addr_t rt = rb + R.t16;
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(rt + 80 * k1);
+    for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(rt + 144 * (k1 >> 1) + 64 * (k1 & 1));
   }
 #pragma unroll
   for (int k1 = 0; k1 < 16; k1 += 2) {
@@ -535,15 +549,10 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   R.w = w;
   R.rr = lane >> 3;
   R.l = lane & 7;
-  R.l0 = (R.l == 0);
   {
-    const unsigned s = R.rr & 1;
-    const unsigned kA = R.l, kB = R.l0 ? 8 : 16 - R.l;
     R.t16 = 8u * R.l;
-    R.qa = 80u * kA;
-    R.qb = 80u * kB;
-    R.fa = 8u * kA;
-    R.fb = 8u * kB;
+    R.qa = 144u * R.l;
+    R.fa = 16u * R.l;
   }
   // twiddles of the row passes W128^(l*k1) in shared memory as [l][k1] with a pitch of
   // 144 bytes: a thread takes its sixteen values with eight 128-bit loads (twl + 16 i =
@@ -676,8 +685,8 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
         const int cb = slot0 ? 64 * round : 128 - slot;
 #pragma unroll
         for (int k2 = 0; k2 < 8; ++k2) {
-          ga[round][k2] = gsub[(ka + 16 * k2) * N + ca];
-          gb[round][k2] = gsub[(kb + 16 * k2) * N + cb];
+          ga[round][k2] = stream_load(gsub + (ka + 16 * k2) * N + ca);
+          gb[round][k2] = stream_load(gsub + (kb + 16 * k2) * N + cb);
         }
         int ka1 = kb, kb1 = ka;
         if (m8 == 0) ka1 = kb1 = 8;
@@ -709,8 +718,8 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
         // forward half: the column spectrum leaves for the 4 x 4 combine kernel
 #pragma unroll
         for (int k2 = 0; k2 < 8; ++k2) {
-          gsub[(kA + 16 * k2) * N + ca] = a[k2];
-          gsub[(kB + 16 * k2) * N + cb] = bb[k2];
+          stream_store(gsub + (kA + 16 * k2) * N + ca, a[k2]);
+          stream_store(gsub + (kB + 16 * k2) * N + cb, bb[k2]);
         }
       } else if (MODE == PSFMC_MODE_INV) {
         // inverse half: ... and comes back multiplied by the PSF spectra
