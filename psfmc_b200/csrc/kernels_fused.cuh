@@ -33,6 +33,7 @@
 // (convolution / likelihood); this file only re-schedules it.
 #pragma once
 #include "pipeline.cuh"
+#include "tma.cuh"
 #include "twiddle128.cuh"
 
 namespace psfmc {
@@ -178,6 +179,55 @@ __device__ __forceinline__ cplx<float> stream_load(const cplx<float> *p) {
 #else
   const float2 v = __ldcs(reinterpret_cast<const float2 *>(p));
   return mk<float>(v.x, v.y);
+#endif
+}
+
+// Tiled path: the sub-spectrum of a job travels between global memory and the tile ROW BY
+// ROW (row ky: 128 complex64 values = 1 KB, contiguous on both sides) with bulk
+// asynchronous copies (TMA, cp.async.bulk): no registers, no LSU instructions, and --
+// the point -- asynchronous, so that the inverse half fetches the NEXT job's rows while it
+// still works on this job's epilogue, and the forward half's results drain while the next
+// job is being rendered. The emulator build copies synchronously at the same places.
+#define PSFMC_SUBROW_BYTES (PSFMC_FUSED_N * 8)
+// one lane: global row -> tile row; completion is counted on `bar` (device builds)
+__device__ __forceinline__ void tile_row_fetch(unsigned char *tile_row,
+                                               const cplx<float> *grow,
+                                               unsigned long long *bar) {
+#ifdef PSFMC_EMU
+  (void)bar;
+  cplx<float> *dst = reinterpret_cast<cplx<float> *>(tile_row);
+  for (int k = 0; k < PSFMC_FUSED_N; ++k) dst[k] = grow[k];
+#else
+  bulk_load(tile_row, grow, PSFMC_SUBROW_BYTES, bar);
+#endif
+}
+// one lane: tile row -> global row (joins the lane's current bulk group, device builds)
+__device__ __forceinline__ void tile_row_store(cplx<float> *grow, const unsigned char *tile_row) {
+#ifdef PSFMC_EMU
+  const cplx<float> *src = reinterpret_cast<const cplx<float> *>(tile_row);
+  for (int k = 0; k < PSFMC_FUSED_N; ++k) grow[k] = src[k];
+#else
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(grow),
+               "r"(smem_u32(tile_row)), "r"((unsigned)PSFMC_SUBROW_BYTES)
+               : "memory");
+#endif
+}
+__device__ __forceinline__ void tile_store_commit() {
+#ifndef PSFMC_EMU
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+// the lane's bulk stores have READ their shared-memory source: the tile may be rewritten
+__device__ __forceinline__ void tile_store_wait_read() {
+#ifndef PSFMC_EMU
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+// generic-proxy accesses of shared memory before this point are ordered before later
+// asynchronous-proxy (TMA) accesses of the same addresses
+__device__ __forceinline__ void async_proxy_fence() {
+#ifndef PSFMC_EMU
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
 }
 
@@ -350,7 +400,11 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
                                                    const RowRole &R, smem_addr_t twl,
                                                    const float *rc0, const double *der0,
                                                    int it, float wsc,
-                                                   const FoldParams *F = nullptr, int sub = 0) {
+                                                   const FoldParams *F = nullptr, int sub = 0,
+                                                   bool drain = false) {
+  // drain (tiled forward half, first row batch of a job): the previous job's results are
+  // still leaving the tile through bulk stores issued by threads 0..127; the tile may
+  // only be written once those have read it (see the kernel)
   const int y = it * 64 + R.w * 4 + R.rr;
   const smem_addr_t rb = tile + (unsigned)y * PSFMC_FUSED_ROWB;
   if (PADDED && y - R.rr >= F->Hr) {
@@ -385,6 +439,10 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
       const cplx2f w = lds128(twl + 16 * (k1 >> 1));
       if (k1 > 0) v[k1] = v[k1] * w.lo;
       v[k1 + 1] = v[k1 + 1] * w.hi;
+    }
+    if (TILED && drain) {
+      if (threadIdx.x < PSFMC_FUSED_N) tile_store_wait_read();
+      group_barrier(6, PSFMC_FUSED_THREADS);
     }
     __syncwarp();   // every lane is done reading this row (previous walker)
     const smem_addr_t rt = rb + R.t16;
@@ -421,11 +479,29 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
                                                      const RowRole &R, smem_addr_t twl,
                                                      int it, float unscale,
                                                      const FoldParams *F = nullptr, int sub = 0,
-                                                     unsigned skip_quads = 0) {
+                                                     unsigned skip_quads = 0,
+                                                     const cplx<float> *gnext = nullptr,
+                                                     unsigned long long *bar = nullptr,
+                                                     unsigned char *tile_ptr = nullptr) {
   const int y = it * 64 + R.w * 4 + R.rr;
+  // gnext (tiled inverse half): once the warp has taken its four rows out of the tile,
+  // lanes 0..3 fetch the same rows of the NEXT job's sub-spectrum into their place
+  auto fetch_next = [&]() {
+    if (!gnext) return;
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    if (lane < 4) {
+      async_proxy_fence();
+      const int row = y - R.rr + lane;
+      tile_row_fetch(tile_ptr + (size_t)row * PSFMC_FUSED_ROWB, gnext + row * PSFMC_FUSED_N, bar);
+    }
+  };
   if (PADDED && y - R.rr >= F->Hr) return 0.0;   // the warp's four rows are padding
   // ... or hold no unmasked pixel: nothing of them enters the sum (models.py:233-236)
-  if ((skip_quads >> (it * 16 + R.w)) & 1u) return 0.0;
+  if ((skip_quads >> (it * 16 + R.w)) & 1u) {
+    fetch_next();
+    return 0.0;
+  }
   const smem_addr_t rb = tile + (unsigned)y * PSFMC_FUSED_ROWB;
   // observation + signed variance of this thread's 16 pixels: issued first, used
   // last (L2 latency hidden behind the whole inverse transform)
@@ -463,6 +539,7 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) v[k1] = lds64(rt + 144 * (k1 >> 1) + 64 * (k1 & 1));
   }
+  fetch_next();   // (the rows' last access to the tile was just made)
 #pragma unroll
   for (int k1 = 0; k1 < 16; k1 += 2) {
     const cplx2f w = lds128(twl + 16 * (k1 >> 1));
@@ -580,6 +657,25 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   };
   stage_params(blockIdx.x);
   __syncthreads();
+  // tiled inverse half: the sub-spectrum of a job arrives in the tile by bulk copies whose
+  // bytes are counted on this barrier (one phase per job)
+  __shared__ __align__(8) unsigned long long tile_bar;
+  unsigned tile_phase = 0;
+  if (MODE == PSFMC_MODE_INV) {
+#ifndef PSFMC_EMU
+    if (tid == 0) mbar_init(&tile_bar, 1);
+    __syncthreads();
+    if (tid == 0 && (long long)blockIdx.x < P.n_batch)
+      mbar_expect_tx(&tile_bar, N * PSFMC_SUBROW_BYTES);
+    __syncthreads();
+#endif
+    // the first job's rows: warp w fetches the rows it will transform (4 w .. and 64 + 4 w ..)
+    if ((long long)blockIdx.x < P.n_batch && lane < 8) {
+      const int row = (lane >> 2) * 64 + 4 * w + (lane & 3);
+      tile_row_fetch(smem_raw + (size_t)row * ROWB,
+                     P.sub_spec + ((size_t)blockIdx.x * N + row) * N, &tile_bar);
+    }
+  }
 
   // Column-pass roles. The four warps of a column group (which meet at the named
   // barriers) sit on four DIFFERENT schedulers (warp w runs on scheduler w & 3), so
@@ -637,6 +733,16 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
     __syncthreads();
     // every warp is past the forward rows of walker b: stage walker b + grid
     stage_params(b + gridDim.x);
+    if (MODE == PSFMC_MODE_INV) {
+#ifndef PSFMC_EMU
+      // this job's sub-spectrum has landed in the tile; the next job's bytes are expected
+      // on the barrier's next phase (its fetches are issued by the row passes below)
+      mbar_wait(&tile_bar, tile_phase);
+      tile_phase ^= 1u;
+      if (tid == 0 && b + (long long)gridDim.x < P.n_batch)
+        mbar_expect_tx(&tile_bar, N * PSFMC_SUBROW_BYTES);
+#endif
+    }
 
     // ------------------------------------------------- columns: radix-16 --
     // both residues n2 = m and m + 4 of this thread in flight at once (ILP)
@@ -674,8 +780,10 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
     if (MODE != PSFMC_MODE_INV) group_barrier(1 + cg, 128);
     // this job's spectrum tile in global memory (tiled frames)
     cplx<float> *gsub = TILED ? P.sub_spec + (size_t)b * N * N : nullptr;
-    // inverse half: the values of BOTH rounds are requested up front (their L2 / HBM
-    // latency is the only thing this phase waits for)
+    // Tiled halves keep the 2 x 16 values of both rounds in registers: the inverse half
+    // finds its input in the tile in FREQUENCY order (row ky, fetched by TMA) and writes
+    // rows 8 k1 + n2 -- the forward half the other way round -- so within a column group
+    // every read has to precede every write (one more group barrier).
     cplx<float> ga[2][8], gb[2][8];
     if (MODE == PSFMC_MODE_INV) {
       int ka = kA, kb = kB;
@@ -685,8 +793,8 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
         const int cb = slot0 ? 64 * round : 128 - slot;
 #pragma unroll
         for (int k2 = 0; k2 < 8; ++k2) {
-          ga[round][k2] = stream_load(gsub + (ka + 16 * k2) * N + ca);
-          gb[round][k2] = stream_load(gsub + (kb + 16 * k2) * N + cb);
+          ga[round][k2] = lds64(tile + (unsigned)(ka + 16 * k2) * ROWB + 8u * ca);
+          gb[round][k2] = lds64(tile + (unsigned)(kb + 16 * k2) * ROWB + 8u * cb);
         }
         int ka1 = kb, kb1 = ka;
         if (m8 == 0) ka1 = kb1 = 8;
@@ -694,6 +802,7 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
         ka = ka1;
         kb = kb1;
       }
+      group_barrier(1 + cg, 128);
     }
 
     // ---------- columns: radix-8, mirror-pair spectrum product, inverse radix-8 --
@@ -715,11 +824,11 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
         dft8<float, false>(bb);   // bb[k2] = U[kB + 16 k2][cb]
       }
       if (MODE == PSFMC_MODE_FWD) {
-        // forward half: the column spectrum leaves for the 4 x 4 combine kernel
+        // forward half: the column spectrum is kept until the group has read all its input
 #pragma unroll
         for (int k2 = 0; k2 < 8; ++k2) {
-          stream_store(gsub + (kA + 16 * k2) * N + ca, a[k2]);
-          stream_store(gsub + (kB + 16 * k2) * N + cb, bb[k2]);
+          ga[round][k2] = a[k2];
+          gb[round][k2] = bb[k2];
         }
       } else if (MODE == PSFMC_MODE_INV) {
         // inverse half: ... and comes back multiplied by the PSF spectra
@@ -768,6 +877,28 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
       kB = kB1;
     }
     if (MODE != PSFMC_MODE_FWD) group_barrier(1 + cg, 128);
+    if (MODE == PSFMC_MODE_FWD) {
+      // forward half: the column spectrum goes back into the tile in frequency order (row
+      // ky, column kx) and leaves for the 4 x 4 combine kernel row by row (bulk stores)
+      group_barrier(1 + cg, 128);
+      int ka = m8, kb = zpat ? 8 : (16 - m8) & 15;
+#pragma unroll
+      for (int round = 0; round < 2; ++round) {
+        const int ca = slot0 ? 64 * round : slot;
+        const int cb = slot0 ? 64 * round : 128 - slot;
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+          sts64(tile + (unsigned)(ka + 16 * k2) * ROWB + 8u * ca, ga[round][k2]);
+          sts64(tile + (unsigned)(kb + 16 * k2) * ROWB + 8u * cb, gb[round][k2]);
+        }
+        int ka1 = kb, kb1 = ka;
+        if (m8 == 0) ka1 = kb1 = 8;
+        if (zpat) ka1 = 0;
+        ka = ka1;
+        kb = kb1;
+      }
+      async_proxy_fence();
+    }
 
     // ----------------------------------------- columns: inverse radix-16 --
     if (MODE != PSFMC_MODE_FWD) {
@@ -790,6 +921,10 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
       for (int j = 0; j < 16; ++j) sts64(cb1 + 8 * j * ROWB, v1[j]);
     }
     __syncthreads();
+    if (MODE == PSFMC_MODE_FWD && tid < N) {
+      tile_row_store(gsub + (size_t)tid * N, smem_raw + (size_t)tid * ROWB);
+      tile_store_commit();
+    }
     if (PADDED) {
       // fold the linear convolution back modulo Hr (see Frame): row p receives rows
       // p + Hr (p <= fy_hi) and 128 + p - Hr (p >= fy_lo); the sources lie at or beyond
@@ -829,10 +964,13 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
         if (cur && MODE != PSFMC_MODE_FWD)
           acc += fused_rows_inverse<true, PADDED>(
               P, tile, R, twl, it, unscale, &F, sub,
-              MODE == PSFMC_MODE_INV ? __ldg(P.skip_tab + sub) : P.skip_quads);
+              MODE == PSFMC_MODE_INV ? __ldg(P.skip_tab + sub) : P.skip_quads,
+              (MODE == PSFMC_MODE_INV && has_next) ? P.sub_spec + (size_t)bn * N * N : nullptr,
+              &tile_bar, smem_raw);
       } else if (has_next && MODE != PSFMC_MODE_INV) {
         fused_rows_forward<true, PADDED, TILED>(P, tile, R, twl, rc_s, der_s, it, wsc_next, &F,
-                                                TILED ? (int)(bn & 15) : 0);
+                                                TILED ? (int)(bn & 15) : 0,
+                                                MODE == PSFMC_MODE_FWD && cur && it == 0);
       }
       if (cur && MODE != PSFMC_MODE_FWD &&
           ((interleave && step == 2) || (!interleave && step == 1))) {
@@ -872,6 +1010,10 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
       }
     }
   }
+#ifndef PSFMC_EMU
+  if (MODE == PSFMC_MODE_FWD && tid < N)
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last job's rows
+#endif
 }
 
 // -------------------------------------------------------------- host side --
