@@ -119,6 +119,8 @@ struct DeviceState {
   DevBuf<float> rconst;
   float4 *fspec = nullptr, *fspecx = nullptr;   // fused kernel (128 x 128)
   float2 *fow = nullptr;
+  float2 *fkpv = nullptr;             // fused 128 kernel: real-space (PSF, v * variance) kernels
+  DevBuf<int> hot;                    // [B][ncomp] hot-pixel flags of the batch
   unsigned short *fmaskw = nullptr;   // fused 128 kernel: good-pixel bits per row-pass thread
   double lnl_const = 0.0;             // ln(2 pi) * number of good pixels
   float4 *cspec = nullptr, *cspecx = nullptr;   // cluster kernel (256 x 256)
@@ -179,6 +181,10 @@ struct EngineBase {
   // whether the device looked for non-finite results, how many it found and whether it
   // already repeated them
   bool scan_wanted = false;
+  // host calls of an engine whose owner repeats non-finite results in float64: the fused
+  // 128 x 128 kernel then reports them as NaN and keeps -inf for walkers that are dead by
+  // construction (FusedParams::nan_marks); marks_active = the last host call did so
+  bool want_marks = false, mark_next = false, marks_active = false;
   EngineBase *rescue_peer = nullptr;
   bool scan_valid = false, scan_rescued = false;
   int scan_flagged = 0;
@@ -223,7 +229,7 @@ struct EngineBase {
 __global__ void rescue_scan_kernel(const double *__restrict__ lnl, long long n_batch,
                                    double *__restrict__ out_host, int *__restrict__ flags,
                                    int *__restrict__ flags_host,
-                                   cudaGraphConditionalHandle handle, int armed) {
+                                   cudaGraphConditionalHandle handle, int armed, int marks) {
   __shared__ int count;
   __shared__ int rows[PSFMC_RESCUE_MAX];
   if (threadIdx.x == 0) count = 0;
@@ -231,7 +237,8 @@ __global__ void rescue_scan_kernel(const double *__restrict__ lnl, long long n_b
   for (long long b = threadIdx.x; b < n_batch; b += blockDim.x) {
     const double v = lnl[b];
     out_host[b] = v;
-    if (!(v > -INFINITY)) {
+    // (marks: NaN = worth repeating, -inf = final; otherwise every non-finite result)
+    if (marks ? (v != v) : !(v > -INFINITY)) {
       const int k = atomicAdd(&count, 1);
       if (k < PSFMC_RESCUE_MAX) rows[k] = (int)b;
     }
@@ -305,6 +312,8 @@ struct Engine : EngineBase {
       cudaFree(d.fspecx);
       cudaFree(d.fow);
       cudaFree(d.fmaskw);
+      cudaFree(d.fkpv);
+      d.hot.release();
       cudaFree(d.cspec);
       cudaFree(d.cspecx);
       cudaFree(d.tspec);
@@ -396,6 +405,8 @@ struct Engine : EngineBase {
     if (path >= 1 && !for_images) {
       if (d.rconst.ensure(nb * ncomp * PSFMC_RC_STRIDE))
         return fail(PSFMC_ERR_CUDA, "device allocation failed (render constants)");
+      if (path == 1 && d.fkpv && d.hot.ensure(nb * ncomp))
+        return fail(PSFMC_ERR_CUDA, "device allocation failed (hot-pixel flags)");
 #ifndef PSFMC_NO_FUSED
       if (path == 3) {
         const long long chunk = B < d.tchunk ? B : d.tchunk;
@@ -432,6 +443,9 @@ struct Engine : EngineBase {
       fb.lnl_const = d.lnl_const;
       fb.n_sms = d.n_sms;
       fb.skip_quads = d.skip_quads;
+      fb.hot = d.fkpv ? d.hot.ptr : nullptr;
+      fb.kpv = d.fkpv;
+      fb.nan_marks = mark_next;
       peer_direct = false;
       if (peer_n > 0 && &d == &devs[0]) {
         fb.lnl_peer = peer_dst;
@@ -556,7 +570,8 @@ struct Engine : EngineBase {
            cudaSuccess;
     if (ok) {
       rescue_scan_kernel<<<1, 1024, 0, d.stream>>>(d.lnl.ptr, B, dst, d.r_flags.ptr,
-                                                   d.r_flags_host.ptr, handle, body ? 1 : 0);
+                                                   d.r_flags_host.ptr, handle, body ? 1 : 0,
+                                                   marks_active ? 1 : 0);
       ++launches;
     }
     if (ok && body) {
@@ -808,7 +823,16 @@ struct Engine : EngineBase {
     pend_graph = false;
     pend_B = B;
     pend_out = out;
+    marks_active = false;
     if (B <= 0) return 0;
+#ifndef PSFMC_NO_FUSED
+    marks_active = want_marks && path == 1 && devs[0].fkpv != nullptr && !plan.fr.padded;
+#endif
+    struct MarkScope {   // the kernels of THIS host call mark; device-pointer calls never do
+      bool &flag;
+      MarkScope(bool &f, bool v) : flag(f) { flag = v; }
+      ~MarkScope() { flag = false; }
+    } mark_scope(mark_next, marks_active);
 #ifdef PSFMC_EMU
     const bool zero_copy_out = true;    // "device" memory is host memory
 #else
@@ -1489,6 +1513,30 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       if ((rc = upload(&ds.fspec, fspec)) || (rc = upload(&ds.fspecx, fspecx)) ||
           (rc = upload(&ds.fow, ow)) || (rc = upload(&ds.fmaskw, maskw)))
         break;
+      // Real-space kernels of the reference's convolution (psfMC/utils.py:9-32): conv[x] =
+      // sum_u img[u] * pad[(x - u + N/2) mod N] with the PSF stamp padded at offset
+      // (N - psf_n) // 2, i.e. kernel[d] = pad[(d + N/2) mod N]. Used for the pixels the
+      // float32 kernel takes out of the transform (prepare_kernel, `hot`); unpadded
+      // frames only. PSFMC_NO_HOT_PIXEL=1 switches the feature off.
+      const char *nohot = getenv("PSFMC_NO_HOT_PIXEL");
+      if (!eng->plan.fr.padded && !(nohot && nohot[0] == '1')) {
+        std::vector<float2> kpv((size_t)d->n_psf * N * N);
+        const int ph = d->psf_height, pw = d->psf_width;
+        const int oy = ((int)N - ph) / 2, ox = ((int)N - pw) / 2;
+        for (int k = 0; k < d->n_psf; ++k)
+          for (size_t dy = 0; dy < N; ++dy)
+            for (size_t dx = 0; dx < N; ++dx) {
+              const int yy = (int)((dy + N / 2) % N) - oy, xx = (int)((dx + N / 2) % N) - ox;
+              float2 v = {0.0f, 0.0f};
+              if (yy >= 0 && yy < ph && xx >= 0 && xx < pw) {
+                const size_t e = ((size_t)k * ph + yy) * pw + xx;
+                v.x = (float)d->psf[e];
+                v.y = (float)(d->psf_var[e] * vs[k]);
+              }
+              kpv[((size_t)k * N + dy) * N + dx] = v;
+            }
+        if ((rc = upload(&ds.fkpv, kpv))) break;
+      }
       // rows whose four-row group holds no good pixel never enter the sum
       ds.skip_quads = 0;
       const char *noskip = getenv("PSFMC_NO_ROW_SKIP");
@@ -1752,8 +1800,12 @@ struct psfmc_engine {
 static int rescue_nonfinite(psfmc_engine *engine, const double *theta, int64_t n_batch,
                             int64_t ld, double *lnl_out) {
   engine->r_rows.clear();
+  // (an engine that marks reports "worth repeating" as NaN and keeps -inf for walkers that
+  // are dead by construction, FusedParams::nan_marks)
+  const bool marks = engine->impl->marks_active;
   for (int64_t b = 0; b < n_batch; ++b)
-    if (!(lnl_out[b] > -INFINITY)) engine->r_rows.push_back(b);
+    if (marks ? (lnl_out[b] != lnl_out[b]) : !(lnl_out[b] > -INFINITY))
+      engine->r_rows.push_back(b);
   if (engine->r_rows.empty()) return 0;
   if (!engine->rescue) {
     int rc = create_engine<double>(&engine->saved->d, &engine->rescue);
@@ -1844,6 +1896,7 @@ int psfmc_lnlike_batch_begin(psfmc_engine *engine, const double *theta, int64_t 
   const char *always = getenv("PSFMC_GRAPH_ALWAYS");
   const bool small = always ? always[0] == '1' : n_batch <= 160;
   engine->impl->scan_wanted = engine->saved && (engine->rescue_heat > 0 || small);
+  engine->impl->want_marks = engine->saved != nullptr;
   int rc = engine->impl->lnlike_host_begin(theta, n_batch, ld, lnl_out);
   cudaSetDevice(prev);
   if (rc) return rc;
@@ -1879,6 +1932,10 @@ int psfmc_lnlike_batch_end(psfmc_engine *engine) {
       engine->rescue_heat = 64;
     else if (engine->rescue_heat > 0)
       --engine->rescue_heat;
+    // no NaN leaves the library (a failed repeat, a row list that overflowed)
+    if (impl->marks_active && !(impl->scan_valid && impl->scan_flagged == 0))
+      for (int64_t b = 0; b < engine->f_batch; ++b)
+        if (engine->f_lnl[b] != engine->f_lnl[b]) engine->f_lnl[b] = -INFINITY;
   }
   cudaSetDevice(prev);
   return rc;

@@ -728,6 +728,12 @@ inline int launch_cluster_lnlike(const StagedPlan &plan, const StagedBuffers<T> 
   P.maskw = nullptr;
   P.lnl_const = 0.0;
   P.n_peer = 0;
+  P.hot = nullptr;
+  P.nan_marks = 0;
+  P.kpv = nullptr;
+  P.sub_spec = nullptr;
+  P.partials = nullptr;
+  P.skip_tab = nullptr;
   P.lnl = lnl;
   P.n_batch = n_batch;
   P.ncomp = ncomp;

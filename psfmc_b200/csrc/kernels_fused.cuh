@@ -71,6 +71,17 @@ struct FusedParams {
   cplx<float> *sub_spec;
   double *partials;
   const unsigned *skip_tab;
+  // Hot pixels (prepare_kernel): hot[b][c] = (py << 16 | px) of the pixel that component c
+  // of walker b has taken out of the transform, or -1 (null: feature off); kpv[K][dy][dx] =
+  // (PSF, v * PSF variance) real-space kernels of the circular convolution, lag (dy, dx)
+  const int *hot;
+  const float2 *kpv;
+  // nan_marks (host calls of an engine with the float64 repeat): a result that came out
+  // non-finite is reported as NaN = "worth repeating in float64"; -inf is then reserved
+  // for walkers that are dead by construction (PSF index out of range, Sersic constants
+  // poisoned by the prepare kernel: the reference is -inf there too), which are final.
+  // The host turns whatever NaN is left into -inf.
+  int nan_marks;
   // lnL gather over peer memory (engine.cu, psfmc_lnlike_batch_exchange): with n_peer > 0
   // the result of walker b goes to lnl_peer[p][b] for every rank p (the ranks' mailboxes,
   // mapped through CUDA IPC; plain stores over NVLink) instead of lnl[b]
@@ -381,6 +392,17 @@ __device__ __forceinline__ void mirror_self(cplx<float> &z, float4 s) {
   mirror_pair(z, zm, s);
 }
 
+// Hot pixels of the two walkers a CTA has in flight (the one whose inverse rows run and the
+// next one, whose forward rows run in the same phase): positions from the prepare kernel,
+// the values the render found there ((raw, w raw^2) of the whole pixel, which then enters
+// the transform as zero).
+struct HotState {
+  int pos[2][PSFMC_MAX_COMPONENTS];
+  float val[2][PSFMC_MAX_COMPONENTS][2];
+  int any[2];
+  int dead[2];   // a component's float32 constants are poisoned (prepare_kernel): -inf, final
+};
+
 // Per-thread constants of the row passes (4 rows per warp, 8 threads per row).
 struct RowRole {
   int w, rr, l;
@@ -401,7 +423,8 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
                                                    const float *rc0, const double *der0,
                                                    int it, float wsc,
                                                    const FoldParams *F = nullptr, int sub = 0,
-                                                   bool drain = false) {
+                                                   bool drain = false, HotState *hs = nullptr,
+                                                   int hpar = 0) {
   // drain (tiled forward half, first row batch of a job): the previous job's results are
   // still leaving the tile through bulk stores issued by threads 0..127; the tile may
   // only be written once those have read it (see the kernel)
@@ -424,6 +447,23 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
                                    v);
       else
         fused_render16<8, STAGED>(P, rc0, der0, y, R.l, wsc, v);
+      if (!PADDED && !TILED && __builtin_expect(hs != nullptr, 0)) {
+        // take the walker's hot pixels out of the transform (see prepare_kernel): the
+        // thread that rendered one records its value and zeroes it
+        for (int c = 0; c < P.ncomp; ++c) {
+          const int hp = hs->pos[hpar][c];
+          if (hp >= 0 && (hp >> 16) == y && ((hp & 7) == R.l)) {
+            const int jj = (hp & 0xffff) >> 3;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j == jj) {
+                hs->val[hpar][c][0] = v[j].x;
+                hs->val[hpar][c][1] = v[j].y;
+                v[j] = mk<float>(0.0f, 0.0f);
+              }
+          }
+        }
+      }
       if (PADDED) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -482,7 +522,9 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
                                                      unsigned skip_quads = 0,
                                                      const cplx<float> *gnext = nullptr,
                                                      unsigned long long *bar = nullptr,
-                                                     unsigned char *tile_ptr = nullptr) {
+                                                     unsigned char *tile_ptr = nullptr,
+                                                     const HotState *hs = nullptr, int hpar = 0,
+                                                     const float2 *kpv = nullptr) {
   const int y = it * 64 + R.w * 4 + R.rr;
   // gnext (tiled inverse half): once the warp has taken its four rows out of the tile,
   // lanes 0..3 fetch the same rows of the NEXT job's sub-spectrum into their place
@@ -568,6 +610,23 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
   }
+  if (!PADDED && __builtin_expect(hs != nullptr, 0)) {
+    // the hot pixels' own contribution, convolved exactly: value x real-space kernel
+    for (int c = 0; c < P.ncomp; ++c) {
+      const int hp = hs->pos[hpar][c];
+      if (hp < 0) continue;
+      const float c1 = hs->val[hpar][c][0], c2 = hs->val[hpar][c][1];
+      const int dy = (y - (hp >> 16)) & (PSFMC_FUSED_N - 1);
+      const float2 *krow = kpv + dy * PSFMC_FUSED_N;
+      const int x0 = R.l - (hp & 0xffff);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 k = __ldg(krow + ((x0 + 8 * j) & (PSFMC_FUSED_N - 1)));
+        v[j].x = fmaf(c1, k.x, v[j].x);
+        v[j].y = fmaf(c2, k.y, v[j].y);
+      }
+    }
+  }
   // Chi-square terms (psfMC/models.py:233-236) of the 16 pixels, float32, summed in
   // float32 over 8 pixels before they enter the float64 sum:
   //     resid^2 ivm - log(ivm / 2 pi) = resid^2 / tot + ln2 log2(tot) + ln(2 pi),
@@ -646,8 +705,33 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   __shared__ __align__(16) float rc_s[PSFMC_MAX_COMPONENTS * PSFMC_RC_STRIDE];
   __shared__ double der_s[PSFMC_MAX_COMPONENTS * PSFMC_DERIVED_STRIDE];
   __shared__ float wsc_s;
+  __shared__ HotState hot_s;
+#ifdef PSFMC_HOT_COMPILED_OUT
+  constexpr bool use_hot = false;
+#else
+  const bool use_hot = MODE == PSFMC_MODE_FULL && !PADDED && P.hot != nullptr;
+#endif
+  int hpar = 1;   // hot-state half of the walker whose inverse rows run (the next: hpar ^ 1)
+  if (tid == 1) hot_s.any[1] = hot_s.dead[1] = 0;   // (half 0 is staged below)
   auto stage_params = [&](long long bs) {
     if (bs >= P.n_batch || MODE == PSFMC_MODE_INV) return;
+    if (use_hot && tid >= 64 && tid < 64 + 32) {
+      // one warp: the next walker's hot-pixel positions and whether its float32 constants
+      // are poisoned (flags by warp votes)
+      const int c = tid - 64, half = hpar ^ 1;
+      const int hp = c < P.ncomp ? __ldg(P.hot + bs * P.ncomp + c) : -1;
+      hot_s.pos[half][c] = hp;
+      hot_s.val[half][c][0] = 0.0f;
+      hot_s.val[half][c][1] = 0.0f;
+      const int some = __any_sync(0xffffffffu, hp >= 0);
+      const float c0 = c < P.ncomp ? __ldg(P.rconst + (bs * P.ncomp + c) * PSFMC_RC_STRIDE + 9)
+                                   : 0.0f;
+      const int dead = __any_sync(0xffffffffu, c0 != c0);
+      if (c == 0) {
+        hot_s.any[half] = some;
+        hot_s.dead[half] = dead;
+      }
+    }
     if (TILED) bs >>= 4;   // job -> walker
     if (tid < P.ncomp * PSFMC_RC_STRIDE)
       rc_s[tid] = __ldg(P.rconst + bs * P.ncomp * PSFMC_RC_STRIDE + tid);
@@ -953,6 +1037,10 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
     // ------ rows: inverse + chi-square of walker b, render + forward of the next --
     const long long bn = b + gridDim.x;
     const bool has_next = bn < P.n_batch;
+    // (hot pixels are rare: the row passes get a null pointer unless this walker / the next
+    // one has any)
+    HotState *hot_cur = (use_hot && cur && hot_s.any[hpar]) ? &hot_s : nullptr;
+    HotState *hot_nxt = (use_hot && has_next && hot_s.any[hpar ^ 1]) ? &hot_s : nullptr;
     const float wsc_next = has_next ? wsc_s : 0.0f;
     double acc = 0.0;
 #pragma unroll 1
@@ -966,11 +1054,12 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
               P, tile, R, twl, it, unscale, &F, sub,
               MODE == PSFMC_MODE_INV ? __ldg(P.skip_tab + sub) : P.skip_quads,
               (MODE == PSFMC_MODE_INV && has_next) ? P.sub_spec + (size_t)bn * N * N : nullptr,
-              &tile_bar, smem_raw);
+              &tile_bar, smem_raw, hot_cur, hpar, P.kpv + (size_t)sel * N * N);
       } else if (has_next && MODE != PSFMC_MODE_INV) {
         fused_rows_forward<true, PADDED, TILED>(P, tile, R, twl, rc_s, der_s, it, wsc_next, &F,
                                                 TILED ? (int)(bn & 15) : 0,
-                                                MODE == PSFMC_MODE_FWD && cur && it == 0);
+                                                MODE == PSFMC_MODE_FWD && cur && it == 0,
+                                                hot_nxt, hpar ^ 1);
       }
       if (cur && MODE != PSFMC_MODE_FWD &&
           ((interleave && step == 2) || (!interleave && step == 1))) {
@@ -995,7 +1084,8 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
               P.partials[b] = sub == 0 ? tot + P.lnl_const : tot;
             } else {
               double val = -0.5 * (tot + P.lnl_const);
-              if (!isfinite(val) || invalid) val = -INFINITY;
+              if (!isfinite(val)) val = P.nan_marks ? NAN : -INFINITY;
+              if (invalid || (use_hot && hot_s.dead[hpar])) val = -INFINITY;
               if (P.n_peer > 0) {
 #pragma unroll
                 for (int p = 0; p < 16; ++p)
@@ -1009,6 +1099,7 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
         }
       }
     }
+    hpar ^= 1;   // the next walker becomes the current one
   }
 #ifndef PSFMC_EMU
   if (MODE == PSFMC_MODE_FWD && tid < N)
@@ -1082,6 +1173,9 @@ struct FusedBuffers {
   int n_sms = 148;
   double *const *lnl_peer = nullptr;   // [n_peer] destinations of the results, or null
   int n_peer = 0;
+  int *hot = nullptr;                  // [B][ncomp] hot-pixel flags (prepare kernel), or null
+  const float2 *kpv = nullptr;         // [K][128][128] real-space kernels
+  bool nan_marks = false;              // see FusedParams
   unsigned skip_quads = 0;   // see FusedParams
 };
 
@@ -1095,8 +1189,9 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
                                cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr) {
   if (n_batch <= 0) return 0;
   const int ncomp = prog_h.n_components;
+  int *hot = (fb.hot && fb.kpv && !plan.fr.padded) ? fb.hot : nullptr;
   launch_prepare(*buf.prog_host, theta, n_batch, ld, plan.fr.Hr, plan.fr.Wr, ncomp, buf.derived,
-                 buf.psf_sel, buf.wscale, fb.rconst, stream);
+                 buf.psf_sel, buf.wscale, fb.rconst, stream, hot);
   FusedParams P;
   FoldParams F;
   F.Hr = plan.fr.Hr;
@@ -1115,6 +1210,12 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
   P.ow = fb.ow;
   P.maskw = fb.maskw;
   P.lnl_const = fb.lnl_const;
+  P.hot = hot;
+  P.kpv = fb.kpv;
+  P.nan_marks = (fb.nan_marks && hot) ? 1 : 0;
+  P.sub_spec = nullptr;
+  P.partials = nullptr;
+  P.skip_tab = nullptr;
   P.n_peer = fb.n_peer;
   for (int p = 0; p < 16; ++p) P.lnl_peer[p] = p < fb.n_peer ? fb.lnl_peer[p] : nullptr;
   P.lnl = lnl;

@@ -161,7 +161,8 @@ inline StagedPlan make_padded_plan(int Hr, int Wr, int psf_h, int psf_w, int n_c
 // (bound by the float64 pipe).
 inline void launch_prepare(const Program &prog, const double *theta, long long n_batch,
                            long long ld, int H, int W, int n_components, double *derived,
-                           int *psf_sel, double *wscale, float *rconst, cudaStream_t stream) {
+                           int *psf_sel, double *wscale, float *rconst, cudaStream_t stream,
+                           int *hot = nullptr) {
   const int ncomp = n_components > 0 ? n_components : 1;
   const long long ngroups = n_batch * ncomp;
   const int block = 128;
@@ -177,10 +178,10 @@ inline void launch_prepare(const Program &prog, const double *theta, long long n
   if (!stage) smem = 0;
   if (wide)
     launch_kernel(prepare_kernel<32>, dim3(grid), dim3(block), smem, stream, prog, theta,
-                  n_batch, ld, H, W, derived, psf_sel, wscale, rconst, stage);
+                  n_batch, ld, H, W, derived, psf_sel, wscale, rconst, stage, hot);
   else
     launch_kernel(prepare_kernel<8>, dim3(grid), dim3(block), smem, stream, prog, theta,
-                  n_batch, ld, H, W, derived, psf_sel, wscale, rconst, stage);
+                  n_batch, ld, H, W, derived, psf_sel, wscale, rconst, stage, hot);
 }
 
 // Device-resident state the launch sequence needs (one per device per precision).

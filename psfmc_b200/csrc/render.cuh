@@ -103,7 +103,8 @@ __global__ void prepare_kernel(const __grid_constant__ Program prog_c,
                                const double *__restrict__ theta, long long n_batch,
                                long long ld, int H, int W, double *__restrict__ derived,
                                int *__restrict__ psf_sel, double *__restrict__ wscale,
-                               float *__restrict__ rconst, int stage) {
+                               float *__restrict__ rconst, int stage,
+                               int *__restrict__ hot = nullptr) {
   // stage: the theta rows of this CTA's walkers go through shared memory first, read
   // once with coalesced loads. (Tried on the B200: handing the kernel the caller's
   // page-locked HOST rows instead of copying them first -- per C-ABI call 70.6 us against
@@ -262,6 +263,27 @@ __global__ void prepare_kernel(const __grid_constant__ Program prog_c,
     out[D_SER_P] = 0.5 / n;
     out[D_SER_KAPPA] = kappa;
     out[D_SER_SBEFF] = sersic_sb_eff(flux, n, reff, reff_b, kappa, gamma_2n);
+  }
+  // hot[b][c] (optional, fused 128 x 128 path): the pixel (py << 16 | px) the float32
+  // kernel takes out of the transform for this component, or -1. A Sersic of index n > 1
+  // whose centre lies within 0.05 px of a pixel centre: the reference's centroid
+  // correction g^2 |d|^2 / 12 grows like |d|^(2/n - 2) there, so that ONE pixel outshines
+  // its neighbours by 10^2 .. 10^5 -- and the rounding noise of a float32 transform,
+  // which is relative to the largest element, swamps the rest of the frame (negative
+  // convolved variances; round 1 repeated such walkers in float64). The pixel's
+  // contribution is convolved exactly instead: (value) x (real-space PSF / PSF-variance
+  // stamp) is added in the epilogue (FusedParams::kpv).
+  if (hot && writer) {
+    int flag = -1;
+    if (kind == PSFMC_SERSIC) {
+      const double x0 = out[D_SER_X0], y0 = out[D_SER_Y0];
+      const double px = rint(x0), py = rint(y0);
+      const double r2 = (x0 - px) * (x0 - px) + (y0 - py) * (y0 - py);
+      if (n_index > 1.0 && r2 < 0.0025 && px >= 0.0 && px < (double)W && py >= 0.0 &&
+          py < (double)H)
+        flag = ((int)py << 16) | (int)px;
+    }
+    hot[b * ncomp + c] = flag;
   }
   if (rconst && writer) {
     float *rc = rconst + (b * ncomp + c) * PSFMC_RC_STRIDE;

@@ -240,9 +240,66 @@ HIGH_DYNAMIC_RANGE_THETAS = [
      7.63948e+00, 2.47298e+01, 5.87249e+00, 3.92618e+00, 4.20018e+01, 8.49977e+01]]
 
 
+class _no_hot_pixel(object):
+    """The float64 repeat is exercised with the walkers that needed it in round 1; the
+    fused kernel now treats them itself (hot pixels, check_hot_pixel_walkers), so these
+    tests switch that off."""
+
+    def __enter__(self):
+        self.old = os.environ.get('PSFMC_NO_HOT_PIXEL')
+        os.environ['PSFMC_NO_HOT_PIXEL'] = '1'
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            del os.environ['PSFMC_NO_HOT_PIXEL']
+        else:
+            os.environ['PSFMC_NO_HOT_PIXEL'] = self.old
+
+
+def check_hot_pixel_walkers(library, c1_golden):
+    """A Sersic centre within 0.05 px of a pixel centre at index > 1: one pixel outshines
+    the frame by up to 1e5 (the reference's centroid correction diverges at the centre) and
+    the float32 transform's rounding noise used to swamp the far pixels (negative variances
+    -> NaN -> repeated in float64). The fused kernel takes that pixel out of the transform
+    and convolves it exactly in real space: the walkers are finite in float32, within the
+    float32 bound, with no float64 repeat; walkers without a hot pixel are bit-identical
+    with the feature off."""
+    exact = c1_golden['names'].index('C_exact_centre')
+    near = np.array(c1_golden['theta'][0])
+    near[9:11] = [64.03, 63.98]                 # Sersic 1: 0.036 px from pixel (64, 64)
+    near[5] = 6.5
+    twice = np.array(near)
+    twice[16:18] = [46.0 + 1e-3, 85.0 - 2e-3]   # both Sersics hot (index 1.2: just above 1)
+    thetas = np.array(HIGH_DYNAMIC_RANGE_THETAS + [near, twice, c1_golden['theta'][exact],
+                                                   c1_golden['theta'][0],
+                                                   c1_golden['theta'][1]])
+    model = model_from_file('j0005/model_c1.py', 'fp32', library=library,
+                            obs_dtype=np.float64)
+    oracle = oracle_from_model(model)
+    expect = oracle.lnlike_batch(thetas)
+    assert np.all(np.isfinite(expect[[0, 1, 2, 3, 5, 6]])) and expect[4] == -np.inf
+    got = model.log_likelihood_batch(thetas)
+    assert model.engine.info()['rescued_total'] == 1      # only the exact-centre walker
+    assert_lnl_close(got, expect, 'fp32', fp32_bounds(model, thetas, oracle))
+    with _no_hot_pixel():
+        off = model_from_file('j0005/model_c1.py', 'fp32', library=library,
+                              obs_dtype=np.float64, fp64_rescue=False)
+        got_off = off.log_likelihood_batch(thetas)
+    assert np.array_equal(got_off[5:], got[5:])           # no hot pixel: same arithmetic
+    assert np.all(got_off[:2] == -np.inf)                 # round 1's behaviour
+    # batch composition and persistent-CTA loops do not matter
+    assert np.array_equal(model.log_likelihood_batch(thetas[::-1])[::-1], got)
+    return got
+
+
 def check_fp64_rescue(library, c1_golden):
     """float32 mode: non-finite float32 results are repeated in float64 on the device
     (psfmc_lnlike_batch); really infinite walkers stay -inf; the flag turns it off."""
+    with _no_hot_pixel():
+        return _check_fp64_rescue(library, c1_golden)
+
+
+def _check_fp64_rescue(library, c1_golden):
     exact = c1_golden['names'].index('C_exact_centre')
     thetas = np.array(HIGH_DYNAMIC_RANGE_THETAS + [c1_golden['theta'][exact],
                                                    c1_golden['theta'][0]])
@@ -266,6 +323,11 @@ def check_fp64_rescue(library, c1_golden):
 
 
 def check_fp64_rescue_on_device(library, c1_golden, monkeypatch):
+    monkeypatch.setenv('PSFMC_NO_HOT_PIXEL', '1')
+    return _check_fp64_rescue_on_device(library, c1_golden, monkeypatch)
+
+
+def _check_fp64_rescue_on_device(library, c1_golden, monkeypatch):
     """Host calls of a single-device float32 engine are replayed as CUDA graphs whose
     conditional node repeats non-finite walkers in float64 without a host round trip
     (engine.cu: lnlike_host_graph). Same numbers as the host-side repeat, bit for bit;

@@ -10,7 +10,7 @@ import pytest
 
 from conftest import (ARBITRARY_FRAMES, assert_lnl_close, check_arbitrary_frame,
                       check_cluster_path_256, check_tiled_path_512, check_cropped_golden, check_nan_propagation,
-                      check_fp64_rescue, check_near_centre_walkers, check_pssub_golden,
+                      check_fp64_rescue, check_hot_pixel_walkers, check_near_centre_walkers, check_pssub_golden,
                       mixed_model_128, fp32_bounds, load_golden, model_from_file,
                       oracle_from_model)
 
@@ -266,6 +266,11 @@ def test_emu_mixed_components_fused_and_fp64(emu_library):
 
 def test_emu_fp64_rescue_of_high_dynamic_range_walkers(emu_library, c1_golden):
     check_fp64_rescue(emu_library, c1_golden)
+
+
+def test_emu_hot_pixel_walkers(emu_library, c1_golden, monkeypatch):
+    monkeypatch.setenv('PSFMC_FUSED_CTAS', '2')      # walker loops: both hot-state halves
+    check_hot_pixel_walkers(emu_library, c1_golden)
 
 
 def test_emu_fused_near_centre_walkers(emu_library):

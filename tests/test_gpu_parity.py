@@ -518,12 +518,13 @@ def test_gpu_fp64_rescue_inside_the_graph(cuda_library, c1_golden, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_gpu_split_host_call_and_overlapped_priors(cuda_library, c1_golden):
+def test_gpu_split_host_call_and_overlapped_priors(cuda_library, c1_golden, monkeypatch):
     """psfmc_lnlike_batch_begin / _end on the GPU (plain launches and graph replay):
     the numbers of the blocking call; log_posterior_batch with the priors evaluated
     between the two halves equals lnL + lnprior of the separate calls."""
     from conftest import HIGH_DYNAMIC_RANGE_THETAS, model_from_file
     from psfmc_b200.synthetic import draw_walkers_fast
+    monkeypatch.setenv('PSFMC_NO_HOT_PIXEL', '1')    # (the walker below must need the repeat)
     model = model_from_file('j0005/model_c1.py', 'fp32', library=cuda_library,
                             obs_dtype=np.float64)
     engine = model.engine
@@ -594,6 +595,11 @@ def test_gpu_tiny_sersic_index_is_minus_inf_like_the_reference(cuda_library):
 
 
 @pytest.mark.gpu
+def test_gpu_hot_pixel_walkers(cuda_library, c1_golden):
+    from conftest import check_hot_pixel_walkers
+    check_hot_pixel_walkers(cuda_library, c1_golden)
+
+
 def test_gpu_fused_near_centre_walkers(cuda_library):
     from conftest import check_near_centre_walkers
     check_near_centre_walkers(cuda_library)
