@@ -450,6 +450,7 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
       if (!PADDED && !TILED && __builtin_expect(hs != nullptr, 0)) {
         // take the walker's hot pixels out of the transform (see prepare_kernel): the
         // thread that rendered one records its value and zeroes it
+#pragma unroll 1
         for (int c = 0; c < P.ncomp; ++c) {
           const int hp = hs->pos[hpar][c];
           if (hp >= 0 && (hp >> 16) == y && ((hp & 7) == R.l)) {
@@ -612,6 +613,7 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   }
   if (!PADDED && __builtin_expect(hs != nullptr, 0)) {
     // the hot pixels' own contribution, convolved exactly: value x real-space kernel
+#pragma unroll 1
     for (int c = 0; c < P.ncomp; ++c) {
       const int hp = hs->pos[hpar][c];
       if (hp < 0) continue;

@@ -1,0 +1,16 @@
+# Strong-scaling lines on one box (run under gpurun --gpus 8): ONE ensemble sharded over N ranks.
+run() {  # n, tag, extra args
+  n=$1; tag=$2; shift 2
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $n --no-cpu-baseline "$@" > gpurun_out/r2_bench_${tag}_${n}gpu.json 2> gpurun_out/r2_bench_${tag}_${n}gpu.err
+  python - <<PY
+import json
+d=json.loads([l for l in open("gpurun_out/r2_bench_${tag}_${n}gpu.json") if l.startswith("{")][-1])
+print("$tag N=$n value",d["value"],"ms",d["ms_per_step"],"e2e",d["e2e"]["value"],"nccl",(d.get("with_nccl_gather") or {}).get("value"),"replicas",(d.get("replicas_weak") or {}).get("value"),"k_us",d["roofline"]["kernel_us_per_launch"])
+PY
+}
+python -m pytest tests -m gpu -q -k "multi" > gpurun_out/r2_pytest_multi_gpu.log 2>&1; tail -2 gpurun_out/r2_pytest_multi_gpu.log
+for n in 2 4 8; do run $n c1 --steps 200 --warmup 5; done
+run 8 c1_65536 --walkers 65536 --steps 20 --warmup 3
+run 8 c4 --workload c4 --steps 10 --warmup 3
+run 8 c1_16384 --walkers 16384 --steps 50 --warmup 3
