@@ -627,6 +627,42 @@ def run_ours(args):
     map_s = host_timed(step_pool_map, map_steps)
     map_inside_s = max_over_ranks(inside_map[0])
 
+    # ---- the whole sampler iteration (stretch-move proposals, priors, lnL, acceptance)
+    # inside the library: psfmc_ensemble_run, what this package's sampler calls; beside it
+    # the same sampler with its numpy loop, at the bench ensemble and at the reference
+    # example's 250 walkers (examples/run_example.py:9)
+    loop = None
+    if world == 1:
+        from psfmc_b200.sampler import EnsembleSampler
+        loop = {}
+
+        def sampler_rate(nwalk, native, iters):
+            os.environ['PSFMC_NATIVE_SAMPLER'] = '1' if native else '0'
+            start = thetas[0][:nwalk]
+            smp = EnsembleSampler(nwalk, ndim, model.log_posterior, kwargs={'model': model},
+                                  pool=BatchPool(model), live_dangerously=True)
+            smp._random.seed(7)
+            pos, lnp, _ = smp.run_mcmc(start, 3)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            smp.run_mcmc(pos, iters, lnprob0=lnp)
+            return nwalk * iters / (time.perf_counter() - t0)
+        try:
+            loop['library'] = round(sampler_rate(walkers, True, args.steps), 1)
+            loop['numpy_loop'] = round(sampler_rate(walkers, False, max(10, args.steps // 3)), 1)
+            small = min(250, walkers)
+            loop['walkers_small'] = small
+            loop['library_small'] = round(sampler_rate(small, True, 4 * args.steps), 1)
+            loop['numpy_loop_small'] = round(sampler_rate(small, False, args.steps), 1)
+            loop['prior_columns_in_python'] = bool(model._sampler_plan and
+                                                   model._sampler_plan['python_columns'])
+            loop['note'] = ('stretch-move iterations of one ensemble end to end (proposals, '
+                            'log-priors, lnL through host buffers, acceptance, chain storage): '
+                            'library = psfmc_ensemble_run, numpy_loop = the same sampler with '
+                            'its Python loop; *_small = the reference example\'s ensemble size')
+        finally:
+            os.environ.pop('PSFMC_NATIVE_SAMPLER', None)
+
     info = engine.info()
     result = None
     if rank == 0:
@@ -738,6 +774,7 @@ def run_ours(args):
                                      'row views it builds, the floats it picks out of the '
                                      'result tuples), pool_map_inside only the map call'.format(
                                          type(pool).__name__),
+                    'sampler_loop': loop,
                     'fp64_rescued_walkers_per_step': round(rescued_per_step, 2),
                     'without_fp64_rescue': None if e2e_raw is None else round(e2e_raw, 1)},
             'gpu_launches': int(launches),

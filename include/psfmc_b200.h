@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PSFMC_ABI_VERSION 1
+#define PSFMC_ABI_VERSION 2
 
 /* error codes */
 #define PSFMC_OK 0
@@ -237,6 +237,14 @@ int psfmc_accumulate_batch(psfmc_engine *engine, const double *theta, int64_t n_
 #define PSFMC_PRIOR_OTHER 0   /* column evaluated by the caller (any other scipy family) */
 #define PSFMC_PRIOR_UNIFORM 1 /* scipy.stats.uniform(loc, scale)                        */
 #define PSFMC_PRIOR_NORMAL 2  /* scipy.stats.norm(loc, scale)                           */
+#define PSFMC_PRIOR_WEIBULL_MIN 3 /* scipy.stats.weibull_min(c, loc, scale): log(c) +
+                                   * xlogy(c - 1, x) - pow(x, c) with the C library's log /
+                                   * pow -- what numpy 1.21 (the reference's pin) calls;
+                                   * numpy >= 1.22 on AVX-512 hosts uses SVML's pow instead,
+                                   * which differs in the last bit for ~5 % of the arguments.
+                                   * The Python caller accepts this family only if it agrees
+                                   * with rv_frozen.logpdf to 4 ulps on its first batch, and
+                                   * keeps it out (PSFMC_PRIOR_OTHER) in strict mode.        */
 typedef struct psfmc_prior_column {
   int32_t family;      /* PSFMC_PRIOR_*                                                 */
   int32_t theta_index; /* column of theta                                               */
@@ -245,6 +253,8 @@ typedef struct psfmc_prior_column {
   double loc, scale;
   double log_scale;    /* numpy.log(scale)                                              */
   double log_norm;     /* NORMAL: scipy's log(sqrt(2 pi)) constant                      */
+  double shape;        /* WEIBULL_MIN: c                                                */
+  double log_shape;    /* WEIBULL_MIN: numpy.log(c)                                     */
 } psfmc_prior_column;
 /* logp_out[b*ld_out + c] for every column c whose family is not PSFMC_PRIOR_OTHER. */
 int psfmc_prior_columns(const psfmc_prior_column *columns, int32_t n_columns,
@@ -264,6 +274,61 @@ int psfmc_prior_sum(const double *logp, int64_t n_batch, int64_t ld_logp, const 
                     int64_t ld, const psfmc_prior_term *terms, int32_t n_terms,
                     const psfmc_prior_rule *rules, int32_t n_rules, int32_t n_components,
                     double *lnprior_out);
+
+/* ---- the sampler's inner loop on the host side of the library ----
+ * psfMC hands `MultiComponentModel.log_posterior` to emcee 2.x's EnsembleSampler
+ * (psfMC/fitting.py:55-78); per iteration emcee evaluates two sequentially dependent
+ * half-ensembles (stretch move, emcee/ensemble.py: _propose_stretch). At the reference
+ * example's ensemble size (250 walkers, examples/run_example.py:9) the GPU needs ~35 us
+ * per half-ensemble and a Python loop ~300 us, so the loop itself is offered here:
+ * proposals, log-priors, lnL (psfmc_lnlike_batch_begin / _end with the priors evaluated
+ * while the GPU computes), acceptance and chain storage for n_iterations without leaving
+ * the library. Random numbers come from numpy.random.RandomState's own generator state
+ * (MT19937 key + position, handed over and returned), consumed in emcee's call order --
+ * rand(Ns), randint(Nc, size=Ns), rand(Ns) per half-step -- with numpy's algorithms
+ * (53-bit doubles from two draws, masked rejection for bounded integers), so a seeded
+ * run continues bit for bit the stream a Python emcee loop would have drawn. */
+typedef struct psfmc_prior_plan {
+  const psfmc_prior_column *columns; /* [n_columns], one per theta column             */
+  const psfmc_prior_term *terms;     /* [n_terms], see psfmc_prior_sum                 */
+  const psfmc_prior_rule *rules;     /* [n_rules]                                      */
+  int32_t n_columns, n_terms, n_rules, n_components;
+  /* columns of family PSFMC_PRIOR_OTHER are filled by the caller (any scipy family, custom
+   * Distribution subclasses, discrete priors): logp[b*ld_logp + c]; non-zero return
+   * aborts the run. May be null when no column is OTHER. */
+  int (*other_columns)(void *user, const double *theta, int64_t n_batch, int64_t ld,
+                       double *logp, int64_t ld_logp);
+  void *user;
+} psfmc_prior_plan;
+
+/* lnpost_out[b] = lnL + lnprior, or -inf where either is not finite
+ * (psfMC/models.py:205-211, 238-243). */
+int psfmc_lnpost_batch(psfmc_engine *engine, const psfmc_prior_plan *priors,
+                       const double *theta, int64_t n_batch, int64_t ld, double *lnpost_out);
+
+typedef struct psfmc_ensemble {
+  int64_t n_walkers;     /* k, even                                                    */
+  int64_t n_dim;         /* D = row length of pos                                      */
+  double a;              /* stretch scale (emcee default 2.0)                          */
+  double *pos;           /* [k][D] in / out                                            */
+  double *lnprob;        /* [k]    in / out (must be the lnpost of pos on entry)       */
+  uint32_t *mt_key;      /* [624]  numpy RandomState.get_state()[1], in / out          */
+  int32_t *mt_pos;       /*        ... get_state()[2], in / out                        */
+  double *chain;         /* [k][chain_len][D] (emcee's layout) or null                 */
+  double *lnprob_chain;  /* [k][chain_len] or null                                     */
+  int64_t chain_len;     /* allocated iterations per walker                            */
+  int64_t chain_start;   /* index the first stored iteration goes to                   */
+  int64_t thin;          /* store every thin-th iteration (>= 1)                       */
+  double *n_accepted;    /* [k], incremented (emcee keeps it as float64)               */
+} psfmc_ensemble;
+/* Advances the ensemble by n_iterations stretch-move iterations. Errors: a proposal with
+ * an infinite / NaN coordinate (emcee raises ValueError), a failing callback. */
+int psfmc_ensemble_run(psfmc_engine *engine, const psfmc_prior_plan *priors,
+                       psfmc_ensemble *ensemble, int64_t n_iterations);
+/* The generator on its own (tests): kind 0 = n doubles of RandomState.random_sample,
+ * kind 1 = n values of RandomState.randint(bound) (as doubles). */
+int psfmc_rng_fill(uint32_t *mt_key, int32_t *mt_pos, int32_t kind, int64_t n, int64_t bound,
+                   double *out);
 
 /* Introspection (roofline bookkeeping for bench.py). */
 typedef struct psfmc_info {

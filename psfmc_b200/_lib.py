@@ -9,7 +9,7 @@ import ctypes
 import os
 
 PEER_HANDLE_BYTES = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SKY, POINT, SERSIC = 0, 1, 2
 FLAG_ANGLE_DEGREES, FLAG_BILINEAR = 1, 2
@@ -73,14 +73,15 @@ class Info(ctypes.Structure):
     ]
 
 
-PRIOR_OTHER, PRIOR_UNIFORM, PRIOR_NORMAL = 0, 1, 2
+PRIOR_OTHER, PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_WEIBULL_MIN = 0, 1, 2, 3
 
 
 class PriorColumn(ctypes.Structure):
     _fields_ = [('family', ctypes.c_int32), ('theta_index', ctypes.c_int32),
                 ('valid', ctypes.c_int32), ('reserved', ctypes.c_int32),
                 ('loc', ctypes.c_double), ('scale', ctypes.c_double),
-                ('log_scale', ctypes.c_double), ('log_norm', ctypes.c_double)]
+                ('log_scale', ctypes.c_double), ('log_norm', ctypes.c_double),
+                ('shape', ctypes.c_double), ('log_shape', ctypes.c_double)]
 
 
 class PriorTerm(ctypes.Structure):
@@ -94,6 +95,37 @@ class PriorRule(ctypes.Structure):
                 ('a_value', ctypes.c_double), ('b_value', ctypes.c_double)]
 
 
+# int (*other_columns)(void *user, const double *theta, int64 n, int64 ld, double *logp,
+#                      int64 ld_logp)
+OTHER_COLUMNS_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.POINTER(ctypes.c_double), ctypes.c_int64,
+                                    ctypes.c_int64, ctypes.POINTER(ctypes.c_double),
+                                    ctypes.c_int64)
+
+
+class PriorPlan(ctypes.Structure):
+    _fields_ = [('columns', ctypes.POINTER(PriorColumn)),
+                ('terms', ctypes.POINTER(PriorTerm)),
+                ('rules', ctypes.POINTER(PriorRule)),
+                ('n_columns', ctypes.c_int32), ('n_terms', ctypes.c_int32),
+                ('n_rules', ctypes.c_int32), ('n_components', ctypes.c_int32),
+                ('other_columns', OTHER_COLUMNS_FN), ('user', ctypes.c_void_p)]
+
+
+class Ensemble(ctypes.Structure):
+    _fields_ = [('n_walkers', ctypes.c_int64), ('n_dim', ctypes.c_int64),
+                ('a', ctypes.c_double),
+                ('pos', ctypes.POINTER(ctypes.c_double)),
+                ('lnprob', ctypes.POINTER(ctypes.c_double)),
+                ('mt_key', ctypes.POINTER(ctypes.c_uint32)),
+                ('mt_pos', ctypes.POINTER(ctypes.c_int32)),
+                ('chain', ctypes.POINTER(ctypes.c_double)),
+                ('lnprob_chain', ctypes.POINTER(ctypes.c_double)),
+                ('chain_len', ctypes.c_int64), ('chain_start', ctypes.c_int64),
+                ('thin', ctypes.c_int64),
+                ('n_accepted', ctypes.POINTER(ctypes.c_double))]
+
+
 # every symbol include/psfmc_b200.h declares
 EXPORTED_SYMBOLS = (
     'psfmc_engine_create', 'psfmc_engine_destroy', 'psfmc_lnlike_batch',
@@ -103,7 +135,7 @@ EXPORTED_SYMBOLS = (
     'psfmc_engine_profile', 'psfmc_engine_profile_read',
     'psfmc_fp32_peak_probe', 'psfmc_last_error', 'psfmc_abi_version',
     'psfmc_peer_create', 'psfmc_peer_connect', 'psfmc_lnlike_batch_exchange',
-    'psfmc_peer_gathered',
+    'psfmc_peer_gathered', 'psfmc_lnpost_batch', 'psfmc_ensemble_run', 'psfmc_rng_fill',
 )
 
 _DEFAULT_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)),
@@ -188,6 +220,16 @@ def load(path=None):
         ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
     lib.psfmc_peer_gathered.restype = ctypes.c_int
     lib.psfmc_peer_gathered.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.psfmc_lnpost_batch.restype = ctypes.c_int
+    lib.psfmc_lnpost_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(PriorPlan), dbl_p,
+                                       ctypes.c_int64, ctypes.c_int64, dbl_p]
+    lib.psfmc_ensemble_run.restype = ctypes.c_int
+    lib.psfmc_ensemble_run.argtypes = [ctypes.c_void_p, ctypes.POINTER(PriorPlan),
+                                       ctypes.POINTER(Ensemble), ctypes.c_int64]
+    lib.psfmc_rng_fill.restype = ctypes.c_int
+    lib.psfmc_rng_fill.argtypes = [ctypes.POINTER(ctypes.c_uint32),
+                                   ctypes.POINTER(ctypes.c_int32), ctypes.c_int32,
+                                   ctypes.c_int64, ctypes.c_int64, dbl_p]
     lib.psfmc_fp32_peak_probe.restype = ctypes.c_int
     lib.psfmc_fp32_peak_probe.argtypes = [ctypes.c_int32, dbl_p, dbl_p]
     if lib.psfmc_abi_version() != ABI_VERSION:

@@ -22,6 +22,7 @@
 
 #include "pipeline.cuh"
 #include "priors_host.cuh"
+#include "sampler_host.cuh"
 #ifndef PSFMC_NO_FUSED
 #include "kernels_fused.cuh"
 #include "kernels_cluster.cuh"
@@ -1786,6 +1787,9 @@ struct psfmc_engine {
   int64_t f_batch = 0, f_ld = 0;
   std::vector<double> r_theta, r_lnl;
   std::vector<long long> r_rows;
+  // psfmc_ensemble_run / psfmc_lnpost_batch: proposals and their lnL in page-locked memory
+  // (stable addresses: the host call is then one replayed graph, no staging copies)
+  PinBuf<double> ens_q, ens_lnl;
 };
 
 // A float32 evaluation that came back non-finite is repeated in float64 on the GPU:
@@ -1869,6 +1873,8 @@ void psfmc_engine_destroy(psfmc_engine *engine) {
     cudaFree(engine->peer.base);
   }
 #endif
+  engine->ens_q.release();
+  engine->ens_lnl.release();
   delete engine->impl;
   delete engine->rescue;
   delete engine->saved;
@@ -2174,7 +2180,7 @@ int psfmc_prior_columns(const psfmc_prior_column *columns, int32_t n_columns,
   if (n_batch == 0 || n_columns == 0) return 0;
   if (!columns || !theta || !logp_out) return fail(PSFMC_ERR_INVALID_ARG, "null pointer");
   for (int c = 0; c < n_columns; ++c) {
-    if (columns[c].family < PSFMC_PRIOR_OTHER || columns[c].family > PSFMC_PRIOR_NORMAL)
+    if (columns[c].family < PSFMC_PRIOR_OTHER || columns[c].family > PSFMC_PRIOR_WEIBULL_MIN)
       return fail(PSFMC_ERR_INVALID_ARG, "unknown prior family");
     if (columns[c].family != PSFMC_PRIOR_OTHER &&
         (columns[c].theta_index < 0 || columns[c].theta_index >= ld))
@@ -2206,6 +2212,91 @@ int psfmc_prior_sum(const double *logp, int64_t n_batch, int64_t ld_logp, const 
       return fail(PSFMC_ERR_INVALID_ARG, "prior rule outside theta");
   prior_sum_host(logp, n_batch, ld_logp, theta, ld, terms, n_terms, rules, n_rules,
                  n_components, lnprior_out);
+  return 0;
+}
+
+static int ens_begin(void *self, const double *theta, long long n, long long ld, double *lnl) {
+  return psfmc_lnlike_batch_begin((psfmc_engine *)self, theta, n, ld, lnl);
+}
+static int ens_end(void *self) { return psfmc_lnlike_batch_end((psfmc_engine *)self); }
+
+int psfmc_lnpost_batch(psfmc_engine *engine, const psfmc_prior_plan *priors,
+                       const double *theta, int64_t n_batch, int64_t ld, double *lnpost_out) {
+  if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
+  if (n_batch < 0 || ld < 0) return fail(PSFMC_ERR_INVALID_ARG, "negative batch or ld");
+  if (n_batch == 0) return 0;
+  if (!theta || !lnpost_out) return fail(PSFMC_ERR_INVALID_ARG, "null theta / lnpost_out");
+  const char *why = nullptr;
+  if (check_prior_plan(priors, ld, &why)) return fail(PSFMC_ERR_INVALID_ARG, why);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(engine->impl->first_ordinal);
+  const int bad = engine->ens_lnl.ensure((size_t)n_batch);
+  cudaSetDevice(prev);
+  if (bad) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
+  LnlikeCalls calls{engine, ens_begin, ens_end};
+  LnpostWork wk;
+  int rc = lnpost_rows(calls, priors, theta, n_batch, ld, engine->ens_lnl.ptr, lnpost_out, wk);
+  if (rc == -1) return fail(PSFMC_ERR_INVALID_ARG, "the other_columns callback failed");
+  return rc;
+}
+
+int psfmc_ensemble_run(psfmc_engine *engine, const psfmc_prior_plan *priors,
+                       psfmc_ensemble *ens, int64_t n_iterations) {
+  if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
+  if (!ens) return fail(PSFMC_ERR_INVALID_ARG, "ensemble is null");
+  if (n_iterations < 0) return fail(PSFMC_ERR_INVALID_ARG, "negative number of iterations");
+  if (ens->n_walkers < 2 || (ens->n_walkers & 1))
+    return fail(PSFMC_ERR_INVALID_ARG, "the number of walkers must be even and at least 2");
+  if (ens->n_walkers / 2 >= 0xffffffffLL)
+    return fail(PSFMC_ERR_INVALID_ARG, "too many walkers");
+  if (ens->n_dim < 1 || ens->n_dim < engine->impl->n_theta)
+    return fail(PSFMC_ERR_INVALID_ARG,
+                "n_dim is smaller than the number of theta columns the component program reads");
+  if (!ens->pos || !ens->lnprob || !ens->mt_key || !ens->mt_pos)
+    return fail(PSFMC_ERR_INVALID_ARG, "null pos / lnprob / generator state");
+  if (!(ens->a > 1.0)) return fail(PSFMC_ERR_INVALID_ARG, "the stretch scale a must exceed 1");
+  if ((ens->chain || ens->lnprob_chain) && (ens->chain_len < 0 || ens->chain_start < 0))
+    return fail(PSFMC_ERR_INVALID_ARG, "negative chain length / start");
+  if (engine->in_flight) return fail(PSFMC_ERR_INVALID_ARG, "a batch is already in flight");
+  const char *why = nullptr;
+  if (check_prior_plan(priors, ens->n_dim, &why)) return fail(PSFMC_ERR_INVALID_ARG, why);
+  if (n_iterations == 0) return 0;
+  const size_t half = (size_t)(ens->n_walkers / 2);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(engine->impl->first_ordinal);
+  const int bad = engine->ens_q.ensure(half * (size_t)ens->n_dim) || engine->ens_lnl.ensure(half);
+  cudaSetDevice(prev);
+  if (bad) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
+  LnlikeCalls calls{engine, ens_begin, ens_end};
+  int rc = run_ensemble(calls, priors, ens, n_iterations, engine->ens_q.ptr, engine->ens_lnl.ptr);
+  switch (rc) {
+    case PSFMC_ENS_OK: return 0;
+    case PSFMC_ENS_CALLBACK:
+      return fail(PSFMC_ERR_INVALID_ARG, "the other_columns callback failed");
+    case PSFMC_ENS_POS_INF:
+      return fail(PSFMC_ERR_INVALID_ARG, "At least one parameter value was infinite.");
+    case PSFMC_ENS_POS_NAN:
+      return fail(PSFMC_ERR_INVALID_ARG, "At least one parameter value was NaN.");
+    case PSFMC_ENS_LNPROB_NAN: return fail(PSFMC_ERR_INVALID_ARG, "lnprob returned NaN.");
+    default: return rc;   // engine error, message already set
+  }
+}
+
+int psfmc_rng_fill(uint32_t *mt_key, int32_t *mt_pos, int32_t kind, int64_t n, int64_t bound,
+                   double *out) {
+  if (!mt_key || !mt_pos || (n > 0 && !out)) return fail(PSFMC_ERR_INVALID_ARG, "null pointer");
+  if (n < 0) return fail(PSFMC_ERR_INVALID_ARG, "negative count");
+  NumpyMT19937 mt{mt_key, mt_pos};
+  if (kind == 0) {
+    for (int64_t i = 0; i < n; ++i) out[i] = mt.next_double();
+  } else if (kind == 1) {
+    if (bound < 1 || bound > 0xffffffffLL) return fail(PSFMC_ERR_INVALID_ARG, "bound out of range");
+    for (int64_t i = 0; i < n; ++i) out[i] = (double)mt.next_bounded((uint32_t)bound);
+  } else {
+    return fail(PSFMC_ERR_INVALID_ARG, "unknown kind");
+  }
   return 0;
 }
 

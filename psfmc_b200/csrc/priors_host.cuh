@@ -42,6 +42,23 @@ inline void prior_columns_host(const psfmc_prior_column *cols, int n_cols, const
         if (std_ != std_) v = NAN;
         out[b * ld_out] = v;
       }
+    } else if (pc.family == PSFMC_PRIOR_WEIBULL_MIN) {
+      // weibull_min_gen._logpdf = np.log(c) + sc.xlogy(c - 1, x) - pow(x, c); support
+      // [0, inf). xlogy(a, y) = 0 for a == 0 and y not NaN, else a * log(y). The only family
+      // here with library calls (log, pow): see PSFMC_PRIOR_WEIBULL_MIN in the header.
+      const double cshape = pc.shape, cm1 = pc.shape - 1.0, log_c = pc.log_shape;
+      const double log_scale = pc.log_scale;
+      for (long long b = 0; b < n_batch; ++b) {
+        const double std_ = (x[b * ld] - loc) / scale;
+        double v = -INFINITY;
+        if (std_ >= 0.0 && std_ <= INFINITY) {
+          volatile double xl = (cm1 == 0.0) ? 0.0 : cm1 * log(std_);
+          volatile double pw = pow(std_, cshape);
+          v = ((log_c + xl) - pw) - log_scale;
+        }
+        if (std_ != std_) v = NAN;
+        out[b * ld_out] = v;
+      }
     } else {
       // norm_gen._logpdf = -x**2 / 2.0 - log(sqrt(2 pi)); support (-inf, inf)
       const double log_norm = pc.log_norm, log_scale = pc.log_scale;

@@ -180,6 +180,72 @@ class LikelihoodEngine(object):
             self._in_flight = None
         return out
 
+    # -- the sampler's inner loop in the library (psfmc_ensemble_run) ------------
+    def lnpost(self, plan, thetas, out=None):
+        """lnL + log-prior (``plan``: a ``_lib.PriorPlan``) per row; -inf where either
+        is not finite (psfMC/models.py:205-211, 238-243)."""
+        thetas = np.ascontiguousarray(np.atleast_2d(thetas), dtype=np.float64)
+        n_batch, ld = thetas.shape
+        if out is None:
+            out = np.empty(n_batch, dtype=np.float64)
+        dbl_p = ctypes.POINTER(ctypes.c_double)
+        _lib.check(self._lib, self._lib.psfmc_lnpost_batch(
+            self._handle, ctypes.byref(plan), thetas.ctypes.data_as(dbl_p), n_batch, ld,
+            out.ctypes.data_as(dbl_p)))
+        return out
+
+    def ensemble_run(self, plan, pos, lnprob, mt_key, mt_pos, n_iterations, a=2.0,
+                     chain=None, lnprob_chain=None, chain_start=0, thin=1,
+                     n_accepted=None):
+        """``n_iterations`` stretch-move iterations of the whole ensemble inside the
+        library (emcee 2.x semantics, numpy RandomState stream; see the header).
+        ``pos`` (k, D), ``lnprob`` (k,), ``mt_key`` (624,) uint32, ``n_accepted`` (k,)
+        are updated in place; ``mt_pos`` is a ``ctypes.c_int32``; ``chain``
+        (k, L, D) / ``lnprob_chain`` (k, L) receive every ``thin``-th iteration from
+        index ``chain_start`` on."""
+        dbl_p = ctypes.POINTER(ctypes.c_double)
+        for arr, dtype in ((pos, np.float64), (lnprob, np.float64), (mt_key, np.uint32),
+                           (chain, np.float64), (lnprob_chain, np.float64),
+                           (n_accepted, np.float64)):
+            if arr is not None and not (isinstance(arr, np.ndarray) and arr.dtype == dtype
+                                        and arr.flags.c_contiguous and arr.flags.writeable):
+                raise ValueError('ensemble_run needs writable C-contiguous arrays of '
+                                 'the documented dtypes (updated in place)')
+        ens = _lib.Ensemble()
+        ens.n_walkers, ens.n_dim = pos.shape
+        if lnprob.shape != (pos.shape[0],) or mt_key.shape != (624,):
+            raise ValueError('lnprob must be (k,), mt_key (624,)')
+        ens.a = float(a)
+        ens.pos = pos.ctypes.data_as(dbl_p)
+        ens.lnprob = lnprob.ctypes.data_as(dbl_p)
+        ens.mt_key = mt_key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+        ens.mt_pos = ctypes.pointer(mt_pos)
+        if chain is not None:
+            if chain.ndim != 3 or chain.shape[0] != pos.shape[0] or \
+                    chain.shape[2] != pos.shape[1]:
+                raise ValueError('chain must be (k, L, D)')
+            ens.chain = chain.ctypes.data_as(dbl_p)
+            ens.chain_len = chain.shape[1]
+        if lnprob_chain is not None:
+            if lnprob_chain.ndim != 2 or lnprob_chain.shape[0] != pos.shape[0] or \
+                    (chain is not None and lnprob_chain.shape[1] != chain.shape[1]):
+                raise ValueError('lnprob_chain must be (k, L)')
+            ens.lnprob_chain = lnprob_chain.ctypes.data_as(dbl_p)
+            ens.chain_len = lnprob_chain.shape[1]
+        ens.chain_start, ens.thin = int(chain_start), int(thin)
+        if n_accepted is not None:
+            if n_accepted.shape != (pos.shape[0],):
+                raise ValueError('n_accepted must be (k,)')
+            ens.n_accepted = n_accepted.ctypes.data_as(dbl_p)
+        code = self._lib.psfmc_ensemble_run(
+            self._handle, ctypes.byref(plan) if plan is not None else None,
+            ctypes.byref(ens), int(n_iterations))
+        if code != 0:
+            message = self._lib.psfmc_last_error().decode('utf-8', 'replace')
+            if 'parameter value was' in message or 'lnprob returned NaN' in message:
+                raise ValueError(message)      # what emcee raises
+            raise _lib.EngineError(code, message)
+
     def lnlike_device(self, theta_ptr, n_batch, ld, lnl_ptr, stream=0,
                       device_slot=0):
         """Asynchronous evaluation on device-resident buffers (raw addresses,

@@ -30,6 +30,22 @@ def print_progress(step, total, label=''):
         print('{}: {:d}%'.format(label, int(100 * (step + 1) / total)))
 
 
+def advance(sampler, pos, lnprob, total, label='', verbose=True):
+    """``total`` sampler iterations from ``pos`` in at most ten ``run_mcmc`` calls, a
+    progress line after each (the reference prints from inside its per-iteration loop,
+    psfMC/fitting.py:66-83; with the loop inside the library -- sampler.py -- a call
+    covers a tenth of the run). Returns the final ``(pos, lnprob)``."""
+    done, chunk = 0, max(1, int(total) // 10)
+    while done < total:
+        count = min(chunk, total - done)
+        pos, lnprob = sampler.run_mcmc(pos, count, lnprob0=lnprob)[:2]
+        sampler.clear_blobs()
+        done += count
+        if verbose:
+            print_progress(done - 1, total, label)
+    return pos, lnprob
+
+
 def check_convergence_autocorr(sampler, min_chain_to_tau_ratio=10, verbose=0):
     """True when the chain is longer than ``min_chain_to_tau_ratio`` integrated
     autocorrelation times of every parameter (cf. analysis/statistics.py:134-155)."""
@@ -145,19 +161,12 @@ def model_galaxy_mcmc(model_file, output_name=None, write_fits=default_filetypes
     db_name = output_name.format('db') + '.fits'
     if not os.path.exists(db_name):
         param_vec = mc_model.init_params_from_priors(chains)
-        for step, result in enumerate(sampler.sample(param_vec, iterations=burn)):
-            param_vec = result[0]
-            sampler.clear_blobs()
-            if verbose:
-                print_progress(step, burn, 'Burning')
+        param_vec, lnprob = advance(sampler, param_vec, None, burn, 'Burning', verbose)
         sampler.reset()
         converged = False
         for sampling_iter in range(max_iterations):
-            for step, result in enumerate(
-                    sampler.sample(param_vec, iterations=iterations)):
-                sampler.clear_blobs()
-                if verbose:
-                    print_progress(step, iterations, 'Sampling')
+            # (every round starts from the end of the burn-in, like the reference's)
+            advance(sampler, param_vec, lnprob, iterations, 'Sampling', verbose)
             if convergence_check(sampler):
                 converged = True
                 break

@@ -236,7 +236,7 @@ class MultiComponentModel(object):
         return out
 
     # -- native evaluation (include/psfmc_b200.h: psfmc_prior_columns / _sum) ------
-    def _native_prior_plan(self):
+    def _native_prior_plan(self, weibull=False):
         """Tables for the library's host-side prior evaluation: Uniform and Normal
         columns are evaluated there (closed forms whose constants -- log(scale), the
         normal's log sqrt(2 pi) -- are computed HERE by numpy/scipy, so only IEEE-exact
@@ -248,17 +248,22 @@ class MultiComponentModel(object):
         groups, others = self._prior_plan
         ndim = self.num_params
         columns = (_lib.PriorColumn * max(ndim, 1))()
-        families = {'uniform_gen': _lib.PRIOR_UNIFORM, 'norm_gen': _lib.PRIOR_NORMAL}
+        families = {'uniform_gen': (_lib.PRIOR_UNIFORM, 0), 'norm_gen': (_lib.PRIOR_NORMAL, 0)}
+        if weibull:
+            # (libm's log / pow: what numpy 1.21 calls; see PSFMC_PRIOR_WEIBULL_MIN)
+            families['weibull_min_gen'] = (_lib.PRIOR_WEIBULL_MIN, 1)
         rest = []
         for group in groups:
-            family = families.get(type(group['dist']).__name__)
-            if family is None or len(group['args']) != 0:
+            family, nargs = families.get(type(group['dist']).__name__, (None, 0))
+            if family is None or len(group['args']) != nargs:
                 rest.append(group)
                 continue
             dist, scale = group['dist'], group['scale'][:, None]
+            args = tuple(arg[:, None] for arg in group['args'])
             with np.errstate(all='ignore'):
-                cond0 = np.broadcast_to(dist._argcheck() & (scale > 0), scale.shape)
+                cond0 = np.broadcast_to(dist._argcheck(*args) & (scale > 0), scale.shape)
                 log_scale = np.log(scale)
+                log_shape = np.log(args[0]) if nargs else None
             for k, col in enumerate(group['cols']):
                 entry = columns[int(col)]
                 entry.family = family
@@ -268,6 +273,9 @@ class MultiComponentModel(object):
                 entry.scale = float(group['scale'][k])
                 entry.log_scale = float(log_scale[k, 0])
                 entry.log_norm = float(_cd._norm_pdf_logC)
+                if nargs:
+                    entry.shape = float(group['args'][0][k])
+                    entry.log_shape = float(log_shape[k, 0])
         terms, rules, start = [], [], 0
         for num, comp in enumerate(self.components):
             where = {}
@@ -320,6 +328,90 @@ class MultiComponentModel(object):
             plan['rules'], plan['n_rules'], plan['n_components'],
             lnprior.ctypes.data_as(dbl_p)))
         return lnprior
+
+    def native_sampler_plan(self, thetas):
+        """The ``psfmc_prior_plan`` for ``psfmc_ensemble_run`` / ``psfmc_lnpost_batch``
+        (include/psfmc_b200.h): Uniform / Normal columns and every sum in the library's
+        host code, bit-identical to scipy; WeibullMinimum columns there too (the C
+        library's log / pow) if that reproduces ``log_priors_batch(thetas)`` to 4 ulps
+        and ``PSFMC_PRIORS_STRICT`` is not 1; every other family, custom priors and
+        discrete priors through a callback into ``_column_logp``. ``thetas``: the
+        validation batch (the starting ensemble). Returns None when no plan reproduces
+        the Python priors -- the caller then keeps the Python loop."""
+        import ctypes
+        from . import _lib
+        cached = getattr(self, '_sampler_plan', None)
+        if cached is not None:
+            return cached or None
+        self._sampler_plan = False
+        thetas = np.ascontiguousarray(np.atleast_2d(thetas), dtype=np.float64)
+        expect = self.log_priors_batch(thetas)
+        if not hasattr(self, '_prior_plan'):
+            return None
+        strict = os.environ.get('PSFMC_PRIORS_STRICT', '0') == '1'
+        dbl_p = ctypes.POINTER(ctypes.c_double)
+        for weibull in ((False,) if strict else (True, False)):
+            try:
+                table = self._native_prior_plan(weibull=weibull)
+            except Exception:
+                continue
+            rest, others = table['rest'], table['others']
+
+            def other_columns(user, theta_p, n_batch, ld, logp_p, ld_logp,
+                              rest=rest, others=others):
+                try:
+                    block = np.ctypeslib.as_array(theta_p, shape=(n_batch, ld))
+                    logp = np.ctypeslib.as_array(logp_p, shape=(n_batch, ld_logp))
+                    self._column_logp(block, rest, others, out=logp)
+                    return 0
+                except Exception:          # never unwind through the C frames
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+
+            for col in [c for g in rest for c in g['cols']] + \
+                    [c for _, cols in others for c in cols]:
+                table['columns'][int(col)].family = _lib.PRIOR_OTHER
+            plan = _lib.PriorPlan()
+            plan.columns = ctypes.cast(table['columns'], ctypes.POINTER(_lib.PriorColumn))
+            plan.terms = ctypes.cast(table['terms'], ctypes.POINTER(_lib.PriorTerm))
+            plan.rules = ctypes.cast(table['rules'], ctypes.POINTER(_lib.PriorRule))
+            plan.n_columns, plan.n_terms = table['ndim'], table['n_terms']
+            plan.n_rules, plan.n_components = table['n_rules'], table['n_components']
+            callback = _lib.OTHER_COLUMNS_FN(other_columns)
+            if rest or others:
+                plan.other_columns = callback
+            holder = {'plan': plan, 'table': table, 'callback': callback,
+                      'weibull_native': weibull, 'python_columns': bool(rest or others)}
+            # validate: lnpost - lnL on the validation batch == the Python priors
+            lib = self.engine._lib
+            got = np.empty(thetas.shape[0])
+            logp = np.empty((thetas.shape[0], max(table['ndim'], 1)))
+            try:
+                _lib.check(lib, lib.psfmc_prior_columns(
+                    table['columns'], table['ndim'], thetas.ctypes.data_as(dbl_p),
+                    thetas.shape[0], thetas.shape[1], logp.ctypes.data_as(dbl_p),
+                    logp.shape[1]))
+                if rest or others:
+                    self._column_logp(thetas, rest, others, out=logp)
+                _lib.check(lib, lib.psfmc_prior_sum(
+                    logp.ctypes.data_as(dbl_p), thetas.shape[0], logp.shape[1],
+                    thetas.ctypes.data_as(dbl_p), thetas.shape[1], table['terms'],
+                    table['n_terms'], table['rules'], table['n_rules'],
+                    table['n_components'], got.ctypes.data_as(dbl_p)))
+            except Exception:
+                continue
+            same = np.array_equal(got, expect, equal_nan=True)
+            if not same and weibull:
+                finite = np.isfinite(expect)
+                same = np.array_equal(np.isfinite(got), finite) and \
+                    np.array_equal(np.isnan(got), np.isnan(expect)) and \
+                    np.all(np.abs(got[finite] - expect[finite]) <=
+                           4 * np.spacing(np.abs(expect[finite])))
+            if same:
+                self._sampler_plan = holder
+                return holder
+        return None
 
     def log_priors_batch(self, thetas):
         """Joint log-prior of every row of ``thetas`` (B, D). Three implementations,

@@ -116,6 +116,24 @@ class BatchPool(object):
         return (np.array([r[0] for r in results], dtype=np.float64),
                 [r[1] for r in results])
 
+    def native_sampler(self, start_positions):
+        """What this package's sampler needs to run its inner loop inside the library
+        (``psfmc_ensemble_run``): ``(engine, prior plan holder)``, or None when the loop
+        has to stay in Python -- blobs wanted, ``PSFMC_NATIVE_SAMPLER=0``, or no prior
+        plan reproduces the Python priors on ``start_positions``
+        (:meth:`MultiComponentModel.native_sampler_plan`)."""
+        import os
+        if self.with_blobs or os.environ.get('PSFMC_NATIVE_SAMPLER', '1') == '0':
+            return None
+        engine = getattr(self.model, 'engine', None)
+        if engine is None or not hasattr(engine, 'ensemble_run') or \
+                not hasattr(self.model, 'native_sampler_plan'):
+            return None
+        holder = self.model.native_sampler_plan(start_positions)
+        if holder is None:
+            return None
+        return engine, holder
+
     # multiprocessing.Pool look-alikes some callers use
     def close(self):
         pass

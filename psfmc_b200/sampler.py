@@ -10,7 +10,17 @@ for the partners, ``rand(Ns)`` for the acceptance -- drawn from a
 The posterior is evaluated through ``pool.map`` once for the starting ensemble and
 then for two sequentially dependent half-ensembles per iteration: those are the
 batches the GPU engine sees.
+
+With a pool that offers ``native_sampler`` (``BatchPool`` without blobs) the iterations
+themselves run inside the library (``psfmc_ensemble_run``, include/psfmc_b200.h): same
+moves, same random stream -- the RandomState's MT19937 state is handed over and taken
+back -- so a seeded chain is the one this module's numpy loop produces (the tests compare
+them bit for bit), at ~50 us instead of ~300 us per half-ensemble of the example's
+250 walkers. ``run_mcmc`` makes ONE library call for all its steps; ``sample`` one per
+iteration (it has to yield in between).
 """
+import ctypes
+
 import numpy as np
 
 __all__ = ['EnsembleSampler', 'AutocorrError', 'integrated_time']
@@ -174,6 +184,40 @@ class EnsembleSampler(object):
             raise ValueError('lnprob returned NaN.')
         return lnprob, blob
 
+    # -- the loop inside the library ------------------------------------------------
+    def _native(self, pos):
+        getter = getattr(self.pool, 'native_sampler', None)
+        if getter is None:
+            return None
+        return getter(pos)
+
+    def _native_advance(self, native, p, lnprob, first, count, start, thin, storechain):
+        """Iterations ``first`` .. ``first + count - 1`` of a sample() call in one
+        library call; p / lnprob / naccepted / chain are updated in place, the random
+        state is taken from and returned to ``self._random``."""
+        engine, holder = native
+        state = self._random.get_state()
+        key = np.array(state[1], dtype=np.uint32)
+        mt_pos = ctypes.c_int32(int(state[2]))
+        if storechain:
+            # emcee stores iteration `it` at start + it // thin when it % thin == 0: skip
+            # ahead to the first such iteration of this call
+            skip = (-first) % thin
+            if skip:
+                done = min(skip, count)
+                engine.ensemble_run(holder['plan'], p, lnprob, key, mt_pos, done, a=self.a,
+                                    n_accepted=self.naccepted)
+                first, count = first + done, count - done
+            if count > 0:
+                engine.ensemble_run(holder['plan'], p, lnprob, key, mt_pos, count, a=self.a,
+                                    chain=self._chain, lnprob_chain=self._lnprob,
+                                    chain_start=start + first // thin, thin=thin,
+                                    n_accepted=self.naccepted)
+        elif count > 0:
+            engine.ensemble_run(holder['plan'], p, lnprob, key, mt_pos, count, a=self.a,
+                                n_accepted=self.naccepted)
+        self._random.set_state((state[0], key, int(mt_pos.value), state[3], state[4]))
+
     def _propose_stretch(self, active, complement, lnprob_active):
         s = np.atleast_2d(active)
         c = np.atleast_2d(complement)
@@ -209,6 +253,20 @@ class EnsembleSampler(object):
                 (self._chain, np.zeros((self.k, nstore, self.dim))), axis=1)
             self._lnprob = np.concatenate(
                 (self._lnprob, np.zeros((self.k, nstore))), axis=1)
+        native = self._native(p) if blobs is None else None
+        if native is not None:
+            single = getattr(self, '_one_call', False)
+            steps = [int(iterations)] if single else [1] * int(iterations)
+            done = 0
+            for count in steps:
+                if count <= 0:
+                    continue
+                self._native_advance(native, p, lnprob, done, count, start, int(thin),
+                                     storechain)
+                done += count
+                self.iterations += count
+                yield p, lnprob, self.random_state
+            return
         halves = (slice(0, halfk), slice(halfk, self.k))
         for it in range(int(iterations)):
             self.iterations += 1
@@ -239,6 +297,11 @@ class EnsembleSampler(object):
 
     def run_mcmc(self, pos0, nsteps, rstate0=None, lnprob0=None, **kwargs):
         results = None
-        for results in self.sample(pos0, lnprob0, rstate0, iterations=nsteps, **kwargs):
-            pass
+        # (with the loop in the library: one call for all steps, one yield at the end)
+        self._one_call = True
+        try:
+            for results in self.sample(pos0, lnprob0, rstate0, iterations=nsteps, **kwargs):
+                pass
+        finally:
+            self._one_call = False
         return results

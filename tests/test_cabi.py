@@ -56,6 +56,10 @@ def test_struct_layout_matches_header(cuda_library, tmp_path):
         'sizeof(psfmc_component), sizeof(psfmc_desc), sizeof(psfmc_info),'
         'offsetof(psfmc_desc, psf_index), offsetof(psfmc_desc, devices),'
         'offsetof(psfmc_info, flops_per_eval), offsetof(psfmc_info, launches_total));'
+        'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(psfmc_prior_column),'
+        'offsetof(psfmc_prior_column, log_shape), sizeof(psfmc_prior_plan),'
+        'offsetof(psfmc_prior_plan, other_columns), sizeof(psfmc_ensemble),'
+        'offsetof(psfmc_ensemble, mt_pos), offsetof(psfmc_ensemble, n_accepted));'
         'return 0;}\n')
     exe = tmp_path / 'layout'
     subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)],
@@ -65,7 +69,11 @@ def test_struct_layout_matches_header(cuda_library, tmp_path):
     want = [ctypes.sizeof(_lib.Slot), ctypes.sizeof(_lib.Component),
             ctypes.sizeof(_lib.Desc), ctypes.sizeof(_lib.Info),
             _lib.Desc.psf_index.offset, _lib.Desc.devices.offset,
-            _lib.Info.flops_per_eval.offset, _lib.Info.launches_total.offset]
+            _lib.Info.flops_per_eval.offset, _lib.Info.launches_total.offset,
+            ctypes.sizeof(_lib.PriorColumn), _lib.PriorColumn.log_shape.offset,
+            ctypes.sizeof(_lib.PriorPlan), _lib.PriorPlan.other_columns.offset,
+            ctypes.sizeof(_lib.Ensemble), _lib.Ensemble.mt_pos.offset,
+            _lib.Ensemble.n_accepted.offset]
     assert got == want
 
 

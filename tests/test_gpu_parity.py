@@ -475,6 +475,44 @@ def test_seeded_run_on_the_j0005_model(cuda_library, c1_golden):
     _seeded_runs_agree(model, start, nburn=40, nkeep=80)
 
 
+@pytest.mark.parametrize('strict', ['1', '0'])
+def test_library_sampler_loop_reproduces_the_numpy_loop(cuda_library, c1_golden, monkeypatch,
+                                                        strict):
+    """psfmc_ensemble_run (the sampler's iterations inside the library) on the J0005-0006
+    model, float32 engine: same seed, same start -> the chain of the numpy loop
+    (sampler.py), bit for bit with the Weibull priors through the callback (strict), with
+    identical positions when they are evaluated in the library with the C library's pow."""
+    from psfmc_b200 import BatchPool
+    from psfmc_b200.sampler import EnsembleSampler
+    monkeypatch.setenv('PSFMC_PRIORS_STRICT', strict)
+    model = model_from_file('j0005/model_c1.py', 'fp32')
+    centre = np.array(c1_golden['theta'][0])
+    nwalk = 250
+    rng = np.random.RandomState(23)
+    start = centre + 1e-3 * rng.standard_normal((nwalk, len(centre))) * \
+        np.maximum(np.abs(centre), 1.0)
+    runs = {}
+    for native in ('0', '1'):
+        monkeypatch.setenv('PSFMC_NATIVE_SAMPLER', native)
+        sampler = EnsembleSampler(nwalk, len(centre), model.log_posterior,
+                                  kwargs={'model': model}, pool=BatchPool(model))
+        sampler._random.seed(11)
+        pos, lnp, _ = sampler.run_mcmc(start, 12)
+        sampler.run_mcmc(pos, 12, lnprob0=lnp, thin=3)
+        runs[native] = (sampler.chain.copy(), sampler.lnprobability.copy(),
+                        sampler.naccepted.copy(), sampler._random.rand(3))
+    assert model._sampler_plan and model._sampler_plan['python_columns'] == (strict == '1')
+    assert runs['1'][0].shape == (nwalk, 16, len(centre))
+    assert 0.05 < runs['0'][2].mean() / 24 < 0.95
+    assert np.array_equal(runs['0'][0], runs['1'][0])
+    assert np.array_equal(runs['0'][2], runs['1'][2])
+    assert np.array_equal(runs['0'][3], runs['1'][3])
+    if strict == '1':
+        assert np.array_equal(runs['0'][1], runs['1'][1])
+    else:
+        np.testing.assert_allclose(runs['1'][1], runs['0'][1], rtol=1e-13)
+
+
 def test_accumulate_on_device_matches_rendered_images(cuda_library, c1_golden):
     """Posterior-image sums accumulated on the device (float32 engine) against the
     individually rendered images; the IVM is summed in variance space."""

@@ -1,0 +1,191 @@
+"""
+The sampler's inner loop inside the library (psfmc_ensemble_run, psfmc_lnpost_batch,
+psfmc_rng_fill; include/psfmc_b200.h) against this package's numpy loop (sampler.py, emcee
+2.x semantics) and against numpy's own random stream. CPU tier: the library is the
+emulator build of the same sources (tests/emu); the GPU tier repeats the chain comparison
+on the real library (test_gpu_parity.py).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import oracle_from_model
+
+
+def _state_arrays(rng):
+    state = rng.get_state()
+    return np.array(state[1], dtype=np.uint32), ctypes.c_int32(int(state[2]))
+
+
+def test_rng_fill_continues_numpys_stream(emu_library):
+    """random_sample and randint(bound) of a RandomState, interleaved, from a handed-over
+    MT19937 state; the state handed back continues numpy's stream."""
+    from psfmc_b200 import _lib
+    lib = _lib.load(emu_library)
+    dbl_p = ctypes.POINTER(ctypes.c_double)
+    u32_p = ctypes.POINTER(ctypes.c_uint32)
+    for seed in (0, 5, 12345):
+        ref = np.random.RandomState(seed)
+        mine = np.random.RandomState(seed)
+        key, pos = _state_arrays(mine)
+        for kind, n, bound in ((0, 700, 0), (1, 333, 125), (1, 10, 1), (0, 5, 0),
+                               (1, 400, 2), (1, 257, 1000), (1, 50, 2 ** 31 + 7),
+                               (1, 64, 4096), (0, 1300, 0)):
+            out = np.empty(n)
+            _lib.check(lib, lib.psfmc_rng_fill(key.ctypes.data_as(u32_p), ctypes.byref(pos),
+                                               kind, n, bound, out.ctypes.data_as(dbl_p)))
+            expect = ref.rand(n) if kind == 0 else ref.randint(bound, size=(n,))
+            assert np.array_equal(out, np.asarray(expect, dtype=np.float64)), (seed, kind, bound)
+        state = mine.get_state()
+        mine.set_state((state[0], key, int(pos.value), state[3], state[4]))
+        assert np.array_equal(mine.rand(10), ref.rand(10))
+        assert np.array_equal(mine.standard_normal(4), ref.standard_normal(4))
+
+
+def _small_model(library, weibull):
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.components import Sersic
+    from psfmc_b200.distributions import Uniform, WeibullMinimum
+    from psfmc_b200.synthetic import synthetic_components
+    size = 16
+    comps = synthetic_components(size, 0 if weibull else 1, dtype=np.float64, psf_size=8)
+    if weibull:
+        centre, box = np.array((size / 2.0, size / 2.0)), np.array((3.0, 3.0))
+        comps.append(Sersic(xy=Uniform(loc=centre - box, scale=2 * box),
+                            mag=Uniform(loc=21, scale=4), reff=Uniform(loc=3, scale=4),
+                            reff_b=Uniform(loc=2, scale=3),
+                            index=WeibullMinimum(c=1.5, scale=4),
+                            angle=Uniform(loc=0, scale=180), angle_degrees=True))
+    return MultiComponentModel(comps, precision='fp64', library=library)
+
+
+def _run(model, start, native, monkeypatch, iterations=5, thin=1, stepwise=False):
+    from psfmc_b200 import BatchPool
+    from psfmc_b200.sampler import EnsembleSampler
+    monkeypatch.setenv('PSFMC_NATIVE_SAMPLER', '1' if native else '0')
+    nwalk, ndim = start.shape
+    sampler = EnsembleSampler(nwalk, ndim, model.log_posterior, kwargs={'model': model},
+                              pool=BatchPool(model))
+    sampler._random.seed(5)
+    if stepwise:
+        yielded = []
+        for pos, lnprob, rstate in sampler.sample(start, iterations=iterations, thin=thin):
+            yielded.append((pos.copy(), lnprob.copy(), rstate[2]))
+        pos, lnprob = yielded[-1][:2]
+    else:
+        pos, lnprob, _ = sampler.run_mcmc(start, iterations, thin=thin)
+        yielded = None
+    return {'pos': pos.copy(), 'lnprob': lnprob.copy(), 'chain': sampler.chain.copy(),
+            'lnprobability': sampler.lnprobability.copy(),
+            'naccepted': sampler.naccepted.copy(), 'iterations': sampler.iterations,
+            'next': sampler._random.rand(4), 'yielded': yielded}
+
+
+@pytest.mark.parametrize('case', ['uniform', 'weibull_strict', 'weibull_native'])
+def test_library_loop_reproduces_the_numpy_loop(emu_library, monkeypatch, case):
+    """Same seed, same start: chain, lnprobability, acceptance counts and the random
+    stream after the run are those of the numpy loop. 'uniform': every prior evaluated in
+    the library; 'weibull_strict': the Weibull column through the callback (bit for bit);
+    'weibull_native': the Weibull column in the library with the C library's log / pow --
+    positions identical, lnprob to the last digits (numpy's SVML pow on AVX-512 hosts)."""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    weibull = case != 'uniform'
+    monkeypatch.setenv('PSFMC_PRIORS_STRICT', '1' if case == 'weibull_strict' else '0')
+    model = _small_model(emu_library, weibull)
+    nwalk = 2 * model.num_params + 2
+    start = draw_walkers_fast(model, nwalk, seed=3)
+    # tighten the ensemble so that a good share of the proposals is accepted
+    start = start[0] + 0.02 * (start - start[0])
+    assert np.all(np.isfinite(model.log_posterior_batch(start)))
+    ref = _run(model, start, False, monkeypatch)
+    got = _run(model, start, True, monkeypatch)
+    holder = model._sampler_plan
+    assert holder, 'the library loop was not used'
+    assert holder['weibull_native'] == (case != 'weibull_strict')
+    assert holder['python_columns'] == (case == 'weibull_strict')
+    assert 0 < ref['naccepted'].sum() < ref['naccepted'].size * ref['iterations']
+    assert np.array_equal(got['chain'], ref['chain'])
+    assert np.array_equal(got['naccepted'], ref['naccepted'])
+    assert np.array_equal(got['next'], ref['next'])
+    assert got['iterations'] == ref['iterations']
+    if case == 'weibull_native':
+        np.testing.assert_allclose(got['lnprobability'], ref['lnprobability'], rtol=1e-13)
+    else:
+        assert np.array_equal(got['lnprobability'], ref['lnprobability'])
+        assert np.array_equal(got['lnprob'], ref['lnprob'])
+    # the stored lnprob is the posterior of the stored position
+    np.testing.assert_allclose(got['lnprobability'][:, -1],
+                               model.log_posterior_batch(got['chain'][:, -1]), rtol=1e-13)
+
+
+def test_library_loop_stepwise_and_thinned(emu_library, monkeypatch):
+    """sample() (one library call per iteration, a yield after each) and thin = 2."""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model = _small_model(emu_library, False)
+    nwalk = 2 * model.num_params + 2
+    start = draw_walkers_fast(model, nwalk, seed=4)
+    start = start[0] + 0.02 * (start - start[0])
+    ref = _run(model, start, False, monkeypatch, iterations=6, thin=2, stepwise=True)
+    got = _run(model, start, True, monkeypatch, iterations=6, thin=2, stepwise=True)
+    assert got['chain'].shape == (nwalk, 3, model.num_params)
+    assert np.array_equal(got['chain'], ref['chain'])
+    assert np.array_equal(got['lnprobability'], ref['lnprobability'])
+    assert len(got['yielded']) == 6
+    for (p1, l1, s1), (p2, l2, s2) in zip(got['yielded'], ref['yielded']):
+        assert np.array_equal(p1, p2) and np.array_equal(l1, l2) and s1 == s2
+    one = _run(model, start, True, monkeypatch, iterations=6, thin=2)
+    assert np.array_equal(one['chain'], ref['chain'])
+    assert np.array_equal(one['next'], ref['next'])
+
+
+def test_lnpost_batch_matches_log_posterior_batch(emu_library):
+    """psfmc_lnpost_batch: priors in the library while the engine computes; rows with a
+    dead prior (reff_b > reff, outside a Uniform) and a dead likelihood come out -inf."""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model = _small_model(emu_library, True)
+    thetas = draw_walkers_fast(model, 12, seed=9)
+    names = model.param_names
+    thetas[1, 0] = 1e3                   # far outside the sky prior's bulk, still finite
+    thetas[2, -1] = 400.0                # angle outside Uniform(0, 180)
+    reff = [i for i, n in enumerate(names) if n.endswith('reff')][0]
+    reff_b = [i for i, n in enumerate(names) if n.endswith('reff_b')][0]
+    thetas[3, reff_b] = thetas[3, reff] + 0.5
+    expect = model.log_posterior_batch(thetas)
+    holder = model.native_sampler_plan(draw_walkers_fast(model, 8, seed=1))
+    assert holder is not None
+    got = model.engine.lnpost(holder['plan'], thetas)
+    assert np.array_equal(np.isfinite(got), np.isfinite(expect))
+    assert not np.isfinite(got[2]) and not np.isfinite(got[3])
+    finite = np.isfinite(expect)
+    np.testing.assert_allclose(got[finite], expect[finite], rtol=1e-13)
+    # against the oracle's lnL + scipy priors
+    oracle = oracle_from_model(model)
+    lnl = oracle.lnlike_batch(thetas[finite])
+    np.testing.assert_allclose(got[finite], lnl + model.log_priors_batch(thetas[finite]),
+                               rtol=1e-9)
+
+
+def test_ensemble_run_rejects_bad_input(emu_library):
+    from psfmc_b200 import _lib
+    model = _small_model(emu_library, False)
+    engine = model.engine
+    ndim = model.num_params
+    key, pos = _state_arrays(np.random.RandomState(1))
+    p = np.zeros((4, ndim))
+    lnp = np.zeros(4)
+    with pytest.raises(_lib.EngineError):     # odd ensemble
+        engine.ensemble_run(None, np.zeros((3, ndim)), np.zeros(3), key, pos, 1)
+    with pytest.raises(_lib.EngineError):     # rows shorter than the program's theta
+        engine.ensemble_run(None, np.zeros((4, ndim - 1)), lnp, key, pos, 1)
+    with pytest.raises(_lib.EngineError):
+        engine.ensemble_run(None, p, lnp, key, pos, 1, a=1.0)
+    with pytest.raises(ValueError):           # not updated in place: refused
+        engine.ensemble_run(None, p.astype(np.float32), lnp, key, pos, 1)
+    # a proposal with an infinite coordinate is emcee's ValueError
+    p = np.ones((4, ndim))
+    p[0, 0] = 1e308
+    p[2, 0] = -1e308
+    p[3, 0] = -1e308
+    with pytest.raises(ValueError, match='infinite'):
+        engine.ensemble_run(None, p, lnp, key, pos, 3)
