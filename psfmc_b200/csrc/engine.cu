@@ -1789,7 +1789,7 @@ struct psfmc_engine {
   std::vector<long long> r_rows;
   // psfmc_ensemble_run / psfmc_lnpost_batch: proposals and their lnL in page-locked memory
   // (stable addresses: the host call is then one replayed graph, no staging copies)
-  PinBuf<double> ens_q, ens_lnl;
+  PinBuf<double> ens_q, ens_lnl, ens_scratch;
 };
 
 // A float32 evaluation that came back non-finite is repeated in float64 on the GPU:
@@ -1875,6 +1875,7 @@ void psfmc_engine_destroy(psfmc_engine *engine) {
 #endif
   engine->ens_q.release();
   engine->ens_lnl.release();
+  engine->ens_scratch.release();
   delete engine->impl;
   delete engine->rescue;
   delete engine->saved;
@@ -2231,12 +2232,14 @@ int psfmc_lnpost_batch(psfmc_engine *engine, const psfmc_prior_plan *priors,
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(engine->impl->first_ordinal);
-  const int bad = engine->ens_lnl.ensure((size_t)n_batch);
+  const int bad = engine->ens_lnl.ensure((size_t)n_batch) ||
+                  engine->ens_scratch.ensure((size_t)n_batch * (size_t)ld);
   cudaSetDevice(prev);
   if (bad) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
   LnlikeCalls calls{engine, ens_begin, ens_end};
   LnpostWork wk;
-  int rc = lnpost_rows(calls, priors, theta, n_batch, ld, engine->ens_lnl.ptr, lnpost_out, wk);
+  int rc = lnpost_rows(calls, priors, theta, n_batch, ld, engine->ens_lnl.ptr, lnpost_out, wk,
+                       engine->ens_scratch.ptr);
   if (rc == -1) return fail(PSFMC_ERR_INVALID_ARG, "the other_columns callback failed");
   return rc;
 }
@@ -2266,11 +2269,14 @@ int psfmc_ensemble_run(psfmc_engine *engine, const psfmc_prior_plan *priors,
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(engine->impl->first_ordinal);
-  const int bad = engine->ens_q.ensure(half * (size_t)ens->n_dim) || engine->ens_lnl.ensure(half);
+  const int bad = engine->ens_q.ensure(half * (size_t)ens->n_dim) ||
+                  engine->ens_lnl.ensure(half) ||
+                  engine->ens_scratch.ensure(half * (size_t)ens->n_dim);
   cudaSetDevice(prev);
   if (bad) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
   LnlikeCalls calls{engine, ens_begin, ens_end};
-  int rc = run_ensemble(calls, priors, ens, n_iterations, engine->ens_q.ptr, engine->ens_lnl.ptr);
+  int rc = run_ensemble(calls, priors, ens, n_iterations, engine->ens_q.ptr, engine->ens_lnl.ptr,
+                        engine->ens_scratch.ptr);
   switch (rc) {
     case PSFMC_ENS_OK: return 0;
     case PSFMC_ENS_CALLBACK:

@@ -24,6 +24,11 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/psfmc_b200.h"
@@ -134,39 +139,222 @@ inline int check_prior_plan(const psfmc_prior_plan *pl, long long ld, const char
   return 0;
 }
 
-struct LnpostWork {
-  std::vector<double> logp, lnprior;
+// A few persistent host threads for the per-row work of large ensembles (the priors of
+// 2048 walkers cost as much host time as their lnL costs GPU time). parallel_rows splits
+// [0, n) into contiguous ranges, the calling thread takes the first.
+class HostPool {
+ public:
+  static HostPool &instance() {
+    static HostPool pool;
+    return pool;
+  }
+  template <typename F>
+  void parallel_rows(long long n, long long min_rows_per_thread, const F &fn) {
+    int parts = (int)(n / (min_rows_per_thread > 0 ? min_rows_per_thread : 1));
+    if (parts > max_threads_) parts = max_threads_;
+    if (parts <= 1) {
+      fn(0ll, n);
+      return;
+    }
+    std::lock_guard<std::mutex> call_guard(call_m_);   // one parallel region at a time
+    ensure_threads(parts - 1);
+    const long long step = (n + parts - 1) / parts;
+    std::function<void(long long, long long)> job = fn;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &job;
+      step_ = step;
+      n_ = n;
+      parts_ = parts;
+      pending_ = parts - 1;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    fn(0ll, step < n ? step : n);
+    std::unique_lock<std::mutex> lk(m_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : threads_)
+      if (t.joinable()) t.join();
+  }
+
+ private:
+  HostPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    max_threads_ = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    if (const char *env = getenv("PSFMC_HOST_THREADS")) {
+      const int v = atoi(env);
+      if (v >= 1 && v <= 64) max_threads_ = v;
+    }
+  }
+  void ensure_threads(int count) {
+    while ((int)threads_.size() < count) {
+      const int index = (int)threads_.size() + 1;
+      threads_.emplace_back([this, index] { loop(index); });
+    }
+  }
+  void loop(int index) {
+    unsigned long long seen = 0;
+    for (;;) {
+      std::function<void(long long, long long)> *job = nullptr;
+      long long lo = 0, hi = 0;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+        if (stop_) return;
+        seen = epoch_;
+        if (index >= parts_) continue;      // not part of this region
+        job = job_;
+        lo = step_ * index;
+        hi = lo + step_ < n_ ? lo + step_ : n_;
+      }
+      if (lo < hi) (*job)(lo, hi);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        --pending_;
+      }
+      done_cv_.notify_one();
+    }
+  }
+  std::mutex m_, call_m_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> threads_;
+  std::function<void(long long, long long)> *job_ = nullptr;
+  long long step_ = 0, n_ = 0;
+  int parts_ = 0, pending_ = 0, max_threads_ = 1;
+  unsigned long long epoch_ = 0;
+  bool stop_ = false;
 };
 
-// lnpost of n rows: the GPU is started on ALL rows, the priors run on this thread
-// meanwhile; rows with a dead prior were evaluated for nothing (models.py:209-211 skips
-// them -- same result, a walker's lnL does not depend on its batch).
+struct LnpostWork {
+  std::vector<double> logp, lnprior;
+  std::vector<long long> alive;     // rows sent to the GPU (when some were left out)
+  std::vector<unsigned char> dead;
+};
+
+// rows up to which a host call is served by replaying a captured graph (engine.cu:
+// psfmc_lnlike_batch_begin): the batch size must not change from call to call there
+#define PSFMC_ENS_FIXED_BATCH 160
+
+// lnpost of n rows.
+//  1. the closed-form prior columns (Uniform, Normal) and the component rules decide which
+//     rows are dead before the GPU is started: a dead row's lnL is never looked at
+//     (psfMC/models.py:209-211 returns before evaluating it). Large batches leave the dead
+//     rows out (fewer rows on the GPU); batches of at most PSFMC_ENS_FIXED_BATCH rows keep
+//     their size and carry a copy of a live row in the place of a dead one (a dead row's
+//     parameters may be anything -- negative radii, a NaN-producing index -- and would be
+//     repeated in float64 for nothing). `scratch` [n][ld] (page-locked) takes those rows;
+//  2. the GPU is started (begin); while it works: the prior columns with library calls
+//     (Weibull), the caller's columns (callback), the sums, and `overlap()` -- the
+//     sampler's own logarithms;
+//  3. end; lnpost = lnL + lnprior where both are finite, else -inf (models.py:238-243).
 // Returns 0, an engine error code (> 0, message already set), or -1: the callback failed.
 inline int lnpost_rows(const LnlikeCalls &eng, const psfmc_prior_plan *pl, const double *theta,
-                       long long n, long long ld, double *lnl, double *lnpost, LnpostWork &wk) {
+                       long long n, long long ld, double *lnl, double *lnpost, LnpostWork &wk,
+                       double *scratch, const std::function<void()> *overlap = nullptr) {
   if (n <= 0) return 0;
-  int rc = eng.begin(eng.self, theta, n, ld, lnl);
-  if (rc) return rc;
-  int cb = 0;
+  HostPool &pool = HostPool::instance();
+  const long long ldp = (pl && pl->n_columns > 0) ? pl->n_columns : 1;
+  bool other = false, costly = false;
+  long long n_alive = n;
   if (pl) {
-    const long long ldp = pl->n_columns > 0 ? pl->n_columns : 1;
     wk.logp.resize((size_t)n * ldp);
     wk.lnprior.resize((size_t)n);
-    prior_columns_host(pl->columns, pl->n_columns, theta, n, ld, wk.logp.data(), ldp);
-    bool other = false;
-    for (int c = 0; c < pl->n_columns; ++c) other |= pl->columns[c].family == PSFMC_PRIOR_OTHER;
-    if (other) cb = pl->other_columns(pl->user, theta, n, ld, wk.logp.data(), ldp);
-    if (!cb)
-      prior_sum_host(wk.logp.data(), n, ldp, theta, ld, pl->terms, pl->n_terms, pl->rules,
-                     pl->n_rules, pl->n_components, wk.lnprior.data());
+    wk.dead.assign((size_t)n, 0);
+    for (int c = 0; c < pl->n_columns; ++c) {
+      other |= pl->columns[c].family == PSFMC_PRIOR_OTHER;
+      costly |= pl->columns[c].family == PSFMC_PRIOR_WEIBULL_MIN;
+    }
+    double *logp = wk.logp.data();
+    unsigned char *dead = wk.dead.data();
+    pool.parallel_rows(n, 1024, [&](long long lo, long long hi) {
+      prior_columns_host(pl->columns, pl->n_columns, theta + lo * ld, hi - lo, ld, logp + lo * ldp,
+                         ldp, PSFMC_PRIOR_FAMILIES_CHEAP);
+      for (long long b = lo; b < hi; ++b) {
+        bool d = false;
+        for (int c = 0; c < pl->n_columns; ++c) {
+          const int f = pl->columns[c].family;
+          if (f == PSFMC_PRIOR_UNIFORM || f == PSFMC_PRIOR_NORMAL)
+            d |= !std::isfinite(logp[b * ldp + c]);
+        }
+        for (int r = 0; r < pl->n_rules && !d; ++r) {
+          const psfmc_prior_rule &ru = pl->rules[r];
+          const double a = ru.a_index >= 0 ? theta[b * ld + ru.a_index] : ru.a_value;
+          const double bb = ru.b_index >= 0 ? theta[b * ld + ru.b_index] : ru.b_value;
+          d |= bb > a;
+        }
+        dead[b] = d ? 1 : 0;
+      }
+    });
+    n_alive = 0;
+    for (long long b = 0; b < n; ++b) n_alive += dead[b] ? 0 : 1;
   }
-  rc = eng.end(eng.self);   // (always: the batch in flight must be finished)
+  const double *gpu_theta = theta;
+  long long gpu_n = n;
+  bool compacted = false;
+  if (n_alive < n && n_alive > 0 && scratch) {
+    if (n <= PSFMC_ENS_FIXED_BATCH) {
+      long long first = 0;
+      while (wk.dead[first]) ++first;
+      for (long long b = 0; b < n; ++b)
+        memcpy(scratch + b * ld, theta + (wk.dead[b] ? first : b) * ld, (size_t)ld * sizeof(double));
+    } else {
+      wk.alive.clear();
+      for (long long b = 0; b < n; ++b)
+        if (!wk.dead[b]) {
+          memcpy(scratch + (long long)wk.alive.size() * ld, theta + b * ld,
+                 (size_t)ld * sizeof(double));
+          wk.alive.push_back(b);
+        }
+      gpu_n = n_alive;
+      compacted = true;
+    }
+    gpu_theta = scratch;
+  }
+  int rc = 0;
+  const bool launched = n_alive > 0;
+  if (launched && (rc = eng.begin(eng.self, gpu_theta, gpu_n, ld, lnl))) return rc;
+  int cb = 0;
+  if (pl) {
+    double *logp = wk.logp.data();
+    if (costly)
+      pool.parallel_rows(n, 256, [&](long long lo, long long hi) {
+        prior_columns_host(pl->columns, pl->n_columns, theta + lo * ld, hi - lo, ld,
+                           logp + lo * ldp, ldp, 1u << PSFMC_PRIOR_WEIBULL_MIN);
+      });
+    if (other) cb = pl->other_columns(pl->user, theta, n, ld, logp, ldp);
+    if (!cb)
+      pool.parallel_rows(n, 1024, [&](long long lo, long long hi) {
+        prior_sum_host(logp + lo * ldp, hi - lo, ldp, theta + lo * ld, ld, pl->terms,
+                       pl->n_terms, pl->rules, pl->n_rules, pl->n_components,
+                       wk.lnprior.data() + lo);
+      });
+  }
+  if (overlap && *overlap) (*overlap)();
+  if (launched) rc = eng.end(eng.self);   // (always: the batch in flight must be finished)
   if (rc) return rc;
   if (cb) return -1;
+  if (compacted) {
+    for (long long b = 0; b < n; ++b) lnpost[b] = -INFINITY;
+    for (size_t i = 0; i < wk.alive.size(); ++i) {
+      const long long b = wk.alive[i];
+      const double lp = wk.lnprior[b], sum = lnl[i] + lp;
+      lnpost[b] = (std::isfinite(lp) && std::isfinite(lnl[i])) ? sum : -INFINITY;
+    }
+    return 0;
+  }
   for (long long b = 0; b < n; ++b) {
     const double lp = pl ? wk.lnprior[b] : 0.0;
-    const double sum = lnl[b] + lp;
-    lnpost[b] = (std::isfinite(lp) && std::isfinite(lnl[b])) ? sum : -INFINITY;
+    const bool gone = !launched || (pl && wk.dead[b]);
+    const double sum = gone ? -INFINITY : lnl[b] + lp;
+    lnpost[b] = (!gone && std::isfinite(lp) && std::isfinite(lnl[b])) ? sum : -INFINITY;
   }
   return 0;
 }
@@ -178,23 +366,28 @@ inline int lnpost_rows(const LnlikeCalls &eng, const psfmc_prior_plan *pl, const
 #define PSFMC_ENS_POS_NAN (-3)
 #define PSFMC_ENS_LNPROB_NAN (-4)
 
-// q, lnl: [k/2][D] / [k/2] buffers the engine reads / writes (page-locked where the caller
-// can: the engine then skips its staging copies and replays one captured graph per call)
+// q, scratch: [k/2][D], lnl: [k/2] buffers the engine reads / writes (page-locked where the
+// caller can: the engine then skips its staging copies and replays one captured graph per
+// call)
 inline int run_ensemble(const LnlikeCalls &eng, const psfmc_prior_plan *pl, psfmc_ensemble *e,
-                        long long n_iter, double *q, double *lnl) {
+                        long long n_iter, double *q, double *lnl, double *scratch) {
   const long long k = e->n_walkers, D = e->n_dim, half = k / 2;
   NumpyMT19937 mt{e->mt_key, e->mt_pos};
-  std::vector<double> zz((size_t)half), newlnp((size_t)half);
+  std::vector<double> zz((size_t)half), newlnp((size_t)half), lzz((size_t)half),
+      lu((size_t)half);
   std::vector<long long> partner((size_t)half);
   LnpostWork wk;
   const double a = e->a, dm1 = (double)D - 1.0;
   const long long thin = e->thin > 0 ? e->thin : 1;
+  HostPool &pool = HostPool::instance();
   for (long long it = 0; it < n_iter; ++it) {
     for (int h = 0; h < 2; ++h) {
       const long long s0 = h == 0 ? 0 : half, c0 = h == 0 ? half : 0;
       const long long ns = h == 0 ? half : k - half, nc = k - ns;
       double *s = e->pos + s0 * D;
       const double *c = e->pos + c0 * D;
+      // the half-step's draws in emcee's order: rand(Ns), randint(Nc, size=Ns), then -- after
+      // the posterior call, which draws nothing -- rand(Ns) for the acceptance
       for (long long i = 0; i < ns; ++i) {
         volatile double t = (a - 1.0) * mt.next_double();   // (no contraction into an FMA)
         const double t1 = t + 1.0;
@@ -202,31 +395,45 @@ inline int run_ensemble(const LnlikeCalls &eng, const psfmc_prior_plan *pl, psfm
         zz[i] = sq / a;
       }
       for (long long i = 0; i < ns; ++i) partner[i] = (long long)mt.next_bounded((uint32_t)nc);
-      bool has_inf = false, has_nan = false;
-      for (long long i = 0; i < ns; ++i) {
-        const double *cp = c + partner[i] * D;
-        const double *sp = s + i * D;
-        double *qp = q + i * D;
-        const double z = zz[i];
-        for (long long j = 0; j < D; ++j) {
-          volatile double m = z * (cp[j] - sp[j]);
-          const double v = cp[j] - m;
-          qp[j] = v;
-          has_inf |= std::isinf(v);
-          has_nan |= v != v;
+      for (long long i = 0; i < ns; ++i) lu[i] = mt.next_double();
+      std::atomic<int> bad_inf{0}, bad_nan{0};
+      pool.parallel_rows(ns, 1024, [&](long long lo, long long hi) {
+        bool has_inf = false, has_nan = false;
+        for (long long i = lo; i < hi; ++i) {
+          const double *cp = c + partner[i] * D;
+          const double *sp = s + i * D;
+          double *qp = q + i * D;
+          const double z = zz[i];
+          for (long long j = 0; j < D; ++j) {
+            volatile double m = z * (cp[j] - sp[j]);
+            const double v = cp[j] - m;
+            qp[j] = v;
+            has_inf |= std::isinf(v);
+            has_nan |= v != v;
+          }
         }
-      }
-      if (has_inf) return PSFMC_ENS_POS_INF;   // emcee: ValueError
-      if (has_nan) return PSFMC_ENS_POS_NAN;
-      int rc = lnpost_rows(eng, pl, q, ns, D, lnl, newlnp.data(), wk);
+        if (has_inf) bad_inf = 1;
+        if (has_nan) bad_nan = 1;
+      });
+      if (bad_inf) return PSFMC_ENS_POS_INF;   // emcee: ValueError
+      if (bad_nan) return PSFMC_ENS_POS_NAN;
+      // the logarithms of the acceptance test run while the GPU computes
+      const std::function<void()> overlap = [&]() {
+        pool.parallel_rows(ns, 512, [&](long long lo, long long hi) {
+          for (long long i = lo; i < hi; ++i) {
+            lzz[i] = dm1 * log(zz[i]);
+            lu[i] = log(lu[i]);
+          }
+        });
+      };
+      int rc = lnpost_rows(eng, pl, q, ns, D, lnl, newlnp.data(), wk, scratch, &overlap);
       if (rc) return rc;
       double *lnp = e->lnprob + s0;
       for (long long i = 0; i < ns; ++i) {
         if (newlnp[i] != newlnp[i]) return PSFMC_ENS_LNPROB_NAN;
-        volatile double dl = dm1 * log(zz[i]);
-        const double lnpdiff = (dl + newlnp[i]) - lnp[i];
-        const double lu = log(mt.next_double());
-        if (lnpdiff > lu) {
+        volatile double part = lzz[i] + newlnp[i];
+        const double lnpdiff = part - lnp[i];
+        if (lnpdiff > lu[i]) {
           lnp[i] = newlnp[i];
           memcpy(s + i * D, q + i * D, (size_t)D * sizeof(double));
           if (e->n_accepted) e->n_accepted[s0 + i] += 1.0;

@@ -461,6 +461,17 @@ class MultiComponentModel(object):
         are not sent to the GPU (cf. models.py:209-211).
         """
         thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        # priors and lnL in ONE library call (psfmc_lnpost_batch: closed-form priors first,
+        # dead rows left out, the rest of the priors while the GPU computes) once a prior
+        # plan has reproduced the Python priors on a batch (native_sampler_plan);
+        # PSFMC_NATIVE_SAMPLER=0 keeps the Python path below
+        if os.environ.get('PSFMC_NATIVE_SAMPLER', '1') != '0' and \
+                hasattr(self.engine, 'lnpost'):
+            holder = getattr(self, '_sampler_plan', None)
+            if holder is None and thetas.shape[0] >= 2:
+                holder = self.native_sampler_plan(thetas)
+            if holder:
+                return self.engine.lnpost(holder['plan'], thetas)
         if thetas.shape[0] >= self.overlap_min_batch:
             # large batches: the GPU works on ALL rows (psfmc_lnlike_batch_begin returns
             # once they are enqueued) while the priors are evaluated here; rows with a

@@ -166,6 +166,32 @@ def test_lnpost_batch_matches_log_posterior_batch(emu_library):
                                rtol=1e-9)
 
 
+def test_lnpost_batch_leaves_dead_rows_out(emu_library):
+    """More rows than a fixed-size (graph) batch: rows whose closed-form priors are dead
+    are not sent to the engine at all, the others come back in their places; an all-dead
+    batch makes no engine call."""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model = _small_model(emu_library, True)
+    thetas = draw_walkers_fast(model, 1300, seed=11)   # (several host threads)
+    rng = np.random.RandomState(2)
+    kill = rng.rand(1300) < 0.3
+    thetas[kill, -1] = -5.0 - rng.rand(kill.sum())        # angle below Uniform(0, 180)
+    # a dead row with parameters the engine could not digest: never evaluated
+    thetas[np.flatnonzero(kill)[0], :] = np.nan
+    thetas[np.flatnonzero(kill)[0], -1] = -1.0
+    holder = model.native_sampler_plan(draw_walkers_fast(model, 8, seed=1))
+    before = model.engine.info()['launches_total']
+    got = model.engine.lnpost(holder['plan'], thetas)
+    assert np.all(np.isneginf(got[kill])) and np.all(np.isfinite(got[~kill]))
+    expect = model.log_posterior_batch(thetas[~kill])
+    np.testing.assert_allclose(got[~kill], expect, rtol=1e-13)
+    launched = model.engine.info()['launches_total']
+    assert launched > before
+    dead = thetas[kill]
+    assert np.all(np.isneginf(model.engine.lnpost(holder['plan'], dead)))
+    assert model.engine.info()['launches_total'] == launched
+
+
 def test_ensemble_run_rejects_bad_input(emu_library):
     from psfmc_b200 import _lib
     model = _small_model(emu_library, False)
