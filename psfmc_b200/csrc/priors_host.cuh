@@ -26,7 +26,10 @@ namespace psfmc {
 #define PSFMC_PRIOR_FAMILIES_CHEAP ((1u << PSFMC_PRIOR_UNIFORM) | (1u << PSFMC_PRIOR_NORMAL))
 inline void prior_columns_host(const psfmc_prior_column *cols, int n_cols, const double *theta,
                                long long n_batch, long long ld, double *logp,
-                               long long ld_out, unsigned families = PSFMC_PRIOR_FAMILIES_ALL) {
+                               long long ld_out, unsigned families = PSFMC_PRIOR_FAMILIES_ALL,
+                               unsigned char *dead = nullptr) {
+  // dead (optional, [n_batch], zeroed by the caller): set to 1 where an evaluated column is
+  // not finite
   // blocks of rows, column by column inside a block: the family switch and the constants
   // stay out of the inner loop, the block's theta rows stay in the L1 cache
   const long long BLOCK = 128;
@@ -41,6 +44,8 @@ inline void prior_columns_host(const psfmc_prior_column *cols, int n_cols, const
       const double loc = pc.loc, scale = pc.scale;
       if (!pc.valid) {                                 // rv_continuous.badvalue
         for (long long b = b0; b < b1; ++b) out[b * ld_out] = NAN;
+        if (dead)
+          for (long long b = b0; b < b1; ++b) dead[b] = 1;
         continue;
       }
       if (pc.family == PSFMC_PRIOR_UNIFORM) {
@@ -98,6 +103,11 @@ inline void prior_columns_host(const psfmc_prior_column *cols, int n_cols, const
           out[b * ld_out] = v;
         }
       }
+      if (dead)
+        for (long long b = b0; b < b1; ++b) {
+          const double v = out[b * ld_out];
+          if (!(v - v == 0.0)) dead[b] = 1;          // -inf, NaN (and +inf): not finite
+        }
     }
   }
 }

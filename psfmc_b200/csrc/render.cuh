@@ -88,60 +88,22 @@ __device__ __forceinline__ float sersic_pixel_f32(const SersicF32 &s, float x, f
 
 __device__ __forceinline__ double sersic_pixel(const double *d, double x, double y);
 
-// One G-lane GROUP per (walker, component): theta -> derived constants, float64.
-// The lanes of a group share the scalar work and split the incomplete-gamma series
-// of the Sersic kappa (devmath.cuh) and the point-source stamp taps; the four
-// groups of a warp walk through the same shuffles (groups without a Sersic idle).
-//   grid = ceil(G * B * n_components / blockDim), blockDim a multiple of 32
-// wscale[b] receives the packing scale of the walker (see below);
-// psf_sel[b] receives the rint-ed PSF index (psfMC/distributions.py:130-138), or
-// -1 when it is out of range (the prior is -inf there; the walker gets -inf).
-// The program travels as a kernel parameter (constant bank): its per-slot lookups
-// are then constant loads instead of dependent global loads.
+// The work of ONE G-lane group: component c of walker b, theta row `th` -> derived
+// constants (see prepare_kernel, which calls it for a whole batch; the low-latency
+// instance of the fused 128 x 128 kernel calls it for its own walker, one warp per
+// component). All lanes of a warp must call it together (shuffles); groups that are
+// not `live` take part in them and write nothing.
 template <int G>
-__global__ void prepare_kernel(const __grid_constant__ Program prog_c,
-                               const double *__restrict__ theta, long long n_batch,
-                               long long ld, int H, int W, double *__restrict__ derived,
-                               int *__restrict__ psf_sel, double *__restrict__ wscale,
-                               float *__restrict__ rconst, int stage,
-                               int *__restrict__ hot = nullptr) {
-  // stage: the theta rows of this CTA's walkers go through shared memory first, read
-  // once with coalesced loads. (Tried on the B200: handing the kernel the caller's
-  // page-locked HOST rows instead of copying them first -- per C-ABI call 70.6 us against
-  // 57.8 us with the H2D copy in front at 100 walkers, 120.6 / 113.4 us at 512, 304 / 303
-  // us at 2048: reads over the bus from inside a kernel cost more than the copy engine.)
-  PSFMC_DYN_SMEM(smem_raw);
-  const Program *prog = &prog_c;
+__device__ __forceinline__ void prepare_group(const Program *prog, const double *th,
+                                              long long b, int c, int glane, bool live, int H,
+                                              int W, double *__restrict__ derived,
+                                              int *__restrict__ psf_sel,
+                                              double *__restrict__ wscale,
+                                              float *__restrict__ rconst,
+                                              int *__restrict__ hot) {
   const int ncomp_prog = prog->n_components;
-  const int ncomp = ncomp_prog > 0 ? ncomp_prog : 1;   // an empty model still gets its
-                                                       // per-walker PSF index and scale
-  const int glane = threadIdx.x & (G - 1);
-  // Groups are numbered component-major, every component's run padded to whole CTAs:
-  // gid = c * n_pad + b. A warp then holds groups of ONE component kind (the Sky, point
-  // source and Sersic branches below no longer run one after the other in every warp)
-  // and a CTA the same component of consecutive walkers.
-  const int gpc = (int)blockDim.x / G;
-  const long long n_pad = (n_batch + gpc - 1) / gpc * gpc;
-  const long long gid0 = (long long)blockIdx.x * gpc;
-  const long long gid = gid0 + threadIdx.x / G;
-  const int c = (int)(gid / n_pad);
-  const long long b0 = gid0 - (long long)c * n_pad;   // the CTA's first walker: always live
-  long long b = gid - (long long)c * n_pad;
-  const bool live = b < n_batch;
-  if (!live) b = b0;                        // idle groups shadow the CTA's first group,
-                                            // write nothing
+  const int ncomp = ncomp_prog > 0 ? ncomp_prog : 1;
   const bool writer = live && (glane == 0);
-  const double *th = theta + b * ld;
-  if (stage) {
-    double *th_s = reinterpret_cast<double *>(smem_raw);
-    long long b1 = b0 + gpc;
-    if (b1 > n_batch) b1 = n_batch;
-    const long long nel = (b1 - b0) * ld;
-    const double *src = theta + b0 * ld;
-    for (long long e = threadIdx.x; e < nel; e += blockDim.x) th_s[e] = src[e];
-    __syncthreads();
-    th = th_s + (b - b0) * ld;
-  }
   double *out = derived + (b * ncomp + c) * PSFMC_DERIVED_STRIDE;
   const int kind = c < ncomp_prog ? prog->kind[c] : -1;
   const int flags = c < ncomp_prog ? prog->flags[c] : 0;
@@ -312,6 +274,62 @@ __global__ void prepare_kernel(const __grid_constant__ Program prog_c,
       rc[8] = s.p; rc[9] = s.c0; rc[10] = s.c1; rc[11] = s.kq;
     }
   }
+}
+
+// One G-lane GROUP per (walker, component): theta -> derived constants, float64.
+// The lanes of a group share the scalar work and split the incomplete-gamma series
+// of the Sersic kappa (devmath.cuh) and the point-source stamp taps; the four
+// groups of a warp walk through the same shuffles (groups without a Sersic idle).
+//   grid = ceil(G * B * n_components / blockDim), blockDim a multiple of 32
+// wscale[b] receives the packing scale of the walker (see below);
+// psf_sel[b] receives the rint-ed PSF index (psfMC/distributions.py:130-138), or
+// -1 when it is out of range (the prior is -inf there; the walker gets -inf).
+// The program travels as a kernel parameter (constant bank): its per-slot lookups
+// are then constant loads instead of dependent global loads.
+template <int G>
+__global__ void prepare_kernel(const __grid_constant__ Program prog_c,
+                               const double *__restrict__ theta, long long n_batch,
+                               long long ld, int H, int W, double *__restrict__ derived,
+                               int *__restrict__ psf_sel, double *__restrict__ wscale,
+                               float *__restrict__ rconst, int stage,
+                               int *__restrict__ hot = nullptr) {
+  // stage: the theta rows of this CTA's walkers go through shared memory first, read
+  // once with coalesced loads. (Tried on the B200: handing the kernel the caller's
+  // page-locked HOST rows instead of copying them first -- per C-ABI call 70.6 us against
+  // 57.8 us with the H2D copy in front at 100 walkers, 120.6 / 113.4 us at 512, 304 / 303
+  // us at 2048: reads over the bus from inside a kernel cost more than the copy engine.)
+  PSFMC_DYN_SMEM(smem_raw);
+  const Program *prog = &prog_c;
+  const int ncomp_prog = prog->n_components;
+  const int ncomp = ncomp_prog > 0 ? ncomp_prog : 1;   // an empty model still gets its
+                                                       // per-walker PSF index and scale
+  const int glane = threadIdx.x & (G - 1);
+  // Groups are numbered component-major, every component's run padded to whole CTAs:
+  // gid = c * n_pad + b. A warp then holds groups of ONE component kind (the Sky, point
+  // source and Sersic branches below no longer run one after the other in every warp)
+  // and a CTA the same component of consecutive walkers.
+  const int gpc = (int)blockDim.x / G;
+  const long long n_pad = (n_batch + gpc - 1) / gpc * gpc;
+  const long long gid0 = (long long)blockIdx.x * gpc;
+  const long long gid = gid0 + threadIdx.x / G;
+  const int c = (int)(gid / n_pad);
+  const long long b0 = gid0 - (long long)c * n_pad;   // the CTA's first walker: always live
+  long long b = gid - (long long)c * n_pad;
+  const bool live = b < n_batch;
+  if (!live) b = b0;                        // idle groups shadow the CTA's first group,
+                                            // write nothing
+  const double *th = theta + b * ld;
+  if (stage) {
+    double *th_s = reinterpret_cast<double *>(smem_raw);
+    long long b1 = b0 + gpc;
+    if (b1 > n_batch) b1 = n_batch;
+    const long long nel = (b1 - b0) * ld;
+    const double *src = theta + b0 * ld;
+    for (long long e = threadIdx.x; e < nel; e += blockDim.x) th_s[e] = src[e];
+    __syncthreads();
+    th = th_s + (b - b0) * ld;
+  }
+  prepare_group<G>(prog, th, b, c, glane, live, H, W, derived, psf_sel, wscale, rconst, hot);
 }
 
 // kappa at n_nodes values of a = 2n by the iteration (one warp per node): used once at

@@ -24,7 +24,11 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -166,19 +170,22 @@ class HostPool {
       step_ = step;
       n_ = n;
       parts_ = parts;
-      pending_ = parts - 1;
-      ++epoch_;
+      pending_.store(parts - 1, std::memory_order_relaxed);
+      epoch_.fetch_add(1, std::memory_order_release);
     }
     cv_.notify_all();
     fn(0ll, step < n ? step : n);
-    std::unique_lock<std::mutex> lk(m_);
-    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    // the regions are short (tens of microseconds): spin for the others
+    for (unsigned spins = 0; pending_.load(std::memory_order_acquire) != 0; ++spins) {
+      if (spins > 4096) std::this_thread::yield();
+      else cpu_relax();
+    }
     job_ = nullptr;
   }
   ~HostPool() {
     {
       std::lock_guard<std::mutex> lk(m_);
-      stop_ = true;
+      stop_.store(true);
     }
     cv_.notify_all();
     for (auto &t : threads_)
@@ -186,9 +193,14 @@ class HostPool {
   }
 
  private:
+  static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
   HostPool() {
     unsigned hw = std::thread::hardware_concurrency();
-    max_threads_ = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    max_threads_ = hw >= 16 ? 8 : (hw >= 8 ? 4 : (hw >= 4 ? 2 : 1));
     if (const char *env = getenv("PSFMC_HOST_THREADS")) {
       const int v = atoi(env);
       if (v >= 1 && v <= 64) max_threads_ = v;
@@ -200,40 +212,84 @@ class HostPool {
       threads_.emplace_back([this, index] { loop(index); });
     }
   }
+  // A worker spins for a short while after a region (the next one of the same posterior
+  // call follows within microseconds), then sleeps on the condition variable.
   void loop(int index) {
     unsigned long long seen = 0;
     for (;;) {
+      bool changed = false;
+      for (int spins = 0; spins < 20000; ++spins) {
+        if (stop_.load(std::memory_order_relaxed) ||
+            epoch_.load(std::memory_order_acquire) != seen) {
+          changed = true;
+          break;
+        }
+        cpu_relax();
+      }
+      if (!changed) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] {
+          return stop_.load() || epoch_.load(std::memory_order_acquire) != seen;
+        });
+      }
+      if (stop_.load()) return;
       std::function<void(long long, long long)> *job = nullptr;
       long long lo = 0, hi = 0;
       {
-        std::unique_lock<std::mutex> lk(m_);
-        cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
-        if (stop_) return;
-        seen = epoch_;
+        // (the region's parameters were published before the epoch moved; taking the
+        // mutex orders this read after a region that is still being set up)
+        std::lock_guard<std::mutex> lk(m_);
+        seen = epoch_.load(std::memory_order_acquire);
         if (index >= parts_) continue;      // not part of this region
         job = job_;
         lo = step_ * index;
         hi = lo + step_ < n_ ? lo + step_ : n_;
       }
-      if (lo < hi) (*job)(lo, hi);
-      {
-        std::lock_guard<std::mutex> lk(m_);
-        --pending_;
-      }
-      done_cv_.notify_one();
+      if (job && lo < hi) (*job)(lo, hi);
+      pending_.fetch_sub(1, std::memory_order_release);
     }
   }
   std::mutex m_, call_m_;
-  std::condition_variable cv_, done_cv_;
+  std::condition_variable cv_;
   std::vector<std::thread> threads_;
   std::function<void(long long, long long)> *job_ = nullptr;
   long long step_ = 0, n_ = 0;
-  int parts_ = 0, pending_ = 0, max_threads_ = 1;
-  unsigned long long epoch_ = 0;
-  bool stop_ = false;
+  int parts_ = 0, max_threads_ = 1;
+  std::atomic<int> pending_{0};
+  std::atomic<unsigned long long> epoch_{0};
+  std::atomic<bool> stop_{false};
+};
+
+// PSFMC_ENS_PROFILE=1: where the host time of psfmc_ensemble_run goes (stderr, per run)
+struct EnsProfile {
+  bool on = false;
+  double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long calls = 0, rows = 0, rows_gpu = 0;
+  double t_begin = 0.0;
+  EnsProfile() {
+    const char *env = getenv("PSFMC_ENS_PROFILE");
+    on = env && env[0] == '1';
+    if (on) t_begin = now();
+  }
+  static double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch())
+        .count();
+  }
+  void report(const char *what) {
+    if (!on || !calls) return;
+    fprintf(stderr,
+            "[psfmc] %s: %lld posterior calls, %lld rows (%lld on the GPU); per call (us): "
+            "draws+proposals %.1f, closed-form priors %.1f, begin %.1f, priors behind the GPU "
+            "%.1f, logs behind the GPU %.1f, wait %.1f, combine+accept %.1f, store %.1f; "
+            "whole run %.1f\n",
+            what, calls, rows, rows_gpu, 1e6 * t[0] / calls, 1e6 * t[1] / calls,
+            1e6 * t[2] / calls, 1e6 * t[3] / calls, 1e6 * t[4] / calls, 1e6 * t[5] / calls,
+            1e6 * t[6] / calls, 1e6 * t[7] / calls, 1e6 * (now() - t_begin) / calls);
+  }
 };
 
 struct LnpostWork {
+  EnsProfile prof;
   std::vector<double> logp, lnprior;
   std::vector<long long> alive;     // rows sent to the GPU (when some were left out)
   std::vector<unsigned char> dead;
@@ -261,6 +317,14 @@ inline int lnpost_rows(const LnlikeCalls &eng, const psfmc_prior_plan *pl, const
                        double *scratch, const std::function<void()> *overlap = nullptr) {
   if (n <= 0) return 0;
   HostPool &pool = HostPool::instance();
+  EnsProfile &pf = wk.prof;
+  double tm = pf.on ? EnsProfile::now() : 0.0;
+  auto lap = [&](int slot) {
+    if (!pf.on) return;
+    const double t = EnsProfile::now();
+    pf.t[slot] += t - tm;
+    tm = t;
+  };
   const long long ldp = (pl && pl->n_columns > 0) ? pl->n_columns : 1;
   bool other = false, costly = false;
   long long n_alive = n;
@@ -274,23 +338,16 @@ inline int lnpost_rows(const LnlikeCalls &eng, const psfmc_prior_plan *pl, const
     }
     double *logp = wk.logp.data();
     unsigned char *dead = wk.dead.data();
-    pool.parallel_rows(n, 1024, [&](long long lo, long long hi) {
+    pool.parallel_rows(n, 512, [&](long long lo, long long hi) {
       prior_columns_host(pl->columns, pl->n_columns, theta + lo * ld, hi - lo, ld, logp + lo * ldp,
-                         ldp, PSFMC_PRIOR_FAMILIES_CHEAP);
-      for (long long b = lo; b < hi; ++b) {
-        bool d = false;
-        for (int c = 0; c < pl->n_columns; ++c) {
-          const int f = pl->columns[c].family;
-          if (f == PSFMC_PRIOR_UNIFORM || f == PSFMC_PRIOR_NORMAL)
-            d |= !std::isfinite(logp[b * ldp + c]);
-        }
-        for (int r = 0; r < pl->n_rules && !d; ++r) {
-          const psfmc_prior_rule &ru = pl->rules[r];
+                         ldp, PSFMC_PRIOR_FAMILIES_CHEAP, dead + lo);
+      for (int r = 0; r < pl->n_rules; ++r) {
+        const psfmc_prior_rule &ru = pl->rules[r];
+        for (long long b = lo; b < hi; ++b) {
           const double a = ru.a_index >= 0 ? theta[b * ld + ru.a_index] : ru.a_value;
           const double bb = ru.b_index >= 0 ? theta[b * ld + ru.b_index] : ru.b_value;
-          d |= bb > a;
+          if (bb > a) dead[b] = 1;
         }
-        dead[b] = d ? 1 : 0;
       }
     });
     n_alive = 0;
@@ -320,7 +377,12 @@ inline int lnpost_rows(const LnlikeCalls &eng, const psfmc_prior_plan *pl, const
   }
   int rc = 0;
   const bool launched = n_alive > 0;
+  lap(1);
   if (launched && (rc = eng.begin(eng.self, gpu_theta, gpu_n, ld, lnl))) return rc;
+  lap(2);
+  ++pf.calls;
+  pf.rows += n;
+  pf.rows_gpu += launched ? gpu_n : 0;
   int cb = 0;
   if (pl) {
     double *logp = wk.logp.data();
@@ -337,8 +399,11 @@ inline int lnpost_rows(const LnlikeCalls &eng, const psfmc_prior_plan *pl, const
                        wk.lnprior.data() + lo);
       });
   }
+  lap(3);
   if (overlap && *overlap) (*overlap)();
+  lap(4);
   if (launched) rc = eng.end(eng.self);   // (always: the batch in flight must be finished)
+  lap(5);
   if (rc) return rc;
   if (cb) return -1;
   if (compacted) {
@@ -374,30 +439,72 @@ inline int run_ensemble(const LnlikeCalls &eng, const psfmc_prior_plan *pl, psfm
   const long long k = e->n_walkers, D = e->n_dim, half = k / 2;
   NumpyMT19937 mt{e->mt_key, e->mt_pos};
   std::vector<double> zz((size_t)half), newlnp((size_t)half), lzz((size_t)half),
-      lu((size_t)half);
-  std::vector<long long> partner((size_t)half);
+      lu((size_t)half), zz_next((size_t)half), lu_next((size_t)half);
+  std::vector<long long> partner((size_t)half), partner_next((size_t)half);
   LnpostWork wk;
   const double a = e->a, dm1 = (double)D - 1.0;
   const long long thin = e->thin > 0 ? e->thin : 1;
   HostPool &pool = HostPool::instance();
+  // The draws of a half-step in emcee's order: rand(Ns) for the stretch factors,
+  // randint(Nc, size=Ns) for the partners, then -- after the posterior call, which draws
+  // nothing -- rand(Ns) for the acceptance. None of them depends on a result, so the draws
+  // of the NEXT half-step are made while the GPU works on this one (one serial MT19937
+  // stream: ~40 us per 2048 walkers that the GPU would otherwise wait for). The last
+  // half-step of the run draws nothing ahead: the state handed back is exactly the one
+  // a Python loop would hold.
+  auto draw = [&](std::vector<double> &z, std::vector<long long> &p, std::vector<double> &u,
+                  long long ns, long long nc) {
+    for (long long i = 0; i < ns; ++i) {
+      volatile double t = (a - 1.0) * mt.next_double();   // (no contraction into an FMA)
+      const double t1 = t + 1.0;
+      volatile double sq = t1 * t1;
+      z[i] = sq / a;
+    }
+    for (long long i = 0; i < ns; ++i) p[i] = (long long)mt.next_bounded((uint32_t)nc);
+    for (long long i = 0; i < ns; ++i) u[i] = mt.next_double();
+  };
+  // Chain storage. emcee's layout is (walker, iteration, D): one iteration scatters k short
+  // rows over the whole array (141 us per 2048 walkers, measured: every row a cache miss).
+  // Iterations are collected in a staging block [T][k][D] and written out per walker as
+  // runs of T consecutive iterations (by the host threads).
+  long long T = 1;
+  if (e->chain || e->lnprob_chain) {
+    T = (long long)(4u << 20) / (k * D * (long long)sizeof(double));
+    T = T < 1 ? 1 : (T > 64 ? 64 : T);
+  }
+  std::vector<double> stage(e->chain ? (size_t)(T * k * D) : 0);
+  std::vector<double> stage_lnp(e->lnprob_chain ? (size_t)(T * k) : 0);
+  long long staged = 0, stage_first = 0;
+  auto flush = [&]() {
+    if (!staged) return;
+    pool.parallel_rows(k, 256, [&](long long lo, long long hi) {
+      for (long long w = lo; w < hi; ++w)
+        for (long long t = 0; t < staged; ++t) {
+          if (e->chain)
+            memcpy(e->chain + ((size_t)w * e->chain_len + stage_first + t) * D,
+                   stage.data() + ((size_t)t * k + w) * D, (size_t)D * sizeof(double));
+          if (e->lnprob_chain)
+            e->lnprob_chain[(size_t)w * e->chain_len + stage_first + t] =
+                stage_lnp[(size_t)t * k + w];
+        }
+    });
+    staged = 0;
+  };
+  // (an error return leaves the iterations completed so far in the chain)
+  struct FlushGuard {
+    std::function<void()> fn;
+    ~FlushGuard() { fn(); }
+  } flush_guard{flush};
+  draw(zz, partner, lu, half, k - half);
   for (long long it = 0; it < n_iter; ++it) {
     for (int h = 0; h < 2; ++h) {
       const long long s0 = h == 0 ? 0 : half, c0 = h == 0 ? half : 0;
       const long long ns = h == 0 ? half : k - half, nc = k - ns;
       double *s = e->pos + s0 * D;
       const double *c = e->pos + c0 * D;
-      // the half-step's draws in emcee's order: rand(Ns), randint(Nc, size=Ns), then -- after
-      // the posterior call, which draws nothing -- rand(Ns) for the acceptance
-      for (long long i = 0; i < ns; ++i) {
-        volatile double t = (a - 1.0) * mt.next_double();   // (no contraction into an FMA)
-        const double t1 = t + 1.0;
-        volatile double sq = t1 * t1;
-        zz[i] = sq / a;
-      }
-      for (long long i = 0; i < ns; ++i) partner[i] = (long long)mt.next_bounded((uint32_t)nc);
-      for (long long i = 0; i < ns; ++i) lu[i] = mt.next_double();
+      const double t_half = wk.prof.on ? EnsProfile::now() : 0.0;
       std::atomic<int> bad_inf{0}, bad_nan{0};
-      pool.parallel_rows(ns, 1024, [&](long long lo, long long hi) {
+      pool.parallel_rows(ns, 512, [&](long long lo, long long hi) {
         bool has_inf = false, has_nan = false;
         for (long long i = lo; i < hi; ++i) {
           const double *cp = c + partner[i] * D;
@@ -417,7 +524,9 @@ inline int run_ensemble(const LnlikeCalls &eng, const psfmc_prior_plan *pl, psfm
       });
       if (bad_inf) return PSFMC_ENS_POS_INF;   // emcee: ValueError
       if (bad_nan) return PSFMC_ENS_POS_NAN;
-      // the logarithms of the acceptance test run while the GPU computes
+      const bool more = !(it == n_iter - 1 && h == 1);
+      // behind the GPU: the logarithms of this half-step's acceptance test, the next
+      // half-step's draws
       const std::function<void()> overlap = [&]() {
         pool.parallel_rows(ns, 512, [&](long long lo, long long hi) {
           for (long long i = lo; i < hi; ++i) {
@@ -425,33 +534,54 @@ inline int run_ensemble(const LnlikeCalls &eng, const psfmc_prior_plan *pl, psfm
             lu[i] = log(lu[i]);
           }
         });
+        if (more) draw(zz_next, partner_next, lu_next, nc, ns);
       };
+      if (wk.prof.on) wk.prof.t[0] += EnsProfile::now() - t_half;
       int rc = lnpost_rows(eng, pl, q, ns, D, lnl, newlnp.data(), wk, scratch, &overlap);
       if (rc) return rc;
+      const double t_acc = wk.prof.on ? EnsProfile::now() : 0.0;
       double *lnp = e->lnprob + s0;
-      for (long long i = 0; i < ns; ++i) {
-        if (newlnp[i] != newlnp[i]) return PSFMC_ENS_LNPROB_NAN;
-        volatile double part = lzz[i] + newlnp[i];
-        const double lnpdiff = part - lnp[i];
-        if (lnpdiff > lu[i]) {
-          lnp[i] = newlnp[i];
-          memcpy(s + i * D, q + i * D, (size_t)D * sizeof(double));
-          if (e->n_accepted) e->n_accepted[s0 + i] += 1.0;
+      std::atomic<int> bad_lnp{0};
+      pool.parallel_rows(ns, 512, [&](long long lo, long long hi) {
+        for (long long i = lo; i < hi; ++i) {
+          if (newlnp[i] != newlnp[i]) {
+            bad_lnp = 1;
+            continue;
+          }
+          volatile double part = lzz[i] + newlnp[i];
+          const double lnpdiff = part - lnp[i];
+          if (lnpdiff > lu[i]) {
+            lnp[i] = newlnp[i];
+            memcpy(s + i * D, q + i * D, (size_t)D * sizeof(double));
+            if (e->n_accepted) e->n_accepted[s0 + i] += 1.0;
+          }
         }
+      });
+      if (bad_lnp) return PSFMC_ENS_LNPROB_NAN;
+      if (more) {
+        zz.swap(zz_next);
+        partner.swap(partner_next);
+        lu.swap(lu_next);
       }
+      if (wk.prof.on) wk.prof.t[6] += EnsProfile::now() - t_acc;
     }
+    const double t_store = wk.prof.on ? EnsProfile::now() : 0.0;
     if (it % thin == 0) {
       const long long ind = e->chain_start + it / thin;
       if (ind < e->chain_len) {
-        if (e->chain)
-          for (long long w = 0; w < k; ++w)
-            memcpy(e->chain + ((size_t)w * e->chain_len + ind) * D, e->pos + w * D,
-                   (size_t)D * sizeof(double));
-        if (e->lnprob_chain)
-          for (long long w = 0; w < k; ++w) e->lnprob_chain[(size_t)w * e->chain_len + ind] = e->lnprob[w];
+        if (e->chain || e->lnprob_chain) {
+          if (!staged) stage_first = ind;
+          if (e->chain)
+            memcpy(stage.data() + (size_t)staged * k * D, e->pos, (size_t)k * D * sizeof(double));
+          if (e->lnprob_chain)
+            memcpy(stage_lnp.data() + (size_t)staged * k, e->lnprob, (size_t)k * sizeof(double));
+          if (++staged == T) flush();
+        }
       }
     }
+    if (wk.prof.on) wk.prof.t[7] += EnsProfile::now() - t_store;
   }
+  wk.prof.report("ensemble_run");
   return PSFMC_ENS_OK;
 }
 

@@ -249,10 +249,14 @@ class EnsembleSampler(object):
         start = self._chain.shape[1]
         if storechain:
             nstore = int(iterations / thin)
-            self._chain = np.concatenate(
-                (self._chain, np.zeros((self.k, nstore, self.dim))), axis=1)
-            self._lnprob = np.concatenate(
-                (self._lnprob, np.zeros((self.k, nstore))), axis=1)
+            if self._chain.shape[1] == 0:     # (nothing to copy: fresh, lazily zeroed pages)
+                self._chain = np.zeros((self.k, nstore, self.dim))
+                self._lnprob = np.zeros((self.k, nstore))
+            else:
+                self._chain = np.concatenate(
+                    (self._chain, np.zeros((self.k, nstore, self.dim))), axis=1)
+                self._lnprob = np.concatenate(
+                    (self._lnprob, np.zeros((self.k, nstore))), axis=1)
         native = self._native(p) if blobs is None else None
         if native is not None:
             single = getattr(self, '_one_call', False)
