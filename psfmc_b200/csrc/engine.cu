@@ -396,7 +396,25 @@ struct Engine : EngineBase {
     return b;
   }
 
-  // for_images: the blob images always come from the staged kernels
+#ifndef PSFMC_NO_FUSED
+  FusedBuffers fused_buffers(DeviceState<T> &d) {
+    FusedBuffers fb;
+    fb.rconst = d.rconst.ptr;
+    fb.spec4 = d.fspec;
+    fb.specx4 = d.fspecx;
+    fb.ow = d.fow;
+    fb.maskw = d.fmaskw;
+    fb.lnl_const = d.lnl_const;
+    fb.n_sms = d.n_sms;
+    fb.skip_quads = d.skip_quads;
+    fb.hot = d.fkpv ? d.hot.ptr : nullptr;
+    fb.kpv = d.fkpv;
+    return fb;
+  }
+#endif
+
+  // for_images: blob images from the staged kernels (the fused 128 x 128 path renders
+  // its own, see render_device)
   int ensure_batch(DeviceState<T> &d, long long B, bool for_images = false) {
     size_t nb = (size_t)B;
     size_t ncomp = prog_h.n_components > 0 ? prog_h.n_components : 1;
@@ -435,17 +453,7 @@ struct Engine : EngineBase {
     StagedBuffers<T> buf = buffers(d);
 #ifndef PSFMC_NO_FUSED
     if (path == 1) {
-      FusedBuffers fb;
-      fb.rconst = d.rconst.ptr;
-      fb.spec4 = d.fspec;
-      fb.specx4 = d.fspecx;
-      fb.ow = d.fow;
-      fb.maskw = d.fmaskw;
-      fb.lnl_const = d.lnl_const;
-      fb.n_sms = d.n_sms;
-      fb.skip_quads = d.skip_quads;
-      fb.hot = d.fkpv ? d.hot.ptr : nullptr;
-      fb.kpv = d.fkpv;
+      FusedBuffers fb = fused_buffers(d);
       fb.nan_marks = mark_next;
       peer_direct = false;
       if (peer_n > 0 && &d == &devs[0]) {
@@ -1002,6 +1010,18 @@ struct Engine : EngineBase {
     const int FH = plan.fr.H, FW = plan.fr.W;
     const size_t npx = (size_t)FH * FW, npx_out = (size_t)H * W;
     long long chunk = plan.chunk < 256 ? plan.chunk : 256;
+    // Unpadded 128 x 128 frames in float32: the images come out of the fused kernel (an
+    // IMAGES instance writes them on its way to lnL: ~8 M walkers/s against ~1.2 M for
+    // the staged kernels), in chunks of four walkers per SM. PSFMC_STAGED_IMAGES=1 keeps
+    // the staged kernels (tests compare the two).
+    bool fused_img = false;
+#ifndef PSFMC_NO_FUSED
+    {
+      const char *env = getenv("PSFMC_STAGED_IMAGES");
+      fused_img = path == 1 && sizeof(T) == 4 && !plan.fr.padded && !(env && env[0] == '1');
+      if (fused_img) chunk = 4ll * d.n_sms;
+    }
+#endif
     if (chunk > nrows) chunk = nrows;
     for (int k = 0; k < 4; ++k)
       if (d.img[k].ensure((size_t)chunk * npx))
@@ -1009,15 +1029,18 @@ struct Engine : EngineBase {
     if (d.theta.ensure((size_t)chunk * ld) || d.lnl.ensure((size_t)chunk))
       return fail(PSFMC_ERR_CUDA, "allocation failed (image staging)");
     if (accumulate) {
-      if (d.img_acc.ensure((size_t)nsel * npx))
+      // [nsel][PSFMC_ACC_SLICES][npx] partial sums (accumulate_kernel) + [nsel][npx] totals
+      if (d.img_acc.ensure((size_t)nsel * (PSFMC_ACC_SLICES + 1) * npx))
         return fail(PSFMC_ERR_CUDA, "device allocation failed (image sums)");
-      CUDA_TRY(cudaMemsetAsync(d.img_acc.ptr, 0, (size_t)nsel * npx * sizeof(double), d.stream));
+      CUDA_TRY(cudaMemsetAsync(d.img_acc.ptr, 0,
+                               (size_t)nsel * (PSFMC_ACC_SLICES + 1) * npx * sizeof(double),
+                               d.stream));
     } else if (d.img_pin.ensure((size_t)chunk * npx)) {
       return fail(PSFMC_ERR_CUDA, "allocation failed (image staging)");
     }
     for (long long start = 0; start < nrows; start += chunk) {
       long long nb = nrows - start < chunk ? nrows - start : chunk;
-      int rc = ensure_batch(d, nb, true);
+      int rc = ensure_batch(d, nb, !fused_img);
       if (rc) return rc;
       // (pageable source: the copy is staged by the driver before the call returns)
       CUDA_TRY(cudaMemcpyAsync(d.theta.ptr, theta + (row0 + start) * ld,
@@ -1029,9 +1052,26 @@ struct Engine : EngineBase {
       io.conv = d.img[1].ptr;
       io.resid = d.img[2].ptr;
       io.ivm = d.img[3].ptr;
-      launch_staged_lnlike<T>(plan, buf, prog_h.n_components, precision, d.theta.ptr, nb, ld,
-                              d.lnl.ptr, d.stream, false, &io);
-      launches += count_launches<T>(plan, nb);
+#ifndef PSFMC_NO_FUSED
+      FusedBuffers fb;
+      FusedImages fi;
+      if (fused_img) {
+        fb = fused_buffers(d);
+        fi.raw = reinterpret_cast<float *>(io.raw);
+        fi.conv = reinterpret_cast<float *>(io.conv);
+        fi.resid = reinterpret_cast<float *>(io.resid);
+        fi.ivm = reinterpret_cast<float *>(io.ivm);
+        fi.obs = reinterpret_cast<const float *>(d.obs);
+        fi.ovar = reinterpret_cast<const float *>(d.ovar);
+        launches += launch_fused_lnlike<T>(plan, buf, fb, prog_h, d.theta.ptr, nb, ld, d.lnl.ptr,
+                                           d.stream, nullptr, nullptr, &fi);
+      } else
+#endif
+      {
+        launch_staged_lnlike<T>(plan, buf, prog_h.n_components, precision, d.theta.ptr, nb, ld,
+                                d.lnl.ptr, d.stream, false, &io);
+        launches += count_launches<T>(plan, nb);
+      }
       CUDA_TRY(cudaGetLastError());
       int sel = 0;
       for (int k = 0; k < 5; ++k) {
@@ -1044,17 +1084,32 @@ struct Engine : EngineBase {
           // point sources only -> convolve -> obs - that (models.py:296-306)
           ImageOutputs<T> ps;
           ps.resid = d.img[0].ptr;
-          launch_staged_lnlike<T>(plan, buf, prog_h.n_components, precision, d.theta.ptr, nb,
-                                  ld, d.lnl.ptr, d.stream, true, &ps);
-          launches += count_launches<T>(plan, nb);
+#ifndef PSFMC_NO_FUSED
+          if (fused_img) {
+            FusedImages fp;
+            fp.resid = reinterpret_cast<float *>(ps.resid);
+            fp.obs = fi.obs;
+            fp.ovar = fi.ovar;
+            fp.ps_only = true;
+            launches += launch_fused_lnlike<T>(plan, buf, fb, prog_h, d.theta.ptr, nb, ld,
+                                               d.lnl.ptr, d.stream, nullptr, nullptr, &fp);
+          } else
+#endif
+          {
+            launch_staged_lnlike<T>(plan, buf, prog_h.n_components, precision, d.theta.ptr, nb,
+                                    ld, d.lnl.ptr, d.stream, true, &ps);
+            launches += count_launches<T>(plan, nb);
+          }
           CUDA_TRY(cudaGetLastError());
           src = d.img[0].ptr;
         }
         if (accumulate) {
           const int block = 256;
-          launch_kernel(accumulate_kernel<T>, dim3((unsigned)((npx + block - 1) / block)),
+          launch_kernel(accumulate_kernel<T>,
+                        dim3((unsigned)((npx + block - 1) / block), PSFMC_ACC_SLICES),
                         dim3(block), 0, d.stream, (const T *)src, (int)nb, (long long)npx,
-                        k == 3 ? 1 : 0, d.img_acc.ptr + (size_t)sel * npx);
+                        k == 3 ? 1 : 0,
+                        d.img_acc.ptr + (size_t)sel * PSFMC_ACC_SLICES * npx);
           ++launches;
           CUDA_TRY(cudaGetLastError());
         } else {
@@ -1078,7 +1133,17 @@ struct Engine : EngineBase {
         full.resize((size_t)nsel * npx);
         dst = full.data();
       }
-      CUDA_TRY(cudaMemcpyAsync(dst, d.img_acc.ptr, (size_t)nsel * npx * sizeof(double),
+      double *totals = d.img_acc.ptr + (size_t)nsel * PSFMC_ACC_SLICES * npx;
+      for (int sel = 0; sel < nsel; ++sel) {
+        const int block = 256;
+        launch_kernel(accumulate_reduce_kernel, dim3((unsigned)((npx + block - 1) / block)),
+                      dim3(block), 0, d.stream,
+                      (const double *)(d.img_acc.ptr + (size_t)sel * PSFMC_ACC_SLICES * npx),
+                      (long long)npx, totals + (size_t)sel * npx);
+        ++launches;
+      }
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaMemcpyAsync(dst, totals, (size_t)nsel * npx * sizeof(double),
                                cudaMemcpyDeviceToHost, d.stream));
       CUDA_TRY(cudaStreamSynchronize(d.stream));
       if (plan.fr.padded)
@@ -1790,6 +1855,7 @@ struct psfmc_engine {
   // psfmc_ensemble_run / psfmc_lnpost_batch: proposals and their lnL in page-locked memory
   // (stable addresses: the host call is then one replayed graph, no staging copies)
   PinBuf<double> ens_q, ens_lnl, ens_scratch;
+  LnpostWork ens_work;
 };
 
 // A float32 evaluation that came back non-finite is repeated in float64 on the GPU:
@@ -2237,9 +2303,8 @@ int psfmc_lnpost_batch(psfmc_engine *engine, const psfmc_prior_plan *priors,
   cudaSetDevice(prev);
   if (bad) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
   LnlikeCalls calls{engine, ens_begin, ens_end};
-  LnpostWork wk;
-  int rc = lnpost_rows(calls, priors, theta, n_batch, ld, engine->ens_lnl.ptr, lnpost_out, wk,
-                       engine->ens_scratch.ptr);
+  int rc = lnpost_rows(calls, priors, theta, n_batch, ld, engine->ens_lnl.ptr, lnpost_out,
+                       engine->ens_work, engine->ens_scratch.ptr);
   if (rc == -1) return fail(PSFMC_ERR_INVALID_ARG, "the other_columns callback failed");
   return rc;
 }
@@ -2276,7 +2341,7 @@ int psfmc_ensemble_run(psfmc_engine *engine, const psfmc_prior_plan *priors,
   if (bad) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
   LnlikeCalls calls{engine, ens_begin, ens_end};
   int rc = run_ensemble(calls, priors, ens, n_iterations, engine->ens_q.ptr, engine->ens_lnl.ptr,
-                        engine->ens_scratch.ptr);
+                        engine->ens_scratch.ptr, engine->ens_work);
   switch (rc) {
     case PSFMC_ENS_OK: return 0;
     case PSFMC_ENS_CALLBACK:

@@ -89,6 +89,14 @@ struct FusedParams {
   int n_peer;
   unsigned long long kind_bits;   // 2 bits per component (a kernel-parameter ARRAY indexed
                                   // by a loop variable is copied to local memory)
+  // Blob images (IMAGES instance only; psfmc_render_batch / psfmc_accumulate_batch,
+  // psfMC/models.py:213-226): [B][128 * 128] float each, or null. The observation and its
+  // variance as the staged kernels see them (img_obs / img_ovar: no (0, 1e30) at excluded
+  // pixels -- the images cover every pixel). ps_only: only the point sources are rendered;
+  // img_resid is then the point-source-subtracted image (models.py:296-306).
+  float *img_raw, *img_conv, *img_resid, *img_ivm;
+  const float *img_obs, *img_ovar;
+  int ps_only;
 };
 
 // padded frames (see Frame in common.cuh): observation frame and fold bounds
@@ -279,7 +287,7 @@ __device__ __forceinline__ smem_addr_t smem_base(unsigned char *ptr) {
 // Raw model at the 16 pixels x = l + XS*j of row y -> packed z = raw + i*wsc*raw^2
 // (XS = 8: 128-wide rows, XS = 16: 256-wide rows of the cluster kernel).
 // Pixels are rendered in pairs (j, j+1) with element-wise pair arithmetic.
-template <int XS, bool STAGED>
+template <int XS, bool STAGED, bool IMAGES = false>
 __device__ __forceinline__ void fused_render16(const FusedParams &P, const float *rc0,
                                                const double *der0, int y, int l, float wsc,
                                                cplx<float> *v) {
@@ -291,6 +299,7 @@ __device__ __forceinline__ void fused_render16(const FusedParams &P, const float
   for (int c = 0; c < P.ncomp; ++c) {
     const int kind = (int)((P.kind_bits >> (2 * c)) & 3ull);
     const float *rc = rc0 + c * PSFMC_RC_STRIDE;
+    if (IMAGES && P.ps_only && kind != PSFMC_POINT) continue;
     if (kind == PSFMC_SKY) {
       const cplx<float> adu = bcast(STAGED ? *rc : __ldg(rc));
 #pragma unroll
@@ -417,14 +426,15 @@ struct RowRole {
 // frame; nothing is rendered outside it.
 // TILED: the tile is sub-image `sub` = 4 ry + rx of a 512 x 512 frame: tile pixel (y, x)
 // is frame pixel (4 y + ry, 4 x + rx).
-template <bool STAGED, bool PADDED = false, bool TILED = false>
+template <bool STAGED, bool PADDED = false, bool TILED = false, bool IMAGES = false>
 __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_addr_t tile,
                                                    const RowRole &R, smem_addr_t twl,
                                                    const float *rc0, const double *der0,
                                                    int it, float wsc,
                                                    const FoldParams *F = nullptr, int sub = 0,
                                                    bool drain = false, HotState *hs = nullptr,
-                                                   int hpar = 0) {
+                                                   int hpar = 0, long long bw = 0) {
+  // bw (IMAGES): the walker whose rows are rendered
   // drain (tiled forward half, first row batch of a job): the previous job's results are
   // still leaving the tile through bulk stores issued by threads 0..127; the tile may
   // only be written once those have read it (see the kernel)
@@ -446,7 +456,12 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
         fused_render16<32, STAGED>(P, rc0, der0, 4 * y + (sub >> 2), 4 * R.l + (sub & 3), wsc,
                                    v);
       else
-        fused_render16<8, STAGED>(P, rc0, der0, y, R.l, wsc, v);
+        fused_render16<8, STAGED, IMAGES>(P, rc0, der0, y, R.l, wsc, v);
+      if (IMAGES && P.img_raw) {
+        float *dst = P.img_raw + ((size_t)bw * PSFMC_FUSED_N + y) * PSFMC_FUSED_N + R.l;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[8 * j] = v[j].x;
+      }
       if (!PADDED && !TILED && __builtin_expect(hs != nullptr, 0)) {
         // take the walker's hot pixels out of the transform (see prepare_kernel): the
         // thread that rendered one records its value and zeroes it
@@ -515,7 +530,7 @@ __device__ __forceinline__ void fused_rows_forward(const FusedParams &P, smem_ad
 // inverse row transform + chi-square terms of row batch `it`;
 // returns this thread's float64 partial sum over its 16 pixels. PREFETCH: issue the
 // observation loads before the transform (needs 32 registers for its duration).
-template <bool PREFETCH, bool PADDED = false>
+template <bool PREFETCH, bool PADDED = false, bool IMAGES = false>
 __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_addr_t tile,
                                                      const RowRole &R, smem_addr_t twl,
                                                      int it, float unscale,
@@ -525,7 +540,9 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
                                                      unsigned long long *bar = nullptr,
                                                      unsigned char *tile_ptr = nullptr,
                                                      const HotState *hs = nullptr, int hpar = 0,
-                                                     const float2 *kpv = nullptr) {
+                                                     const float2 *kpv = nullptr,
+                                                     long long bw = 0) {
+  // bw (IMAGES): the walker whose rows come back
   const int y = it * 64 + R.w * 4 + R.rr;
   // gnext (tiled inverse half): once the warp has taken its four rows out of the tile,
   // lanes 0..3 fetch the same rows of the NEXT job's sub-spectrum into their place
@@ -629,6 +646,21 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
       }
     }
   }
+  if (IMAGES) {
+    // convolved model, residual and composite IVM of EVERY pixel, with the staged
+    // kernels' float32 expressions (Epilogue<float>::term)
+    const size_t g0 = (size_t)y * PSFMC_FUSED_N + R.l, w0 = (size_t)bw * PSFMC_FUSED_N * PSFMC_FUSED_N;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const size_t g = g0 + 8 * j;
+      const float conv = v[j].x, mvar = v[j].y * unscale;
+      const float resid = __ldg(P.img_obs + g) - conv;
+      const float ivm = fast_rcp(mvar + __ldg(P.img_ovar + g));
+      if (P.img_conv) P.img_conv[w0 + g] = conv;
+      if (P.img_resid) P.img_resid[w0 + g] = resid;
+      if (P.img_ivm) P.img_ivm[w0 + g] = ivm;
+    }
+  }
   // Chi-square terms (psfMC/models.py:233-236) of the 16 pixels, float32, summed in
   // float32 over 8 pixels before they enter the float64 sum:
   //     resid^2 ivm - log(ivm / 2 pi) = resid^2 / tot + ln2 log2(tot) + ln(2 pi),
@@ -669,7 +701,8 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
 #define PSFMC_MODE_FULL 0
 #define PSFMC_MODE_FWD 1
 #define PSFMC_MODE_INV 2
-template <bool PADDED, int MODE = PSFMC_MODE_FULL>
+// IMAGES: the blob images of every walker are written out on the way (FusedParams::img_*).
+template <bool PADDED, int MODE = PSFMC_MODE_FULL, bool IMAGES = false>
 __global__ void __launch_bounds__(PSFMC_FUSED_THREADS, 1)
 fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
   constexpr bool TILED = MODE != PSFMC_MODE_FULL;
@@ -1052,16 +1085,15 @@ fused_lnlike_kernel(const FusedParams P, const FoldParams F) {
       const int it = interleave ? (step >> 1) : (step & 1);
       if (!fwd) {
         if (cur && MODE != PSFMC_MODE_FWD)
-          acc += fused_rows_inverse<true, PADDED>(
+          acc += fused_rows_inverse<true, PADDED, IMAGES>(
               P, tile, R, twl, it, unscale, &F, sub,
               MODE == PSFMC_MODE_INV ? __ldg(P.skip_tab + sub) : P.skip_quads,
               (MODE == PSFMC_MODE_INV && has_next) ? P.sub_spec + (size_t)bn * N * N : nullptr,
-              &tile_bar, smem_raw, hot_cur, hpar, P.kpv + (size_t)sel * N * N);
+              &tile_bar, smem_raw, hot_cur, hpar, P.kpv + (size_t)sel * N * N, b);
       } else if (has_next && MODE != PSFMC_MODE_INV) {
-        fused_rows_forward<true, PADDED, TILED>(P, tile, R, twl, rc_s, der_s, it, wsc_next, &F,
-                                                TILED ? (int)(bn & 15) : 0,
-                                                MODE == PSFMC_MODE_FWD && cur && it == 0,
-                                                hot_nxt, hpar ^ 1);
+        fused_rows_forward<true, PADDED, TILED, IMAGES>(
+            P, tile, R, twl, rc_s, der_s, it, wsc_next, &F, TILED ? (int)(bn & 15) : 0,
+            MODE == PSFMC_MODE_FWD && cur && it == 0, hot_nxt, hpar ^ 1, bn);
       }
       if (cur && MODE != PSFMC_MODE_FWD &&
           ((interleave && step == 2) || (!interleave && step == 1))) {
@@ -1127,6 +1159,9 @@ inline int fused_prepare_device(const StagedPlan &) {
                            PSFMC_FUSED_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(fused_lnlike_kernel<true>,
                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           PSFMC_FUSED_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(fused_lnlike_kernel<false, PSFMC_MODE_FULL, true>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                            PSFMC_FUSED_SMEM) != cudaSuccess)
     return 1;
 #endif
@@ -1181,6 +1216,14 @@ struct FusedBuffers {
   unsigned skip_quads = 0;   // see FusedParams
 };
 
+// Blob images wanted from a launch (unpadded 128 x 128 frames): [n_batch][128 * 128] float
+// each, null = not wanted; obs / ovar: the staged path's observation arrays.
+struct FusedImages {
+  float *raw = nullptr, *conv = nullptr, *resid = nullptr, *ivm = nullptr;
+  const float *obs = nullptr, *ovar = nullptr;
+  bool ps_only = false;
+};
+
 // theta -> lnL for n_batch walkers: prepare kernel + one persistent fused kernel.
 // Returns the number of kernels launched.
 template <typename T>
@@ -1188,10 +1231,13 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
                                const FusedBuffers &fb, const Program &prog_h,
                                const double *theta, long long n_batch, long long ld,
                                double *lnl, cudaStream_t stream,
-                               cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr) {
+                               cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr,
+                               const FusedImages *img = nullptr) {
   if (n_batch <= 0) return 0;
   const int ncomp = prog_h.n_components;
-  int *hot = (fb.hot && fb.kpv && !plan.fr.padded) ? fb.hot : nullptr;
+  // (images: every pixel of every walker is wanted as the float32 kernels compute it --
+  // no hot pixels taken out, no row skipped)
+  int *hot = (fb.hot && fb.kpv && !plan.fr.padded && !img) ? fb.hot : nullptr;
   launch_prepare(*buf.prog_host, theta, n_batch, ld, plan.fr.Hr, plan.fr.Wr, ncomp, buf.derived,
                  buf.psf_sel, buf.wscale, fb.rconst, stream, hot);
   FusedParams P;
@@ -1223,12 +1269,22 @@ inline int launch_fused_lnlike(const StagedPlan &plan, const StagedBuffers<T> &b
   P.lnl = lnl;
   P.n_batch = n_batch;
   P.ncomp = ncomp;
-  P.skip_quads = fb.skip_quads;
+  P.skip_quads = img ? 0u : fb.skip_quads;
+  P.img_raw = img ? img->raw : nullptr;
+  P.img_conv = img ? img->conv : nullptr;
+  P.img_resid = img ? img->resid : nullptr;
+  P.img_ivm = img ? img->ivm : nullptr;
+  P.img_obs = img ? img->obs : nullptr;
+  P.img_ovar = img ? img->ovar : nullptr;
+  P.ps_only = (img && img->ps_only) ? 1 : 0;
   P.kind_bits = 0;
   for (int c = 0; c < ncomp; ++c) P.kind_bits |= (unsigned long long)(prog_h.kind[c] & 3) << (2 * c);
   unsigned grid = (unsigned)(n_batch < fb.n_sms ? n_batch : fb.n_sms);
   if (ev_begin) cudaEventRecord(ev_begin, stream);
-  if (plan.fr.padded)
+  if (img)
+    launch_kernel(fused_lnlike_kernel<false, PSFMC_MODE_FULL, true>, dim3(grid),
+                  dim3(PSFMC_FUSED_THREADS), (size_t)PSFMC_FUSED_SMEM, stream, P, F);
+  else if (plan.fr.padded)
     launch_kernel(fused_lnlike_kernel<true>, dim3(grid), dim3(PSFMC_FUSED_THREADS),
                   (size_t)PSFMC_FUSED_SMEM, stream, P, F);
   else

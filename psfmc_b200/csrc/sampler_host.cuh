@@ -290,6 +290,7 @@ struct EnsProfile {
 
 struct LnpostWork {
   EnsProfile prof;
+  double last_dead_frac = 1.0;   // share of rows the closed-form priors killed in the last call
   std::vector<double> logp, lnprior;
   std::vector<long long> alive;     // rows sent to the GPU (when some were left out)
   std::vector<unsigned char> dead;
@@ -300,6 +301,10 @@ struct LnpostWork {
 #define PSFMC_ENS_FIXED_BATCH 160
 
 // lnpost of n rows.
+//  0. large batches whose previous call lost at most 2 % of its rows to step 1 skip the
+//     screening: the GPU is started on all rows at once and step 1 runs behind it with the
+//     rest (a converged chain proposes few dead rows; 40 us per 2048 rows not spent in front
+//     of the launch);
 //  1. the closed-form prior columns (Uniform, Normal) and the component rules decide which
 //     rows are dead before the GPU is started: a dead row's lnL is never looked at
 //     (psfMC/models.py:209-211 returns before evaluating it). Large batches leave the dead
@@ -328,14 +333,8 @@ inline int lnpost_rows(const LnlikeCalls &eng, const psfmc_prior_plan *pl, const
   const long long ldp = (pl && pl->n_columns > 0) ? pl->n_columns : 1;
   bool other = false, costly = false;
   long long n_alive = n;
-  if (pl) {
-    wk.logp.resize((size_t)n * ldp);
-    wk.lnprior.resize((size_t)n);
-    wk.dead.assign((size_t)n, 0);
-    for (int c = 0; c < pl->n_columns; ++c) {
-      other |= pl->columns[c].family == PSFMC_PRIOR_OTHER;
-      costly |= pl->columns[c].family == PSFMC_PRIOR_WEIBULL_MIN;
-    }
+  const bool screen_first = pl && (n <= PSFMC_ENS_FIXED_BATCH || wk.last_dead_frac > 0.02);
+  auto screen = [&]() {
     double *logp = wk.logp.data();
     unsigned char *dead = wk.dead.data();
     pool.parallel_rows(n, 512, [&](long long lo, long long hi) {
@@ -350,8 +349,20 @@ inline int lnpost_rows(const LnlikeCalls &eng, const psfmc_prior_plan *pl, const
         }
       }
     });
-    n_alive = 0;
-    for (long long b = 0; b < n; ++b) n_alive += dead[b] ? 0 : 1;
+    long long alive = 0;
+    for (long long b = 0; b < n; ++b) alive += dead[b] ? 0 : 1;
+    wk.last_dead_frac = (double)(n - alive) / (double)n;
+    return alive;
+  };
+  if (pl) {
+    wk.logp.resize((size_t)n * ldp);
+    wk.lnprior.resize((size_t)n);
+    wk.dead.assign((size_t)n, 0);
+    for (int c = 0; c < pl->n_columns; ++c) {
+      other |= pl->columns[c].family == PSFMC_PRIOR_OTHER;
+      costly |= pl->columns[c].family == PSFMC_PRIOR_WEIBULL_MIN;
+    }
+    if (screen_first) n_alive = screen();
   }
   const double *gpu_theta = theta;
   long long gpu_n = n;
@@ -386,6 +397,7 @@ inline int lnpost_rows(const LnlikeCalls &eng, const psfmc_prior_plan *pl, const
   int cb = 0;
   if (pl) {
     double *logp = wk.logp.data();
+    if (!screen_first) screen();     // (behind the GPU; every row is being evaluated)
     if (costly)
       pool.parallel_rows(n, 256, [&](long long lo, long long hi) {
         prior_columns_host(pl->columns, pl->n_columns, theta + lo * ld, hi - lo, ld,
@@ -435,13 +447,14 @@ inline int lnpost_rows(const LnlikeCalls &eng, const psfmc_prior_plan *pl, const
 // caller can: the engine then skips its staging copies and replays one captured graph per
 // call)
 inline int run_ensemble(const LnlikeCalls &eng, const psfmc_prior_plan *pl, psfmc_ensemble *e,
-                        long long n_iter, double *q, double *lnl, double *scratch) {
+                        long long n_iter, double *q, double *lnl, double *scratch,
+                        LnpostWork &wk) {
   const long long k = e->n_walkers, D = e->n_dim, half = k / 2;
   NumpyMT19937 mt{e->mt_key, e->mt_pos};
   std::vector<double> zz((size_t)half), newlnp((size_t)half), lzz((size_t)half),
       lu((size_t)half), zz_next((size_t)half), lu_next((size_t)half);
   std::vector<long long> partner((size_t)half), partner_next((size_t)half);
-  LnpostWork wk;
+  wk.prof = EnsProfile();
   const double a = e->a, dm1 = (double)D - 1.0;
   const long long thin = e->thin > 0 ? e->thin : 1;
   HostPool &pool = HostPool::instance();

@@ -196,6 +196,60 @@ def check_pssub_golden(library, precision, tag='c1', rows=None):
     model.engine.close()
 
 
+def check_fused_images(library, c1_golden, monkeypatch, n_extra=0):
+    """The blob images of a float32 engine on an unpadded 128 x 128 frame come out of the
+    fused kernel (IMAGES instance): against the reference's pixels (golden, mode M3) at
+    float32 accuracy, against the staged kernels' images (PSFMC_STAGED_IMAGES=1), through a
+    persistent-CTA loop (more walkers than CTAs), two PSFs, and summed on the device."""
+    thetas = np.array(c1_golden['theta'][:3] + c1_golden['theta'][6:8])
+    if n_extra:
+        rng = np.random.RandomState(4)
+        extra = thetas[rng.randint(0, len(thetas), n_extra)] * (
+            1 + 1e-3 * rng.standard_normal((n_extra, thetas.shape[1])))
+        thetas = np.concatenate([thetas, extra])
+    px = np.array(c1_golden['sample_px'])
+    monkeypatch.setenv('PSFMC_FUSED_CTAS', '4')
+    monkeypatch.delenv('PSFMC_STAGED_IMAGES', raising=False)
+    model = model_from_file('j0005/model_c1.py', 'fp32', library=library)
+    assert model.engine.info()['path'] == 1
+    before = model.engine.info()['launches_total']
+    imgs = model.engine.render(thetas)
+    fused_launches = model.engine.info()['launches_total'] - before
+    sums = model.engine.accumulate(thetas)
+    monkeypatch.setenv('PSFMC_STAGED_IMAGES', '1')
+    before = model.engine.info()['launches_total']
+    staged = model.engine.render(thetas)
+    staged_launches = model.engine.info()['launches_total'] - before
+    staged_sums = model.engine.accumulate(thetas)
+    monkeypatch.delenv('PSFMC_STAGED_IMAGES')
+    # (prepare + kernel for the four lnL-path images, the same for the point sources alone,
+    # per chunk of four walkers per CTA; the staged path: five kernels per pass)
+    assert fused_launches == 4 * -(-len(thetas) // 16), fused_launches
+    assert staged_launches == 10 * -(-len(thetas) // 256), staged_launches
+    for name in imgs:
+        finite = np.isfinite(staged[name])
+        assert np.array_equal(np.isfinite(imgs[name]), finite), name
+        scale = np.abs(staged[name][finite]).max()
+        tol = 2e-5 if name == 'composite_ivm' else 4e-6
+        err = np.abs(imgs[name][finite] - staged[name][finite]).max() / scale
+        assert err < tol, (name, err)
+        want = (1 / imgs[name]).sum(axis=0) if name == 'composite_ivm' \
+            else imgs[name].sum(axis=0)
+        assert np.allclose(sums[name], want, rtol=1e-12, atol=0, equal_nan=True), name
+        ok = np.isfinite(staged_sums[name]) & np.isfinite(sums[name])
+        assert np.allclose(sums[name][ok], staged_sums[name][ok], rtol=0,
+                           atol=len(thetas) * 2e-5 * np.abs(staged_sums[name][ok]).max()), name
+    for row in range(2):
+        ref = c1_golden['pixels']['M3'][row]
+        for key in ('raw_model', 'convolved_model', 'residual', 'composite_ivm'):
+            got = imgs[key][row].ravel()[px]
+            scale = np.abs(np.array(ref[key])).max()
+            assert np.allclose(got, ref[key], rtol=2e-5, atol=4e-6 * scale), (key, row)
+    monkeypatch.delenv('PSFMC_FUSED_CTAS')
+    check_pssub_golden(library, 'fp32', 'c1_2psf', rows=[0, 1])
+    return imgs
+
+
 def mixed_model_128(precision, library=None):
     """128 x 128 model exercising the fused kernel's less common render paths: two
     point sources (bilinear and Lanczos, one clipped at the frame edge), a Sersic with

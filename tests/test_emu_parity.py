@@ -10,7 +10,7 @@ import pytest
 
 from conftest import (ARBITRARY_FRAMES, assert_lnl_close, check_arbitrary_frame,
                       check_cluster_path_256, check_tiled_path_512, check_cropped_golden, check_nan_propagation,
-                      check_fp64_rescue, check_hot_pixel_walkers, check_near_centre_walkers, check_pssub_golden,
+                      check_fp64_rescue, check_fused_images, check_hot_pixel_walkers, check_near_centre_walkers, check_pssub_golden,
                       mixed_model_128, fp32_bounds, load_golden, model_from_file,
                       oracle_from_model)
 
@@ -138,6 +138,10 @@ def test_emu_images_and_point_source_subtracted(emu_library, c1_golden):
 def test_emu_point_source_subtracted_matches_the_reference(emu_library, precision):
     check_pssub_golden(emu_library, precision, 'c1', rows=[0, 4, 5])
     check_pssub_golden(emu_library, precision, 'c1_2psf', rows=[0, 1])
+
+
+def test_emu_images_from_the_fused_kernel(emu_library, c1_golden, monkeypatch):
+    check_fused_images(emu_library, c1_golden, monkeypatch)
 
 
 def test_emu_short_theta_rows_are_rejected(emu_library, c1_golden):

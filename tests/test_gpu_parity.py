@@ -8,7 +8,8 @@ import os
 import numpy as np
 import pytest
 
-from conftest import (assert_lnl_close, check_pssub_golden, fp32_bounds, load_golden,
+from conftest import (assert_lnl_close, check_fused_images, check_pssub_golden, fp32_bounds,
+                      load_golden,
                       mixed_model_128, model_from_file, oracle_from_model)
 
 pytestmark = pytest.mark.gpu
@@ -511,6 +512,20 @@ def test_library_sampler_loop_reproduces_the_numpy_loop(cuda_library, c1_golden,
         assert np.array_equal(runs['0'][1], runs['1'][1])
     else:
         np.testing.assert_allclose(runs['1'][1], runs['0'][1], rtol=1e-13)
+
+
+def test_images_from_the_fused_kernel(cuda_library, c1_golden, monkeypatch):
+    """Blob images of the float32 engine through the IMAGES instance of the fused kernel,
+    several walkers per CTA (700 walkers on 4 CTAs, then on all SMs)."""
+    check_fused_images(None, c1_golden, monkeypatch, n_extra=700)
+    model = model_from_file('j0005/model_c1.py', 'fp32')
+    thetas = np.array(c1_golden['theta'][:8])
+    big = np.tile(thetas, (100, 1))
+    sums = model.engine.accumulate(big)
+    one = model.engine.accumulate(thetas)
+    for name in sums:
+        ok = np.isfinite(one[name])
+        assert np.allclose(sums[name][ok], 100 * one[name][ok], rtol=1e-10), name
 
 
 def test_accumulate_on_device_matches_rendered_images(cuda_library, c1_golden):

@@ -187,8 +187,15 @@ def test_lnpost_batch_leaves_dead_rows_out(emu_library):
     np.testing.assert_allclose(got[~kill], expect, rtol=1e-13)
     launched = model.engine.info()['launches_total']
     assert launched > before
+    # (a batch is screened before the launch when it is small or when the previous call
+    # lost more than 2 % of its rows; the call above -- all rows alive -- switched that off)
+    launched = model.engine.info()['launches_total']
     dead = thetas[kill]
-    assert np.all(np.isneginf(model.engine.lnpost(holder['plan'], dead)))
+    assert np.all(np.isneginf(model.engine.lnpost(holder['plan'], dead[1:])))     # unscreened
+    assert model.engine.info()['launches_total'] > launched
+    launched = model.engine.info()['launches_total']
+    assert np.all(np.isneginf(model.engine.lnpost(holder['plan'], dead)))         # screened
+    assert np.all(np.isneginf(model.engine.lnpost(holder['plan'], dead[:100])))   # small
     assert model.engine.info()['launches_total'] == launched
 
 
