@@ -643,6 +643,7 @@ def run_ours(args):
                                   pool=BatchPool(model), live_dangerously=True)
             smp._random.seed(7)
             pos, lnp, _ = smp.run_mcmc(start, 3)
+            smp.reset()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             smp.run_mcmc(pos, iters, lnprob0=lnp)

@@ -280,7 +280,8 @@ struct EnsProfile {
     fprintf(stderr,
             "[psfmc] %s: %lld posterior calls, %lld rows (%lld on the GPU); per call (us): "
             "draws+proposals %.1f, closed-form priors %.1f, begin %.1f, priors behind the GPU "
-            "%.1f, logs behind the GPU %.1f, wait %.1f, combine+accept %.1f, store %.1f; "
+            "%.1f, logs + draws + chain storage behind the GPU %.1f, wait %.1f, combine+accept "
+            "%.1f, last store %.1f; "
             "whole run %.1f\n",
             what, calls, rows, rows_gpu, 1e6 * t[0] / calls, 1e6 * t[1] / calls,
             1e6 * t[2] / calls, 1e6 * t[3] / calls, 1e6 * t[4] / calls, 1e6 * t[5] / calls,
@@ -503,11 +504,29 @@ inline int run_ensemble(const LnlikeCalls &eng, const psfmc_prior_plan *pl, psfm
     });
     staged = 0;
   };
-  // (an error return leaves the iterations completed so far in the chain)
+  // An iteration is stored while the GPU works on the first half-step of the NEXT one (the
+  // positions do not change before that half-step's acceptance); the last one, and
+  // whatever is still staged, on the way out -- also of an error return.
+  long long pending_it = -1;
+  auto store_pending = [&]() {
+    if (pending_it < 0) return;
+    const long long ind = e->chain_start + pending_it / thin;
+    pending_it = -1;
+    if (ind >= e->chain_len || !(e->chain || e->lnprob_chain)) return;
+    if (!staged) stage_first = ind;
+    if (e->chain)
+      memcpy(stage.data() + (size_t)staged * k * D, e->pos, (size_t)k * D * sizeof(double));
+    if (e->lnprob_chain)
+      memcpy(stage_lnp.data() + (size_t)staged * k, e->lnprob, (size_t)k * sizeof(double));
+    if (++staged == T) flush();
+  };
   struct FlushGuard {
     std::function<void()> fn;
     ~FlushGuard() { fn(); }
-  } flush_guard{flush};
+  } flush_guard{[&]() {
+    store_pending();
+    flush();
+  }};
   draw(zz, partner, lu, half, k - half);
   for (long long it = 0; it < n_iter; ++it) {
     for (int h = 0; h < 2; ++h) {
@@ -548,6 +567,7 @@ inline int run_ensemble(const LnlikeCalls &eng, const psfmc_prior_plan *pl, psfm
           }
         });
         if (more) draw(zz_next, partner_next, lu_next, nc, ns);
+        store_pending();
       };
       if (wk.prof.on) wk.prof.t[0] += EnsProfile::now() - t_half;
       int rc = lnpost_rows(eng, pl, q, ns, D, lnl, newlnp.data(), wk, scratch, &overlap);
@@ -578,20 +598,12 @@ inline int run_ensemble(const LnlikeCalls &eng, const psfmc_prior_plan *pl, psfm
       }
       if (wk.prof.on) wk.prof.t[6] += EnsProfile::now() - t_acc;
     }
+    if (it % thin == 0) pending_it = it;
+  }
+  {
     const double t_store = wk.prof.on ? EnsProfile::now() : 0.0;
-    if (it % thin == 0) {
-      const long long ind = e->chain_start + it / thin;
-      if (ind < e->chain_len) {
-        if (e->chain || e->lnprob_chain) {
-          if (!staged) stage_first = ind;
-          if (e->chain)
-            memcpy(stage.data() + (size_t)staged * k * D, e->pos, (size_t)k * D * sizeof(double));
-          if (e->lnprob_chain)
-            memcpy(stage_lnp.data() + (size_t)staged * k, e->lnprob, (size_t)k * sizeof(double));
-          if (++staged == T) flush();
-        }
-      }
-    }
+    store_pending();
+    flush();
     if (wk.prof.on) wk.prof.t[7] += EnsProfile::now() - t_store;
   }
   wk.prof.report("ensemble_run");

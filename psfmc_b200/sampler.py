@@ -115,9 +115,35 @@ class EnsembleSampler(object):
     def reset(self):
         self.iterations = 0
         self.naccepted = np.zeros(self.k)
-        self._chain = np.empty((self.k, 0, self.dim))
-        self._lnprob = np.empty((self.k, 0))
+        # storage with spare capacity: emcee concatenates a fresh block onto the chain in
+        # every sample() call, which copies the whole chain each time a long run is
+        # advanced in pieces (fitting.advance); here the arrays grow geometrically and
+        # `chain` / `lnprobability` are views of the filled part
+        self._chain_buf = np.zeros((self.k, 0, self.dim))
+        self._lnprob_buf = np.zeros((self.k, 0))
+        self._stored = 0
         self._blobs = []
+
+    @property
+    def _chain(self):
+        return self._chain_buf[:, :self._stored]
+
+    @property
+    def _lnprob(self):
+        return self._lnprob_buf[:, :self._stored]
+
+    def _reserve(self, extra):
+        """Room for ``extra`` more stored iterations; returns the index of the first."""
+        start, need = self._stored, self._stored + int(extra)
+        if need > self._chain_buf.shape[1]:
+            capacity = max(need, 2 * self._chain_buf.shape[1])
+            chain = np.zeros((self.k, capacity, self.dim))
+            lnprob = np.zeros((self.k, capacity))
+            chain[:, :start] = self._chain_buf[:, :start]
+            lnprob[:, :start] = self._lnprob_buf[:, :start]
+            self._chain_buf, self._lnprob_buf = chain, lnprob
+        self._stored = need
+        return start
 
     def clear_blobs(self):
         self._blobs = []
@@ -210,7 +236,7 @@ class EnsembleSampler(object):
                 first, count = first + done, count - done
             if count > 0:
                 engine.ensemble_run(holder['plan'], p, lnprob, key, mt_pos, count, a=self.a,
-                                    chain=self._chain, lnprob_chain=self._lnprob,
+                                    chain=self._chain_buf, lnprob_chain=self._lnprob_buf,
                                     chain_start=start + first // thin, thin=thin,
                                     n_accepted=self.naccepted)
         elif count > 0:
@@ -246,17 +272,9 @@ class EnsembleSampler(object):
         lnprob = np.array(lnprob, dtype=np.float64)
         if np.any(np.isnan(lnprob)):
             raise ValueError('The initial lnprob was NaN.')
-        start = self._chain.shape[1]
+        start = self._stored
         if storechain:
-            nstore = int(iterations / thin)
-            if self._chain.shape[1] == 0:     # (nothing to copy: fresh, lazily zeroed pages)
-                self._chain = np.zeros((self.k, nstore, self.dim))
-                self._lnprob = np.zeros((self.k, nstore))
-            else:
-                self._chain = np.concatenate(
-                    (self._chain, np.zeros((self.k, nstore, self.dim))), axis=1)
-                self._lnprob = np.concatenate(
-                    (self._lnprob, np.zeros((self.k, nstore))), axis=1)
+            start = self._reserve(int(iterations / thin))
         native = self._native(p) if blobs is None else None
         if native is not None:
             single = getattr(self, '_one_call', False)
@@ -290,8 +308,8 @@ class EnsembleSampler(object):
                             blobs[dst] = blob[src]
             if storechain and it % thin == 0:
                 ind = start + it // thin
-                self._chain[:, ind, :] = p
-                self._lnprob[:, ind] = lnprob
+                self._chain_buf[:, ind, :] = p
+                self._lnprob_buf[:, ind] = lnprob
                 if blobs is not None:
                     self._blobs.append(list(blobs))
             if blobs is not None:

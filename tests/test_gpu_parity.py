@@ -290,6 +290,23 @@ def test_multi_device_sharding(cuda_library, c1_golden):
     with pytest.raises(ValueError):
         multi.engine.lnlike(thetas[:, :17])
     assert np.array_equal(want, multi.log_likelihood_batch(thetas))
+    # the sampler loop inside the library (psfmc_ensemble_run) over the device list:
+    # the chain of the one-device engine
+    from psfmc_b200 import BatchPool
+    from psfmc_b200.sampler import EnsembleSampler
+    centre = np.array(c1_golden['theta'][0])
+    start = centre + 1e-3 * np.random.RandomState(3).standard_normal((600, len(centre))) * \
+        np.maximum(np.abs(centre), 1.0)
+    chains = []
+    for model in (single, multi):
+        sampler = EnsembleSampler(600, len(centre), model.log_posterior,
+                                  kwargs={'model': model}, pool=BatchPool(model))
+        sampler._random.seed(4)
+        sampler.run_mcmc(start, 10)
+        assert model._sampler_plan
+        chains.append((sampler.chain.copy(), sampler.lnprobability.copy()))
+    assert np.array_equal(chains[0][0], chains[1][0])
+    assert np.array_equal(chains[0][1], chains[1][1])
 
 
 def test_multi_process_sharded_pool_nccl(cuda_library, tmp_path):

@@ -34,6 +34,7 @@ def main():
                           pool=BatchPool(model), live_dangerously=True)
     smp._random.seed(7)
     pos, lnp, _ = smp.run_mcmc(start, 3)
+    smp.reset()
     info0 = model.engine.info()
     t0 = time.perf_counter()
     pos, lnp, _ = smp.run_mcmc(pos, iters, lnprob0=lnp)
