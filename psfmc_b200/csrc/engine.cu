@@ -1564,14 +1564,14 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       std::vector<unsigned short> maskw(N * 8, 0);
       long long n_good = 0;
       for (size_t e = 0; e < npx; ++e) {
+        const size_t y = e / N, x = e % N, o = y * N + fused_ow_index(x);
         if (bad[e]) {
-          ow[e].x = 0.0f;
-          ow[e].y = 1.0e30f;
+          ow[o].x = 0.0f;
+          ow[o].y = 1.0e30f;
           continue;
         }
-        ow[e].x = (float)obs[e];
-        ow[e].y = fabsf((float)ovar[e]);
-        const size_t y = e / N, x = e % N;
+        ow[o].x = (float)obs[e];
+        ow[o].y = fabsf((float)ovar[e]);
         maskw[y * 8 + (x & 7)] |= (unsigned short)(1u << (x >> 3));
         ++n_good;
       }
@@ -1656,7 +1656,8 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
         const size_t ry = sb >> 2, rx = sb & 3;
         for (size_t y = 0; y < M; ++y)
           for (size_t x = 0; x < M; ++x) {
-            const size_t e = (4 * y + ry) * NT + 4 * x + rx, o = (sb * M + y) * M + x;
+            const size_t e = (4 * y + ry) * NT + 4 * x + rx,
+                         o = (sb * M + y) * M + fused_ow_index(x);
             if (bad[e]) {
               ow[o].x = 0.0f;
               ow[o].y = 1.0e30f;

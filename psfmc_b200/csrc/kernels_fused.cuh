@@ -567,12 +567,20 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   // last (L2 latency hidden behind the whole inverse transform)
   float2 o[16];
   // (sub-image tables of a tiled frame follow each other)
-  const float2 *owr = P.ow + (sub * PSFMC_FUSED_N + y) * PSFMC_FUSED_N + R.l;
+  // (pixel x = l + 8 j of a row sits at position 16 (j >> 1) + 2 l + (j & 1) of the row's
+  // table, see fused_ow_index: a thread's pixels j = 2 i, 2 i + 1 are one 16-byte load, the
+  // eight threads of a row read 128 contiguous bytes)
+  const float4 *owr = reinterpret_cast<const float4 *>(
+      P.ow + (sub * PSFMC_FUSED_N + y) * PSFMC_FUSED_N + 2 * R.l);
   const unsigned mw = __ldg(P.maskw + (sub * PSFMC_FUSED_N + y) * 8 + R.l);   // bit j: pixel
                                                                          // x = l + 8 j is good
   if (PREFETCH) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
+    for (int i = 0; i < 8; ++i) {
+      const float4 q = __ldg(owr + 8 * i);
+      o[2 * i] = make_float2(q.x, q.y);
+      o[2 * i + 1] = make_float2(q.z, q.w);
+    }
   }
   cplx<float> a[8], bb[8];   // a[k2] = Y[2 l + 16 k2], bb[k2] = Y[2 l + 1 + 16 k2]
 #pragma unroll
@@ -626,7 +634,11 @@ __device__ __forceinline__ double fused_rows_inverse(const FusedParams &P, smem_
   }
   if (!PREFETCH) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 8 * j);
+    for (int i = 0; i < 8; ++i) {
+      const float4 q = __ldg(owr + 8 * i);
+      o[2 * i] = make_float2(q.x, q.y);
+      o[2 * i + 1] = make_float2(q.z, q.w);
+    }
   }
   if (!PADDED && __builtin_expect(hs != nullptr, 0)) {
     // the hot pixels' own contribution, convolved exactly: value x real-space kernel
@@ -1199,6 +1211,12 @@ inline void fused_spectrum_layout(const cplx<double> *spec64, int n_psf,
           specx4[(size_t)k * N + ky] = o;
       }
   }
+}
+
+// position of pixel x in a row of the (obs, ovar) table of the row passes' epilogue
+inline size_t fused_ow_index(size_t x) {
+  const size_t l = x & 7, j = x >> 3;
+  return 16 * (j >> 1) + 2 * l + (j & 1);
 }
 
 struct FusedBuffers {
