@@ -1705,8 +1705,12 @@ int create_engine(const psfmc_desc *d, EngineBase **out) {
       std::vector<float2> ow(npx), ctw(256);
       for (size_t e = 0; e < npx; ++e) {   // over the transform frame (padding: excluded)
         float v = fabsf((float)ovar[e]);
-        ow[e].x = (float)obs[e];
-        ow[e].y = bad[e] ? -v : v;
+        // pixel x = l + 16 j of a row at position 32 (j >> 1) + 2 l + (j & 1): the pixels
+        // j = 2 i, 2 i + 1 of a row-pass thread are one 16-byte load
+        const size_t y = e / N, x = e % N, l = x & 15, j = x >> 4;
+        const size_t o = y * N + 32 * (j >> 1) + 2 * l + (j & 1);
+        ow[o].x = (float)obs[e];
+        ow[o].y = bad[e] ? -v : v;
       }
       cluster_twiddles(ctw.data());
       if ((rc = upload(&ds.cspec, cspec)) || (rc = upload(&ds.cspecx, cspecx)) ||

@@ -536,9 +536,16 @@ cluster256_lnlike_kernel(const ClusterParams CP, const FoldParams F) {
     // the cluster barrier
     float2 o[16];
     {
-      const float2 *owr = P.ow + (64 * (int)rank + yl0) * PSFMC_CL_N + R.l;
+      // (pixel x = l + 16 j sits at position 32 (j >> 1) + 2 l + (j & 1) of its row, see
+      // cluster_ow_index: a thread's pixels j = 2 i, 2 i + 1 are one 16-byte load)
+      const float4 *owr = reinterpret_cast<const float4 *>(
+          P.ow + (64 * (int)rank + yl0) * PSFMC_CL_N + 2 * R.l);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 16 * j);
+      for (int i = 0; i < 8; ++i) {
+        const float4 q = __ldg(owr + 16 * i);
+        o[2 * i] = make_float2(q.x, q.y);
+        o[2 * i + 1] = make_float2(q.z, q.w);
+      }
     }
     cl_wait();
 
@@ -550,9 +557,13 @@ cluster256_lnlike_kernel(const ClusterParams CP, const FoldParams F) {
       const int y = 64 * (int)rank + yl;
       if (PADDED && y - R.rr >= F.Hr) continue;   // both rows of the warp are padding
       if (it) {
-        const float2 *owr = P.ow + y * PSFMC_CL_N + R.l;
+        const float4 *owr = reinterpret_cast<const float4 *>(P.ow + y * PSFMC_CL_N + 2 * R.l);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = __ldg(owr + 16 * j);
+        for (int i = 0; i < 8; ++i) {
+          const float4 q = __ldg(owr + 16 * i);
+          o[2 * i] = make_float2(q.x, q.y);
+          o[2 * i + 1] = make_float2(q.z, q.w);
+        }
       }
       smem_addr_t ra[PSFMC_CL_CTAS], rm[PSFMC_CL_CTAS];
 #pragma unroll
