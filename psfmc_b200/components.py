@@ -135,11 +135,9 @@ class ComponentBase(object):
         """
         block = np.asarray(block, dtype=np.float64)
         total = np.zeros(block.shape[0])
-        start = 0
-        for _, prior, length in self.free_parameters():
+        for _, prior, start, length in self.prior_terms():
             if column_logp is not None:
                 total = total + np.sum(column_logp[:, start:start + length], axis=1)
-                start += length
                 continue
             cols = block[:, start:start + length]
             if getattr(prior, 'discrete', False):
@@ -147,8 +145,18 @@ class ComponentBase(object):
             batched = getattr(prior, 'logp_batch', prior.logp)
             with np.errstate(all='ignore'):
                 total = total + np.sum(batched(cols), axis=1)
-            start += length
         return total
+
+    def prior_terms(self):
+        """[(attribute, prior, first column, n_columns)] in the order the reference ADDS
+        the priors up -- the insertion order of ``_priors`` (ComponentBase.py:121-129:
+        ``for prior in self._priors.values()``) -- with the columns of the component's
+        block, which is laid out in sorted attribute order (:meth:`free_parameters`)."""
+        where, start = {}, 0
+        for name, _, length in self.free_parameters():
+            where[name] = (start, length)
+            start += length
+        return [(name, prior) + where[name] for name, prior in self._priors.items()]
 
     def column_of(self, attr, block, sub=0):
         """Per-walker values of parameter ``attr`` given the component's block."""

@@ -280,9 +280,11 @@ class MultiComponentModel(object):
         for num, comp in enumerate(self.components):
             where = {}
             for name, _, length in comp.free_parameters():
-                terms.append((num, start, length))
                 where[name] = start
                 start += length
+            # terms in the order the reference adds them (ComponentBase.prior_terms)
+            for name, _, _, length in comp.prior_terms():
+                terms.append((num, where[name], length))
             if isinstance(comp, Sersic):
                 rule = _lib.PriorRule()
                 rule.component = num
