@@ -687,7 +687,8 @@ def run_ours(args):
                     ('c3', 2): 'r2_cluster256_ncu_summary.json'}.get(
                         (args.workload, info['path']))
         if ncu_file and args.walkers == 0 and world == 1:
-            for name in (ncu_file, ncu_file.replace('r2_', 'r1_')):
+            for name in (ncu_file.replace('r2_', 'r2b_'), ncu_file,
+                         ncu_file.replace('r2_', 'r1_')):
                 try:
                     with open(os.path.join(ROOT, 'profiles', name)) as fobj:
                         ncu = json.load(fobj)
