@@ -631,8 +631,11 @@ def run_ours(args):
     # inside the library: psfmc_ensemble_run, what this package's sampler calls; beside it
     # the same sampler with its numpy loop, at the bench ensemble and at the reference
     # example's 250 walkers (examples/run_example.py:9)
+    # (N > 1: every rank runs the same seeded sampler on a ShardedPool; the library loop
+    # then evaluates this rank's share of every half-ensemble and gathers the lnL over
+    # peer memory, PSFMC_ENS_SHARDED)
     loop = None
-    if world == 1:
+    if True:
         from psfmc_b200.sampler import EnsembleSampler
         loop = {}
 
@@ -640,14 +643,15 @@ def run_ours(args):
             os.environ['PSFMC_NATIVE_SAMPLER'] = '1' if native else '0'
             start = thetas[0][:nwalk]
             smp = EnsembleSampler(nwalk, ndim, model.log_posterior, kwargs={'model': model},
-                                  pool=BatchPool(model), live_dangerously=True)
+                                  pool=(ShardedPool(model) if world > 1 else BatchPool(model)),
+                                  live_dangerously=True)
             smp._random.seed(7)
             pos, lnp, _ = smp.run_mcmc(start, 3)
             smp.reset()
-            torch.cuda.synchronize()
+            barrier()
             t0 = time.perf_counter()
             smp.run_mcmc(pos, iters, lnprob0=lnp)
-            return nwalk * iters / (time.perf_counter() - t0)
+            return nwalk * iters / max_over_ranks(time.perf_counter() - t0)
         try:
             loop['library'] = round(sampler_rate(walkers, True, args.steps), 1)
             loop['numpy_loop'] = round(sampler_rate(walkers, False, max(10, args.steps // 3)), 1)
@@ -660,7 +664,11 @@ def run_ours(args):
             loop['note'] = ('stretch-move iterations of one ensemble end to end (proposals, '
                             'log-priors, lnL through host buffers, acceptance, chain storage): '
                             'library = psfmc_ensemble_run, numpy_loop = the same sampler with '
-                            'its Python loop; *_small = the reference example\'s ensemble size')
+                            'its Python loop; *_small = the reference example\'s ensemble size'
+                            + ('' if world == 1 else
+                               '; {} ranks, each its share of every half-ensemble: library = '
+                               'PSFMC_ENS_SHARDED (lnL over peer memory), numpy_loop = '
+                               'ShardedPool.map_batch (NCCL all_gather)'.format(world)))
         finally:
             os.environ.pop('PSFMC_NATIVE_SAMPLER', None)
 

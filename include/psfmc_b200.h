@@ -320,7 +320,15 @@ typedef struct psfmc_ensemble {
   int64_t chain_start;   /* index the first stored iteration goes to                   */
   int64_t thin;          /* store every thin-th iteration (>= 1)                       */
   double *n_accepted;    /* [k], incremented (emcee keeps it as float64)               */
+  int64_t flags;         /* PSFMC_ENS_*                                                */
 } psfmc_ensemble;
+/* One process per GPU (torchrun): every rank makes the same psfmc_ensemble_run call on the
+ * same ensemble and random state -- the proposals are then identical on all ranks -- and
+ * evaluates only its contiguous share of every half-ensemble; the lnL of all rows is
+ * gathered over peer memory (psfmc_peer_create / _connect first; the mailbox capacity must
+ * cover n_walkers / 2). Non-finite float32 results are -inf here (no float64 repeat, as
+ * for every device-pointer call). */
+#define PSFMC_ENS_SHARDED 1
 /* Advances the ensemble by n_iterations stretch-move iterations. Errors: a proposal with
  * an infinite / NaN coordinate (emcee raises ValueError), a failing callback. */
 int psfmc_ensemble_run(psfmc_engine *engine, const psfmc_prior_plan *priors,

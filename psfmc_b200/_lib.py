@@ -123,7 +123,11 @@ class Ensemble(ctypes.Structure):
                 ('lnprob_chain', ctypes.POINTER(ctypes.c_double)),
                 ('chain_len', ctypes.c_int64), ('chain_start', ctypes.c_int64),
                 ('thin', ctypes.c_int64),
-                ('n_accepted', ctypes.POINTER(ctypes.c_double))]
+                ('n_accepted', ctypes.POINTER(ctypes.c_double)),
+                ('flags', ctypes.c_int64)]
+
+
+ENS_SHARDED = 1
 
 
 # every symbol include/psfmc_b200.h declares

@@ -176,6 +176,10 @@ struct EngineBase {
   // device 0: evaluate B device-resident rows into the engine's own lnL buffer
   virtual int lnlike_local(const double *theta, long long B, long long ld, void *stream,
                            double **lnl_out) = 0;
+  // device 0: B host rows -> the engine's own theta buffer (asynchronous, on the engine's
+  // stream, which is returned)
+  virtual int shard_upload(const double *theta_host, long long B, long long ld,
+                           const double **theta_dev, void **stream) = 0;
   bool profiling = false;
   // float64 rescue on the device (float32 engines, see lnlike_host_graph): the owner
   // sets scan_wanted and, once it exists, the float64 engine; every host call reports
@@ -538,6 +542,20 @@ struct Engine : EngineBase {
     *lnl_out = d.lnl.ptr;
     if (B <= 0) return 0;
     return enqueue(d, theta, B, ld, d.lnl.ptr, (cudaStream_t)stream);
+  }
+
+  int shard_upload(const double *theta_host, long long B, long long ld,
+                   const double **theta_dev, void **stream) override {
+    DeviceState<T> &d = devs[0];
+    CUDA_TRY(cudaSetDevice(d.ordinal));
+    if (d.theta.ensure((size_t)(B > 0 ? B * ld : 1)))
+      return fail(PSFMC_ERR_CUDA, "device allocation failed (theta)");
+    if (B > 0)
+      CUDA_TRY(cudaMemcpyAsync(d.theta.ptr, theta_host, (size_t)(B * ld) * sizeof(double),
+                               cudaMemcpyHostToDevice, d.stream));
+    *theta_dev = d.theta.ptr;
+    *stream = (void *)d.stream;
+    return 0;
   }
 
 #ifndef PSFMC_EMU
@@ -1861,6 +1879,10 @@ struct psfmc_engine {
   // (stable addresses: the host call is then one replayed graph, no staging copies)
   PinBuf<double> ens_q, ens_lnl, ens_scratch;
   LnpostWork ens_work;
+  // sharded loop (PSFMC_ENS_SHARDED): the exchange in flight
+  void *ens_stream = nullptr;
+  double *ens_gathered = nullptr;
+  long long ens_total = 0;
 };
 
 // A float32 evaluation that came back non-finite is repeated in float64 on the GPU:
@@ -2292,6 +2314,60 @@ static int ens_begin(void *self, const double *theta, long long n, long long ld,
 }
 static int ens_end(void *self) { return psfmc_lnlike_batch_end((psfmc_engine *)self); }
 
+// One process per GPU: this rank's contiguous share of the n rows (the split of
+// distributed.py:shard_bounds and of the in-process device list) goes through
+// psfmc_lnlike_batch_exchange; the gathered lnL of all rows comes back from this rank's
+// mailbox into the (page-locked) lnl buffer.
+static int ens_shard_begin(void *self, const double *theta, long long n, long long ld,
+                           double *lnl) {
+#ifdef PSFMC_EMU
+  (void)self; (void)theta; (void)n; (void)ld; (void)lnl;
+  return fail(PSFMC_ERR_UNSUPPORTED, "the sharded loop needs real devices");
+#else
+  psfmc_engine *engine = (psfmc_engine *)self;
+  PeerState &ps = engine->peer;
+  const long long base = n / ps.world, extra = n % ps.world;
+  const long long lo = ps.rank * base + (ps.rank < extra ? ps.rank : extra);
+  const long long count = base + (ps.rank < extra ? 1 : 0);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  const double *theta_dev = nullptr;
+  void *stream = nullptr;
+  int rc = engine->impl->shard_upload(theta + lo * ld, count, ld, &theta_dev, &stream);
+  if (!rc) rc = psfmc_lnlike_batch_exchange(engine, theta_dev, count, ld, lo, n, nullptr, stream);
+  double *gathered = nullptr;
+  if (!rc) rc = psfmc_peer_gathered(engine, &gathered);
+  if (!rc) {
+    cudaSetDevice(engine->impl->first_ordinal);
+    if (cudaMemcpyAsync(lnl, gathered, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
+                        (cudaStream_t)stream) != cudaSuccess)
+      rc = fail(PSFMC_ERR_CUDA, "copy of the gathered lnL failed");
+  }
+  engine->ens_stream = stream;
+  engine->ens_gathered = lnl;
+  engine->ens_total = n;
+  cudaSetDevice(prev);
+  return rc;
+#endif
+}
+static int ens_shard_end(void *self) {
+#ifdef PSFMC_EMU
+  (void)self;
+  return fail(PSFMC_ERR_UNSUPPORTED, "the sharded loop needs real devices");
+#else
+  psfmc_engine *engine = (psfmc_engine *)self;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(engine->impl->first_ordinal);
+  const cudaError_t err = cudaStreamSynchronize((cudaStream_t)engine->ens_stream);
+  cudaSetDevice(prev);
+  if (err != cudaSuccess) return fail(PSFMC_ERR_CUDA, cudaGetErrorString(err));
+  for (long long b = 0; b < engine->ens_total; ++b)
+    if (!std::isfinite(engine->ens_gathered[b])) engine->ens_gathered[b] = -INFINITY;
+  return 0;
+#endif
+}
+
 int psfmc_lnpost_batch(psfmc_engine *engine, const psfmc_prior_plan *priors,
                        const double *theta, int64_t n_batch, int64_t ld, double *lnpost_out) {
   if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
@@ -2345,6 +2421,14 @@ int psfmc_ensemble_run(psfmc_engine *engine, const psfmc_prior_plan *priors,
   cudaSetDevice(prev);
   if (bad) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
   LnlikeCalls calls{engine, ens_begin, ens_end};
+  if (ens->flags & PSFMC_ENS_SHARDED) {
+    if (!engine->peer.world)
+      return fail(PSFMC_ERR_INVALID_ARG, "PSFMC_ENS_SHARDED: call psfmc_peer_connect first");
+    if ((long long)half > engine->peer.capacity)
+      return fail(PSFMC_ERR_INVALID_ARG,
+                  "PSFMC_ENS_SHARDED: the mailbox capacity is below n_walkers / 2");
+    calls = LnlikeCalls{engine, ens_shard_begin, ens_shard_end};
+  }
   int rc = run_ensemble(calls, priors, ens, n_iterations, engine->ens_q.ptr, engine->ens_lnl.ptr,
                         engine->ens_scratch.ptr, engine->ens_work);
   switch (rc) {

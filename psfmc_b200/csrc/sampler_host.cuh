@@ -24,6 +24,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -148,9 +149,17 @@ inline int check_prior_plan(const psfmc_prior_plan *pl, long long ld, const char
 // [0, n) into contiguous ranges, the calling thread takes the first.
 class HostPool {
  public:
+  // One pool per process, never destroyed (its threads end with the process: a static
+  // destructor would have to join them, and in a forked child -- multiprocessing workers,
+  // which inherit the object but not the threads -- that join would never return). A
+  // forked child starts with a fresh, empty pool.
   static HostPool &instance() {
-    static HostPool pool;
-    return pool;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      current() = new HostPool();
+      pthread_atfork(nullptr, nullptr, [] { current() = new HostPool(); });
+    });
+    return *current();
   }
   template <typename F>
   void parallel_rows(long long n, long long min_rows_per_thread, const F &fn) {
@@ -182,17 +191,11 @@ class HostPool {
     }
     job_ = nullptr;
   }
-  ~HostPool() {
-    {
-      std::lock_guard<std::mutex> lk(m_);
-      stop_.store(true);
-    }
-    cv_.notify_all();
-    for (auto &t : threads_)
-      if (t.joinable()) t.join();
-  }
-
  private:
+  static HostPool *&current() {
+    static HostPool *pool = nullptr;
+    return pool;
+  }
   static void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)
     __builtin_ia32_pause();

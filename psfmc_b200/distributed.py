@@ -145,6 +145,7 @@ class PeerExchange(object):
         engine.peer_connect(self.rank, handles)
         dist.barrier(group=group)
         self.capacity = int(capacity)
+        engine._peer_exchange = self      # (an engine has one mailbox: later users share it)
 
     def lnlike(self, theta_dev, n_rows, ld, gathered, stream, row_offset=0):
         """``theta_dev``: float64 CUDA tensor holding the FULL batch (identical on every
@@ -183,6 +184,42 @@ class ShardedPool(object):
         (B, D) -> ((B,) lnpost, None)."""
         block = np.ascontiguousarray(block, dtype=np.float64)
         return self._evaluator(block), None
+
+    def native_sampler(self, start_positions):
+        """The sampler's loop inside the library for a one-process-per-GPU job
+        (``psfmc_ensemble_run`` with ``PSFMC_ENS_SHARDED``): every rank runs the same
+        seeded loop, evaluates its contiguous share of every half-ensemble and the lnL of
+        all rows is gathered over peer memory (:class:`PeerExchange`). NCCL groups on
+        CUDA devices only; otherwise -- and with ``PSFMC_NATIVE_SAMPLER=0`` -- None: the
+        numpy loop with :meth:`map_batch`. Non-finite float32 results are -inf on this
+        path (no float64 repeat)."""
+        import os
+        import torch.distributed as dist
+        if os.environ.get('PSFMC_NATIVE_SAMPLER', '1') == '0':
+            return None
+        if not (dist.is_available() and dist.is_initialized()) or \
+                dist.get_backend(self.group) != 'nccl':
+            return None
+        engine = getattr(self.model, 'engine', None)
+        if engine is None or not hasattr(engine, 'ensemble_run') or \
+                not hasattr(self.model, 'native_sampler_plan'):
+            return None
+        holder = self.model.native_sampler_plan(start_positions)
+        # (every rank must take the same branch: the plan is validated on the same rows)
+        if holder is None:
+            return None
+        need = max(int(len(start_positions)), 2)
+        peer = getattr(engine, '_peer_exchange', None)
+        if peer is None:
+            try:
+                peer = PeerExchange(engine, max(need, 65536), self.group)
+            except Exception:            # no peer access between the ranks' devices
+                return None
+        if need // 2 > peer.capacity:
+            return None
+        sharded = dict(holder)
+        sharded['sharded'] = True
+        return engine, sharded
 
     def close(self):
         pass

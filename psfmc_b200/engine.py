@@ -196,13 +196,15 @@ class LikelihoodEngine(object):
 
     def ensemble_run(self, plan, pos, lnprob, mt_key, mt_pos, n_iterations, a=2.0,
                      chain=None, lnprob_chain=None, chain_start=0, thin=1,
-                     n_accepted=None):
+                     n_accepted=None, sharded=False):
         """``n_iterations`` stretch-move iterations of the whole ensemble inside the
         library (emcee 2.x semantics, numpy RandomState stream; see the header).
         ``pos`` (k, D), ``lnprob`` (k,), ``mt_key`` (624,) uint32, ``n_accepted`` (k,)
         are updated in place; ``mt_pos`` is a ``ctypes.c_int32``; ``chain``
         (k, L, D) / ``lnprob_chain`` (k, L) receive every ``thin``-th iteration from
-        index ``chain_start`` on."""
+        index ``chain_start`` on. ``sharded``: one process per GPU -- every rank makes
+        the same call and evaluates its share of every half-ensemble, the lnL is gathered
+        over peer memory (:meth:`peer_create` / :meth:`peer_connect` first)."""
         dbl_p = ctypes.POINTER(ctypes.c_double)
         for arr, dtype in ((pos, np.float64), (lnprob, np.float64), (mt_key, np.uint32),
                            (chain, np.float64), (lnprob_chain, np.float64),
@@ -233,6 +235,7 @@ class LikelihoodEngine(object):
             ens.lnprob_chain = lnprob_chain.ctypes.data_as(dbl_p)
             ens.chain_len = lnprob_chain.shape[1]
         ens.chain_start, ens.thin = int(chain_start), int(thin)
+        ens.flags = _lib.ENS_SHARDED if sharded else 0
         if n_accepted is not None:
             if n_accepted.shape != (pos.shape[0],):
                 raise ValueError('n_accepted must be (k,)')

@@ -351,9 +351,31 @@ for count in (1001, 64, 999):
     stream.synchronize()
     peer.append(gathered.cpu().numpy()[:count])
 alone = raw.log_likelihood_batch(thetas)
+# the sampler's loop inside the library, sharded (psfmc_ensemble_run + PSFMC_ENS_SHARDED:
+# every rank the same seeded loop, its share of every half-ensemble, lnL over peer
+# memory) against the same loop on this rank's engine alone; 250 walkers (ragged shards
+# of 125 rows) and 1000
+from psfmc_b200 import BatchPool
+from psfmc_b200.sampler import EnsembleSampler
+import json
+centre = np.array(json.load(open(os.path.join({root!r}, 'tests', 'golden',
+                                              'c1_golden.json')))['theta'][0])
+chains = {{}}
+for nwalk in (250, 1000):
+    start = centre + 1e-3 * np.random.RandomState(3).standard_normal((nwalk, len(centre))) * \
+        np.maximum(np.abs(centre), 1.0)
+    for name, pl in (('sharded', ShardedPool(model)), ('single', BatchPool(model))):
+        smp = EnsembleSampler(nwalk, len(centre), model.log_posterior,
+                              kwargs={{'model': model}}, pool=pl)
+        smp._random.seed(4)
+        smp.run_mcmc(start, 8)
+        if name == 'sharded':
+            assert pl.native_sampler(start) is not None, 'the sharded library loop was not used'
+        chains['%s_%d' % (name, nwalk)] = smp.chain.copy()
+        chains['%s_lnp_%d' % (name, nwalk)] = smp.lnprobability.copy()
 np.savez(os.path.join({out!r}, 'rank%d.npz' % dist.get_rank()), got=got, listed=listed,
          want=model.log_posterior_batch(thetas), alone=alone, peer0=peer[0],
-         peer1=peer[1], peer2=peer[2])
+         peer1=peer[1], peer2=peer[2], **chains)
 dist.barrier()
 dist.destroy_process_group()
 """.format(root=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
@@ -371,6 +393,10 @@ dist.destroy_process_group()
         assert np.array_equal(data['peer0'], data['alone'])
         assert np.array_equal(data['peer1'], data['alone'][:64])
         assert np.array_equal(data['peer2'], data['alone'][:999])
+        for nwalk in (250, 1000):
+            for key in ('%d' % nwalk, 'lnp_%d' % nwalk):
+                assert np.array_equal(data['sharded_' + key], data['single_' + key]), key
+                assert np.array_equal(data['sharded_' + key], first['sharded_' + key]), key
 
 
 @pytest.mark.parametrize('table', ['1', '0'])

@@ -199,6 +199,39 @@ def test_lnpost_batch_leaves_dead_rows_out(emu_library):
     assert model.engine.info()['launches_total'] == launched
 
 
+def test_host_threads_and_fork(emu_library, monkeypatch):
+    """The library's host threads (per-row work of large batches) are not inherited by a
+    forked child: the child gets a fresh pool and computes the same numbers."""
+    import os
+    import time
+    from psfmc_b200.synthetic import draw_walkers_fast
+    monkeypatch.setenv('PSFMC_HOST_THREADS', '4')
+    model = _small_model(emu_library, True)
+    thetas = draw_walkers_fast(model, 1100, seed=12)
+    holder = model.native_sampler_plan(thetas[:16])
+    want = model.engine.lnpost(holder['plan'], thetas)       # (threads exist from here on)
+    pid = os.fork()
+    if pid == 0:
+        code = 1
+        try:
+            got = model.engine.lnpost(holder['plan'], thetas)
+            code = 0 if np.array_equal(got, want) else 2
+        finally:
+            os._exit(code)
+    deadline = time.time() + 120
+    while time.time() < deadline:
+        done, status = os.waitpid(pid, os.WNOHANG)
+        if done:
+            assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0, status
+            break
+        time.sleep(0.05)
+    else:
+        os.kill(pid, 9)
+        os.waitpid(pid, 0)
+        raise AssertionError('the forked child hung in the library')
+    assert np.array_equal(model.engine.lnpost(holder['plan'], thetas), want)
+
+
 def test_ensemble_run_rejects_bad_input(emu_library):
     from psfmc_b200 import _lib
     model = _small_model(emu_library, False)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """The stretch-move loop inside the library (psfmc_ensemble_run) on the C1 model: rate,
 host-time profile (PSFMC_ENS_PROFILE), float64 repeats and graph replays per iteration.
-    python tools/time_sampler_loop.py [walkers] [iterations] [start: prior|ball]"""
+    python tools/time_sampler_loop.py [walkers] [iterations] [start: prior|ball] [n_devices]"""
 import os
 import sys
 import time
@@ -21,7 +21,9 @@ def main():
     walkers = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 50
     how = sys.argv[3] if len(sys.argv) > 3 else 'prior'
-    model = MultiComponentModel(os.path.join(ROOT, 'examples', 'model_J0005-0006.py'))
+    ndev = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    model = MultiComponentModel(os.path.join(ROOT, 'examples', 'model_J0005-0006.py'),
+                                devices=list(range(ndev)))
     ndim = model.num_params
     if how == 'prior':
         start = draw_walkers_fast(model, walkers, seed=1)
@@ -40,6 +42,7 @@ def main():
     pos, lnp, _ = smp.run_mcmc(pos, iters, lnprob0=lnp)
     dt = time.perf_counter() - t0
     info1 = model.engine.info()
+    print('{} device(s), '.format(ndev), end='')
     print('{} walkers, {} start: {:.3f} M evals/s, {:.1f} us per half-ensemble; per iteration: '
           '{:.2f} float64 repeats, {:.2f} graph replays, {:.1f} kernel launches; acceptance {:.3f}'
           .format(walkers, how, walkers * iters / dt / 1e6, 1e6 * dt / iters / 2,
