@@ -203,6 +203,13 @@ class HostPool {
   }
   HostPool() {
     unsigned hw = std::thread::hardware_concurrency();
+    // (one process per GPU: the ranks of a node share its cores -- torchrun's
+    // LOCAL_WORLD_SIZE; eight spinning pools of eight threads on 32 cores ran the sharded
+    // loop at a seventh of the speed of four)
+    if (const char *lws = getenv("LOCAL_WORLD_SIZE")) {
+      const int ranks = atoi(lws);
+      if (ranks > 1) hw = hw / (unsigned)ranks;
+    }
     max_threads_ = hw >= 16 ? 8 : (hw >= 8 ? 4 : (hw >= 4 ? 2 : 1));
     if (const char *env = getenv("PSFMC_HOST_THREADS")) {
       const int v = atoi(env);
@@ -221,7 +228,7 @@ class HostPool {
     unsigned long long seen = 0;
     for (;;) {
       bool changed = false;
-      for (int spins = 0; spins < 20000; ++spins) {
+      for (int spins = 0; spins < 4000; ++spins) {
         if (stop_.load(std::memory_order_relaxed) ||
             epoch_.load(std::memory_order_acquire) != seen) {
           changed = true;
