@@ -329,6 +329,13 @@ typedef struct psfmc_ensemble {
  * cover n_walkers / 2). Non-finite float32 results are -inf here (no float64 repeat, as
  * for every device-pointer call). */
 #define PSFMC_ENS_SHARDED 1
+/* Proposals, log-priors and acceptance on the device, around the lnL kernels on one stream;
+ * the host only draws the random numbers (and the logarithms of the acceptance test) ahead
+ * and enqueues -- no host round trip per half-ensemble. Needs a single-device engine and a
+ * prior plan without PSFMC_PRIOR_OTHER columns (else PSFMC_ERR_UNSUPPORTED: the caller
+ * falls back to the host loop). Same chain as the host loop up to the last bits of the
+ * Weibull columns' log / pow (the device's) and the missing float64 repeat. */
+#define PSFMC_ENS_DEVICE 2
 /* Advances the ensemble by n_iterations stretch-move iterations. Errors: a proposal with
  * an infinite / NaN coordinate (emcee raises ValueError), a failing callback. */
 int psfmc_ensemble_run(psfmc_engine *engine, const psfmc_prior_plan *priors,

@@ -127,7 +127,7 @@ class Ensemble(ctypes.Structure):
                 ('flags', ctypes.c_int64)]
 
 
-ENS_SHARDED = 1
+ENS_SHARDED, ENS_DEVICE = 1, 2
 
 
 # every symbol include/psfmc_b200.h declares

@@ -27,6 +27,7 @@
 #include "kernels_fused.cuh"
 #include "kernels_cluster.cuh"
 #include "kernels_tiled.cuh"
+#include "sampler_device.cuh"
 #endif
 
 using namespace psfmc;
@@ -180,6 +181,7 @@ struct EngineBase {
   // stream, which is returned)
   virtual int shard_upload(const double *theta_host, long long B, long long ld,
                            const double **theta_dev, void **stream) = 0;
+  virtual void *device0_stream() = 0;
   bool profiling = false;
   // float64 rescue on the device (float32 engines, see lnlike_host_graph): the owner
   // sets scan_wanted and, once it exists, the float64 engine; every host call reports
@@ -530,6 +532,8 @@ struct Engine : EngineBase {
   int reserve(long long B) override {
     DeviceState<T> &d = devs[0];
     CUDA_TRY(cudaSetDevice(d.ordinal));
+    if (d.lnl.ensure((size_t)(B > 0 ? B : 1)))
+      return fail(PSFMC_ERR_CUDA, "device allocation failed (lnl)");
     return ensure_batch(d, B);
   }
 
@@ -543,6 +547,8 @@ struct Engine : EngineBase {
     if (B <= 0) return 0;
     return enqueue(d, theta, B, ld, d.lnl.ptr, (cudaStream_t)stream);
   }
+
+  void *device0_stream() override { return (void *)devs[0].stream; }
 
   int shard_upload(const double *theta_host, long long B, long long ld,
                    const double **theta_dev, void **stream) override {
@@ -1883,6 +1889,41 @@ struct psfmc_engine {
   void *ens_stream = nullptr;
   double *ens_gathered = nullptr;
   long long ens_total = 0;
+  // device loop (PSFMC_ENS_DEVICE, sampler_device.cuh)
+  DevBuf<double> dl_pos, dl_lnprob, dl_nacc, dl_q, dl_qgpu, dl_lnprior, dl_rng, dl_chain, dl_lnpc;
+  DevBuf<int> dl_partner;
+  DevBuf<unsigned char> dl_plan;
+  PinBuf<double> hl_rng, hl_stage, hl_state;
+  PinBuf<int> hl_partner;
+  cudaStream_t dl_copy_stream = nullptr;
+#ifndef PSFMC_EMU
+  // one captured half-step per ring slot (copy of the slot, propose, prepare + lnL, accept)
+  struct LoopGraphs {
+    cudaGraphExec_t exec[8] = {};
+    long long k = 0, D = 0, epoch = -1, launches = 0;
+    int n_columns = -1, n_terms = -1, n_rules = -1, n_components = -1;
+    bool ok = false;
+    void drop() {
+      for (auto &x : exec)
+        if (x) {
+          cudaGraphExecDestroy(x);
+          x = nullptr;
+        }
+      ok = false;
+    }
+  } dl_graphs;
+#endif
+  void release_device_loop() {
+#ifndef PSFMC_EMU
+    dl_graphs.drop();
+#endif
+    dl_pos.release(); dl_lnprob.release(); dl_nacc.release(); dl_q.release();
+    dl_qgpu.release(); dl_lnprior.release(); dl_rng.release(); dl_chain.release();
+    dl_lnpc.release(); dl_partner.release(); dl_plan.release();
+    hl_rng.release(); hl_stage.release(); hl_state.release(); hl_partner.release();
+    if (dl_copy_stream) cudaStreamDestroy(dl_copy_stream);
+    dl_copy_stream = nullptr;
+  }
 };
 
 // A float32 evaluation that came back non-finite is repeated in float64 on the GPU:
@@ -1969,6 +2010,7 @@ void psfmc_engine_destroy(psfmc_engine *engine) {
   engine->ens_q.release();
   engine->ens_lnl.release();
   engine->ens_scratch.release();
+  engine->release_device_loop();
   delete engine->impl;
   delete engine->rescue;
   delete engine->saved;
@@ -2368,6 +2410,344 @@ static int ens_shard_end(void *self) {
 #endif
 }
 
+// psfmc_ensemble_run with PSFMC_ENS_DEVICE (sampler_device.cuh): the ensemble lives on
+// the engine's first device for the whole call; per half-step the host draws numpy's
+// random numbers (and takes the logarithms of the acceptance test) into one of RING
+// page-locked slots, copies the slot to the device and enqueues propose -> prepare + lnL ->
+// accept (-> store) on the engine's stream. It waits only when it is RING half-steps ahead,
+// and at the end of a block of stored iterations.
+static int run_ensemble_device(psfmc_engine *engine, const psfmc_prior_plan *pl,
+                               psfmc_ensemble *e, long long n_iter) {
+  const long long k = e->n_walkers, D = e->n_dim, half = k / 2;
+  const int RING = 8;
+  EngineBase *impl = engine->impl;
+  // PSFMC_ENS_PROFILE=1: host seconds in set-up, random draws, enqueueing, waiting for a
+  // ring slot, chain blocks, the final state
+  EnsProfile prof;
+  double tm = prof.on ? EnsProfile::now() : 0.0;
+  auto lap = [&](int slot) {
+    if (!prof.on) return;
+    const double t = EnsProfile::now();
+    prof.t[slot] += t - tm;
+    tm = t;
+  };
+  cudaStream_t stream = (cudaStream_t)impl->device0_stream();
+  // the prior plan as one device blob: columns | terms | rules
+  const size_t cb = (size_t)pl->n_columns * sizeof(psfmc_prior_column);
+  const size_t tb = (size_t)pl->n_terms * sizeof(psfmc_prior_term);
+  const size_t rb = (size_t)pl->n_rules * sizeof(psfmc_prior_rule);
+  const size_t t_off = (cb + 15) & ~(size_t)15, r_off = (t_off + tb + 15) & ~(size_t)15;
+  const long long thin = e->thin > 0 ? e->thin : 1;
+  const bool storing = e->chain || e->lnprob_chain;
+  long long block_cap = 0;            // slots per device block
+  // stored iterations per block: at most 8 MB of chain. Two blocks: while one fills, the
+  // other travels to the host on a second stream and is sorted into the caller's arrays.
+  long long block_bytes = 8ll << 20;
+  if (const char *env = getenv("PSFMC_CHAIN_BLOCK_BYTES")) {   // tests: many small blocks
+    const long long v = atoll(env);
+    if (v > 0) block_bytes = v;
+  }
+  long long block_store = block_bytes / (k * D * (long long)sizeof(double));
+  if (block_store < 1) block_store = 1;
+  if (engine->dl_plan.ensure(r_off + rb + 16) || engine->dl_pos.ensure((size_t)(k * D)) ||
+      engine->dl_lnprob.ensure((size_t)k) || engine->dl_nacc.ensure((size_t)k) ||
+      engine->dl_q.ensure((size_t)(half * D)) || engine->dl_qgpu.ensure((size_t)(half * D)) ||
+      engine->dl_lnprior.ensure((size_t)half) ||
+      engine->dl_rng.ensure((size_t)(RING * 4 * half)) ||
+      engine->hl_rng.ensure((size_t)(RING * 4 * half)) ||
+      engine->hl_state.ensure((size_t)(k * D + 2 * k)))
+    return fail(PSFMC_ERR_CUDA, "allocation failed (device loop)");
+  if (storing) {
+    long long want = (n_iter + thin - 1) / thin;
+    if (want > block_store) want = block_store;
+    if (engine->dl_chain.ensure((size_t)(2 * k * want * D)) ||
+        engine->dl_lnpc.ensure((size_t)(2 * k * want)) ||
+        engine->hl_stage.ensure((size_t)(2 * k * want * (D + 1))))
+      return fail(PSFMC_ERR_CUDA, "allocation failed (device loop, chain block)");
+    block_cap = want;
+    if (!engine->dl_copy_stream &&
+        cudaStreamCreateWithFlags(&engine->dl_copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+      return fail(PSFMC_ERR_CUDA, "stream creation failed (device loop)");
+  }
+  std::vector<unsigned char> blob(r_off + rb + 16, 0);
+  memcpy(blob.data(), pl->columns, cb);
+  memcpy(blob.data() + t_off, pl->terms, tb);
+  memcpy(blob.data() + r_off, pl->rules, rb);
+  CUDA_TRY(cudaMemcpyAsync(engine->dl_plan.ptr, blob.data(), blob.size(), cudaMemcpyHostToDevice,
+                           stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));   // (blob is pageable and about to go away)
+  DevPriorPlan dp;
+  dp.columns = reinterpret_cast<const psfmc_prior_column *>(engine->dl_plan.ptr);
+  dp.terms = reinterpret_cast<const psfmc_prior_term *>(engine->dl_plan.ptr + t_off);
+  dp.rules = reinterpret_cast<const psfmc_prior_rule *>(engine->dl_plan.ptr + r_off);
+  dp.n_columns = pl->n_columns;
+  dp.n_terms = pl->n_terms;
+  dp.n_rules = pl->n_rules;
+  dp.n_components = pl->n_components;
+  // state in: positions, lnprob, acceptance counts
+  double *hs = engine->hl_state.ptr;
+  memcpy(hs, e->pos, (size_t)(k * D) * sizeof(double));
+  memcpy(hs + k * D, e->lnprob, (size_t)k * sizeof(double));
+  if (e->n_accepted)
+    memcpy(hs + k * D + k, e->n_accepted, (size_t)k * sizeof(double));
+  else
+    memset(hs + k * D + k, 0, (size_t)k * sizeof(double));
+  CUDA_TRY(cudaMemcpyAsync(engine->dl_pos.ptr, hs, (size_t)(k * D) * sizeof(double),
+                           cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(engine->dl_lnprob.ptr, hs + k * D, (size_t)k * sizeof(double),
+                           cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(engine->dl_nacc.ptr, hs + k * D + k, (size_t)k * sizeof(double),
+                           cudaMemcpyHostToDevice, stream));
+  cudaEvent_t used[12] = {};          // ring slots, then filled[2], copied[2]
+  for (int r = 0; r < RING + 4; ++r)
+    if (cudaEventCreate(&used[r]) != cudaSuccess)
+      return fail(PSFMC_ERR_CUDA, "event creation failed (device loop)");
+  struct EventGuard {
+    cudaEvent_t *ev;
+    int n;
+    ~EventGuard() {
+      for (int r = 0; r < n; ++r)
+        if (ev[r]) cudaEventDestroy(ev[r]);
+    }
+  } guard{used, RING + 4};
+  cudaEvent_t *filled = used + RING, *copied = used + RING + 2;
+  NumpyMT19937 mt{e->mt_key, e->mt_pos};
+  const double a = e->a, dm1 = (double)D - 1.0;
+  HostPool &pool = HostPool::instance();
+  // one half-step on the stream: the ring slot to the device, propose, prepare + lnL,
+  // accept (ring slots alternate between the two halves: RING is even)
+  auto enqueue_half = [&](int slot) -> int {
+    const int h = slot & 1;
+    const long long s0 = h == 0 ? 0 : half, c0 = h == 0 ? half : 0, ns = half;
+    double *hz = engine->hl_rng.ptr + (size_t)slot * 4 * half;
+    double *dz = engine->dl_rng.ptr + (size_t)slot * 4 * half, *dlzz = dz + half, *dlu = dlzz + half;
+    int *dpart = reinterpret_cast<int *>(dlu + half);
+    CUDA_TRY(cudaMemcpyAsync(dz, hz, (size_t)(3 * half) * sizeof(double) + (size_t)half * sizeof(int),
+                             cudaMemcpyHostToDevice, stream));
+    const int block = 128;
+    const unsigned grid = (unsigned)((ns + block - 1) / block);
+    launch_kernel(propose_kernel, dim3((unsigned)((ns + 3) / 4)), dim3(128), 0, stream, dp,
+                  (const double *)engine->dl_pos.ptr, s0, c0, ns, (int)D, (const double *)dz,
+                  (const int *)dpart, engine->dl_q.ptr, engine->dl_qgpu.ptr,
+                  engine->dl_lnprior.ptr);
+    double *lnl_dev = nullptr;
+    int rc_l = impl->lnlike_local(engine->dl_qgpu.ptr, ns, D, (void *)stream, &lnl_dev);
+    if (rc_l) return rc_l;
+    launch_kernel(accept_kernel, dim3(grid), dim3(block), 0, stream, engine->dl_pos.ptr,
+                  engine->dl_lnprob.ptr, engine->dl_nacc.ptr, s0, ns, (int)D,
+                  (const double *)engine->dl_q.ptr, (const double *)lnl_dev,
+                  (const double *)engine->dl_lnprior.ptr, (const double *)dlzz,
+                  (const double *)dlu);
+    impl->launches += 2;
+    return 0;
+  };
+  bool use_graphs = false;
+  long long launches_per_half = 0;
+#ifndef PSFMC_EMU
+  {
+    // Replayed half-steps: eight graphs (one per ring slot), captured once per ensemble
+    // shape / prior plan / buffer generation. A half-step is five dependent operations of
+    // a few microseconds each at the reference example's 125 rows: launched one by one
+    // they cost 20 us of host time and ~4 us of gap each on the device.
+    const char *env = getenv("PSFMC_NO_GRAPH");
+    auto &G = engine->dl_graphs;
+    const bool want = !(env && env[0] == '1') && !impl->profiling && n_iter * 2 >= 2 * RING;
+    if (want) {
+      // size every buffer the lnL launch needs BEFORE anything is captured
+      const int rc_r = impl->reserve(half);
+      if (rc_r) return rc_r;
+      const long long now = g_alloc_epoch.load();
+      if (G.ok && (G.k != k || G.D != D || G.epoch != now || G.n_columns != pl->n_columns ||
+                   G.n_terms != pl->n_terms || G.n_rules != pl->n_rules ||
+                   G.n_components != pl->n_components))
+        G.drop();
+      if (!G.ok) {
+        bool good = true;
+        const long long before = impl->launches;
+        for (int slot = 0; slot < RING && good; ++slot) {
+          good = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+          if (!good) break;
+          const long long l0 = impl->launches;
+          const int rc_c = enqueue_half(slot);
+          launches_per_half = impl->launches - l0;
+          cudaGraph_t graph = nullptr;
+          const bool ended = cudaStreamEndCapture(stream, &graph) == cudaSuccess;
+          good = rc_c == 0 && ended && graph &&
+                 cudaGraphInstantiate(&G.exec[slot], graph, 0) == cudaSuccess;
+          if (graph) cudaGraphDestroy(graph);
+        }
+        impl->launches = before;            // (captured, not run)
+        if (good && g_alloc_epoch.load() == now) {
+          G.ok = true;
+          G.k = k;
+          G.D = D;
+          G.epoch = now;
+          G.n_columns = pl->n_columns;
+          G.n_terms = pl->n_terms;
+          G.n_rules = pl->n_rules;
+          G.n_components = pl->n_components;
+          G.launches = launches_per_half;
+        } else {
+          cudaGetLastError();
+          G.drop();
+        }
+      }
+      use_graphs = G.ok;
+      launches_per_half = G.launches;
+    }
+  }
+#endif
+  lap(0);
+  long long step = 0;                 // half-steps enqueued
+  long long block_first = -1, block_count = 0;   // stored iterations of the current block
+  int rc = 0;
+  // Chain blocks. The current block (buffer `bi` of two on the device) has rows of
+  // block_len slots, block_count of them filled. A full block is copied to its page-locked
+  // staging area on the copy stream while the other buffer fills, and sorted into the
+  // caller's (walker, iteration, D) arrays when that buffer is needed again, or at the end.
+  long long block_len = 0;
+  int bi = 0;
+  struct Pending {
+    bool active = false;
+    long long first = 0, count = 0, pitch = 0;
+  } pending[2];
+  auto dev_chain = [&](int b) { return engine->dl_chain.ptr + (size_t)b * k * block_cap * D; };
+  auto dev_lnpc = [&](int b) { return engine->dl_lnpc.ptr + (size_t)b * k * block_cap; };
+  auto stage_of = [&](int b) { return engine->hl_stage.ptr + (size_t)b * k * block_cap * (D + 1); };
+  auto sort_block = [&](int b) -> int {      // staging area b -> the caller's arrays
+    if (!pending[b].active) return 0;
+    CUDA_TRY(cudaEventSynchronize(copied[b]));
+    const long long first = pending[b].first, count = pending[b].count, pitch = pending[b].pitch;
+    const double *stage = stage_of(b), *stage_lnp = stage + k * pitch * D;
+    pool.parallel_rows(k, 256, [&](long long lo, long long hi) {
+      for (long long w = lo; w < hi; ++w) {
+        if (e->chain)
+          memcpy(e->chain + ((size_t)w * e->chain_len + first) * D, stage + (size_t)w * pitch * D,
+                 (size_t)(count * D) * sizeof(double));
+        if (e->lnprob_chain)
+          memcpy(e->lnprob_chain + (size_t)w * e->chain_len + first, stage_lnp + (size_t)w * pitch,
+                 (size_t)count * sizeof(double));
+      }
+    });
+    pending[b].active = false;
+    return 0;
+  };
+  auto flush_block = [&]() -> int {          // the current block leaves for the host
+    if (!block_count) return 0;
+    cudaStream_t cs = engine->dl_copy_stream;
+    double *stage = stage_of(bi), *stage_lnp = stage + k * block_len * D;
+    CUDA_TRY(cudaEventRecord(filled[bi], stream));
+    CUDA_TRY(cudaStreamWaitEvent(cs, filled[bi], 0));
+    if (e->chain)
+      CUDA_TRY(cudaMemcpyAsync(stage, dev_chain(bi), (size_t)(k * block_len * D) * sizeof(double),
+                               cudaMemcpyDeviceToHost, cs));
+    if (e->lnprob_chain)
+      CUDA_TRY(cudaMemcpyAsync(stage_lnp, dev_lnpc(bi), (size_t)(k * block_len) * sizeof(double),
+                               cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaEventRecord(copied[bi], cs));
+    pending[bi].active = true;
+    pending[bi].first = block_first;
+    pending[bi].count = block_count;
+    pending[bi].pitch = block_len;
+    block_count = 0;
+    block_first = -1;
+    bi ^= 1;
+    // the buffer that fills next must have reached the caller's arrays
+    return sort_block(bi);
+  };
+  for (long long it = 0; it < n_iter && !rc; ++it) {
+    for (int h = 0; h < 2 && !rc; ++h, ++step) {
+      const long long s0 = h == 0 ? 0 : half, c0 = h == 0 ? half : 0;
+      const long long ns = half, nc = k - half;
+      const int slot = (int)(step % RING);
+      lap(5);
+      if (step >= RING) CUDA_TRY(cudaEventSynchronize(used[slot]));
+      lap(1);
+      // a slot: zz | (D - 1) log zz | log u | partner (int32, in the fourth quarter)
+      double *hz = engine->hl_rng.ptr + (size_t)slot * 4 * half, *hlzz = hz + half, *hlu = hlzz + half;
+      int *hp = reinterpret_cast<int *>(hlu + half);
+      for (long long i = 0; i < ns; ++i) {
+        volatile double t = (a - 1.0) * mt.next_double();
+        const double t1 = t + 1.0;
+        volatile double sq = t1 * t1;
+        hz[i] = sq / a;
+      }
+      for (long long i = 0; i < ns; ++i) hp[i] = (int)mt.next_bounded((uint32_t)nc);
+      for (long long i = 0; i < ns; ++i) hlu[i] = mt.next_double();
+      pool.parallel_rows(ns, 512, [&](long long lo, long long hi) {
+        for (long long i = lo; i < hi; ++i) {
+          hlzz[i] = dm1 * log(hz[i]);
+          hlu[i] = log(hlu[i]);
+        }
+      });
+      lap(2);
+#ifndef PSFMC_EMU
+      if (use_graphs) {
+        CUDA_TRY(cudaGraphLaunch(engine->dl_graphs.exec[slot], stream));
+        impl->launches += launches_per_half;
+      } else
+#endif
+      {
+        rc = enqueue_half(slot);
+        if (rc) break;
+      }
+      CUDA_TRY(cudaEventRecord(used[slot], stream));
+      lap(3);
+    }
+    if (rc) break;
+    if (storing && it % thin == 0) {
+      const long long ind = e->chain_start + it / thin;
+      if (ind < e->chain_len) {
+        if (!block_count) {
+          block_first = ind;
+          // this block holds the stored iterations from here to the end of the call, at
+          // most block_store of them: its rows have that many slots
+          long long left = (n_iter - 1 - it) / thin + 1;
+          if (left > e->chain_len - ind) left = e->chain_len - ind;
+          block_len = left < block_store ? left : block_store;
+        }
+        const unsigned grid = (unsigned)((k * D + 255) / 256);
+        launch_kernel(store_kernel, dim3(grid), dim3(256), 0, stream,
+                      (const double *)engine->dl_pos.ptr, (const double *)engine->dl_lnprob.ptr, k,
+                      (int)D, block_len, block_count,
+                      e->chain ? dev_chain(bi) : (double *)nullptr,
+                      e->lnprob_chain ? dev_lnpc(bi) : (double *)nullptr);
+        ++impl->launches;
+        if (++block_count == block_len) rc = flush_block();
+      }
+    }
+  }
+  lap(5);
+  if (!rc) rc = flush_block();
+  if (!rc) rc = sort_block(0);
+  if (!rc) rc = sort_block(1);
+  lap(4);
+  // state out (also after a failure: whatever was completed)
+  cudaMemcpyAsync(hs, engine->dl_pos.ptr, (size_t)(k * D) * sizeof(double), cudaMemcpyDeviceToHost,
+                  stream);
+  cudaMemcpyAsync(hs + k * D, engine->dl_lnprob.ptr, (size_t)k * sizeof(double),
+                  cudaMemcpyDeviceToHost, stream);
+  cudaMemcpyAsync(hs + k * D + k, engine->dl_nacc.ptr, (size_t)k * sizeof(double),
+                  cudaMemcpyDeviceToHost, stream);
+  const cudaError_t err = cudaStreamSynchronize(stream);
+  if (err != cudaSuccess && !rc) rc = fail(PSFMC_ERR_CUDA, cudaGetErrorString(err));
+  if (err == cudaSuccess) {
+    memcpy(e->pos, hs, (size_t)(k * D) * sizeof(double));
+    memcpy(e->lnprob, hs + k * D, (size_t)k * sizeof(double));
+    if (e->n_accepted) memcpy(e->n_accepted, hs + k * D + k, (size_t)k * sizeof(double));
+  }
+  lap(6);
+  if (prof.on && step)
+    fprintf(stderr,
+            "[psfmc] ensemble_run (device loop): %lld half-steps; ms: set-up %.2f, waiting for a "
+            "ring slot %.2f, draws + logs %.2f, enqueue %.2f, chain blocks %.2f, other %.2f, "
+            "final state + drain %.2f; per half-step %.1f us\n",
+            step, 1e3 * prof.t[0], 1e3 * prof.t[1], 1e3 * prof.t[2], 1e3 * prof.t[3],
+            1e3 * prof.t[4], 1e3 * prof.t[5], 1e3 * prof.t[6],
+            1e6 * (EnsProfile::now() - prof.t_begin) / step);
+  return rc;
+}
+
 int psfmc_lnpost_batch(psfmc_engine *engine, const psfmc_prior_plan *priors,
                        const double *theta, int64_t n_batch, int64_t ld, double *lnpost_out) {
   if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
@@ -2420,6 +2800,32 @@ int psfmc_ensemble_run(psfmc_engine *engine, const psfmc_prior_plan *priors,
                   engine->ens_scratch.ensure(half * (size_t)ens->n_dim);
   cudaSetDevice(prev);
   if (bad) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
+  if (ens->flags & PSFMC_ENS_DEVICE) {
+    if (ens->flags & PSFMC_ENS_SHARDED)
+      return fail(PSFMC_ERR_UNSUPPORTED, "PSFMC_ENS_DEVICE with PSFMC_ENS_SHARDED");
+    if (engine->impl->n_devices != 1)
+      return fail(PSFMC_ERR_UNSUPPORTED, "PSFMC_ENS_DEVICE needs a single-device engine");
+    if (!priors) return fail(PSFMC_ERR_UNSUPPORTED, "PSFMC_ENS_DEVICE needs a prior plan");
+    for (int c = 0; c < priors->n_columns; ++c)
+      if (priors->columns[c].family == PSFMC_PRIOR_OTHER)
+        return fail(PSFMC_ERR_UNSUPPORTED,
+                    "PSFMC_ENS_DEVICE: a prior column is evaluated by the caller");
+    if (priors->n_columns > PSFMC_PROPOSE_MAXD)
+      return fail(PSFMC_ERR_UNSUPPORTED, "PSFMC_ENS_DEVICE: too many prior columns");
+    // a non-finite coordinate in the starting ensemble is the caller's error either way
+    for (int64_t i = 0; i < ens->n_walkers * ens->n_dim; ++i) {
+      if (std::isinf(ens->pos[i]))
+        return fail(PSFMC_ERR_INVALID_ARG, "At least one parameter value was infinite.");
+      if (ens->pos[i] != ens->pos[i])
+        return fail(PSFMC_ERR_INVALID_ARG, "At least one parameter value was NaN.");
+    }
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    cudaSetDevice(engine->impl->first_ordinal);
+    const int rc_dev = run_ensemble_device(engine, priors, ens, n_iterations);
+    cudaSetDevice(prev_dev);
+    return rc_dev;
+  }
   LnlikeCalls calls{engine, ens_begin, ens_end};
   if (ens->flags & PSFMC_ENS_SHARDED) {
     if (!engine->peer.world)

@@ -196,7 +196,7 @@ class LikelihoodEngine(object):
 
     def ensemble_run(self, plan, pos, lnprob, mt_key, mt_pos, n_iterations, a=2.0,
                      chain=None, lnprob_chain=None, chain_start=0, thin=1,
-                     n_accepted=None, sharded=False):
+                     n_accepted=None, sharded=False, device=False):
         """``n_iterations`` stretch-move iterations of the whole ensemble inside the
         library (emcee 2.x semantics, numpy RandomState stream; see the header).
         ``pos`` (k, D), ``lnprob`` (k,), ``mt_key`` (624,) uint32, ``n_accepted`` (k,)
@@ -204,7 +204,10 @@ class LikelihoodEngine(object):
         (k, L, D) / ``lnprob_chain`` (k, L) receive every ``thin``-th iteration from
         index ``chain_start`` on. ``sharded``: one process per GPU -- every rank makes
         the same call and evaluates its share of every half-ensemble, the lnL is gathered
-        over peer memory (:meth:`peer_create` / :meth:`peer_connect` first)."""
+        over peer memory (:meth:`peer_create` / :meth:`peer_connect` first). ``device``:
+        proposals, priors and acceptance on the device (``PSFMC_ENS_DEVICE``); falls back
+        to the host loop where the library cannot (several devices, a prior column that is
+        evaluated in Python)."""
         dbl_p = ctypes.POINTER(ctypes.c_double)
         for arr, dtype in ((pos, np.float64), (lnprob, np.float64), (mt_key, np.uint32),
                            (chain, np.float64), (lnprob_chain, np.float64),
@@ -235,7 +238,8 @@ class LikelihoodEngine(object):
             ens.lnprob_chain = lnprob_chain.ctypes.data_as(dbl_p)
             ens.chain_len = lnprob_chain.shape[1]
         ens.chain_start, ens.thin = int(chain_start), int(thin)
-        ens.flags = _lib.ENS_SHARDED if sharded else 0
+        ens.flags = (_lib.ENS_SHARDED if sharded else 0) | \
+            (_lib.ENS_DEVICE if device and not sharded else 0)
         if n_accepted is not None:
             if n_accepted.shape != (pos.shape[0],):
                 raise ValueError('n_accepted must be (k,)')
@@ -243,6 +247,11 @@ class LikelihoodEngine(object):
         code = self._lib.psfmc_ensemble_run(
             self._handle, ctypes.byref(plan) if plan is not None else None,
             ctypes.byref(ens), int(n_iterations))
+        if code == 2 and (ens.flags & _lib.ENS_DEVICE):     # PSFMC_ERR_UNSUPPORTED
+            ens.flags &= ~_lib.ENS_DEVICE
+            code = self._lib.psfmc_ensemble_run(
+                self._handle, ctypes.byref(plan) if plan is not None else None,
+                ctypes.byref(ens), int(n_iterations))
         if code != 0:
             message = self._lib.psfmc_last_error().decode('utf-8', 'replace')
             if 'parameter value was' in message or 'lnprob returned NaN' in message:

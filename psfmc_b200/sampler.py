@@ -223,6 +223,7 @@ class EnsembleSampler(object):
         state is taken from and returned to ``self._random``."""
         engine, holder = native
         sharded = bool(holder.get('sharded', False))
+        device = bool(holder.get('device_loop', False)) and not sharded
         state = self._random.get_state()
         key = np.array(state[1], dtype=np.uint32)
         mt_pos = ctypes.c_int32(int(state[2]))
@@ -233,16 +234,16 @@ class EnsembleSampler(object):
             if skip:
                 done = min(skip, count)
                 engine.ensemble_run(holder['plan'], p, lnprob, key, mt_pos, done, a=self.a,
-                                    n_accepted=self.naccepted, sharded=sharded)
+                                    n_accepted=self.naccepted, sharded=sharded, device=device)
                 first, count = first + done, count - done
             if count > 0:
                 engine.ensemble_run(holder['plan'], p, lnprob, key, mt_pos, count, a=self.a,
                                     chain=self._chain_buf, lnprob_chain=self._lnprob_buf,
                                     chain_start=start + first // thin, thin=thin,
-                                    n_accepted=self.naccepted, sharded=sharded)
+                                    n_accepted=self.naccepted, sharded=sharded, device=device)
         elif count > 0:
             engine.ensemble_run(holder['plan'], p, lnprob, key, mt_pos, count, a=self.a,
-                                n_accepted=self.naccepted, sharded=sharded)
+                                n_accepted=self.naccepted, sharded=sharded, device=device)
         self._random.set_state((state[0], key, int(mt_pos.value), state[3], state[4]))
 
     def _propose_stretch(self, active, complement, lnprob_active):

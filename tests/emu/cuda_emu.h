@@ -455,6 +455,7 @@ inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = n
 inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDevice(int *d) { *d = 0; return 0; }

@@ -519,16 +519,19 @@ def test_seeded_run_on_the_j0005_model(cuda_library, c1_golden):
     _seeded_runs_agree(model, start, nburn=40, nkeep=80)
 
 
-@pytest.mark.parametrize('strict', ['1', '0'])
+@pytest.mark.parametrize('strict,device', [('1', '0'), ('0', '0'), ('0', '1')])
 def test_library_sampler_loop_reproduces_the_numpy_loop(cuda_library, c1_golden, monkeypatch,
-                                                        strict):
+                                                        strict, device):
     """psfmc_ensemble_run (the sampler's iterations inside the library) on the J0005-0006
     model, float32 engine: same seed, same start -> the chain of the numpy loop
     (sampler.py), bit for bit with the Weibull priors through the callback (strict), with
     identical positions when they are evaluated in the library with the C library's pow."""
     from psfmc_b200 import BatchPool
     from psfmc_b200.sampler import EnsembleSampler
+    # device = '1': proposals, priors and acceptance in kernels around the lnL kernels
+    # (PSFMC_ENS_DEVICE): no host round trip per half-ensemble
     monkeypatch.setenv('PSFMC_PRIORS_STRICT', strict)
+    monkeypatch.setenv('PSFMC_DEVICE_LOOP', device)
     model = model_from_file('j0005/model_c1.py', 'fp32')
     centre = np.array(c1_golden['theta'][0])
     nwalk = 250

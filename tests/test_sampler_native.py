@@ -60,10 +60,12 @@ def _small_model(library, weibull):
     return MultiComponentModel(comps, precision='fp64', library=library)
 
 
-def _run(model, start, native, monkeypatch, iterations=5, thin=1, stepwise=False):
+def _run(model, start, native, monkeypatch, iterations=5, thin=1, stepwise=False,
+         device=False):
     from psfmc_b200 import BatchPool
     from psfmc_b200.sampler import EnsembleSampler
     monkeypatch.setenv('PSFMC_NATIVE_SAMPLER', '1' if native else '0')
+    monkeypatch.setenv('PSFMC_DEVICE_LOOP', '1' if device else '0')
     nwalk, ndim = start.shape
     sampler = EnsembleSampler(nwalk, ndim, model.log_posterior, kwargs={'model': model},
                               pool=BatchPool(model))
@@ -82,8 +84,9 @@ def _run(model, start, native, monkeypatch, iterations=5, thin=1, stepwise=False
             'next': sampler._random.rand(4), 'yielded': yielded}
 
 
+@pytest.mark.parametrize('device', [False, True])
 @pytest.mark.parametrize('case', ['uniform', 'weibull_strict', 'weibull_native'])
-def test_library_loop_reproduces_the_numpy_loop(emu_library, monkeypatch, case):
+def test_library_loop_reproduces_the_numpy_loop(emu_library, monkeypatch, case, device):
     """Same seed, same start: chain, lnprobability, acceptance counts and the random
     stream after the run are those of the numpy loop. 'uniform': every prior evaluated in
     the library; 'weibull_strict': the Weibull column through the callback (bit for bit);
@@ -98,9 +101,18 @@ def test_library_loop_reproduces_the_numpy_loop(emu_library, monkeypatch, case):
     # tighten the ensemble so that a good share of the proposals is accepted
     start = start[0] + 0.02 * (start - start[0])
     assert np.all(np.isfinite(model.log_posterior_batch(start)))
+    # device: proposals, priors and acceptance in kernels around the lnL kernels
+    # (PSFMC_ENS_DEVICE; with the Weibull column in Python the library falls back to its
+    # host loop)
     ref = _run(model, start, False, monkeypatch)
-    got = _run(model, start, True, monkeypatch)
+    launches = model.engine.info()['launches_total']
+    got = _run(model, start, True, monkeypatch, device=device)
+    per_half = (model.engine.info()['launches_total'] - launches) / 10.0
     holder = model._sampler_plan
+    if device and case != 'weibull_strict':
+        assert per_half > 6.9, per_half       # propose + prepare + 3 staged + finalize + accept
+    else:
+        assert per_half < 6.9, per_half
     assert holder, 'the library loop was not used'
     assert holder['weibull_native'] == (case != 'weibull_strict')
     assert holder['python_columns'] == (case == 'weibull_strict')
@@ -127,6 +139,17 @@ def test_library_loop_stepwise_and_thinned(emu_library, monkeypatch):
     start = draw_walkers_fast(model, nwalk, seed=4)
     start = start[0] + 0.02 * (start - start[0])
     ref = _run(model, start, False, monkeypatch, iterations=6, thin=2, stepwise=True)
+    for device in (True, False):
+        got = _run(model, start, True, monkeypatch, iterations=6, thin=3, device=device)
+        want = _run(model, start, False, monkeypatch, iterations=6, thin=3)
+        assert got['chain'].shape == (nwalk, 2, model.num_params)
+        assert np.array_equal(got['chain'], want['chain'])
+        assert np.array_equal(got['lnprobability'], want['lnprobability'])
+        assert np.array_equal(got['pos'], want['pos'])
+        assert np.array_equal(got['next'], want['next'])
+    got = _run(model, start, True, monkeypatch, iterations=6, thin=2, stepwise=True,
+               device=True)
+    assert np.array_equal(got['chain'], ref['chain'])
     got = _run(model, start, True, monkeypatch, iterations=6, thin=2, stepwise=True)
     assert got['chain'].shape == (nwalk, 3, model.num_params)
     assert np.array_equal(got['chain'], ref['chain'])
@@ -137,6 +160,25 @@ def test_library_loop_stepwise_and_thinned(emu_library, monkeypatch):
     one = _run(model, start, True, monkeypatch, iterations=6, thin=2)
     assert np.array_equal(one['chain'], ref['chain'])
     assert np.array_equal(one['next'], ref['next'])
+
+
+def test_device_loop_chain_blocks(emu_library, monkeypatch):
+    """The device loop hands its chain over in blocks (two buffers: one fills while the
+    other travels): blocks of 3 iterations, 11 iterations, thin 1 and 2."""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model = _small_model(emu_library, False)
+    nwalk = 2 * model.num_params + 2
+    start = draw_walkers_fast(model, nwalk, seed=6)
+    start = start[0] + 0.02 * (start - start[0])
+    monkeypatch.setenv('PSFMC_CHAIN_BLOCK_BYTES', str(3 * nwalk * model.num_params * 8))
+    for thin, iters in ((1, 11), (2, 10)):
+        want = _run(model, start, False, monkeypatch, iterations=iters, thin=thin)
+        got = _run(model, start, True, monkeypatch, iterations=iters, thin=thin, device=True)
+        assert got['chain'].shape[1] == iters // thin
+        assert np.array_equal(got['chain'], want['chain'])
+        assert np.array_equal(got['lnprobability'], want['lnprobability'])
+        assert np.array_equal(got['naccepted'], want['naccepted'])
+        assert np.array_equal(got['next'], want['next'])
 
 
 def test_lnpost_batch_matches_log_posterior_batch(emu_library):

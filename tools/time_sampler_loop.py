@@ -35,7 +35,7 @@ def main():
     smp = EnsembleSampler(walkers, ndim, model.log_posterior, kwargs={'model': model},
                           pool=BatchPool(model), live_dangerously=True)
     smp._random.seed(7)
-    pos, lnp, _ = smp.run_mcmc(start, 3)
+    pos, lnp, _ = smp.run_mcmc(start, iters)      # (buffers sized, graphs captured)
     smp.reset()
     info0 = model.engine.info()
     t0 = time.perf_counter()
