@@ -646,7 +646,7 @@ def run_ours(args):
                                   pool=(ShardedPool(model) if world > 1 else BatchPool(model)),
                                   live_dangerously=True)
             smp._random.seed(7)
-            pos, lnp, _ = smp.run_mcmc(start, 3)
+            pos, lnp, _ = smp.run_mcmc(start, 16)   # (buffers sized, half-step graphs captured)
             smp.reset()
             barrier()
             t0 = time.perf_counter()

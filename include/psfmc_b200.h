@@ -333,7 +333,9 @@ typedef struct psfmc_ensemble {
  * the host only draws the random numbers (and the logarithms of the acceptance test) ahead
  * and enqueues -- no host round trip per half-ensemble. Needs a single-device engine and a
  * prior plan without PSFMC_PRIOR_OTHER columns (else PSFMC_ERR_UNSUPPORTED: the caller
- * falls back to the host loop). Same chain as the host loop up to the last bits of the
+ * falls back to the host loop). Together with PSFMC_ENS_SHARDED every rank runs this loop
+ * on its own device -- the proposals are identical on all ranks -- and the lnL kernels
+ * store their results into every rank's mailbox themselves. Same chain as the host loop up to the last bits of the
  * Weibull columns' log / pow (the device's) and the missing float64 repeat. */
 #define PSFMC_ENS_DEVICE 2
 /* Advances the ensemble by n_iterations stretch-move iterations. Errors: a proposal with

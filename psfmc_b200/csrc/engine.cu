@@ -2421,6 +2421,7 @@ static int run_ensemble_device(psfmc_engine *engine, const psfmc_prior_plan *pl,
   const long long k = e->n_walkers, D = e->n_dim, half = k / 2;
   const int RING = 8;
   EngineBase *impl = engine->impl;
+  const bool sharded = (e->flags & PSFMC_ENS_SHARDED) != 0;
   // PSFMC_ENS_PROFILE=1: host seconds in set-up, random draws, enqueueing, waiting for a
   // ring slot, chain blocks, the final state
   EnsProfile prof;
@@ -2531,7 +2532,22 @@ static int run_ensemble_device(psfmc_engine *engine, const psfmc_prior_plan *pl,
                   (const int *)dpart, engine->dl_q.ptr, engine->dl_qgpu.ptr,
                   engine->dl_lnprior.ptr);
     double *lnl_dev = nullptr;
-    int rc_l = impl->lnlike_local(engine->dl_qgpu.ptr, ns, D, (void *)stream, &lnl_dev);
+    int rc_l = 0;
+    if (sharded) {
+      // one process per GPU: this rank's contiguous share of the rows (every rank runs this
+      // same loop on the same random numbers: q is identical everywhere); the lnL of all
+      // rows arrives in this rank's mailbox (psfmc_lnlike_batch_exchange)
+      const PeerState &ps = engine->peer;
+      const long long base = ns / ps.world, extra = ns % ps.world;
+      const long long lo = ps.rank * base + (ps.rank < extra ? ps.rank : extra);
+      const long long count = base + (ps.rank < extra ? 1 : 0);
+      rc_l = psfmc_lnlike_batch_exchange(engine, engine->dl_qgpu.ptr + lo * D, count, D, lo, ns,
+                                         nullptr, (void *)stream);
+      if (!rc_l) rc_l = psfmc_peer_gathered(engine, &lnl_dev);
+      cudaSetDevice(impl->first_ordinal);
+    } else {
+      rc_l = impl->lnlike_local(engine->dl_qgpu.ptr, ns, D, (void *)stream, &lnl_dev);
+    }
     if (rc_l) return rc_l;
     launch_kernel(accept_kernel, dim3(grid), dim3(block), 0, stream, engine->dl_pos.ptr,
                   engine->dl_lnprob.ptr, engine->dl_nacc.ptr, s0, ns, (int)D,
@@ -2551,7 +2567,9 @@ static int run_ensemble_device(psfmc_engine *engine, const psfmc_prior_plan *pl,
     // they cost 20 us of host time and ~4 us of gap each on the device.
     const char *env = getenv("PSFMC_NO_GRAPH");
     auto &G = engine->dl_graphs;
-    const bool want = !(env && env[0] == '1') && !impl->profiling && n_iter * 2 >= 2 * RING;
+    // (not the sharded loop: the flag exchange carries a call counter)
+    const bool want = !(env && env[0] == '1') && !impl->profiling && n_iter * 2 >= 2 * RING &&
+                      !sharded;
     if (want) {
       // size every buffer the lnL launch needs BEFORE anything is captured
       const int rc_r = impl->reserve(half);
@@ -2801,8 +2819,17 @@ int psfmc_ensemble_run(psfmc_engine *engine, const psfmc_prior_plan *priors,
   cudaSetDevice(prev);
   if (bad) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
   if (ens->flags & PSFMC_ENS_DEVICE) {
-    if (ens->flags & PSFMC_ENS_SHARDED)
-      return fail(PSFMC_ERR_UNSUPPORTED, "PSFMC_ENS_DEVICE with PSFMC_ENS_SHARDED");
+    if (ens->flags & PSFMC_ENS_SHARDED) {
+#ifdef PSFMC_EMU
+      return fail(PSFMC_ERR_UNSUPPORTED, "the sharded loop needs real devices");
+#else
+      if (!engine->peer.world)
+        return fail(PSFMC_ERR_INVALID_ARG, "PSFMC_ENS_SHARDED: call psfmc_peer_connect first");
+      if ((long long)(ens->n_walkers / 2) > engine->peer.capacity)
+        return fail(PSFMC_ERR_INVALID_ARG,
+                    "PSFMC_ENS_SHARDED: the mailbox capacity is below n_walkers / 2");
+#endif
+    }
     if (engine->impl->n_devices != 1)
       return fail(PSFMC_ERR_UNSUPPORTED, "PSFMC_ENS_DEVICE needs a single-device engine");
     if (!priors) return fail(PSFMC_ERR_UNSUPPORTED, "PSFMC_ENS_DEVICE needs a prior plan");

@@ -219,6 +219,11 @@ class ShardedPool(object):
             return None
         sharded = dict(holder)
         sharded['sharded'] = True
+        # proposals, priors and acceptance on every rank's device (PSFMC_ENS_DEVICE): with the
+        # GPU share of a half-ensemble shrinking as 1 / ranks, the host part of the loop is
+        # what limits a sharded run otherwise. PSFMC_DEVICE_LOOP=0 keeps it on the host.
+        if os.environ.get('PSFMC_DEVICE_LOOP', 'auto') != '0' and not holder['python_columns']:
+            sharded['device_loop'] = True
         return engine, sharded
 
     def close(self):

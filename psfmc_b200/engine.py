@@ -238,8 +238,7 @@ class LikelihoodEngine(object):
             ens.lnprob_chain = lnprob_chain.ctypes.data_as(dbl_p)
             ens.chain_len = lnprob_chain.shape[1]
         ens.chain_start, ens.thin = int(chain_start), int(thin)
-        ens.flags = (_lib.ENS_SHARDED if sharded else 0) | \
-            (_lib.ENS_DEVICE if device and not sharded else 0)
+        ens.flags = (_lib.ENS_SHARDED if sharded else 0) | (_lib.ENS_DEVICE if device else 0)
         if n_accepted is not None:
             if n_accepted.shape != (pos.shape[0],):
                 raise ValueError('n_accepted must be (k,)')

@@ -223,7 +223,7 @@ class EnsembleSampler(object):
         state is taken from and returned to ``self._random``."""
         engine, holder = native
         sharded = bool(holder.get('sharded', False))
-        device = bool(holder.get('device_loop', False)) and not sharded
+        device = bool(holder.get('device_loop', False))
         state = self._random.get_state()
         key = np.array(state[1], dtype=np.uint32)
         mt_pos = ctypes.c_int32(int(state[2]))

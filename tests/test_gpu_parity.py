@@ -394,9 +394,16 @@ dist.destroy_process_group()
         assert np.array_equal(data['peer1'], data['alone'][:64])
         assert np.array_equal(data['peer2'], data['alone'][:999])
         for nwalk in (250, 1000):
-            for key in ('%d' % nwalk, 'lnp_%d' % nwalk):
-                assert np.array_equal(data['sharded_' + key], data['single_' + key]), key
-                assert np.array_equal(data['sharded_' + key], first['sharded_' + key]), key
+            # (positions bit for bit; lnprob to the last digits: the sharded loop runs on
+            # the devices, whose log / pow serve the Weibull priors, the single-engine loop
+            # of 250 walkers on the host)
+            key = '%d' % nwalk
+            assert np.array_equal(data['sharded_' + key], data['single_' + key]), key
+            assert np.array_equal(data['sharded_' + key], first['sharded_' + key]), key
+            key = 'lnp_%d' % nwalk
+            np.testing.assert_allclose(data['sharded_' + key], data['single_' + key],
+                                       rtol=1e-13)
+            assert np.array_equal(data['sharded_' + key], first['sharded_' + key]), key
 
 
 @pytest.mark.parametrize('table', ['1', '0'])
