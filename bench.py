@@ -27,7 +27,10 @@ lnL stay in HBM, CUDA events on the launching stream); `e2e` = the same metric
 through the C ABI with host buffers (pinned theta in, lnL out, copies inside the
 timed region); `e2e.pool_map` = through the emcee-facing list protocol
 (BatchPool.map / ShardedPool.map: row views in, (lnpost, blob) tuples out, priors
-included).
+included); `e2e.sampler_loop` = the WHOLE stretch-move iteration of this package's
+sampler (proposals, priors, lnL, acceptance, chain storage) -- `library`: the loop
+inside the library (psfmc_ensemble_run; N > 1: sharded over the ranks), `numpy_loop`:
+the same sampler with its Python loop, both also at the reference example's 250 walkers.
 
 `--impl reference` and the `cpu_baseline` leg run the UNMODIFIED reference
 (oracle/_ref/psfMC, placed there verbatim by oracle/make_ref.py; imported through
