@@ -467,14 +467,40 @@ from psfmc_b200.bridge import pool_for_reference_model
 pool = pool_for_reference_model(model, precision='fp64', library=emu_lib)
 rows = [0, 1, 2, 3, 4, 8, 9, 10]
 thetas = [np.array(golden['theta'][r]) for r in rows]
+bad = np.array(golden['theta'][0]); bad[7], bad[8] = 3.0, 5.0      # reff_b > reff
+out = np.array(golden['theta'][1]); out[-1] = 400.0                 # angle outside its prior
+thetas += [bad, out]
 batched = pool.map(None, thetas)
-for r, theta, (lnpost, blob) in zip(rows, thetas, batched):
+# the priors went through the library's plan, validated against the reference's own code
+assert pool.priors and (pool.priors.weibull_native or pool.priors.other)
+for r, theta, (lnpost, blob) in zip(rows + [-1, -2], thetas, batched):
     want, _ = type(model).log_posterior(theta, model=model)     # the reference itself
     assert blob == {}
     if np.isfinite(want):
         assert abs(lnpost - want) <= 1e-10 * abs(want), (r, lnpost, want)
     else:
         assert lnpost == -np.inf, (r, lnpost, want)
+assert batched[-1][0] == -np.inf and batched[-2][0] == -np.inf
+# the plan's priors against the reference's scalar code, row by row, and the per-walker
+# path (PSFMC_BRIDGE_PRIORS=reference) against the batched one
+for theta, got in zip(thetas, pool.priors.lnprior(np.stack(thetas))):
+    model.param_values = theta
+    want = model.log_priors()
+    assert got == want or (np.isfinite(want) and abs(got - want) <= 4 * np.spacing(abs(want))) \
+        or (np.isnan(got) and np.isnan(want)), (got, want)
+os.environ['PSFMC_PRIORS_STRICT'] = '1'
+strict = pool_for_reference_model(model, precision='fp64', library=emu_lib)
+again = strict.map(None, thetas)
+assert strict.priors and not strict.priors.weibull_native and strict.priors.other
+for theta, got in zip(thetas, strict.priors.lnprior(np.stack(thetas))):
+    model.param_values = theta
+    want = model.log_priors()
+    assert got == want or (np.isnan(got) and np.isnan(want)), (got, want)
+os.environ['PSFMC_BRIDGE_PRIORS'] = 'reference'
+slow = pool_for_reference_model(model, precision='fp64', library=emu_lib)
+per_walker = slow.map(None, thetas)
+assert slow.priors is False
+assert [a for a, _ in per_walker] == [a for a, _ in again]
 print('BRIDGE-OK')
 """
 
