@@ -467,8 +467,19 @@ def run_ours(args):
             rows = th[h * half:(h + 1) * half]
             if world == 1:
                 engine.lnlike(rows, out=out[h * half:(h + 1) * half])
+            elif exchange is not None:
+                # one library call per rank: its share of the rows up, lnL of all rows
+                # gathered over peer memory, down to the host (psfmc_lnpost_batch_sharded)
+                engine.lnpost_sharded(None, rows, out=out[h * half:(h + 1) * half])
             else:
                 out[h * half:(h + 1) * half] = lnlike_pool(rows)
+
+    def step_host_nccl(s):
+        """N > 1, the torch.distributed form: ShardedEvaluator (NCCL all_gather)."""
+        th = th_pin[s % nsets].numpy()
+        out = lnl_pin.numpy()
+        for h in range(2):
+            out[h * half:(h + 1) * half] = lnlike_pool(th[h * half:(h + 1) * half])
 
     def step_posterior(s):
         th = thetas[s % nsets]
@@ -605,6 +616,11 @@ def run_ours(args):
     rescued0 = engine.info()['rescued_total']
     e2e_s = host_timed(step_host, args.steps)
     e2e_value = walkers * args.steps / e2e_s
+    e2e_nccl = None
+    if world > 1 and exchange is not None:
+        for s in range(3):
+            step_host_nccl(s)
+        e2e_nccl = walkers * args.steps / host_timed(step_host_nccl, args.steps)
     rescued_per_step = (engine.info()['rescued_total'] - rescued0) / float(args.steps)
     # the same loop with the float64 rescue of non-finite float32 results switched
     # off (for information: prior-drawn ensembles contain a few such walkers, the
@@ -778,7 +794,10 @@ def run_ours(args):
                     'h2d_bytes_per_step': (hi - lo) * 2 * ndim * 8,
                     'd2h_bytes_per_step': walkers * 8,
                     'timer': 'host perf_counter around blocking calls (psfmc_lnlike_batch; '
-                             'N > 1: + the gather to every rank\'s host), max over ranks',
+                             'N > 1: psfmc_lnpost_batch_sharded -- this rank\'s share up, lnL '
+                             'of all rows gathered over peer memory, down to every rank\'s '
+                             'host), max over ranks',
+                    'with_nccl_gather': None if e2e_nccl is None else round(e2e_nccl, 1),
                     'with_python_priors': round(walkers * args.steps / post_s, 1),
                     'pool_map': round(walkers * map_steps / map_s, 1),
                     'pool_map_inside': round(walkers * map_steps / map_inside_s, 1),

@@ -306,6 +306,15 @@ typedef struct psfmc_prior_plan {
 int psfmc_lnpost_batch(psfmc_engine *engine, const psfmc_prior_plan *priors,
                        const double *theta, int64_t n_batch, int64_t ld, double *lnpost_out);
 
+/* The same for a job with one process per GPU (psfmc_peer_create / _connect first): every
+ * rank passes the SAME n_batch rows, evaluates its contiguous share of them and receives the
+ * values of all rows -- lnL gathered over peer memory, host buffers in and out. priors may
+ * be null: lnpost_out is then the lnL itself. Non-finite float32 results are -inf (no
+ * float64 repeat). Every rank must make the same sequence of calls. */
+int psfmc_lnpost_batch_sharded(psfmc_engine *engine, const psfmc_prior_plan *priors,
+                               const double *theta, int64_t n_batch, int64_t ld,
+                               double *lnpost_out);
+
 typedef struct psfmc_ensemble {
   int64_t n_walkers;     /* k, even                                                    */
   int64_t n_dim;         /* D = row length of pos                                      */

@@ -139,7 +139,8 @@ EXPORTED_SYMBOLS = (
     'psfmc_engine_profile', 'psfmc_engine_profile_read',
     'psfmc_fp32_peak_probe', 'psfmc_last_error', 'psfmc_abi_version',
     'psfmc_peer_create', 'psfmc_peer_connect', 'psfmc_lnlike_batch_exchange',
-    'psfmc_peer_gathered', 'psfmc_lnpost_batch', 'psfmc_ensemble_run', 'psfmc_rng_fill',
+    'psfmc_peer_gathered', 'psfmc_lnpost_batch', 'psfmc_lnpost_batch_sharded',
+    'psfmc_ensemble_run', 'psfmc_rng_fill',
 )
 
 _DEFAULT_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)),
@@ -227,6 +228,9 @@ def load(path=None):
     lib.psfmc_lnpost_batch.restype = ctypes.c_int
     lib.psfmc_lnpost_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(PriorPlan), dbl_p,
                                        ctypes.c_int64, ctypes.c_int64, dbl_p]
+    lib.psfmc_lnpost_batch_sharded.restype = ctypes.c_int
+    lib.psfmc_lnpost_batch_sharded.argtypes = [ctypes.c_void_p, ctypes.POINTER(PriorPlan),
+                                               dbl_p, ctypes.c_int64, ctypes.c_int64, dbl_p]
     lib.psfmc_ensemble_run.restype = ctypes.c_int
     lib.psfmc_ensemble_run.argtypes = [ctypes.c_void_p, ctypes.POINTER(PriorPlan),
                                        ctypes.POINTER(Ensemble), ctypes.c_int64]

@@ -2788,6 +2788,41 @@ int psfmc_lnpost_batch(psfmc_engine *engine, const psfmc_prior_plan *priors,
   return rc;
 }
 
+int psfmc_lnpost_batch_sharded(psfmc_engine *engine, const psfmc_prior_plan *priors,
+                               const double *theta, int64_t n_batch, int64_t ld,
+                               double *lnpost_out) {
+  if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");
+  if (n_batch < 0 || ld < 0) return fail(PSFMC_ERR_INVALID_ARG, "negative batch or ld");
+  if (!engine->peer.world)
+    return fail(PSFMC_ERR_INVALID_ARG, "call psfmc_peer_connect first");
+  if (n_batch > engine->peer.capacity)
+    return fail(PSFMC_ERR_INVALID_ARG, "the batch exceeds the mailbox capacity");
+  if (n_batch == 0) return 0;
+  if (!theta || !lnpost_out) return fail(PSFMC_ERR_INVALID_ARG, "null theta / lnpost_out");
+  if (ld < engine->impl->n_theta)
+    return fail(PSFMC_ERR_INVALID_ARG,
+                "ld is smaller than the number of theta columns the component program reads");
+  const char *why = nullptr;
+  if (check_prior_plan(priors, ld, &why)) return fail(PSFMC_ERR_INVALID_ARG, why);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(engine->impl->first_ordinal);
+  const int bad = engine->ens_lnl.ensure((size_t)n_batch);
+  cudaSetDevice(prev);
+  if (bad) return fail(PSFMC_ERR_CUDA, "pinned host allocation failed");
+  // (no row is left out here: every rank must make the same exchange, and the split of
+  // the rows must not depend on which of them are dead -- scratch = null)
+  LnlikeCalls calls{engine, ens_shard_begin, ens_shard_end};
+  LnpostWork &wk = engine->ens_work;
+  const double keep = wk.last_dead_frac;
+  wk.last_dead_frac = 0.0;            // screen behind the GPU, all rows evaluated
+  int rc = lnpost_rows(calls, priors, theta, n_batch, ld, engine->ens_lnl.ptr, lnpost_out, wk,
+                       nullptr);
+  wk.last_dead_frac = keep;
+  if (rc == -1) return fail(PSFMC_ERR_INVALID_ARG, "the other_columns callback failed");
+  return rc;
+}
+
 int psfmc_ensemble_run(psfmc_engine *engine, const psfmc_prior_plan *priors,
                        psfmc_ensemble *ens, int64_t n_iterations) {
   if (!engine || !engine->impl) return fail(PSFMC_ERR_INVALID_ARG, "engine is null");

@@ -176,13 +176,48 @@ class ShardedPool(object):
             return []
         from itertools import repeat
         from .pool import rows_as_block
-        lnpost = self._evaluator(rows_as_block(thetas))
+        block = rows_as_block(thetas)
+        lnpost = self._library_lnpost(block)
+        if lnpost is None:
+            lnpost = self._evaluator(block)
         return list(zip(lnpost.tolist(), repeat({})))
+
+    def _library_lnpost(self, block):
+        """The whole sharded evaluation in one library call per rank
+        (``psfmc_lnpost_batch_sharded``: priors on every rank, this rank's share of the
+        lnL, gathered over peer memory) once a prior plan has been validated and the ranks'
+        mailboxes are connected; None: the torch.distributed path."""
+        import os
+        import torch.distributed as dist
+        if os.environ.get('PSFMC_NATIVE_SAMPLER', '1') == '0' or len(block) < 2:
+            return None
+        if not (dist.is_available() and dist.is_initialized()) or \
+                dist.get_backend(self.group) != 'nccl':
+            return None
+        engine = getattr(self.model, 'engine', None)
+        if engine is None or not hasattr(engine, 'lnpost_sharded') or \
+                not hasattr(self.model, 'native_sampler_plan'):
+            return None
+        holder = self.model.native_sampler_plan(block)
+        if holder is None:
+            return None
+        peer = getattr(engine, '_peer_exchange', None)
+        if peer is None:
+            try:
+                peer = PeerExchange(engine, max(len(block), 65536), self.group)
+            except Exception:
+                return None
+        if len(block) > peer.capacity:
+            return None
+        return engine.lnpost_sharded(holder['plan'], block)
 
     def map_batch(self, func, block):
         """Array protocol of this package's sampler (cf. BatchPool.map_batch):
         (B, D) -> ((B,) lnpost, None)."""
         block = np.ascontiguousarray(block, dtype=np.float64)
+        lnpost = self._library_lnpost(block)
+        if lnpost is not None:
+            return lnpost, None
         return self._evaluator(block), None
 
     def native_sampler(self, start_positions):

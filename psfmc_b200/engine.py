@@ -194,6 +194,20 @@ class LikelihoodEngine(object):
             out.ctypes.data_as(dbl_p)))
         return out
 
+    def lnpost_sharded(self, plan, thetas, out=None):
+        """One process per GPU (:meth:`peer_create` / :meth:`peer_connect` first): every
+        rank passes the same rows, evaluates its share and gets the values of all rows
+        (lnL gathered over peer memory; host buffers). ``plan`` None: the lnL itself."""
+        thetas = np.ascontiguousarray(np.atleast_2d(thetas), dtype=np.float64)
+        n_batch, ld = thetas.shape
+        if out is None:
+            out = np.empty(n_batch, dtype=np.float64)
+        dbl_p = ctypes.POINTER(ctypes.c_double)
+        _lib.check(self._lib, self._lib.psfmc_lnpost_batch_sharded(
+            self._handle, ctypes.byref(plan) if plan is not None else None,
+            thetas.ctypes.data_as(dbl_p), n_batch, ld, out.ctypes.data_as(dbl_p)))
+        return out
+
     def ensemble_run(self, plan, pos, lnprob, mt_key, mt_pos, n_iterations, a=2.0,
                      chain=None, lnprob_chain=None, chain_start=0, thin=1,
                      n_accepted=None, sharded=False, device=False):

@@ -351,6 +351,9 @@ for count in (1001, 64, 999):
     stream.synchronize()
     peer.append(gathered.cpu().numpy()[:count])
 alone = raw.log_likelihood_batch(thetas)
+# the same gather with host buffers in one library call (psfmc_lnpost_batch_sharded)
+host_sharded = raw.engine.lnpost_sharded(None, thetas)
+host_sharded_37 = raw.engine.lnpost_sharded(None, thetas[:37])
 # the sampler's loop inside the library, sharded (psfmc_ensemble_run + PSFMC_ENS_SHARDED:
 # every rank the same seeded loop, its share of every half-ensemble, lnL over peer
 # memory) against the same loop on this rank's engine alone; 250 walkers (ragged shards
@@ -375,7 +378,8 @@ for nwalk in (250, 1000):
         chains['%s_lnp_%d' % (name, nwalk)] = smp.lnprobability.copy()
 np.savez(os.path.join({out!r}, 'rank%d.npz' % dist.get_rank()), got=got, listed=listed,
          want=model.log_posterior_batch(thetas), alone=alone, peer0=peer[0],
-         peer1=peer[1], peer2=peer[2], **chains)
+         peer1=peer[1], peer2=peer[2], host_sharded=host_sharded,
+         host_sharded_37=host_sharded_37, **chains)
 dist.barrier()
 dist.destroy_process_group()
 """.format(root=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
@@ -393,6 +397,8 @@ dist.destroy_process_group()
         assert np.array_equal(data['peer0'], data['alone'])
         assert np.array_equal(data['peer1'], data['alone'][:64])
         assert np.array_equal(data['peer2'], data['alone'][:999])
+        assert np.array_equal(data['host_sharded'], data['alone'])
+        assert np.array_equal(data['host_sharded_37'], data['alone'][:37])
         for nwalk in (250, 1000):
             # (positions bit for bit; lnprob to the last digits: the sharded loop runs on
             # the devices, whose log / pow serve the Weibull priors, the single-engine loop
