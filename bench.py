@@ -14,12 +14,15 @@ its target on.
 
 Multi-GPU (torchrun, one rank per GPU): STRONG scaling. The one ensemble is sharded
 over the N ranks: every rank evaluates its contiguous rows of each half-ensemble
-on its own engine and the per-walker lnL is all-gathered (NCCL, B doubles) INSIDE
-the timed region, because the next half-ensemble's proposals depend on it. This
-is the pool.map of /root/reference/psfMC/fitting.py:55-58, timed as
-psfmc_b200.distributed.sharded_lnlike_device (device buffers, `value`) and
-ShardedPool.map_batch / .map (host buffers, `e2e`). The replica throughput (every
-rank its own ensemble, no gather; weak scaling) is reported beside it as
+on its own engine and the per-walker lnL of ALL rows reaches every rank INSIDE the
+timed region, because the next half-ensemble's proposals depend on it. This is the
+pool.map of /root/reference/psfMC/fitting.py:55-58. The gather is the lnL kernel's
+own: it stores each result into every rank's mailbox over CUDA-IPC peer memory
+(psfmc_b200.distributed.PeerExchange / psfmc_lnlike_batch_exchange, device buffers:
+`value`; psfmc_lnpost_batch_sharded, host buffers: `e2e`). The same step with an NCCL
+all_gather_into_tensor of B doubles is timed beside it (`with_nccl_gather`,
+`e2e.with_nccl_gather`; PSFMC_BENCH_GATHER=nccl makes it the headline), and so is the
+replica throughput (every rank its own ensemble, no gather; weak scaling) as
 `replicas_weak`.
 
 Prints ONE JSON line (rank 0). `value` = device-resident throughput (theta and
