@@ -129,6 +129,31 @@ def test_invalid_arguments_are_reported_not_thrown(cuda_library):
     lib.psfmc_engine_destroy(None)              # no-op, must not crash
 
 
+def test_every_engine_entry_point_rejects_a_null_engine(cuda_library):
+    """No entry point dereferences a null handle: each one that takes an engine reports
+    PSFMC_ERR_INVALID_ARG (1) with a message -- without a GPU, before any CUDA call."""
+    from psfmc_b200 import _lib
+    lib = _lib.load(cuda_library)
+    checked = []
+    for name in _lib.EXPORTED_SYMBOLS:
+        func = getattr(lib, name)
+        argtypes = func.argtypes
+        if not argtypes or argtypes[0] is not ctypes.c_void_p or \
+                name == 'psfmc_engine_destroy':
+            continue
+        args = [None]
+        for kind in argtypes[1:]:
+            args.append(0 if kind in (ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32)
+                        else None)
+        assert func(*args) == 1, name
+        assert lib.psfmc_last_error(), name
+        checked.append(name)
+    assert len(checked) >= 15, checked
+    for must in ('psfmc_lnpost_batch_sharded', 'psfmc_ensemble_run',
+                 'psfmc_lnlike_batch_exchange', 'psfmc_peer_connect'):
+        assert must in checked
+
+
 def test_product_fails_loudly_without_the_library(tmp_path, monkeypatch):
     from psfmc_b200 import _lib
     monkeypatch.setenv('PSFMC_B200_LIB', str(tmp_path / 'nope.so'))
