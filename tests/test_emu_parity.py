@@ -308,3 +308,44 @@ def test_emu_nan_parameters_give_minus_inf(emu_library, monkeypatch):
 @pytest.mark.parametrize('tag', ['crop100', 'crop75x100'])
 def test_emu_cropped_frames_match_the_reference(emu_library, tag):
     check_cropped_golden(emu_library, tag)
+
+
+def test_emu_wide_box_fuzz(emu_library):
+    """Parameter vectors from boxes far wider than the example's priors (tools/emu_fuzz.py,
+    profiles/r2e_emu_fuzz.txt): what the stated tolerances do NOT promise, pinned as what
+    they do. 'typical' (reff >= 0.5 px, index >= 0.3, components up to 1500 ADU on 0.007 ADU
+    of noise): float64 within FP64_RTOL, float32 within the bound extended by the
+    variance-channel term and nearly always within the plain one. 'wide' (centres outside
+    the frame, reff down to 0.05 px, index down to 0.05, single pixels of 10^7 ADU): the
+    same walkers are finite in the engine and in the reference, float64 agrees to the
+    rounding of ITS transform at that dynamic range, float32 to 5e-4 of |lnL|."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), 'tools'))
+    from emu_fuzz import draw, extended_bounds
+    from conftest import FP64_RTOL
+    models = {prec: model_from_file('j0005/model_c1.py', prec, library=emu_library,
+                                    obs_dtype=np.float64) for prec in ('fp64', 'fp32')}
+    oracle = oracle_from_model(models['fp64'])
+    for box, count in (('typical', 40), ('wide', 40)):
+        thetas = draw(np.random.RandomState(17), count, box)
+        with np.errstate(all='ignore'):
+            expect = oracle.lnlike_batch(thetas)
+        finite = np.isfinite(expect)
+        assert finite.sum() >= count - 4
+        got = {prec: models[prec].log_likelihood_batch(thetas) for prec in models}
+        for prec in got:
+            assert np.array_equal(np.isfinite(got[prec]), finite), (box, prec)
+            assert np.all(got[prec][~finite] == -np.inf)
+        rel = {prec: np.abs(got[prec][finite] - expect[finite]) / np.abs(expect[finite])
+               for prec in got}
+        if box == 'typical':
+            assert rel['fp64'].max() <= FP64_RTOL
+            err = np.abs(got['fp32'] - expect)[finite]
+            assert np.all(err <= extended_bounds(models['fp32'], thetas, oracle)[finite])
+            plain = fp32_bounds(models['fp32'], thetas, oracle)[finite]
+            assert np.mean(err <= plain) >= 0.9
+        else:
+            assert rel['fp64'].max() <= 1e-7
+            assert rel['fp32'].max() <= 5e-4
