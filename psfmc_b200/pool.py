@@ -66,6 +66,7 @@ class BatchPool(object):
         self.with_blobs = with_blobs
         self.calls = 0
         self.evaluations = 0
+        self._fp32_enough = None        # see _float32_is_enough
 
     def map(self, func, iterable):
         """Order-preserving, synchronous. ``func`` is emcee's wrapper around
@@ -142,9 +143,35 @@ class BatchPool(object):
         choice = os.environ.get('PSFMC_DEVICE_LOOP', 'auto')
         if not holder['python_columns'] and (
                 choice == '1' or (choice != '0' and len(start_positions) > 512)):
-            holder = dict(holder)
-            holder['device_loop'] = True
+            if choice == '1' or self._float32_is_enough(start_positions):
+                holder = dict(holder)
+                holder['device_loop'] = True
         return engine, holder
+
+    def _float32_is_enough(self, start_positions):
+        """The device loop has no float64 repeat: a walker whose float32 transform comes
+        out non-finite counts as -inf there, where the reference -- and the host loop, which
+        repeats it in float64 -- has a finite posterior. That is nothing for the odd
+        prior-drawn walker and a stuck chain for a model whose dynamic range float32 cannot
+        hold (a component 10^5 times brighter than the pixel noise: DESIGN.md 4.5, 'outside
+        the priors'). Probe once per pool: the starting ensemble through the host call,
+        which repeats and counts; more than 1 % repeated keeps the loop on the host."""
+        if self._fp32_enough is None:
+            engine = self.model.engine
+            before = engine.info()['rescued_total']
+            self.model.log_posterior_batch(
+                np.ascontiguousarray(start_positions, dtype=np.float64))
+            repeated = engine.info()['rescued_total'] - before
+            self._fp32_enough = repeated <= 0.01 * len(start_positions)
+            if not self._fp32_enough:
+                import warnings
+                warnings.warn(
+                    'psfmc_b200: {} of the {} starting walkers needed the float64 repeat of '
+                    'the float32 likelihood; the sampler loop stays on the host (which '
+                    'repeats them) instead of the device loop (which would count them as '
+                    '-inf). precision=\'fp64\' suits this model better.'.format(
+                        repeated, len(start_positions)))
+        return self._fp32_enough
 
     # multiprocessing.Pool look-alikes some callers use
     def close(self):

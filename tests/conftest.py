@@ -598,7 +598,8 @@ ARBITRARY_FRAMES = ((100, 100, 64, 64), (75, 100, 31, 17), (50, 36, 21, 36),
                     (65, 64, 64, 64))
 
 
-def arbitrary_frame_model(height, width, psf_h, psf_w, precision, library=None):
+def arbitrary_frame_model(height, width, psf_h, psf_w, precision, library=None,
+                          fp64_rescue=False):
     """A frame that is not a power of two (odd heights, odd PSF stamps, a PSF as wide as
     the frame): asymmetric PSF (pins the kernel origin), a point source in the frame
     corner whose PSF wings wrap around (the reference's convolution is circular at the
@@ -628,7 +629,7 @@ def arbitrary_frame_model(height, width, psf_h, psf_w, precision, library=None):
                     reff_b=Uniform(loc=2, scale=2), index=Uniform(loc=0.5, scale=4),
                     angle=Uniform(loc=0, scale=180), angle_degrees=True)]
     return MultiComponentModel(comps, precision=precision, library=library,
-                               fp64_rescue=False)
+                               fp64_rescue=fp64_rescue)
 
 
 def check_arbitrary_frame(library, dims, n_walkers=3):

@@ -297,3 +297,57 @@ def test_ensemble_run_rejects_bad_input(emu_library):
     p[3, 0] = -1e308
     with pytest.raises(ValueError, match='infinite'):
         engine.ensemble_run(None, p, lnp, key, pos, 3)
+
+
+def test_device_loop_is_not_chosen_for_a_model_float32_cannot_hold(emu_library, monkeypatch):
+    """The device loop has no float64 repeat. BatchPool probes the starting ensemble once:
+    a model whose walkers need the repeat (a point source 10^7 times brighter than the
+    pixel noise) keeps its loop on the host, with a warning; an ordinary model gets the
+    device loop. PSFMC_DEVICE_LOOP=1 forces it either way."""
+    import warnings
+
+    from psfmc_b200 import BatchPool, MultiComponentModel
+    from psfmc_b200.components import PointSource
+    from psfmc_b200.distributions import Uniform
+    from psfmc_b200.synthetic import synthetic_components
+    monkeypatch.setenv('PSFMC_NATIVE_SAMPLER', '1')
+    monkeypatch.delenv('PSFMC_DEVICE_LOOP', raising=False)
+    size = 32
+    centre, box = np.array((size / 2.0, size / 2.0)), np.array((3.0, 3.0))
+
+    def model_with(point_mag):
+        comps = synthetic_components(size, 1, dtype=np.float64, psf_size=16)
+        comps = [c for c in comps if not isinstance(c, PointSource)]
+        comps.append(PointSource(xy=Uniform(loc=centre - box, scale=2 * box),
+                                 mag=Uniform(loc=point_mag, scale=0.5)))
+        return MultiComponentModel(comps, precision='fp32', library=emu_library)
+
+    ordinary = model_with(21.0)
+    start = ordinary.init_params_from_priors(520)
+    with warnings.catch_warnings():
+        warnings.simplefilter('error')
+        pool = BatchPool(ordinary)
+        engine, holder = pool.native_sampler(start)
+        assert holder.get('device_loop') is True
+        assert pool.native_sampler(start)[1].get('device_loop') is True     # cached
+    assert ordinary.engine.info()['rescued_total'] == 0
+
+    bright = model_with(8.0)            # 10^(0.4 * 17.9) = 1.4e7 ADU on 0.02 ADU of noise
+    start = bright.init_params_from_priors(520)
+    oracle = oracle_from_model(bright)
+    assert np.all(np.isfinite(oracle.lnlike_batch(start[:8])))
+    pool = BatchPool(bright)
+    with pytest.warns(UserWarning, match='float64 repeat'):
+        engine, holder = pool.native_sampler(start)
+    assert not holder.get('device_loop')
+    assert bright.engine.info()['rescued_total'] > 5
+    with warnings.catch_warnings():
+        warnings.simplefilter('error')                                       # warned once
+        assert not pool.native_sampler(start)[1].get('device_loop')
+    monkeypatch.setenv('PSFMC_DEVICE_LOOP', '1')
+    assert BatchPool(bright).native_sampler(start)[1].get('device_loop') is True
+    # small ensembles never ask
+    monkeypatch.delenv('PSFMC_DEVICE_LOOP')
+    fresh = BatchPool(bright)
+    assert not fresh.native_sampler(start[:100])[1].get('device_loop')
+    assert fresh._fp32_enough is None

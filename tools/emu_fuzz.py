@@ -5,7 +5,8 @@ frames with parameter vectors drawn from a box far WIDER than the model's priors
 outside the frame, reff 0.05 ... 300 px, axis ratios down to 0.005, indices 0.05 ... 12,
 magnitudes 14 ... 32): what a user's model with other priors could hand the engine.
 
-    python tools/emu_fuzz.py [n_walkers] [seed] [wide|typical] [brightest_mag]
+    python tools/emu_fuzz.py [n_walkers] [seed] [wide|typical] [c1|mixed128|mixed256|frame75x100]
+                              [brightest_mag]
 
 Prints, per precision mode, the rows whose result disagrees with the oracle: finiteness,
 fp64 beyond FP64_RTOL, fp32 beyond the stated bound of tests/conftest.py (fp32_bounds).
@@ -31,24 +32,81 @@ BOXES = {
 }
 
 
-def draw(rng, count, box='wide', bright=None):
+def draw(rng, count, box='wide', bright=None, names=None, lens=None, shape=(128, 128),
+         n_psf=1):
+    """(count, D) parameter vectors for a model whose parameters are ``names`` / ``lens``
+    (MultiComponentModel.param_names / param_lens; default: the C1 layout)."""
     mag0, margin, (r_lo, r_hi), q_lo, (n_lo, n_hi) = BOXES[box]
     if bright is not None:
         mag0 = bright
+    if names is None:
+        names = ['0_Sky_adu', '1_PointSource_mag', '1_PointSource_xy']
+        lens = [1, 1, 2]
+        for comp in (2, 3):
+            names += ['%d_Sersic_%s' % (comp, attr) for attr in
+                      ('angle', 'index', 'mag', 'reff', 'reff_b', 'xy')]
+            lens += [1, 1, 1, 1, 1, 2]
+    height, width = shape
+    scale = max(height, width) / 128.0
 
-    def logu(lo, hi, size):
-        return np.exp(rng.uniform(np.log(lo), np.log(hi), size))
-    cols = [rng.uniform(-0.05, 0.05, count), rng.uniform(mag0 + 1.0, 30.0, count),
-            rng.uniform(-0.5 * margin, 128.0 + 0.5 * margin, count),
-            rng.uniform(-0.5 * margin, 128.0 + 0.5 * margin, count)]
-    for _ in range(2):
-        reff = logu(r_lo, r_hi, count)
-        cols += [rng.uniform(-360.0, 720.0, count), logu(n_lo, n_hi, count),
-                 rng.uniform(mag0, 32.0, count), reff,
-                 reff * rng.uniform(q_lo, 1.0, count),
-                 rng.uniform(-margin, 128.0 + margin, count),
-                 rng.uniform(-margin, 128.0 + margin, count)]
+    def logu(lo, hi):
+        return np.exp(rng.uniform(np.log(lo), np.log(hi), count))
+    cols, reff_of = [], {}
+    for name, length in zip(names, lens):
+        comp, attr = name.split('_', 1)[0], name.split('_', 2)[-1]
+        point = 'PointSource' in name
+        if attr == 'adu':
+            cols.append(rng.uniform(-0.05, 0.05, count))
+        elif attr == 'mag':
+            cols.append(rng.uniform(mag0 + (1.0 if point else 0.0),
+                                    30.0 if point else 32.0, count))
+        elif attr == 'xy':
+            edge = 0.5 * margin if point else margin
+            cols.append(rng.uniform(-edge, width + edge, count))
+            cols.append(rng.uniform(-edge, height + edge, count))
+        elif attr == 'angle':
+            cols.append(rng.uniform(-360.0, 720.0, count))
+        elif attr == 'index':
+            cols.append(logu(n_lo, n_hi))
+        elif attr == 'reff':
+            reff_of[comp] = logu(r_lo, r_hi * scale)
+            cols.append(reff_of[comp])
+        elif attr == 'reff_b':
+            major = reff_of.get(comp)
+            if major is None:                 # reff fixed in the model: a range of its own
+                major = logu(r_lo, r_hi * scale)
+            cols.append(major * rng.uniform(q_lo, 1.0, count))
+        elif 'psf' in name.lower():
+            # in range, half-integers (rint is half-to-even) and a little beyond both ends
+            cols.append(rng.uniform(-0.75, n_psf - 0.25, count))
+        else:
+            raise ValueError('emu_fuzz: no rule for parameter ' + name)
+        assert length == (2 if attr == 'xy' else 1), name
     return np.ascontiguousarray(np.stack(cols, axis=1))
+
+
+def build_model(which, precision, env=()):
+    """The fuzzed models: c1 (fused 128^2 / staged), mixed128 (bilinear and clipped point
+    sources, fixed parameters, radians), mixed256 (two PSFs, the four-CTA cluster kernel),
+    frame75x100 (75 x 100 frame, 31 x 17 PSF: zero-padded transform frame + fold)."""
+    import conftest
+    for key, val in env:
+        os.environ[key] = val
+    try:
+        if which == 'c1':
+            return conftest.model_from_file('j0005/model_c1.py', precision,
+                                            library=conftest.EMU_LIB, obs_dtype=np.float64)
+        if which == 'mixed128':
+            return conftest.mixed_model_128(precision, library=conftest.EMU_LIB)
+        if which == 'mixed256':
+            return conftest.mixed_model_256(precision, library=conftest.EMU_LIB)
+        if which == 'frame75x100':
+            return conftest.arbitrary_frame_model(75, 100, 31, 17, precision=precision,
+                                                  library=conftest.EMU_LIB, fp64_rescue=True)
+        raise SystemExit('emu_fuzz: unknown model ' + which)
+    finally:
+        for key, _ in env:
+            os.environ.pop(key, None)
 
 
 def extended_bounds(model, thetas, oracle):
@@ -77,57 +135,62 @@ def extended_bounds(model, thetas, oracle):
 
 
 def main():
-    from conftest import (EMU_LIB, FP64_RTOL, fp32_bounds, model_from_file,
-                          oracle_from_model)
+    from conftest import FP64_RTOL, fp32_bounds, oracle_from_model
     count = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     box = sys.argv[3] if len(sys.argv) > 3 else 'wide'
-    bright = float(sys.argv[4]) if len(sys.argv) > 4 else None
-    thetas = draw(np.random.RandomState(seed), count, box, bright)
-    names = None
+    which = sys.argv[4] if len(sys.argv) > 4 else 'c1'
+    bright = float(sys.argv[5]) if len(sys.argv) > 5 else None
+    thetas = None
     worst = {}
-    for precision, env in (('fp64', {}), ('fp32', {}), ('fp32', {'PSFMC_FORCE_STAGED': '1'})):
-        for key, val in env.items():
-            os.environ[key] = val
-        model = model_from_file('j0005/model_c1.py', precision, library=EMU_LIB,
-                                obs_dtype=np.float64)
-        for key in env:
-            os.environ.pop(key)
-        if names is None:
-            names = model.param_names
+    modes = [('fp64', ()), ('fp32', ()), ('fp32', (('PSFMC_FORCE_STAGED', '1'),))]
+    for precision, env in modes:
+        model = build_model(which, precision, env)
+        if thetas is None:
+            n_psf = len(model.config.psf_selector.psf_images)
+            thetas = draw(np.random.RandomState(seed), count, box, bright,
+                          model.param_names, model.param_lens, tuple(model.engine.shape),
+                          n_psf)
             oracle = oracle_from_model(model)
             with np.errstate(all='ignore'):
                 expect = oracle.lnlike_batch(thetas)
+            # a PSF index that rounds outside the list: the prior is -inf there, the reference
+            # never reaches the likelihood (psfMC/models.py:209-211); the engine answers -inf
+            if model.psf_index_slot[0] == 'theta':
+                sel = np.rint(thetas[:, model.psf_index_slot[1]])
+                expect[(sel < 0) | (sel >= n_psf)] = -np.inf
             bounds = fp32_bounds(model, thetas, oracle)
             extended = extended_bounds(model, thetas, oracle)
         rescued0 = model.engine.info()['rescued_total']
         got = model.log_likelihood_batch(thetas)
         rescued = model.engine.info()['rescued_total'] - rescued0
-        tag = precision + ('/staged' if env else '') + ' path {}'.format(
-            model.engine.info()['path'])
+        tag = '{} {}{} path {}'.format(which, precision, '/staged' if env else '',
+                                       model.engine.info()['path'])
         fin_e, fin_g = np.isfinite(expect), np.isfinite(got)
         bad_fin = np.flatnonzero(fin_e != fin_g)
         both = fin_e & fin_g
-        err = np.abs(got - expect)
-        limit = bounds if precision == 'fp32' else FP64_RTOL * np.abs(expect)
         with np.errstate(all='ignore'):
+            err = np.where(both, np.abs(got - expect), 0.0)
+            limit = bounds if precision == 'fp32' else FP64_RTOL * np.abs(expect)
             ratio = np.where(both, err / limit, 0.0)
         over = np.flatnonzero(ratio > 1.0)
         print('{}: {} rows, {} finite in the oracle, {} finiteness mismatches, {} beyond the '
               'bound, worst err/bound {:.3g}, float64 repeats {}'.format(
                   tag, count, int(fin_e.sum()), len(bad_fin), len(over), ratio.max(), rescued))
+        with np.errstate(all='ignore'):
+            rel = np.where(both, err / np.abs(expect), 0.0)
+        line = '   relative error |dlnL| / |lnL|: median {:.2g}, 99 % {:.2g}, max {:.2g}'.format(
+            np.median(rel[both]), np.percentile(rel[both], 99), rel.max())
         if precision == 'fp32':
-            with np.errstate(all='ignore'):
-                rel = np.where(both, err / np.abs(expect), 0.0)
-            print('   relative error |dlnL| / |lnL|: median {:.2g}, 99 % {:.2g}, max {:.2g}; beyond '
-                  'the extended bound (variance-channel term added): {}'.format(
-                      np.median(rel), np.percentile(rel, 99), rel.max(),
-                      int(np.sum(both & (err > extended)))))
+            line += '; beyond the extended bound (variance-channel term added): {}'.format(
+                int(np.sum(both & (err > extended))))
+        print(line)
         for row in list(bad_fin[:5]) + list(over[np.argsort(-ratio[over])][:5]):
             print('   row {}: got {!r} expect {!r} bound {:.3g}'.format(
                 row, got[row], expect[row], limit[row]))
             print('      theta', np.array2string(thetas[row], precision=5, max_line_width=200))
         worst[tag] = float(ratio.max())
+        model.engine.close()
     return worst
 
 
