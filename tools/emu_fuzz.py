@@ -152,15 +152,22 @@ def main():
                           model.param_names, model.param_lens, tuple(model.engine.shape),
                           n_psf)
             oracle = oracle_from_model(model)
-            with np.errstate(all='ignore'):
-                expect = oracle.lnlike_batch(thetas)
             # a PSF index that rounds outside the list: the prior is -inf there, the reference
-            # never reaches the likelihood (psfMC/models.py:209-211); the engine answers -inf
+            # never reaches the likelihood (psfMC/models.py:209-211; its PSF list would
+            # raise IndexError); the engine answers -inf
+            inside = np.ones(count, dtype=bool)
+            usable = thetas
             if model.psf_index_slot[0] == 'theta':
-                sel = np.rint(thetas[:, model.psf_index_slot[1]])
-                expect[(sel < 0) | (sel >= n_psf)] = -np.inf
-            bounds = fp32_bounds(model, thetas, oracle)
-            extended = extended_bounds(model, thetas, oracle)
+                column = model.psf_index_slot[1]
+                sel = np.rint(thetas[:, column])
+                inside = (sel >= 0) & (sel < n_psf)
+                usable = thetas.copy()
+                usable[~inside, column] = 0.0
+            with np.errstate(all='ignore'):
+                expect = oracle.lnlike_batch(usable)
+            expect[~inside] = -np.inf
+            bounds = fp32_bounds(model, usable, oracle)
+            extended = extended_bounds(model, usable, oracle)
         rescued0 = model.engine.info()['rescued_total']
         got = model.log_likelihood_batch(thetas)
         rescued = model.engine.info()['rescued_total'] - rescued0
