@@ -241,3 +241,26 @@ def test_oracle_tiny_sersic_index_vectors(mode):
     with np.errstate(all='ignore'):
         got = oracle.lnlike_batch(thetas)
     assert np.array_equal(got, want)
+
+
+def test_oracle_equals_reference_bitwise_outside_the_priors():
+    """tools/ref_fuzz.py: the oracle against the unmodified reference's own raw_model /
+    convolved_model / residual / composite_ivm on parameter vectors far outside the priors
+    (centres off the frame, reff 0.05 ... 300 px, index 0.05 ... 12, 60 000 ADU components,
+    both PSFs) -- images and lnL bit for bit in the three precision modes. The golden
+    vectors pin prior draws and named edge cases; profiles/r2e_ref_fuzz.txt holds the
+    4096-vector run of this check."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if not os.path.isdir('/root/reference/psfMC'):
+        pytest.skip('/root/reference not present (GPU box)')
+    for which in ('c1', 'c1_2psf'):
+        proc = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ref_fuzz.py'),
+                               '96', '31', 'wide', which], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, universal_newlines=True, timeout=600)
+        lines = [line for line in proc.stdout.splitlines() if line.startswith(which)]
+        assert proc.returncode == 0 and len(lines) == 3, proc.stdout
+        for line in lines:
+            assert 'lnL differing 0 ' in line, line
+            assert line.count(': 0') == 4, line        # the four images
