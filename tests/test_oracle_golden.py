@@ -263,4 +263,4 @@ def test_oracle_equals_reference_bitwise_outside_the_priors():
         assert proc.returncode == 0 and len(lines) == 3, proc.stdout
         for line in lines:
             assert 'lnL differing 0 ' in line, line
-            assert line.count(': 0') == 4, line        # the four images
+            assert line.count(': 0') == 5, line        # the five images

@@ -5,7 +5,8 @@ needs /root/reference, imported through oracle/refshim.py): the golden vectors p
 on prior draws and named edge cases; this drives both with parameter vectors from the wide
 box of tools/emu_fuzz.py (centres outside the frame, reff 0.05 ... 300 px, index 0.05 ... 12,
 any angle, 60 000 ADU components) through the reference's own raw_model / convolved_model /
-residual / composite_ivm (psfMC/models.py:245-294) and compares images and lnL BITWISE in the
+residual / composite_ivm / point_source_subtracted (psfMC/models.py:245-306) and compares
+the five images and lnL BITWISE in the
 three precision modes of SURVEY.md 8c.
 
     python tools/ref_fuzz.py [n_thetas] [seed] [wide|typical] [c1|c1_2psf]
@@ -54,12 +55,14 @@ def main():
         model = refshim.build_reference_model(model_file, mode)
         oracle = mg.oracle_for(model, mode, raw_inputs)
         bad_img = {key: 0 for key in ('raw_model', 'convolved_model', 'residual',
-                                      'composite_ivm')}
+                                      'composite_ivm', 'point_source_subtracted')}
         bad_lnl = finite = 0
         worst = 0.0
         for theta in thetas:
             lnl, _, imgs = mg.ref_images_and_lnl(model, theta)
-            o_imgs = oracle.images(theta, with_point_source_subtracted=False)
+            with np.errstate(all='ignore'):      # (param_values are set: models.py:296-306)
+                imgs['point_source_subtracted'] = model.point_source_subtracted()
+                o_imgs = oracle.images(theta)
             for key in bad_img:
                 if not np.array_equal(imgs[key], o_imgs[key], equal_nan=True):
                     bad_img[key] += 1
