@@ -351,3 +351,76 @@ def test_device_loop_is_not_chosen_for_a_model_float32_cannot_hold(emu_library, 
     fresh = BatchPool(bright)
     assert not fresh.native_sampler(start[:100])[1].get('device_loop')
     assert fresh._fp32_enough is None
+
+
+def _random_model(rng, library):
+    """A random small model: constants and priors mixed at random over every parameter,
+    Uniform / Normal columns (library), Gamma / WeibullMinimum ones (callback into scipy
+    under PSFMC_PRIORS_STRICT), bilinear and Lanczos point sources, angles in degrees and
+    radians -- everything the prior plan and the propose / accept kernels branch on."""
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.components import Configuration, PointSource, Sersic, Sky
+    from psfmc_b200.distributions import Gamma, Normal, Uniform, WeibullMinimum
+    from psfmc_b200.synthetic import synthetic_psf
+    size = 16
+    obs = 0.02 * rng.standard_normal((size, size))
+    ivm = np.full((size, size), 2500.0)
+    psf, psf_ivm = synthetic_psf(8)
+    comps = [Configuration(obs_file=obs, obsivm_file=ivm, psf_files=psf, psfivm_files=psf_ivm,
+                           mag_zeropoint=25.0)]
+
+    def maybe(prior, constant):
+        return prior if rng.rand() < 0.7 else constant
+
+    def position():
+        lo = rng.uniform(3.0, 9.0, 2)
+        return maybe(Uniform(loc=lo, scale=rng.uniform(2.0, 4.0, 2)), tuple(lo + 1.3))
+
+    def magnitude():
+        kind = rng.randint(3)
+        if kind == 0:
+            return Uniform(loc=rng.uniform(20, 22), scale=rng.uniform(1, 3))
+        if kind == 1:
+            return Normal(loc=rng.uniform(21, 23), scale=rng.uniform(0.2, 1.0))
+        return float(rng.uniform(21, 23))
+    comps.append(Sky(adu=maybe(Normal(loc=0, scale=0.01), 0.002)))
+    for _ in range(rng.randint(0, 3)):
+        comps.append(PointSource(xy=position(), mag=magnitude(),
+                                 shift_method=('bilinear', 'lanczos3')[rng.randint(2)]))
+    for _ in range(rng.randint(1, 3)):
+        degrees = bool(rng.randint(2))
+        span = 180.0 if degrees else np.pi
+        index = (Uniform(loc=0.5, scale=5.0), WeibullMinimum(c=1.5, scale=4),
+                 Gamma(a=2.0, scale=1.2), 1.7)[rng.randint(4)]
+        comps.append(Sersic(xy=position(), mag=magnitude(),
+                            reff=maybe(Uniform(loc=2.0, scale=rng.uniform(2, 5)), 3.9),
+                            reff_b=maybe(Uniform(loc=1.0, scale=rng.uniform(1.5, 4)), 1.9),
+                            index=index,
+                            angle=maybe(Uniform(loc=0, scale=span), 0.3 * span),
+                            angle_degrees=degrees))
+    return MultiComponentModel(comps, precision='fp64', library=library)
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_library_loops_on_random_models(emu_library, monkeypatch, seed):
+    """Randomised models (see _random_model): the host loop and the device loop of
+    psfmc_ensemble_run continue the numpy loop's chain bit for bit -- positions,
+    lnprobability, acceptance counts, the random stream afterwards. (Strict priors: a
+    Weibull / Gamma column goes through scipy, and a plan with such a column keeps the loop
+    on the host.)"""
+    from psfmc_b200.synthetic import draw_walkers_fast
+    monkeypatch.setenv('PSFMC_PRIORS_STRICT', '1')
+    model = _random_model(np.random.RandomState(100 + seed), emu_library)
+    if model.num_params == 0:
+        pytest.skip('every parameter came out constant')
+    nwalk = 2 * model.num_params + 2
+    start = draw_walkers_fast(model, nwalk, seed=seed)
+    start = start[0] + 0.05 * (start - start[0])
+    assert np.any(np.isfinite(model.log_posterior_batch(start)))
+    ref = _run(model, start, False, monkeypatch, iterations=6)
+    for device in (False, True):
+        got = _run(model, start, True, monkeypatch, iterations=6, device=device)
+        assert model._sampler_plan, 'the library loop was not used'
+        for key in ('chain', 'lnprobability', 'naccepted', 'next', 'pos', 'lnprob'):
+            assert np.array_equal(got[key], ref[key]), (key, device)
+    assert 0 < ref['naccepted'].sum()
