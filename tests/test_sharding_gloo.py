@@ -49,13 +49,19 @@ def _worker(rank, world, port, emu_lib, outdir):
         return model.log_likelihood_batch(rows)
     gathered = sharded_lnlike(evaluate, thetas)
     one_row = sharded_lnlike(evaluate, thetas[:1])        # rank 1 gets no rows
+    # emcee's list protocol (row views in, (lnpost, blob) tuples out) and the array one
+    pool = ShardedPool(model)
+    listed = np.array([r[0] for r in pool.map(None, [thetas[i] for i in range(len(thetas))])])
+    batched = pool.map_batch(None, thetas)[0]
+    assert pool.map(None, []) == []
     nwalk = 2 * model.num_params + 2
     sampler = EnsembleSampler(nwalk, model.num_params, model.log_posterior,
                               kwargs={'model': model}, pool=ShardedPool(model))
     sampler._random.seed(3)
     pos, lnp = sampler.run_mcmc(draw_walkers_fast(model, nwalk, seed=2), 2)[:2]
     np.savez(os.path.join(outdir, 'rank{}.npz'.format(rank)), gathered=gathered,
-             one_row=one_row, calls=np.array(calls), pos=pos, lnp=lnp)
+             one_row=one_row, calls=np.array(calls), pos=pos, lnp=lnp, listed=listed,
+             batched=batched)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -77,6 +83,10 @@ def test_world_size_two_gloo(emu_library, tmp_path):
                                 precision='fp32', library=emu_library)
     thetas = draw_walkers_fast(model, 7, seed=1)
     assert np.array_equal(model.log_likelihood_batch(thetas), r0['gathered'])
+    want = model.log_posterior_batch(thetas)
+    for data in (r0, r1):
+        assert np.array_equal(data['listed'], want)
+        assert np.array_equal(data['batched'], want)
     nwalk = 2 * model.num_params + 2
     sampler = EnsembleSampler(nwalk, model.num_params, model.log_posterior,
                               kwargs={'model': model}, pool=BatchPool(model))
