@@ -73,6 +73,57 @@ class MultiComponentModel(object):
         self.posterior_images = {}
         self.accumulated_samples = 0
         self.reset_images()
+        if precision == 'fp32':
+            self._warn_if_float32_is_short()
+
+    def float32_dynamic_range(self):
+        """Brightest model pixel the priors allow (the 0.1 % quantile of every magnitude /
+        radius prior, or the constant) over the median noise of an unmasked pixel. The
+        float32 transform carries errors relative to the LARGEST values on the frame
+        ('outside the priors'): up to ~1e5 they stay below the stated
+        tolerance, beyond it ``precision='fp64'`` is the mode to use."""
+        good = ~np.asarray(self.config.bad_px, dtype=bool)
+        if not good.any():
+            return 0.0
+        sigma = float(np.sqrt(np.median(np.asarray(self.config.obs_var,
+                                                   dtype=np.float64)[good])))
+        def low_end(comp, attr):
+            prior = getattr(comp, '_priors', {}).get(attr)
+            if prior is not None:
+                frozen = getattr(prior, 'rv_frozen', None)
+                return float(np.min(frozen.ppf(1e-3) if frozen is not None
+                                    else prior.median()))
+            if attr in getattr(comp, '_constants', {}):
+                return float(np.min(comp._constants[attr]))
+            return None
+        peak = 0.0
+        for comp in self.components:
+            mag = low_end(comp, 'mag')
+            if mag is None:
+                continue
+            flux = 10.0 ** (0.4 * (float(self.config.mag_zeropoint) - mag))
+            # a point source puts its flux into a pixel or two; a Sersic profile about
+            # 1 / (reff reff_b) of it into its brightest pixel
+            reff, reff_b = low_end(comp, 'reff'), low_end(comp, 'reff_b')
+            if reff is not None and reff_b is not None and reff * reff_b > 1.0:
+                flux /= reff * reff_b
+            peak = max(peak, flux)
+        if not np.isfinite(peak) or not sigma > 0:
+            return 0.0
+        return peak / sigma
+
+    def _warn_if_float32_is_short(self):
+        try:
+            ratio = self.float32_dynamic_range()
+        except Exception:                 # a prior without a quantile function: no advice
+            return
+        if ratio > 1.0e5:
+            import warnings
+            warnings.warn(
+                'psfmc_b200: the priors allow a component {:.1e} times brighter than the '
+                'median pixel noise; the float32 likelihood is stated for up to ~1e5 (host '
+                'calls repeat what comes out non-finite in float64, device loops do not). '
+                'Consider precision=\'fp64\'.'.format(ratio))
 
     # -- parameter bookkeeping -------------------------------------------------
     @property

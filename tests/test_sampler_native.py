@@ -332,7 +332,10 @@ def test_device_loop_is_not_chosen_for_a_model_float32_cannot_hold(emu_library, 
         assert pool.native_sampler(start)[1].get('device_loop') is True     # cached
     assert ordinary.engine.info()['rescued_total'] == 0
 
-    bright = model_with(8.0)            # 10^(0.4 * 17.9) = 1.4e7 ADU on 0.02 ADU of noise
+    assert 1e3 < ordinary.float32_dynamic_range() < 1e5
+    with pytest.warns(UserWarning, match='fp64'):      # the advice at construction
+        bright = model_with(8.0)        # 10^(0.4 * 17.9) = 1.4e7 ADU on 0.02 ADU of noise
+    assert bright.float32_dynamic_range() > 1e8
     start = bright.init_params_from_priors(520)
     oracle = oracle_from_model(bright)
     assert np.all(np.isfinite(oracle.lnlike_batch(start[:8])))
