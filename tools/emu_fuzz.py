@@ -5,7 +5,7 @@ frames with parameter vectors drawn from a box far WIDER than the model's priors
 outside the frame, reff 0.05 ... 300 px, axis ratios down to 0.005, indices 0.05 ... 12,
 magnitudes 14 ... 32): what a user's model with other priors could hand the engine.
 
-    python tools/emu_fuzz.py [n_walkers] [seed] [wide|typical] [c1|mixed128|mixed256|frame75x100]
+    python tools/emu_fuzz.py [n_walkers] [seed] [wide|typical] [c1|mixed128|mixed256|mixed512|frame75x100]
                               [brightest_mag]
 
 Prints, per precision mode, the rows whose result disagrees with the oracle: finiteness,
@@ -87,7 +87,8 @@ def draw(rng, count, box='wide', bright=None, names=None, lens=None, shape=(128,
 
 def build_model(which, precision, env=()):
     """The fuzzed models: c1 (fused 128^2 / staged), mixed128 (bilinear and clipped point
-    sources, fixed parameters, radians), mixed256 (two PSFs, the four-CTA cluster kernel),
+    sources, fixed parameters, radians), mixed256 (two PSFs, the four-CTA cluster kernel), mixed512 (the same scene on the tiled
+    512 x 512 path),
     frame75x100 (75 x 100 frame, 31 x 17 PSF: zero-padded transform frame + fold)."""
     import conftest
     for key, val in env:
@@ -100,6 +101,8 @@ def build_model(which, precision, env=()):
             return conftest.mixed_model_128(precision, library=conftest.EMU_LIB)
         if which == 'mixed256':
             return conftest.mixed_model_256(precision, library=conftest.EMU_LIB)
+        if which == 'mixed512':
+            return conftest.mixed_model_256(precision, library=conftest.EMU_LIB, n=512)
         if which == 'frame75x100':
             return conftest.arbitrary_frame_model(75, 100, 31, 17, precision=precision,
                                                   library=conftest.EMU_LIB, fp64_rescue=True)
