@@ -2684,14 +2684,15 @@ static int run_ensemble_device(psfmc_engine *engine, const psfmc_prior_plan *pl,
       // a slot: zz | (D - 1) log zz | log u | partner (int32, in the fourth quarter)
       double *hz = engine->hl_rng.ptr + (size_t)slot * 4 * half, *hlzz = hz + half, *hlu = hlzz + half;
       int *hp = reinterpret_cast<int *>(hlu + half);
+      mt.fill_double(hz, ns);
       for (long long i = 0; i < ns; ++i) {
-        volatile double t = (a - 1.0) * mt.next_double();
+        volatile double t = (a - 1.0) * hz[i];
         const double t1 = t + 1.0;
         volatile double sq = t1 * t1;
         hz[i] = sq / a;
       }
-      for (long long i = 0; i < ns; ++i) hp[i] = (int)mt.next_bounded((uint32_t)nc);
-      for (long long i = 0; i < ns; ++i) hlu[i] = mt.next_double();
+      mt.fill_bounded(hp, ns, (uint32_t)nc);
+      mt.fill_double(hlu, ns);
       pool.parallel_rows(ns, 512, [&](long long lo, long long hi) {
         for (long long i = lo; i < hi; ++i) {
           hlzz[i] = dm1 * log(hz[i]);
@@ -2918,10 +2919,10 @@ int psfmc_rng_fill(uint32_t *mt_key, int32_t *mt_pos, int32_t kind, int64_t n, i
   if (n < 0) return fail(PSFMC_ERR_INVALID_ARG, "negative count");
   NumpyMT19937 mt{mt_key, mt_pos};
   if (kind == 0) {
-    for (int64_t i = 0; i < n; ++i) out[i] = mt.next_double();
+    mt.fill_double(out, n);
   } else if (kind == 1) {
     if (bound < 1 || bound > 0xffffffffLL) return fail(PSFMC_ERR_INVALID_ARG, "bound out of range");
-    for (int64_t i = 0; i < n; ++i) out[i] = (double)mt.next_bounded((uint32_t)bound);
+    mt.fill_bounded(out, n, (uint32_t)bound);
   } else {
     return fail(PSFMC_ERR_INVALID_ARG, "unknown kind");
   }

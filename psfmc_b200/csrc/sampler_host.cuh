@@ -74,6 +74,69 @@ struct NumpyMT19937 {
     const int32_t a = (int32_t)(next32() >> 5), b = (int32_t)(next32() >> 6);
     return (a * 67108864.0 + b) / 9007199254740992.0;
   }
+  static inline uint32_t temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
+  // The next n words of the stream at once (the same words n calls of next32 return): the
+  // state array is tempered in runs, position and bounds in registers -- the per-word form
+  // reloads *pos through the pointer for every word and does not vectorise.
+  void fill32(uint32_t *out, long long n) {
+    while (n > 0) {
+      if (*pos >= 624 || *pos < 0) reload();
+      const int p = *pos;
+      const long long m = n < (long long)(624 - p) ? n : (long long)(624 - p);
+      const uint32_t *src = key + p;
+      for (long long i = 0; i < m; ++i) out[i] = temper(src[i]);
+      *pos = p + (int)m;
+      out += m;
+      n -= m;
+    }
+  }
+  // n times random_sample (two words each)
+  void fill_double(double *out, long long n) {
+    uint32_t words[512];
+    while (n > 0) {
+      const long long m = n < 256 ? n : 256;
+      fill32(words, 2 * m);
+      for (long long i = 0; i < m; ++i) {
+        const int32_t a = (int32_t)(words[2 * i] >> 5), b = (int32_t)(words[2 * i + 1] >> 6);
+        out[i] = (a * 67108864.0 + b) / 9007199254740992.0;
+      }
+      out += m;
+      n -= m;
+    }
+  }
+  // n times randint(bound): masked rejection consumes a data-dependent number of words, so
+  // the run over the state array stops at the word that completes the request
+  template <typename T>
+  void fill_bounded(T *out, long long n, uint32_t bound) {
+    const uint32_t rng = bound - 1u;
+    if (rng == 0u) {
+      for (long long i = 0; i < n; ++i) out[i] = (T)0;
+      return;
+    }
+    uint32_t mask = rng;
+    mask |= mask >> 1;
+    mask |= mask >> 2;
+    mask |= mask >> 4;
+    mask |= mask >> 8;
+    mask |= mask >> 16;
+    long long done = 0;
+    while (done < n) {
+      if (*pos >= 624 || *pos < 0) reload();
+      int p = *pos;
+      while (p < 624 && done < n) {      // (branch-free: a rejected value is overwritten)
+        const uint32_t val = temper(key[p++]) & mask;
+        out[done] = (T)val;
+        done += (long long)(val <= rng);
+      }
+      *pos = p;
+    }
+  }
   // RandomState.randint(bound), 0 < bound <= 2^32 - 1
   uint32_t next_bounded(uint32_t bound) {
     const uint32_t rng = bound - 1u;
@@ -478,14 +541,15 @@ inline int run_ensemble(const LnlikeCalls &eng, const psfmc_prior_plan *pl, psfm
   // a Python loop would hold.
   auto draw = [&](std::vector<double> &z, std::vector<long long> &p, std::vector<double> &u,
                   long long ns, long long nc) {
+    mt.fill_double(z.data(), ns);
     for (long long i = 0; i < ns; ++i) {
-      volatile double t = (a - 1.0) * mt.next_double();   // (no contraction into an FMA)
+      volatile double t = (a - 1.0) * z[i];               // (no contraction into an FMA)
       const double t1 = t + 1.0;
       volatile double sq = t1 * t1;
       z[i] = sq / a;
     }
-    for (long long i = 0; i < ns; ++i) p[i] = (long long)mt.next_bounded((uint32_t)nc);
-    for (long long i = 0; i < ns; ++i) u[i] = mt.next_double();
+    mt.fill_bounded(p.data(), ns, (uint32_t)nc);
+    mt.fill_double(u.data(), ns);
   };
   // Chain storage. emcee's layout is (walker, iteration, D): one iteration scatters k short
   // rows over the whole array (141 us per 2048 walkers, measured: every row a cache miss).
