@@ -169,6 +169,7 @@ class ShardedPool(object):
         self.model = model
         self.group = group
         self._evaluator = ShardedEvaluator(model.log_posterior_batch, group)
+        self._fp32_enough = None        # pool.float32_is_enough, probed once
 
     def map(self, func, iterable):
         thetas = iterable if isinstance(iterable, list) else list(iterable)
@@ -201,6 +202,8 @@ class ShardedPool(object):
         holder = self.model.native_sampler_plan(block)
         if holder is None:
             return None
+        if not self._float32_is_enough(block):
+            return None
         peer = getattr(engine, '_peer_exchange', None)
         if peer is None:
             try:
@@ -210,6 +213,16 @@ class ShardedPool(object):
         if len(block) > peer.capacity:
             return None
         return engine.lnpost_sharded(holder['plan'], block)
+
+    def _float32_is_enough(self, rows):
+        """The sharded library calls have no float64 repeat; the torch.distributed path
+        has (every rank's host call). Probed once per pool on the first rows it sees, on
+        every rank for ALL of them -- the same deterministic answer on every rank, no
+        collective -- see :func:`psfmc_b200.pool.float32_is_enough`."""
+        if self._fp32_enough is None:
+            from .pool import float32_is_enough
+            self._fp32_enough = float32_is_enough(self.model, rows)
+        return self._fp32_enough
 
     def map_batch(self, func, block):
         """Array protocol of this package's sampler (cf. BatchPool.map_batch):
@@ -227,7 +240,8 @@ class ShardedPool(object):
         all rows is gathered over peer memory (:class:`PeerExchange`). NCCL groups on
         CUDA devices only; otherwise -- and with ``PSFMC_NATIVE_SAMPLER=0`` -- None: the
         numpy loop with :meth:`map_batch`. Non-finite float32 results are -inf on this
-        path (no float64 repeat)."""
+        path (no float64 repeat): a model whose starting walkers need the repeat stays on
+        the numpy loop and the torch.distributed gather (:meth:`_float32_is_enough`)."""
         import os
         import torch.distributed as dist
         if os.environ.get('PSFMC_NATIVE_SAMPLER', '1') == '0':
@@ -242,6 +256,8 @@ class ShardedPool(object):
         holder = self.model.native_sampler_plan(start_positions)
         # (every rank must take the same branch: the plan is validated on the same rows)
         if holder is None:
+            return None
+        if not self._float32_is_enough(start_positions):
             return None
         need = max(int(len(start_positions)), 2)
         peer = getattr(engine, '_peer_exchange', None)

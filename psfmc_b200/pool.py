@@ -51,6 +51,31 @@ def rows_as_block(rows):
         return np.stack([np.asarray(p, dtype=np.float64) for p in rows])
 
 
+def float32_is_enough(model, start_positions):
+    """The device loop and the sharded calls have no float64 repeat: a walker whose float32
+    transform comes out non-finite counts as -inf there, where the reference -- and the
+    host call, which repeats it in float64 -- has a finite posterior. That is nothing for
+    the odd prior-drawn walker and a stuck chain for a model whose dynamic range float32
+    cannot hold (a component 10^5 times brighter than the pixel noise: DESIGN.md 4.5,
+    'outside the priors'). Probe: the starting ensemble through the host call of THIS
+    process's engine, which repeats and counts; more than 1 % repeated -> False, with a
+    warning. (Deterministic: every rank of a sharded job comes to the same answer.)"""
+    engine = model.engine
+    before = engine.info()['rescued_total']
+    model.log_posterior_batch(np.ascontiguousarray(start_positions, dtype=np.float64))
+    repeated = engine.info()['rescued_total'] - before
+    enough = repeated <= 0.01 * len(start_positions)
+    if not enough:
+        import warnings
+        warnings.warn(
+            'psfmc_b200: {} of the {} starting walkers needed the float64 repeat of the '
+            'float32 likelihood; the sampler stays on the host calls (which repeat them) '
+            'instead of the device loop / the sharded library calls (which would count them '
+            'as -inf). precision=\'fp64\' suits this model better.'.format(
+                repeated, len(start_positions)))
+    return enough
+
+
 class BatchPool(object):
     """
     :param model: :class:`psfmc_b200.models.MultiComponentModel`
@@ -149,28 +174,8 @@ class BatchPool(object):
         return engine, holder
 
     def _float32_is_enough(self, start_positions):
-        """The device loop has no float64 repeat: a walker whose float32 transform comes
-        out non-finite counts as -inf there, where the reference -- and the host loop, which
-        repeats it in float64 -- has a finite posterior. That is nothing for the odd
-        prior-drawn walker and a stuck chain for a model whose dynamic range float32 cannot
-        hold (a component 10^5 times brighter than the pixel noise: DESIGN.md 4.5, 'outside
-        the priors'). Probe once per pool: the starting ensemble through the host call,
-        which repeats and counts; more than 1 % repeated keeps the loop on the host."""
         if self._fp32_enough is None:
-            engine = self.model.engine
-            before = engine.info()['rescued_total']
-            self.model.log_posterior_batch(
-                np.ascontiguousarray(start_positions, dtype=np.float64))
-            repeated = engine.info()['rescued_total'] - before
-            self._fp32_enough = repeated <= 0.01 * len(start_positions)
-            if not self._fp32_enough:
-                import warnings
-                warnings.warn(
-                    'psfmc_b200: {} of the {} starting walkers needed the float64 repeat of '
-                    'the float32 likelihood; the sampler loop stays on the host (which '
-                    'repeats them) instead of the device loop (which would count them as '
-                    '-inf). precision=\'fp64\' suits this model better.'.format(
-                        repeated, len(start_positions)))
+            self._fp32_enough = float32_is_enough(self.model, start_positions)
         return self._fp32_enough
 
     # multiprocessing.Pool look-alikes some callers use

@@ -94,3 +94,68 @@ def test_world_size_two_gloo(emu_library, tmp_path):
     pos, lnp = sampler.run_mcmc(draw_walkers_fast(model, nwalk, seed=2), 2)[:2]
     assert np.array_equal(pos, r0['pos']) and np.array_equal(pos, r1['pos'])
     assert np.array_equal(lnp, r0['lnp'])
+
+
+def _probe_worker(rank, world, port, emu_lib, outdir):
+    """One rank, the backend reported as nccl: walks ShardedPool's library branches up to
+    the peer-memory setup (which needs CUDA IPC and gives up here)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
+                      RANK=str(rank), WORLD_SIZE=str(world), PSFMC_NATIVE_SAMPLER='1')
+    os.environ.pop('PSFMC_DEVICE_LOOP', None)
+    import warnings
+    import torch.distributed as dist
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from psfmc_b200 import MultiComponentModel
+    from psfmc_b200.components import PointSource
+    from psfmc_b200.distributed import ShardedPool
+    from psfmc_b200.distributions import Uniform
+    from psfmc_b200.synthetic import synthetic_components
+    real_backend = dist.get_backend
+    dist.get_backend = lambda group=None: 'nccl'
+    size = 32
+    centre, box = np.array((size / 2.0, size / 2.0)), np.array((3.0, 3.0))
+
+    def model_with(point_mag):
+        comps = synthetic_components(size, 1, dtype=np.float64, psf_size=16)
+        comps = [c for c in comps if not isinstance(c, PointSource)]
+        comps.append(PointSource(xy=Uniform(loc=centre - box, scale=2 * box),
+                                 mag=Uniform(loc=point_mag, scale=0.5)))
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            return MultiComponentModel(comps, precision='fp32', library=emu_lib)
+    out = {}
+    for name, mag in (('ordinary', 21.0), ('bright', 8.0)):
+        model = model_with(mag)
+        start = model.init_params_from_priors(64)
+        pool = ShardedPool(model)
+        with warnings.catch_warnings(record=True) as caught:
+            warnings.simplefilter('always')
+            lnpost, _ = pool.map_batch(None, start)
+            native = pool.native_sampler(start)
+            listed = np.array([r[0] for r in pool.map(None, [row for row in start])])
+        out[name + '_enough'] = pool._fp32_enough
+        out[name + '_warned'] = sum('float64 repeat' in str(w.message) for w in caught)
+        out[name + '_native_none'] = native is None
+        out[name + '_same'] = bool(np.array_equal(lnpost, model.log_posterior_batch(start))
+                                   and np.array_equal(listed, lnpost))
+        out[name + '_rescued'] = model.engine.info()['rescued_total']
+    dist.get_backend = real_backend
+    np.savez(os.path.join(outdir, 'probe.npz'), **out)
+    dist.destroy_process_group()
+
+
+def test_sharded_pool_keeps_the_float64_repeat_when_float32_is_short(emu_library, tmp_path):
+    """ShardedPool's library paths (psfmc_lnpost_batch_sharded, the sharded loops) have no
+    float64 repeat: a model whose walkers need it stays on the torch.distributed gather of
+    host calls, decided once per pool by a probe every rank runs on all rows."""
+    import torch.multiprocessing as mp
+    mp.spawn(_probe_worker, args=(1, _free_port(), emu_library, str(tmp_path)), nprocs=1,
+             join=True)
+    got = np.load(str(tmp_path / 'probe.npz'))
+    assert bool(got['ordinary_enough']) and int(got['ordinary_warned']) == 0
+    assert bool(got['ordinary_same']) and int(got['ordinary_rescued']) == 0
+    assert not bool(got['bright_enough']) and int(got['bright_warned']) == 1
+    assert bool(got['bright_native_none']) and bool(got['bright_same'])
+    assert int(got['bright_rescued']) > 0
