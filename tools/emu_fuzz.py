@@ -5,7 +5,7 @@ frames with parameter vectors drawn from a box far WIDER than the model's priors
 outside the frame, reff 0.05 ... 300 px, axis ratios down to 0.005, indices 0.05 ... 12,
 magnitudes 14 ... 32): what a user's model with other priors could hand the engine.
 
-    python tools/emu_fuzz.py [n_walkers] [seed] [wide|typical] [c1|mixed128|mixed256|mixed512|frame75x100]
+    python tools/emu_fuzz.py [n_walkers] [seed] [wide|typical|hot] [c1|mixed128|mixed256|mixed512|frame75x100]
                               [brightest_mag]
 
 Prints, per precision mode, the rows whose result disagrees with the oracle: finiteness,
@@ -85,6 +85,30 @@ def draw(rng, count, box='wide', bright=None, names=None, lens=None, shape=(128,
     return np.ascontiguousarray(np.stack(cols, axis=1))
 
 
+def hot_centres(rng, model, count):
+    """Prior draws whose Sersic centres are moved to within 0.05 ... 5e-6 px of a pixel
+    centre at indices 1 ... 10: the reference's centroid correction makes ONE pixel outshine
+    the frame by up to 10^13 there (the hot pixels of DESIGN.md 4.5)."""
+    np.random.seed(int(rng.randint(2 ** 31 - 1)))       # (the priors draw from numpy's global state)
+    thetas = model.init_params_from_priors(count)
+    names, column = [], 0
+    for name, length in zip(model.param_names, model.param_lens):
+        names.append((name, column))
+        column += length
+    where = dict(names)
+    for name, column in names:
+        if 'Sersic' in name and name.endswith('_xy'):
+            sel = rng.rand(count) < 0.7
+            for axis in (0, 1):
+                shrink = rng.choice([1.0, 0.1, 0.01, 1e-4], sel.sum())
+                thetas[sel, column + axis] = np.rint(thetas[sel, column + axis]) + \
+                    rng.uniform(-0.05, 0.05, sel.sum()) * shrink
+            index = where.get(name[:-3] + '_index')
+            if index is not None:
+                thetas[sel, index] = rng.uniform(1.0, 10.0, sel.sum())
+    return thetas
+
+
 def build_model(which, precision, env=()):
     """The fuzzed models: c1 (fused 128^2 / staged), mixed128 (bilinear and clipped point
     sources, fixed parameters, radians), mixed256 (two PSFs, the four-CTA cluster kernel), mixed512 (the same scene on the tiled
@@ -151,9 +175,12 @@ def main():
         model = build_model(which, precision, env)
         if thetas is None:
             n_psf = len(model.config.psf_selector.psf_images)
-            thetas = draw(np.random.RandomState(seed), count, box, bright,
-                          model.param_names, model.param_lens, tuple(model.engine.shape),
-                          n_psf)
+            if box == 'hot':
+                thetas = hot_centres(np.random.RandomState(seed), model, count)
+            else:
+                thetas = draw(np.random.RandomState(seed), count, box, bright,
+                              model.param_names, model.param_lens,
+                              tuple(model.engine.shape), n_psf)
             oracle = oracle_from_model(model)
             # a PSF index that rounds outside the list: the prior is -inf there, the reference
             # never reaches the likelihood (psfMC/models.py:209-211; its PSF list would
