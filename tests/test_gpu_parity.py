@@ -790,3 +790,33 @@ def test_gpu_nan_parameters_give_minus_inf(cuda_library, monkeypatch):
 def test_gpu_cropped_frames_match_the_reference(cuda_library, tag):
     from conftest import check_cropped_golden
     check_cropped_golden(cuda_library, tag)
+
+
+@pytest.mark.gpu
+def test_gpu_wide_box_fuzz(cuda_library):
+    """(Last in the file on purpose: added after the round's last GPU session, its gates are
+    what the emulator run of the same vectors needs, times ten.) Parameter vectors far
+    outside the priors -- tools/emu_fuzz.py, DESIGN.md 4.5 'outside the priors': the same
+    walkers are finite in the engine and in the oracle, float64 agrees to the rounding of a
+    float64 transform at that dynamic range, float32 (non-finite results repeated in
+    float64) to 1e-3 of |lnL|; in the 'typical' box float64 holds its 1e-10 gate."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), 'tools'))
+    from emu_fuzz import draw
+    models = {prec: model_from_file('j0005/model_c1.py', prec, library=cuda_library,
+                                    obs_dtype=np.float64) for prec in ('fp64', 'fp32')}
+    oracle = oracle_from_model(models['fp64'])
+    for box, count in (('typical', 96), ('wide', 96)):
+        thetas = draw(np.random.RandomState(17), count, box)
+        with np.errstate(all='ignore'):
+            expect = oracle.lnlike_batch(thetas)
+        finite = np.isfinite(expect)
+        for prec, model in models.items():
+            got = model.log_likelihood_batch(thetas)
+            assert np.array_equal(np.isfinite(got), finite), (box, prec)
+            rel = np.abs(got[finite] - expect[finite]) / np.abs(expect[finite])
+            if prec == 'fp64':
+                assert rel.max() <= (1e-10 if box == 'typical' else 1e-6), (box, rel.max())
+            else:
+                assert rel.max() <= (1e-4 if box == 'typical' else 1e-3), (box, rel.max())
