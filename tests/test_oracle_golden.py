@@ -247,17 +247,19 @@ def test_oracle_equals_reference_bitwise_outside_the_priors():
     """tools/ref_fuzz.py: the oracle against the unmodified reference's own raw_model /
     convolved_model / residual / composite_ivm on parameter vectors far outside the priors
     (centres off the frame, reff 0.05 ... 300 px, index 0.05 ... 12, 60 000 ADU components,
-    both PSFs) -- images and lnL bit for bit in the three precision modes. The golden
-    vectors pin prior draws and named edge cases; profiles/r2e_ref_fuzz.txt holds the
-    4096-vector run of this check."""
+    both PSFs, a cropped frame, a GALFIT fixture, Sersic centres on and next to pixel
+    centres where a third of the walkers is NaN) -- images and lnL bit for bit in the three
+    precision modes. The golden vectors pin prior draws and named edge cases;
+    profiles/r2e_ref_fuzz.txt holds the 7168-vector run of this check."""
     import subprocess
     import sys
     from conftest import ROOT
     if not os.path.isdir('/root/reference/psfMC'):
         pytest.skip('/root/reference not present (GPU box)')
-    for which in ('c1', 'c1_2psf'):
+    for which, box in (('c1', 'wide'), ('c1_2psf', 'wide'), ('crop75x100', 'wide'),
+                       ('c2_n4.0', 'wide'), ('c1', 'hot')):
         proc = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ref_fuzz.py'),
-                               '96', '31', 'wide', which], stdout=subprocess.PIPE,
+                               '64', '31', box, which], stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT, universal_newlines=True, timeout=600)
         lines = [line for line in proc.stdout.splitlines() if line.startswith(which)]
         assert proc.returncode == 0 and len(lines) == 3, proc.stdout
