@@ -115,6 +115,8 @@ def build_model(which, precision, env=()):
     512 x 512 path),
     frame75x100 (75 x 100 frame, 31 x 17 PSF: zero-padded transform frame + fold)."""
     import conftest
+    if os.environ.get('PSFMC_EMU_LIB'):          # an experimental emulator build
+        conftest.EMU_LIB = os.environ['PSFMC_EMU_LIB']
     for key, val in env:
         os.environ[key] = val
     try:
