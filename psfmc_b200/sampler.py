@@ -276,7 +276,10 @@ class EnsembleSampler(object):
             raise ValueError('The initial lnprob was NaN.')
         start = self._stored
         if storechain:
-            start = self._reserve(int(iterations / thin))
+            # one slot per stored iteration (it % thin == 0). emcee 2.x reserves
+            # int(iterations / thin) and fails with an IndexError at the last store when
+            # iterations is not a multiple of thin; here that sample is kept.
+            start = self._reserve(-(-int(iterations) // int(thin)))
         native = self._native(p) if blobs is None else None
         if native is not None:
             single = getattr(self, '_one_call', False)

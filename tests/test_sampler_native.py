@@ -427,3 +427,53 @@ def test_library_loops_on_random_models(emu_library, monkeypatch, seed):
         for key in ('chain', 'lnprobability', 'naccepted', 'next', 'pos', 'lnprob'):
             assert np.array_equal(got[key], ref[key]), (key, device)
     assert 0 < ref['naccepted'].sum()
+
+
+def test_library_loops_follow_any_call_pattern(emu_library, monkeypatch):
+    """Random sequences of run_mcmc / sample calls with random iteration counts (zero
+    included), thin factors (iterations need not be a multiple: the last sample is kept,
+    where emcee 2.x fails with an IndexError) and storechain on / off: the host and the
+    device loop leave the chain, lnprobability, acceptance counts, the iteration counter
+    and the random stream of the numpy loop."""
+    from psfmc_b200 import BatchPool
+    from psfmc_b200.sampler import EnsembleSampler
+    from psfmc_b200.synthetic import draw_walkers_fast
+    model = _small_model(emu_library, False)
+    nwalk = 2 * model.num_params + 2
+    start = draw_walkers_fast(model, nwalk, seed=3)
+    start = start[0] + 0.02 * (start - start[0])
+
+    def run(native, device, calls):
+        monkeypatch.setenv('PSFMC_NATIVE_SAMPLER', '1' if native else '0')
+        monkeypatch.setenv('PSFMC_DEVICE_LOOP', '1' if device else '0')
+        smp = EnsembleSampler(nwalk, model.num_params, model.log_posterior,
+                              kwargs={'model': model}, pool=BatchPool(model))
+        smp._random.seed(9)
+        pos, lnp = start, None
+        for its, thin, store, how in calls:
+            if how == 'run':
+                res = smp.run_mcmc(pos, its, lnprob0=lnp, thin=thin, storechain=store)
+            else:
+                res = None
+                for res in smp.sample(pos, lnprob0=lnp, iterations=its, thin=thin,
+                                      storechain=store):
+                    pass
+            if res is not None:
+                pos, lnp = res[0], res[1]
+        return (smp.chain.copy(), smp.lnprobability.copy(), smp.naccepted.copy(),
+                smp.iterations, smp._random.rand(3))
+
+    rng = np.random.RandomState(0)
+    stored = 0
+    for trial in range(8):
+        calls = [(int(rng.randint(0, 7)), int(rng.randint(1, 4)), bool(rng.rand() < 0.8),
+                  ('run', 'sample')[rng.randint(2)]) for _ in range(rng.randint(1, 4))]
+        ref = run(False, False, calls)
+        assert ref[0].shape[1] == sum(-(-its // thin) for its, thin, store, _ in calls
+                                      if store)
+        stored += ref[0].shape[1]
+        for device in (False, True):
+            got = run(True, device, calls)
+            for mine, want in zip(got, ref):
+                assert np.array_equal(mine, want), (trial, calls, device)
+    assert stored > 10
