@@ -250,7 +250,7 @@ def test_oracle_equals_reference_bitwise_outside_the_priors():
     both PSFs, a cropped frame, a GALFIT fixture, Sersic centres on and next to pixel
     centres where a third of the walkers is NaN) -- images and lnL bit for bit in the three
     precision modes. The golden vectors pin prior draws and named edge cases;
-    profiles/r2e_ref_fuzz.txt holds the 7168-vector run of this check."""
+    profiles/r2e_ref_fuzz.txt holds the 17408-vector run of this check."""
     import subprocess
     import sys
     from conftest import ROOT
